@@ -1,0 +1,8 @@
+"""anqs_quantum_chemistry_b200 — B200-native VMC inner loop of Exferro/anqs_quantum_chemistry.
+
+Host surface mirrors the reference's `nqs` objects on the hot path; compute runs in
+hand-written sm_100a kernels behind the C ABI of libanqs_b200.so (include/anqs_b200.h).
+"""
+from .constants import BASE_INT_TYPE, BASE_REAL_TYPE, BASE_COMPLEX_TYPE  # noqa: F401
+from .hilbert_space import HilbertSpace, SampleTable  # noqa: F401
+from .pauli_observable import PauliObservable, PauliArraysOperator, LocalEnergyMetrics  # noqa: F401

@@ -1,0 +1,94 @@
+"""ctypes binding of libanqs_b200.so (C ABI in include/anqs_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the caller gets a
+RuntimeError.  PyTorch is used only to own device memory and streams; every signature below is plain
+pointers and sizes.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, 'libanqs_b200.so')
+
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_vp = ctypes.c_void_p
+
+_SIGNATURES = {
+    'anqs_abi_version': (_c_int, []),
+    'anqs_last_error': (ctypes.c_char_p, []),
+    'anqs_device_check': (_c_int, [_c_int, _vp, _vp, _vp]),
+    'anqs_popcount_i64': (_c_int, [_vp, _vp, _c_i64, _vp]),
+    'anqs_tables_create': (_c_int, [_vp, _c_int, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp]),
+    'anqs_tables_destroy': (_c_int, [_vp]),
+    'anqs_tables_info': (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    'anqs_k1_filter': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp]),
+    'anqs_scan_workspace': (ctypes.c_size_t, [_c_i64]),
+    'anqs_exclusive_scan_i64': (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
+    'anqs_k1_emit': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),
+    'anqs_matrix_elements': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
+    'anqs_hash_capacity': (_c_i64, [_c_i64]),
+    'anqs_hash_build': (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _vp]),
+    'anqs_hash_probe': (_c_int, [_vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp]),
+    'anqs_local_energy_sample_aware': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _vp]),
+    'anqs_accumulate_rows': (_c_int, [_vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
+}
+
+# entry points added by later kernel families register themselves here (name -> (restype, argtypes))
+OPTIONAL_SIGNATURES = {}
+
+_lib = None
+
+
+def declared_symbols():
+    return sorted(list(_SIGNATURES) + list(OPTIONAL_SIGNATURES))
+
+
+def lib():
+    """Loads libanqs_b200.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} not found: the CUDA library is not built. Run `make -C anqs_quantum_chemistry_b200/csrc` '
+                f'(or __graft_entry__.build()). There is no CPU fallback.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in list(_SIGNATURES.items()) + list(OPTIONAL_SIGNATURES.items()):
+            fn = getattr(handle, name)  # AttributeError here means header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        if handle.anqs_abi_version() != 1:
+            raise RuntimeError('libanqs_b200.so ABI version mismatch')
+        _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(lib().anqs_last_error().decode('utf-8', 'replace'))
+
+
+def stream_ptr(device=None):
+    return _vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+def dptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return _vp(0)
+    if not t.is_cuda:
+        raise RuntimeError('expected a CUDA tensor: the anqs_b200 kernels have no CPU path')
+    if not t.is_contiguous():
+        raise RuntimeError('expected a contiguous tensor')
+    return _vp(t.data_ptr())
+
+
+def require_cuda(device):
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise RuntimeError(f'device {device} is not a CUDA device: the anqs_b200 kernels have no CPU path')
+    if not torch.cuda.is_available():
+        raise RuntimeError('CUDA is not available: the anqs_b200 kernels have no CPU path')
+    return device

@@ -1,0 +1,98 @@
+"""Data-parallel sharding of the local-energy pass over the GPUs of one box.
+
+The reference is single-process / single-GPU (energy_opt_exp.py:350); this layer is new design.  Units
+(destination samples) are independent given the table {configuration -> amplitude}, and the connection
+count per sample is (nearly) constant for a fixed (N_alpha, N_beta), so contiguous equal-row shards balance
+the work.  Per pass there is exactly one exchange step:
+
+  1. all_gather of each rank's shard of (packed index int64, amplitude complex128)  -> every rank holds the
+     whole sampled set and builds the lookup table locally (24 B per unique sample);
+  2. each rank evaluates E_loc for its own rows (fused kernel, no communication);
+  3. one all_reduce of the packed statistics [sum w, sum w E, sum w E^2] (5 doubles), w = |psi|^2, from which
+     the MonteCarloEstimator mean / variance (compute_local_energies.py:48-62) follow.
+
+One process per GPU, torch.distributed (NCCL on GPUs; gloo works for the host-side logic on CPU).
+"""
+from typing import Tuple
+
+import torch as pt
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n rows: the first n % world_size ranks get one extra row."""
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None):
+    """Concatenation over ranks (in rank order) of variable-length shards.
+    Returns (global_idx [N] int64, global_amps [N] complex128, lo, hi) with [lo, hi) this rank's rows."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    local_idx = local_idx.contiguous().view(-1)
+    local_amps = local_amps.contiguous().view(-1)
+    if world == 1:
+        return local_idx, local_amps, 0, local_idx.shape[0]
+    rank = dist.get_rank(group)
+    dev = local_idx.device
+    sizes = pt.zeros(world, dtype=pt.int64, device=dev)
+    sizes[rank] = local_idx.shape[0]
+    dist.all_reduce(sizes, group=group)
+    sizes_h = sizes.cpu().tolist()
+    cap = max(sizes_h)
+    # one packed buffer per rank: [idx as 1 double-width word | re | im] = 3 x 8 bytes per sample
+    packed = pt.zeros((cap, 3), dtype=pt.float64, device=dev)
+    packed[:local_idx.shape[0], 0] = local_idx.view(pt.float64)
+    packed[:local_idx.shape[0], 1:] = pt.view_as_real(local_amps)
+    out = pt.empty((world, cap, 3), dtype=pt.float64, device=dev)
+    dist.all_gather_into_tensor(out.view(-1), packed.view(-1), group=group)
+    parts_idx, parts_amp = [], []
+    for r, sz in enumerate(sizes_h):
+        parts_idx.append(out[r, :sz, 0].contiguous().view(pt.int64))
+        parts_amp.append(pt.view_as_complex(out[r, :sz, 1:].contiguous()))
+    lo = sum(sizes_h[:rank])
+    return pt.cat(parts_idx), pt.cat(parts_amp), lo, lo + sizes_h[rank]
+
+
+def local_energy_stats(eloc: pt.Tensor, amps: pt.Tensor) -> pt.Tensor:
+    """Packed partial sums [sum w, Re sum wE, Im sum wE, Re sum wE^2, Im sum wE^2], w = |psi|^2."""
+    w = (amps.real * amps.real + amps.imag * amps.imag)
+    we = w * eloc
+    wee = we * eloc
+    return pt.stack((w.sum(), we.real.sum(), we.imag.sum(), wee.real.sum(), wee.imag.sum()))
+
+
+def reduce_energy_stats(stats: pt.Tensor, group=None):
+    """all_reduce of the packed sums, then MonteCarloEstimator semantics with theoretical frequencies
+    f = |psi|^2 / sum |psi|^2 (compute_local_energies.py:48-62, 107-113):
+    mean = sum f E,  var = sum f (E - mean)^2 = sum f E^2 - mean^2 (complex square, as in the reference)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, group=group)
+    norm = stats[0]
+    mean = pt.complex(stats[1], stats[2]) / norm
+    var = pt.complex(stats[3], stats[4]) / norm - mean * mean
+    return mean, var, norm
+
+
+class ShardedLocalEnergy:
+    """Sample-aware local energies of a batch that is sharded over the ranks of `group`."""
+
+    def __init__(self, ham, alpha_num: int, beta_num: int, group=None):
+        self.ham = ham
+        self.alpha_num = alpha_num
+        self.beta_num = beta_num
+        self.group = group
+
+    @pt.no_grad()
+    def __call__(self, local_idx: pt.Tensor, local_amps: pt.Tensor):
+        """local_idx [n_r] or [n_r,1] int64, local_amps [n_r] complex128: this rank's shard.
+        Returns (E_loc of the local rows, mean, var) with mean/var over the global batch."""
+        from .hilbert_space import SampleTable
+        g_idx, g_amps, lo, hi = all_gather_shards(local_idx, local_amps, self.group)
+        table = SampleTable(g_idx, g_amps)
+        eloc, _, _ = self.ham.compute_var_local_energy_proxy(
+            unq_batch_as_base_indices=g_idx.view(-1, 1), unq_batch_as_amps=g_amps, coupling_method='ham',
+            alpha_num=self.alpha_num, beta_num=self.beta_num, row_start=lo, row_len=hi - lo, table=table)
+        mean, var, _ = reduce_energy_stats(local_energy_stats(eloc, g_amps[lo:hi]), self.group)
+        return eloc, mean, var

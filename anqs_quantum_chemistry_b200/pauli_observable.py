@@ -1,0 +1,348 @@
+"""PauliObservable drop-in (reference: nqs/nqs/stochastic/observables/pauli_observable.py:89-1105).
+
+Same constructor keywords, attributes, table tensors, `.npy` cache file names and method signatures as the
+reference, so `experiments/calculations/compute_local_energies.py:75-163` can drive it unchanged.  All
+compute goes through the sm_100a kernels of libanqs_b200.so:
+
+  compute_var_local_energy_proxy  -> anqs_local_energy_sample_aware (fused filter+probe+matrix element+sum)
+  find_sampled_and_coupled_via_ham -> anqs_k1_filter / anqs_k1_emit + anqs_hash_probe
+  compute_matrix_elements         -> anqs_matrix_elements
+  compute_local_energies (full)   -> anqs_k1_emit with matrix elements, hash join, wf.amplitude on the
+                                     de-duplicated non-sampled configurations, anqs_accumulate_rows
+
+The three working coupling methods of the reference ('ham', 'all_to_all', 'trie') produce the same numbers
+(SURVEY.md §4); they all map to the fused kernel here.  'hamming_ball' is broken in the reference
+(PO:698) and is rejected.
+"""
+import os
+import time
+from typing import Tuple
+
+import numpy as np
+import torch as pt
+
+from . import _lib
+from .abstract_hilbert_space_object import AbstractHilbertSpaceObject
+from .hilbert_space import SampleTable
+
+
+class LocalEnergyMetrics:
+    """Same field names as the reference's Config subclass (PO:25-86)."""
+    FIELDS = ('candidate_x_primes_num', 'sampled_unq_x_primes_num', 'sampled_x_primes_num', 'sampled_coupled_yz_num',
+              'non_sampled_unq_x_primes_num', 'non_sampled_x_primes_num', 'non_sampled_coupled_yz_num',
+              'candidates_time', 'filter_candidates_time', 'find_a_in_b_time', 'find_sampled_and_coupled_time',
+              'sampled_matrix_elements_time', 'sampled_scatter_time', 'non_sampled_matrix_elements_time',
+              'non_sampled_scatter_time', 'eval_non_sampled_amps_time')
+
+    def __init__(self, **kwargs):
+        for f in self.FIELDS:
+            setattr(self, f, kwargs.get(f, np.nan))
+
+    def to_flat_dict(self):
+        return {f: getattr(self, f) for f in self.FIELDS}
+
+    def accumulate(self, other):
+        for f in self.FIELDS:
+            v, o = getattr(self, f), getattr(other, f)
+            setattr(self, f, o if (isinstance(v, float) and np.isnan(v)) else v + o)
+
+
+def parse_of_qubit_operator_arrays(of_qubit_operator, qubit_num: int):
+    """PO:150-183 for single-word indices: (weights c128[T], xy int64[T], yz int64[T]) in dict order.
+    Qubit q -> bit qubit_num-1-q (PO:162); bit 63 is the int64 sign bit (PO:164-167); each Y multiplies
+    the weight by i (PO:176-177)."""
+    arrays = getattr(of_qubit_operator, 'pauli_arrays', None)
+    if arrays is not None:  # (xy, yz, w) already in X^x Z^z form: skips the python loop for 1e5+ terms
+        xy, yz, w = arrays
+        return (np.ascontiguousarray(w, dtype=np.complex128), np.ascontiguousarray(xy).view(np.int64).copy(),
+                np.ascontiguousarray(yz).view(np.int64).copy())
+    terms = of_qubit_operator.terms
+    T = len(terms)
+    w = np.zeros(T, np.complex128)
+    xy = np.zeros(T, np.uint64)
+    yz = np.zeros(T, np.uint64)
+    i_pow = (1.0 + 0j, 1j, -1.0 + 0j, -1j)
+    for t, (qubit_ops, weight) in enumerate(terms.items()):
+        x = z = ny = 0
+        for q, p in qubit_ops:
+            bit = 1 << (qubit_num - 1 - q)
+            if p == 'X' or p == 'Y':
+                x |= bit
+            if p == 'Y' or p == 'Z':
+                z |= bit
+            if p == 'Y':
+                ny += 1
+        xy[t], yz[t] = x, z
+        w[t] = (weight + 0j) * i_pow[ny & 3]
+    return w, xy.view(np.int64), yz.view(np.int64)
+
+
+def count_qubits(of_qubit_operator) -> int:
+    n = getattr(of_qubit_operator, 'qubit_num', None)
+    if n is not None:
+        return int(n)
+    return 1 + max((q for t in of_qubit_operator.terms for q, _ in t), default=-1)
+
+
+class PauliArraysOperator:
+    """Minimal QubitOperator-like carrier for operators that already exist as (xy, yz, weight) arrays
+    (what `synthetic.synthetic_hamiltonian` returns); `.terms` is built lazily for code that wants the dict."""
+
+    def __init__(self, xy, yz, w, qubit_num):
+        self.pauli_arrays = (np.asarray(xy), np.asarray(yz), np.asarray(w))
+        self.qubit_num = qubit_num
+        self._terms = None
+
+    @property
+    def terms(self):
+        if self._terms is None:
+            from .synthetic import pauli_arrays_to_terms
+            xy, yz, w = self.pauli_arrays
+            self._terms = pauli_arrays_to_terms(xy.view(np.uint64), yz.view(np.uint64), w, self.qubit_num)
+        return self._terms
+
+    def __len__(self):
+        return int(self.pauli_arrays[0].shape[0])
+
+
+class PauliObservable(AbstractHilbertSpaceObject):
+    ALLOWED_COUPLING_METHODS = ('ham', 'all_to_all', 'hamming_ball', 'trie')
+    MEMORY_MAGIC_CONSTANT = 25
+
+    def __init__(self, *args, of_qubit_operator=None, **kwargs):
+        super().__init__(*args, **kwargs)
+        assert self.qubit_num == count_qubits(of_qubit_operator)
+        self.of_qubit_operator = of_qubit_operator
+        self.term_num = len(of_qubit_operator) if isinstance(of_qubit_operator, PauliArraysOperator) else len(of_qubit_operator.terms)
+
+        self.local_energy_structure_tensor_names = ('unq_xy_masks', 'unq_xy_masks_inv', 'unq_xy_to_yz_num',
+                                                    'unq_xy_to_yz_start', 'rearranged_yz', 'rearranged_weights')
+        self.tensor_name2tensor_path = {name: os.path.join(self.hilbert_space.parent_dir, f'{name}.npy')
+                                        for name in self.local_energy_structure_tensor_names}
+        if all(os.path.exists(p) for p in self.tensor_name2tensor_path.values()):  # PO:119-129
+            host = {name: np.load(path) for name, path in self.tensor_name2tensor_path.items()}
+        else:
+            weights, xy_masks, yz_masks = parse_of_qubit_operator_arrays(of_qubit_operator, self.qubit_num)
+            host = self.compute_local_energy_structures_host(xy_masks, yz_masks, weights)
+            os.makedirs(self.hilbert_space.parent_dir, exist_ok=True)
+            for name, path in self.tensor_name2tensor_path.items():
+                np.save(path, host[name])
+        self._host_tables = host
+        for name in self.local_energy_structure_tensor_names:
+            setattr(self, name, pt.from_numpy(host[name]).to(self.device))
+        self.unq_xy_masks_num = self.unq_xy_masks.shape[0]
+        self._tables = None
+
+    @staticmethod
+    def compute_local_energy_structures_host(xy_masks, yz_masks, weights):
+        """PO:131-142 + PO:185-211 without the python loops: unique XY masks in signed ascending order
+        (torch.unique semantics), CSR (num, exclusive-cumsum start), YZ masks and weights regrouped with the
+        original term order preserved inside each group."""
+        unq, inv = np.unique(xy_masks, return_inverse=True)
+        inv = inv.reshape(-1).astype(np.int64)
+        num = np.bincount(inv, minlength=unq.shape[0]).astype(np.int64)
+        start = np.cumsum(num) - num
+        order = np.argsort(inv, kind='stable')
+        return dict(unq_xy_masks=unq.reshape(-1, 1).astype(np.int64), unq_xy_masks_inv=inv,
+                    unq_xy_to_yz_num=num, unq_xy_to_yz_start=start.astype(np.int64),
+                    rearranged_yz=yz_masks[order].reshape(-1, 1).astype(np.int64),
+                    rearranged_weights=np.ascontiguousarray(weights[order], dtype=np.complex128))
+
+    # ---- device handle ----------------------------------------------------------------------------------
+    @property
+    def tables(self):
+        if self._tables is None:
+            _lib.require_cuda(self.device)
+            h = self._host_tables
+            handle = _lib._vp()
+            arrs = [np.ascontiguousarray(h['unq_xy_masks'].reshape(-1)), np.ascontiguousarray(h['unq_xy_to_yz_num']),
+                    np.ascontiguousarray(h['unq_xy_to_yz_start']), np.ascontiguousarray(h['rearranged_yz'].reshape(-1)),
+                    np.ascontiguousarray(h['rearranged_weights']).view(np.float64)]
+            with pt.cuda.device(self.device):
+                _lib.check(_lib.lib().anqs_tables_create(_lib.ctypes.byref(handle), self.qubit_num, arrs[0].shape[0],
+                                                         arrs[3].shape[0], *[a.ctypes.data for a in arrs]))
+                info = [_lib.ctypes.c_int(), _lib.ctypes.c_int64(), _lib.ctypes.c_int64(), _lib.ctypes.c_int(), _lib.ctypes.c_int64()]
+                _lib.check(_lib.lib().anqs_tables_info(handle, *[_lib.ctypes.byref(i) for i in info]))
+            self._tables = handle
+            self.weights_real = bool(info[3].value)
+            self.bitmap_row_words = int(info[4].value)
+        return self._tables
+
+    def __del__(self):
+        try:
+            if getattr(self, '_tables', None) is not None:
+                _lib.lib().anqs_tables_destroy(self._tables)
+                self._tables = None
+        except Exception:
+            pass
+
+    # ---- kernel 1: connected configurations -------------------------------------------------------------
+    def connected_configurations(self, samples: pt.Tensor, alpha_num: int, beta_num: int, with_dest: bool = True,
+                                 with_xy_ptr: bool = True, matrix_elements: str = None):
+        """Connected list of a batch of packed samples [n] int64, lexicographic in (dest, xy_ptr) like
+        PO:527-567.  matrix_elements in (None, 'real', 'complex').  Returns a dict with offsets [n+1] int64,
+        dest int32 [M], xprime int64 [M], xy_ptr int32 [M], H."""
+        tables = self.tables
+        dev = self.device
+        samples = samples.contiguous().view(-1)
+        n = samples.shape[0]
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        counts = pt.empty(n, dtype=pt.int64, device=dev)
+        bitmap = pt.empty(n * self.bitmap_row_words, dtype=pt.int32, device=dev)
+        _lib.check(lib.anqs_k1_filter(tables, _lib.dptr(samples), n, alpha_num, beta_num, _lib.dptr(counts), _lib.dptr(bitmap), sp))
+        offsets = pt.empty(n + 1, dtype=pt.int64, device=dev)
+        work = pt.empty(max(1, int(lib.anqs_scan_workspace(n)) // 8), dtype=pt.int64, device=dev)
+        _lib.check(lib.anqs_exclusive_scan_i64(_lib.dptr(counts), _lib.dptr(offsets), n, _lib.dptr(work), sp))
+        m = int(offsets[-1].item())  # the list is materialised, so its length has to come back to the host
+        out = dict(offsets=offsets, counts=counts,
+                   dest=pt.empty(m, dtype=pt.int32, device=dev) if with_dest else None,
+                   xprime=pt.empty(m, dtype=pt.int64, device=dev),
+                   xy_ptr=pt.empty(m, dtype=pt.int32, device=dev) if with_xy_ptr else None, H=None)
+        hc = 0
+        if matrix_elements == 'real':
+            assert self.weights_real, 'Hamiltonian weights are complex'
+            out['H'], hc = pt.empty(m, dtype=pt.float64, device=dev), 1
+        elif matrix_elements == 'complex':
+            out['H'], hc = pt.empty(m, dtype=pt.complex128, device=dev), 2
+        h_ptr = _lib.dptr(pt.view_as_real(out['H'])) if hc == 2 else _lib.dptr(out['H'])
+        if m == 0:
+            return out
+        _lib.check(lib.anqs_k1_emit(tables, _lib.dptr(samples), n, _lib.dptr(bitmap), _lib.dptr(offsets), _lib.dptr(out['dest']),
+                                    _lib.dptr(out['xprime']), _lib.dptr(out['xy_ptr']), h_ptr, hc, sp))
+        return out
+
+    # ---- reference method surface -----------------------------------------------------------------------
+    def compute_matrix_elements(self, x_primes: pt.Tensor = None, ham_xy_pointers: pt.Tensor = None,
+                                chunk_size: int = np.inf):
+        """PO:255-324 (including the @timed tuple extension): (H [M] c128, yz_count, seconds)."""
+        start = time.time()
+        assert len(x_primes.shape) == 2
+        assert len(ham_xy_pointers.shape) == 1
+        assert x_primes.shape[0] == ham_xy_pointers.shape[0]
+        m = x_primes.shape[0]
+        H = pt.empty(m, dtype=pt.complex128, device=self.device)
+        xp = x_primes.contiguous().view(-1)
+        ptrs = ham_xy_pointers.to(pt.int64).contiguous()
+        _lib.check(_lib.lib().anqs_matrix_elements(self.tables, _lib.dptr(xp), _lib.dptr(ptrs), m,
+                                                   _lib.dptr(pt.view_as_real(H)), _lib.stream_ptr(self.device)))
+        yz_num = int(self.unq_xy_to_yz_num[ptrs].sum().item()) if m > 0 else 0
+        return H, yz_num, time.time() - start
+
+    def find_sampled_and_coupled_via_ham(self, chunk_as_unq_batch_ptrs: pt.Tensor = None,
+                                         unq_batch_as_base_indices: pt.Tensor = None, alpha_num: int = None,
+                                         beta_num: int = None, metrics: LocalEnergyMetrics = None):
+        """PO:569-600: (dest_as_chunk_ptrs, src_as_unq_batch_ptrs, src_as_base_indices [M,1],
+        coupling_xy_as_unq_ham_xy_ptrs, metrics, seconds)."""
+        start = time.time()
+        metrics = metrics if metrics is not None else LocalEnergyMetrics()
+        batch = unq_batch_as_base_indices.contiguous().view(-1)
+        chunk = batch[chunk_as_unq_batch_ptrs]
+        conn = self.connected_configurations(chunk, alpha_num, beta_num)
+        metrics.candidate_x_primes_num = conn['xprime'].shape[0]
+        mask, ptr = self.find_a_in_b(a=conn['xprime'].view(-1, 1), b=batch.view(-1, 1))
+        metrics.candidates_time = metrics.filter_candidates_time = metrics.find_a_in_b_time = 0.0
+        return (conn['dest'][mask].to(pt.int64), ptr[mask], conn['xprime'][mask].view(-1, 1),
+                conn['xy_ptr'][mask].to(pt.int64), metrics, time.time() - start)
+
+    def find_sampled_and_coupled(self, chunk_as_unq_batch_ptrs=None, unq_batch_as_base_indices=None,
+                                 coupling_method: str = None, symmetric: bool = None, alpha_num: int = None,
+                                 beta_num: int = None, metrics: LocalEnergyMetrics = None):
+        assert coupling_method in self.ALLOWED_COUPLING_METHODS
+        if coupling_method == 'hamming_ball':
+            raise NotImplementedError("coupling_method='hamming_ball' is broken in the reference (pauli_observable.py:698)")
+        return self.find_sampled_and_coupled_via_ham(chunk_as_unq_batch_ptrs=chunk_as_unq_batch_ptrs,
+                                                     unq_batch_as_base_indices=unq_batch_as_base_indices,
+                                                     alpha_num=alpha_num, beta_num=beta_num, metrics=metrics)
+
+    @pt.no_grad()
+    def compute_var_local_energy_proxy(self, unq_batch_as_base_indices: pt.Tensor = None,
+                                       unq_batch_as_amps: pt.Tensor = None, coupling_method: str = None,
+                                       chunk_size: int = 20000, alpha_num: int = None, beta_num: int = None,
+                                       matrix_element_chunk_size: int = np.inf,
+                                       row_start: int = 0, row_len: int = None,
+                                       table: SampleTable = None) -> Tuple[pt.Tensor, pt.Tensor, LocalEnergyMetrics]:
+        """PO:396-487.  Sample-aware local energies of the whole batch in one fused launch; `chunk_size` and
+        `matrix_element_chunk_size` are accepted for signature compatibility (nothing is materialised, so
+        there is nothing to chunk).  row_start/row_len/table are extensions used by the multi-GPU shard path."""
+        assert coupling_method in self.ALLOWED_COUPLING_METHODS
+        if coupling_method == 'hamming_ball':
+            raise NotImplementedError("coupling_method='hamming_ball' is broken in the reference (pauli_observable.py:698)")
+        dev = _lib.require_cuda(self.device)
+        samples = unq_batch_as_base_indices.contiguous().view(-1)
+        amps = unq_batch_as_amps.to(pt.complex128).contiguous()
+        n = samples.shape[0]
+        assert amps.shape[0] == n
+        row_len = n - row_start if row_len is None else row_len
+        if table is None:
+            table = SampleTable(samples, amps)
+        eloc = pt.empty(row_len, dtype=pt.complex128, device=dev)
+        _lib.check(_lib.lib().anqs_local_energy_sample_aware(
+            self.tables, _lib.dptr(samples), _lib.dptr(pt.view_as_real(amps)), n, row_start, row_len,
+            _lib.dptr(table.slots), table.capacity, alpha_num, beta_num, _lib.dptr(pt.view_as_real(eloc)), _lib.stream_ptr(dev)))
+        return eloc, eloc, LocalEnergyMetrics()
+
+    @pt.no_grad()
+    def compute_local_energies(self, wf=None, sampled_indices: pt.Tensor = None, sampled_amps: pt.Tensor = None,
+                               verbose: bool = False, use_tree_for_candidates: bool = False, chunk_size: int = 20000,
+                               sample_aware: bool = False, compute_via_ham_xy_coupling: bool = True,
+                               amps_chunk_size: int = 100000) -> Tuple[pt.Tensor, pt.Tensor, LocalEnergyMetrics]:
+        """PO:326-393 -> PO:992-1105.  Returns (full E_loc, sample-aware E_loc, metrics).  With
+        sample_aware=True both are the sample-aware value (as in the reference); otherwise connected
+        configurations outside the sampled set are de-duplicated, evaluated with wf.amplitude and added."""
+        alpha_num = beta_num = wf.masker.symmetries[0].particle_num // 2  # PO:979,985 (closed shell)
+        samples = sampled_indices.contiguous().view(-1)
+        amps = sampled_amps.to(pt.complex128).contiguous()
+        n = samples.shape[0]
+        table = SampleTable(samples, amps)
+        if sample_aware:
+            return self.compute_var_local_energy_proxy(unq_batch_as_base_indices=sampled_indices, unq_batch_as_amps=amps,
+                                                       coupling_method='ham', alpha_num=alpha_num, beta_num=beta_num, table=table)
+        dev = self.device
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        metrics = LocalEnergyMetrics()
+        full = pt.empty(n, dtype=pt.complex128, device=dev)
+        aware = pt.empty(n, dtype=pt.complex128, device=dev)
+        amps_r = pt.view_as_real(amps)
+        for lo in range(0, n, chunk_size):
+            hi = min(n, lo + chunk_size)
+            cur = LocalEnergyMetrics()
+            conn = self.connected_configurations(samples[lo:hi], alpha_num, beta_num, with_dest=False, with_xy_ptr=False,
+                                                 matrix_elements='real' if self.weights_real else 'complex')
+            xp, H, offsets = conn['xprime'], conn['H'], conn['offsets']
+            hc = 1 if self.weights_real else 2
+            h_ptr = _lib.dptr(H) if hc == 1 else _lib.dptr(pt.view_as_real(H))
+            m = xp.shape[0]
+            cur.candidate_x_primes_num = m
+            ptr = pt.empty(m, dtype=pt.int64, device=dev)
+            _lib.check(lib.anqs_hash_probe(_lib.dptr(table.slots), table.capacity, _lib.dptr(xp), m, _lib.dptr(ptr), _lib.dptr(None), sp))
+            # sampled part: E_s[i] = sum H psi(x') / psi(x_i)   (PO:1048-1057)
+            aware_chunk = pt.empty(hi - lo, dtype=pt.complex128, device=dev)
+            dest_amps = amps_r[lo:hi].contiguous()
+            _lib.check(lib.anqs_accumulate_rows(_lib.dptr(offsets), hi - lo, _lib.dptr(ptr), h_ptr, hc, _lib.dptr(amps_r),
+                                                _lib.dptr(dest_amps), _lib.dptr(pt.view_as_real(aware_chunk)), 0, sp))
+            aware[lo:hi] = aware_chunk
+            # non-sampled part (PO:1062-1103): unique -> amplitudes -> gather back through the inverse map
+            missing = ptr < 0
+            cur.sampled_x_primes_num = int((~missing).sum().item())
+            cur.non_sampled_x_primes_num = m - cur.sampled_x_primes_num
+            if cur.non_sampled_x_primes_num > 0:
+                unq, inv = pt.unique(xp[missing], return_inverse=True)
+                cur.non_sampled_unq_x_primes_num = unq.shape[0]
+                t0 = time.time()
+                unq_amps = pt.cat([wf.amplitude(unq[a:a + amps_chunk_size].view(-1, 1)).detach()
+                                   for a in range(0, unq.shape[0], amps_chunk_size)]).to(pt.complex128).contiguous()
+                cur.eval_non_sampled_amps_time = time.time() - t0
+                inv_full = pt.full((m,), -1, dtype=pt.int64, device=dev)
+                inv_full[missing] = inv
+                rest = pt.empty(hi - lo, dtype=pt.complex128, device=dev)
+                _lib.check(lib.anqs_accumulate_rows(_lib.dptr(offsets), hi - lo, _lib.dptr(inv_full), h_ptr, hc,
+                                                    _lib.dptr(pt.view_as_real(unq_amps)), _lib.dptr(dest_amps),
+                                                    _lib.dptr(pt.view_as_real(rest)), 0, sp))
+                full[lo:hi] = aware_chunk + rest
+            else:
+                # the reference raises IndexError here (expand_pointers on an empty list);
+                # the mathematically correct answer is "nothing to add"
+                cur.non_sampled_unq_x_primes_num = 0
+                full[lo:hi] = aware_chunk
+            metrics.accumulate(cur)
+        return full, aware, metrics

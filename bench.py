@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — local energies/s of the VMC inner loop (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n-unq M]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload: N2 cc-pVDZ shape — 56 qubits, 14 electrons, synthetic-integral
+Jordan-Wigner Hamiltonian with 8 irreps (T = 114 305 Pauli terms, U = 23 157 unique XY masks); synthetic
+unique physical samples (seed 1) with random complex amplitudes (seed 2).  A "step" is one sample-aware
+local-energy pass over the batch: [N>1: all_gather of the (index, amplitude) shards] -> lookup-table build ->
+fused filter + probe + matrix-element + accumulate kernel on this rank's rows -> Monte-Carlo statistics
+[N>1: one all_reduce].  Weak scaling: every rank owns --n-unq rows; the sampled set is the union.
+
+One JSON line on stdout (rank 0).  `value` = rows of all ranks / max-over-ranks device time with inputs resident
+in HBM; `e2e` = the same pass through PauliObservable.compute_var_local_energy_proxy with HOST (pinned)
+inputs and the E_loc vector read back, copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+QUBITS, ELECTRONS, IRREPS, HAM_SEED = 56, 14, 8, 0
+WORKLOAD = 'N2 cc-pVDZ shape (C5): 56 qubits, 14 e-, synthetic integrals with 8 irreps, seed 0'
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(names, r[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return None
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_workload(n_rows_total):
+    from anqs_quantum_chemistry_b200 import synthetic
+    xy, yz, w = synthetic.synthetic_hamiltonian(QUBITS, n_irreps=IRREPS, seed=HAM_SEED)
+    samples = synthetic.random_physical_samples(QUBITS, ELECTRONS // 2, ELECTRONS // 2, n_rows_total, seed=1)
+    amps = synthetic.random_amplitudes(samples.shape[0], seed=2)
+    return xy, yz, w, samples, amps
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference is Python/PyTorch-CPU and cannot travel to the GPU box, so this times the
+    oracle port of its 'ham' local-energy path (oracle/anqs_oracle.c, all host threads) on a bounded sample."""
+    if rank != 0:
+        return
+    from oracle import hamiltonian_oracle as orc
+    n_set = args.n_unq * args.gpus
+    xy, yz, w, samples, amps = make_workload(n_set)
+    tab = orc.Tables(xy, yz, w)
+    rows = args.cpu_rows
+    na = nb = ELECTRONS // 2
+    times = []
+    for it in range(args.warmup + args.steps):
+        lo = (it * rows) % max(1, n_set - rows)
+        t0 = time.perf_counter()
+        orc.local_energy_sample_aware(samples, amps, tab, na, nb, row_start=lo, row_len=rows)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = rows * len(times) / total
+    cores = orc.num_threads()
+    line = {
+        'impl': 'reference', 'metric': 'local_energies_per_sec', 'value': value, 'unit': 'E_loc/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'n_unq_per_gpu': args.n_unq, 'sampled_set': n_set, 'terms': int(tab.term_num),
+                   'unique_xy_masks': int(tab.unq_xy_masks_num)},
+        'cpu_baseline': {'value': value, 'unit': 'E_loc/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{rows} destination rows per step against the full {n_set}-sample table, coupling "ham"'},
+        'e2e': {'value': value, 'unit': 'E_loc/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n-unq', type=int, default=1 << 20, help='unique samples (rows) per GPU')
+    ap.add_argument('--cpu-rows', type=int, default=4096, help='rows per CPU-baseline step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == 'reference' or os.environ.get('ANQS_BENCH_ALLOW_SHORT'), 'need >= 3 warm-up steps'
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from anqs_quantum_chemistry_b200 import HilbertSpace, PauliObservable, PauliArraysOperator, SampleTable, _lib
+    from anqs_quantum_chemistry_b200 import dist as adist
+
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run'
+
+    na = nb = ELECTRONS // 2
+    n_set = args.n_unq * world
+    xy, yz, w, samples, amps = make_workload(n_set)
+    tmp = tempfile.mkdtemp(prefix=f'anqs_bench_r{rank}_')
+    hs = HilbertSpace(qubit_num=QUBITS, device=dev, parent_dir=tmp, rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, QUBITS))
+    lib = _lib.lib()
+    tables = ham.tables
+    lo, hi = adist.shard_bounds(n_set, world, rank)
+    rows = hi - lo
+
+    h_idx = torch.from_numpy(samples.view(np.int64)[lo:hi].copy()).pin_memory()
+    h_amps = torch.from_numpy(amps[lo:hi].copy()).pin_memory()
+    d_idx = h_idx.to(dev)
+    d_amps = h_amps.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    kern_ms = []
+
+    def step(time_kernel=False):
+        g_idx, g_amps, glo, ghi = adist.all_gather_shards(d_idx, d_amps)
+        table = SampleTable(g_idx, g_amps)
+        eloc = torch.empty(ghi - glo, dtype=torch.complex128, device=dev)
+        sp = _lib.stream_ptr(dev)
+        if time_kernel:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(lib.anqs_local_energy_sample_aware(tables, _lib.dptr(g_idx), _lib.dptr(torch.view_as_real(g_amps)), g_idx.shape[0],
+                                                      glo, ghi - glo, _lib.dptr(table.slots), table.capacity, na, nb,
+                                                      _lib.dptr(torch.view_as_real(eloc)), sp))
+        if time_kernel:
+            e1.record()
+            kern_ms.append((e0, e1))
+        mean, var, _ = adist.reduce_energy_stats(adist.local_energy_stats(eloc, g_amps[glo:ghi]))
+        return eloc, mean
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    step_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)  # evict L2 between timed iterations
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eloc, mean = step(time_kernel=True)
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
+
+    # end to end through the public API with host buffers (N=1 semantics per rank; shards gathered on device)
+    e2e_ms = []
+    h_out = torch.empty(rows, dtype=torch.complex128).pin_memory()
+    for it in range(args.warmup + args.steps):
+        flush.fill_(1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        idx_d = h_idx.to(dev, non_blocking=True)
+        amps_d = h_amps.to(dev, non_blocking=True)
+        if world > 1:
+            sle = adist.ShardedLocalEnergy(ham, na, nb)
+            e, m, v = sle(idx_d, amps_d)
+        else:
+            e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=idx_d.view(-1, 1), unq_batch_as_amps=amps_d,
+                                                         coupling_method='ham', alpha_num=na, beta_num=nb)
+        h_out.copy_(e, non_blocking=True)
+        e1.record()
+        barrier()
+        if it >= args.warmup:
+            e2e_ms.append(e0.elapsed_time(e1))
+    e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_total = float(e2e_total.item())
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # algorithmic traffic of the dominant (fused) kernel: one 32-byte slot per probed candidate
+    counts = torch.empty(min(rows, 1 << 16), dtype=torch.int64, device=dev)
+    _lib.check(lib.anqs_k1_filter(tables, _lib.dptr(d_idx), counts.shape[0], na, nb, _lib.dptr(counts), _lib.dptr(None), _lib.stream_ptr(dev)))
+    conn_per_row = float(counts.double().mean().item())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        U, T = ham.unq_xy_masks_num, ham.term_num
+        m_probe = conn_per_row * rows
+        algo_bytes = 32.0 * m_probe + 24.0 * n_set + 16.0 * rows + 8.0 * U + 16.0 * T
+        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {
+            'metric': 'local_energies_per_sec', 'value': n_set * args.steps / (total_ms * 1e-3), 'unit': 'E_loc/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'n_unq_per_gpu': args.n_unq, 'sampled_set': n_set, 'terms': int(T), 'unique_xy_masks': int(U),
+                       'connections_per_sample': conn_per_row, 'mode': 'sample-aware (coupling "ham")',
+                       'l2': 'flushed between timed iterations (256 MiB write)', 'parallelism': f'dp{world} (rows sharded, table replicated)'},
+            'e2e': {'value': n_set * len(e2e_ms) / (e2e_total * 1e-3), 'unit': 'E_loc/s', 'h2d_bytes_per_step': int(24 * rows),
+                    'd2h_bytes_per_step': int(16 * rows)},
+            'gpu_launches': 2 * args.steps,
+            'kernel': {'name': 'fused_eloc_kernel', 'ms': kernel_ms, 'share_of_step': kernel_ms / (total_ms / args.steps),
+                       'filter_tests_per_s': rows * U / (kernel_ms * 1e-3), 'probes_per_s': m_probe / (kernel_ms * 1e-3)},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'peak_source': peak_src,
+                         'algorithmic_bytes': '32 B per probed candidate + 24 B per table sample + 16 B per row + 8U + 16T'},
+            'clocks': clock_info,
+        }
+        if not args.no_cpu_baseline:
+            from oracle import hamiltonian_oracle as orc
+            tab = orc.Tables(xy, yz, w)
+            t0 = time.perf_counter()
+            done = 0
+            while time.perf_counter() - t0 < 10.0:
+                orc.local_energy_sample_aware(samples, amps, tab, na, nb, row_start=done % max(1, n_set - args.cpu_rows), row_len=args.cpu_rows)
+                done += args.cpu_rows
+            dt = time.perf_counter() - t0
+            line['cpu_baseline'] = {'value': done / dt, 'unit': 'E_loc/s', 'cores': orc.num_threads(), 'kind': 'port',
+                                    'sample': f'{done} destination rows ({dt:.1f} s) against the same {n_set}-sample table and Hamiltonian'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

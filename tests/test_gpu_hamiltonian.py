@@ -1,0 +1,200 @@
+"""GPU parity: the CUDA local-energy path (through the C ABI) against the reference's golden outputs and,
+on larger seeded inputs, against the CPU oracle.  Bit-exact for connected configurations, pointers and
+counts; 1e-10 for matrix elements and local energies (fp64)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, HAM_CASES, HAM_CASES_WITH_LISTS
+from anqs_quantum_chemistry_b200 import HilbertSpace, PauliObservable, PauliArraysOperator, synthetic
+from oracle import hamiltonian_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+def _ham(g, tmp_path):
+    n = int(g['qubit_num'])
+    hs = HilbertSpace(qubit_num=n, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    return hs, PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(g['in_xy'], g['in_yz'], g['in_w'], n))
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize('case', HAM_CASES)
+def test_connected_list_matches_reference(case, tmp_path):
+    g = load_golden(case)
+    hs, ham = _ham(g, tmp_path)
+    na = nb = int(g['particle_num']) // 2
+    conn = ham.connected_configurations(_dev(g['samples']), na, nb, matrix_elements='complex')
+    np.testing.assert_array_equal(conn['counts'].cpu().numpy(), g['conn_count_per_sample'])
+    off = conn['offsets'].cpu().numpy()
+    np.testing.assert_array_equal(off, np.concatenate(([0], np.cumsum(g['conn_count_per_sample']))))
+    xp = conn['xprime'].cpu().numpy()
+    H = conn['H'].cpu().numpy()
+    mask, ptr = hs.find_a_in_b(a=conn['xprime'].view(-1, 1), b=_dev(g['samples']).view(-1, 1))
+    if case in HAM_CASES_WITH_LISTS:
+        np.testing.assert_array_equal(conn['dest'].cpu().numpy(), g['conn_dest'])
+        np.testing.assert_array_equal(xp, g['conn_xprime'])
+        np.testing.assert_array_equal(conn['xy_ptr'].cpu().numpy(), g['conn_xy_ptr'])
+        assert np.abs(H - g['conn_H']).max() < 1e-10
+        np.testing.assert_array_equal(mask.cpu().numpy(), g['conn_in_mask'])
+        np.testing.assert_array_equal(ptr.cpu().numpy(), g['conn_in_ptr'])
+    else:
+        assert np.bitwise_xor.reduce(xp) == g['conn_xprime_xor']
+        assert abs(H.sum() - g['conn_H_sum']) < 1e-9
+        assert int(mask.sum().item()) == int(g['conn_in_count'])
+    # real-valued matrix elements (20-byte rows) agree with the complex ones
+    if ham.weights_real:
+        conn_r = ham.connected_configurations(_dev(g['samples']), na, nb, with_dest=False, with_xy_ptr=False, matrix_elements='real')
+        np.testing.assert_array_equal(conn_r['H'].cpu().numpy(), H.real)
+        np.testing.assert_array_equal(conn_r['xprime'].cpu().numpy(), xp)
+
+
+@pytest.mark.parametrize('case', HAM_CASES)
+def test_local_energy_matches_reference(case, tmp_path):
+    g = load_golden(case)
+    hs, ham = _ham(g, tmp_path)
+    na = nb = int(g['particle_num']) // 2
+    s, a = _dev(g['samples']).view(-1, 1), _dev(g['amps'])
+    scale = max(1.0, np.abs(g['eloc_ham']).max())
+    for method in ('ham', 'trie', 'all_to_all'):
+        e, e2, metrics = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a,
+                                                            coupling_method=method, chunk_size=20000, alpha_num=na, beta_num=nb)
+        assert e.dtype == torch.complex128 and tuple(e.shape) == (s.shape[0],)
+        assert np.abs(e.cpu().numpy() - g[f'eloc_{method}']).max() < 1e-10 * scale
+    with pytest.raises(NotImplementedError):
+        ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='hamming_ball',
+                                           alpha_num=na, beta_num=nb)
+    # a window of rows (the multi-GPU shard path) equals the same rows of the full evaluation
+    n = s.shape[0]
+    lo, ln = n // 3, n // 2
+    w, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
+                                                 alpha_num=na, beta_num=nb, row_start=lo, row_len=ln)
+    assert torch.equal(w, e[lo:lo + ln])
+
+
+@pytest.mark.parametrize('case', HAM_CASES_WITH_LISTS)
+def test_reference_method_surface(case, tmp_path):
+    """find_sampled_and_coupled_via_ham (PO:569-600) and compute_matrix_elements (PO:255-324)."""
+    g = load_golden(case)
+    hs, ham = _ham(g, tmp_path)
+    na = nb = int(g['particle_num']) // 2
+    s = _dev(g['samples']).view(-1, 1)
+    n = s.shape[0]
+    dest, src_ptr, src_idx, xy_ptr, metrics, seconds = ham.find_sampled_and_coupled(
+        chunk_as_unq_batch_ptrs=torch.arange(n, device=DEV), unq_batch_as_base_indices=s, coupling_method='ham',
+        symmetric=False, alpha_num=na, beta_num=nb, metrics=None)
+    m = g['conn_in_mask']
+    np.testing.assert_array_equal(dest.cpu().numpy(), g['conn_dest'][m])
+    np.testing.assert_array_equal(src_ptr.cpu().numpy(), g['conn_in_ptr'][m])
+    np.testing.assert_array_equal(src_idx.cpu().numpy().reshape(-1), g['conn_xprime'][m])
+    np.testing.assert_array_equal(xy_ptr.cpu().numpy(), g['conn_xy_ptr'][m])
+    assert dest.dtype == torch.int64 and tuple(src_idx.shape) == (int(m.sum()), 1)
+    assert metrics.candidate_x_primes_num == g['conn_xprime'].shape[0]
+    H, yz_num, secs = ham.compute_matrix_elements(x_primes=_dev(g['conn_xprime']).view(-1, 1), ham_xy_pointers=_dev(g['conn_xy_ptr']))
+    assert np.abs(H.cpu().numpy() - g['conn_H']).max() < 1e-10
+    assert yz_num == int(g['unq_xy_to_yz_num'][g['conn_xy_ptr']].sum())
+
+
+def test_hilbert_helpers_match_reference(tmp_path):
+    g = load_golden('hilbert')
+    hs = HilbertSpace(qubit_num=64, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    a = _dev(g['a']).view(-1, 1)
+    np.testing.assert_array_equal(hs.popcount(a).cpu().numpy(), g['popcount'])
+    odd = _dev(np.concatenate((g['a'], g['a'][:1])))[1:]  # unaligned start, odd length
+    np.testing.assert_array_equal(hs.popcount(odd.view(-1, 1)).cpu().numpy(), g['popcount'][1:].tolist() + [g['popcount'][0]])
+    inplace = a.clone()
+    out = hs.popcount_(inplace)
+    np.testing.assert_array_equal(out.cpu().numpy().reshape(-1), g['popcount'])
+    s, p = hs.sort_base_idx(_dev(g['dup']).view(-1, 1))
+    np.testing.assert_array_equal(s.cpu().numpy().reshape(-1), g['sorted'])
+    np.testing.assert_array_equal(p.cpu().numpy(), g['sort_perm'])
+    u, inv = hs.compute_unique_indices(_dev(g['dup']).view(-1, 1))
+    np.testing.assert_array_equal(u.cpu().numpy().reshape(-1), g['unq'])
+    np.testing.assert_array_equal(inv.cpu().numpy(), g['unq_inv'])
+    m, ptr = hs.find_a_in_b(a=a, b=_dev(g['b']).view(-1, 1))
+    np.testing.assert_array_equal(m.cpu().numpy(), g['a_in_b_mask'])
+    np.testing.assert_array_equal(ptr.cpu().numpy(), g['a_in_b_ptr'])
+    assert hs.popcount(torch.empty((0, 1), dtype=torch.int64, device=DEV)).numel() == 0
+
+
+@pytest.mark.parametrize('qubits,electrons,irreps,n_samples', [(24, 10, 2, 3000), (56, 14, 8, 1500)])
+def test_against_oracle_on_seeded_inputs(qubits, electrons, irreps, n_samples, tmp_path):
+    """Sizes the CPU oracle finishes in seconds, including the headline 56-qubit shape (U ~ 2.3e4, streamed
+    when the table does not fit in shared memory is covered by test_streamed_table)."""
+    xy, yz, w = synthetic.synthetic_hamiltonian(qubits, n_irreps=irreps, seed=4)
+    na = nb = electrons // 2
+    samples = synthetic.random_physical_samples(qubits, na, nb, n_samples, seed=5)
+    # make the sampled set connected: add single and double excitations of the first samples
+    tab = orc.Tables(xy, yz, w)
+    _, xp, _ = orc.candidates_ham(samples, 0, 4, tab, na, nb)
+    samples = np.unique(np.concatenate((samples, xp.view(np.uint64)[:: max(1, xp.shape[0] // n_samples)])))
+    amps = synthetic.random_amplitudes(samples.shape[0], seed=6)
+    hs = HilbertSpace(qubit_num=qubits, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, qubits))
+    s, a = _dev(samples.view(np.int64)), _dev(amps)
+    e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s.view(-1, 1), unq_batch_as_amps=a, coupling_method='ham',
+                                                 alpha_num=na, beta_num=nb)
+    e_ref = orc.local_energy_sample_aware(samples, amps, tab, na, nb)
+    scale = max(1.0, np.abs(e_ref).max())
+    assert np.abs(e.cpu().numpy() - e_ref).max() < 1e-10 * scale
+    sub = 256
+    conn = ham.connected_configurations(s[:sub], na, nb, matrix_elements='real')
+    dest, xp, ptr = orc.candidates_ham(samples, 0, sub, tab, na, nb)
+    np.testing.assert_array_equal(conn['dest'].cpu().numpy(), dest)
+    np.testing.assert_array_equal(conn['xprime'].cpu().numpy(), xp)
+    np.testing.assert_array_equal(conn['xy_ptr'].cpu().numpy(), ptr)
+    H = orc.matrix_elements(xp, ptr, tab)
+    assert np.abs(conn['H'].cpu().numpy() - H.real).max() < 1e-10 * max(1.0, np.abs(H).max())
+    # hermiticity of the restricted Hamiltonian: sum_i conj(psi_i) (H psi)_i is real
+    a_np = amps
+    assert abs((np.conj(a_np) * (e.cpu().numpy() * a_np)).sum().imag) < 1e-9
+
+
+def test_streamed_table(tmp_path):
+    """U > 25600 forces the double-buffered TMA tile path (dense 36-qubit shape: U = 29 836)."""
+    xy, yz, w = synthetic.synthetic_hamiltonian(36, n_irreps=1, seed=2)
+    na = nb = 6
+    samples = synthetic.random_physical_samples(36, na, nb, 300, seed=3)
+    tab = orc.Tables(xy, yz, w)
+    assert tab.unq_xy_masks_num > 25600
+    _, xp, _ = orc.candidates_ham(samples, 0, 2, tab, na, nb)
+    samples = np.unique(np.concatenate((samples, xp.view(np.uint64)[::7])))
+    amps = synthetic.random_amplitudes(samples.shape[0], seed=6)
+    hs = HilbertSpace(qubit_num=36, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, 36))
+    s, a = _dev(samples.view(np.int64)), _dev(amps)
+    e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s.view(-1, 1), unq_batch_as_amps=a, coupling_method='ham',
+                                                 alpha_num=na, beta_num=nb)
+    e_ref = orc.local_energy_sample_aware(samples, amps, tab, na, nb)
+    assert np.abs(e.cpu().numpy() - e_ref).max() < 1e-10 * max(1.0, np.abs(e_ref).max())
+    conn = ham.connected_configurations(s[:64], na, nb, matrix_elements='real')
+    dest, xp, ptr = orc.candidates_ham(samples, 0, 64, tab, na, nb)
+    np.testing.assert_array_equal(conn['xprime'].cpu().numpy(), xp)
+    np.testing.assert_array_equal(conn['xy_ptr'].cpu().numpy(), ptr)
+    np.testing.assert_array_equal(conn['dest'].cpu().numpy(), dest)
+
+
+def test_edge_cases(tmp_path):
+    g = load_golden('ham_n8_dense')
+    hs, ham = _ham(g, tmp_path)
+    empty = torch.empty(0, dtype=torch.int64, device=DEV)
+    conn = ham.connected_configurations(empty, 2, 2, matrix_elements='complex')
+    assert conn['xprime'].numel() == 0 and conn['offsets'].cpu().tolist() == [0]
+    e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=empty.view(-1, 1),
+                                                 unq_batch_as_amps=torch.empty(0, dtype=torch.complex128, device=DEV),
+                                                 coupling_method='ham', alpha_num=2, beta_num=2)
+    assert e.numel() == 0
+    # a single sample: only the diagonal couples
+    s = _dev(g['samples'][:1]).view(-1, 1)
+    a = _dev(g['amps'][:1])
+    e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham', alpha_num=2, beta_num=2)
+    H = orc.dense_matrix_from_arrays(g['in_xy'], g['in_yz'], g['in_w'], 8)
+    x = int(g['samples'][0])
+    assert abs(e.cpu().numpy()[0] - H[x, x]) < 1e-12
+    # an electron count nobody satisfies: no connections at all
+    conn = ham.connected_configurations(_dev(g['samples']), 3, 1)
+    assert conn['xprime'].numel() == 0 and int(conn['counts'].sum().item()) == 0
