@@ -225,13 +225,15 @@ int anqs_tables_create(anqs_tables_t **out, int qubit_num, int64_t U, int64_t T,
     bool real = true;
     std::vector<double> wre(T), wim(T);
     std::vector<ulonglong2> rec(T);
+    std::vector<uint64_t> yzd(T);
     for (int64_t k = 0; k < T; ++k) {
         wre[k] = h_weights[2 * k];
         wim[k] = h_weights[2 * k + 1];
         if (wim[k] != 0.0) real = false;
         unsigned long long bits;
         std::memcpy(&bits, &wre[k], 8);
-        rec[k] = make_ulonglong2((unsigned long long)h_yz[k], bits);
+        yzd[k] = deinterleave((uint64_t)h_yz[k]);
+        rec[k] = make_ulonglong2((unsigned long long)yzd[k], bits);
     }
     t->weights_real = real ? 1 : 0;
 
@@ -244,7 +246,7 @@ int anqs_tables_create(anqs_tables_t **out, int qubit_num, int64_t U, int64_t T,
     if (e == cudaSuccess) e = up((void **)&t->xy, xy.data(), xy.size() * sizeof(uint64_t));
     if (e == cudaSuccess) e = up((void **)&t->mab, mab.data(), mab.size() * sizeof(uint2));
     if (e == cudaSuccess) e = up((void **)&t->grp, grp.data(), grp.size() * sizeof(int2));
-    if (e == cudaSuccess) e = up((void **)&t->yz, h_yz, (size_t)T * sizeof(uint64_t));
+    if (e == cudaSuccess) e = up((void **)&t->yz_d, yzd.data(), (size_t)T * sizeof(uint64_t));
     if (e == cudaSuccess) e = up((void **)&t->w_re, wre.data(), (size_t)T * sizeof(double));
     if (e == cudaSuccess && !real) e = up((void **)&t->w_im, wim.data(), (size_t)T * sizeof(double));
     if (e == cudaSuccess && real) e = up((void **)&t->term_real, rec.data(), (size_t)T * sizeof(ulonglong2));
@@ -263,7 +265,7 @@ int anqs_tables_destroy(anqs_tables_t *h) {
     cudaFree(t->xy);
     cudaFree(t->mab);
     cudaFree(t->grp);
-    cudaFree(t->yz);
+    cudaFree(t->yz_d);
     cudaFree(t->w_re);
     cudaFree(t->w_im);
     cudaFree(t->term_real);

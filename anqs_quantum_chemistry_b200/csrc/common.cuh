@@ -44,11 +44,37 @@ struct Tables {
     uint64_t *xy;            // [U_pad]  unique XY masks, ascending (signed order, as torch.unique gives)
     uint2 *mab;              // [U_pad]  de-interleaved masks: .x = even (alpha) bits, .y = odd (beta) bits
     int2 *grp;               // [U_pad]  (start, num) of the YZ group of each XY mask
-    uint64_t *yz;            // [T]
+    uint64_t *yz_d;          // [T]  YZ masks, de-interleaved: low word = even (alpha) bits, high word = odd bits
     double *w_re;            // [T]
     double *w_im;            // [T] (NULL when weights_real)
-    ulonglong2 *term_real;   // [T] packed {yz, bits(w_re)} records for one 16-byte load (weights_real only)
+    ulonglong2 *term_real;   // [T] packed {yz_d, bits(w_re)} records for one 16-byte load (weights_real only)
 };
+
+// ---- sampled-set lookup table (kernel family 2) ------------------------------------------------------
+// Memory layout of the caller-allocated buffer: (capacity + 1) slots of 32 bytes, then capacity bytes of
+// blocked-Bloom presence bits (capacity / 4 words of 32 bits; every key sets 3 bits of ONE word).  Keys are
+// stored DE-INTERLEAVED so that the fused kernel can form the probe key (xa ^ ma, xb ^ mb) without touching
+// the 64-bit masks.
+constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;  // de-interleaving maps all-ones to all-ones
+struct __align__(32) HashSlot {
+    uint64_t key;    // de-interleaved configuration
+    long long idx;   // position in the key array (-1 = empty)
+    double re, im;   // amplitude psi(key)
+};
+struct HashView {
+    const HashSlot *slots;
+    const uint32_t *bloom;
+    uint32_t capmask;    // capacity - 1
+    uint32_t wordmask;   // number of Bloom words - 1
+};
+inline HashView make_hash_view(const void *d_table, int64_t capacity) {
+    HashView hv;
+    hv.slots = (const HashSlot *)d_table;
+    hv.bloom = (const uint32_t *)(hv.slots + capacity + 1);
+    hv.capmask = (uint32_t)(capacity - 1);
+    hv.wordmask = (uint32_t)(capacity / 4 - 1);
+    return hv;
+}
 
 // Even bits of v gathered into the low 32 bits ("Morton decode").
 __host__ __device__ __forceinline__ uint32_t compress_even_bits(uint64_t v) {
@@ -61,16 +87,67 @@ __host__ __device__ __forceinline__ uint32_t compress_even_bits(uint64_t v) {
     return (uint32_t)v;
 }
 
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
-    return z ^ (z >> 31);
+// (even bits, odd bits) of v as (low word, high word): a bijection on 64-bit values
+__host__ __device__ __forceinline__ uint64_t deinterleave(uint64_t v) {
+    return (uint64_t)compress_even_bits(v) | ((uint64_t)compress_even_bits(v >> 1) << 32);
+}
+
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t v, int r) { return (v << r) | (v >> (32 - r)); }
+
+// 32-bit hash of a de-interleaved key (murmur3-style mixing of the two halves)
+__host__ __device__ __forceinline__ uint32_t hash_key(uint32_t a, uint32_t b) {
+    uint32_t h = a * 0xcc9e2d51u;
+    h = rotl32(h, 15) * 0x1b873593u;
+    uint32_t g = b * 0x85ebca6bu;
+    g = rotl32(g, 13) * 0xc2b2ae35u;
+    h ^= g;
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+// blocked Bloom filter: word index and 3-bit pattern, both decorrelated from the slot index (= low hash bits)
+__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t h) {
+    h ^= h >> 15;
+    h *= 0x2c1b3c6du;
+    h ^= h >> 12;
+    h *= 0x297a2d39u;
+    h ^= h >> 15;
+    return h;
+}
+__host__ __device__ __forceinline__ uint32_t bloom_pattern(uint32_t h) {
+    uint32_t g = h * 0x9E3779B1u;
+    return (1u << (g >> 27)) | (1u << ((g >> 22) & 31u)) | (1u << ((g >> 17) & 31u));
 }
 
 #ifdef __CUDACC__
 // parity of popcount(v) with a single POPC: fold the two halves first
 __device__ __forceinline__ uint32_t parity64(uint64_t v) {
     return __popc((uint32_t)v ^ (uint32_t)(v >> 32)) & 1u;
+}
+
+// Looks a de-interleaved key up.  Returns the position (or -1) and, on a hit, the stored amplitude.
+__device__ __forceinline__ long long hash_lookup(const HashView &hv, uint64_t key, double &re, double &im) {
+    if (key == EMPTY_KEY) {  // dedicated slot after the table proper
+        const HashSlot *sl = hv.slots + (size_t)hv.capmask + 1;
+        re = sl->re;
+        im = sl->im;
+        return sl->idx;
+    }
+    uint32_t h = hash_key((uint32_t)key, (uint32_t)(key >> 32)) & hv.capmask;
+    for (;;) {
+        ulonglong2 kv = __ldg(reinterpret_cast<const ulonglong2 *>(hv.slots + h));
+        if (kv.x == key) {
+            double2 a = __ldg(reinterpret_cast<const double2 *>(hv.slots + h) + 1);
+            re = a.x;
+            im = a.y;
+            return (long long)kv.y;
+        }
+        if (kv.x == EMPTY_KEY) return -1;
+        h = (h + 1) & hv.capmask;
+    }
 }
 
 // w with its sign flipped when par == 1

@@ -150,7 +150,8 @@ class SampleTable:
         n = keys.shape[0]
         self.n = n
         self.capacity = int(_lib.lib().anqs_hash_capacity(n))
-        self.slots = pt.empty(((self.capacity + 1) * 4,), dtype=pt.int64, device=dev)
+        nbytes = int(_lib.lib().anqs_hash_bytes(self.capacity))
+        self.slots = pt.empty(((nbytes + 31) // 32 * 4,), dtype=pt.int64, device=dev)  # slots + Bloom words
         amps_real = None
         if amps is not None:
             assert amps.dtype == pt.complex128 and amps.shape[0] == n

@@ -87,13 +87,17 @@ int anqs_matrix_elements(const anqs_tables_t *t, const int64_t *d_xprime, const 
                          double *d_H /* m complex128 */, void *stream);
 
 /* ---- A5  kernel 2: membership join, HilbertSpace.find_a_in_b (HS:263-284) -----------------------------
- * Open-addressing table of 32-byte slots {key, index, amp.re, amp.im}.  capacity is a power of two
- * >= anqs_hash_capacity(n); d_slots holds capacity*32 bytes.  d_amps may be NULL. */
+ * Open-addressing table in one caller-allocated buffer of anqs_hash_bytes(capacity) bytes:
+ * (capacity + 1) 32-byte slots {key, index, amp.re, amp.im} followed by capacity bytes of presence bits
+ * (8 per slot; a probe tests one bit first, so most misses cost a single 4-byte load).  Keys are stored
+ * de-interleaved (even bits | odd bits << 32).  capacity: power of two >= anqs_hash_capacity(n).
+ * d_amps may be NULL. */
 int64_t anqs_hash_capacity(int64_t n);
-int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_slots, int64_t capacity,
+size_t anqs_hash_bytes(int64_t capacity);
+int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                     void *stream);
-/* d_ptr[i] = position of d_queries[i] in the key array, or -1; d_mask[i] = (d_ptr[i] != -1) (may be NULL). */
-int anqs_hash_probe(const void *d_slots, int64_t capacity, const int64_t *d_queries, int64_t m,
+/* d_ptr[i] = position of d_queries[i] in the key array, or -1; d_mask[i] = (d_ptr[i] != -1) (either may be NULL). */
+int anqs_hash_probe(const void *d_table, int64_t capacity, const int64_t *d_queries, int64_t m,
                     int64_t *d_ptr, uint8_t *d_mask, void *stream);
 
 /* ---- A2+A3+A5+A6+A7  fused sample-aware local energy --------------------------------------------------
@@ -102,7 +106,7 @@ int anqs_hash_probe(const void *d_slots, int64_t capacity, const int64_t *d_quer
  * for rows [row_start, row_start+row_len) of the batch; the sampled set is the table built by
  * anqs_hash_build(d_samples, d_amps, n_total).  Nothing is materialised. */
 int anqs_local_energy_sample_aware(const anqs_tables_t *t, const int64_t *d_samples, const double *d_amps,
-                                   int64_t n_total, int64_t row_start, int64_t row_len, const void *d_slots,
+                                   int64_t n_total, int64_t row_start, int64_t row_len, const void *d_table,
                                    int64_t capacity, int alpha_num, int beta_num, double *d_eloc, void *stream);
 
 /* ---- A7  scatter of the materialised list (PO:453-478 / PO:1048-1057): E[dest] += H * psi(src) -------
