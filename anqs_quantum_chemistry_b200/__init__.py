@@ -6,3 +6,7 @@ hand-written sm_100a kernels behind the C ABI of libanqs_b200.so (include/anqs_b
 from .constants import BASE_INT_TYPE, BASE_REAL_TYPE, BASE_COMPLEX_TYPE  # noqa: F401
 from .hilbert_space import HilbertSpace, SampleTable  # noqa: F401
 from .pauli_observable import PauliObservable, PauliArraysOperator, LocalEnergyMetrics  # noqa: F401
+from .symmetries import ParticleNumberSymmetry, SpinHalfProjectionSymmetry, Z2Symmetry, IdleSymmetry  # noqa: F401
+from .masker import LocallyDecomposableMasker  # noqa: F401
+from .qubit_grouping import QubitGrouping, QubitGroupingConfig  # noqa: F401
+from .anqs import LogAbsPhaseANQS, ANQSConfig, MLPConfig, LocalSamplingConfig  # noqa: F401

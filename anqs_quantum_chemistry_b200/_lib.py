@@ -35,7 +35,24 @@ _SIGNATURES = {
     'anqs_hash_probe': (_c_int, [_vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp]),
     'anqs_local_energy_sample_aware': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _vp]),
     'anqs_accumulate_rows': (_c_int, [_vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
+    'anqs_made_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
+    'anqs_made_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
+    'anqs_sampler_split_level': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, _c_int, ctypes.c_uint64,
+                                          _c_i64, _vp, _vp, _vp]),
+    'anqs_sampler_emit_children': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp]),
+    'anqs_sampler_gumbel_level': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, ctypes.c_uint64,
+                                           _c_i64, _vp, _vp, _vp, _vp]),
 }
+
+
+class MadeDesc(ctypes.Structure):
+    """anqs_made_desc_t (include/anqs_b200.h)."""
+    _fields_ = [('qubit_num', ctypes.c_int32), ('qudit_num', ctypes.c_int32), ('max_qudit_dim', ctypes.c_int32),
+                ('depth', ctypes.c_int32), ('width', ctypes.c_int32), ('use_res', ctypes.c_int32),
+                ('subtract_mean', ctypes.c_int32), ('sym_num', ctypes.c_int32),
+                ('qudit_starts', ctypes.c_int32 * 65), ('du', ctypes.c_uint8 * 64), ('sym', (ctypes.c_int64 * 8) * 8),
+                ('w_abs', ctypes.c_void_p * 5), ('b_abs', ctypes.c_void_p * 5), ('w_phase', ctypes.c_void_p * 5),
+                ('b_phase', ctypes.c_void_p * 5), ('cont_mask', ctypes.c_void_p), ('memo_size', ctypes.c_int64)]
 
 # entry points added by later kernel families register themselves here (name -> (restype, argtypes))
 OPTIONAL_SIGNATURES = {}

@@ -1,0 +1,431 @@
+"""LogAbsPhaseANQS drop-in in MADE mode (reference: nqs/nqs/stochastic/ansatzes/anqs/{abstract_anqs,
+log_abs_phase_anqs,mlp}.py).
+
+Same constructor keywords, parameter names (`log_abs_subnet.layers.{i}.{weight,bias}`,
+`phase_subnet.layers.{i}.{weight,bias}`) and initialisation order as the reference, so `state_dict`s interchange and
+`pt.manual_seed(s)` followed by construction gives the reference's initial weights.  Method surface used by the
+reference's callers (SMP:51-101, EXP:525-545, CLE, SR, PG): amplitude, log_psi, sample_stats, sample_indices_gumbel,
+cond_log_abs, cat_grad, param_num, clip_grad_norm, compute_cat_log_jac, sort_base_idx, spin_flip_base_idx.
+
+Compute: forward passes run in the sm_100a kernels of libanqs_b200.so (k3_made.cu, k4_sampler.cu); the backward
+pass of log_psi is a hand-derived chain (no torch autograd graph through the network) whose GEMMs are plain
+library fp64 matmuls on the activations saved by the forward kernel.  There is no CPU path.
+"""
+import ctypes
+import math
+from typing import Tuple
+
+import numpy as np
+import torch as pt
+from torch import nn
+
+from . import _lib
+from .abstract_hilbert_space_object import AbstractHilbertSpaceObject
+from .constants import BASE_REAL_TYPE, BASE_COMPLEX_TYPE, NEGINF
+from .masker import LocallyDecomposableMasker
+from .qubit_grouping import QubitGrouping, QubitGroupingConfig
+
+LOCAL_SAMPLING_STRATEGIES = ('DU', 'MU')
+
+
+class LocalSamplingConfig:
+    """ANQS:20-50."""
+
+    def __init__(self, *args, pattern_type: str = 'uniform', strategy: str = 'MU', masking_depth: int = 0, **kwargs):
+        self.pattern_type, self.strategy, self.masking_depth = pattern_type, strategy, masking_depth
+
+    def create_local_sampling_pattern(self, qudit_num: int = None):
+        assert self.pattern_type == 'uniform'
+        assert self.strategy in LOCAL_SAMPLING_STRATEGIES
+        return (self.strategy,) * (qudit_num - self.masking_depth) + ('DU',) * self.masking_depth
+
+
+class MLPConfig:
+    """MLP:83-99 with the uniform width / bias / activation patterns of MLP:13-70 flattened into plain fields."""
+
+    def __init__(self, *args, depth: int = 2, width: int = 64, use_res: bool = True, use_bias: bool = True,
+                 activation=nn.Tanh, activate_last_layer: bool = False, **kwargs):
+        self.depth, self.width, self.use_res, self.use_bias = depth, width, use_res, use_bias
+        self.activation, self.activate_last_layer = activation, activate_last_layer
+
+
+class ANQSConfig:
+    """ANQS:68-109.  de_mode defaults to 'NADE' in the reference; only 'MADE' is implemented here."""
+    ALLOWED_DE_MODES = ('MADE', 'NADE')
+
+    def __init__(self, *args, dtype=BASE_REAL_TYPE, de_mode: str = 'MADE', qubit_grouping_config: QubitGroupingConfig = None,
+                 local_sampling_config: LocalSamplingConfig = None, subtract_mean: bool = True,
+                 main_subnet_config: MLPConfig = None, aux_subnet_config: MLPConfig = None,
+                 use_sign_structure: bool = False, **kwargs):
+        self.dtype = dtype
+        self.de_mode = de_mode
+        self.qubit_grouping_config = qubit_grouping_config if qubit_grouping_config is not None else QubitGroupingConfig()
+        self.local_sampling_config = local_sampling_config if local_sampling_config is not None else LocalSamplingConfig()
+        self.subtract_mean = subtract_mean
+        self.main_subnet_config = main_subnet_config if main_subnet_config is not None else MLPConfig()
+        self.aux_subnet_config = aux_subnet_config if aux_subnet_config is not None else MLPConfig()
+        self.use_sign_structure = use_sign_structure
+
+
+class MLP(nn.Module):
+    """MADE-masked MLP (MLP:102-246): parameters and causal masks only; the forward pass lives in k3_made.cu."""
+
+    def __init__(self, in_num: int = None, is_made: bool = True, qubit_grouping: QubitGrouping = None,
+                 dtype=BASE_REAL_TYPE, is_out_complex: bool = False, config: MLPConfig = None):
+        super().__init__()
+        assert is_made and qubit_grouping is not None, 'only the MADE form (one masked network) is implemented'
+        assert dtype == BASE_REAL_TYPE and not is_out_complex
+        self.config = config if config is not None else MLPConfig()
+        cfg = self.config
+        assert cfg.activation is nn.Tanh and not cfg.activate_last_layer, 'the kernels implement tanh hidden / identity output'
+        self.in_num, self.depth, self.dtype = in_num, cfg.depth, dtype
+        self.out_num = qubit_grouping.qudit_num
+        self.val_per_out = max(qubit_grouping.qudit_dims_host)
+        width = (cfg.width,) * cfg.depth
+        in_nums = (in_num,) + width
+        out_nums = width + (self.out_num * self.val_per_out,)
+        self.layers = nn.ModuleList([nn.Linear(in_nums[l], out_nums[l], bias=cfg.use_bias, dtype=dtype)
+                                     for l in range(cfg.depth + 1)])
+        # causal masks (MLP:170-203)
+        allowed = []
+        for l in range(cfg.depth):
+            row = []
+            for g in range(self.out_num):
+                row += [g] * (width[l] // self.out_num + 1 * ((self.out_num - g - 1) < (width[l] % self.out_num)))
+            allowed.append(row)
+        allowed = pt.tensor(allowed)
+        ends = qubit_grouping.qudit_ends
+        start_connect = []
+        for g in range(self.out_num):
+            start_connect += [g] * (ends[g] - (ends[g - 1] if g > 0 else 0))
+        start_connect = pt.tensor(start_connect)
+        start_mask = pt.greater(allowed[0].unsqueeze(-1), start_connect.unsqueeze(0)).type(dtype)
+        mid_masks = [pt.ge(allowed[l].unsqueeze(-1), allowed[l - 1].unsqueeze(0)).type(dtype) for l in range(1, cfg.depth)]
+        end_connect = pt.arange(self.out_num).unsqueeze(-1).tile((1, self.val_per_out)).reshape(-1)
+        end_mask = pt.ge(end_connect.unsqueeze(-1), allowed[-1].unsqueeze(0)).type(dtype)
+        self.made_masks = (start_mask,) + tuple(mid_masks) + (end_mask,)
+
+    def apply_made_masks_(self):
+        """MLP:230-233: the reference overwrites weight.data with weight.data * mask on every forward."""
+        with pt.no_grad():
+            for layer, mask in zip(self.layers, self.made_masks):
+                layer.weight.data.mul_(mask.to(layer.weight.device))
+
+
+class _MadeLogPsi(pt.autograd.Function):
+    """log psi(x) of a batch of packed configurations; backward by hand from the saved activations."""
+
+    @staticmethod
+    def forward(ctx, wf, idx, *params):
+        need_grad = any(p.requires_grad for p in params) and pt.is_grad_enabled()
+        log_psi, saved = wf._launch_log_psi(idx, save=need_grad)
+        ctx.wf, ctx.saved, ctx.idx = wf, saved, idx
+        ctx.weights = [p.detach() for p in params]
+        return log_psi
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        wf, idx = ctx.wf, ctx.idx
+        save_h, save_p = ctx.saved
+        B, Q, DM, depth = idx.shape[0], wf.qudit_num, wf.max_qudit_dim, wf.depth
+        g_re, g_im = grad_out.real.contiguous(), grad_out.imag.contiguous()
+        x = (1.0 - 2.0 * ((idx.view(-1, 1) >> wf.hilbert_space.shifts) & 1).to(pt.float64))  # [B, n]
+        chosen = wf.chosen_outcomes(idx)                                                    # [B, Q]
+        rows = chosen + DM * pt.arange(Q, device=idx.device).view(1, -1)                    # row of the output layer
+        n_layer = depth + 1
+        per_net = 2 * n_layer if wf.use_bias else n_layer
+        grads = [None] * (2 * per_net)
+
+        def put(net, layer, gw, gb):
+            base = net * per_net
+            if wf.use_bias:
+                grads[base + 2 * layer], grads[base + 2 * layer + 1] = gw, gb
+            else:
+                grads[base + layer] = gw
+
+        for net in range(2):
+            W = [ctx.weights[net * per_net + (2 * l if wf.use_bias else l)] for l in range(n_layer)]
+            h = [save_h[net, l] for l in range(depth)]  # [B, width] each
+            if net == 0:
+                # d log|psi| / d y_qd = [d == chosen] - p_qd (the mean subtraction drops out: the entries sum to zero)
+                dY = -(g_re.view(-1, 1, 1) * save_p)
+                dY.view(B, Q * DM).scatter_add_(1, rows, g_re.view(-1, 1).expand(B, Q))
+                dY = dY.view(B, Q * DM)
+                gw, gb = dY.t() @ h[-1], dY.sum(0)
+                dh = dY @ W[depth]
+            else:
+                coeff = (math.pi * g_im).view(-1, 1)                                        # arg psi = pi * sum_q y[q, chosen]
+                gw = pt.zeros_like(W[depth])
+                gw.index_add_(0, rows.reshape(-1), (coeff * h[-1]).unsqueeze(1).expand(B, Q, h[-1].shape[1]).reshape(B * Q, -1))
+                gb = pt.zeros(W[depth].shape[0], dtype=pt.float64, device=idx.device)
+                gb.index_add_(0, rows.reshape(-1), coeff.expand(B, Q).reshape(-1))
+                dh = coeff * W[depth][rows.reshape(-1)].view(B, Q, -1).sum(1)
+            put(net, depth, gw, gb)
+            for l in range(depth - 1, -1, -1):
+                da = dh * (1.0 - h[l] * h[l])
+                inp = x if l == 0 else h[l - 1]
+                put(net, l, da.t() @ inp, da.sum(0))
+                if l > 0:
+                    dh = da @ W[l]
+                    if wf.use_res:
+                        dh = dh + da
+        return (None, None) + tuple(grads)
+
+
+class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
+    def __init__(self, *args, config: ANQSConfig = None, masker: LocallyDecomposableMasker = None, **kwargs):
+        AbstractHilbertSpaceObject.__init__(self, *args, **kwargs)
+        nn.Module.__init__(self)
+        self.config = config if config is not None else ANQSConfig()
+        if self.config.de_mode != 'MADE':
+            raise NotImplementedError("anqs_b200 implements de_mode='MADE' (one masked network); 'NADE' is not built")
+        assert self.config.dtype == BASE_REAL_TYPE
+        assert not self.config.use_sign_structure
+        self.dtype, self.de_mode = self.config.dtype, 'MADE'
+        self.masker = masker
+        self.qubit_grouping_config = self.config.qubit_grouping_config
+        self.qubit_grouping = QubitGrouping.create(hs=self.hilbert_space, config=self.qubit_grouping_config, masker=masker)
+        self.max_qudit_dim = max(self.qubit_grouping.qudit_dims_host)
+        self.local_sampling_config = self.config.local_sampling_config
+        self.local_sampling_pattern = self.local_sampling_config.create_local_sampling_pattern(qudit_num=self.qudit_num)
+        main, aux = self.config.main_subnet_config, self.config.aux_subnet_config
+        assert (main.depth, main.width, main.use_res, main.use_bias) == (aux.depth, aux.width, aux.use_res, aux.use_bias), \
+            'the kernel evaluates both sub-networks with one shape'
+        self.depth, self.width, self.use_res, self.use_bias = main.depth, main.width, main.use_res, main.use_bias
+        # construction order = reference order (LAP:43-56), so the global torch RNG yields the same initial weights
+        self.log_abs_subnet = MLP(in_num=self.qubit_num, is_made=True, qubit_grouping=self.qubit_grouping, dtype=self.dtype, config=main)
+        self.phase_subnet = MLP(in_num=self.qubit_num, is_made=True, qubit_grouping=self.qubit_grouping, dtype=self.dtype, config=aux)
+        self.to(self.device)
+        self._param_num = None
+        self._next_memo = None
+        self.sampler_seed = int(self.rng_seed)
+        self._sampler_calls = 0
+
+    # ---- shapes ------------------------------------------------------------------------------------------------
+    qudit_num = property(lambda self: self.qubit_grouping.qudit_num)
+    qudit_dims = property(lambda self: self.qubit_grouping.qudit_dims)
+    qudit_starts = property(lambda self: self.qubit_grouping.qudit_starts)
+    qudit_ends = property(lambda self: self.qubit_grouping.qudit_ends)
+
+    @property
+    def param_num(self):
+        if self._param_num is None:
+            self._param_num = sum(p.numel() for p in self.parameters())
+        return self._param_num
+
+    @property
+    def param_shapes(self):
+        return tuple(p.shape for p in self.parameters())
+
+    @property
+    def cat_grad_splits(self):
+        return tuple(p.numel() for p in self.parameters())
+
+    @property
+    def cat_grad(self):
+        return pt.cat([(p.grad.data if p.grad is not None else pt.zeros_like(p)).reshape(-1) for p in self.parameters()])
+
+    @cat_grad.setter
+    def cat_grad(self, cat_grad: pt.Tensor):
+        for p, g in zip(self.parameters(), pt.split(cat_grad, self.cat_grad_splits)):
+            p.grad = g.reshape(p.shape)
+
+    def clip_grad_norm(self, value: float = None):
+        pt.nn.utils.clip_grad_norm_(self.parameters(), value)
+
+    # ---- kernel plumbing ---------------------------------------------------------------------------------------
+    def _descriptor(self) -> _lib.MadeDesc:
+        dev = _lib.require_cuda(self.device)
+        self.log_abs_subnet.apply_made_masks_()
+        self.phase_subnet.apply_made_masks_()
+        d = _lib.MadeDesc()
+        qg = self.qubit_grouping
+        d.qubit_num, d.qudit_num, d.max_qudit_dim = self.qubit_num, qg.qudit_num, self.max_qudit_dim
+        d.depth, d.width, d.use_res = self.depth, self.width, int(self.use_res)
+        d.subtract_mean, d.sym_num = int(self.config.subtract_mean), self.masker.sym_num
+        for q in range(qg.qudit_num):
+            d.qudit_starts[q] = qg.qudit_starts[q]
+            d.du[q] = 1 if self.local_sampling_pattern[q] == 'DU' else 0
+        d.qudit_starts[qg.qudit_num] = self.qubit_num
+        for s, row in enumerate(self.masker.symmetry_descriptors()):
+            for j, v in enumerate(row):
+                d.sym[s][j] = int(v)
+        keep = []
+        for name, net in (('abs', self.log_abs_subnet), ('phase', self.phase_subnet)):
+            for l, layer in enumerate(net.layers):
+                w = layer.weight.data
+                assert w.is_contiguous() and w.dtype == pt.float64 and w.device == dev
+                getattr(d, f'w_{name}')[l] = w.data_ptr()
+                getattr(d, f'b_{name}')[l] = layer.bias.data.data_ptr() if layer.bias is not None else None
+                keep.append(w)
+        d.cont_mask = qg.cont_mask_words.data_ptr()
+        d.memo_size = self.masker.memo_size
+        d._keep = keep
+        return d
+
+    def _launch_log_psi(self, idx: pt.Tensor, save: bool):
+        dev = _lib.require_cuda(self.device)
+        assert idx.dtype == pt.int64 and idx.dim() == 1 and idx.is_contiguous() and idx.device == dev
+        B = idx.shape[0]
+        out = pt.empty(B, dtype=pt.complex128, device=dev)
+        save_h = pt.empty((2, self.depth, B, self.width), dtype=pt.float64, device=dev) if save else None
+        save_p = pt.empty((B, self.qudit_num, self.max_qudit_dim), dtype=pt.float64, device=dev) if save else None
+        desc = self._descriptor()
+        _lib.check(_lib.lib().anqs_made_log_psi(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(out)),
+                                                _lib.dptr(save_h), _lib.dptr(save_p), _lib.stream_ptr(dev)))
+        return out, (save_h, save_p)
+
+    def chosen_outcomes(self, idx: pt.Tensor) -> pt.Tensor:
+        """[B, Q] local outcome index of every qudit (QG:148-154) straight from the packed word."""
+        starts = pt.tensor(self.qudit_starts, dtype=pt.int64, device=idx.device)
+        widths = pt.tensor(self.qubit_grouping.qubits_per_qudit, dtype=pt.int64, device=idx.device)
+        return (idx.view(-1, 1) >> starts) & ((1 << widths) - 1)
+
+    # ---- reference surface ---------------------------------------------------------------------------------------
+    def log_psi_of_indices(self, base_idx: pt.Tensor) -> pt.Tensor:
+        idx = base_idx.contiguous().view(-1)
+        return _MadeLogPsi.apply(self, idx, *list(self.parameters()))
+
+    def log_psi(self, base_vec: pt.Tensor, just_return: bool = False) -> pt.Tensor:
+        """ANQS:407-481 (argument is the unpacked bit matrix, as in the reference)."""
+        return self.log_psi_of_indices(self.base_vec2base_idx(base_vec))
+
+    def amplitude(self, base_idx: pt.Tensor) -> pt.Tensor:
+        """ANQS:483-485."""
+        return pt.exp(self.log_psi_of_indices(base_idx))
+
+    def phase(self, base_idx: pt.Tensor) -> pt.Tensor:
+        return self.log_psi_of_indices(base_idx).imag
+
+    def forward(self, base_idx: pt.Tensor) -> pt.Tensor:
+        return self.amplitude(base_idx)
+
+    @pt.no_grad()
+    def cond_log_abs(self, qudit_idx: int = None, base_vec: pt.Tensor = None, return_all_if_made: bool = False,
+                     mask: pt.Tensor = None, prefix_idx: pt.Tensor = None) -> pt.Tensor:
+        """LAP:105-163 for one qudit: [B, max_qudit_dim] normalised conditional log|psi| (-inf where masked).
+        `mask` is accepted for signature compatibility; the kernel derives it from the prefix (QG:199-213)."""
+        assert not return_all_if_made
+        dev = _lib.require_cuda(self.device)
+        if prefix_idx is None:
+            prefix_idx = self.hilbert_space.base_vec2base_idx(base_vec).view(-1) if base_vec.shape[-1] > 0 else \
+                pt.zeros(base_vec.shape[0], dtype=pt.int64, device=dev)
+        prefix_idx = prefix_idx.contiguous().view(-1)
+        B = prefix_idx.shape[0]
+        out = pt.empty((B, self.max_qudit_dim), dtype=pt.float64, device=dev)
+        desc = self._descriptor()
+        _lib.check(_lib.lib().anqs_made_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
+                                                     _lib.stream_ptr(dev)))
+        return out
+
+    # ---- samplers ------------------------------------------------------------------------------------------------
+    def _level_tables(self, q: int):
+        qg = self.qubit_grouping
+        if self._next_memo is None:
+            self._next_memo = [pt.from_numpy(np.ascontiguousarray(t.astype(np.int32))).to(self.device) for t in qg.next_memo_host]
+        return qg.cont_mask_words[q], self._next_memo[q]
+
+    def _start_memo_idx(self) -> int:
+        start = np.array([[sym.start_eig for sym in self.masker.symmetries]], dtype=np.int64)
+        return int(self.masker.acc_eigs2memo_idx_np(start)[0])
+
+    @pt.no_grad()
+    def sample_stats(self, sample_num: int, draw_mode: str = 'philox', seed: int = None) -> Tuple[pt.Tensor, pt.Tensor]:
+        """ANQS:494-525: breadth-first count splitting.  Returns (unique indices [N,1] int64, counts [N] complex128).
+        draw_mode 'philox' draws binomials from the counter-based generator (seeded by hilbert_space.rng_seed and a
+        per-call counter); 'rint' replaces every draw by its rounded mean (deterministic)."""
+        dev = _lib.require_cuda(self.device)
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        qg = self.qubit_grouping
+        if seed is None:
+            seed = (self.sampler_seed * 0x9E3779B97F4A7C15 + self._sampler_calls) & 0xFFFFFFFFFFFFFFFF
+            self._sampler_calls += 1
+        mode = {'rint': 0, 'philox': 1}[draw_mode]
+        prefix = pt.zeros(1, dtype=pt.int64, device=dev)
+        counts = pt.tensor([float(sample_num)], dtype=pt.float64, device=dev)
+        memo = pt.tensor([self._start_memo_idx()], dtype=pt.int32, device=dev)
+        for q in range(qg.qudit_num):
+            B = prefix.shape[0]
+            k, D = qg.qubits_per_qudit[q], qg.qudit_dims_host[q]
+            cont_q, next_q = self._level_tables(q)
+            cond = self.cond_log_abs(qudit_idx=q, prefix_idx=prefix)
+            child = pt.empty((B, D), dtype=pt.float64, device=dev)
+            n_child = pt.empty(B, dtype=pt.int64, device=dev)
+            _lib.check(lib.anqs_sampler_split_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(counts), _lib.dptr(memo),
+                                                    _lib.dptr(cont_q), self.masker.memo_size, B, q, mode, seed, 0,
+                                                    _lib.dptr(child), _lib.dptr(n_child), sp))
+            offsets = pt.empty(B + 1, dtype=pt.int64, device=dev)
+            work = pt.empty(max(1, int(lib.anqs_scan_workspace(B)) // 8), dtype=pt.int64, device=dev)
+            _lib.check(lib.anqs_exclusive_scan_i64(_lib.dptr(n_child), _lib.dptr(offsets), B, _lib.dptr(work), sp))
+            total = int(offsets[-1].item())
+            new_prefix = pt.empty(total, dtype=pt.int64, device=dev)
+            new_counts = pt.empty(total, dtype=pt.float64, device=dev)
+            new_memo = pt.empty(total, dtype=pt.int32, device=dev)
+            if total > 0:
+                _lib.check(lib.anqs_sampler_emit_children(_lib.dptr(child), k, qg.qudit_starts[q], _lib.dptr(prefix), _lib.dptr(memo),
+                                                          _lib.dptr(cont_q), _lib.dptr(next_q), self.masker.memo_size, B,
+                                                          _lib.dptr(offsets), _lib.dptr(new_prefix), _lib.dptr(new_counts),
+                                                          _lib.dptr(new_memo), sp))
+            prefix, counts, memo = new_prefix, new_counts, new_memo
+        return prefix.view(-1, 1), counts.to(BASE_COMPLEX_TYPE)
+
+    @pt.no_grad()
+    def sample_indices_gumbel(self, sample_num: int, seed: int = None, uniforms=None):
+        """ANQS:778-818: stochastic-beam (Gumbel top-k) sampling without replacement.  Returns (indices [N,1],
+        freqs [N] = model probabilities renormalised over the kept set).  `uniforms`, if given, is a callable
+        (level, B, D) -> [B, D] float64 tensor of U(0,1) variates (parity tests)."""
+        dev = _lib.require_cuda(self.device)
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        qg = self.qubit_grouping
+        if seed is None:
+            seed = (self.sampler_seed * 0x9E3779B97F4A7C15 + 0x5bd1e995 + self._sampler_calls) & 0xFFFFFFFFFFFFFFFF
+            self._sampler_calls += 1
+        prefix = pt.zeros(1, dtype=pt.int64, device=dev)
+        log_prob = pt.zeros(1, dtype=pt.float64, device=dev)
+        gumbel = pt.zeros(1, dtype=pt.float64, device=dev)
+        memo = pt.tensor([self._start_memo_idx()], dtype=pt.int32, device=dev)
+        for q in range(qg.qudit_num):
+            B = prefix.shape[0]
+            k, D = qg.qubits_per_qudit[q], qg.qudit_dims_host[q]
+            cont_q, next_q = self._level_tables(q)
+            cond = self.cond_log_abs(qudit_idx=q, prefix_idx=prefix)
+            out_lp = pt.empty((B, D), dtype=pt.float64, device=dev)
+            out_g = pt.empty((B, D), dtype=pt.float64, device=dev)
+            u = uniforms(q, B, D).to(dev).contiguous() if uniforms is not None else None
+            _lib.check(lib.anqs_sampler_gumbel_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(log_prob), _lib.dptr(gumbel),
+                                                     _lib.dptr(memo), _lib.dptr(cont_q), self.masker.memo_size, B, q, seed, 0,
+                                                     _lib.dptr(u), _lib.dptr(out_lp), _lib.dptr(out_g), sp))
+            flat_g = out_g.view(-1)
+            keep = min(sample_num, flat_g.shape[0])
+            top_g, top_i = pt.sort(flat_g, descending=True, stable=True)   # ANQS:733
+            top_g, top_i = top_g[:keep], top_i[:keep]
+            alive = top_g > -math.inf                                       # masked children (ANQS:804-809 phys_mask)
+            top_g, top_i = top_g[alive], top_i[alive]
+            parent, outcome = top_i // D, top_i % D
+            prefix = prefix[parent] | (outcome << qg.qudit_starts[q])
+            memo = next_q.view(-1)[memo[parent].to(pt.int64) * D + outcome]
+            log_prob, gumbel = out_lp.view(-1)[top_i], top_g
+        log_prob = log_prob - pt.logsumexp(log_prob, dim=0)
+        return prefix.view(-1, 1), pt.exp(log_prob)
+
+    # ---- per-sample log-Jacobian for stochastic reconfiguration (ANQS:820-839) ----------------------------------
+    def compute_cat_log_jac(self, indices: pt.Tensor) -> pt.Tensor:
+        """[B, param_num] complex128: d log(conj psi(x_b)) / d theta, parameters concatenated in .parameters() order."""
+        idx = indices.contiguous().view(-1)
+        B = idx.shape[0]
+        rows = []
+        params = list(self.parameters())
+        for b in range(B):  # the reference restricts this to max_indices_num = 25..50 samples (SR:20-32)
+            lp = _MadeLogPsi.apply(self, idx[b:b + 1], *params)
+            g_re = pt.autograd.grad(lp.real.sum(), params, retain_graph=True)
+            g_im = pt.autograd.grad(lp.imag.sum(), params)
+            rows.append(pt.complex(pt.cat([g.reshape(-1) for g in g_re]), -pt.cat([g.reshape(-1) for g in g_im])))
+        return pt.stack(rows)
+
+    @staticmethod
+    def spin_flip_base_vec(base_vec):
+        assert (base_vec.shape[-1] % 2) == 0
+        return pt.stack((base_vec[..., 1::2], base_vec[..., ::2]), dim=-1).reshape(base_vec.shape)
+
+    def spin_flip_base_idx(self, base_idx):
+        return self.base_vec2base_idx(self.spin_flip_base_vec(self.base_idx2base_vec(base_idx)))

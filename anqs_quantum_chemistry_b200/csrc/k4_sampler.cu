@@ -1,0 +1,347 @@
+// Kernel family 4: one level of the autoregressive batch samplers.
+//
+//   split_level_kernel    exact multinomial split of every parent count over the D = 2^k outcomes of the next
+//                         qudit as k rounds of binomial draws on a cumulative-probability tree
+//                         (reference ANQS:557-591 sample_mult_new_new inside ANQS:593-662)
+//   emit_children_kernel  ordered compaction of the surviving (allowed, count > 0) children (ANQS:645-660)
+//   gumbel_level_kernel   conditional Gumbel perturbation of the children of every parent for stochastic-beam
+//                         (top-k without replacement) sampling (ANQS:676-688, 718-731)
+//
+// One warp owns one parent.  The split keeps the binomial tree in registers: after round j lane t holds the
+// count of tree node t (path bits most-significant first), children are handed down with two shuffles, and the
+// last round leaves outcomes 2*lane and 2*lane+1 in every lane.  Random numbers are counter-based (Philox4x32-10
+// keyed by the seed, counter = level / round / node / parent), so a level is reproducible independently of how
+// parents are distributed over warps, launches or GPUs - which is what lets sub-trees be sharded with no
+// communication.  draw_mode 0 replaces the binomial draw by its rounded mean rint(n p): the deterministic mode
+// the parity tests use against the reference with torch.distributions.Binomial patched the same way.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace anqs {
+
+// ---- Philox4x32-10 ---------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    __device__ __forceinline__ Philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+        key[0] = (uint32_t)seed;
+        key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = c0; ctr[1] = c1; ctr[2] = c2; ctr[3] = c3;
+    }
+    __device__ __forceinline__ uint4 operator()() const {
+        uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+// uniform in (0, 1) with 53 random bits
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
+    uint64_t v = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11) ^ ((uint64_t)(b & 0x7FFu) << 42);
+    v &= (1ull << 53) - 1ull;
+    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// Binomial(n, p) variate: inversion for n*min(p,1-p) < 10, BTRS (Hormann 1993) otherwise.
+__device__ double binomial_draw(double n, double p, uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2) {
+    if (!(n > 0.0) || !(p > 0.0)) return 0.0;
+    if (p >= 1.0) return n;
+    const bool flip = p > 0.5;
+    const double pp = flip ? 1.0 - p : p, q = 1.0 - pp;
+    double k;
+    uint32_t it = 0;
+    if (n * pp < 10.0) {
+        Philox g(seed, c0, c1, c2, it);
+        uint4 r = g();
+        double u = u01(r.x, r.y);
+        const double ratio = pp / q;
+        double f = exp(n * log1p(-pp));
+        k = 0.0;
+        while (u > f && k < n) {
+            u -= f;
+            k += 1.0;
+            f *= ratio * (n - k + 1.0) / k;
+            if (f <= 0.0) break;
+        }
+    } else {
+        const double spq = sqrt(n * pp * q);
+        const double b = 1.15 + 2.53 * spq, a = -0.0873 + 0.0248 * b + 0.01 * pp, c = n * pp + 0.5;
+        const double vr = 0.92 - 4.2 / b, alpha = (2.83 + 5.1 / b) * spq;
+        const double lpq = log(pp / q), m = floor((n + 1.0) * pp);
+        const double h = lgamma(m + 1.0) + lgamma(n - m + 1.0);
+        for (;;) {
+            Philox g(seed, c0, c1, c2, it++);
+            uint4 r = g();
+            const double u = u01(r.x, r.y) - 0.5;
+            double v = u01(r.z, r.w);
+            const double us = 0.5 - fabs(u);
+            k = floor((2.0 * a / us + b) * u + c);
+            if (k < 0.0 || k > n) continue;
+            if (us >= 0.07 && v <= vr) break;
+            v = log(v * alpha / (a / (us * us) + b));
+            if (v <= h - lgamma(k + 1.0) - lgamma(n - k + 1.0) + (k - m) * lpq) break;
+        }
+    }
+    return flip ? n - k : k;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+constexpr int K4_WARPS = 8;
+
+// cond [B][DM]: normalised conditional log|psi| (-inf = masked).  child_counts [B][D] out; n_children [B] out.
+__global__ void __launch_bounds__(K4_WARPS * 32)
+split_level_kernel(const double *__restrict__ cond, int DM, int k, const double *__restrict__ counts,
+                   const int32_t *__restrict__ memo_idx, const unsigned long long *__restrict__ cont_mask_q,
+                   int64_t memo_size, int64_t B, int level, int draw_mode, uint64_t seed, int64_t parent_offset,
+                   double *__restrict__ child_counts, int64_t *__restrict__ n_children) {
+    __shared__ double cum_all[K4_WARPS][66];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *cum = cum_all[warp];
+    const int D = 1 << k;
+    for (int64_t b = (int64_t)blockIdx.x * K4_WARPS + warp; b < B; b += (int64_t)gridDim.x * K4_WARPS) {
+        // probabilities = softmax(2 * logits), nan -> 0 (ANQS:560-561)
+        const double l0 = lane < D ? 2.0 * cond[b * DM + lane] : -INFINITY;
+        const double l1 = lane + 32 < D ? 2.0 * cond[b * DM + lane + 32] : -INFINITY;
+        const double mx = warp_max(fmax(l0, l1));
+        double e0 = lane < D ? exp(l0 - mx) : 0.0, e1 = lane + 32 < D ? exp(l1 - mx) : 0.0;
+        if (!(mx > -INFINITY)) e0 = e1 = 0.0;
+        const double sum = warp_sum(e0 + e1);
+        double p0 = e0 / sum, p1 = e1 / sum;
+        if (!(sum > 0.0)) p0 = p1 = 0.0;
+        __syncwarp();
+        cum[1 + lane] = p0;
+        cum[33 + lane] = p1;
+        __syncwarp();
+        if (lane == 0) {  // sequential prefix sum, like a cumsum along the row (ANQS:562-565)
+            double acc = 0.0;
+            cum[0] = 0.0;
+            for (int d = 1; d <= D; ++d) {
+                acc += cum[d];
+                cum[d] = acc;
+            }
+        }
+        __syncwarp();
+        // binomial tree, most significant outcome bit first (ANQS:568-585)
+        double cnt = counts[b];  // count of tree node `lane` (valid for lane < 2^j in round j)
+        double c_even = 0.0, c_odd = 0.0;
+        for (int j = 0; j < k; ++j) {
+            const int nodes = 1 << j, span = D >> j;
+            double left = 0.0;
+            if (lane < nodes) {
+                const int lo = lane * span, mid = lo + (span >> 1), hi = lo + span;
+                const double succ = cum[mid] - cum[lo], fail = cum[hi] - cum[mid];
+                double pr = succ / (succ + fail);
+                if (!(pr == pr)) pr = 0.0;  // nan_to_num (ANQS:578)
+                if (draw_mode == 0) {
+                    left = fmin(cnt, fmax(0.0, rint(cnt * pr)));
+                } else {
+                    const uint64_t parent = (uint64_t)(parent_offset + b);
+                    left = binomial_draw(cnt, pr, seed, (uint32_t)parent, (uint32_t)(parent >> 32),
+                                         ((uint32_t)level << 16) | ((uint32_t)j << 8) | (uint32_t)lane);
+                }
+            }
+            if (j + 1 < k) {
+                const double n_par = __shfl_sync(0xffffffffu, cnt, lane >> 1);
+                const double l_par = __shfl_sync(0xffffffffu, left, lane >> 1);
+                cnt = (lane & 1) ? n_par - l_par : l_par;
+            } else {
+                c_even = left;        // outcome 2*lane
+                c_odd = cnt - left;   // outcome 2*lane + 1
+            }
+        }
+        const int half = D >> 1;
+        unsigned long long mw = 0ull;
+        const int mi = memo_idx[b];
+        if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];
+        const bool s_even = lane < half && ((mw >> (2 * lane)) & 1ull) && c_even > 0.0;
+        const bool s_odd = lane < half && ((mw >> (2 * lane + 1)) & 1ull) && c_odd > 0.0;
+        if (lane < half) {
+            child_counts[b * D + 2 * lane] = c_even;
+            child_counts[b * D + 2 * lane + 1] = c_odd;
+        }
+        const unsigned be = __ballot_sync(0xffffffffu, s_even), bo = __ballot_sync(0xffffffffu, s_odd);
+        if (lane == 0) n_children[b] = __popc(be) + __popc(bo);
+    }
+}
+
+__global__ void __launch_bounds__(K4_WARPS * 32)
+emit_children_kernel(const double *__restrict__ child_counts, int k, int start, const int64_t *__restrict__ prefix,
+                     const int32_t *__restrict__ memo_idx, const unsigned long long *__restrict__ cont_mask_q,
+                     const int32_t *__restrict__ next_memo_q, int64_t memo_size, int64_t B,
+                     const int64_t *__restrict__ offsets, int64_t *__restrict__ out_prefix,
+                     double *__restrict__ out_counts, int32_t *__restrict__ out_memo) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = lanemask_lt();
+    const int D = 1 << k, half = D >> 1;
+    for (int64_t b = (int64_t)blockIdx.x * K4_WARPS + warp; b < B; b += (int64_t)gridDim.x * K4_WARPS) {
+        const int mi = memo_idx[b];
+        unsigned long long mw = 0ull;
+        if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];
+        double c_even = 0.0, c_odd = 0.0;
+        if (lane < half) {
+            c_even = child_counts[b * D + 2 * lane];
+            c_odd = child_counts[b * D + 2 * lane + 1];
+        }
+        const bool s_even = lane < half && ((mw >> (2 * lane)) & 1ull) && c_even > 0.0;
+        const bool s_odd = lane < half && ((mw >> (2 * lane + 1)) & 1ull) && c_odd > 0.0;
+        const unsigned be = __ballot_sync(0xffffffffu, s_even), bo = __ballot_sync(0xffffffffu, s_odd);
+        const int64_t base = offsets[b];
+        const uint64_t px = (uint64_t)prefix[b];
+        const int before = __popc(be & lt) + __popc(bo & lt);
+        if (s_even) {
+            const int64_t r = base + before;
+            const int d = 2 * lane;
+            out_prefix[r] = (int64_t)(px | ((uint64_t)d << start));
+            out_counts[r] = c_even;
+            out_memo[r] = next_memo_q[(size_t)mi * D + d];
+        }
+        if (s_odd) {
+            const int64_t r = base + before + (s_even ? 1 : 0);
+            const int d = 2 * lane + 1;
+            out_prefix[r] = (int64_t)(px | ((uint64_t)d << start));
+            out_counts[r] = c_odd;
+            out_memo[r] = next_memo_q[(size_t)mi * D + d];
+        }
+    }
+}
+
+__device__ __forceinline__ double log1mexp(double x) {  // ANQS:664-668
+    return x > -0.693 ? log(-expm1(x)) : log1p(-exp(x));
+}
+__device__ __forceinline__ double log1pexp(double x) {  // ANQS:670-674
+    return x < 18.0 ? log1p(exp(x)) : x + exp(-x);
+}
+
+// children of every parent: log_prob = parent log_prob + 2 cond; Gumbel conditioned on the parent's Gumbel being
+// the maximum (ANQS:676-688).  Outputs are [B][D]; masked children get gumbel = -inf.
+__global__ void __launch_bounds__(K4_WARPS * 32)
+gumbel_level_kernel(const double *__restrict__ cond, int DM, int k, const double *__restrict__ parent_log_prob,
+                    const double *__restrict__ parent_gumbel, const int32_t *__restrict__ memo_idx,
+                    const unsigned long long *__restrict__ cont_mask_q, int64_t memo_size, int64_t B, int level,
+                    uint64_t seed, int64_t parent_offset, const double *__restrict__ uniforms,
+                    double *__restrict__ out_log_prob, double *__restrict__ out_gumbel) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = 1 << k;
+    for (int64_t b = (int64_t)blockIdx.x * K4_WARPS + warp; b < B; b += (int64_t)gridDim.x * K4_WARPS) {
+        const double lp = parent_log_prob[b], G = parent_gumbel[b];
+        const int mi = memo_idx[b];
+        unsigned long long mw = 0ull;
+        if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];
+        double phi[2], g[2];
+        bool in[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int d = lane + 32 * h;
+            in[h] = d < D;
+            phi[h] = -INFINITY;
+            g[h] = -INFINITY;
+            if (in[h]) {
+                double v = lp + 2.0 * cond[b * DM + d];
+                if (!(v == v)) v = -INFINITY;  // nan_to_num (ANQS:726)
+                phi[h] = v;
+                double u;
+                if (uniforms) {
+                    u = uniforms[b * D + d];
+                } else {
+                    const uint64_t parent = (uint64_t)(parent_offset + b);
+                    Philox rng(seed, (uint32_t)parent, (uint32_t)(parent >> 32), ((uint32_t)level << 16) | (uint32_t)d, 0x47u);
+                    uint4 r = rng();
+                    u = u01(r.x, r.y);
+                }
+                g[h] = v - log(-log(u));
+            }
+        }
+        const double Z = warp_max(fmax(g[0], g[1]));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!in[h]) continue;
+            const int d = lane + 32 * h;
+            const double v = G - g[h] + log1mexp(g[h] - Z);
+            double out = G - fmax(v, 0.0) - log1pexp(-fabs(v));
+            if (!(out == out) || !((mw >> d) & 1ull)) out = -INFINITY;  // nan_to_num (ANQS:731); masked children never survive
+            out_log_prob[b * D + d] = phi[h];
+            out_gumbel[b * D + d] = out;
+        }
+    }
+}
+
+}  // namespace anqs
+
+using namespace anqs;
+
+extern "C" {
+
+int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits_in_qudit, const double *d_counts,
+                             const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n,
+                             int level, int draw_mode, uint64_t seed, int64_t parent_offset, double *d_child_counts,
+                             int64_t *d_n_children, void *stream) {
+    ANQS_REQUIRE(n >= 0, "negative parent count");
+    ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6 && (1 << qubits_in_qudit) <= max_qudit_dim && max_qudit_dim <= 64,
+                 "qudit must have 1..6 qubits and fit max_qudit_dim <= 64");
+    ANQS_REQUIRE(draw_mode == 0 || draw_mode == 1, "draw_mode must be 0 (rounded mean) or 1 (Philox binomial)");
+    if (n == 0) return 0;
+    ANQS_REQUIRE(d_cond && d_counts && d_memo_idx && d_cont_mask_q && d_child_counts && d_n_children, "null pointer");
+    int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
+    split_level_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        d_cond, max_qudit_dim, qubits_in_qudit, d_counts, d_memo_idx, (const unsigned long long *)d_cont_mask_q, memo_size, n,
+        level, draw_mode, seed, parent_offset, d_child_counts, d_n_children);
+    ANQS_LAUNCH_CHECK();
+    return 0;
+}
+
+int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit, int qudit_start,
+                               const int64_t *d_prefix, const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q,
+                               const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,
+                               int64_t *d_out_prefix, double *d_out_counts, int32_t *d_out_memo_idx, void *stream) {
+    ANQS_REQUIRE(n >= 0, "negative parent count");
+    ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6, "qudit must have 1..6 qubits");
+    ANQS_REQUIRE(qudit_start >= 0 && qudit_start + qubits_in_qudit <= 64, "qudit outside the 64-bit word");
+    if (n == 0) return 0;
+    ANQS_REQUIRE(d_child_counts && d_prefix && d_memo_idx && d_cont_mask_q && d_next_memo_q && d_offsets && d_out_prefix &&
+                     d_out_counts && d_out_memo_idx, "null pointer");
+    int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
+    emit_children_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        d_child_counts, qubits_in_qudit, qudit_start, d_prefix, d_memo_idx, (const unsigned long long *)d_cont_mask_q,
+        d_next_memo_q, memo_size, n, d_offsets, d_out_prefix, d_out_counts, d_out_memo_idx);
+    ANQS_LAUNCH_CHECK();
+    return 0;
+}
+
+int anqs_sampler_gumbel_level(const double *d_cond, int max_qudit_dim, int qubits_in_qudit,
+                              const double *d_parent_log_prob, const double *d_parent_gumbel, const int32_t *d_memo_idx,
+                              const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n, int level, uint64_t seed,
+                              int64_t parent_offset, const double *d_uniforms, double *d_out_log_prob,
+                              double *d_out_gumbel, void *stream) {
+    ANQS_REQUIRE(n >= 0, "negative parent count");
+    ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6 && (1 << qubits_in_qudit) <= max_qudit_dim && max_qudit_dim <= 64,
+                 "qudit must have 1..6 qubits and fit max_qudit_dim <= 64");
+    if (n == 0) return 0;
+    ANQS_REQUIRE(d_cond && d_parent_log_prob && d_parent_gumbel && d_memo_idx && d_cont_mask_q && d_out_log_prob && d_out_gumbel,
+                 "null pointer");
+    int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
+    gumbel_level_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        d_cond, max_qudit_dim, qubits_in_qudit, d_parent_log_prob, d_parent_gumbel, d_memo_idx,
+        (const unsigned long long *)d_cont_mask_q, memo_size, n, level, seed, parent_offset, d_uniforms, d_out_log_prob, d_out_gumbel);
+    ANQS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

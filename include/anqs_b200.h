@@ -13,7 +13,7 @@
  *
  * Conventions
  *   - every pointer named d_* is a DEVICE pointer on the current CUDA device, h_* is a HOST pointer;
- *   - all buffers are caller-allocated; the library owns only opaque handles (anqs_tables_t, anqs_made_t);
+ *   - all buffers are caller-allocated; the library owns only the opaque anqs_tables_t handle;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous
  *     with respect to the host unless stated otherwise;
  *   - return value 0 = success, non-zero = failure with a thread-local message in anqs_last_error();
@@ -34,7 +34,6 @@ extern "C" {
 #define ANQS_ABI_VERSION 1
 
 typedef struct anqs_tables anqs_tables_t; /* device-resident Hamiltonian term tables (PO:103-115)   */
-typedef struct anqs_made anqs_made_t;     /* device-resident MADE network + symmetry tables           */
 
 int anqs_abi_version(void);
 const char *anqs_last_error(void);
@@ -88,9 +87,9 @@ int anqs_matrix_elements(const anqs_tables_t *t, const int64_t *d_xprime, const 
 
 /* ---- A5  kernel 2: membership join, HilbertSpace.find_a_in_b (HS:263-284) -----------------------------
  * Open-addressing table in one caller-allocated buffer of anqs_hash_bytes(capacity) bytes:
- * (capacity + 1) 32-byte slots {key, index, amp.re, amp.im} followed by capacity bytes of presence bits
- * (8 per slot; a probe tests one bit first, so most misses cost a single 4-byte load).  Keys are stored
- * de-interleaved (even bits | odd bits << 32).  capacity: power of two >= anqs_hash_capacity(n).
+ * (capacity + 1) 32-byte slots {key, index, amp.re, amp.im} followed by capacity bytes of blocked-Bloom
+ * presence bits (3 bits of one 32-bit word per key; a probe tests that word first, so ~99 % of the misses cost
+ * a single 4-byte load).  Keys are stored de-interleaved (even bits | odd bits << 32).  capacity: power of two >= anqs_hash_capacity(n).
  * d_amps may be NULL. */
 int64_t anqs_hash_capacity(int64_t n);
 size_t anqs_hash_bytes(int64_t capacity);
@@ -115,6 +114,67 @@ int anqs_local_energy_sample_aware(const anqs_tables_t *t, const int64_t *d_samp
 int anqs_accumulate_rows(const int64_t *d_offsets, int64_t n, const int64_t *d_src_ptr, const double *d_H,
                          int h_components, const double *d_src_amps, const double *d_amps_dest, double *d_eloc,
                          int accumulate, void *stream);
+
+/* ---- A9 + A10  kernel 3: MADE wave function (ANQS:309-485, LAP:14-163, MLP:102-246, QG:99-213, MSK:62-167) ----
+ * Plain-data description of a LogAbsPhaseANQS in MADE mode.  Weight pointers are DEVICE pointers to the
+ * nn.Linear tensors of log_abs_subnet.layers[l] / phase_subnet.layers[l] (row-major [out][in], already multiplied
+ * by the MADE masks as MLP:230-233 does on every forward); biases may be NULL.  depth = number of hidden layers
+ * (MLPConfig.depth, default 2), all of width `width` (64), tanh activations, identity on the output layer
+ * (MLP:144-148), residual adds on hidden layers 1..depth-1 when use_res (MLP:237-239).
+ * sym[s] = {kind, plus_mask, minus_mask, ordinal_mul, ordinal_add, ordinal_div, base, start_eig} describes
+ * symmetry s of the LocallyDecomposableMasker: kind 0 (additive) eig = start + popcount(prefix & plus) -
+ * popcount(prefix & minus); kind 1 (multiplicative) eig = start * (-1)^popcount(prefix & plus);
+ * memo_idx = sum_s ((eig*mul + add) floordiv div) * base (MSK:67-73).
+ * cont_mask[q * memo_size + memo_idx] has bit d set iff outcome d of qudit q keeps the prefix physical
+ * (QubitGrouping.qudit_idx2cont_mask_mul_table, QG:99-108). */
+typedef struct {
+    int32_t qubit_num, qudit_num, max_qudit_dim, depth, width, use_res, subtract_mean, sym_num;
+    int32_t qudit_starts[65];  /* qudit_starts[qudit_num] == qubit_num */
+    uint8_t du[64];            /* 1: local sampling strategy 'DU' for this qudit = all-ones mask (ANQS:417-418) */
+    int64_t sym[8][8];
+    const double *w_abs[5], *b_abs[5], *w_phase[5], *b_phase[5];
+    const uint64_t *cont_mask;
+    int64_t memo_size;
+} anqs_made_desc_t;
+
+/* AbstractANQS.log_psi (ANQS:407-481) for packed configurations: d_log_psi[i] = (log|psi|, arg psi) as
+ * complex128.  Optional training buffers (NULL to skip): d_save_h[2][depth][n][width] = hidden activations of
+ * the (log-abs, phase) networks, d_save_p[n][qudit_num][max_qudit_dim] = masked conditional probabilities. */
+int anqs_made_log_psi(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, double *d_log_psi,
+                      double *d_save_h, double *d_save_p, void *stream);
+/* LogAbsPhaseANQS.cond_log_abs (LAP:105-163) of qudit `qudit_idx` for n packed prefixes (bits at and above
+ * qudit_starts[qudit_idx] are ignored): d_cond[n][max_qudit_dim], -inf where the continuation is masked. */
+int anqs_made_cond_log_abs(const anqs_made_desc_t *desc, int qudit_idx, const int64_t *d_prefix, int64_t n,
+                           double *d_cond, void *stream);
+
+/* ---- A11  kernel 4: one level of the count-splitting batch sampler (ANQS:593-662) ----------------------
+ * Parents i = 0..n-1 carry a packed prefix, a count (double, exact below 2^53), and a memo index.
+ * split:  d_child_counts[i][D] (D = 2^qubits_in_qudit) = exact multinomial split of d_counts[i] with
+ *         probabilities softmax(2*d_cond[i][:D]) drawn as qubits_in_qudit rounds of binomials on the cumulative
+ *         tree, most significant outcome bit first (ANQS:557-591); d_n_children[i] = number of children that
+ *         are allowed by d_cont_mask_q[memo_idx] and have count > 0 (ANQS:653-660).
+ *         draw_mode 0: every binomial draw is replaced by rint(n*p) (deterministic, used for parity tests);
+ *         draw_mode 1: Philox4x32-10 binomial variates keyed by (seed; parent_offset+i, level, round, node).
+ * emit:   writes the surviving children in (parent, outcome) order at d_offsets[i] (exclusive scan of
+ *         d_n_children): prefix | outcome << qudit_start, count, next memo index (QG:99-108 tables as int32). */
+int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits_in_qudit, const double *d_counts,
+                             const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n,
+                             int level, int draw_mode, uint64_t seed, int64_t parent_offset, double *d_child_counts,
+                             int64_t *d_n_children, void *stream);
+int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit, int qudit_start,
+                               const int64_t *d_prefix, const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q,
+                               const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,
+                               int64_t *d_out_prefix, double *d_out_counts, int32_t *d_out_memo_idx, void *stream);
+
+/* ---- A12  one level of Gumbel top-k (stochastic beam) sampling (ANQS:676-688, 718-731) -----------------
+ * d_out_log_prob[i][D] = d_parent_log_prob[i] + 2*d_cond[i][:D]; d_out_gumbel[i][D] = Gumbel(log_prob)
+ * conditioned on max = d_parent_gumbel[i]; masked children get -inf.  Uniforms come from d_uniforms[i][D]
+ * when given (parity tests), otherwise from Philox4x32-10 keyed like the split kernel. */
+int anqs_sampler_gumbel_level(const double *d_cond, int max_qudit_dim, int qubits_in_qudit,
+                              const double *d_parent_log_prob, const double *d_parent_gumbel, const int32_t *d_memo_idx,
+                              const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n, int level, uint64_t seed,
+                              int64_t parent_offset, const double *d_uniforms, double *d_out_log_prob,
+                              double *d_out_gumbel, void *stream);
 
 #ifdef __cplusplus
 }

@@ -143,7 +143,128 @@ def make_ham():
     _hilbert_case()
 
 
-GROUPS = {'ham': make_ham}
+# ---- wave function, masks, samplers -------------------------------------------------------------------------------
+def made_weights(n, Q, DM, depth=2, width=64, seed=0):
+    """Deterministic (numpy PCG64) network weights shared by the golden generator and the tests, so that fixtures
+    only need to store the seed.  Layout = reference parameter order: per sub-network, per layer, (weight, bias)."""
+    rng = np.random.default_rng(seed)
+    dims = [n] + [width] * depth + [Q * DM]
+    nets = []
+    for _net in range(2):
+        layers = []
+        for l in range(depth + 1):
+            bound = 1.0 / np.sqrt(dims[l])
+            layers.append((rng.uniform(-bound, bound, size=(dims[l + 1], dims[l])), rng.uniform(-bound, bound, size=dims[l + 1])))
+        nets.append(layers)
+    return nets
+
+
+def load_weights_into(wf, nets):
+    sd = {}
+    for name, layers in zip(('log_abs_subnet', 'phase_subnet'), nets):
+        for l, (w, b) in enumerate(layers):
+            sd[f'{name}.layers.{l}.weight'] = torch.from_numpy(w.copy())
+            sd[f'{name}.layers.{l}.bias'] = torch.from_numpy(b.copy())
+    wf.load_state_dict(sd)
+
+
+class _RintBinomial:
+    """Stand-in for torch.distributions.Binomial in the reference run: sample() = rint(n p) (what draw_mode 0 of
+    anqs_sampler_split_level and oracle/anqs_numpy.split_counts_rint compute)."""
+
+    def __init__(self, total_count=None, probs=None):
+        self.n, self.p = total_count.to(torch.float64), probs
+
+    def sample(self):
+        return torch.minimum(self.n, torch.clamp(torch.round(self.n * self.p), min=0.0))
+
+
+def _anqs_case(name, n, n_el, sample_count, stats_num, gumbel_num, seed):
+    tmp = tempfile.mkdtemp(prefix='anqs_golden_')
+    try:
+        o = ref_shim.build_reference_objects(None, n, n_el, tmp)
+        wf, masker, qg = o.wf, o.masker, o.wf.qubit_grouping
+        Q, DM = qg.qudit_num, int(max(qg.qudit_dims))
+        out = dict(qubit_num=n, particle_num=n_el, weight_seed=seed, qudit_num=Q, max_qudit_dim=DM)
+        # initial weights under pt.manual_seed(0) (build_reference_objects seeds before constructing the ansatz)
+        out['init_checksums'] = np.array([[float(p.sum()), float((p * p).sum()), float(p.reshape(-1)[0]), float(p.reshape(-1)[-1])]
+                                          for p in wf.parameters()])
+        out['param_num'] = wf.param_num
+        nets = made_weights(n, Q, DM, seed=seed)
+        load_weights_into(wf, nets)
+        # tables
+        out['memo'] = np.packbits(masker.memo.numpy())
+        out['cont_mask_words'] = np.stack([(qg.qudit_idx2cont_mask_mul_table[q].numpy().astype(np.uint64)
+                                            << np.arange(int(qg.qudit_dims[q]), dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
+                                           for q in range(Q)])
+        out['next_memo_masked_sum'] = np.array([int((qg.qudit_idx2memo_idx_mul_table[q] * qg.qudit_idx2cont_mask_mul_table[q]).sum())
+                                                for q in range(Q)])
+        na = nb = n_el // 2
+        phys = synthetic.random_physical_samples(n, na, nb, sample_count, seed=seed + 1)
+        rng = np.random.default_rng(seed + 2)
+        unphys = rng.integers(0, 2 ** min(n, 62), size=8, dtype=np.int64).astype(np.uint64)
+        samples = np.concatenate((phys, unphys))
+        s_t = _t(samples.view(np.int64)).reshape(-1, 1)
+        base_vec = wf.base_idx2base_vec(s_t)
+        with torch.no_grad():
+            lp = wf.log_psi(base_vec)
+            amp = wf.amplitude(s_t)
+        out.update(samples=samples.view(np.int64), n_phys=phys.shape[0], log_psi=lp.numpy(), amplitude=amp.numpy())
+        # conditional log-amplitudes of two levels for the prefixes of the physical samples
+        for q in sorted({0, Q // 2, Q - 1}):
+            with torch.no_grad():
+                prefix_vec = base_vec[:phys.shape[0], :qg.qudit_starts[q]]
+                rolling = masker.compute_rolling_acc_eigs(prefix_vec)[-1]
+                mask = qg.qudit_idx2cont_mask_mul_table[q][masker.acc_eigs2memo_idx(rolling)]
+                full = torch.zeros((mask.shape[0], DM), dtype=torch.bool)
+                full[:, :mask.shape[1]] = mask
+                out[f'cond_log_abs_q{q}'] = wf.cond_log_abs(qudit_idx=q, base_vec=prefix_vec, mask=full).numpy()
+        # gradient of sum_b Re(conj(c_b) log psi_b) with fixed random complex c, through the reference's autograd
+        c = rng.standard_normal(phys.shape[0]) + 1j * rng.standard_normal(phys.shape[0])
+        wf.zero_grad()
+        lp = wf.log_psi(base_vec[:phys.shape[0]])
+        loss = (torch.conj(_t(c)) * lp).real.sum()
+        loss.backward()
+        grad = wf.cat_grad.numpy()
+        proj = np.random.default_rng(seed + 3).standard_normal((16, grad.shape[0]))
+        out.update(grad_coeff=c, grad_loss=float(loss), grad_proj=proj @ grad, grad_norms=np.array([float(p.grad.norm()) for p in wf.parameters()]),
+                   grad_head=grad[:64].copy(), grad_tail=grad[-64:].copy())
+        # amplitude path: d/dtheta of sum_b Re(conj(c_b) psi_b) (exp on top of log psi, ANQS:483-485)
+        wf.zero_grad()
+        loss2 = (torch.conj(_t(c)) * wf.amplitude(s_t[:phys.shape[0]])).real.sum()
+        loss2.backward()
+        out['grad_amp_proj'] = proj @ wf.cat_grad.numpy()
+        # count-splitting sampler with the binomial draw replaced by its rounded mean
+        real_binomial = torch.distributions.Binomial
+        torch.distributions.Binomial = _RintBinomial
+        try:
+            idx, cnt = wf.sample_stats(stats_num)
+        finally:
+            torch.distributions.Binomial = real_binomial
+        out.update(stats_num=stats_num, stats_idx=idx.numpy().reshape(-1), stats_counts=cnt.numpy().real)
+        # Gumbel top-k with uniforms from a recorded numpy stream
+        urng = np.random.default_rng(seed + 4)
+        real_rand = torch.rand
+        torch.rand = lambda shape, **kw: torch.from_numpy(urng.random(tuple(shape)))
+        try:
+            gidx, gfreq = wf.sample_indices_gumbel(gumbel_num)
+        finally:
+            torch.rand = real_rand
+        out.update(gumbel_num=gumbel_num, gumbel_idx=gidx.numpy().reshape(-1), gumbel_freqs=gfreq.numpy())
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f'{name}.npz'), **out)
+        print(f'{name}: P={wf.param_num} stats_unique={idx.shape[0]} gumbel_unique={gidx.shape[0]}')
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def make_anqs():
+    _anqs_case('anqs_n12', 12, 4, 100, 10 ** 4, 64, seed=0)
+    _anqs_case('anqs_n20', 20, 14, 200, 10 ** 6, 300, seed=1)
+    _anqs_case('anqs_n56', 56, 14, 200, 3000, 200, seed=2)
+    _anqs_case('anqs_n14', 14, 10, 100, 10 ** 5, 500, seed=3)
+
+
+GROUPS = {'ham': make_ham, 'anqs': make_anqs}
 
 
 def main(argv):

@@ -1,0 +1,79 @@
+"""CPU: host-side logic of the wave-function drop-ins (tables, parameter layout, initialisation) against the golden
+vectors from the reference.  No kernels are launched."""
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from anqs_quantum_chemistry_b200 import (HilbertSpace, ParticleNumberSymmetry, SpinHalfProjectionSymmetry, Z2Symmetry,
+                                         LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig)
+
+CASES = ['anqs_n12', 'anqs_n14', 'anqs_n20', 'anqs_n56']
+
+
+def build(n, ne, device='cpu', seed=0):
+    tmp = tempfile.mkdtemp(prefix='anqs_test_')
+    hs = HilbertSpace(qubit_num=n, device=device, parent_dir=tmp, rng_seed=seed)
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=ne),
+                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    torch.manual_seed(seed)
+    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='MADE'))
+    return hs, masker, wf
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_tables_and_init_match_reference(name):
+    g = load_golden(name)
+    n, ne = int(g['qubit_num']), int(g['particle_num'])
+    hs, masker, wf = build(n, ne)
+    memo_ref = np.unpackbits(g['memo'])[:(n + 1) * masker.memo_size].reshape(n + 1, masker.memo_size).astype(bool)
+    assert np.array_equal(masker.memo_host, memo_ref)
+    qg = wf.qubit_grouping
+    assert np.array_equal(qg.cont_mask_words_host, g['cont_mask_words'])
+    for q in range(qg.qudit_num):
+        assert int((qg.next_memo_host[q] * qg.qudit_idx2cont_mask_mul_table[q].numpy()).sum()) == int(g['next_memo_masked_sum'][q])
+    assert wf.param_num == int(g['param_num'])
+    # same construction order + same torch seed => the reference's initial weights
+    sums = np.array([[float(p.sum()), float((p * p).sum()), float(p.reshape(-1)[0]), float(p.reshape(-1)[-1])] for p in wf.parameters()])
+    assert np.allclose(sums, g['init_checksums'], rtol=0, atol=1e-12)
+    names = [k for k, _ in wf.named_parameters()]
+    assert names[:2] == ['log_abs_subnet.layers.0.weight', 'log_abs_subnet.layers.0.bias']
+    assert names[-1] == 'phase_subnet.layers.2.bias'
+
+
+def test_symmetry_descriptors():
+    hs, masker, wf = build(12, 4)
+    d = masker.symmetry_descriptors()
+    assert d[0].tolist() == [0, 4095, 0, 1, 0, 1, 1, 0]
+    assert d[1].tolist() == [0, 0x555, 0xAAA, 1, 6, 1, 13, 0]
+    # memo index of a prefix computed from the descriptors equals the reference formula N + (n+1)(Sz + n//2)
+    x = 0b101101
+    N = bin(x).count('1')
+    sz = bin(x & 0x555).count('1') - bin(x & 0xAAA).count('1')
+    assert int(masker.acc_eigs2memo_idx_np(np.array([[N, sz]]))[0]) == N + 13 * (sz + 6)
+
+
+def test_z2_symmetry_tables():
+    tmp = tempfile.mkdtemp(prefix='anqs_test_')
+    hs = HilbertSpace(qubit_num=8, device='cpu', parent_dir=tmp, rng_seed=0)
+    syms = (ParticleNumberSymmetry(hilbert_space=hs, particle_num=4), SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0),
+            Z2Symmetry(hilbert_space=hs, value=1, pauli_z_positions=[0, 1, 4, 5]))
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=syms)
+    assert masker.memo_size == 9 * 9 * 2
+    # brute force: physical = 4 electrons, Sz = 0, even parity on the Z string
+    vec = (np.arange(256)[:, None] >> np.arange(8)) & 1
+    phys = (vec.sum(1) == 4) & ((vec[:, ::2].sum(1) - vec[:, 1::2].sum(1)) == 0) & ((vec[:, [0, 1, 4, 5]].sum(1) % 2) == 0)
+    got = masker.mask(torch.from_numpy(vec)).numpy()
+    assert np.array_equal(got, phys)
+    d = masker.symmetry_descriptors()
+    assert d[2].tolist() == [1, 0b110011, 0, -1, 1, 2, 81, 1]
+
+
+def test_no_cpu_fallback():
+    hs, masker, wf = build(12, 4)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        wf.amplitude(torch.zeros((4, 1), dtype=torch.int64))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        wf.sample_stats(100)
