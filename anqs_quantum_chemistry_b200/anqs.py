@@ -117,7 +117,7 @@ class _MadeLogPsi(pt.autograd.Function):
 
     @staticmethod
     def forward(ctx, wf, idx, *params):
-        need_grad = any(p.requires_grad for p in params) and pt.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad[2:])  # all False under no_grad (grad mode is always off inside forward)
         log_psi, saved = wf._launch_log_psi(idx, save=need_grad)
         ctx.wf, ctx.saved, ctx.idx = wf, saved, idx
         ctx.weights = [p.detach() for p in params]

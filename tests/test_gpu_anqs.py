@@ -1,0 +1,238 @@
+"""GPU parity: the MADE wave-function kernels (k3) and the sampler kernels (k4), driven through the LogAbsPhaseANQS
+drop-in and the C ABI, against the golden vectors written by the unmodified reference (tests/golden/anqs_*.npz) and
+against the numpy oracle on larger seeded inputs.  Tolerances: 1e-10 on log psi / amplitudes / gradients (fp64);
+sampled configurations and counts bit-exact given identical draws."""
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from anqs_quantum_chemistry_b200 import (HilbertSpace, ParticleNumberSymmetry, SpinHalfProjectionSymmetry,
+                                         LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig, synthetic)
+from oracle import anqs_numpy as onp
+from oracle.make_golden import made_weights
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+CASES = ['anqs_n12', 'anqs_n14', 'anqs_n20', 'anqs_n56']
+
+
+def build(n, ne, nets=None, seed=0):
+    tmp = tempfile.mkdtemp(prefix='anqs_gpu_test_')
+    hs = HilbertSpace(qubit_num=n, device=DEV, parent_dir=tmp, rng_seed=seed)
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=ne),
+                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    torch.manual_seed(seed)
+    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='MADE'))
+    if nets is not None:
+        sd = {}
+        for name, layers in zip(('log_abs_subnet', 'phase_subnet'), nets):
+            for l, (w, b) in enumerate(layers):
+                sd[f'{name}.layers.{l}.weight'] = torch.from_numpy(w.copy())
+                sd[f'{name}.layers.{l}.bias'] = torch.from_numpy(b.copy())
+        wf.load_state_dict(sd)
+    return hs, masker, wf
+
+
+def setup_case(name):
+    g = load_golden(name)
+    n, ne = int(g['qubit_num']), int(g['particle_num'])
+    masks = onp.NumberSpinMasks(n, ne)
+    nets = made_weights(n, masks.Q, masks.DM, seed=int(g['weight_seed']))
+    hs, masker, wf = build(n, ne, nets)
+    return g, masks, nets, wf
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_log_psi_and_amplitude_match_reference(name):
+    g, masks, nets, wf = setup_case(name)
+    s = _dev(g['samples']).view(-1, 1)
+    nphys = int(g['n_phys'])
+    with torch.no_grad():
+        lp = wf.log_psi_of_indices(s).cpu().numpy()
+        amp = wf.amplitude(s).cpu().numpy()
+        lp_vec = wf.log_psi(wf.base_idx2base_vec(s)).cpu().numpy()
+    assert np.abs(lp[:nphys] - g['log_psi'][:nphys]).max() < 1e-10
+    # unphysical configurations: log|psi| = -inf, amplitude exactly 0 (ANQS:399-401)
+    assert np.array_equal(np.isneginf(lp.real), np.isneginf(g['log_psi'].real))
+    assert np.abs(amp - g['amplitude']).max() < 1e-10
+    assert np.array_equal(lp_vec, lp)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_cond_log_abs_matches_reference(name):
+    g, masks, nets, wf = setup_case(name)
+    nphys = int(g['n_phys'])
+    s = _dev(g['samples'][:nphys])
+    for key in [k for k in g if k.startswith('cond_log_abs_q')]:
+        q = int(key.split('q')[-1])
+        c = wf.cond_log_abs(qudit_idx=q, prefix_idx=s).cpu().numpy()   # bits above the prefix are ignored by the kernel
+        ref = g[key]
+        assert np.array_equal(np.isneginf(c), np.isneginf(ref))
+        fin = ~np.isneginf(ref)
+        assert np.abs(c[fin] - ref[fin]).max() < 1e-10
+        # the reference signature (bit-vector prefix) gives the same numbers
+        vec = wf.base_idx2base_vec(s.view(-1, 1))[:, :wf.qudit_starts[q]]
+        c2 = wf.cond_log_abs(qudit_idx=q, base_vec=vec).cpu().numpy()
+        assert np.array_equal(c2, c)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_gradients_match_reference_autograd(name):
+    g, masks, nets, wf = setup_case(name)
+    nphys = int(g['n_phys'])
+    s = _dev(g['samples'][:nphys]).view(-1, 1)
+    c = _dev(g['grad_coeff'])
+    proj = np.random.default_rng(int(g['weight_seed']) + 3).standard_normal((16, wf.param_num))
+    wf.zero_grad()
+    lp = wf.log_psi_of_indices(s)
+    loss = (torch.conj(c) * lp).real.sum()
+    loss.backward()
+    grad = wf.cat_grad.cpu().numpy()
+    assert abs(float(loss) - float(g['grad_loss'])) < 1e-9 * max(1.0, abs(float(g['grad_loss'])))
+    scale = max(1.0, np.abs(g['grad_proj']).max())
+    assert np.abs(proj @ grad - g['grad_proj']).max() < 1e-10 * scale
+    norms = np.array([float(p.grad.norm()) for p in wf.parameters()])
+    assert np.abs(norms - g['grad_norms']).max() < 1e-10 * max(1.0, g['grad_norms'].max())   # includes Q4: grads on masked weights
+    assert np.abs(grad[:64] - g['grad_head']).max() < 1e-10 * scale
+    assert np.abs(grad[-64:] - g['grad_tail']).max() < 1e-10 * scale
+    # amplitude path (exp on top of log psi, ANQS:483-485)
+    wf.zero_grad()
+    loss2 = (torch.conj(c) * wf.amplitude(s)).real.sum()
+    loss2.backward()
+    ga = wf.cat_grad.cpu().numpy()
+    assert np.abs(proj @ ga - g['grad_amp_proj']).max() < 1e-10 * max(1.0, np.abs(g['grad_amp_proj']).max())
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_sample_stats_rint_matches_reference(name):
+    g, masks, nets, wf = setup_case(name)
+    idx, cnt = wf.sample_stats(int(g['stats_num']), draw_mode='rint')
+    assert idx.dtype == torch.int64 and idx.dim() == 2 and cnt.dtype == torch.complex128
+    assert np.array_equal(idx.view(-1).cpu().numpy(), g['stats_idx'])
+    assert np.array_equal(cnt.real.cpu().numpy(), g['stats_counts'])
+    assert float(cnt.real.sum()) == float(g['stats_num'])
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_gumbel_matches_reference(name):
+    g, masks, nets, wf = setup_case(name)
+    urng = np.random.default_rng(int(g['weight_seed']) + 4)
+    idx, freqs = wf.sample_indices_gumbel(int(g['gumbel_num']), uniforms=lambda q, B, D: torch.from_numpy(urng.random((B, D))))
+    assert np.array_equal(idx.view(-1).cpu().numpy(), g['gumbel_idx'])
+    assert np.abs(freqs.cpu().numpy() - g['gumbel_freqs']).max() < 1e-10
+
+
+@pytest.mark.parametrize('n,ne', [(12, 4), (14, 10)])
+def test_normalisation_over_physical_sector(n, ne):
+    """sum over the (N, S_z) sector of |psi|^2 is 1; everything outside has amplitude 0."""
+    hs, masker, wf = build(n, ne)
+    allx = torch.arange(2 ** n, dtype=torch.int64, device=DEV).view(-1, 1)
+    with torch.no_grad():
+        amp = wf.amplitude(allx)
+    p = (amp.abs() ** 2).cpu().numpy()
+    x = np.arange(2 ** n, dtype=np.uint64)
+    ev = np.array([bin(int(v) & 0x5555555555555555).count('1') for v in x])
+    od = np.array([bin(int(v) & 0xAAAAAAAAAAAAAAAA).count('1') for v in x])
+    phys = (ev == ne // 2) & (od == ne // 2)
+    assert abs(p[phys].sum() - 1.0) < 1e-12
+    assert p[~phys].max() == 0.0
+
+
+@pytest.mark.parametrize('name', ['anqs_n20', 'anqs_n56'])
+def test_log_psi_matches_oracle_on_large_batch(name):
+    g, masks, nets, wf = setup_case(name)
+    n, ne = masks.n, masks.particle_num
+    x = synthetic.random_physical_samples(n, ne // 2, ne // 2, 5000 if n == 20 else 20011, seed=11)
+    Wa, ba, Wp, bp = onp.masked_weights(nets, masks)
+    ref = onp.log_psi(x, masks, Wa, ba, Wp, bp)
+    with torch.no_grad():
+        lp = wf.log_psi_of_indices(_dev(x.view(np.int64))).cpu().numpy()
+    assert np.abs(lp - ref).max() < 1e-10
+
+
+def test_sample_stats_philox_properties():
+    """Count conservation, physicality, reproducibility, distribution."""
+    hs, masker, wf = build(20, 14)
+    N = 10 ** 7
+    idx, cnt = wf.sample_stats(N, seed=123)
+    idx2, cnt2 = wf.sample_stats(N, seed=123)
+    assert torch.equal(idx, idx2) and torch.equal(cnt, cnt2)
+    idx3, cnt3 = wf.sample_stats(N, seed=124)
+    assert not (idx3.shape == idx.shape and torch.equal(cnt3, cnt))
+    c = cnt.real
+    assert float(c.sum()) == float(N) and float(c.min()) >= 1.0 and torch.equal(c, c.round())
+    x = idx.view(-1)
+    assert torch.equal(x.unique(), x.sort().values)                       # unique configurations
+    ev = hs.popcount(x & 0x5555555555555555)
+    od = hs.popcount(x & ~0x5555555555555555)
+    assert bool((ev == 7).all()) and bool((od == 7).all())
+    # empirical frequencies follow |psi|^2: chi-square per degree of freedom close to 1
+    with torch.no_grad():
+        p = wf.amplitude(idx).abs() ** 2
+    expect = p * N
+    big = expect > 20
+    chi2 = float((((c - expect) ** 2) / expect)[big].sum() / big.sum())
+    assert 0.8 < chi2 < 1.2, chi2
+
+
+def test_sample_stats_philox_small_counts():
+    """Inversion branch of the binomial generator (n p < 10) and the 56-qubit tree (10 levels)."""
+    hs, masker, wf = build(56, 14)
+    idx, cnt = wf.sample_stats(5000, seed=7)
+    c = cnt.real
+    assert float(c.sum()) == 5000.0 and float(c.min()) >= 1.0
+    x = idx.view(-1)
+    assert bool((hs.popcount(x & 0x5555555555555555) == 7).all()) and bool((hs.popcount(x & ~0x5555555555555555) == 7).all())
+    assert x.unique().shape[0] == x.shape[0]
+
+
+def test_gumbel_philox_properties():
+    hs, masker, wf = build(20, 14)
+    idx, freqs = wf.sample_indices_gumbel(2000, seed=5)
+    x = idx.view(-1)
+    assert x.shape[0] == 2000 and x.unique().shape[0] == 2000
+    assert bool((hs.popcount(x & 0x5555555555555555) == 7).all()) and bool((hs.popcount(x & ~0x5555555555555555) == 7).all())
+    assert abs(float(freqs.sum()) - 1.0) < 1e-12
+    with torch.no_grad():
+        p = wf.amplitude(idx).abs() ** 2
+    assert torch.allclose(freqs, p / p.sum(), rtol=0, atol=1e-12)
+    idx2, _ = wf.sample_indices_gumbel(2000, seed=5)
+    assert torch.equal(idx, idx2)
+
+
+def test_cat_log_jac_matches_finite_differences():
+    hs, masker, wf = build(12, 4)
+    x = _dev(synthetic.random_physical_samples(12, 2, 2, 6, seed=3).view(np.int64)).view(-1, 1)
+    jac = wf.compute_cat_log_jac(x)
+    assert tuple(jac.shape) == (6, wf.param_num) and jac.dtype == torch.complex128
+    params = list(wf.parameters())
+    # central differences on a few unmasked first-layer biases and last-layer weights
+    for p, flat_off in ((params[1], sum(q.numel() for q in params[:1])), (params[5], sum(q.numel() for q in params[:5]))):
+        for j in (0, p.numel() - 1):
+            eps = 1e-6
+            with torch.no_grad():
+                old = p.view(-1)[j].item()
+                p.view(-1)[j] = old + eps
+                lp_p = wf.log_psi_of_indices(x)
+                p.view(-1)[j] = old - eps
+                lp_m = wf.log_psi_of_indices(x)
+                p.view(-1)[j] = old
+            fd = torch.conj((lp_p - lp_m) / (2 * eps))
+            assert torch.allclose(jac[:, flat_off + j], fd, rtol=0, atol=1e-7)
+
+
+def test_empty_and_ragged_batches():
+    hs, masker, wf = build(12, 4)
+    with torch.no_grad():
+        assert wf.amplitude(torch.zeros((0, 1), dtype=torch.int64, device=DEV)).shape[0] == 0
+        x = _dev(synthetic.random_physical_samples(12, 2, 2, 65, seed=4).view(np.int64)).view(-1, 1)
+        a65 = wf.amplitude(x)
+        a1 = torch.cat([wf.amplitude(x[i:i + 1]) for i in range(65)])
+    assert torch.equal(a65, a1)   # tile boundaries (64 samples per tile) do not change results
