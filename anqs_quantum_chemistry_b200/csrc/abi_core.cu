@@ -122,6 +122,108 @@ __global__ void scan_apply(const int64_t *__restrict__ in, int64_t n, const int6
     }
 }
 
+
+// ---- product layout of the XY masks (Tables::prod_*, consumed by k1_fused.cu) --------------------------------
+constexpr uint32_t PROD_TILE_MAX = 200 * 1024;  // bytes of shared memory one tile may take
+constexpr uint32_t PROD_ROW_CHUNK = 2048;       // longer rows are split so that tiles pack evenly
+constexpr uint32_t PROD_SINGLE_MAX = 2;         // rows with <= this many members become singleton records
+
+struct HostProd {
+    std::vector<ProdTile> tiles;
+    std::vector<uint8_t> blob;
+    std::vector<uint32_t> row_u, mem_u;
+    uint32_t tile_bytes_max = 0;
+};
+
+static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostProd &out) {
+    // masks sorted by (alpha part, spread bits of the member hash, beta part)
+    struct M { uint32_t pa, mb, hash, u; };
+    std::vector<M> ms((size_t)U);
+    for (int64_t u = 0; u < U; ++u) {
+        uint32_t pa = mab[u].x, mb = mab[u].y;
+        ms[u] = {pa, mb, (lin_host(LIN_POSA, pa) & 0x3FFu) ^ (lin_host(LIN_POSB, mb) & 0xFFFFu), (uint32_t)u};
+    }
+    std::sort(ms.begin(), ms.end(), [](const M &x, const M &y) {
+        if (x.pa != y.pa) return x.pa < y.pa;
+        uint32_t sx = x.hash >> 10, sy = y.hash >> 10;
+        if (sx != sy) return sx < sy;
+        return x.mb < y.mb;
+    });
+    // row chunks: [begin, end) ranges of ms with one alpha part and at most PROD_ROW_CHUNK members
+    struct Chunk { size_t begin, end; };
+    std::vector<Chunk> multi, single;
+    for (size_t i = 0; i < ms.size();) {
+        size_t j = i;
+        while (j < ms.size() && ms[j].pa == ms[i].pa) ++j;
+        if (j - i <= PROD_SINGLE_MAX) {
+            for (size_t k = i; k < j; ++k) single.push_back({k, k + 1});
+        } else {
+            for (size_t k = i; k < j; k += PROD_ROW_CHUNK) multi.push_back({k, std::min(j, k + (size_t)PROD_ROW_CHUNK)});
+        }
+        i = j;
+    }
+    auto chunk_bytes = [](const Chunk &c, bool is_multi) -> size_t {
+        return sizeof(RowRec) + (is_multi ? (c.end - c.begin) * sizeof(MemRec) : 0);
+    };
+    size_t total = 0;
+    for (auto &c : multi) total += chunk_bytes(c, true);
+    for (auto &c : single) total += chunk_bytes(c, false);
+    const size_t n_tiles = std::max<size_t>(1, (total + PROD_TILE_MAX - 1) / PROD_TILE_MAX);
+    const size_t target = (total + n_tiles - 1) / n_tiles;
+    // greedy packing in order (multi rows first, then singletons); a tile closes once it reaches the target
+    size_t im = 0, is = 0;
+    uint32_t row_base = 0, member_base = 0;
+    while (im < multi.size() || is < single.size()) {
+        std::vector<Chunk> tm, ts;
+        size_t bytes = 0;
+        while (im < multi.size() && bytes < target && bytes + chunk_bytes(multi[im], true) <= PROD_TILE_MAX) {
+            bytes += chunk_bytes(multi[im], true);
+            tm.push_back(multi[im++]);
+        }
+        if (im == multi.size()) {
+            while (is < single.size() && bytes + sizeof(RowRec) <= PROD_TILE_MAX && bytes < target) {
+                bytes += sizeof(RowRec);
+                ts.push_back(single[is++]);
+            }
+        }
+        ProdTile tile{};
+        tile.n_multi = (uint32_t)tm.size();
+        tile.n_single = (uint32_t)ts.size();
+        tile.row_base = row_base;
+        tile.member_base = member_base;
+        std::vector<RowRec> rows;
+        std::vector<MemRec> mems;
+        for (auto &c : tm) {
+            const uint32_t pa = ms[c.begin].pa;
+            rows.push_back({pa, lin_host(LIN_LINE, pa), (uint32_t)mems.size(), (uint32_t)(c.end - c.begin)});
+            out.row_u.push_back(0);
+            for (size_t k = c.begin; k < c.end; ++k) {
+                mems.push_back({ms[k].mb, ms[k].hash});
+                out.mem_u.push_back(ms[k].u);
+            }
+        }
+        for (auto &c : ts) {
+            const M &m = ms[c.begin];
+            rows.push_back({m.pa, lin_host(LIN_LINE, m.pa), m.mb, m.hash});
+            out.row_u.push_back(m.u);
+        }
+        tile.n_members = (uint32_t)mems.size();
+        size_t off = (out.blob.size() + 127) / 128 * 128;
+        size_t nbytes = rows.size() * sizeof(RowRec) + mems.size() * sizeof(MemRec);
+        nbytes = (nbytes + 15) / 16 * 16;
+        out.blob.resize(off + nbytes, 0);
+        std::memcpy(out.blob.data() + off, rows.data(), rows.size() * sizeof(RowRec));
+        std::memcpy(out.blob.data() + off + rows.size() * sizeof(RowRec), mems.data(), mems.size() * sizeof(MemRec));
+        tile.blob_off = (uint32_t)off;
+        tile.blob_bytes = (uint32_t)nbytes;
+        out.tile_bytes_max = std::max(out.tile_bytes_max, tile.blob_bytes);
+        out.tiles.push_back(tile);
+        row_base += (uint32_t)rows.size();
+        member_base += (uint32_t)mems.size();
+    }
+    if (out.mem_u.empty()) out.mem_u.push_back(0);
+}
+
 }  // namespace anqs
 
 using namespace anqs;
@@ -250,6 +352,14 @@ int anqs_tables_create(anqs_tables_t **out, int qubit_num, int64_t U, int64_t T,
     if (e == cudaSuccess) e = up((void **)&t->w_re, wre.data(), (size_t)T * sizeof(double));
     if (e == cudaSuccess && !real) e = up((void **)&t->w_im, wim.data(), (size_t)T * sizeof(double));
     if (e == cudaSuccess && real) e = up((void **)&t->term_real, rec.data(), (size_t)T * sizeof(ulonglong2));
+    HostProd prod;
+    build_product_layout(mab, U, prod);
+    t->n_tiles = (int)prod.tiles.size();
+    t->tile_bytes_max = (int)prod.tile_bytes_max;
+    if (e == cudaSuccess) e = up((void **)&t->prod_tiles, prod.tiles.data(), prod.tiles.size() * sizeof(ProdTile));
+    if (e == cudaSuccess) e = up((void **)&t->prod_blob, prod.blob.data(), prod.blob.size());
+    if (e == cudaSuccess) e = up((void **)&t->prod_row_u, prod.row_u.data(), prod.row_u.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = up((void **)&t->prod_mem_u, prod.mem_u.data(), prod.mem_u.size() * sizeof(uint32_t));
     if (e != cudaSuccess) {
         anqs_tables_destroy((anqs_tables_t *)t);
         set_error(std::string("anqs_tables_create: device upload failed: ") + cudaGetErrorString(e));
@@ -269,6 +379,10 @@ int anqs_tables_destroy(anqs_tables_t *h) {
     cudaFree(t->w_re);
     cudaFree(t->w_im);
     cudaFree(t->term_real);
+    cudaFree(t->prod_tiles);
+    cudaFree(t->prod_blob);
+    cudaFree(t->prod_row_u);
+    cudaFree(t->prod_mem_u);
     delete t;
     return 0;
 }

@@ -32,6 +32,26 @@ int sm_count_of_current_device();
 
 #define ANQS_LAUNCH_CHECK() ANQS_CUDA(cudaGetLastError())
 
+// Product-layout records (see Tables below)
+struct ProdTile {
+    uint32_t blob_off;     // byte offset of the tile in prod_blob (multiple of 128)
+    uint32_t blob_bytes;   // multiple of 16
+    uint32_t n_multi, n_single, n_members;
+    uint32_t row_base;     // global index of the tile's first row (into prod_row_u)
+    uint32_t member_base;  // global index of the tile's first member (into prod_mem_u)
+    uint32_t pad;
+};
+struct RowRec {            // 16 bytes
+    uint32_t pa;           // alpha part of the masks of this row
+    uint32_t hline;        // lin(LIN_LINE, pa)
+    uint32_t a;            // multi: first member (tile-local index) | singleton: beta part mb
+    uint32_t b;            // multi: member count                   | singleton: member hash
+};
+struct MemRec {            // 8 bytes
+    uint32_t mb;           // beta part
+    uint32_t hash;         // lin(LIN_POSA, pa) ^ lin(LIN_POSB, mb)
+};
+
 // Device-resident Hamiltonian tables (reference tensors PO:103-115, re-laid-out for the kernels).
 struct Tables {
     int qubit_num;
@@ -48,31 +68,59 @@ struct Tables {
     double *w_re;            // [T]
     double *w_im;            // [T] (NULL when weights_real)
     ulonglong2 *term_real;   // [T] packed {yz_d, bits(w_re)} records for one 16-byte load (weights_real only)
+
+    // ---- product layout (k1_fused.cu): masks factorised into (alpha part, beta part) ---------------------
+    // A "row" is one distinct alpha part pa together with the beta parts that occur with it.  The electron-count
+    // filter factorises, popc(xa ^ pa) == N_alpha and popc(xb ^ mb) == N_beta, so a row whose alpha part fails
+    // is skipped as a whole.  Rows are packed into tiles (one bulk copy each):
+    //   [RowRec x (n_multi + n_single)] [MemRec x n_members]
+    // multi rows list their members in the tile's MemRec array; rows with <= 2 members are expanded to
+    // "singleton" records that carry their one member inline.
+    int n_tiles;
+    int tile_bytes_max;
+    ProdTile *prod_tiles;     // [n_tiles] directory (device)
+    uint8_t *prod_blob;       // tile blobs, each 128-byte aligned (device)
+    uint32_t *prod_row_u;     // [total rows]    mask index u of a singleton row (device)
+    uint32_t *prod_mem_u;     // [total members] mask index u of a member (device)
 };
 
 // ---- sampled-set lookup table (kernel family 2) ------------------------------------------------------
-// Memory layout of the caller-allocated buffer: (capacity + 1) slots of 32 bytes, then capacity bytes of
-// blocked-Bloom presence bits (capacity / 4 words of 32 bits; every key sets 3 bits of ONE word).  Keys are
-// stored DE-INTERLEAVED so that the fused kernel can form the probe key (xa ^ ma, xb ^ mb) without touching
-// the 64-bit masks.
+// Memory layout of the caller-allocated buffer (128-byte aligned):
+//   [capacity slots of 32 bytes][dedicated slot for the all-ones key, 32 bytes][header, 96 bytes][filter]
+// The filter is a line-blocked presence filter of 2*capacity bytes (32..64 bits per key, ONE bit set per key):
+// the 128-byte line is chosen by the ALPHA half of the key (lin LIN_LINE), optionally spread over 2^G lines by
+// G hash bits of the beta half, and the bit inside the line by both halves (LIN_POSA ^ LIN_POSB).  All the hashes
+// are GF(2)-linear, so the fused kernel gets the filter address of x' = x ^ mask with one XOR per candidate, and
+// every candidate that shares the sample and the alpha part of the mask (a whole row of the product layout) tests a
+// bit of the SAME line: one L1 wavefront per warp step instead of one per candidate.  G is chosen at build time
+// from the occupancy of the lines (k2_hash.cu) and stored in the header.  Keys are stored DE-INTERLEAVED.
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;  // de-interleaving maps all-ones to all-ones
+constexpr int FILTER_MAX_SPREAD_BITS = 6;
 struct __align__(32) HashSlot {
     uint64_t key;    // de-interleaved configuration
     long long idx;   // position in the key array (-1 = empty)
     double re, im;   // amplitude psi(key)
 };
+struct FilterHeader {  // lives in the 96 bytes behind the dedicated slot
+    uint32_t spread_bits;   // G
+    uint32_t gmask;         // (1 << G) - 1
+    uint32_t overloaded[FILTER_MAX_SPREAD_BITS + 1];  // keys in lines holding more than 128 << g keys, per candidate g
+    uint32_t n_keys;
+};
 struct HashView {
     const HashSlot *slots;
-    const uint32_t *bloom;
-    uint32_t capmask;    // capacity - 1
-    uint32_t wordmask;   // number of Bloom words - 1
+    const FilterHeader *header;
+    const uint8_t *filter;   // nlines * 128 bytes
+    uint32_t capmask;        // capacity - 1
+    uint32_t linemask;       // nlines - 1, nlines = capacity / 64
 };
 inline HashView make_hash_view(const void *d_table, int64_t capacity) {
     HashView hv;
     hv.slots = (const HashSlot *)d_table;
-    hv.bloom = (const uint32_t *)(hv.slots + capacity + 1);
+    hv.header = (const FilterHeader *)(hv.slots + capacity + 1);
+    hv.filter = (const uint8_t *)(hv.slots + capacity) + 128;
     hv.capmask = (uint32_t)(capacity - 1);
-    hv.wordmask = (uint32_t)(capacity / 4 - 1);
+    hv.linemask = (uint32_t)(capacity / 64 - 1);
     return hv;
 }
 
@@ -108,18 +156,35 @@ __host__ __device__ __forceinline__ uint32_t hash_key(uint32_t a, uint32_t b) {
     h ^= h >> 16;
     return h;
 }
-// blocked Bloom filter: word index and 3-bit pattern, both decorrelated from the slot index (= low hash bits)
-__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t h) {
-    h ^= h >> 15;
-    h *= 0x2c1b3c6du;
-    h ^= h >> 12;
-    h *= 0x297a2d39u;
-    h ^= h >> 15;
+// ---- GF(2)-linear hashes of the two halves of a de-interleaved configuration ------------------------------
+// lin(f, v) = XOR of LIN_C[f][i] over the set bits i of v, so lin(f, x ^ m) = lin(f, x) ^ lin(f, m): the hash of a
+// connected configuration x' = x ^ mask is the hash of the sample XOR a per-mask constant precomputed at table
+// build time.  Columns are fixed random constants (full-rank matrices), identical on host and device.
+#define ANQS_LIN_TABLE                                                                                                    \
+    {                                                                                                                     \
+        /* LIN_LINE: alpha half -> 32-bit line hash */                                                                    \
+        {0xb2285d19u, 0xc35cafefu, 0xb18c34eeu, 0x2c91baccu, 0x2ede2defu, 0x06f094b1u, 0xe5fb86d2u, 0xd176b960u,          \
+         0x810729c9u, 0x22bb38deu, 0xfa9dbac4u, 0x11ab6a6du, 0x81d0ff89u, 0x1e7b2ca5u, 0x92eea3a6u, 0x24949e26u,          \
+         0x90f3f271u, 0x68f545b0u, 0x2e32da50u, 0xd9779982u, 0x0712e2ccu, 0x7ca6fa6eu, 0x09e2c4a5u, 0xd73e2794u,          \
+         0x61f91774u, 0x3f9b14f2u, 0x9dd55901u, 0x05ad50e5u, 0x9400cb1cu, 0xb4e13945u, 0x3424af98u, 0x0d95e497u},         \
+        /* LIN_POSA: alpha half -> 10 position bits */                                                                    \
+        {0x000002b0u, 0x0000028cu, 0x00000297u, 0x00000256u, 0x000001d5u, 0x000000f4u, 0x0000034eu, 0x0000007fu,          \
+         0x000003a6u, 0x0000024eu, 0x0000026cu, 0x000001a3u, 0x0000037eu, 0x000003cau, 0x00000349u, 0x000001f3u,          \
+         0x0000015cu, 0x00000251u, 0x00000219u, 0x00000190u, 0x000003e0u, 0x000001c6u, 0x00000112u, 0x00000350u,          \
+         0x0000021eu, 0x0000000cu, 0x000000beu, 0x0000025fu, 0x000001f4u, 0x000002e9u, 0x000000fcu, 0x000000a9u},         \
+        /* LIN_POSB: beta half -> 10 position bits | 6 spread bits << 10 */                                               \
+        {0x0000b105u, 0x000025ecu, 0x0000ab22u, 0x0000f7f8u, 0x00009e12u, 0x00008e3fu, 0x00005d46u, 0x00004ad5u,          \
+         0x00002ed1u, 0x0000dca6u, 0x000087b8u, 0x0000a571u, 0x0000135cu, 0x0000c5cau, 0x0000ea64u, 0x000027bdu,          \
+         0x00000f7bu, 0x0000d998u, 0x00001e3fu, 0x00001a9au, 0x000045e8u, 0x0000a9b5u, 0x0000e677u, 0x000021c0u,          \
+         0x00001bdeu, 0x0000bf2au, 0x0000231fu, 0x000093dcu, 0x0000262fu, 0x000009d9u, 0x00009f5eu, 0x0000ea50u}          \
+    }
+constexpr int LIN_LINE = 0, LIN_POSA = 1, LIN_POSB = 2;
+static const uint32_t LIN_C_HOST[3][32] = ANQS_LIN_TABLE;
+inline uint32_t lin_host(int f, uint32_t v) {
+    uint32_t h = 0;
+    for (int i = 0; i < 32; ++i)
+        if ((v >> i) & 1u) h ^= LIN_C_HOST[f][i];
     return h;
-}
-__host__ __device__ __forceinline__ uint32_t bloom_pattern(uint32_t h) {
-    uint32_t g = h * 0x9E3779B1u;
-    return (1u << (g >> 27)) | (1u << ((g >> 22) & 31u)) | (1u << ((g >> 17) & 31u));
 }
 
 #ifdef __CUDACC__
@@ -196,6 +261,24 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+static __device__ const uint32_t LIN_C_DEV[3][32] = ANQS_LIN_TABLE;
+// per-thread evaluation (a few set bits per key: configurations have N_alpha / N_beta electrons per half)
+__device__ __forceinline__ uint32_t lin_dev(int f, uint32_t v) {
+    uint32_t h = 0;
+    while (v) {
+        int i = __ffs(v) - 1;
+        v &= v - 1;
+        h ^= __ldg(&LIN_C_DEV[f][i]);
+    }
+    return h;
+}
+// warp-cooperative evaluation: lane i contributes column i, one REDUX per hash; every lane gets the result
+__device__ __forceinline__ uint32_t lin_warp(int f, uint32_t v) {
+    const int lane = threadIdx.x & 31;
+    uint32_t c = ((v >> lane) & 1u) ? __ldg(&LIN_C_DEV[f][lane]) : 0u;
+    return __reduce_xor_sync(0xffffffffu, c);
+}
 #endif
+
 
 }  // namespace anqs

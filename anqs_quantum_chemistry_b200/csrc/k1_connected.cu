@@ -4,7 +4,7 @@
 //                      (reference PO:527-567), result = per-sample count + ballot bitmap
 //   k1_emit_kernel     bitmap -> ordered list (dest, x', xy_ptr, H_{x,x'})   (PO:527-567 + PO:256-324)
 //   matrix_elements    H_{x,x'} for an arbitrary (x', xy_ptr) list              (PO:256-324)
-//   fused_eloc_kernel  filter + hash probe + matrix element + accumulate        (PO:396-487, 'ham')
+//   (the fused sample-aware local-energy kernel lives in k1_fused.cu)
 //   accumulate_rows    E[dest] += H * psi(src) over a CSR list                  (PO:453-478)
 //
 // Data layout: the XY masks are de-interleaved once at table-build time into (even bits, odd bits) =
@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "matrix_elements.cuh"
 
 namespace anqs {
 
@@ -24,7 +25,6 @@ constexpr int K1_THREADS = 512;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int TILE_STREAM = 8192;         // masks per streamed tile (64 KB)
 constexpr int TILE_RESIDENT_MAX = 24576;  // masks kept resident (192 KB); multiple of 1024
-constexpr int BIG_GROUP = 48;             // YZ groups longer than this are summed by the whole warp
 
 // ---- mask-table staging ------------------------------------------------------------------------
 struct TileStager {
@@ -67,77 +67,6 @@ struct TileStager {
         return buf + (size_t)b * tile_masks;
     }
 };
-
-// ---- H_{x,x'} = sum_t w_t (-1)^{popcount(x' & yz_t)} over one YZ group, per lane ------------------
-// xp and the YZ masks are both DE-INTERLEAVED (a bit permutation, so the parity is unchanged).
-template <bool REAL>
-__device__ __forceinline__ void group_sum_lane(const Tables &t, int start, int num, uint64_t xp, double &hr,
-                                               double &hi) {
-    hr = 0.0;
-    hi = 0.0;
-    if (REAL) {
-        const ulonglong2 *rec = t.term_real + start;
-#pragma unroll 4
-        for (int k = 0; k < num; ++k) {
-            ulonglong2 r = __ldg(rec + k);
-            hr += flip_sign(__longlong_as_double((long long)r.y), parity64(xp & r.x));
-        }
-    } else {
-        for (int k = start; k < start + num; ++k) {
-            uint32_t par = parity64(xp & __ldg(t.yz_d + k));
-            hr += flip_sign(__ldg(t.w_re + k), par);
-            hi += flip_sign(__ldg(t.w_im + k), par);
-        }
-    }
-}
-
-// whole warp sums one group; every lane returns the total
-template <bool REAL>
-__device__ __forceinline__ void group_sum_warp(const Tables &t, int start, int num, uint64_t xp, double &hr,
-                                               double &hi) {
-    double sr = 0.0, si = 0.0;
-    for (int k = start + lane_id(); k < start + num; k += 32) {
-        if (REAL) {
-            ulonglong2 r = __ldg(t.term_real + k);
-            sr += flip_sign(__longlong_as_double((long long)r.y), parity64(xp & r.x));
-        } else {
-            uint32_t par = parity64(xp & __ldg(t.yz_d + k));
-            sr += flip_sign(__ldg(t.w_re + k), par);
-            si += flip_sign(__ldg(t.w_im + k), par);
-        }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        sr += __shfl_xor_sync(0xffffffffu, sr, d);
-        if (!REAL) si += __shfl_xor_sync(0xffffffffu, si, d);
-    }
-    hr = sr;
-    hi = si;
-}
-
-// Matrix elements for up to 32 (group, x') pairs held one per lane.  Must be called by the whole warp.
-template <bool REAL>
-__device__ __forceinline__ void warp_matrix_elements(const Tables &t, bool active, int2 g, uint64_t xp, double &hr,
-                                                     double &hi) {
-    hr = 0.0;
-    hi = 0.0;
-    bool big = active && g.y > BIG_GROUP;
-    if (active && !big) group_sum_lane<REAL>(t, g.x, g.y, xp, hr, hi);
-    unsigned bigmask = __ballot_sync(0xffffffffu, big);
-    while (bigmask) {
-        int src = __ffs(bigmask) - 1;
-        bigmask &= bigmask - 1;
-        int gx = __shfl_sync(0xffffffffu, g.x, src);
-        int gy = __shfl_sync(0xffffffffu, g.y, src);
-        uint64_t xs = __shfl_sync(0xffffffffu, xp, src);
-        double sr, si;
-        group_sum_warp<REAL>(t, gx, gy, xs, sr, si);
-        if (lane_id() == src) {
-            hr = sr;
-            hi = si;
-        }
-    }
-}
 
 // ---- kernel 1a: filter ---------------------------------------------------------------------------
 template <int SPW, bool CHECK>
@@ -323,214 +252,6 @@ matrix_elements_kernel(Tables t, const int64_t *__restrict__ xprime, const int64
     }
 }
 
-// ---- fused sample-aware local energy -------------------------------------------------------------------
-// Per warp and sample: filter (32 masks per step, from shared memory) -> queue 1 (mask indices that pass the
-// electron-count filter) -> every 128 entries: 4 independent Bloom-word loads per lane -> queue 2 (Bloom
-// positives, ~1 % of the misses + every hit) -> every 32 entries: slot probe -> hits: matrix element and
-// accumulate.  The two queues turn the dependent-load chain of a plain probe into batches of independent
-// loads; both are a few hundred bytes of shared memory per warp.
-constexpr int FUSED_SPW = 2;
-constexpr int Q1_BATCH = 128, Q1_CAP = Q1_BATCH + 32, Q2_CAP = 64;
-constexpr int FUSED_QUEUE_BYTES = K1_WARPS * FUSED_SPW * (Q1_CAP + Q2_CAP) * 4;
-
-struct FusedCtx {
-    Tables t;
-    HashView hv;
-    const uint2 *mab;  // de-interleaved masks: the resident shared-memory copy, or global memory when streaming
-};
-
-template <bool REAL>
-__device__ __forceinline__ void fused_probe(const FusedCtx &c, uint32_t xa, uint32_t xb, bool active, uint32_t u,
-                                            double &er, double &ei) {
-    uint64_t key = 0;
-    long long j = -1;
-    double ar = 0.0, ai = 0.0;
-    int2 g = make_int2(0, 0);
-    if (active) {
-        uint2 m = c.mab[u];
-        key = (uint64_t)(xa ^ m.x) | ((uint64_t)(xb ^ m.y) << 32);
-        j = hash_lookup(c.hv, key, ar, ai);
-        if (j >= 0) g = __ldg(c.t.grp + u);
-    }
-    bool hit = active && j >= 0;
-    if (__any_sync(0xffffffffu, hit)) {
-        double hr, hi;
-        warp_matrix_elements<REAL>(c.t, hit, g, key, hr, hi);
-        if (hit) {
-            if (REAL) {
-                er += hr * ar;
-                ei += hr * ai;
-            } else {
-                er += hr * ar - hi * ai;
-                ei += hr * ai + hi * ar;
-            }
-        }
-    }
-}
-
-// Bloom-tests the first `count` (<= 128) entries of q1; positives go through q2 to fused_probe.
-template <bool REAL>
-__device__ __forceinline__ void fused_bloom_drain(const FusedCtx &c, uint32_t xa, uint32_t xb, const uint32_t *q1,
-                                                  int count, uint32_t *q2, int &qlen2, double &er, double &ei) {
-    const int lane = lane_id();
-    const uint32_t lt = lanemask_lt();
-    constexpr int R = Q1_BATCH / 32;
-    uint32_t u[R], word[R], pat[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        int i = r * 32 + lane;
-        bool act = i < count;
-        u[r] = act ? q1[i] : 0u;
-        uint2 m = c.mab[u[r]];
-        uint32_t a = xa ^ m.x, b = xb ^ m.y;
-        uint32_t h = hash_key(a, b);
-        pat[r] = bloom_pattern(h);
-        word[r] = act ? __ldg(c.hv.bloom + (bloom_word(h) & c.hv.wordmask)) : 0u;
-        if ((a & b) == 0xFFFFFFFFu) word[r] = act ? 0xFFFFFFFFu : 0u;  // all-ones key: dedicated slot, no Bloom bits
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        bool pos = (word[r] & pat[r]) == pat[r];  // inactive lanes have word == 0 and pat != 0
-        unsigned b = __ballot_sync(0xffffffffu, pos);
-        if (b) {
-            if (pos) q2[qlen2 + __popc(b & lt)] = u[r];
-            qlen2 += __popc(b);
-            __syncwarp();
-            if (qlen2 >= 32) {
-                uint32_t uu = q2[lane];
-                int rem = qlen2 - 32;
-                uint32_t v = lane < rem ? q2[32 + lane] : 0u;
-                __syncwarp();
-                if (lane < rem) q2[lane] = v;
-                __syncwarp();
-                qlen2 = rem;
-                fused_probe<REAL>(c, xa, xb, true, uu, er, ei);
-            }
-        }
-    }
-}
-
-template <int SPW, bool REAL, bool CHECK>
-__device__ __forceinline__ void fused_steps(const FusedCtx &c, const uint2 *tile, int it_begin, int it_end,
-                                            int64_t base_idx, const uint32_t (&xa)[SPW], const uint32_t (&xb)[SPW],
-                                            const int (&alpha)[SPW], int beta, uint32_t *q1, uint32_t *q2,
-                                            int (&qlen1)[SPW], int (&qlen2)[SPW], double (&er)[SPW], double (&ei)[SPW]) {
-    const int lane = lane_id();
-    const uint32_t lt = lanemask_lt();
-    for (int it = it_begin; it < it_end; ++it) {
-        int i = it * 32 + lane;
-        uint2 m = tile[i];
-        bool valid = CHECK ? (base_idx + i < c.t.U) : true;
-#pragma unroll
-        for (int k = 0; k < SPW; ++k) {
-            bool p = valid && (__popc(xa[k] ^ m.x) == alpha[k]) && (__popc(xb[k] ^ m.y) == beta);
-            unsigned b = __ballot_sync(0xffffffffu, p);
-            if (b) {
-                uint32_t *q = q1 + k * Q1_CAP;
-                if (p) q[qlen1[k] + __popc(b & lt)] = (uint32_t)(base_idx + i);
-                qlen1[k] += __popc(b);
-                if (qlen1[k] >= Q1_BATCH) {
-                    __syncwarp();
-                    fused_bloom_drain<REAL>(c, xa[k], xb[k], q, Q1_BATCH, q2 + k * Q2_CAP, qlen2[k], er[k], ei[k]);
-                    int rem = qlen1[k] - Q1_BATCH;
-                    uint32_t v = lane < rem ? q[Q1_BATCH + lane] : 0u;
-                    __syncwarp();
-                    if (lane < rem) q[lane] = v;
-                    __syncwarp();
-                    qlen1[k] = rem;
-                }
-            }
-        }
-    }
-}
-
-template <int SPW, bool REAL>
-__global__ void __launch_bounds__(K1_THREADS, 1)
-fused_eloc_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples, const double2 *__restrict__ amps,
-                  int64_t row_start, int64_t row_len, int alpha, int beta, double2 *__restrict__ eloc, int tile_masks,
-                  int ntiles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t bars[2];
-    // dynamic shared memory: [queues | mask tile(s)]
-    uint32_t *queues = reinterpret_cast<uint32_t *>(smem_raw);
-    TileStager st;
-    st.init(reinterpret_cast<uint2 *>(smem_raw + FUSED_QUEUE_BYTES), bars, t.mab, t.U_pad, tile_masks, ntiles);
-
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    uint32_t *q1 = queues + warp * SPW * (Q1_CAP + Q2_CAP);
-    uint32_t *q2 = q1 + SPW * Q1_CAP;
-    FusedCtx c;
-    c.t = t;
-    c.hv = hv;
-    c.mab = ntiles == 1 ? st.buf : t.mab;
-    const int64_t per_group = (int64_t)K1_WARPS * SPW;
-    const int64_t ngroups = (row_len + per_group - 1) / per_group;
-    for (int64_t group = blockIdx.x; group < ngroups; group += gridDim.x) {
-        const int64_t r0 = group * per_group + (int64_t)warp * SPW;
-        uint32_t xa[SPW], xb[SPW];
-        int qlen1[SPW], qlen2[SPW], alpha_k[SPW];
-        double er[SPW], ei[SPW];
-#pragma unroll
-        for (int k = 0; k < SPW; ++k) {
-            uint64_t x = (r0 + k < row_len) ? (uint64_t)samples[row_start + r0 + k] : 0ull;
-            xa[k] = compress_even_bits(x);
-            xb[k] = compress_even_bits(x >> 1);
-            qlen1[k] = qlen2[k] = 0;
-            er[k] = ei[k] = 0.0;
-            // rows past the end get an impossible electron count so that nothing passes
-            alpha_k[k] = (r0 + k < row_len) ? alpha : -1;
-        }
-        if (ntiles > 1) st.issue(0);
-        for (int tI = 0; tI < ntiles; ++tI) {
-            const uint2 *tile;
-            if (ntiles == 1) {
-                if (!st.resident_loaded) {
-                    st.issue(0);
-                    tile = st.wait(0);
-                    st.resident_loaded = true;
-                } else {
-                    tile = st.buf;
-                }
-            } else {
-                if (tI + 1 < ntiles) st.issue(tI + 1);
-                tile = st.wait(tI);
-            }
-            const int tl = st.tile_len(tI);
-            const int64_t base_idx = (int64_t)tI * tile_masks;
-            int64_t valid_masks = t.U - base_idx;
-            if (valid_masks < 0) valid_masks = 0;
-            if (valid_masks > tl) valid_masks = tl;
-            const int full_its = (int)(valid_masks >> 5), all_its = (int)((valid_masks + 31) >> 5);
-            fused_steps<SPW, REAL, false>(c, tile, 0, full_its, base_idx, xa, xb, alpha_k, beta, q1, q2, qlen1, qlen2, er, ei);
-            fused_steps<SPW, REAL, true>(c, tile, full_its, all_its, base_idx, xa, xb, alpha_k, beta, q1, q2, qlen1, qlen2, er, ei);
-            if (ntiles > 1) __syncthreads();
-        }
-#pragma unroll
-        for (int k = 0; k < SPW; ++k) {
-            __syncwarp();
-            if (qlen1[k] > 0)
-                fused_bloom_drain<REAL>(c, xa[k], xb[k], q1 + k * Q1_CAP, qlen1[k], q2 + k * Q2_CAP, qlen2[k], er[k], ei[k]);
-            if (qlen2[k] > 0) {
-                __syncwarp();
-                uint32_t uu = q2[k * Q2_CAP + lane];
-                fused_probe<REAL>(c, xa[k], xb[k], lane < qlen2[k], lane < qlen2[k] ? uu : 0u, er[k], ei[k]);
-            }
-            __syncwarp();
-            double sr = er[k], si = ei[k];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                sr += __shfl_xor_sync(0xffffffffu, sr, d);
-                si += __shfl_xor_sync(0xffffffffu, si, d);
-            }
-            if (lane == 0 && r0 + k < row_len) {
-                double2 a = amps[row_start + r0 + k];
-                double den = a.x * a.x + a.y * a.y;
-                eloc[r0 + k] = make_double2((sr * a.x + si * a.y) / den, (si * a.x - sr * a.y) / den);
-            }
-        }
-    }
-}
-
 // ---- E[dest] += H * psi(src) over CSR rows ---------------------------------------------------------------
 template <int HC>
 __global__ void __launch_bounds__(256)
@@ -655,39 +376,6 @@ int anqs_matrix_elements(const anqs_tables_t *h, const int64_t *d_xprime, const 
         matrix_elements_kernel<true><<<grid, 256, 0, s>>>(*t, d_xprime, d_xy_ptr, m, (double2 *)d_H);
     else
         matrix_elements_kernel<false><<<grid, 256, 0, s>>>(*t, d_xprime, d_xy_ptr, m, (double2 *)d_H);
-    ANQS_LAUNCH_CHECK();
-    return 0;
-}
-
-int anqs_local_energy_sample_aware(const anqs_tables_t *h, const int64_t *d_samples, const double *d_amps,
-                                   int64_t n_total, int64_t row_start, int64_t row_len, const void *d_table,
-                                   int64_t capacity, int alpha_num, int beta_num, double *d_eloc, void *stream) {
-    ANQS_REQUIRE(h, "null tables handle");
-    ANQS_REQUIRE(row_start >= 0 && row_len >= 0 && row_start + row_len <= n_total, "row window out of range");
-    if (row_len == 0) return 0;
-    ANQS_REQUIRE(d_samples && d_amps && d_table && d_eloc, "null pointer");
-    ANQS_REQUIRE(capacity >= 1024 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 1024");
-    const Tables *t = (const Tables *)h;
-    constexpr int SPW = FUSED_SPW;
-    int tile_masks, ntiles;
-    size_t smem;
-    pick_tiling(t, &tile_masks, &ntiles, &smem);
-    smem += FUSED_QUEUE_BYTES;
-    HashView hv = make_hash_view(d_table, capacity);
-    int64_t ngroups = (row_len + K1_WARPS * SPW - 1) / (K1_WARPS * SPW);
-    int grid = (int)std::min<int64_t>(ngroups, sm_count_of_current_device());
-    cudaStream_t s = (cudaStream_t)stream;
-    if (t->weights_real) {
-        auto kern = fused_eloc_kernel<SPW, true>;
-        ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, K1_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num,
-                                            beta_num, (double2 *)d_eloc, tile_masks, ntiles);
-    } else {
-        auto kern = fused_eloc_kernel<SPW, false>;
-        ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, K1_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num,
-                                            beta_num, (double2 *)d_eloc, tile_masks, ntiles);
-    }
     ANQS_LAUNCH_CHECK();
     return 0;
 }

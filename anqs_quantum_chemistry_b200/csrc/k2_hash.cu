@@ -3,29 +3,88 @@
 //
 // Open-addressing table with linear probing.  One slot is one 32-byte sector
 // {key u64 (de-interleaved), index i64, amp.re f64, amp.im f64}, so a probe that hits returns the amplitude
-// psi(x') from the same sector.  A blocked Bloom filter (capacity/4 words of 32 bits behind the slots, 3
-// bits of one word per key, >= 16 bits per key) decides ~99 % of the misses with one 4-byte load of an
-// array that stays L2-resident even when the slot array does not.  The all-ones key is the EMPTY sentinel; a real all-ones key (only possible at
-// qubit_num == 64, or for generic int64 inputs such as -1) lives in a dedicated slot at index `capacity`.
+// psi(x') from the same sector.  In front of it sits a line-blocked presence filter (layout and rationale in
+// common.cuh): one bit per key, 32..64 bits per key, the 128-byte line chosen by a GF(2)-linear hash of the alpha
+// half of the key.  The fused local-energy kernel (k1_fused.cu) consults only the filter for ~97 % of its
+// candidates.  The all-ones key is the EMPTY sentinel; a real all-ones key (only possible at qubit_num == 64, or for
+// generic int64 inputs such as -1) lives in a dedicated slot at index `capacity`.
+//
+// Build = 5 stream-ordered launches, no host synchronisation:
+//   memset -> count keys per line (in the filter region itself) -> pick the spread G -> memset filter -> insert.
+// G spreads the keys that share an alpha half over 2^G lines (selected by hash bits of the beta half) when sample
+// sets concentrate on few alpha strings; G = 0 when at most 5 % of the keys sit in lines holding more than 128 keys.
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace anqs {
 
+__device__ __forceinline__ void key_hashes(uint64_t key, uint32_t &hl, uint32_t &hp) {
+    const uint32_t ka = (uint32_t)key, kb = (uint32_t)(key >> 32);
+    hl = lin_dev(LIN_LINE, ka);
+    hp = (lin_dev(LIN_POSA, ka) & 0x3FFu) ^ (lin_dev(LIN_POSB, kb) & 0xFFFFu);
+}
+
+__global__ void __launch_bounds__(256)
+filter_count_kernel(const int64_t *__restrict__ keys, int64_t n, uint32_t *counts, uint32_t linemask) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        uint32_t hl, hp;
+        key_hashes(deinterleave((uint64_t)keys[j]), hl, hp);
+        atomicAdd(counts + (hl & linemask), 1u);
+    }
+}
+
+// one block: overloaded[g] = number of keys in alpha-lines that hold more than 128 << g keys; G = first g whose
+// overloaded share is <= 5 %
+__global__ void __launch_bounds__(1024)
+filter_pick_spread_kernel(const uint32_t *__restrict__ counts, uint32_t nlines, uint32_t n_keys, FilterHeader *hdr,
+                          int forced_spread) {
+    const uint32_t ncount = forced_spread < 0 ? nlines : 0u;
+    __shared__ unsigned long long acc[FILTER_MAX_SPREAD_BITS + 1];
+    if (threadIdx.x <= FILTER_MAX_SPREAD_BITS) acc[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned long long local[FILTER_MAX_SPREAD_BITS + 1] = {0};
+    for (uint32_t i = threadIdx.x; i < ncount; i += blockDim.x) {
+        const uint32_t c = counts[i];
+#pragma unroll
+        for (int g = 0; g <= FILTER_MAX_SPREAD_BITS; ++g)
+            if (c > (128u << g)) local[g] += c;
+    }
+#pragma unroll
+    for (int g = 0; g <= FILTER_MAX_SPREAD_BITS; ++g)
+        if (local[g]) atomicAdd(&acc[g], local[g]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int G = FILTER_MAX_SPREAD_BITS;
+        for (int g = FILTER_MAX_SPREAD_BITS; g >= 0; --g) {
+            hdr->overloaded[g] = (uint32_t)acc[g];
+            if (acc[g] * 20ull <= (unsigned long long)n_keys) G = g;
+        }
+        if (forced_spread >= 0) G = forced_spread;
+        while (G > 0 && (1u << G) > nlines) --G;
+        hdr->spread_bits = (uint32_t)G;
+        hdr->gmask = (1u << G) - 1u;
+        hdr->n_keys = n_keys;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 hash_build_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ amps, int64_t n, HashSlot *slots,
-                  uint32_t *bloom, uint32_t capmask, uint32_t wordmask) {
+                  uint32_t *filter_words, const FilterHeader *hdr, uint32_t capmask, uint32_t linemask) {
+    const uint32_t gmask = hdr->gmask;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         uint64_t key = deinterleave((uint64_t)keys[j]);
+        uint32_t hl, hp;
+        key_hashes(key, hl, hp);
+        const uint32_t line = (hl ^ ((hp >> 10) & gmask)) & linemask;
+        atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), 1u << (hp & 31u));
         HashSlot *sl;
         if (key == EMPTY_KEY) {
             sl = slots + (size_t)capmask + 1;
         } else {
-            uint32_t hh = hash_key((uint32_t)key, (uint32_t)(key >> 32));
-            atomicOr(bloom + (bloom_word(hh) & wordmask), bloom_pattern(hh));
-            uint32_t h = hh & capmask;
+            uint32_t h = hash_key((uint32_t)key, (uint32_t)(key >> 32)) & capmask;
             for (;;) {
                 unsigned long long prev = atomicCAS((unsigned long long *)&slots[h].key, (unsigned long long)EMPTY_KEY,
                                                     (unsigned long long)key);
@@ -50,16 +109,8 @@ hash_probe_kernel(HashView hv, const int64_t *__restrict__ queries, int64_t m, i
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
         uint64_t q = deinterleave((uint64_t)queries[i]);
-        long long j = -1;
-        bool maybe = true;
-        if (q != EMPTY_KEY) {
-            uint32_t hh = hash_key((uint32_t)q, (uint32_t)(q >> 32)), pat = bloom_pattern(hh);
-            maybe = (__ldg(hv.bloom + (bloom_word(hh) & hv.wordmask)) & pat) == pat;
-        }
-        if (maybe) {
-            double re, im;
-            j = hash_lookup(hv, q, re, im);
-        }
+        double re, im;
+        long long j = hash_lookup(hv, q, re, im);
         if (ptr) ptr[i] = j;
         if (mask) mask[i] = j >= 0 ? 1 : 0;
     }
@@ -69,6 +120,40 @@ hash_probe_kernel(HashView hv, const int64_t *__restrict__ queries, int64_t m, i
 
 using namespace anqs;
 
+static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
+                       int forced_spread, void *stream) {
+    ANQS_REQUIRE(n >= 0, "negative key count");
+    ANQS_REQUIRE(d_table, "null table buffer");
+    ANQS_REQUIRE(capacity >= 1024 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 1024");
+    ANQS_REQUIRE(capacity >= 2 * n, "capacity must be at least 2n (use anqs_hash_capacity)");
+    ANQS_REQUIRE(capacity <= ((int64_t)1 << 29), "capacity above 2^29 slots is not supported");
+    ANQS_REQUIRE(((uintptr_t)d_table & 127) == 0, "table buffer must be 128-byte aligned");
+    ANQS_REQUIRE(forced_spread <= FILTER_MAX_SPREAD_BITS, "spread_bits must be at most 6");
+    cudaStream_t s = (cudaStream_t)stream;
+    HashView hv = make_hash_view(d_table, capacity);
+    HashSlot *slots = (HashSlot *)d_table;
+    FilterHeader *hdr = (FilterHeader *)hv.header;
+    uint32_t *filter_words = (uint32_t *)hv.filter;
+    const uint32_t nlines = hv.linemask + 1;
+    // 0xFF over the slots: key = EMPTY, idx = -1; zero header and filter
+    ANQS_CUDA(cudaMemsetAsync(slots, 0xFF, (size_t)(capacity + 1) * sizeof(HashSlot), s));
+    ANQS_CUDA(cudaMemsetAsync(hdr, 0, 96 + (size_t)2 * capacity, s));
+    if (n == 0) return 0;
+    ANQS_REQUIRE(d_keys, "null key array");
+    int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 16);
+    if (forced_spread < 0) {
+        // per-line key counts, kept in the (still empty) filter region: nlines * 4 bytes <= 2 * capacity bytes
+        filter_count_kernel<<<grid, 256, 0, s>>>(d_keys, n, filter_words, hv.linemask);
+        ANQS_LAUNCH_CHECK();
+    }
+    filter_pick_spread_kernel<<<1, 1024, 0, s>>>(filter_words, nlines, (uint32_t)n, hdr, forced_spread);
+    ANQS_LAUNCH_CHECK();
+    if (forced_spread < 0) ANQS_CUDA(cudaMemsetAsync(filter_words, 0, (size_t)nlines * sizeof(uint32_t), s));
+    hash_build_kernel<<<grid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, filter_words, hdr, hv.capmask, hv.linemask);
+    ANQS_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" {
 
 int64_t anqs_hash_capacity(int64_t n) {
@@ -77,28 +162,28 @@ int64_t anqs_hash_capacity(int64_t n) {
     return cap;
 }
 
-size_t anqs_hash_bytes(int64_t capacity) { return (size_t)(capacity + 1) * sizeof(HashSlot) + (size_t)capacity; }
+size_t anqs_hash_bytes(int64_t capacity) { return (size_t)capacity * sizeof(HashSlot) + 128 + (size_t)2 * capacity; }
 
 int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                     void *stream) {
-    ANQS_REQUIRE(n >= 0, "negative key count");
+    return build_table(d_keys, d_amps, n, d_table, capacity, -1, stream);
+}
+
+int anqs_hash_build_spread(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
+                           int spread_bits, void *stream) {
+    return build_table(d_keys, d_amps, n, d_table, capacity, spread_bits, stream);
+}
+
+int anqs_hash_filter_info(const void *d_table, int64_t capacity, int *spread_bits, int64_t *overloaded_keys, void *stream) {
     ANQS_REQUIRE(d_table, "null table buffer");
     ANQS_REQUIRE(capacity >= 1024 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 1024");
-    ANQS_REQUIRE(capacity >= 2 * n, "capacity must be at least 2n (use anqs_hash_capacity)");
-    ANQS_REQUIRE(capacity <= ((int64_t)1 << 29), "capacity above 2^29 slots is not supported");
-    ANQS_REQUIRE(((uintptr_t)d_table & 31) == 0, "table buffer must be 32-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream;
-    HashSlot *slots = (HashSlot *)d_table;
-    uint32_t *bits = (uint32_t *)(slots + capacity + 1);
-    // 0xFF over the slots: key = EMPTY, idx = -1; zero Bloom words
-    ANQS_CUDA(cudaMemsetAsync(slots, 0xFF, (size_t)(capacity + 1) * sizeof(HashSlot), s));
-    ANQS_CUDA(cudaMemsetAsync(bits, 0, (size_t)capacity, s));
-    if (n == 0) return 0;
-    ANQS_REQUIRE(d_keys, "null key array");
-    int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 16);
-    hash_build_kernel<<<grid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, bits, (uint32_t)(capacity - 1),
-                                           (uint32_t)(capacity / 4 - 1));
-    ANQS_LAUNCH_CHECK();
+    HashView hv = make_hash_view(d_table, capacity);
+    FilterHeader h;
+    ANQS_CUDA(cudaMemcpyAsync(&h, hv.header, sizeof(FilterHeader), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ANQS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (spread_bits) *spread_bits = (int)h.spread_bits;
+    if (overloaded_keys)
+        for (int g = 0; g <= FILTER_MAX_SPREAD_BITS; ++g) overloaded_keys[g] = (int64_t)h.overloaded[g];
     return 0;
 }
 

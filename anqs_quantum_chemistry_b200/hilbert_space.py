@@ -142,20 +142,34 @@ class HilbertSpace:
 
 
 class SampleTable:
-    """Open-addressing table {configuration -> (position, amplitude)} in device memory."""
+    """Open-addressing table {configuration -> (position, amplitude)} plus its presence filter, in device memory."""
 
-    def __init__(self, keys: pt.Tensor, amps: pt.Tensor = None):
+    def __init__(self, keys: pt.Tensor, amps: pt.Tensor = None, spread_bits: int = None):
         dev = _lib.require_cuda(keys.device)
         assert keys.dtype == pt.int64 and keys.dim() == 1 and keys.is_contiguous()
         n = keys.shape[0]
         self.n = n
         self.capacity = int(_lib.lib().anqs_hash_capacity(n))
         nbytes = int(_lib.lib().anqs_hash_bytes(self.capacity))
-        self.slots = pt.empty(((nbytes + 31) // 32 * 4,), dtype=pt.int64, device=dev)  # slots + Bloom words
+        self.slots = pt.empty(((nbytes + 7) // 8,), dtype=pt.int64, device=dev)  # slots + header + filter
+        assert self.slots.data_ptr() % 128 == 0
         amps_real = None
         if amps is not None:
             assert amps.dtype == pt.complex128 and amps.shape[0] == n
             amps_real = pt.view_as_real(amps.contiguous())
         self._keep = (keys, amps_real)
-        _lib.check(_lib.lib().anqs_hash_build(_lib.dptr(keys), _lib.dptr(amps_real), n, _lib.dptr(self.slots), self.capacity,
-                                              _lib.stream_ptr(dev)))
+        if spread_bits is None:
+            _lib.check(_lib.lib().anqs_hash_build(_lib.dptr(keys), _lib.dptr(amps_real), n, _lib.dptr(self.slots), self.capacity,
+                                                  _lib.stream_ptr(dev)))
+        else:
+            _lib.check(_lib.lib().anqs_hash_build_spread(_lib.dptr(keys), _lib.dptr(amps_real), n, _lib.dptr(self.slots),
+                                                         self.capacity, int(spread_bits), _lib.stream_ptr(dev)))
+
+    def filter_info(self):
+        """(G, overloaded[0..6]): the spread chosen by the build and the line-occupancy statistic behind it."""
+        import ctypes
+        g = ctypes.c_int(0)
+        over = (ctypes.c_int64 * 7)()
+        _lib.check(_lib.lib().anqs_hash_filter_info(_lib.dptr(self.slots), self.capacity, ctypes.byref(g), over,
+                                                    _lib.stream_ptr(self.slots.device)))
+        return int(g.value), [int(v) for v in over]

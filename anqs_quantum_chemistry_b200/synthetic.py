@@ -177,6 +177,46 @@ def random_physical_samples(qubit_num: int, alpha_num: int, beta_num: int, count
     return out
 
 
+def clustered_physical_samples(qubit_num: int, alpha_num: int, beta_num: int, count: int, seed: int = 1,
+                               mean_rank: float = 3.0) -> np.ndarray:
+    """`count` distinct physical configurations concentrated around the Hartree-Fock determinant (lowest orbitals
+    occupied = highest bits set, create_masker.py:29): each one is HF with k ~ 1 + Poisson(mean_rank - 1) random
+    single excitations (occupied -> virtual within one spin sector).  This is what a VMC sample set looks like - many
+    samples share their alpha (or beta) string and connected configurations are often sampled too - as opposed to
+    `random_physical_samples`, whose uniform draws almost never connect to each other at large qubit counts."""
+    assert qubit_num % 2 == 0
+    m = qubit_num // 2
+    rng = np.random.default_rng(seed)
+    hf_a = np.zeros(m, bool); hf_a[m - alpha_num:] = True
+    hf_b = np.zeros(m, bool); hf_b[m - beta_num:] = True
+    total = _sector_size(m, alpha_num, beta_num)
+    count = min(count, total)
+    out = np.zeros(0, dtype=U64)
+    weights = U64(1) << (U64(2) * np.arange(m, dtype=U64))
+    while out.shape[0] < count:
+        need = int((count - out.shape[0]) * 1.5) + 64
+        occ = np.stack((np.tile(hf_a, (need, 1)), np.tile(hf_b, (need, 1))), axis=1)  # [need, 2, m]
+        k = 1 + rng.poisson(max(mean_rank - 1.0, 0.0), size=need)
+        rows = np.arange(need)
+        for step in range(int(k.max())):
+            act = k > step
+            spin = rng.integers(0, 2, size=need)
+            cur = occ[rows, spin]                                      # [need, m]
+            r = rng.random((need, m))
+            src = np.argmax(np.where(cur, r, -1.0), axis=1)            # a random occupied orbital
+            dst = np.argmax(np.where(~cur, r, -1.0), axis=1)           # a random empty orbital
+            ok = act & cur.any(axis=1) & (~cur).any(axis=1)
+            occ[rows[ok], spin[ok], src[ok]] = False
+            occ[rows[ok], spin[ok], dst[ok]] = True
+        a = (occ[:, 0, :] * weights).sum(axis=1, dtype=U64)
+        b = (occ[:, 1, :] * (weights << U64(1))).sum(axis=1, dtype=U64)
+        out = np.unique(np.concatenate((out, a | b)))
+        mean_rank += 0.25  # widen the cloud if the shell is exhausted
+    if out.shape[0] > count:
+        out = np.sort(rng.permutation(out)[:count])
+    return out
+
+
 def _sector_size(m, na, nb):
     from math import comb
     return comb(m, na) * comb(m, nb)

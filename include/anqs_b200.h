@@ -86,15 +86,23 @@ int anqs_matrix_elements(const anqs_tables_t *t, const int64_t *d_xprime, const 
                          double *d_H /* m complex128 */, void *stream);
 
 /* ---- A5  kernel 2: membership join, HilbertSpace.find_a_in_b (HS:263-284) -----------------------------
- * Open-addressing table in one caller-allocated buffer of anqs_hash_bytes(capacity) bytes:
- * (capacity + 1) 32-byte slots {key, index, amp.re, amp.im} followed by capacity bytes of blocked-Bloom
- * presence bits (3 bits of one 32-bit word per key; a probe tests that word first, so ~99 % of the misses cost
- * a single 4-byte load).  Keys are stored de-interleaved (even bits | odd bits << 32).  capacity: power of two >= anqs_hash_capacity(n).
- * d_amps may be NULL. */
+ * Open-addressing table in one caller-allocated, 128-byte aligned buffer of anqs_hash_bytes(capacity) bytes:
+ * capacity 32-byte slots {key, index, amp.re, amp.im}, one dedicated slot for the all-ones key, a 96-byte header, and
+ * a presence filter of 2*capacity bytes (one bit per key; the 128-byte line is chosen by a GF(2)-linear hash of the
+ * alpha half of the key, so all the candidates of one sample that share the alpha part of their mask test the same
+ * line).  Keys are stored de-interleaved (even bits | odd bits << 32).  capacity: power of two >=
+ * anqs_hash_capacity(n).  d_amps may be NULL.  The build is stream-ordered (no host synchronisation); it picks the
+ * number of "spread bits" G (keys sharing an alpha half are spread over 2^G lines) from the line occupancy. */
 int64_t anqs_hash_capacity(int64_t n);
 size_t anqs_hash_bytes(int64_t capacity);
 int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                     void *stream);
+/* Same with G forced to spread_bits (0..6) instead of chosen from the data. */
+int anqs_hash_build_spread(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
+                           int spread_bits, void *stream);
+/* Reads back G and overloaded_keys[g] (g = 0..6) = keys living in lines that hold more than 128 << g keys.
+ * Synchronises the stream. */
+int anqs_hash_filter_info(const void *d_table, int64_t capacity, int *spread_bits, int64_t *overloaded_keys, void *stream);
 /* d_ptr[i] = position of d_queries[i] in the key array, or -1; d_mask[i] = (d_ptr[i] != -1) (either may be NULL). */
 int anqs_hash_probe(const void *d_table, int64_t capacity, const int64_t *d_queries, int64_t m,
                     int64_t *d_ptr, uint8_t *d_mask, void *stream);

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from conftest import load_golden, HAM_CASES, HAM_CASES_WITH_LISTS
-from anqs_quantum_chemistry_b200 import HilbertSpace, PauliObservable, PauliArraysOperator, synthetic
+from anqs_quantum_chemistry_b200 import HilbertSpace, PauliObservable, PauliArraysOperator, SampleTable, synthetic
 from oracle import hamiltonian_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -176,6 +176,65 @@ def test_streamed_table(tmp_path):
     np.testing.assert_array_equal(conn['xprime'].cpu().numpy(), xp)
     np.testing.assert_array_equal(conn['xy_ptr'].cpu().numpy(), ptr)
     np.testing.assert_array_equal(conn['dest'].cpu().numpy(), dest)
+
+
+@pytest.mark.parametrize('qubits,electrons,irreps,n_samples', [(20, 14, 1, 6000), (56, 14, 8, 4000)])
+def test_clustered_samples_and_filter_spread(qubits, electrons, irreps, n_samples, tmp_path):
+    """Sample sets concentrated around the Hartree-Fock determinant: many samples share their alpha string (so the
+    line-blocked presence filter is heavily loaded on a few lines) and a large share of the connected configurations
+    is itself sampled (the matrix-element path is busy).  Every forced filter spread G = 0..6 and the data-driven
+    choice must give the oracle's local energies."""
+    xy, yz, w = synthetic.synthetic_hamiltonian(qubits, n_irreps=irreps, seed=4)
+    na = nb = electrons // 2
+    samples = synthetic.clustered_physical_samples(qubits, na, nb, n_samples, seed=7, mean_rank=2.0)
+    amps = synthetic.random_amplitudes(samples.shape[0], seed=8)
+    tab = orc.Tables(xy, yz, w)
+    e_ref = orc.local_energy_sample_aware(samples, amps, tab, na, nb)
+    scale = max(1.0, np.abs(e_ref).max())
+    hs = HilbertSpace(qubit_num=qubits, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, qubits))
+    s, a = _dev(samples.view(np.int64)), _dev(amps)
+    # hits are frequent in this workload
+    conn = ham.connected_configurations(s[:128], na, nb, with_dest=False, with_xy_ptr=False)
+    mask, _ = hs.find_a_in_b(a=conn['xprime'].view(-1, 1), b=s.view(-1, 1))
+    assert float(mask.double().mean()) > (0.05 if qubits == 20 else 0.001)
+    for spread in (None, 0, 1, 3, 6):
+        table = SampleTable(s, a, spread_bits=spread)
+        e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s.view(-1, 1), unq_batch_as_amps=a, coupling_method='ham',
+                                                     alpha_num=na, beta_num=nb, table=table)
+        assert np.abs(e.cpu().numpy() - e_ref).max() < 1e-10 * scale, spread
+        g, over = table.filter_info()
+        assert g == (spread if spread is not None else g) and 0 <= g <= 6
+        assert all(over[i] >= over[i + 1] for i in range(6))
+
+
+def test_filter_spread_is_chosen_from_the_data(tmp_path):
+    """Uniform samples have ~1 key per alpha string -> G = 0; a set with one dominant alpha string -> G > 0."""
+    uni = _dev(synthetic.random_physical_samples(56, 7, 7, 50000, seed=9).view(np.int64))
+    g_uni, over = SampleTable(uni).filter_info()
+    assert g_uni == 0 and over[0] == 0
+    # all beta strings on top of a single alpha string: 20000 keys want the same line
+    base = synthetic.random_physical_samples(56, 7, 7, 20000, seed=10)
+    one_alpha = np.unique((base & np.uint64(0xAAAAAAAAAAAAAAAA)) | (base[0] & np.uint64(0x5555555555555555)))
+    g_hot, over = SampleTable(_dev(one_alpha.view(np.int64))).filter_info()
+    assert g_hot == 6 and over[0] == one_alpha.shape[0]
+
+
+def test_multi_tile_product_layout(tmp_path):
+    """The headline Hamiltonian (56 qubits, 8 irreps: U = 23 157) does not fit one 200 KB tile: the fused kernel
+    re-streams two tiles per group of samples.  Also rows past the end of a partial group (n not a multiple of 32)."""
+    xy, yz, w = synthetic.synthetic_hamiltonian(56, n_irreps=8, seed=0)
+    na = nb = 7
+    samples = synthetic.clustered_physical_samples(56, na, nb, 3001, seed=3, mean_rank=2.5)
+    amps = synthetic.random_amplitudes(samples.shape[0], seed=6)
+    tab = orc.Tables(xy, yz, w)
+    hs = HilbertSpace(qubit_num=56, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, 56))
+    s, a = _dev(samples.view(np.int64)), _dev(amps)
+    e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s.view(-1, 1), unq_batch_as_amps=a, coupling_method='ham',
+                                                 alpha_num=na, beta_num=nb)
+    e_ref = orc.local_energy_sample_aware(samples, amps, tab, na, nb)
+    assert np.abs(e.cpu().numpy() - e_ref).max() < 1e-10 * max(1.0, np.abs(e_ref).max())
 
 
 def test_edge_cases(tmp_path):
