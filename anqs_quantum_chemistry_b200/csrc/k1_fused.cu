@@ -81,11 +81,10 @@ __device__ __forceinline__ void fz_resolve(const Tables &t, const HashView &hv, 
 }
 
 // Appends the candidates flagged in `positive` to the warp's queue; resolves a batch when 32 are waiting.
+// `b` is the ballot of `positive` (non-zero).
 template <bool REAL>
-__device__ __forceinline__ void fz_push(const Tables &t, const HashView &hv, FzWarp &w, bool positive, uint32_t ka,
-                                        uint32_t kb, uint32_t uref) {
-    const unsigned b = __ballot_sync(0xffffffffu, positive);
-    if (b == 0) return;
+__device__ __forceinline__ void fz_push(const Tables &t, const HashView &hv, FzWarp &w, unsigned b, bool positive,
+                                        uint32_t ka, uint32_t kb, uint32_t uref) {
     const int lane = lane_id();
     if (positive) {
         const int p = w.qlen + __popc(b & lanemask_lt());
@@ -116,12 +115,23 @@ __device__ __forceinline__ void fz_push(const Tables &t, const HashView &hv, FzW
     }
 }
 
+// Two probe results per lane (one double step): a single vote decides whether anything has to be queued at all.
+template <bool REAL>
+__device__ __forceinline__ void fz_push2(const Tables &t, const HashView &hv, FzWarp &w, bool f1, bool f2, uint32_t ka1,
+                                         uint32_t kb1, uint32_t u1, uint32_t ka2, uint32_t kb2, uint32_t u2) {
+    if (!__any_sync(0xffffffffu, f1 | f2)) return;
+    const unsigned b1 = __ballot_sync(0xffffffffu, f1);
+    if (b1) fz_push<REAL>(t, hv, w, b1, f1, ka1, kb1, u1);
+    const unsigned b2 = __ballot_sync(0xffffffffu, f2);
+    if (b2) fz_push<REAL>(t, hv, w, b2, f2, ka2, kb2, u2);
+}
+
 // filter bit of the candidate with member hash `mhash` in the line group `rowline` (byte offset of the row's line)
 __device__ __forceinline__ bool fz_filter_bit(const FzWarp &w, bool pass, uint32_t rowline, uint32_t mhash) {
     const uint32_t h = w.hp ^ mhash;
     const uint32_t off = (rowline ^ ((h >> 3) & w.gshift)) + ((h >> 3) & 0x7Cu);  // line * 128 + word * 4
     uint32_t word = 0;
-    if (pass) word = __ldg(reinterpret_cast<const uint32_t *>(w.filter + off));
+    if (pass) word = __ldg(reinterpret_cast<const uint32_t *>(w.filter + off));  // 32-bit offset: filters are <= 1 GiB
     return (word >> (h & 31u)) & 1u;
 }
 
@@ -153,8 +163,8 @@ __device__ __forceinline__ void fz_process_tile(const Tables &t, const HashView 
                 const bool p2 = j2 < len && __popc(w.xb ^ m2.x) == w.beta;
                 const bool f1 = fz_filter_bit(w, p1, rowline, m1.y);
                 const bool f2 = fz_filter_bit(w, p2, rowline, m2.y);
-                fz_push<REAL>(t, hv, w, f1, ka, w.xb ^ m1.x, tile.member_base + start + j1);
-                if (j0 + 32 < len) fz_push<REAL>(t, hv, w, f2, ka, w.xb ^ m2.x, tile.member_base + start + j2);
+                fz_push2<REAL>(t, hv, w, f1, f2, ka, w.xb ^ m1.x, tile.member_base + start + j1, ka, w.xb ^ m2.x,
+                               tile.member_base + start + j2);
             }
         }
     }
@@ -169,9 +179,8 @@ __device__ __forceinline__ void fz_process_tile(const Tables &t, const HashView 
         const bool p2 = r2 < tile.n_single && __popc(w.xa ^ c2.x) == w.alpha && __popc(w.xb ^ c2.z) == w.beta;
         const bool f1 = fz_filter_bit(w, p1, ((w.hl ^ c1.y) & w.linemask) << 7, c1.w);
         const bool f2 = fz_filter_bit(w, p2, ((w.hl ^ c2.y) & w.linemask) << 7, c2.w);
-        fz_push<REAL>(t, hv, w, f1, w.xa ^ c1.x, w.xb ^ c1.z, UREF_ROW | (tile.row_base + tile.n_multi + r1));
-        if (r0 + 32 < tile.n_single)
-            fz_push<REAL>(t, hv, w, f2, w.xa ^ c2.x, w.xb ^ c2.z, UREF_ROW | (tile.row_base + tile.n_multi + r2));
+        fz_push2<REAL>(t, hv, w, f1, f2, w.xa ^ c1.x, w.xb ^ c1.z, UREF_ROW | (tile.row_base + tile.n_multi + r1), w.xa ^ c2.x,
+                       w.xb ^ c2.z, UREF_ROW | (tile.row_base + tile.n_multi + r2));
     }
 }
 
