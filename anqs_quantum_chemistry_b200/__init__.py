@@ -10,3 +10,5 @@ from .symmetries import ParticleNumberSymmetry, SpinHalfProjectionSymmetry, Z2Sy
 from .masker import LocallyDecomposableMasker  # noqa: F401
 from .qubit_grouping import QubitGrouping, QubitGroupingConfig  # noqa: F401
 from .anqs import LogAbsPhaseANQS, ANQSConfig, MLPConfig, LocalSamplingConfig  # noqa: F401
+from .calculations import (SamplingConfig, SamplingResult, sample, LocalEnergyCalculationConfig, MonteCarloEstimator,  # noqa: F401
+                           LocalEnergyResult, compute_local_energies, vmc_loss)

@@ -1,0 +1,131 @@
+"""Call sites of the hot path (reference: nqs/nqs/applications/quantum_chemistry/experiments/calculations/
+{sample,compute_local_energies}.py).  Same names, keywords and return shapes, so a driver written against the
+reference (EnergyOptExp.iter, energy_opt_exp.py:626-679) runs unchanged on the B200 objects.
+
+  sample(wf, config)                    SMP:51-101   -> SamplingResult, unique count, repetitions, next sample_num
+  compute_local_energies(wf, ...)       CLE:75-163   -> LocalEnergyResult(full / sample-aware MonteCarloEstimator), metrics
+  MonteCarloEstimator                   CLE:48-62    mean / var under frequencies counts / sum(counts)
+  vmc_loss(...)                         EXP:609      2 Re sum f log(conj psi) (E - <E>)
+"""
+import numpy as np
+import torch as pt
+
+
+class SamplingConfig:
+    """SMP:18-36."""
+    FIELDS = ('sample_indices', 'sample_num', 'sample_precisely', 'upscale_factor', 'downscale_factor', 'couple_spin_flip')
+
+    def __init__(self, *args, sample_indices: bool = True, sample_num: int = 10000, sample_precisely: bool = False,
+                 upscale_factor: float = 3.0, downscale_factor: float = 2.0, couple_spin_flip: bool = False, **kwargs):
+        self.sample_indices, self.sample_num, self.sample_precisely = sample_indices, sample_num, sample_precisely
+        self.upscale_factor, self.downscale_factor, self.couple_spin_flip = upscale_factor, downscale_factor, couple_spin_flip
+
+
+class SamplingResult:
+    """SMP:39-48."""
+
+    def __init__(self, *args, indices: pt.Tensor = None, counts: pt.Tensor = None, **kwargs):
+        self.indices, self.counts = indices, counts
+
+
+def sample(wf=None, config: SamplingConfig = None, starting_sample_num: int = None, verbose: bool = False, **sampler_kwargs):
+    """SMP:51-101.  `sampler_kwargs` (seed=, draw_mode=, uniforms=) are forwarded to the wave function's sampler."""
+    repetition_num = 1
+    next_rep_sample_num = starting_sample_num
+    if config.sample_indices:
+        indices, counts = wf.sample_indices_gumbel(sample_num=config.sample_num, **sampler_kwargs)
+        next_rep_sample_num = config.sample_num
+        actual_unq_num = indices.shape[0]
+    elif config.sample_precisely:
+        # grow the number of samples until at least sample_num unique configurations come back, keep the top ones
+        while True:
+            indices, counts = wf.sample_stats(sample_num=int(next_rep_sample_num), **sampler_kwargs)
+            if indices.shape[0] > config.sample_num:
+                if next_rep_sample_num / config.downscale_factor > config.sample_num:
+                    next_rep_sample_num /= config.downscale_factor
+                break
+            if indices.shape[0] == config.sample_num:
+                break
+            repetition_num += 1
+            next_rep_sample_num *= config.upscale_factor
+        actual_unq_num = indices.shape[0]
+        counts, order = pt.sort(counts.real, descending=True)
+        indices = indices[order[:config.sample_num]]
+    else:
+        indices, counts = wf.sample_stats(sample_num=config.sample_num, **sampler_kwargs)
+        next_rep_sample_num = config.sample_num
+        actual_unq_num = indices.shape[0]
+    counts = counts.type(wf.cdtype).to(wf.device)
+    if verbose:
+        print(f'sampled {indices.shape[0]} unique configurations carrying {counts.sum()} samples')
+    if config.couple_spin_flip:
+        with pt.no_grad():
+            indices = pt.cat((indices, wf.spin_flip_base_idx(indices)), dim=0)
+            indices, _ = wf.hilbert_space.compute_unique_indices(indices)
+            counts = wf.amplitude(indices)
+            counts = pt.conj(counts) * counts
+            counts = counts / pt.sum(counts)
+    return SamplingResult(indices=indices, counts=counts), actual_unq_num, repetition_num, next_rep_sample_num
+
+
+class LocalEnergyCalculationConfig:
+    """CLE:25-45."""
+    ALLOWED_CODE_VERSIONS = ('old', 'new')
+
+    def __init__(self, *args, use_theor_freqs: bool = True, use_tree_for_candidates: str = 'all_to_all',
+                 sampled_indices_chunk_size: int = 20000, amps_chunk_size: int = 100000, code_version: str = 'new',
+                 matrix_element_chunk_size=np.inf, **kwargs):
+        assert code_version in self.ALLOWED_CODE_VERSIONS
+        self.use_theor_freqs, self.use_tree_for_candidates = use_theor_freqs, use_tree_for_candidates
+        self.sampled_indices_chunk_size, self.amps_chunk_size = sampled_indices_chunk_size, amps_chunk_size
+        self.code_version, self.matrix_element_chunk_size = code_version, matrix_element_chunk_size
+
+
+class MonteCarloEstimator:
+    """CLE:48-62: freqs = counts / sum(counts); mean = values . freqs; var = (values - mean)^2 . freqs (complex square)."""
+
+    def __init__(self, *args, values: pt.Tensor = None, counts: pt.Tensor = None, **kwargs):
+        self.values = values
+        self.freqs = counts / pt.sum(counts)
+        if self.values is not None and self.freqs is not None:
+            self.mean = pt.dot(self.values, self.freqs)
+            self.var = pt.dot(pt.pow(self.values - self.mean, 2), self.freqs)
+        else:
+            self.mean = self.var = None
+
+
+class LocalEnergyResult:
+    def __init__(self, *args, full_e_loc_mc_est: MonteCarloEstimator = None, sample_aware_e_loc_mc_est: MonteCarloEstimator = None,
+                 **kwargs):
+        self.full_e_loc_mc_est, self.sample_aware_e_loc_mc_est = full_e_loc_mc_est, sample_aware_e_loc_mc_est
+
+
+@pt.no_grad()
+def compute_local_energies(wf=None, sampling_result: SamplingResult = None, sampled_amps: pt.Tensor = None, ham=None,
+                           config: LocalEnergyCalculationConfig = None, sample_aware: bool = True, verbose: bool = False):
+    """CLE:75-163.  The reference's code_version='new' has no full (not sample-aware) energy (CLE:93-94) and
+    its 'old' version is the only route to it; here both versions accept both modes and give the same numbers."""
+    config = config if config is not None else LocalEnergyCalculationConfig()
+    if config.use_tree_for_candidates not in ('ham', 'all_to_all', 'trie'):
+        raise ValueError(f'Wrong coupling mode: {config.use_tree_for_candidates}')
+    indices = sampling_result.indices
+    theor_freqs = pt.conj(sampled_amps) * sampled_amps
+    theor_freqs = theor_freqs / pt.sum(theor_freqs)
+    if sample_aware:
+        n_el = wf.masker.symmetries[0].particle_num
+        full, aware, metrics = ham.compute_var_local_energy_proxy(
+            unq_batch_as_base_indices=indices, unq_batch_as_amps=sampled_amps, coupling_method=config.use_tree_for_candidates,
+            chunk_size=config.sampled_indices_chunk_size, alpha_num=n_el // 2, beta_num=n_el // 2,
+            matrix_element_chunk_size=config.matrix_element_chunk_size)
+    else:
+        full, aware, metrics = ham.compute_local_energies(wf=wf, sampled_indices=indices, sampled_amps=sampled_amps, verbose=verbose,
+                                                          sample_aware=False, chunk_size=config.sampled_indices_chunk_size,
+                                                          compute_via_ham_xy_coupling=True, amps_chunk_size=config.amps_chunk_size)
+    full_counts = theor_freqs if config.use_theor_freqs else sampling_result.counts
+    return LocalEnergyResult(full_e_loc_mc_est=MonteCarloEstimator(values=full, counts=full_counts),
+                             sample_aware_e_loc_mc_est=MonteCarloEstimator(values=aware, counts=theor_freqs)), metrics
+
+
+def vmc_loss(sampled_amps: pt.Tensor, estimator: MonteCarloEstimator) -> pt.Tensor:
+    """EXP:609: 2 Re sum_i f_i log(conj psi_i) (E_i - <E>); its gradient is the energy gradient."""
+    return 2 * (estimator.freqs * pt.log(pt.conj(sampled_amps)) * (estimator.values - estimator.mean)).sum().real

@@ -312,7 +312,7 @@ class PauliObservable(AbstractHilbertSpaceObject):
             hc = 1 if self.weights_real else 2
             h_ptr = _lib.dptr(H) if hc == 1 else _lib.dptr(pt.view_as_real(H))
             m = xp.shape[0]
-            cur.candidate_x_primes_num = m
+            cur.candidate_x_primes_num = (hi - lo) * self.unq_xy_masks_num  # pre-filter count, as PO:1006 reports it
             ptr = pt.empty(m, dtype=pt.int64, device=dev)
             _lib.check(lib.anqs_hash_probe(_lib.dptr(table.slots), table.capacity, _lib.dptr(xp), m, _lib.dptr(ptr), _lib.dptr(None), sp))
             # sampled part: E_s[i] = sum H psi(x') / psi(x_i)   (PO:1048-1057)

@@ -264,7 +264,61 @@ def make_anqs():
     _anqs_case('anqs_n14', 14, 10, 100, 10 ** 5, 500, seed=3)
 
 
-GROUPS = {'ham': make_ham, 'anqs': make_anqs}
+# ---- one whole VMC iteration (EXP:626-679 without SR): sample -> amplitudes -> local energies -> loss -> backward ----
+def _vmc_case(name, n, n_el, n_irreps, sample_num, seed):
+    xy, yz, w = synthetic.synthetic_hamiltonian(n, n_irreps=n_irreps, seed=seed)
+    terms = synthetic.pauli_arrays_to_terms(xy, yz, w, n)
+    tmp = tempfile.mkdtemp(prefix='anqs_golden_')
+    try:
+        o = ref_shim.build_reference_objects(terms, n, n_el, tmp)
+        ref, wf, ham = o.ref, o.wf, o.ham
+        Q, DM = wf.qubit_grouping.qudit_num, int(max(wf.qubit_grouping.qudit_dims))
+        load_weights_into(wf, made_weights(n, Q, DM, seed=seed))
+        out = dict(qubit_num=n, particle_num=n_el, n_irreps=n_irreps, ham_seed=seed, weight_seed=seed, sample_num=sample_num)
+        # sampling through calculations.sample (SMP:51-101), count splitting with the deterministic binomial stand-in
+        real_binomial = torch.distributions.Binomial
+        torch.distributions.Binomial = _RintBinomial
+        try:
+            res, _, _, _ = ref.sample(wf=wf, config=ref.SamplingConfig(sample_indices=False, sample_num=sample_num))
+        finally:
+            torch.distributions.Binomial = real_binomial
+        indices, perm = wf.sort_base_idx(res.indices)                       # EXP:511
+        counts = res.counts[perm]
+        out.update(indices=indices.numpy().reshape(-1), counts=counts.numpy().real)
+        # compute_loss (EXP:548-611) with loss_type='sample_aware_e_loc', coupling 'ham'
+        wf.zero_grad()
+        amps = wf.amplitude(indices)
+        sr = ref.SamplingResult(indices=indices, counts=counts)
+        cfg = ref.LocalEnergyCalculationConfig(use_tree_for_candidates='ham')
+        le, _ = ref.compute_local_energies(wf=wf, sampling_result=sr, sampled_amps=amps.detach(), ham=ham, config=cfg, sample_aware=True)
+        est = le.sample_aware_e_loc_mc_est
+        loss = 2 * (est.freqs * torch.log(torch.conj(amps)) * (est.values - est.mean)).sum().real   # EXP:609
+        loss.backward()
+        grad = wf.cat_grad.numpy()
+        proj = np.random.default_rng(seed + 3).standard_normal((16, grad.shape[0]))
+        out.update(amps=amps.detach().numpy(), eloc=est.values.numpy(), energy_mean=complex(est.mean), energy_var=complex(est.var),
+                   loss=float(loss), grad_proj=proj @ grad, grad_norm=float(np.linalg.norm(grad)), grad_head=grad[:64].copy(),
+                   grad_tail=grad[-64:].copy())
+        # the full (not sample-aware) local energy through the old code path (CLE:117-163 -> PO:326-393, 992-1105)
+        cfg_old = ref.LocalEnergyCalculationConfig(use_tree_for_candidates='ham', code_version='old')
+        le_full, metrics = ref.compute_local_energies(wf=wf, sampling_result=sr, sampled_amps=amps.detach(), ham=ham, config=cfg_old,
+                                                      sample_aware=False)
+        out.update(eloc_full=le_full.full_e_loc_mc_est.values.numpy(), eloc_full_aware=le_full.sample_aware_e_loc_mc_est.values.numpy(),
+                   full_energy_mean=complex(le_full.full_e_loc_mc_est.mean),
+                   non_sampled_unq=int(metrics.non_sampled_unq_x_primes_num), candidates=int(metrics.candidate_x_primes_num))
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f'{name}.npz'), **out)
+        print(f'{name}: N_unq={indices.shape[0]} <E>={complex(est.mean):.6f} full <E>={complex(le_full.full_e_loc_mc_est.mean):.6f} '
+              f'loss={float(loss):.6e} non-sampled unique x\'={int(metrics.non_sampled_unq_x_primes_num)}')
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def make_vmc():
+    _vmc_case('vmc_n12', 12, 4, 1, 300, seed=0)          # C1 shape (LiH STO-3G): 12 qubits, 4 electrons
+    _vmc_case('vmc_n20', 20, 14, 1, 20000, seed=1)       # C3 shape (N2 STO-3G): 20 qubits, 14 electrons, T = 14 251
+
+
+GROUPS = {'ham': make_ham, 'anqs': make_anqs, 'vmc': make_vmc}
 
 
 def main(argv):
