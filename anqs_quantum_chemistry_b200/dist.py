@@ -41,16 +41,18 @@ def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None):
     dist.all_reduce(sizes, group=group)
     sizes_h = sizes.cpu().tolist()
     cap = max(sizes_h)
-    # one packed buffer per rank: [idx as 1 double-width word | re | im] = 3 x 8 bytes per sample
-    packed = pt.zeros((cap, 3), dtype=pt.float64, device=dev)
-    packed[:local_idx.shape[0], 0] = local_idx.view(pt.float64)
-    packed[:local_idx.shape[0], 1:] = pt.view_as_real(local_amps)
-    out = pt.empty((world, cap, 3), dtype=pt.float64, device=dev)
+    # one packed buffer per rank, three planes of `cap` doubles: [index bits | re | im] = 24 bytes per sample
+    n_loc = local_idx.shape[0]
+    packed = pt.zeros((3, cap), dtype=pt.float64, device=dev)
+    packed[0, :n_loc] = local_idx.view(pt.float64)
+    packed[1, :n_loc] = local_amps.real
+    packed[2, :n_loc] = local_amps.imag
+    out = pt.empty((world, 3, cap), dtype=pt.float64, device=dev)
     dist.all_gather_into_tensor(out.view(-1), packed.view(-1), group=group)
     parts_idx, parts_amp = [], []
     for r, sz in enumerate(sizes_h):
-        parts_idx.append(out[r, :sz, 0].contiguous().view(pt.int64))
-        parts_amp.append(pt.view_as_complex(out[r, :sz, 1:].contiguous()))
+        parts_idx.append(out[r, 0, :sz].clone().view(pt.int64))
+        parts_amp.append(pt.complex(out[r, 1, :sz], out[r, 2, :sz]))
     lo = sum(sizes_h[:rank])
     return pt.cat(parts_idx), pt.cat(parts_amp), lo, lo + sizes_h[rank]
 
