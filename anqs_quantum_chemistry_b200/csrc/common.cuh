@@ -87,7 +87,7 @@ struct Tables {
 // ---- sampled-set lookup table (kernel family 2) ------------------------------------------------------
 // Memory layout of the caller-allocated buffer (128-byte aligned):
 //   [capacity slots of 32 bytes][dedicated slot for the all-ones key, 32 bytes][header, 96 bytes][filter]
-// The filter is a line-blocked presence filter of 2*capacity bytes (32..64 bits per key, ONE bit set per key):
+// The filter is a line-blocked presence filter of 4*capacity bytes (64..128 bits per key, ONE bit set per key):
 // the 128-byte line is chosen by the ALPHA half of the key (lin LIN_LINE), optionally spread over 2^G lines by
 // G hash bits of the beta half, and the bit inside the line by both halves (LIN_POSA ^ LIN_POSB).  All the hashes
 // are GF(2)-linear, so the fused kernel gets the filter address of x' = x ^ mask with one XOR per candidate, and
@@ -96,6 +96,7 @@ struct Tables {
 // from the occupancy of the lines (k2_hash.cu) and stored in the header.  Keys are stored DE-INTERLEAVED.
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;  // de-interleaving maps all-ones to all-ones
 constexpr int FILTER_MAX_SPREAD_BITS = 6;
+constexpr int FILTER_BYTES_PER_SLOT = 4;  // filter size = 4 * capacity bytes: 64..128 bits per key, ~1.5 % false positives
 struct __align__(32) HashSlot {
     uint64_t key;    // de-interleaved configuration
     long long idx;   // position in the key array (-1 = empty)
@@ -112,7 +113,7 @@ struct HashView {
     const FilterHeader *header;
     const uint8_t *filter;   // nlines * 128 bytes
     uint32_t capmask;        // capacity - 1
-    uint32_t linemask;       // nlines - 1, nlines = capacity / 64
+    uint32_t linemask;       // nlines - 1, nlines = capacity * FILTER_BYTES_PER_SLOT / 128
 };
 inline HashView make_hash_view(const void *d_table, int64_t capacity) {
     HashView hv;
@@ -120,7 +121,7 @@ inline HashView make_hash_view(const void *d_table, int64_t capacity) {
     hv.header = (const FilterHeader *)(hv.slots + capacity + 1);
     hv.filter = (const uint8_t *)(hv.slots + capacity) + 128;
     hv.capmask = (uint32_t)(capacity - 1);
-    hv.linemask = (uint32_t)(capacity / 64 - 1);
+    hv.linemask = (uint32_t)(capacity * FILTER_BYTES_PER_SLOT / 128 - 1);
     return hv;
 }
 

@@ -4,7 +4,7 @@
 // Open-addressing table with linear probing.  One slot is one 32-byte sector
 // {key u64 (de-interleaved), index i64, amp.re f64, amp.im f64}, so a probe that hits returns the amplitude
 // psi(x') from the same sector.  In front of it sits a line-blocked presence filter (layout and rationale in
-// common.cuh): one bit per key, 32..64 bits per key, the 128-byte line chosen by a GF(2)-linear hash of the alpha
+// common.cuh): one bit per key, 64..128 bits per key, the 128-byte line chosen by a GF(2)-linear hash of the alpha
 // half of the key.  The fused local-energy kernel (k1_fused.cu) consults only the filter for ~97 % of its
 // candidates.  The all-ones key is the EMPTY sentinel; a real all-ones key (only possible at qubit_num == 64, or for
 // generic int64 inputs such as -1) lives in a dedicated slot at index `capacity`.
@@ -137,12 +137,12 @@ static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, v
     const uint32_t nlines = hv.linemask + 1;
     // 0xFF over the slots: key = EMPTY, idx = -1; zero header and filter
     ANQS_CUDA(cudaMemsetAsync(slots, 0xFF, (size_t)(capacity + 1) * sizeof(HashSlot), s));
-    ANQS_CUDA(cudaMemsetAsync(hdr, 0, 96 + (size_t)2 * capacity, s));
+    ANQS_CUDA(cudaMemsetAsync(hdr, 0, 96 + (size_t)FILTER_BYTES_PER_SLOT * capacity, s));
     if (n == 0) return 0;
     ANQS_REQUIRE(d_keys, "null key array");
     int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 16);
     if (forced_spread < 0) {
-        // per-line key counts, kept in the (still empty) filter region: nlines * 4 bytes <= 2 * capacity bytes
+        // per-line key counts, kept in the (still empty) filter region: nlines * 4 bytes <= the filter's size
         filter_count_kernel<<<grid, 256, 0, s>>>(d_keys, n, filter_words, hv.linemask);
         ANQS_LAUNCH_CHECK();
     }
@@ -162,7 +162,7 @@ int64_t anqs_hash_capacity(int64_t n) {
     return cap;
 }
 
-size_t anqs_hash_bytes(int64_t capacity) { return (size_t)capacity * sizeof(HashSlot) + 128 + (size_t)2 * capacity; }
+size_t anqs_hash_bytes(int64_t capacity) { return (size_t)capacity * sizeof(HashSlot) + 128 + (size_t)FILTER_BYTES_PER_SLOT * capacity; }
 
 int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                     void *stream) {

@@ -26,9 +26,11 @@ def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None):
-    """Concatenation over ranks (in rank order) of variable-length shards.
-    Returns (global_idx [N] int64, global_amps [N] complex128, lo, hi) with [lo, hi) this rank's rows."""
+def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None, sizes=None):
+    """Concatenation over ranks (in rank order) of the per-rank shards.
+    Returns (global_idx [N] int64, global_amps [N] complex128, lo, hi) with [lo, hi) this rank's rows.
+    `sizes` (shard length of every rank, identical on all ranks) skips the size exchange and its host
+    synchronisation; equal shards are gathered straight into the result with no staging copies."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     local_idx = local_idx.contiguous().view(-1)
     local_amps = local_amps.contiguous().view(-1)
@@ -36,12 +38,22 @@ def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None):
         return local_idx, local_amps, 0, local_idx.shape[0]
     rank = dist.get_rank(group)
     dev = local_idx.device
-    sizes = pt.zeros(world, dtype=pt.int64, device=dev)
-    sizes[rank] = local_idx.shape[0]
-    dist.all_reduce(sizes, group=group)
-    sizes_h = sizes.cpu().tolist()
-    cap = max(sizes_h)
-    # one packed buffer per rank, three planes of `cap` doubles: [index bits | re | im] = 24 bytes per sample
+    if sizes is None:
+        sz = pt.zeros(world, dtype=pt.int64, device=dev)
+        sz[rank] = local_idx.shape[0]
+        dist.all_reduce(sz, group=group)
+        sizes = sz.cpu().tolist()
+    sizes = [int(v) for v in sizes]
+    assert sizes[rank] == local_idx.shape[0]
+    lo = sum(sizes[:rank])
+    cap = max(sizes)
+    if min(sizes) == cap:  # equal shards: two collectives, no packing
+        g_idx = pt.empty(world * cap, dtype=pt.int64, device=dev)
+        g_amps = pt.empty(world * cap, dtype=pt.complex128, device=dev)
+        dist.all_gather_into_tensor(g_idx, local_idx, group=group)
+        dist.all_gather_into_tensor(pt.view_as_real(g_amps).view(-1), pt.view_as_real(local_amps).reshape(-1), group=group)
+        return g_idx, g_amps, lo, lo + cap
+    # ragged shards: one packed buffer per rank, three planes of `cap` doubles [index bits | re | im]
     n_loc = local_idx.shape[0]
     packed = pt.zeros((3, cap), dtype=pt.float64, device=dev)
     packed[0, :n_loc] = local_idx.view(pt.float64)
@@ -50,11 +62,10 @@ def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None):
     out = pt.empty((world, 3, cap), dtype=pt.float64, device=dev)
     dist.all_gather_into_tensor(out.view(-1), packed.view(-1), group=group)
     parts_idx, parts_amp = [], []
-    for r, sz in enumerate(sizes_h):
+    for r, sz in enumerate(sizes):
         parts_idx.append(out[r, 0, :sz].clone().view(pt.int64))
         parts_amp.append(pt.complex(out[r, 1, :sz], out[r, 2, :sz]))
-    lo = sum(sizes_h[:rank])
-    return pt.cat(parts_idx), pt.cat(parts_amp), lo, lo + sizes_h[rank]
+    return pt.cat(parts_idx), pt.cat(parts_amp), lo, lo + sizes[rank]
 
 
 def local_energy_stats(eloc: pt.Tensor, amps: pt.Tensor) -> pt.Tensor:
@@ -80,7 +91,8 @@ def reduce_energy_stats(stats: pt.Tensor, group=None):
 class ShardedLocalEnergy:
     """Sample-aware local energies of a batch that is sharded over the ranks of `group`."""
 
-    def __init__(self, ham, alpha_num: int, beta_num: int, group=None):
+    def __init__(self, ham, alpha_num: int, beta_num: int, group=None, sizes=None):
+        self.sizes = sizes
         self.ham = ham
         self.alpha_num = alpha_num
         self.beta_num = beta_num
@@ -91,7 +103,7 @@ class ShardedLocalEnergy:
         """local_idx [n_r] or [n_r,1] int64, local_amps [n_r] complex128: this rank's shard.
         Returns (E_loc of the local rows, mean, var) with mean/var over the global batch."""
         from .hilbert_space import SampleTable
-        g_idx, g_amps, lo, hi = all_gather_shards(local_idx, local_amps, self.group)
+        g_idx, g_amps, lo, hi = all_gather_shards(local_idx, local_amps, self.group, self.sizes)
         table = SampleTable(g_idx, g_amps)
         eloc, _, _ = self.ham.compute_var_local_energy_proxy(
             unq_batch_as_base_indices=g_idx.view(-1, 1), unq_batch_as_amps=g_amps, coupling_method='ham',

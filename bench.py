@@ -171,6 +171,7 @@ def main():
     tables = ham.tables
     lo, hi = adist.shard_bounds(n_set, world, rank)
     rows = hi - lo
+    shard_sizes = [adist.shard_bounds(n_set, world, r)[1] - adist.shard_bounds(n_set, world, r)[0] for r in range(world)]
 
     h_idx = torch.from_numpy(samples.view(np.int64)[lo:hi].copy()).pin_memory()
     h_amps = torch.from_numpy(amps[lo:hi].copy()).pin_memory()
@@ -181,7 +182,7 @@ def main():
     kern_ms = []
 
     def step(time_kernel=False):
-        g_idx, g_amps, glo, ghi = adist.all_gather_shards(d_idx, d_amps)
+        g_idx, g_amps, glo, ghi = adist.all_gather_shards(d_idx, d_amps, sizes=shard_sizes)
         table = SampleTable(g_idx, g_amps)
         eloc = torch.empty(ghi - glo, dtype=torch.complex128, device=dev)
         sp = _lib.stream_ptr(dev)
@@ -236,7 +237,7 @@ def main():
         idx_d = h_idx.to(dev, non_blocking=True)
         amps_d = h_amps.to(dev, non_blocking=True)
         if world > 1:
-            sle = adist.ShardedLocalEnergy(ham, na, nb)
+            sle = adist.ShardedLocalEnergy(ham, na, nb, sizes=shard_sizes)
             e, m, v = sle(idx_d, amps_d)
         else:
             e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=idx_d.view(-1, 1), unq_batch_as_amps=amps_d,

@@ -41,6 +41,10 @@ def _worker(rank, world, port, n_total, out_dir):
         assert abs(complex(mean) - complex(est.mean)) < 1e-12
         assert abs(complex(var) - complex(est.var)) < 1e-10
         assert abs(float(norm) - float(w.real.sum())) < 1e-9
+        # equal shards with the sizes known up front (no size exchange, no staging)
+        lo2, hi2 = adist.shard_bounds(1000, world, rank)
+        g_idx, g_amps, glo, ghi = adist.all_gather_shards(idx[lo2:hi2].clone(), amps[lo2:hi2].clone(), sizes=[500, 500])
+        assert (glo, ghi) == (lo2, hi2) and torch.equal(g_idx, idx[:1000]) and torch.equal(g_amps, amps[:1000])
         # empty shard on one rank
         e_idx = idx[:0] if rank == 0 else idx
         e_amps = amps[:0] if rank == 0 else amps
