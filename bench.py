@@ -95,6 +95,72 @@ def make_workload(n_rows_total):
     return xy, yz, w, samples, amps
 
 
+def _time_ms(fn, reps=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.mean(ts))
+
+
+def secondary_measurements(ham, hs, d_idx, na, nb, dev):
+    """The other kernels of the path on the same workload (not part of `value`): ordered term enumeration with matrix
+    elements (the materialising path of the full local energy), MADE amplitudes and the count-splitting sampler."""
+    import torch
+    from anqs_quantum_chemistry_b200 import (ParticleNumberSymmetry, SpinHalfProjectionSymmetry, LocallyDecomposableMasker,
+                                             LogAbsPhaseANQS, ANQSConfig, _lib)
+    lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+    out = {}
+    # ---- term enumeration: filter (bitmap) -> scan -> emit (x' int64, H fp64, dest int32) = 20 B per connection
+    n = min(16384, d_idx.shape[0])
+    rows = d_idx[:n].contiguous()
+    conn = ham.connected_configurations(rows, na, nb, with_xy_ptr=False, matrix_elements='real')
+    m = int(conn['xprime'].shape[0])
+    counts, offsets, bitmap_words = conn['counts'], conn['offsets'], ham.bitmap_row_words
+    bitmap = torch.empty(n * bitmap_words, dtype=torch.int32, device=dev)
+    t_filter = _time_ms(lambda: _lib.check(lib.anqs_k1_filter(ham.tables, _lib.dptr(rows), n, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), sp)))
+    t_emit = _time_ms(lambda: _lib.check(lib.anqs_k1_emit(ham.tables, _lib.dptr(rows), n, _lib.dptr(bitmap), _lib.dptr(offsets),
+                                                          _lib.dptr(conn['dest']), _lib.dptr(conn['xprime']), _lib.dptr(None),
+                                                          _lib.dptr(conn['H']), 1, sp)))
+    t_emit_noh = _time_ms(lambda: _lib.check(lib.anqs_k1_emit(ham.tables, _lib.dptr(rows), n, _lib.dptr(bitmap), _lib.dptr(offsets),
+                                                              _lib.dptr(conn['dest']), _lib.dptr(conn['xprime']), _lib.dptr(None),
+                                                              _lib.dptr(None), 0, sp)))
+    algo = 20.0 * m + 8.0 * n + 4.0 * bitmap_words * n * 2
+    out['enumeration'] = {'rows': n, 'connections': m, 'filter_ms': t_filter, 'emit_ms': t_emit, 'emit_without_H_ms': t_emit_noh,
+                          'connections_per_s': m / ((t_filter + t_emit) * 1e-3), 'achieved_gbs': algo / ((t_filter + t_emit) * 1e-3) / 1e9,
+                          'algorithmic_bytes': '20 B per emitted connection (x\' 8 + H 8 + dest 4) + bitmap write and read + 8 B per row',
+                          'bound': 'hbm'}
+    del conn, bitmap
+    # ---- MADE amplitudes (fp64) and the count-splitting sampler at this qubit count
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=na + nb),
+                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    torch.manual_seed(0)
+    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='MADE'))
+    b = min(1 << 18, d_idx.shape[0])
+    x = d_idx[:b].contiguous()
+    with torch.no_grad():
+        t_amp = _time_ms(lambda: wf.amplitude(x.view(-1, 1)), reps=3, warm=1)
+    flops = 2.0 * 2 * (wf.qubit_num * 64 + 64 * 64 + 64 * wf.qudit_num * wf.max_qudit_dim)
+    out['amplitudes'] = {'batch': b, 'ms': t_amp, 'amplitudes_per_s': b / (t_amp * 1e-3), 'dtype': 'f64 (CUDA-core DFMA)',
+                         'tflops_f64': flops * b / (t_amp * 1e-3) / 1e12, 'params': wf.param_num}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    idx, cnt = wf.sample_stats(10 ** 6, seed=1)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out['sample_stats'] = {'samples': 10 ** 6, 'unique': int(idx.shape[0]), 'seconds': dt, 'unique_per_s': idx.shape[0] / dt,
+                           'note': 'untrained MADE (near-uniform): the reference needs 105.7 s for this call on 8 CPU threads (BASELINE.md)'}
+    return out
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference is Python/PyTorch-CPU and cannot travel to the GPU box, so this times the
     oracle port of its 'ham' local-energy path (oracle/anqs_oracle.c, all host threads) on a bounded sample."""
@@ -139,6 +205,7 @@ def main():
     ap.add_argument('--n-unq', type=int, default=1 << 20, help='unique samples (rows) per GPU')
     ap.add_argument('--cpu-rows', type=int, default=4096, help='rows per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary kernel measurements')
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == 'reference' or os.environ.get('ANQS_BENCH_ALLOW_SHORT'), 'need >= 3 warm-up steps'
 
@@ -258,6 +325,8 @@ def main():
     _lib.check(lib.anqs_k1_filter(tables, _lib.dptr(d_idx), counts.shape[0], na, nb, _lib.dptr(counts), _lib.dptr(None), _lib.stream_ptr(dev)))
     conn_per_row = float(counts.double().mean().item())
 
+    extras = secondary_measurements(ham, hs, d_idx, na, nb, dev) if (rank == 0 and not args.no_extras) else None
+
     if rank == 0:
         peak, peak_src = load_peaks()
         U, T = ham.unq_xy_masks_num, ham.term_num
@@ -281,6 +350,11 @@ def main():
                          'algorithmic_bytes': '32 B per probed candidate + 24 B per table sample + 16 B per row + 8U + 16T'},
             'clocks': clock_info,
         }
+        if extras is not None:
+            for v in extras.values():
+                if isinstance(v, dict) and 'achieved_gbs' in v:
+                    v['frac_of_hbm_peak'] = v['achieved_gbs'] / peak
+            line['secondary'] = extras
         if not args.no_cpu_baseline:
             from oracle import hamiltonian_oracle as orc
             tab = orc.Tables(xy, yz, w)
