@@ -198,6 +198,10 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
         self.to(self.device)
         self._param_num = None
         self._next_memo = None
+        self._masked_key = None        # parameter versions right after the MADE masks were last applied
+        self._packed_tc = None         # weights in the tensor cores' operand layout (k3_made_tc.cu)
+        self._packed_key = None
+        self.inference_precision = 'fp64'   # 'tf32': no-grad amplitudes and the samplers' conditionals run on tcgen05
         self.sampler_seed = int(self.rng_seed)
         self._sampler_calls = 0
 
@@ -234,10 +238,22 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
         pt.nn.utils.clip_grad_norm_(self.parameters(), value)
 
     # ---- kernel plumbing ---------------------------------------------------------------------------------------
+    def set_inference_precision(self, precision: str):
+        """'fp64' (default; the reference's precision, every path) or 'tf32' (tcgen05 tensor cores for evaluations that do
+        not need gradients: amplitudes of non-sampled configurations, the samplers' conditional probabilities)."""
+        assert precision in ('fp64', 'tf32')
+        self.inference_precision = precision
+
+    def _param_key(self):
+        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+
     def _descriptor(self) -> _lib.MadeDesc:
         dev = _lib.require_cuda(self.device)
-        self.log_abs_subnet.apply_made_masks_()
-        self.phase_subnet.apply_made_masks_()
+        if self._param_key() != self._masked_key:
+            # MLP:230-233 re-masks on every forward; masking is idempotent, so it is skipped while no parameter changed
+            self.log_abs_subnet.apply_made_masks_()
+            self.phase_subnet.apply_made_masks_()
+            self._masked_key = self._param_key()
         d = _lib.MadeDesc()
         qg = self.qubit_grouping
         d.qubit_num, d.qudit_num, d.max_qudit_dim = self.qubit_num, qg.qudit_num, self.max_qudit_dim
@@ -275,6 +291,30 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
                                                 _lib.dptr(save_h), _lib.dptr(save_p), _lib.stream_ptr(dev)))
         return out, (save_h, save_p)
 
+    def _packed_weights(self, desc):
+        """Weights packed for the tensor-core kernels; repacked when a parameter changed."""
+        dev = self.device
+        if self._packed_tc is None or self._packed_key != self._masked_key:
+            nbytes = int(_lib.lib().anqs_made_tc_packed_bytes(ctypes.byref(desc)))
+            if self._packed_tc is None or self._packed_tc.numel() * 8 < nbytes:
+                self._packed_tc = pt.empty((nbytes + 7) // 8, dtype=pt.int64, device=dev)
+            _lib.check(_lib.lib().anqs_made_tc_pack(ctypes.byref(desc), _lib.dptr(self._packed_tc), _lib.stream_ptr(dev)))
+            self._packed_key = self._masked_key
+        return self._packed_tc
+
+    @pt.no_grad()
+    def log_psi_tc(self, base_idx: pt.Tensor) -> pt.Tensor:
+        """log psi through the tcgen05 kernels (tf32 products, fp32 accumulation); no gradients."""
+        dev = _lib.require_cuda(self.device)
+        idx = base_idx.contiguous().view(-1)
+        B = idx.shape[0]
+        out = pt.empty(B, dtype=pt.complex128, device=dev)
+        desc = self._descriptor()
+        packed = self._packed_weights(desc)
+        _lib.check(_lib.lib().anqs_made_log_psi_tc(ctypes.byref(desc), _lib.dptr(packed), _lib.dptr(idx), B,
+                                                   _lib.dptr(pt.view_as_real(out)), _lib.stream_ptr(dev)))
+        return out
+
     def chosen_outcomes(self, idx: pt.Tensor) -> pt.Tensor:
         """[B, Q] local outcome index of every qudit (QG:148-154) straight from the packed word."""
         starts = pt.tensor(self.qudit_starts, dtype=pt.int64, device=idx.device)
@@ -284,6 +324,8 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
     # ---- reference surface ---------------------------------------------------------------------------------------
     def log_psi_of_indices(self, base_idx: pt.Tensor) -> pt.Tensor:
         idx = base_idx.contiguous().view(-1)
+        if self.inference_precision == 'tf32' and not pt.is_grad_enabled():
+            return self.log_psi_tc(idx)
         return _MadeLogPsi.apply(self, idx, *list(self.parameters()))
 
     def log_psi(self, base_vec: pt.Tensor, just_return: bool = False) -> pt.Tensor:
@@ -314,8 +356,13 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
         B = prefix_idx.shape[0]
         out = pt.empty((B, self.max_qudit_dim), dtype=pt.float64, device=dev)
         desc = self._descriptor()
-        _lib.check(_lib.lib().anqs_made_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
-                                                     _lib.stream_ptr(dev)))
+        if self.inference_precision == 'tf32':
+            packed = self._packed_weights(desc)
+            _lib.check(_lib.lib().anqs_made_cond_log_abs_tc(ctypes.byref(desc), _lib.dptr(packed), qudit_idx, _lib.dptr(prefix_idx), B,
+                                                            _lib.dptr(out), _lib.stream_ptr(dev)))
+        else:
+            _lib.check(_lib.lib().anqs_made_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
+                                                         _lib.stream_ptr(dev)))
         return out
 
     # ---- samplers ------------------------------------------------------------------------------------------------

@@ -155,6 +155,19 @@ int anqs_made_log_psi(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_
 int anqs_made_cond_log_abs(const anqs_made_desc_t *desc, int qudit_idx, const int64_t *d_prefix, int64_t n,
                            double *d_cond, void *stream);
 
+/* ---- A9  kernel 3, tensor-core mode: the same two functions with every GEMM on tcgen05 (kind::tf32, fp32 accumulate in
+ * TMEM) and fp32 epilogue math.  Inference only (no activations are saved); agreement with the fp64 entry points above
+ * is ~1e-3 in log|psi| and ~1e-2 rad in the phase (tf32 products carry 10 mantissa bits), see tests/test_gpu_anqs.py.
+ * The weights are first packed into the tensor cores' shared-memory operand layout: anqs_made_tc_pack must be called
+ * again whenever a weight changes.  d_packed: anqs_made_tc_packed_bytes(desc) bytes, 128-byte aligned.
+ * Requires width == 64 and max_qudit_dim <= 64 like the fp64 kernels. */
+size_t anqs_made_tc_packed_bytes(const anqs_made_desc_t *desc);
+int anqs_made_tc_pack(const anqs_made_desc_t *desc, void *d_packed, void *stream);
+int anqs_made_log_psi_tc(const anqs_made_desc_t *desc, const void *d_packed, const int64_t *d_idx, int64_t n,
+                         double *d_log_psi, void *stream);
+int anqs_made_cond_log_abs_tc(const anqs_made_desc_t *desc, const void *d_packed, int qudit_idx, const int64_t *d_prefix,
+                              int64_t n, double *d_cond, void *stream);
+
 /* ---- A11  kernel 4: one level of the count-splitting batch sampler (ANQS:593-662) ----------------------
  * Parents i = 0..n-1 carry a packed prefix, a count (double, exact below 2^53), and a memo index.
  * split:  d_child_counts[i][D] (D = 2^qubits_in_qudit) = exact multinomial split of d_counts[i] with

@@ -236,3 +236,71 @@ def test_empty_and_ragged_batches():
         a65 = wf.amplitude(x)
         a1 = torch.cat([wf.amplitude(x[i:i + 1]) for i in range(65)])
     assert torch.equal(a65, a1)   # tile boundaries (64 samples per tile) do not change results
+
+
+# ---- tensor-core (tcgen05, tf32) inference mode ---------------------------------------------------------------------
+TC_TOL_LOG_ABS, TC_TOL_PHASE = 2e-2, 1e-1   # absolute, on log|psi| and arg psi (rad); tf32 products carry 10 mantissa bits
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_tensor_core_log_psi_within_tolerance(name):
+    g, masks, nets, wf = setup_case(name)
+    s = _dev(g['samples']).view(-1, 1)
+    nphys = int(g['n_phys'])
+    lp = wf.log_psi_tc(s).cpu().numpy()
+    ref = g['log_psi']
+    assert np.array_equal(np.isneginf(lp.real), np.isneginf(ref.real))          # unphysical configurations exactly
+    assert np.abs(lp.real[:nphys] - ref.real[:nphys]).max() < TC_TOL_LOG_ABS
+    assert np.abs(lp.imag[:nphys] - ref.imag[:nphys]).max() < TC_TOL_PHASE
+    # typical error is far below the bound
+    assert np.abs(lp.real[:nphys] - ref.real[:nphys]).mean() < 5e-3
+    # routing: no-grad amplitudes use the tensor cores once the mode is switched on; gradients stay fp64
+    wf.set_inference_precision('tf32')
+    with torch.no_grad():
+        amp = wf.amplitude(s).cpu().numpy()
+    assert np.abs(amp - np.exp(lp)).max() < 1e-14
+    lp64 = wf.log_psi_of_indices(s[:nphys])
+    assert lp64.requires_grad and np.abs(lp64.detach().cpu().numpy() - ref[:nphys]).max() < 1e-10
+
+
+@pytest.mark.parametrize('name', ['anqs_n12', 'anqs_n56'])
+def test_tensor_core_cond_log_abs_and_sampling(name):
+    g, masks, nets, wf = setup_case(name)
+    nphys = int(g['n_phys'])
+    s = _dev(g['samples'][:nphys])
+    wf.set_inference_precision('tf32')
+    for key in [k for k in g if k.startswith('cond_log_abs_q')]:
+        q = int(key.split('q')[-1])
+        c = wf.cond_log_abs(qudit_idx=q, prefix_idx=s).cpu().numpy()
+        ref = g[key]
+        assert np.array_equal(np.isneginf(c), np.isneginf(ref))                 # masks are exact
+        fin = ~np.isneginf(ref)
+        assert np.abs(c[fin] - ref[fin]).max() < TC_TOL_LOG_ABS
+        assert np.abs(np.exp(2 * c).sum(axis=1) - 1.0).max() < 1e-5              # conditionals stay normalised
+    idx, cnt = wf.sample_stats(10 ** 5, seed=3)
+    c = cnt.real
+    assert float(c.sum()) == 1e5 and float(c.min()) >= 1.0
+    x = idx.view(-1)
+    ne = int(g['particle_num']) // 2
+    hs = wf.hilbert_space
+    assert bool((hs.popcount(x & 0x5555555555555555) == ne).all()) and bool((hs.popcount(x & ~0x5555555555555555) == ne).all())
+
+
+def test_tensor_core_batch_shapes_and_repack():
+    """Tile boundaries (128 samples per CTA tile), empty batch, and repacking after a parameter update."""
+    hs, masker, wf = build(20, 14)
+    x = _dev(synthetic.random_physical_samples(20, 7, 7, 1000, seed=4).view(np.int64)).view(-1, 1)
+    assert wf.log_psi_tc(x[:0]).shape[0] == 0
+    full = wf.log_psi_tc(x)
+    for b in (1, 127, 128, 129, 333):
+        assert torch.equal(wf.log_psi_tc(x[:b]), full[:b])
+    with torch.no_grad():
+        ref = wf.log_psi_of_indices(x)
+    assert (full.real - ref.real).abs().max() < TC_TOL_LOG_ABS and (full.imag - ref.imag).abs().max() < TC_TOL_PHASE
+    with torch.no_grad():
+        for p in wf.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+        ref2 = wf.log_psi_of_indices(x)
+    full2 = wf.log_psi_tc(x)
+    assert (full2.real - ref2.real).abs().max() < TC_TOL_LOG_ABS and (full2.imag - ref2.imag).abs().max() < TC_TOL_PHASE
+    assert (full2 - full).abs().max() > 1e-3
