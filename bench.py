@@ -151,6 +151,14 @@ def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     flops = 2.0 * 2 * (wf.qubit_num * 64 + 64 * 64 + 64 * wf.qudit_num * wf.max_qudit_dim)
     out['amplitudes'] = {'batch': b, 'ms': t_amp, 'amplitudes_per_s': b / (t_amp * 1e-3), 'dtype': 'f64 (CUDA-core DFMA)',
                          'tflops_f64': flops * b / (t_amp * 1e-3) / 1e12, 'params': wf.param_num}
+    with torch.no_grad():
+        ref = wf.log_psi_of_indices(x)
+        t_tc = _time_ms(lambda: wf.log_psi_tc(x), reps=3, warm=1)
+        lp = wf.log_psi_tc(x)
+    out['amplitudes_tcgen05'] = {'batch': b, 'ms': t_tc, 'amplitudes_per_s': b / (t_tc * 1e-3), 'dtype': 'tf32 products, f32 accumulate (tcgen05, TMEM)',
+                                 'tflops_tf32': flops * b / (t_tc * 1e-3) / 1e12,
+                                 'max_abs_err_log_abs_vs_f64': float((lp.real - ref.real).abs().max()),
+                                 'max_abs_err_phase_vs_f64': float((lp.imag - ref.imag).abs().max())}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     idx, cnt = wf.sample_stats(10 ** 6, seed=1)
@@ -158,6 +166,13 @@ def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     dt = time.perf_counter() - t0
     out['sample_stats'] = {'samples': 10 ** 6, 'unique': int(idx.shape[0]), 'seconds': dt, 'unique_per_s': idx.shape[0] / dt,
                            'note': 'untrained MADE (near-uniform): the reference needs 105.7 s for this call on 8 CPU threads (BASELINE.md)'}
+    wf.set_inference_precision('tf32')
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    idx, cnt = wf.sample_stats(10 ** 6, seed=1)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out['sample_stats_tcgen05'] = {'samples': 10 ** 6, 'unique': int(idx.shape[0]), 'seconds': dt, 'unique_per_s': idx.shape[0] / dt}
     return out
 
 
