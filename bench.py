@@ -111,6 +111,55 @@ def _time_ms(fn, reps=5, warm=2):
     return float(np.mean(ts))
 
 
+def vmc_iteration_rate(dev, n=20, n_el=14, sample_num=10 ** 4, iters=20):
+    """VMC iterations/s (the second half of BASELINE.json's metric) on the C3 shape the reference was timed on in
+    BASELINE.md section 2: 20 qubits, 14 electrons, dense synthetic H (T = 14 251), MADE LogAbsPhaseANQS, Gumbel unique
+    sampling of 1e4 configurations, sample-aware local energies, loss EXP:609, backward, Adam step (EXP:626-679 without
+    stochastic reconfiguration, which is out of scope this round)."""
+    import torch
+    from anqs_quantum_chemistry_b200 import (HilbertSpace, PauliObservable, PauliArraysOperator, ParticleNumberSymmetry,
+                                             SpinHalfProjectionSymmetry, LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig,
+                                             SamplingConfig, SamplingResult, sample, LocalEnergyCalculationConfig,
+                                             compute_local_energies, vmc_loss, synthetic)
+    xy, yz, w = synthetic.synthetic_hamiltonian(n, n_irreps=1, seed=0)
+    hs = HilbertSpace(qubit_num=n, device=dev, parent_dir=tempfile.mkdtemp(prefix='anqs_vmc_'), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, n))
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=n_el),
+                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    torch.manual_seed(0)
+    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='MADE'))
+    opt = torch.optim.Adam(wf.parameters(), lr=1e-3)
+    cfg_s = SamplingConfig(sample_indices=True, sample_num=sample_num)
+    cfg_e = LocalEnergyCalculationConfig(use_tree_for_candidates='ham')
+    energies = []
+
+    def one_iter():
+        opt.zero_grad()
+        res, _, _, _ = sample(wf=wf, config=cfg_s)
+        indices, perm = wf.sort_base_idx(res.indices)
+        amps = wf.amplitude(indices)
+        le, _ = compute_local_energies(wf=wf, sampling_result=SamplingResult(indices=indices, counts=res.counts[perm]),
+                                       sampled_amps=amps.detach(), ham=ham, config=cfg_e, sample_aware=True)
+        est = le.sample_aware_e_loc_mc_est
+        loss = vmc_loss(amps, est)
+        loss.backward()
+        opt.step()
+        return est.mean, indices.shape[0]
+
+    for _ in range(3):
+        one_iter()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        e, n_unq = one_iter()
+        energies.append(e)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {'iters_per_s': iters / dt, 'ms_per_iter': 1e3 * dt / iters, 'n_unq': int(n_unq), 'qubits': n, 'electrons': n_el,
+            'terms': int(ham.term_num), 'energy_first': float(energies[0].real), 'energy_last': float(energies[-1].real),
+            'note': 'reference on 8 CPU threads: 0.17 it/s (MADE, ham) to 0.37 it/s (NADE, trie) at this size, incl. SR (BASELINE.md section 2)'}
+
+
 def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     """The other kernels of the path on the same workload (not part of `value`): ordered term enumeration with matrix
     elements (the materialising path of the full local energy), MADE amplitudes and the count-splitting sampler."""
@@ -166,6 +215,7 @@ def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     dt = time.perf_counter() - t0
     out['sample_stats'] = {'samples': 10 ** 6, 'unique': int(idx.shape[0]), 'seconds': dt, 'unique_per_s': idx.shape[0] / dt,
                            'note': 'untrained MADE (near-uniform): the reference needs 105.7 s for this call on 8 CPU threads (BASELINE.md)'}
+    out['vmc_iteration'] = vmc_iteration_rate(dev)
     wf.set_inference_precision('tf32')
     torch.cuda.synchronize()
     t0 = time.perf_counter()
