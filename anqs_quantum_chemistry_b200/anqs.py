@@ -376,44 +376,59 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
         start = np.array([[sym.start_eig for sym in self.masker.symmetries]], dtype=np.int64)
         return int(self.masker.acc_eigs2memo_idx_np(start)[0])
 
+    def _sampler_seed(self, seed, salt=0):
+        if seed is None:
+            seed = (self.sampler_seed * 0x9E3779B97F4A7C15 + salt + self._sampler_calls) & 0xFFFFFFFFFFFFFFFF
+            self._sampler_calls += 1
+        return seed
+
+    @pt.no_grad()
+    def sample_stats_level(self, q: int, prefix: pt.Tensor, counts: pt.Tensor, memo: pt.Tensor, mode: int, seed: int):
+        """One level of ANQS:593-662 for the live nodes (prefix int64 [B], counts float64 [B], memo int32 [B]): conditional
+        probabilities of qudit q, exact multinomial split of every count, ordered compaction of the surviving children.
+        The binomial draws are keyed by the node's packed prefix, so a level gives the same children no matter how its
+        nodes are spread over calls, ranks or GPUs."""
+        dev = _lib.require_cuda(self.device)
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        qg = self.qubit_grouping
+        B = prefix.shape[0]
+        k, D = qg.qubits_per_qudit[q], qg.qudit_dims_host[q]
+        cont_q, next_q = self._level_tables(q)
+        cond = self.cond_log_abs(qudit_idx=q, prefix_idx=prefix)
+        child = pt.empty((B, D), dtype=pt.float64, device=dev)
+        n_child = pt.empty(B, dtype=pt.int64, device=dev)
+        _lib.check(lib.anqs_sampler_split_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(counts), _lib.dptr(memo),
+                                                _lib.dptr(cont_q), self.masker.memo_size, B, q, mode, seed, 0, _lib.dptr(prefix),
+                                                _lib.dptr(child), _lib.dptr(n_child), sp))
+        offsets = pt.empty(B + 1, dtype=pt.int64, device=dev)
+        work = pt.empty(max(1, int(lib.anqs_scan_workspace(B)) // 8), dtype=pt.int64, device=dev)
+        _lib.check(lib.anqs_exclusive_scan_i64(_lib.dptr(n_child), _lib.dptr(offsets), B, _lib.dptr(work), sp))
+        total = int(offsets[-1].item())
+        new_prefix = pt.empty(total, dtype=pt.int64, device=dev)
+        new_counts = pt.empty(total, dtype=pt.float64, device=dev)
+        new_memo = pt.empty(total, dtype=pt.int32, device=dev)
+        if total > 0:
+            _lib.check(lib.anqs_sampler_emit_children(_lib.dptr(child), k, qg.qudit_starts[q], _lib.dptr(prefix), _lib.dptr(memo),
+                                                      _lib.dptr(cont_q), _lib.dptr(next_q), self.masker.memo_size, B,
+                                                      _lib.dptr(offsets), _lib.dptr(new_prefix), _lib.dptr(new_counts),
+                                                      _lib.dptr(new_memo), sp))
+        return new_prefix, new_counts, new_memo
+
+    def sample_stats_root(self, sample_num: int):
+        dev = _lib.require_cuda(self.device)
+        return (pt.zeros(1, dtype=pt.int64, device=dev), pt.tensor([float(sample_num)], dtype=pt.float64, device=dev),
+                pt.tensor([self._start_memo_idx()], dtype=pt.int32, device=dev))
+
     @pt.no_grad()
     def sample_stats(self, sample_num: int, draw_mode: str = 'philox', seed: int = None) -> Tuple[pt.Tensor, pt.Tensor]:
         """ANQS:494-525: breadth-first count splitting.  Returns (unique indices [N,1] int64, counts [N] complex128).
         draw_mode 'philox' draws binomials from the counter-based generator (seeded by hilbert_space.rng_seed and a
         per-call counter); 'rint' replaces every draw by its rounded mean (deterministic)."""
-        dev = _lib.require_cuda(self.device)
-        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
-        qg = self.qubit_grouping
-        if seed is None:
-            seed = (self.sampler_seed * 0x9E3779B97F4A7C15 + self._sampler_calls) & 0xFFFFFFFFFFFFFFFF
-            self._sampler_calls += 1
+        seed = self._sampler_seed(seed)
         mode = {'rint': 0, 'philox': 1}[draw_mode]
-        prefix = pt.zeros(1, dtype=pt.int64, device=dev)
-        counts = pt.tensor([float(sample_num)], dtype=pt.float64, device=dev)
-        memo = pt.tensor([self._start_memo_idx()], dtype=pt.int32, device=dev)
-        for q in range(qg.qudit_num):
-            B = prefix.shape[0]
-            k, D = qg.qubits_per_qudit[q], qg.qudit_dims_host[q]
-            cont_q, next_q = self._level_tables(q)
-            cond = self.cond_log_abs(qudit_idx=q, prefix_idx=prefix)
-            child = pt.empty((B, D), dtype=pt.float64, device=dev)
-            n_child = pt.empty(B, dtype=pt.int64, device=dev)
-            _lib.check(lib.anqs_sampler_split_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(counts), _lib.dptr(memo),
-                                                    _lib.dptr(cont_q), self.masker.memo_size, B, q, mode, seed, 0,
-                                                    _lib.dptr(child), _lib.dptr(n_child), sp))
-            offsets = pt.empty(B + 1, dtype=pt.int64, device=dev)
-            work = pt.empty(max(1, int(lib.anqs_scan_workspace(B)) // 8), dtype=pt.int64, device=dev)
-            _lib.check(lib.anqs_exclusive_scan_i64(_lib.dptr(n_child), _lib.dptr(offsets), B, _lib.dptr(work), sp))
-            total = int(offsets[-1].item())
-            new_prefix = pt.empty(total, dtype=pt.int64, device=dev)
-            new_counts = pt.empty(total, dtype=pt.float64, device=dev)
-            new_memo = pt.empty(total, dtype=pt.int32, device=dev)
-            if total > 0:
-                _lib.check(lib.anqs_sampler_emit_children(_lib.dptr(child), k, qg.qudit_starts[q], _lib.dptr(prefix), _lib.dptr(memo),
-                                                          _lib.dptr(cont_q), _lib.dptr(next_q), self.masker.memo_size, B,
-                                                          _lib.dptr(offsets), _lib.dptr(new_prefix), _lib.dptr(new_counts),
-                                                          _lib.dptr(new_memo), sp))
-            prefix, counts, memo = new_prefix, new_counts, new_memo
+        prefix, counts, memo = self.sample_stats_root(sample_num)
+        for q in range(self.qubit_grouping.qudit_num):
+            prefix, counts, memo = self.sample_stats_level(q, prefix, counts, memo, mode, seed)
         return prefix.view(-1, 1), counts.to(BASE_COMPLEX_TYPE)
 
     @pt.no_grad()
@@ -424,9 +439,7 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
         dev = _lib.require_cuda(self.device)
         lib, sp = _lib.lib(), _lib.stream_ptr(dev)
         qg = self.qubit_grouping
-        if seed is None:
-            seed = (self.sampler_seed * 0x9E3779B97F4A7C15 + 0x5bd1e995 + self._sampler_calls) & 0xFFFFFFFFFFFFFFFF
-            self._sampler_calls += 1
+        seed = self._sampler_seed(seed, salt=0x5bd1e995)
         prefix = pt.zeros(1, dtype=pt.int64, device=dev)
         log_prob = pt.zeros(1, dtype=pt.float64, device=dev)
         gumbel = pt.zeros(1, dtype=pt.float64, device=dev)

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32)
 split_level_kernel(const double *__restrict__ cond, int DM, int k, const double *__restrict__ counts,
                    const int32_t *__restrict__ memo_idx, const unsigned long long *__restrict__ cont_mask_q,
                    int64_t memo_size, int64_t B, int level, int draw_mode, uint64_t seed, int64_t parent_offset,
-                   double *__restrict__ child_counts, int64_t *__restrict__ n_children) {
+                   const int64_t *__restrict__ rng_keys, double *__restrict__ child_counts, int64_t *__restrict__ n_children) {
     __shared__ double cum_all[K4_WARPS][66];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *cum = cum_all[warp];
@@ -153,7 +153,9 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
                 if (draw_mode == 0) {
                     left = fmin(cnt, fmax(0.0, rint(cnt * pr)));
                 } else {
-                    const uint64_t parent = (uint64_t)(parent_offset + b);
+                    // key of the node: its packed prefix when given (independent of how nodes are spread over launches,
+                    // ranks or GPUs), else its position
+                    const uint64_t parent = rng_keys ? (uint64_t)rng_keys[b] : (uint64_t)(parent_offset + b);
                     left = binomial_draw(cnt, pr, seed, (uint32_t)parent, (uint32_t)(parent >> 32),
                                          ((uint32_t)level << 16) | ((uint32_t)j << 8) | (uint32_t)lane);
                 }
@@ -291,8 +293,8 @@ extern "C" {
 
 int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits_in_qudit, const double *d_counts,
                              const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n,
-                             int level, int draw_mode, uint64_t seed, int64_t parent_offset, double *d_child_counts,
-                             int64_t *d_n_children, void *stream) {
+                             int level, int draw_mode, uint64_t seed, int64_t parent_offset, const int64_t *d_rng_keys,
+                             double *d_child_counts, int64_t *d_n_children, void *stream) {
     ANQS_REQUIRE(n >= 0, "negative parent count");
     ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6 && (1 << qubits_in_qudit) <= max_qudit_dim && max_qudit_dim <= 64,
                  "qudit must have 1..6 qubits and fit max_qudit_dim <= 64");
@@ -302,7 +304,7 @@ int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits
     int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
     split_level_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d_cond, max_qudit_dim, qubits_in_qudit, d_counts, d_memo_idx, (const unsigned long long *)d_cont_mask_q, memo_size, n,
-        level, draw_mode, seed, parent_offset, d_child_counts, d_n_children);
+        level, draw_mode, seed, parent_offset, d_rng_keys, d_child_counts, d_n_children);
     ANQS_LAUNCH_CHECK();
     return 0;
 }

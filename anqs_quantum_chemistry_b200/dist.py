@@ -110,3 +110,36 @@ class ShardedLocalEnergy:
             alpha_num=self.alpha_num, beta_num=self.beta_num, row_start=lo, row_len=hi - lo, table=table)
         mean, var, _ = reduce_energy_stats(local_energy_stats(eloc, g_amps[lo:hi]), self.group)
         return eloc, mean, var
+
+
+@pt.no_grad()
+def sharded_sample_stats(wf, sample_num: int, seed: int, world_size: int = None, rank: int = None, group=None,
+                         draw_mode: str = 'philox', min_nodes_per_rank: int = 64, gather: bool = True):
+    """Count-splitting batch sampling (ANQS:494-525) with the sampling tree sharded by sub-tree.
+
+    Every rank expands the first levels identically (same seed, same draws - they are keyed by the packed prefix of the
+    node, not by its position) until the level holds at least min_nodes_per_rank * world_size nodes; rank r then keeps
+    the contiguous slice shard_bounds(n_nodes, world_size, r) of that level and expands only its own sub-trees: no
+    communication.  The union over ranks is bit-identical to wf.sample_stats(sample_num, seed=seed) on one GPU, in the
+    same order (sub-trees of a contiguous slice stay contiguous).  With gather=True the (index, count) shards are
+    all-gathered (one collective of 16 B per unique sample) and every rank returns the whole set; otherwise the local shard.
+    world_size / rank default to the process group's (pass them explicitly to emulate ranks in one process)."""
+    if world_size is None:
+        world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mode = {'rint': 0, 'philox': 1}[draw_mode]
+    prefix, counts, memo = wf.sample_stats_root(sample_num)
+    sharded = world_size == 1
+    for q in range(wf.qubit_grouping.qudit_num):
+        if not sharded and prefix.shape[0] >= min_nodes_per_rank * world_size:
+            lo, hi = shard_bounds(prefix.shape[0], world_size, rank)
+            prefix, counts, memo = prefix[lo:hi].contiguous(), counts[lo:hi].contiguous(), memo[lo:hi].contiguous()
+            sharded = True
+        prefix, counts, memo = wf.sample_stats_level(q, prefix, counts, memo, mode, seed)
+    if not sharded:  # the tree never got wide enough: every rank holds everything, keep a slice
+        lo, hi = shard_bounds(prefix.shape[0], world_size, rank)
+        prefix, counts = prefix[lo:hi].contiguous(), counts[lo:hi].contiguous()
+    if gather and world_size > 1 and dist.is_initialized():
+        g_idx, g_cnt, _, _ = all_gather_shards(prefix, pt.complex(counts, pt.zeros_like(counts)), group)
+        return g_idx.view(-1, 1), g_cnt
+    return prefix.view(-1, 1), counts.to(pt.complex128)

@@ -175,13 +175,15 @@ int anqs_made_cond_log_abs_tc(const anqs_made_desc_t *desc, const void *d_packed
  *         tree, most significant outcome bit first (ANQS:557-591); d_n_children[i] = number of children that
  *         are allowed by d_cont_mask_q[memo_idx] and have count > 0 (ANQS:653-660).
  *         draw_mode 0: every binomial draw is replaced by rint(n*p) (deterministic, used for parity tests);
- *         draw_mode 1: Philox4x32-10 binomial variates keyed by (seed; parent_offset+i, level, round, node).
+ *         draw_mode 1: Philox4x32-10 binomial variates keyed by (seed; key_i, level, round, node) with key_i =
+ *         d_rng_keys[i] when given (pass the packed prefixes: the draws then do not depend on how the nodes of a level are
+ *         split over launches, ranks or GPUs) else parent_offset + i.
  * emit:   writes the surviving children in (parent, outcome) order at d_offsets[i] (exclusive scan of
  *         d_n_children): prefix | outcome << qudit_start, count, next memo index (QG:99-108 tables as int32). */
 int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits_in_qudit, const double *d_counts,
                              const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n,
-                             int level, int draw_mode, uint64_t seed, int64_t parent_offset, double *d_child_counts,
-                             int64_t *d_n_children, void *stream);
+                             int level, int draw_mode, uint64_t seed, int64_t parent_offset, const int64_t *d_rng_keys,
+                             double *d_child_counts, int64_t *d_n_children, void *stream);
 int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit, int qudit_start,
                                const int64_t *d_prefix, const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q,
                                const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,

@@ -304,3 +304,20 @@ def test_tensor_core_batch_shapes_and_repack():
     full2 = wf.log_psi_tc(x)
     assert (full2.real - ref2.real).abs().max() < TC_TOL_LOG_ABS and (full2.imag - ref2.imag).abs().max() < TC_TOL_PHASE
     assert (full2 - full).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize('n,ne,samples', [(20, 14, 10 ** 6), (56, 14, 20000)])
+def test_sub_tree_sharded_sampling_is_identical(n, ne, samples):
+    """the count-splitting tree sharded by sub-tree over 1, 2, 3 and 8 (emulated) ranks gives,
+    concatenated in rank order, exactly the single-GPU result - the draws are keyed by the node's prefix."""
+    from anqs_quantum_chemistry_b200 import dist as adist
+    hs, masker, wf = build(n, ne)
+    ref_idx, ref_cnt = wf.sample_stats(samples, seed=77)
+    for world in (1, 2, 3, 8):
+        parts = [adist.sharded_sample_stats(wf, samples, seed=77, world_size=world, rank=r, gather=False, min_nodes_per_rank=4)
+                 for r in range(world)]
+        idx = torch.cat([p[0] for p in parts])
+        cnt = torch.cat([p[1] for p in parts])
+        assert torch.equal(idx, ref_idx) and torch.equal(cnt, ref_cnt), world
+        sizes = [p[0].shape[0] for p in parts]
+        assert min(sizes) > 0
