@@ -12,3 +12,4 @@ from .qubit_grouping import QubitGrouping, QubitGroupingConfig  # noqa: F401
 from .anqs import LogAbsPhaseANQS, ANQSConfig, MLPConfig, LocalSamplingConfig  # noqa: F401
 from .calculations import (SamplingConfig, SamplingResult, sample, LocalEnergyCalculationConfig, MonteCarloEstimator,  # noqa: F401
                            LocalEnergyResult, compute_local_energies, vmc_loss)
+from .transformer_anqs import TransformerANQS, TransformerANQSConfig, TransformerMADE  # noqa: F401

@@ -43,6 +43,8 @@ _SIGNATURES = {
     'anqs_made_tc_pack': (_c_int, [_vp, _vp, _vp]),
     'anqs_made_log_psi_tc': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
     'anqs_made_cond_log_abs_tc': (_c_int, [_vp, _vp, _c_int, _vp, _c_i64, _vp, _vp]),
+    'anqs_transformer_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
+    'anqs_transformer_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
     'anqs_sampler_split_level': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, _c_int, ctypes.c_uint64,
                                           _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_sampler_emit_children': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp]),
@@ -59,6 +61,19 @@ class MadeDesc(ctypes.Structure):
                 ('qudit_starts', ctypes.c_int32 * 65), ('du', ctypes.c_uint8 * 64), ('sym', (ctypes.c_int64 * 8) * 8),
                 ('w_abs', ctypes.c_void_p * 5), ('b_abs', ctypes.c_void_p * 5), ('w_phase', ctypes.c_void_p * 5),
                 ('b_phase', ctypes.c_void_p * 5), ('cont_mask', ctypes.c_void_p), ('memo_size', ctypes.c_int64)]
+
+class TransformerDesc(ctypes.Structure):
+    """anqs_transformer_desc_t (include/anqs_b200.h)."""
+    _fields_ = [('qubit_num', ctypes.c_int32), ('dim', ctypes.c_int32), ('depth', ctypes.c_int32), ('head_num', ctypes.c_int32),
+                ('sym_num', ctypes.c_int32), ('pad0', ctypes.c_int32), ('pad1', ctypes.c_int32), ('pad2', ctypes.c_int32),
+                ('sym', (ctypes.c_int64 * 8) * 8), ('tok_emb', ctypes.c_void_p), ('pos_emb', ctypes.c_void_p),
+                ('in_proj_w', ctypes.c_void_p * 4), ('in_proj_b', ctypes.c_void_p * 4), ('out_proj_w', ctypes.c_void_p * 4),
+                ('out_proj_b', ctypes.c_void_p * 4), ('lin1_w', ctypes.c_void_p * 4), ('lin1_b', ctypes.c_void_p * 4),
+                ('lin2_w', ctypes.c_void_p * 4), ('lin2_b', ctypes.c_void_p * 4), ('ln1_w', ctypes.c_void_p * 4),
+                ('ln1_b', ctypes.c_void_p * 4), ('ln2_w', ctypes.c_void_p * 4), ('ln2_b', ctypes.c_void_p * 4),
+                ('dec_w', ctypes.c_void_p), ('dec_b', ctypes.c_void_p), ('cont_mask', ctypes.c_void_p),
+                ('memo_size', ctypes.c_int64), ('ln_eps', ctypes.c_double)]
+
 
 # entry points added by later kernel families register themselves here (name -> (restype, argtypes))
 OPTIONAL_SIGNATURES = {}

@@ -24,6 +24,7 @@ from .abstract_hilbert_space_object import AbstractHilbertSpaceObject
 from .constants import BASE_REAL_TYPE, BASE_COMPLEX_TYPE, NEGINF
 from .masker import LocallyDecomposableMasker
 from .qubit_grouping import QubitGrouping, QubitGroupingConfig
+from .sampler import AutoregressiveSamplerMixin, ParameterVectorMixin
 
 LOCAL_SAMPLING_STRATEGIES = ('DU', 'MU')
 
@@ -172,7 +173,7 @@ class _MadeLogPsi(pt.autograd.Function):
         return (None, None) + tuple(grads)
 
 
-class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
+class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, AbstractHilbertSpaceObject, nn.Module):
     def __init__(self, *args, config: ANQSConfig = None, masker: LocallyDecomposableMasker = None, **kwargs):
         AbstractHilbertSpaceObject.__init__(self, *args, **kwargs)
         nn.Module.__init__(self)
@@ -197,45 +198,17 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
         self.phase_subnet = MLP(in_num=self.qubit_num, is_made=True, qubit_grouping=self.qubit_grouping, dtype=self.dtype, config=aux)
         self.to(self.device)
         self._param_num = None
-        self._next_memo = None
         self._masked_key = None        # parameter versions right after the MADE masks were last applied
         self._packed_tc = None         # weights in the tensor cores' operand layout (k3_made_tc.cu)
         self._packed_key = None
         self.inference_precision = 'fp64'   # 'tf32': no-grad amplitudes and the samplers' conditionals run on tcgen05
-        self.sampler_seed = int(self.rng_seed)
-        self._sampler_calls = 0
+        self._init_sampler()
 
     # ---- shapes ------------------------------------------------------------------------------------------------
     qudit_num = property(lambda self: self.qubit_grouping.qudit_num)
     qudit_dims = property(lambda self: self.qubit_grouping.qudit_dims)
     qudit_starts = property(lambda self: self.qubit_grouping.qudit_starts)
     qudit_ends = property(lambda self: self.qubit_grouping.qudit_ends)
-
-    @property
-    def param_num(self):
-        if self._param_num is None:
-            self._param_num = sum(p.numel() for p in self.parameters())
-        return self._param_num
-
-    @property
-    def param_shapes(self):
-        return tuple(p.shape for p in self.parameters())
-
-    @property
-    def cat_grad_splits(self):
-        return tuple(p.numel() for p in self.parameters())
-
-    @property
-    def cat_grad(self):
-        return pt.cat([(p.grad.data if p.grad is not None else pt.zeros_like(p)).reshape(-1) for p in self.parameters()])
-
-    @cat_grad.setter
-    def cat_grad(self, cat_grad: pt.Tensor):
-        for p, g in zip(self.parameters(), pt.split(cat_grad, self.cat_grad_splits)):
-            p.grad = g.reshape(p.shape)
-
-    def clip_grad_norm(self, value: float = None):
-        pt.nn.utils.clip_grad_norm_(self.parameters(), value)
 
     # ---- kernel plumbing ---------------------------------------------------------------------------------------
     def set_inference_precision(self, precision: str):
@@ -364,109 +337,6 @@ class LogAbsPhaseANQS(AbstractHilbertSpaceObject, nn.Module):
             _lib.check(_lib.lib().anqs_made_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
                                                          _lib.stream_ptr(dev)))
         return out
-
-    # ---- samplers ------------------------------------------------------------------------------------------------
-    def _level_tables(self, q: int):
-        qg = self.qubit_grouping
-        if self._next_memo is None:
-            self._next_memo = [pt.from_numpy(np.ascontiguousarray(t.astype(np.int32))).to(self.device) for t in qg.next_memo_host]
-        return qg.cont_mask_words[q], self._next_memo[q]
-
-    def _start_memo_idx(self) -> int:
-        start = np.array([[sym.start_eig for sym in self.masker.symmetries]], dtype=np.int64)
-        return int(self.masker.acc_eigs2memo_idx_np(start)[0])
-
-    def _sampler_seed(self, seed, salt=0):
-        if seed is None:
-            seed = (self.sampler_seed * 0x9E3779B97F4A7C15 + salt + self._sampler_calls) & 0xFFFFFFFFFFFFFFFF
-            self._sampler_calls += 1
-        return seed
-
-    @pt.no_grad()
-    def sample_stats_level(self, q: int, prefix: pt.Tensor, counts: pt.Tensor, memo: pt.Tensor, mode: int, seed: int):
-        """One level of ANQS:593-662 for the live nodes (prefix int64 [B], counts float64 [B], memo int32 [B]): conditional
-        probabilities of qudit q, exact multinomial split of every count, ordered compaction of the surviving children.
-        The binomial draws are keyed by the node's packed prefix, so a level gives the same children no matter how its
-        nodes are spread over calls, ranks or GPUs."""
-        dev = _lib.require_cuda(self.device)
-        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
-        qg = self.qubit_grouping
-        B = prefix.shape[0]
-        k, D = qg.qubits_per_qudit[q], qg.qudit_dims_host[q]
-        cont_q, next_q = self._level_tables(q)
-        cond = self.cond_log_abs(qudit_idx=q, prefix_idx=prefix)
-        child = pt.empty((B, D), dtype=pt.float64, device=dev)
-        n_child = pt.empty(B, dtype=pt.int64, device=dev)
-        _lib.check(lib.anqs_sampler_split_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(counts), _lib.dptr(memo),
-                                                _lib.dptr(cont_q), self.masker.memo_size, B, q, mode, seed, 0, _lib.dptr(prefix),
-                                                _lib.dptr(child), _lib.dptr(n_child), sp))
-        offsets = pt.empty(B + 1, dtype=pt.int64, device=dev)
-        work = pt.empty(max(1, int(lib.anqs_scan_workspace(B)) // 8), dtype=pt.int64, device=dev)
-        _lib.check(lib.anqs_exclusive_scan_i64(_lib.dptr(n_child), _lib.dptr(offsets), B, _lib.dptr(work), sp))
-        total = int(offsets[-1].item())
-        new_prefix = pt.empty(total, dtype=pt.int64, device=dev)
-        new_counts = pt.empty(total, dtype=pt.float64, device=dev)
-        new_memo = pt.empty(total, dtype=pt.int32, device=dev)
-        if total > 0:
-            _lib.check(lib.anqs_sampler_emit_children(_lib.dptr(child), k, qg.qudit_starts[q], _lib.dptr(prefix), _lib.dptr(memo),
-                                                      _lib.dptr(cont_q), _lib.dptr(next_q), self.masker.memo_size, B,
-                                                      _lib.dptr(offsets), _lib.dptr(new_prefix), _lib.dptr(new_counts),
-                                                      _lib.dptr(new_memo), sp))
-        return new_prefix, new_counts, new_memo
-
-    def sample_stats_root(self, sample_num: int):
-        dev = _lib.require_cuda(self.device)
-        return (pt.zeros(1, dtype=pt.int64, device=dev), pt.tensor([float(sample_num)], dtype=pt.float64, device=dev),
-                pt.tensor([self._start_memo_idx()], dtype=pt.int32, device=dev))
-
-    @pt.no_grad()
-    def sample_stats(self, sample_num: int, draw_mode: str = 'philox', seed: int = None) -> Tuple[pt.Tensor, pt.Tensor]:
-        """ANQS:494-525: breadth-first count splitting.  Returns (unique indices [N,1] int64, counts [N] complex128).
-        draw_mode 'philox' draws binomials from the counter-based generator (seeded by hilbert_space.rng_seed and a
-        per-call counter); 'rint' replaces every draw by its rounded mean (deterministic)."""
-        seed = self._sampler_seed(seed)
-        mode = {'rint': 0, 'philox': 1}[draw_mode]
-        prefix, counts, memo = self.sample_stats_root(sample_num)
-        for q in range(self.qubit_grouping.qudit_num):
-            prefix, counts, memo = self.sample_stats_level(q, prefix, counts, memo, mode, seed)
-        return prefix.view(-1, 1), counts.to(BASE_COMPLEX_TYPE)
-
-    @pt.no_grad()
-    def sample_indices_gumbel(self, sample_num: int, seed: int = None, uniforms=None):
-        """ANQS:778-818: stochastic-beam (Gumbel top-k) sampling without replacement.  Returns (indices [N,1],
-        freqs [N] = model probabilities renormalised over the kept set).  `uniforms`, if given, is a callable
-        (level, B, D) -> [B, D] float64 tensor of U(0,1) variates (parity tests)."""
-        dev = _lib.require_cuda(self.device)
-        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
-        qg = self.qubit_grouping
-        seed = self._sampler_seed(seed, salt=0x5bd1e995)
-        prefix = pt.zeros(1, dtype=pt.int64, device=dev)
-        log_prob = pt.zeros(1, dtype=pt.float64, device=dev)
-        gumbel = pt.zeros(1, dtype=pt.float64, device=dev)
-        memo = pt.tensor([self._start_memo_idx()], dtype=pt.int32, device=dev)
-        for q in range(qg.qudit_num):
-            B = prefix.shape[0]
-            k, D = qg.qubits_per_qudit[q], qg.qudit_dims_host[q]
-            cont_q, next_q = self._level_tables(q)
-            cond = self.cond_log_abs(qudit_idx=q, prefix_idx=prefix)
-            out_lp = pt.empty((B, D), dtype=pt.float64, device=dev)
-            out_g = pt.empty((B, D), dtype=pt.float64, device=dev)
-            u = uniforms(q, B, D).to(dev).contiguous() if uniforms is not None else None
-            _lib.check(lib.anqs_sampler_gumbel_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(log_prob), _lib.dptr(gumbel),
-                                                     _lib.dptr(memo), _lib.dptr(cont_q), self.masker.memo_size, B, q, seed, 0,
-                                                     _lib.dptr(u), _lib.dptr(out_lp), _lib.dptr(out_g), sp))
-            flat_g = out_g.view(-1)
-            keep = min(sample_num, flat_g.shape[0])
-            top_g, top_i = pt.sort(flat_g, descending=True, stable=True)   # ANQS:733
-            top_g, top_i = top_g[:keep], top_i[:keep]
-            alive = top_g > -math.inf                                       # masked children (ANQS:804-809 phys_mask)
-            top_g, top_i = top_g[alive], top_i[alive]
-            parent, outcome = top_i // D, top_i % D
-            prefix = prefix[parent] | (outcome << qg.qudit_starts[q])
-            memo = next_q.view(-1)[memo[parent].to(pt.int64) * D + outcome]
-            log_prob, gumbel = out_lp.view(-1)[top_i], top_g
-        log_prob = log_prob - pt.logsumexp(log_prob, dim=0)
-        return prefix.view(-1, 1), pt.exp(log_prob)
 
     # ---- per-sample log-Jacobian for stochastic reconfiguration (ANQS:820-839) ----------------------------------
     def compute_cat_log_jac(self, indices: pt.Tensor) -> pt.Tensor:

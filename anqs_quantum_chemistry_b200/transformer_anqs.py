@@ -1,0 +1,168 @@
+"""Autoregressive transformer wave function (BASELINE config 3).
+
+Network = the reference's TransformerMADE (nqs/nqs/stochastic/ansatzes/legacy/anqs_primitives/made/transformer_made.py:9-48)
+with the same sub-module names, so `state_dict`s interchange; conditional log-amplitudes as in RealLogPsiTransformerMADE
+(legacy/made/real_log_psi_transformer_made.py:42-58): the decoder's 4 numbers per position are (re, im) of outcome 0 and
+of outcome 1.  The reference's legacy ANQS scaffolding around it is not constructible; here the network
+plugs into the live framework instead: one qubit per qudit, continuation masks from the LocallyDecomposableMasker
+(QG:199-213), masked normalisation re -= 0.5 logsumexp(2 re) (ANQS:392-405), samplers of AbstractANQS (ANQS:494-818).
+
+Compute: inference (amplitudes without gradients, the samplers' conditionals) runs in the hand-written fp64 kernel
+k5_transformer.cu.  When gradients are needed the forward pass is evaluated through the torch module so that autograd can
+differentiate it; both paths agree to 1e-10 (tests/test_gpu_transformer.py).
+"""
+import ctypes
+import math
+
+import torch as pt
+from torch import nn
+
+from . import _lib
+from .abstract_hilbert_space_object import AbstractHilbertSpaceObject
+from .constants import BASE_REAL_TYPE, BASE_COMPLEX_TYPE
+from .masker import LocallyDecomposableMasker
+from .qubit_grouping import QubitGrouping, QubitGroupingConfig
+from .sampler import AutoregressiveSamplerMixin, ParameterVectorMixin
+
+
+class TransformerMADE(nn.Module):
+    """Token + positional embedding, causal post-norm encoder, linear decoder.  Construction order (and therefore the
+    initial weights under a given torch seed) follows transformer_made.py:26-41."""
+
+    def __init__(self, dim: int = None, out_dim: int = None, depth: int = None, qubit_num: int = None, head_num: int = None,
+                 dtype=BASE_REAL_TYPE):
+        super().__init__()
+        self.dim, self.out_dim, self.depth, self.qubit_num, self.head_num, self.dtype = dim, out_dim, depth, qubit_num, head_num, dtype
+        self.pos_embedding = nn.Embedding(qubit_num + 1, dim, dtype=dtype)
+        self.embedding = nn.Embedding(3, dim, dtype=dtype)
+        layer = nn.TransformerEncoderLayer(d_model=dim, nhead=head_num, dim_feedforward=dim, dropout=0.0, batch_first=True, dtype=dtype)
+        self.transformer = nn.TransformerEncoder(encoder_layer=layer, num_layers=depth, enable_nested_tensor=False)
+        self.decoder = nn.Linear(dim, out_dim, dtype=dtype)
+
+    def forward(self, x: pt.Tensor) -> pt.Tensor:
+        """x [B, L] of bits (L <= qubit_num) -> [B, L + 1, out_dim]; position t sees BOS and bits < t."""
+        seq = pt.cat((pt.full((x.shape[0], 1), 2, dtype=pt.long, device=x.device), x.long()), dim=-1)
+        length = seq.shape[-1]
+        causal = pt.triu(pt.full((length, length), float('-inf'), dtype=self.dtype, device=seq.device), diagonal=1)
+        h = self.embedding(seq) + self.pos_embedding(pt.arange(length, device=seq.device))
+        return self.decoder(self.transformer(h, mask=causal, is_causal=True))
+
+
+class TransformerANQSConfig:
+    def __init__(self, *args, dim: int = 64, depth: int = 2, head_num: int = 4, dtype=BASE_REAL_TYPE, **kwargs):
+        self.dim, self.depth, self.head_num, self.dtype = dim, depth, head_num, dtype
+
+
+class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, AbstractHilbertSpaceObject, nn.Module):
+    def __init__(self, *args, config: TransformerANQSConfig = None, masker: LocallyDecomposableMasker = None, **kwargs):
+        AbstractHilbertSpaceObject.__init__(self, *args, **kwargs)
+        nn.Module.__init__(self)
+        self.config = config if config is not None else TransformerANQSConfig()
+        assert self.config.dtype == BASE_REAL_TYPE
+        assert self.config.dim == 64, 'k5_transformer.cu is built for model dimension 64'
+        self.dtype = self.config.dtype
+        self.masker = masker
+        self.qubit_grouping = QubitGrouping.create(hs=self.hilbert_space, config=QubitGroupingConfig(qubit_per_qudit=1), masker=masker)
+        self.max_qudit_dim = 2
+        self.transformer_made = TransformerMADE(dim=self.config.dim, out_dim=4, depth=self.config.depth, qubit_num=self.qubit_num,
+                                                head_num=self.config.head_num, dtype=self.dtype)
+        self.to(self.device)
+        self._param_num = None
+        self._init_sampler()
+
+    qudit_num = property(lambda self: self.qubit_grouping.qudit_num)
+
+    # ---- kernel plumbing ---------------------------------------------------------------------------------------------------
+    def _descriptor(self) -> _lib.TransformerDesc:
+        dev = _lib.require_cuda(self.device)
+        net = self.transformer_made
+        d = _lib.TransformerDesc()
+        d.qubit_num, d.dim, d.depth, d.head_num, d.sym_num = self.qubit_num, net.dim, net.depth, net.head_num, self.masker.sym_num
+        for s, row in enumerate(self.masker.symmetry_descriptors()):
+            for j, v in enumerate(row):
+                d.sym[s][j] = int(v)
+        keep = []
+
+        def ptr(t):
+            if t is None:
+                return None
+            t = t.data
+            assert t.is_contiguous() and t.dtype == pt.float64 and t.device == dev
+            keep.append(t)
+            return t.data_ptr()
+
+        d.tok_emb, d.pos_emb = ptr(net.embedding.weight), ptr(net.pos_embedding.weight)
+        for l, layer in enumerate(net.transformer.layers):
+            d.in_proj_w[l], d.in_proj_b[l] = ptr(layer.self_attn.in_proj_weight), ptr(layer.self_attn.in_proj_bias)
+            d.out_proj_w[l], d.out_proj_b[l] = ptr(layer.self_attn.out_proj.weight), ptr(layer.self_attn.out_proj.bias)
+            d.lin1_w[l], d.lin1_b[l] = ptr(layer.linear1.weight), ptr(layer.linear1.bias)
+            d.lin2_w[l], d.lin2_b[l] = ptr(layer.linear2.weight), ptr(layer.linear2.bias)
+            d.ln1_w[l], d.ln1_b[l] = ptr(layer.norm1.weight), ptr(layer.norm1.bias)
+            d.ln2_w[l], d.ln2_b[l] = ptr(layer.norm2.weight), ptr(layer.norm2.bias)
+            d.ln_eps = float(layer.norm1.eps)
+        d.dec_w, d.dec_b = ptr(net.decoder.weight), ptr(net.decoder.bias)
+        d.cont_mask = self.qubit_grouping.cont_mask_words.data_ptr()
+        d.memo_size = self.masker.memo_size
+        d._keep = keep
+        return d
+
+    @pt.no_grad()
+    def log_psi_kernel(self, base_idx: pt.Tensor) -> pt.Tensor:
+        dev = _lib.require_cuda(self.device)
+        idx = base_idx.contiguous().view(-1)
+        B = idx.shape[0]
+        out = pt.empty(B, dtype=pt.complex128, device=dev)
+        desc = self._descriptor()
+        _lib.check(_lib.lib().anqs_transformer_log_psi(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(out)),
+                                                       _lib.stream_ptr(dev)))
+        return out
+
+    def log_psi_torch(self, base_idx: pt.Tensor) -> pt.Tensor:
+        """The same function through the torch module (differentiable)."""
+        _lib.require_cuda(self.device)
+        idx = base_idx.contiguous().view(-1, 1)
+        bits = self.base_idx2base_vec(idx)                                           # [B, n]
+        B, n = bits.shape
+        out = self.transformer_made(bits)[:, :n, :].reshape(B, n, 2, 2)            # (outcome, re|im)
+        rolling = self.masker.compute_rolling_acc_eigs(bits)                         # acc. quantum numbers after 0..n qubits
+        words = self.qubit_grouping.cont_mask_words                                  # [n, memo_size] int64 bit words
+        memo = pt.stack([self.masker.acc_eigs2memo_idx(rolling[t]) for t in range(n)], dim=1)   # [B, n]
+        w = words[pt.arange(n, device=bits.device).view(1, n), memo]
+        allowed = pt.stack((w & 1, (w >> 1) & 1), dim=-1).bool()                    # [B, n, 2]
+        re = pt.where(allowed, out[..., 0], pt.full_like(out[..., 0], -math.inf))
+        re = re - 0.5 * pt.logsumexp(2.0 * re, dim=-1, keepdim=True)
+        pick = bits.unsqueeze(-1)
+        log_abs = pt.gather(re, -1, pick).squeeze(-1).sum(dim=-1)
+        phase = pt.gather(out[..., 1], -1, pick).squeeze(-1).sum(dim=-1)
+        return pt.complex(log_abs, phase)
+
+    # ---- reference-style surface -------------------------------------------------------------------------------------------------
+    def log_psi_of_indices(self, base_idx: pt.Tensor) -> pt.Tensor:
+        if pt.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self.log_psi_torch(base_idx)
+        return self.log_psi_kernel(base_idx)
+
+    def log_psi(self, base_vec: pt.Tensor, just_return: bool = False) -> pt.Tensor:
+        return self.log_psi_of_indices(self.base_vec2base_idx(base_vec))
+
+    def amplitude(self, base_idx: pt.Tensor) -> pt.Tensor:
+        return pt.exp(self.log_psi_of_indices(base_idx))
+
+    def forward(self, base_idx: pt.Tensor) -> pt.Tensor:
+        return self.amplitude(base_idx)
+
+    @pt.no_grad()
+    def cond_log_abs(self, qudit_idx: int = None, base_vec: pt.Tensor = None, return_all_if_made: bool = False,
+                     mask: pt.Tensor = None, prefix_idx: pt.Tensor = None) -> pt.Tensor:
+        """[B, 2] normalised conditional log|psi| of qubit `qudit_idx` (-inf where masked)."""
+        dev = _lib.require_cuda(self.device)
+        if prefix_idx is None:
+            prefix_idx = self.hilbert_space.base_vec2base_idx(base_vec).view(-1) if base_vec.shape[-1] > 0 else \
+                pt.zeros(base_vec.shape[0], dtype=pt.int64, device=dev)
+        prefix_idx = prefix_idx.contiguous().view(-1)
+        B = prefix_idx.shape[0]
+        out = pt.empty((B, 2), dtype=pt.float64, device=dev)
+        desc = self._descriptor()
+        _lib.check(_lib.lib().anqs_transformer_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
+                                                            _lib.stream_ptr(dev)))
+        return out

@@ -168,6 +168,35 @@ int anqs_made_log_psi_tc(const anqs_made_desc_t *desc, const void *d_packed, con
 int anqs_made_cond_log_abs_tc(const anqs_made_desc_t *desc, const void *d_packed, int qudit_idx, const int64_t *d_prefix,
                               int64_t n, double *d_cond, void *stream);
 
+/* ---- A9 (config 3)  kernel 5: autoregressive transformer wave function ------------------------------------------------
+ * Architecture of the reference's TransformerMADE (stochastic/ansatzes/legacy/anqs_primitives/made/transformer_made.py:9-48):
+ * token embedding [3][dim] (token 2 = BOS) + positional embedding [qubit_num+1][dim]; `depth` post-norm
+ * nn.TransformerEncoderLayer blocks (in_proj [3 dim][dim] + bias, out_proj, linear1 / linear2 with dim_feedforward = dim and
+ * ReLU, norm1 / norm2); decoder [4][dim] -> (re, im) of outcome 0, (re, im) of outcome 1 per position
+ * (legacy/made/real_log_psi_transformer_made.py:42-58).  All pointers are DEVICE pointers to the float64 torch parameters
+ * (row-major [out][in]).  sym / cont_mask / memo_size as in anqs_made_desc_t with ONE qubit per qudit: cont_mask[t *
+ * memo_size + memo_idx] has bit o set iff outcome o of qubit t keeps the prefix physical.  dim must be 64. */
+typedef struct {
+    int32_t qubit_num, dim, depth, head_num, sym_num, pad0, pad1, pad2;
+    int64_t sym[8][8];
+    const double *tok_emb, *pos_emb;
+    const double *in_proj_w[4], *in_proj_b[4], *out_proj_w[4], *out_proj_b[4];
+    const double *lin1_w[4], *lin1_b[4], *lin2_w[4], *lin2_b[4];
+    const double *ln1_w[4], *ln1_b[4], *ln2_w[4], *ln2_b[4];
+    const double *dec_w, *dec_b;
+    const uint64_t *cont_mask;
+    int64_t memo_size;
+    double ln_eps;
+} anqs_transformer_desc_t;
+
+/* d_log_psi[i] = sum over qubits of the masked, normalised conditional log-amplitude at the chosen outcome (complex128:
+ * log|psi|, arg psi); unphysical configurations give (-inf, 0). */
+int anqs_transformer_log_psi(const anqs_transformer_desc_t *desc, const int64_t *d_idx, int64_t n, double *d_log_psi, void *stream);
+/* d_cond[i][2] = normalised conditional log|psi| of qubit `qubit_idx` for the two outcomes given the first qubit_idx bits of
+ * d_prefix[i] (-inf where the continuation is masked). */
+int anqs_transformer_cond_log_abs(const anqs_transformer_desc_t *desc, int qubit_idx, const int64_t *d_prefix, int64_t n,
+                                  double *d_cond, void *stream);
+
 /* ---- A11  kernel 4: one level of the count-splitting batch sampler (ANQS:593-662) ----------------------
  * Parents i = 0..n-1 carry a packed prefix, a count (double, exact below 2^53), and a memo index.
  * split:  d_child_counts[i][D] (D = 2^qubits_in_qudit) = exact multinomial split of d_counts[i] with

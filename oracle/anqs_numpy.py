@@ -276,3 +276,33 @@ def masked_weights(nets, masks_obj: NumberSpinMasks, depth=2, width=64):
         out.append([w * m for (w, _b), m in zip(layers, mm)])
         out.append([b for (_w, b) in layers])
     return out
+
+
+# ---- transformer conditionals (legacy/made/real_log_psi_transformer_made.py:42-58 + the live masking, one qubit per qudit) ----
+def transformer_log_psi_from_logits(logits, x, masks: NumberSpinMasks):
+    """logits [B, >= n, 4] = (re0, im0, re1, im1) per position (the decoder output of TransformerMADE), x uint64 [B];
+    masks built with qubit_per_qudit=1.  Returns complex128 [B]: sum over qubits of the masked, normalised conditional
+    log-amplitude at the chosen outcome (ANQS:392-405 normalisation; unphysical -> -inf)."""
+    n = masks.n
+    x = np.asarray(x, dtype=np.uint64)
+    out = np.asarray(logits)[:, :n, :].reshape(x.shape[0], n, 2, 2)
+    re = np.zeros(x.shape[0])
+    im = np.zeros(x.shape[0])
+    rows = np.arange(x.shape[0])
+    for t in range(n):
+        mi = masks.memo_idx_of_prefix(x, t)
+        allowed = masks.cont_mask[t][mi]                               # [B, 2]
+        cond = _normalise(out[:, t, :, 0], allowed)
+        bit = ((x >> np.uint64(t)) & np.uint64(1)).astype(np.int64)
+        re = re + cond[rows, bit]
+        im = im + np.where(allowed[rows, bit], out[rows, t, bit, 1], 0.0)
+    im = np.where(np.isneginf(re), 0.0, im)
+    return re + 1j * im
+
+
+def transformer_cond_from_logits(logits, x, t, masks: NumberSpinMasks):
+    """[B, 2] normalised conditional log|psi| of qubit t from the logits at position t."""
+    x = np.asarray(x, dtype=np.uint64)
+    out = np.asarray(logits)[:, t, :].reshape(x.shape[0], 2, 2)
+    mi = masks.memo_idx_of_prefix(x, t)
+    return _normalise(out[:, :, 0], masks.cont_mask[t][mi])

@@ -318,7 +318,36 @@ def make_vmc():
     _vmc_case('vmc_n20', 20, 14, 1, 20000, seed=1)       # C3 shape (N2 STO-3G): 20 qubits, 14 electrons, T = 14 251
 
 
-GROUPS = {'ham': make_ham, 'anqs': make_anqs, 'vmc': make_vmc}
+# ---- transformer network (BASELINE config 3): logits of the reference's own TransformerMADE module -----------------------------
+def _tfm_case(name, n, n_el, depth, head_num, seed, sample_count=64):
+    ref_shim.load_reference()
+    from nqs.stochastic.ansatzes.legacy.anqs_primitives.made.transformer_made import TransformerMADE
+    torch.manual_seed(seed)
+    net = TransformerMADE(dim=64, out_dim=4, depth=depth, qubit_num=n, head_num=head_num, dtype=torch.float64)
+    na = nb = n_el // 2
+    phys = synthetic.random_physical_samples(n, na, nb, sample_count, seed=seed + 1)
+    rng = np.random.default_rng(seed + 2)
+    samples = np.concatenate((phys, rng.integers(0, 2 ** n, size=8, dtype=np.int64).astype(np.uint64)))
+    bits = torch.from_numpy(((samples[:, None] >> np.arange(n, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.int64))
+    net.eval()
+    with torch.no_grad():
+        logits = net(bits)                                  # [B, n + 1, 4]
+        short = net(bits[:, :n // 2])                      # a prefix: what the samplers evaluate at level n // 2
+    out = dict(qubit_num=n, particle_num=n_el, depth=depth, head_num=head_num, seed=seed, samples=samples.view(np.int64),
+               n_phys=phys.shape[0], logits=logits.numpy(), prefix_logits=short.numpy(),
+               param_names=np.array([k for k, _ in net.named_parameters()]),
+               param_checksums=np.array([[float(p.sum()), float((p * p).sum())] for p in net.parameters()]))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f'{name}.npz'), **out)
+    print(f'{name}: P={sum(p.numel() for p in net.parameters())} logits {tuple(logits.shape)}')
+
+
+def make_tfm():
+    _tfm_case('tfm_n20', 20, 14, depth=2, head_num=4, seed=7)     # C3 shape
+    _tfm_case('tfm_n12', 12, 4, depth=1, head_num=8, seed=8)
+    _tfm_case('tfm_n14', 14, 10, depth=3, head_num=2, seed=9)     # head_dim 32: the wide-head path of the kernel
+
+
+GROUPS = {'ham': make_ham, 'anqs': make_anqs, 'vmc': make_vmc, 'tfm': make_tfm}
 
 
 def main(argv):

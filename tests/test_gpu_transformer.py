@@ -1,0 +1,134 @@
+"""GPU parity: the transformer wave-function kernel (k5_transformer.cu, through TransformerANQS and the C ABI) against
+(a) the logits of the reference's own TransformerMADE module + the numpy masking oracle and (b) the torch module it mirrors.
+fp64: 1e-10 on log psi and the conditionals; samplers checked by their invariants."""
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from anqs_quantum_chemistry_b200 import (HilbertSpace, ParticleNumberSymmetry, SpinHalfProjectionSymmetry, LocallyDecomposableMasker,
+                                         TransformerANQS, TransformerANQSConfig, synthetic)
+from oracle import anqs_numpy as onp
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+CASES = ['tfm_n12', 'tfm_n14', 'tfm_n20']
+
+
+def build(n, ne, depth, head_num, seed):
+    hs = HilbertSpace(qubit_num=n, device=DEV, parent_dir=tempfile.mkdtemp(prefix='anqs_tfm_test_'), rng_seed=0)
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=ne),
+                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    wf = TransformerANQS(hilbert_space=hs, masker=masker, config=TransformerANQSConfig(dim=64, depth=depth, head_num=head_num))
+    # the network itself is re-created on the CPU under the golden's seed (device-side init would draw other numbers)
+    from anqs_quantum_chemistry_b200.transformer_anqs import TransformerMADE
+    torch.manual_seed(seed)
+    cpu_net = TransformerMADE(dim=64, out_dim=4, depth=depth, qubit_num=n, head_num=head_num, dtype=torch.float64)
+    wf.transformer_made.load_state_dict(cpu_net.state_dict())
+    return hs, masker, wf
+
+
+def case(name):
+    g = load_golden(name)
+    n, ne = int(g['qubit_num']), int(g['particle_num'])
+    hs, masker, wf = build(n, ne, int(g['depth']), int(g['head_num']), int(g['seed']))
+    return g, onp.NumberSpinMasks(n, ne, qubit_per_qudit=1), wf
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_log_psi_matches_reference_logits(name):
+    g, masks, wf = case(name)
+    x = g['samples'].view(np.uint64)
+    ref = onp.transformer_log_psi_from_logits(g['logits'], x, masks)
+    lp = wf.log_psi_kernel(_dev(g['samples'])).cpu().numpy()
+    nphys = int(g['n_phys'])
+    assert np.array_equal(np.isneginf(lp.real), np.isneginf(ref.real))
+    assert np.abs(lp[:nphys] - ref[:nphys]).max() < 1e-10
+    with torch.no_grad():
+        amp = wf.amplitude(_dev(g['samples']).view(-1, 1)).cpu().numpy()
+    assert np.abs(amp - np.exp(ref)).max() < 1e-10
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_conditionals_match_reference_logits(name):
+    g, masks, wf = case(name)
+    n, nphys = masks.n, int(g['n_phys'])
+    x = g['samples'].view(np.uint64)[:nphys]
+    for t in (0, 1, n // 2, n - 1):
+        logits = (g['prefix_logits'] if t == n // 2 else g['logits'])[:nphys]
+        ref = onp.transformer_cond_from_logits(logits, x, t, masks)
+        c = wf.cond_log_abs(qudit_idx=t, prefix_idx=_dev(x.view(np.int64))).cpu().numpy()
+        assert np.array_equal(np.isneginf(c), np.isneginf(ref))
+        fin = ~np.isneginf(ref)
+        assert np.abs(c[fin] - ref[fin]).max() < 1e-10
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_kernel_matches_torch_path_and_gradients_flow(name):
+    g, masks, wf = case(name)
+    n, ne = masks.n, masks.particle_num
+    x = _dev(synthetic.random_physical_samples(n, ne // 2, ne // 2, 200, seed=5).view(np.int64)).view(-1, 1)
+    lp_k = wf.log_psi_kernel(x)
+    lp_t = wf.log_psi_of_indices(x)            # grad mode on -> torch module
+    assert lp_t.requires_grad
+    assert (lp_k - lp_t.detach()).abs().max() < 1e-10
+    wf.zero_grad()
+    (lp_t.real.sum() + 0.3 * lp_t.imag.sum()).backward()
+    g2 = wf.cat_grad
+    assert g2.shape[0] == wf.param_num and bool(torch.isfinite(g2).all()) and float(g2.abs().max()) > 0
+    # tile boundaries: any batch size gives the same numbers
+    for b in (1, 2, 3, 4, 61):
+        assert torch.equal(wf.log_psi_kernel(x[:b]), lp_k[:b])
+    assert wf.log_psi_kernel(x[:0]).shape[0] == 0
+
+
+def test_normalisation_and_samplers():
+    g, masks, wf = case('tfm_n12')
+    allx = torch.arange(2 ** 12, dtype=torch.int64, device=DEV).view(-1, 1)
+    with torch.no_grad():
+        p = (wf.amplitude(allx).abs() ** 2).cpu().numpy()
+    assert abs(p.sum() - 1.0) < 1e-12 and (p > 0).sum() == 225
+    idx, cnt = wf.sample_stats(10 ** 6, seed=3)
+    c = cnt.real
+    assert float(c.sum()) == 1e6 and 100 < idx.shape[0] <= 225 and float(c.min()) >= 1.0
+    assert bool((p[idx.view(-1).cpu().numpy()] > 0).all())                     # every sampled configuration is physical
+    with torch.no_grad():
+        expect = (wf.amplitude(idx).abs() ** 2) * 1e6
+    big = expect > 20
+    chi2 = float((((c - expect) ** 2) / expect)[big].sum() / big.sum())
+    assert 0.6 < chi2 < 1.5, chi2
+    gi, gf = wf.sample_indices_gumbel(100, seed=4)
+    assert gi.shape[0] == 100 and gi.view(-1).unique().shape[0] == 100 and abs(float(gf.sum()) - 1.0) < 1e-12
+
+
+def test_vmc_iterations_lower_the_energy():
+    """Config 3 end to end at a small size: transformer ansatz, Gumbel unique sampling, sample-aware local energies, loss
+    EXP:609, Adam.  The energy after 30 iterations is below the first one and above the sector's ground state."""
+    from anqs_quantum_chemistry_b200 import (PauliObservable, PauliArraysOperator, SamplingConfig, SamplingResult, sample,
+                                             LocalEnergyCalculationConfig, compute_local_energies, vmc_loss)
+    n, ne = 12, 4
+    xy, yz, w = synthetic.synthetic_hamiltonian(n, n_irreps=1, seed=0)
+    hs, masker, wf = build(n, ne, depth=2, head_num=4, seed=1)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, n))
+    opt = torch.optim.Adam(wf.parameters(), lr=3e-3)
+    energies = []
+    for it in range(30):
+        opt.zero_grad()
+        res, _, _, _ = sample(wf=wf, config=SamplingConfig(sample_indices=True, sample_num=225), seed=100 + it)
+        indices, perm = wf.sort_base_idx(res.indices)
+        amps = wf.amplitude(indices)
+        le, _ = compute_local_energies(wf=wf, sampling_result=SamplingResult(indices=indices, counts=res.counts[perm]),
+                                       sampled_amps=amps.detach(), ham=ham,
+                                       config=LocalEnergyCalculationConfig(use_tree_for_candidates='ham'), sample_aware=True)
+        est = le.sample_aware_e_loc_mc_est
+        vmc_loss(amps, est).backward()
+        opt.step()
+        energies.append(float(est.mean.real))
+    assert energies[-1] < energies[0] - 1e-3
+    assert abs(float(est.mean.imag)) < 1e-9
