@@ -39,6 +39,8 @@ _SIGNATURES = {
     'anqs_accumulate_rows': (_c_int, [_vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_made_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_made_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
+    'anqs_nade_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
+    'anqs_nade_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
     'anqs_made_tc_packed_bytes': (ctypes.c_size_t, [_vp]),
     'anqs_made_tc_pack': (_c_int, [_vp, _vp, _vp]),
     'anqs_made_log_psi_tc': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
@@ -61,6 +63,15 @@ class MadeDesc(ctypes.Structure):
                 ('qudit_starts', ctypes.c_int32 * 65), ('du', ctypes.c_uint8 * 64), ('sym', (ctypes.c_int64 * 8) * 8),
                 ('w_abs', ctypes.c_void_p * 5), ('b_abs', ctypes.c_void_p * 5), ('w_phase', ctypes.c_void_p * 5),
                 ('b_phase', ctypes.c_void_p * 5), ('cont_mask', ctypes.c_void_p), ('memo_size', ctypes.c_int64)]
+
+class NadeDesc(ctypes.Structure):
+    """anqs_nade_desc_t (include/anqs_b200.h)."""
+    _fields_ = [('qubit_num', ctypes.c_int32), ('qudit_num', ctypes.c_int32), ('max_qudit_dim', ctypes.c_int32),
+                ('depth', ctypes.c_int32), ('width', ctypes.c_int32), ('use_res', ctypes.c_int32),
+                ('subtract_mean', ctypes.c_int32), ('sym_num', ctypes.c_int32),
+                ('qudit_starts', ctypes.c_int32 * 65), ('du', ctypes.c_uint8 * 64), ('sym', (ctypes.c_int64 * 8) * 8),
+                ('ptrs', ctypes.c_void_p), ('cont_mask', ctypes.c_void_p), ('memo_size', ctypes.c_int64)]
+
 
 class TransformerDesc(ctypes.Structure):
     """anqs_transformer_desc_t (include/anqs_b200.h)."""

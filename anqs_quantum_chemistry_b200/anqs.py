@@ -51,7 +51,8 @@ class MLPConfig:
 
 
 class ANQSConfig:
-    """ANQS:68-109.  de_mode defaults to 'NADE' in the reference; only 'MADE' is implemented here."""
+    """ANQS:68-109.  The reference's default de_mode is 'NADE' (one MLP pair per qudit); the default here is 'MADE' (one masked
+    network), the mode BASELINE.json's configurations name.  Both are implemented."""
     ALLOWED_DE_MODES = ('MADE', 'NADE')
 
     def __init__(self, *args, dtype=BASE_REAL_TYPE, de_mode: str = 'MADE', qubit_grouping_config: QubitGroupingConfig = None,
@@ -69,21 +70,29 @@ class ANQSConfig:
 
 
 class MLP(nn.Module):
-    """MADE-masked MLP (MLP:102-246): parameters and causal masks only; the forward pass lives in k3_made.cu."""
+    """MLP of the reference (MLP:102-246): parameters (and, in MADE form, the causal masks) only; the forward pass lives in
+    k3_made.cu / k3_nade.cu.  is_made=True: one masked network for all qudits; is_made=False: the plain network of one qudit
+    in NADE mode (in_num inputs, out_num outputs)."""
 
-    def __init__(self, in_num: int = None, is_made: bool = True, qubit_grouping: QubitGrouping = None,
+    def __init__(self, in_num: int = None, is_made: bool = True, qubit_grouping: QubitGrouping = None, out_num: int = None,
                  dtype=BASE_REAL_TYPE, is_out_complex: bool = False, config: MLPConfig = None):
         super().__init__()
-        assert is_made and qubit_grouping is not None, 'only the MADE form (one masked network) is implemented'
         assert dtype == BASE_REAL_TYPE and not is_out_complex
         self.config = config if config is not None else MLPConfig()
         cfg = self.config
         assert cfg.activation is nn.Tanh and not cfg.activate_last_layer, 'the kernels implement tanh hidden / identity output'
-        self.in_num, self.depth, self.dtype = in_num, cfg.depth, dtype
-        self.out_num = qubit_grouping.qudit_num
-        self.val_per_out = max(qubit_grouping.qudit_dims_host)
+        self.in_num, self.depth, self.dtype, self.is_made = in_num, cfg.depth, dtype, is_made
         width = (cfg.width,) * cfg.depth
         in_nums = (in_num,) + width
+        if not is_made:
+            self.out_num, self.val_per_out = out_num, 1
+            self.layers = nn.ModuleList([nn.Linear(in_nums[l], (width + (out_num,))[l], bias=cfg.use_bias, dtype=dtype)
+                                         for l in range(cfg.depth + 1)])
+            self.made_masks = ()
+            return
+        assert qubit_grouping is not None
+        self.out_num = qubit_grouping.qudit_num
+        self.val_per_out = max(qubit_grouping.qudit_dims_host)
         out_nums = width + (self.out_num * self.val_per_out,)
         self.layers = nn.ModuleList([nn.Linear(in_nums[l], out_nums[l], bias=cfg.use_bias, dtype=dtype)
                                      for l in range(cfg.depth + 1)])
@@ -173,16 +182,69 @@ class _MadeLogPsi(pt.autograd.Function):
         return (None, None) + tuple(grads)
 
 
+class _NadeLogPsi(pt.autograd.Function):
+    """NADE-mode log psi; backward by hand from the saved activations, one small chain per (sub-network, qudit)."""
+
+    @staticmethod
+    def forward(ctx, wf, idx, *params):
+        need_grad = any(ctx.needs_input_grad[2:])
+        log_psi, saved = wf._launch_log_psi(idx, save=need_grad)
+        ctx.wf, ctx.saved, ctx.idx = wf, saved, idx
+        ctx.weights = [p.detach() for p in params]
+        return log_psi
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        wf, idx = ctx.wf, ctx.idx
+        save_h, save_p = ctx.saved                      # [2, Q, depth, B, width], [B, Q, DM]
+        B, Q, depth = idx.shape[0], wf.qudit_num, wf.depth
+        g_re, g_im = grad_out.real.contiguous(), grad_out.imag.contiguous()
+        bits = (1.0 - 2.0 * ((idx.view(-1, 1) >> wf.hilbert_space.shifts) & 1).to(pt.float64))   # [B, n]
+        chosen = wf.chosen_outcomes(idx)                                                          # [B, Q]
+        n_layer = depth + 1
+        per_mlp = 2 * n_layer if wf.use_bias else n_layer
+        grads = [None] * len(ctx.weights)
+        rows = pt.arange(B, device=idx.device)
+        for net in range(2):
+            for q in range(Q):
+                base = (net * Q + q) * per_mlp
+                W = [ctx.weights[base + (2 * l if wf.use_bias else l)] for l in range(n_layer)]
+                h = [save_h[net, q, l] for l in range(depth)]
+                start, D = wf.qudit_starts[q], wf.qubit_grouping.qudit_dims_host[q]
+                x = bits[:, :start] if start > 0 else pt.zeros((B, 1), dtype=pt.float64, device=idx.device)
+                if net == 0:
+                    dY = -(g_re.view(-1, 1) * save_p[:, q, :D])
+                    dY[rows, chosen[:, q]] += g_re
+                else:
+                    dY = pt.zeros((B, D), dtype=pt.float64, device=idx.device)
+                    dY[rows, chosen[:, q]] = math.pi * g_im
+                out = [(dY.t() @ h[-1], dY.sum(0))]
+                dh = dY @ W[depth]
+                for l in range(depth - 1, -1, -1):
+                    da = dh * (1.0 - h[l] * h[l])
+                    inp = x if l == 0 else h[l - 1]
+                    out.append((da.t() @ inp, da.sum(0)))
+                    if l > 0:
+                        dh = da @ W[l]
+                        if wf.use_res:
+                            dh = dh + da
+                for l, (gw, gb) in zip(range(depth, -1, -1), out):
+                    if wf.use_bias:
+                        grads[base + 2 * l], grads[base + 2 * l + 1] = gw, gb
+                    else:
+                        grads[base + l] = gw
+        return (None, None) + tuple(grads)
+
+
 class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, AbstractHilbertSpaceObject, nn.Module):
     def __init__(self, *args, config: ANQSConfig = None, masker: LocallyDecomposableMasker = None, **kwargs):
         AbstractHilbertSpaceObject.__init__(self, *args, **kwargs)
         nn.Module.__init__(self)
         self.config = config if config is not None else ANQSConfig()
-        if self.config.de_mode != 'MADE':
-            raise NotImplementedError("anqs_b200 implements de_mode='MADE' (one masked network); 'NADE' is not built")
+        assert self.config.de_mode in ANQSConfig.ALLOWED_DE_MODES
         assert self.config.dtype == BASE_REAL_TYPE
         assert not self.config.use_sign_structure
-        self.dtype, self.de_mode = self.config.dtype, 'MADE'
+        self.dtype, self.de_mode = self.config.dtype, self.config.de_mode
         self.masker = masker
         self.qubit_grouping_config = self.config.qubit_grouping_config
         self.qubit_grouping = QubitGrouping.create(hs=self.hilbert_space, config=self.qubit_grouping_config, masker=masker)
@@ -194,8 +256,18 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
             'the kernel evaluates both sub-networks with one shape'
         self.depth, self.width, self.use_res, self.use_bias = main.depth, main.width, main.use_res, main.use_bias
         # construction order = reference order (LAP:43-56), so the global torch RNG yields the same initial weights
-        self.log_abs_subnet = MLP(in_num=self.qubit_num, is_made=True, qubit_grouping=self.qubit_grouping, dtype=self.dtype, config=main)
-        self.phase_subnet = MLP(in_num=self.qubit_num, is_made=True, qubit_grouping=self.qubit_grouping, dtype=self.dtype, config=aux)
+        if self.de_mode == 'MADE':
+            self.log_abs_subnet = MLP(in_num=self.qubit_num, is_made=True, qubit_grouping=self.qubit_grouping, dtype=self.dtype, config=main)
+            self.phase_subnet = MLP(in_num=self.qubit_num, is_made=True, qubit_grouping=self.qubit_grouping, dtype=self.dtype, config=aux)
+        else:  # LAP:24-42: one plain MLP per qudit, all log-abs networks first, then all phase networks
+            qg = self.qubit_grouping
+            def per_qudit(cfg):
+                return nn.ModuleList([MLP(in_num=qg.qudit_ends[q - 1] if q != 0 else 1, is_made=False, qubit_grouping=qg,
+                                          out_num=qg.qudit_dims_host[q], dtype=self.dtype, config=cfg) for q in range(qg.qudit_num)])
+            self.log_abs_subnet = per_qudit(main)
+            self.phase_subnet = per_qudit(aux)
+        self._ptr_table = None
+        self._ptr_key = None
         self.to(self.device)
         self._param_num = None
         self._masked_key = None        # parameter versions right after the MADE masks were last applied
@@ -215,12 +287,47 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         """'fp64' (default; the reference's precision, every path) or 'tf32' (tcgen05 tensor cores for evaluations that do
         not need gradients: amplitudes of non-sampled configurations, the samplers' conditional probabilities)."""
         assert precision in ('fp64', 'tf32')
+        assert precision == 'fp64' or self.de_mode == 'MADE', 'the tensor-core kernels implement MADE mode'
         self.inference_precision = precision
 
     def _param_key(self):
         return tuple((p._version, p.data_ptr()) for p in self.parameters())
 
-    def _descriptor(self) -> _lib.MadeDesc:
+    def _nade_descriptor(self) -> _lib.NadeDesc:
+        dev = _lib.require_cuda(self.device)
+        d = _lib.NadeDesc()
+        qg = self.qubit_grouping
+        d.qubit_num, d.qudit_num, d.max_qudit_dim = self.qubit_num, qg.qudit_num, self.max_qudit_dim
+        d.depth, d.width, d.use_res = self.depth, self.width, int(self.use_res)
+        d.subtract_mean, d.sym_num = int(self.config.subtract_mean), self.masker.sym_num
+        for q in range(qg.qudit_num):
+            d.qudit_starts[q] = qg.qudit_starts[q]
+            d.du[q] = 1 if self.local_sampling_pattern[q] == 'DU' else 0
+        d.qudit_starts[qg.qudit_num] = self.qubit_num
+        for s, row in enumerate(self.masker.symmetry_descriptors()):
+            for j, v in enumerate(row):
+                d.sym[s][j] = int(v)
+        ptrs, keep = [], []
+        for nets in (self.log_abs_subnet, self.phase_subnet):
+            for mlp in nets:
+                for layer in mlp.layers:
+                    w = layer.weight.data
+                    assert w.is_contiguous() and w.dtype == pt.float64 and w.device == dev
+                    keep.append(w)
+                    ptrs += [w.data_ptr(), layer.bias.data.data_ptr() if layer.bias is not None else 0]
+        key = tuple(ptrs)
+        if self._ptr_key != key:  # the table only changes when a parameter is re-allocated
+            self._ptr_table = pt.tensor(ptrs, dtype=pt.int64, device=dev)
+            self._ptr_key = key
+        d.ptrs = self._ptr_table.data_ptr()
+        d.cont_mask = qg.cont_mask_words.data_ptr()
+        d.memo_size = self.masker.memo_size
+        d._keep = keep
+        return d
+
+    def _descriptor(self):
+        if self.de_mode == 'NADE':
+            return self._nade_descriptor()
         dev = _lib.require_cuda(self.device)
         if self._param_key() != self._masked_key:
             # MLP:230-233 re-masks on every forward; masking is idempotent, so it is skipped while no parameter changed
@@ -257,9 +364,14 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         assert idx.dtype == pt.int64 and idx.dim() == 1 and idx.is_contiguous() and idx.device == dev
         B = idx.shape[0]
         out = pt.empty(B, dtype=pt.complex128, device=dev)
-        save_h = pt.empty((2, self.depth, B, self.width), dtype=pt.float64, device=dev) if save else None
+        h_shape = (2, self.depth, B, self.width) if self.de_mode == 'MADE' else (2, self.qudit_num, self.depth, B, self.width)
+        save_h = pt.empty(h_shape, dtype=pt.float64, device=dev) if save else None
         save_p = pt.empty((B, self.qudit_num, self.max_qudit_dim), dtype=pt.float64, device=dev) if save else None
         desc = self._descriptor()
+        if self.de_mode == 'NADE':
+            _lib.check(_lib.lib().anqs_nade_log_psi(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(out)),
+                                                    _lib.dptr(save_h), _lib.dptr(save_p), _lib.stream_ptr(dev)))
+            return out, (save_h, save_p)
         _lib.check(_lib.lib().anqs_made_log_psi(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(out)),
                                                 _lib.dptr(save_h), _lib.dptr(save_p), _lib.stream_ptr(dev)))
         return out, (save_h, save_p)
@@ -297,6 +409,8 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
     # ---- reference surface ---------------------------------------------------------------------------------------
     def log_psi_of_indices(self, base_idx: pt.Tensor) -> pt.Tensor:
         idx = base_idx.contiguous().view(-1)
+        if self.de_mode == 'NADE':
+            return _NadeLogPsi.apply(self, idx, *list(self.parameters()))
         if self.inference_precision == 'tf32' and not pt.is_grad_enabled():
             return self.log_psi_tc(idx)
         return _MadeLogPsi.apply(self, idx, *list(self.parameters()))
@@ -329,7 +443,10 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         B = prefix_idx.shape[0]
         out = pt.empty((B, self.max_qudit_dim), dtype=pt.float64, device=dev)
         desc = self._descriptor()
-        if self.inference_precision == 'tf32':
+        if self.de_mode == 'NADE':
+            _lib.check(_lib.lib().anqs_nade_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
+                                                         _lib.stream_ptr(dev)))
+        elif self.inference_precision == 'tf32':
             packed = self._packed_weights(desc)
             _lib.check(_lib.lib().anqs_made_cond_log_abs_tc(ctypes.byref(desc), _lib.dptr(packed), qudit_idx, _lib.dptr(prefix_idx), B,
                                                             _lib.dptr(out), _lib.stream_ptr(dev)))
@@ -346,7 +463,7 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         rows = []
         params = list(self.parameters())
         for b in range(B):  # the reference restricts this to max_indices_num = 25..50 samples (SR:20-32)
-            lp = _MadeLogPsi.apply(self, idx[b:b + 1], *params)
+            lp = (_NadeLogPsi if self.de_mode == 'NADE' else _MadeLogPsi).apply(self, idx[b:b + 1], *params)
             g_re = pt.autograd.grad(lp.real.sum(), params, retain_graph=True)
             g_im = pt.autograd.grad(lp.imag.sum(), params)
             rows.append(pt.complex(pt.cat([g.reshape(-1) for g in g_re]), -pt.cat([g.reshape(-1) for g in g_im])))

@@ -155,6 +155,26 @@ int anqs_made_log_psi(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_
 int anqs_made_cond_log_abs(const anqs_made_desc_t *desc, int qudit_idx, const int64_t *d_prefix, int64_t n,
                            double *d_cond, void *stream);
 
+/* ---- A9  kernel 3, NADE mode (ANQS:410-428, LAP:24-42): one (log-abs, phase) MLP pair per qudit --------------------------
+ * Same scalar fields as anqs_made_desc_t.  d_ptrs is a DEVICE array of 2 * qudit_num * (depth + 1) * 2 device pointers:
+ * entry ((net * qudit_num + q) * (depth + 1) + layer) * 2 + {0: weight [out][in], 1: bias or NULL}; net 0 =
+ * log_abs_subnet[q], net 1 = phase_subnet[q]; layer 0 has in = max(1, qudit_starts[q]) inputs (LAP:26), the last layer
+ * out = 2^(qubits of qudit q) outputs.  Differences from MADE mode: the mean is subtracted over the qudit's own
+ * outcomes (LAP:118-119).  d_save_h: [2][qudit_num][depth][n][width], d_save_p: [n][qudit_num][max_qudit_dim]. */
+typedef struct {
+    int32_t qubit_num, qudit_num, max_qudit_dim, depth, width, use_res, subtract_mean, sym_num;
+    int32_t qudit_starts[65];
+    uint8_t du[64];
+    int64_t sym[8][8];
+    const double *const *ptrs;
+    const uint64_t *cont_mask;
+    int64_t memo_size;
+} anqs_nade_desc_t;
+int anqs_nade_log_psi(const anqs_nade_desc_t *desc, const int64_t *d_idx, int64_t n, double *d_log_psi, double *d_save_h,
+                      double *d_save_p, void *stream);
+int anqs_nade_cond_log_abs(const anqs_nade_desc_t *desc, int qudit_idx, const int64_t *d_prefix, int64_t n, double *d_cond,
+                           void *stream);
+
 /* ---- A9  kernel 3, tensor-core mode: the same two functions with every GEMM on tcgen05 (kind::tf32, fp32 accumulate in
  * TMEM) and fp32 epilogue math.  Inference only (no activations are saved); agreement with the fp64 entry points above
  * is ~1e-3 in log|psi| and ~1e-2 rad in the phase (tf32 products carry 10 mantissa bits), see tests/test_gpu_anqs.py.

@@ -306,3 +306,35 @@ def transformer_cond_from_logits(logits, x, t, masks: NumberSpinMasks):
     out = np.asarray(logits)[:, t, :].reshape(x.shape[0], 2, 2)
     mi = masks.memo_idx_of_prefix(x, t)
     return _normalise(out[:, :, 0], masks.cont_mask[t][mi])
+
+
+# ---- NADE mode: one MLP pair per qudit (ANQS:410-428, LAP:24-42, 63-103, 114-134) ---------------------------------------------
+def nade_cond_log_abs(x_prefix, q, masks: NumberSpinMasks, W_abs_q, b_abs_q, use_res=True, subtract_mean=True):
+    """[B, D_q]: W_abs_q / b_abs_q are the layer lists of log_abs_subnet[q].  The first qudit's network sees the constant
+    0.5 pushed through 1 - 2x, i.e. the input 0 (MLP:205-215); the mean is over the qudit's own D_q outcomes (LAP:118-119)."""
+    x_prefix = np.asarray(x_prefix, dtype=np.uint64)
+    start, D = masks.starts[q], masks.dims[q]
+    inp = encode(x_prefix, start) if start > 0 else np.zeros((x_prefix.shape[0], 1))
+    y, _ = mlp_forward(inp, W_abs_q, b_abs_q, use_res)
+    if subtract_mean:
+        y = y - y.mean(axis=-1, keepdims=True)
+    mi = masks.memo_idx_of_prefix(x_prefix, start)
+    return _normalise(y, masks.cont_mask[q][mi])
+
+
+def nade_log_psi(x, masks: NumberSpinMasks, W_abs, b_abs, W_ph, b_ph, use_res=True, subtract_mean=True):
+    """complex128 [B]; W_abs[q] etc. are per-qudit layer lists."""
+    x = np.asarray(x, dtype=np.uint64)
+    re = np.zeros(x.shape[0])
+    im = np.zeros(x.shape[0])
+    rows = np.arange(x.shape[0])
+    for q in range(masks.Q):
+        start, D = masks.starts[q], masks.dims[q]
+        cond = nade_cond_log_abs(x, q, masks, W_abs[q], b_abs[q], use_res, subtract_mean)
+        inp = encode(x, start) if start > 0 else np.zeros((x.shape[0], 1))
+        yp, _ = mlp_forward(inp, W_ph[q], b_ph[q], use_res)
+        c = ((x >> np.uint64(start)) & np.uint64(D - 1)).astype(np.int64)
+        re = re + cond[rows, c]
+        im = im + np.pi * yp[rows, c]
+    im = np.where(np.isneginf(re), 0.0, im)
+    return re + 1j * im

@@ -257,6 +257,67 @@ def _anqs_case(name, n, n_el, sample_count, stats_num, gumbel_num, seed):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def _nade_case(name, n, n_el, sample_count, stats_num, gumbel_num, seed):
+    """NADE mode (the reference's default de_mode): one MLP pair per qudit.  Weights are the reference's own initial weights
+    under pt.manual_seed(seed) - the drop-in reproduces them by constructing its modules in the same order."""
+    tmp = tempfile.mkdtemp(prefix='anqs_golden_')
+    try:
+        o = ref_shim.build_reference_objects(None, n, n_el, tmp, de_mode='NADE', rng_seed=seed)
+        wf, masker, qg = o.wf, o.masker, o.wf.qubit_grouping
+        Q, DM = qg.qudit_num, int(max(qg.qudit_dims))
+        out = dict(qubit_num=n, particle_num=n_el, seed=seed, qudit_num=Q, max_qudit_dim=DM, param_num=wf.param_num,
+                   param_names=np.array([k for k, _ in wf.named_parameters()]),
+                   init_checksums=np.array([[float(p.sum()), float((p * p).sum())] for p in wf.parameters()]))
+        na = nb = n_el // 2
+        phys = synthetic.random_physical_samples(n, na, nb, sample_count, seed=seed + 1)
+        rng = np.random.default_rng(seed + 2)
+        samples = np.concatenate((phys, rng.integers(0, 2 ** min(n, 62), size=8, dtype=np.int64).astype(np.uint64)))
+        s_t = _t(samples.view(np.int64)).reshape(-1, 1)
+        base_vec = wf.base_idx2base_vec(s_t)
+        with torch.no_grad():
+            lp = wf.log_psi(base_vec)
+            amp = wf.amplitude(s_t)
+        out.update(samples=samples.view(np.int64), n_phys=phys.shape[0], log_psi=lp.numpy(), amplitude=amp.numpy())
+        for q in sorted({0, Q // 2, Q - 1}):
+            with torch.no_grad():
+                prefix_vec = base_vec[:phys.shape[0], :qg.qudit_starts[q]]
+                rolling = masker.compute_rolling_acc_eigs(prefix_vec)[-1]
+                mask = qg.qudit_idx2cont_mask_mul_table[q][masker.acc_eigs2memo_idx(rolling)]
+                out[f'cond_log_abs_q{q}'] = wf.cond_log_abs(qudit_idx=q, base_vec=prefix_vec, mask=mask).numpy()
+        c = rng.standard_normal(phys.shape[0]) + 1j * rng.standard_normal(phys.shape[0])
+        wf.zero_grad()
+        loss = (torch.conj(_t(c)) * wf.log_psi(base_vec[:phys.shape[0]])).real.sum()
+        loss.backward()
+        grad = wf.cat_grad.numpy()
+        proj = np.random.default_rng(seed + 3).standard_normal((16, grad.shape[0]))
+        out.update(grad_coeff=c, grad_loss=float(loss), grad_proj=proj @ grad, grad_norms=np.array([float(p.grad.norm()) for p in wf.parameters()]))
+        real_binomial = torch.distributions.Binomial
+        torch.distributions.Binomial = _RintBinomial
+        try:
+            idx, cnt = wf.sample_stats(stats_num)
+        finally:
+            torch.distributions.Binomial = real_binomial
+        out.update(stats_num=stats_num, stats_idx=idx.numpy().reshape(-1), stats_counts=cnt.numpy().real)
+        urng = np.random.default_rng(seed + 4)
+        real_rand = torch.rand
+        torch.rand = lambda shape, **kw: torch.from_numpy(urng.random(tuple(shape)))
+        try:
+            gidx, gfreq = wf.sample_indices_gumbel(gumbel_num)
+        finally:
+            torch.rand = real_rand
+        out.update(gumbel_num=gumbel_num, gumbel_idx=gidx.numpy().reshape(-1), gumbel_freqs=gfreq.numpy())
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f'{name}.npz'), **out)
+        print(f'{name}: P={wf.param_num} stats_unique={idx.shape[0]} gumbel_unique={gidx.shape[0]}')
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def make_nade():
+    _nade_case('nade_n12', 12, 4, 100, 10 ** 4, 64, seed=0)
+    _nade_case('nade_n20', 20, 14, 200, 10 ** 6, 300, seed=1)
+    _nade_case('nade_n56', 56, 14, 200, 3000, 200, seed=2)
+
+
 def make_anqs():
     _anqs_case('anqs_n12', 12, 4, 100, 10 ** 4, 64, seed=0)
     _anqs_case('anqs_n20', 20, 14, 200, 10 ** 6, 300, seed=1)
@@ -347,7 +408,7 @@ def make_tfm():
     _tfm_case('tfm_n14', 14, 10, depth=3, head_num=2, seed=9)     # head_dim 32: the wide-head path of the kernel
 
 
-GROUPS = {'ham': make_ham, 'anqs': make_anqs, 'vmc': make_vmc, 'tfm': make_tfm}
+GROUPS = {'ham': make_ham, 'anqs': make_anqs, 'nade': make_nade, 'vmc': make_vmc, 'tfm': make_tfm}
 
 
 def main(argv):

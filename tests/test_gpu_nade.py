@@ -1,0 +1,64 @@
+"""GPU parity, NADE mode (the reference's default de_mode): nade_forward_kernel through LogAbsPhaseANQS(de_mode='NADE')
+against the golden vectors of the unmodified reference.  1e-10 on log psi / conditionals / gradients; sampled
+configurations and counts bit-exact given identical draws."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from test_oracle_nade import build, CASES
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_log_psi_cond_and_gradients(name):
+    g = load_golden(name)
+    wf = build(g, device=DEV)
+    nphys = int(g['n_phys'])
+    s = _dev(g['samples']).view(-1, 1)
+    with torch.no_grad():
+        lp = wf.log_psi_of_indices(s).cpu().numpy()
+        amp = wf.amplitude(s).cpu().numpy()
+    assert np.abs(lp[:nphys] - g['log_psi'][:nphys]).max() < 1e-10
+    assert np.array_equal(np.isneginf(lp.real), np.isneginf(g['log_psi'].real))
+    assert np.abs(amp - g['amplitude']).max() < 1e-10
+    for key in [k for k in g if k.startswith('cond_log_abs_q')]:
+        q = int(key.split('q')[-1])
+        c = wf.cond_log_abs(qudit_idx=q, prefix_idx=s[:nphys].view(-1))[:, :g[key].shape[1]].cpu().numpy()
+        ref = g[key]
+        assert np.array_equal(np.isneginf(c), np.isneginf(ref))
+        fin = ~np.isneginf(ref)
+        assert np.abs(c[fin] - ref[fin]).max() < 1e-10
+    # gradients against the reference's autograd
+    c = _dev(g['grad_coeff'])
+    proj = np.random.default_rng(int(g['seed']) + 3).standard_normal((16, wf.param_num))
+    wf.zero_grad()
+    loss = (torch.conj(c) * wf.log_psi_of_indices(s[:nphys])).real.sum()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g['grad_loss'])) < 1e-9 * max(1.0, abs(float(g['grad_loss'])))
+    grad = wf.cat_grad.cpu().numpy()
+    assert np.abs(proj @ grad - g['grad_proj']).max() < 1e-10 * max(1.0, np.abs(g['grad_proj']).max())
+    norms = np.array([float(p.grad.norm()) for p in wf.parameters()])
+    assert np.abs(norms - g['grad_norms']).max() < 1e-10 * max(1.0, g['grad_norms'].max())
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_samplers_match_reference(name):
+    g = load_golden(name)
+    wf = build(g, device=DEV)
+    idx, cnt = wf.sample_stats(int(g['stats_num']), draw_mode='rint')
+    assert np.array_equal(idx.view(-1).cpu().numpy(), g['stats_idx'])
+    assert np.array_equal(cnt.real.cpu().numpy(), g['stats_counts'])
+    urng = np.random.default_rng(int(g['seed']) + 4)
+    gi, gf = wf.sample_indices_gumbel(int(g['gumbel_num']), uniforms=lambda q, B, D: torch.from_numpy(urng.random((B, D))))
+    assert np.array_equal(gi.view(-1).cpu().numpy(), g['gumbel_idx'])
+    assert np.abs(gf.cpu().numpy() - g['gumbel_freqs']).max() < 1e-10
+    # Philox mode: conservation and physicality
+    idx, cnt = wf.sample_stats(10 ** 5, seed=9)
+    assert float(cnt.real.sum()) == 1e5 and float(cnt.real.min()) >= 1.0
