@@ -141,11 +141,11 @@ static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostP
     std::vector<M> ms((size_t)U);
     for (int64_t u = 0; u < U; ++u) {
         uint32_t pa = mab[u].x, mb = mab[u].y;
-        ms[u] = {pa, mb, (lin_host(LIN_POSA, pa) & 0x3FFu) ^ (lin_host(LIN_POSB, mb) & 0xFFFFu), (uint32_t)u};
+        ms[u] = {pa, mb, (lin_host(LIN_POSA, pa) & POSA_MASK) ^ (lin_host(LIN_POSB, mb) & POSB_MASK), (uint32_t)u};
     }
     std::sort(ms.begin(), ms.end(), [](const M &x, const M &y) {
         if (x.pa != y.pa) return x.pa < y.pa;
-        uint32_t sx = x.hash >> 10, sy = y.hash >> 10;
+        uint32_t sx = x.hash >> 15, sy = y.hash >> 15;
         if (sx != sy) return sx < sy;
         return x.mb < y.mb;
     });

@@ -87,7 +87,7 @@ struct Tables {
 // ---- sampled-set lookup table (kernel family 2) ------------------------------------------------------
 // Memory layout of the caller-allocated buffer (128-byte aligned):
 //   [capacity slots of 32 bytes][dedicated slot for the all-ones key, 32 bytes][header, 96 bytes][filter]
-// The filter is a line-blocked presence filter of 4*capacity bytes (64..128 bits per key, ONE bit set per key):
+// The filter is a line-blocked presence filter of 2*capacity bytes (32..64 bits per key, TWO bits of one word per key):
 // the 128-byte line is chosen by the ALPHA half of the key (lin LIN_LINE), optionally spread over 2^G lines by
 // G hash bits of the beta half, and the bit inside the line by both halves (LIN_POSA ^ LIN_POSB).  All the hashes
 // are GF(2)-linear, so the fused kernel gets the filter address of x' = x ^ mask with one XOR per candidate, and
@@ -96,7 +96,8 @@ struct Tables {
 // from the occupancy of the lines (k2_hash.cu) and stored in the header.  Keys are stored DE-INTERLEAVED.
 constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;  // de-interleaving maps all-ones to all-ones
 constexpr int FILTER_MAX_SPREAD_BITS = 6;
-constexpr int FILTER_BYTES_PER_SLOT = 4;  // filter size = 4 * capacity bytes: 64..128 bits per key, ~1.5 % false positives
+constexpr int FILTER_BYTES_PER_SLOT = 2;  // filter size = 2 * capacity bytes: 32..64 bits per key, TWO bits of one word per key (~0.3 % false positives)
+constexpr uint32_t POSA_MASK = 0x7FFFu, POSB_MASK = 0x1FFFFFu;  // widths of the two position hashes
 struct __align__(32) HashSlot {
     uint64_t key;    // de-interleaved configuration
     long long idx;   // position in the key array (-1 = empty)
@@ -168,16 +169,16 @@ __host__ __device__ __forceinline__ uint32_t hash_key(uint32_t a, uint32_t b) {
          0x810729c9u, 0x22bb38deu, 0xfa9dbac4u, 0x11ab6a6du, 0x81d0ff89u, 0x1e7b2ca5u, 0x92eea3a6u, 0x24949e26u,          \
          0x90f3f271u, 0x68f545b0u, 0x2e32da50u, 0xd9779982u, 0x0712e2ccu, 0x7ca6fa6eu, 0x09e2c4a5u, 0xd73e2794u,          \
          0x61f91774u, 0x3f9b14f2u, 0x9dd55901u, 0x05ad50e5u, 0x9400cb1cu, 0xb4e13945u, 0x3424af98u, 0x0d95e497u},         \
-        /* LIN_POSA: alpha half -> 10 position bits */                                                                    \
-        {0x000002b0u, 0x0000028cu, 0x00000297u, 0x00000256u, 0x000001d5u, 0x000000f4u, 0x0000034eu, 0x0000007fu,          \
-         0x000003a6u, 0x0000024eu, 0x0000026cu, 0x000001a3u, 0x0000037eu, 0x000003cau, 0x00000349u, 0x000001f3u,          \
-         0x0000015cu, 0x00000251u, 0x00000219u, 0x00000190u, 0x000003e0u, 0x000001c6u, 0x00000112u, 0x00000350u,          \
-         0x0000021eu, 0x0000000cu, 0x000000beu, 0x0000025fu, 0x000001f4u, 0x000002e9u, 0x000000fcu, 0x000000a9u},         \
-        /* LIN_POSB: beta half -> 10 position bits | 6 spread bits << 10 */                                               \
-        {0x0000b105u, 0x000025ecu, 0x0000ab22u, 0x0000f7f8u, 0x00009e12u, 0x00008e3fu, 0x00005d46u, 0x00004ad5u,          \
-         0x00002ed1u, 0x0000dca6u, 0x000087b8u, 0x0000a571u, 0x0000135cu, 0x0000c5cau, 0x0000ea64u, 0x000027bdu,          \
-         0x00000f7bu, 0x0000d998u, 0x00001e3fu, 0x00001a9au, 0x000045e8u, 0x0000a9b5u, 0x0000e677u, 0x000021c0u,          \
-         0x00001bdeu, 0x0000bf2au, 0x0000231fu, 0x000093dcu, 0x0000262fu, 0x000009d9u, 0x00009f5eu, 0x0000ea50u}          \
+        /* LIN_POSA: alpha half -> bit 1 (5) | word (5) | bit 2 (5) */                                                    \
+        {0x000036f5u, 0x00006d0eu, 0x0000114du, 0x0000422du, 0x00006ed5u, 0x00001a8du, 0x00004edeu, 0x00002b79u,          \
+         0x000025c0u, 0x00002be8u, 0x0000195eu, 0x000056e7u, 0x00005b3eu, 0x0000158cu, 0x000016d2u, 0x0000047bu,          \
+         0x00000a1bu, 0x00005108u, 0x00000eb0u, 0x00001f49u, 0x00001ab1u, 0x00002125u, 0x0000419bu, 0x0000715cu,          \
+         0x000063feu, 0x000060e6u, 0x0000405cu, 0x00002280u, 0x000051c9u, 0x000047c7u, 0x000066aau, 0x00003fadu},         \
+        /* LIN_POSB: beta half -> bit 1 | word | bit 2 | 6 spread bits << 15 */                                           \
+        {0x0006d8eeu, 0x0001edf6u, 0x00030566u, 0x001160d2u, 0x000e4a15u, 0x00006b8bu, 0x000945f7u, 0x001f9852u,          \
+         0x000350f9u, 0x0010e51cu, 0x0018e6ebu, 0x000637abu, 0x0015615eu, 0x000888e0u, 0x000631d4u, 0x0000256du,          \
+         0x00133b90u, 0x0010cc32u, 0x001c63f7u, 0x00080905u, 0x00052626u, 0x0000542bu, 0x00009522u, 0x0013d69du,          \
+         0x0001de04u, 0x0009fba5u, 0x0012c8acu, 0x000f5319u, 0x0013d81fu, 0x000f4908u, 0x00144f4bu, 0x0013b428u}          \
     }
 constexpr int LIN_LINE = 0, LIN_POSA = 1, LIN_POSB = 2;
 static const uint32_t LIN_C_HOST[3][32] = ANQS_LIN_TABLE;

@@ -129,10 +129,11 @@ __device__ __forceinline__ void fz_push2(const Tables &t, const HashView &hv, Fz
 // filter bit of the candidate with member hash `mhash` in the line group `rowline` (byte offset of the row's line)
 __device__ __forceinline__ bool fz_filter_bit(const FzWarp &w, bool pass, uint32_t rowline, uint32_t mhash) {
     const uint32_t h = w.hp ^ mhash;
-    const uint32_t off = (rowline ^ ((h >> 3) & w.gshift)) + ((h >> 3) & 0x7Cu);  // line * 128 + word * 4
+    const uint32_t off = (rowline ^ ((h >> 8) & w.gshift)) + ((h >> 3) & 0x7Cu);  // line * 128 + word * 4
+    const uint32_t pat = (1u << (h & 31u)) | (1u << ((h >> 10) & 31u));            // the key's two bits of that word
     uint32_t word = 0;
     if (pass) word = __ldg(reinterpret_cast<const uint32_t *>(w.filter + off));  // 32-bit offset: filters are <= 1 GiB
-    return (word >> (h & 31u)) & 1u;
+    return (word & pat) == pat;
 }
 
 template <bool REAL>
@@ -222,7 +223,7 @@ fused_eloc_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples, co
         w.xb = compress_even_bits(x >> 1);
         w.alpha = have ? alpha : -1;  // rows past the end get an impossible electron count: nothing passes
         w.hl = lin_warp(LIN_LINE, w.xa);
-        w.hp = (lin_warp(LIN_POSA, w.xa) & 0x3FFu) ^ (lin_warp(LIN_POSB, w.xb) & 0xFFFFu);
+        w.hp = (lin_warp(LIN_POSA, w.xa) & POSA_MASK) ^ (lin_warp(LIN_POSB, w.xb) & POSB_MASK);
         w.qlen = 0;
         w.er = w.ei = 0.0;
         for (int ti = 0; ti < t.n_tiles; ++ti) {

@@ -22,7 +22,7 @@ namespace anqs {
 __device__ __forceinline__ void key_hashes(uint64_t key, uint32_t &hl, uint32_t &hp) {
     const uint32_t ka = (uint32_t)key, kb = (uint32_t)(key >> 32);
     hl = lin_dev(LIN_LINE, ka);
-    hp = (lin_dev(LIN_POSA, ka) & 0x3FFu) ^ (lin_dev(LIN_POSB, kb) & 0xFFFFu);
+    hp = (lin_dev(LIN_POSA, ka) & POSA_MASK) ^ (lin_dev(LIN_POSB, kb) & POSB_MASK);
 }
 
 __global__ void __launch_bounds__(256)
@@ -78,8 +78,8 @@ hash_build_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ 
         uint64_t key = deinterleave((uint64_t)keys[j]);
         uint32_t hl, hp;
         key_hashes(key, hl, hp);
-        const uint32_t line = (hl ^ ((hp >> 10) & gmask)) & linemask;
-        atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), 1u << (hp & 31u));
+        const uint32_t line = (hl ^ ((hp >> 15) & gmask)) & linemask;
+        atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), (1u << (hp & 31u)) | (1u << ((hp >> 10) & 31u)));
         HashSlot *sl;
         if (key == EMPTY_KEY) {
             sl = slots + (size_t)capmask + 1;
