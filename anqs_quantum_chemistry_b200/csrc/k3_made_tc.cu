@@ -25,13 +25,12 @@
 
 namespace anqs {
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_NT = 4;                        // 128-sample tiles per CTA
+constexpr int TC_THREADS = 128 * TC_NT;
 constexpr int TC_W = 64;                        // hidden width and outcomes per qudit
 constexpr uint32_t TC_ACT_BYTES = 128 * 64 * 4;  // one activation tile
 constexpr uint32_t TC_WH_BYTES = 64 * 64 * 4;    // one hidden-layer weight matrix / one qudit block of the output layer
-constexpr uint32_t TC_CHUNK_BYTES = 2 * TC_WH_BYTES;
 constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr uint32_t TC_COL_HIDDEN = 0, TC_COL_CHUNK = 128;
 
 struct TcPacked {                 // offsets (bytes) into the packed buffer, per sub-network
     uint32_t w1[2], w2[2], w3[2]; // w3: qudit_num blocks of TC_WH_BYTES
@@ -170,22 +169,25 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, ui
         umma_tf32(tmem_d, smem_desc(a_saddr + (k >> 2) * 128, 128, sbo), smem_desc(b_saddr + (k >> 2) * 128, 128, sbo), idesc, k > 0);
 }
 
-// mode 0: log psi of whole configurations; mode 1: normalised conditional log|psi| of qudit level_q for prefixes
+// mode 0: log psi of whole configurations; mode 1: normalised conditional log|psi| of qudit level_q for prefixes.
+// One CTA works on TC_NT tiles of 128 samples at once (4 warps per tile): every GEMM phase issues one MMA group per tile
+// against the same staged weights, and all 4 * TC_NT warps run the epilogue in parallel.
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *__restrict__ packed,
                const int64_t *__restrict__ idx_in, int64_t B, int level_q, double2 *__restrict__ log_psi,
                double *__restrict__ cond_out) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    unsigned char *actA = tc_smem;                         // input, then last hidden activations
-    unsigned char *actB = actA + TC_ACT_BYTES;             // first hidden activations
-    unsigned char *wh = actB + TC_ACT_BYTES;               // hidden-layer weights
-    unsigned char *wc = wh + TC_WH_BYTES;                  // 2 x output-layer chunk
-    float *s_bias = reinterpret_cast<float *>(wc + 2 * TC_CHUNK_BYTES);  // [b1 64][b2 64*(depth-1)][b3 Q*64]
+    unsigned char *acts = tc_smem;                                  // TC_NT activation tiles, rewritten in place per layer
+    unsigned char *wh = acts + TC_NT * TC_ACT_BYTES;                // hidden-layer weights
+    unsigned char *wc = wh + TC_WH_BYTES;                           // 2 x one qudit block of the output layer
+    float *s_bias = reinterpret_cast<float *>(wc + 2 * TC_WH_BYTES);  // [b1 64][b2 64*(depth-1)][b3 Q*64]
     __shared__ uint64_t bar_wh, bar_wc[2], bar_m[2];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int tl = tid >> 7, row = tid & 127;                       // this thread's tile and row
+    unsigned char *act = acts + tl * TC_ACT_BYTES;
     const int n = P.qubit_num, Q = P.qudit_num, depth = P.depth;
     const uint32_t K0 = L.k0pad;
     if (tid == 0) {
@@ -204,33 +206,34 @@ made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;  // this warp's TMEM lanes
+    // TMEM: tile t owns columns [128 t, 128 t + 128): two 64-column accumulator buffers (buffer 0 also serves the hidden layers)
+    const uint32_t my_tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)tl * 128u;
     uint32_t p_wh = 0, p_wc[2] = {0, 0}, p_m[2] = {0, 0};
 
     const int nets = MODE == 1 ? 1 : 2;
     const int q_lo = MODE == 1 ? level_q : 0, q_hi = MODE == 1 ? level_q + 1 : Q;
-    const int nchunks = (q_hi - q_lo + 1) / 2;
+    const int nchunks = q_hi - q_lo;                                // one qudit per chunk
     const int known = MODE == 1 ? P.qudit_starts[level_q] : n;
-    const int64_t ntiles = (B + 127) / 128;
+    const int64_t ngroups = (B + 128 * TC_NT - 1) / (128 * TC_NT);
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t s = tile * 128 + tid;
+    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int64_t s = (grp * TC_NT + tl) * 128 + row;
+        const int64_t left_tiles = (B - grp * TC_NT * 128 + 127) / 128;
+        const int live_tiles = left_tiles < TC_NT ? (int)left_tiles : TC_NT;  // tiles of this group that hold samples
         uint64_t x = s < B ? (uint64_t)idx_in[s] : 0ull;
         if (MODE == 1) x = known >= 64 ? x : (x & ((1ull << known) - 1ull));
         double acc_re = 0.0, acc_im = 0.0;
         bool dead = false;  // an unphysical configuration: log|psi| = -inf (ANQS:399-401)
 
         for (int net = 0; net < nets; ++net) {
-            // ---- stage weights: W1 now; the first two output chunks as early as possible -----------------------
+            // ---- stage weights: W1 now; the first two output blocks as early as possible ------------------------------
             __syncthreads();  // previous users of wh / wc / bias / act buffers are done
             if (tid == 0) {
                 mbar_arrive_expect_tx(&bar_wh, 64 * K0 * 4);
                 bulk_copy_g2s(wh, packed + L.w1[net], 64 * K0 * 4, &bar_wh);
                 for (int c = 0; c < nchunks && c < 2; ++c) {
-                    const int nq = min(2, q_hi - (q_lo + 2 * c));
-                    mbar_arrive_expect_tx(&bar_wc[c], (uint32_t)nq * TC_WH_BYTES);
-                    bulk_copy_g2s(wc + c * TC_CHUNK_BYTES, packed + L.w3[net] + (uint32_t)(q_lo + 2 * c) * TC_WH_BYTES,
-                                  (uint32_t)nq * TC_WH_BYTES, &bar_wc[c]);
+                    mbar_arrive_expect_tx(&bar_wc[c], TC_WH_BYTES);
+                    bulk_copy_g2s(wc + c * TC_WH_BYTES, packed + L.w3[net] + (uint32_t)(q_lo + c) * TC_WH_BYTES, TC_WH_BYTES, &bar_wc[c]);
                 }
             }
             for (int e = tid; e < 64 * depth + Q * 64; e += TC_THREADS)
@@ -244,19 +247,19 @@ made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *
                     const int k = (int)kb + j;
                     vp[j] = k < known ? 1.0f - 2.0f * (float)((x >> k) & 1ull) : 0.0f;
                 }
-                *reinterpret_cast<float4 *>(actA + canon_off((uint32_t)tid, kb, K0)) = v;
+                *reinterpret_cast<float4 *>(act + canon_off((uint32_t)row, kb, K0)) = v;
             }
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
-            // ---- hidden layers ------------------------------------------------------------------------------------
-            unsigned char *cur = actA, *nxt = actB;
+            // ---- hidden layers (activations rewritten in place: the MMA has finished reading before the epilogue writes) --
             for (int l = 0; l < depth; ++l) {
                 const uint32_t K = l == 0 ? K0 : 64u;
                 if (tid == 0) {
                     mbar_wait(&bar_wh, p_wh);
                     tc_fence_after();
-                    issue_gemm(tmem + TC_COL_HIDDEN, smem_u32(cur), smem_u32(wh), K);
+                    for (int t = 0; t < live_tiles; ++t)
+                        issue_gemm(tmem + 128u * t, smem_u32(acts + t * TC_ACT_BYTES), smem_u32(wh), K);
                     umma_commit(&bar_m[0]);
                 }
                 p_wh ^= 1u;
@@ -267,34 +270,31 @@ made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *
                     mbar_arrive_expect_tx(&bar_wh, TC_WH_BYTES);
                     bulk_copy_g2s(wh, packed + L.w2[net] + (uint32_t)l * TC_WH_BYTES, TC_WH_BYTES, &bar_wh);
                 }
-                float v[64];
-                tmem_ld64(tmem + lane_base + TC_COL_HIDDEN, v);
-                const float *bias = s_bias + 64 * l;
+                if (tl < live_tiles) {
+                    float v[64];
+                    tmem_ld64(my_tmem, v);
+                    const float *bias = s_bias + 64 * l;
 #pragma unroll
-                for (int kb = 0; kb < 64; kb += 4) {
-                    float4 o;
-                    float *op = &o.x;
-                    float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (P.use_res && l > 0) res = *reinterpret_cast<const float4 *>(cur + canon_off((uint32_t)tid, kb, 64));  // MLP:237-239
-                    const float *rp = &res.x;
+                    for (int kb = 0; kb < 64; kb += 4) {
+                        float4 o;
+                        float *op = &o.x;
+                        float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (P.use_res && l > 0) res = *reinterpret_cast<const float4 *>(act + canon_off((uint32_t)row, kb, 64));  // MLP:237-239
+                        const float *rp = &res.x;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) op[j] = tanh_fast(v[kb + j] + bias[kb + j] + rp[j]);
-                    *reinterpret_cast<float4 *>(nxt + canon_off((uint32_t)tid, kb, 64)) = o;
+                        for (int j = 0; j < 4; ++j) op[j] = tanh_fast(v[kb + j] + bias[kb + j] + rp[j]);
+                        *reinterpret_cast<float4 *>(act + canon_off((uint32_t)row, kb, 64)) = o;
+                    }
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 __syncthreads();
-                unsigned char *t = cur;
-                cur = nxt;
-                nxt = t;
             }
-            // ---- output layer: chunks of two qudits, MMA of chunk c+1 under the epilogue of chunk c ------------------
+            // ---- output layer: one qudit per chunk, MMA of chunk c+1 under the epilogue of chunk c -------------------------
             if (tid == 0) {
                 mbar_wait(&bar_wc[0], p_wc[0]);
                 tc_fence_after();
-                const int nq = min(2, q_hi - q_lo);
-                for (int j = 0; j < nq; ++j)
-                    issue_gemm(tmem + TC_COL_CHUNK + 64 * j, smem_u32(cur), smem_u32(wc) + j * TC_WH_BYTES, 64);
+                for (int t = 0; t < live_tiles; ++t) issue_gemm(tmem + 128u * t, smem_u32(acts + t * TC_ACT_BYTES), smem_u32(wc), 64);
                 umma_commit(&bar_m[0]);
             }
             for (int c = 0; c < nchunks; ++c) {
@@ -302,21 +302,18 @@ made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *
                 if (tid == 0 && c + 1 < nchunks) {
                     mbar_wait(&bar_wc[b ^ 1], p_wc[b ^ 1]);
                     tc_fence_after();
-                    const int nq = min(2, q_hi - (q_lo + 2 * (c + 1)));
-                    for (int j = 0; j < nq; ++j)
-                        issue_gemm(tmem + TC_COL_CHUNK + 128 * (b ^ 1) + 64 * j, smem_u32(cur),
-                                   smem_u32(wc) + (b ^ 1) * TC_CHUNK_BYTES + j * TC_WH_BYTES, 64);
+                    for (int t = 0; t < live_tiles; ++t)
+                        issue_gemm(tmem + 128u * t + 64u * (b ^ 1), smem_u32(acts + t * TC_ACT_BYTES), smem_u32(wc) + (b ^ 1) * TC_WH_BYTES, 64);
                     umma_commit(&bar_m[b ^ 1]);
                 }
                 p_wc[b] ^= 1u;
                 mbar_wait(&bar_m[b], p_m[b]);
                 p_m[b] ^= 1u;
                 tc_fence_after();
-                const int nq = min(2, q_hi - (q_lo + 2 * c));
-                for (int j = 0; j < nq; ++j) {
-                    const int q = q_lo + 2 * c + j;
+                if (tl < live_tiles) {
+                    const int q = q_lo + c;
                     float z[64];
-                    tmem_ld64(tmem + lane_base + TC_COL_CHUNK + 128 * b + 64 * j, z);
+                    tmem_ld64(my_tmem + 64u * b, z);
                     const float *bias = s_bias + 64 * depth + 64 * q;
                     const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start;
                     const int chosen = (int)((x >> start) & ((1ull << bits) - 1ull));
@@ -330,6 +327,7 @@ made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *
                             const long long mi = tc_memo_index(P, prefix);
                             mw = (mi >= 0 && mi < P.memo_size) ? __ldg(P.cont_mask + (size_t)q * P.memo_size + mi) : 0ull;
                         }
+                        const uint32_t mlo = (uint32_t)mw, mhi = (uint32_t)(mw >> 32);
                         float sum = 0.f;
 #pragma unroll
                         for (int d = 0; d < 64; ++d) {
@@ -340,27 +338,28 @@ made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *
                         float mx = -INFINITY;
 #pragma unroll
                         for (int d = 0; d < 64; ++d) {
-                            z[d] -= mean;
-                            if ((mw >> d) & 1ull) mx = fmaxf(mx, z[d]);
+                            const bool ok = ((d < 32 ? mlo >> d : mhi >> (d - 32)) & 1u) != 0u;
+                            z[d] = ok ? z[d] - mean : -INFINITY;   // masked logits: exp() of them is exactly 0
+                            mx = fmaxf(mx, z[d]);
                         }
+                        const bool any = mw != 0ull;
+                        const float mxs = any ? mx : 0.f;
                         float se = 0.f;
 #pragma unroll
-                        for (int d = 0; d < 64; ++d)
-                            if ((mw >> d) & 1ull) se += __expf(2.0f * (z[d] - mx));
-                        const float Lnorm = mx + 0.5f * __logf(se);  // 0.5 * logsumexp(2 z) over the allowed outcomes
-                        const bool any = mw != 0ull;
+                        for (int d = 0; d < 64; ++d) se += __expf(2.0f * (z[d] - mxs));
+                        const float Lnorm = mxs + 0.5f * __logf(se);  // 0.5 * logsumexp(2 z) over the allowed outcomes
                         if (MODE == 1) {
                             if (s < B) {
 #pragma unroll
                                 for (int d = 0; d < 64; ++d)
-                                    if (d < DM) cond_out[(size_t)s * DM + d] = (any && ((mw >> d) & 1ull)) ? (double)(z[d] - Lnorm) : -INFINITY;
+                                    if (d < DM) cond_out[(size_t)s * DM + d] = any ? (double)(z[d] - Lnorm) : -INFINITY;
                             }
                         } else {
                             float pick = 0.f;
 #pragma unroll
                             for (int d = 0; d < 64; ++d)
                                 if (d == chosen) pick = z[d];
-                            if (any && ((mw >> chosen) & 1ull))
+                            if (any && pick > -INFINITY)
                                 acc_re += (double)(pick - Lnorm);
                             else
                                 dead = true;
@@ -376,10 +375,8 @@ made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *
                 tc_fence_before();
                 __syncthreads();  // everyone has read TMEM buffer b; its MMA is done, so weight buffer b is free
                 if (tid == 0 && c + 2 < nchunks) {
-                    const int nq2 = min(2, q_hi - (q_lo + 2 * (c + 2)));
-                    mbar_arrive_expect_tx(&bar_wc[b], (uint32_t)nq2 * TC_WH_BYTES);
-                    bulk_copy_g2s(wc + b * TC_CHUNK_BYTES, packed + L.w3[net] + (uint32_t)(q_lo + 2 * (c + 2)) * TC_WH_BYTES,
-                                  (uint32_t)nq2 * TC_WH_BYTES, &bar_wc[b]);
+                    mbar_arrive_expect_tx(&bar_wc[b], TC_WH_BYTES);
+                    bulk_copy_g2s(wc + b * TC_WH_BYTES, packed + L.w3[net] + (uint32_t)(q_lo + c + 2) * TC_WH_BYTES, TC_WH_BYTES, &bar_wc[b]);
                 }
             }
         }
@@ -409,7 +406,7 @@ static int tc_check(const anqs_made_desc_t *P) {
 }
 
 static size_t tc_smem_bytes(const anqs_made_desc_t *P) {
-    return 2 * (size_t)TC_ACT_BYTES + TC_WH_BYTES + 2 * (size_t)TC_CHUNK_BYTES + (size_t)(64 * P->depth + P->qudit_num * 64) * 4;
+    return TC_NT * (size_t)TC_ACT_BYTES + 3 * (size_t)TC_WH_BYTES + (size_t)(64 * P->depth + P->qudit_num * 64) * 4;
 }
 
 extern "C" {
@@ -438,8 +435,8 @@ int anqs_made_log_psi_tc(const anqs_made_desc_t *desc, const void *d_packed, con
     const size_t smem = tc_smem_bytes(desc);
     auto kern = made_tc_kernel<0>;
     ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t ntiles = (n + 127) / 128;
-    const int grid = (int)std::min<int64_t>(ntiles, sm_count_of_current_device());
+    const int64_t ngroups = (n + 128 * TC_NT - 1) / (128 * TC_NT);
+    const int grid = (int)std::min<int64_t>(ngroups, sm_count_of_current_device());
     kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*desc, L, (const unsigned char *)d_packed, d_idx, n, 0,
                                                           (double2 *)d_log_psi, nullptr);
     ANQS_LAUNCH_CHECK();
@@ -457,8 +454,8 @@ int anqs_made_cond_log_abs_tc(const anqs_made_desc_t *desc, const void *d_packed
     const size_t smem = tc_smem_bytes(desc);
     auto kern = made_tc_kernel<1>;
     ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t ntiles = (n + 127) / 128;
-    const int grid = (int)std::min<int64_t>(ntiles, sm_count_of_current_device());
+    const int64_t ngroups = (n + 128 * TC_NT - 1) / (128 * TC_NT);
+    const int grid = (int)std::min<int64_t>(ngroups, sm_count_of_current_device());
     kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(*desc, L, (const unsigned char *)d_packed, d_prefix, n, qudit_idx,
                                                           nullptr, d_cond);
     ANQS_LAUNCH_CHECK();
