@@ -11,5 +11,6 @@ from .masker import LocallyDecomposableMasker  # noqa: F401
 from .qubit_grouping import QubitGrouping, QubitGroupingConfig  # noqa: F401
 from .anqs import LogAbsPhaseANQS, ANQSConfig, MLPConfig, LocalSamplingConfig  # noqa: F401
 from .calculations import (SamplingConfig, SamplingResult, sample, LocalEnergyCalculationConfig, MonteCarloEstimator,  # noqa: F401
-                           LocalEnergyResult, compute_local_energies, vmc_loss)
+                           LocalEnergyResult, compute_local_energies, vmc_loss, SRConfig, SRMetrics, sr, ProcessGradConfig,
+                           process_grad)
 from .transformer_anqs import TransformerANQS, TransformerANQSConfig, TransformerMADE  # noqa: F401

@@ -456,18 +456,72 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         return out
 
     # ---- per-sample log-Jacobian for stochastic reconfiguration (ANQS:820-839) ----------------------------------
+    @pt.no_grad()
     def compute_cat_log_jac(self, indices: pt.Tensor) -> pt.Tensor:
-        """[B, param_num] complex128: d log(conj psi(x_b)) / d theta, parameters concatenated in .parameters() order."""
+        """ANQS:820-839: [B, param_num] complex128, row b = d log(conj psi(x_b)) / d theta with the parameters concatenated in
+        .parameters() order.  One forward launch with saved activations, then the per-sample chain rule as batched outer
+        products - no loop over samples (the reference vmaps autograd over the <= 50 samples SR uses, SR:20-32)."""
         idx = indices.contiguous().view(-1)
-        B = idx.shape[0]
-        rows = []
-        params = list(self.parameters())
-        for b in range(B):  # the reference restricts this to max_indices_num = 25..50 samples (SR:20-32)
-            lp = (_NadeLogPsi if self.de_mode == 'NADE' else _MadeLogPsi).apply(self, idx[b:b + 1], *params)
-            g_re = pt.autograd.grad(lp.real.sum(), params, retain_graph=True)
-            g_im = pt.autograd.grad(lp.imag.sum(), params)
-            rows.append(pt.complex(pt.cat([g.reshape(-1) for g in g_re]), -pt.cat([g.reshape(-1) for g in g_im])))
-        return pt.stack(rows)
+        B, Q, depth, dev = idx.shape[0], self.qudit_num, self.depth, idx.device
+        _, (save_h, save_p) = self._launch_log_psi(idx, save=True)
+        bits = (1.0 - 2.0 * ((idx.view(-1, 1) >> self.hilbert_space.shifts) & 1).to(pt.float64))
+        chosen = self.chosen_outcomes(idx)
+        rows = pt.arange(B, device=dev)
+        zero = pt.zeros((), dtype=pt.float64, device=dev)
+
+        def mlp_rows(x, h, W, dY):
+            """Per-sample gradients of one MLP: [(gW [B, out, in], gb [B, out])] for layers 0..depth given dY = d f / d output."""
+            out = [(dY.unsqueeze(2) * h[-1].unsqueeze(1), dY)]
+            dh = dY @ W[depth]
+            for l in range(depth - 1, -1, -1):
+                da = dh * (1.0 - h[l] * h[l])
+                inp = x if l == 0 else h[l - 1]
+                out.append((da.unsqueeze(2) * inp.unsqueeze(1), da))
+                if l > 0:
+                    dh = da @ W[l]
+                    if self.use_res:
+                        dh = dh + da
+            return out[::-1]
+
+        def flat(per_layer, imag):
+            cols = []
+            for gW, gb in per_layer:
+                cols.append(gW.reshape(B, -1))
+                if self.use_bias:
+                    cols.append(gb)
+            g = pt.cat(cols, dim=1)
+            return pt.complex(zero.expand_as(g), -g) if imag else pt.complex(g, zero.expand_as(g))
+
+        blocks = []
+        if self.de_mode == 'MADE':
+            DM = self.max_qudit_dim
+            out_rows = chosen + DM * pt.arange(Q, device=dev).view(1, -1)
+            for net, sub in enumerate((self.log_abs_subnet, self.phase_subnet)):
+                W = [layer.weight.data for layer in sub.layers]
+                h = [save_h[net, l] for l in range(depth)]
+                if net == 0:   # d Re log psi / d y_qd = [d == chosen] - p_qd
+                    dY = -save_p.clone()
+                    dY.view(B, Q * DM).scatter_add_(1, out_rows, pt.ones((B, Q), dtype=pt.float64, device=dev))
+                    dY = dY.view(B, Q * DM)
+                else:          # d Im log psi / d y_qd = pi [d == chosen]
+                    dY = pt.zeros((B, Q * DM), dtype=pt.float64, device=dev)
+                    dY.scatter_(1, out_rows, math.pi)
+                blocks.append(flat(mlp_rows(bits, h, W, dY), imag=net == 1))
+        else:
+            for net, subs in enumerate((self.log_abs_subnet, self.phase_subnet)):
+                for q, mlp in enumerate(subs):
+                    W = [layer.weight.data for layer in mlp.layers]
+                    h = [save_h[net, q, l] for l in range(depth)]
+                    start, D = self.qudit_starts[q], self.qubit_grouping.qudit_dims_host[q]
+                    x = bits[:, :start] if start > 0 else pt.zeros((B, 1), dtype=pt.float64, device=dev)
+                    if net == 0:
+                        dY = -save_p[:, q, :D].clone()
+                        dY[rows, chosen[:, q]] += 1.0
+                    else:
+                        dY = pt.zeros((B, D), dtype=pt.float64, device=dev)
+                        dY[rows, chosen[:, q]] = math.pi
+                    blocks.append(flat(mlp_rows(x, h, W, dY), imag=net == 1))
+        return pt.cat(blocks, dim=1)
 
     @staticmethod
     def spin_flip_base_vec(base_vec):

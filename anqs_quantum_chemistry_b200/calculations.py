@@ -6,6 +6,8 @@ reference (EnergyOptExp.iter, energy_opt_exp.py:626-679) runs unchanged on the B
   compute_local_energies(wf, ...)       CLE:75-163   -> LocalEnergyResult(full / sample-aware MonteCarloEstimator), metrics
   MonteCarloEstimator                   CLE:48-62    mean / var under frequencies counts / sum(counts)
   vmc_loss(...)                         EXP:609      2 Re sum f log(conj psi) (E - <E>)
+  sr(wf, sampling_result, config)       SR:88-136    stochastic reconfiguration of wf.cat_grad on the most frequent samples
+  process_grad(wf, ...)                 PG:55-70     SR, gradient clipping, renormalisation
 """
 import numpy as np
 import torch as pt
@@ -129,3 +131,95 @@ def compute_local_energies(wf=None, sampling_result: SamplingResult = None, samp
 def vmc_loss(sampled_amps: pt.Tensor, estimator: MonteCarloEstimator) -> pt.Tensor:
     """EXP:609: 2 Re sum_i f_i log(conj psi_i) (E_i - <E>); its gradient is the energy gradient."""
     return 2 * (estimator.freqs * pt.log(pt.conj(sampled_amps)) * (estimator.values - estimator.mean)).sum().real
+
+
+# ---- gradient post-processing (SURVEY.md section 8(f) rank 2) ------------------------------------------------------------------
+class SRConfig:
+    """SR:20-32."""
+
+    def __init__(self, *args, max_indices_num: int = 25, use_theor_freqs: bool = False, use_reg: bool = True, reg_eps: float = 1e-4,
+                 **kwargs):
+        self.max_indices_num, self.use_theor_freqs, self.use_reg, self.reg_eps = max_indices_num, use_theor_freqs, use_reg, reg_eps
+
+
+class SRMetrics:
+    FIELDS = ('sr_unq_num', 'sr_sampled_prob', 'sr_max_amp', 'sr_min_amp', 'sr_time')
+
+    def __init__(self, **kwargs):
+        for f in self.FIELDS:
+            setattr(self, f, kwargs.get(f, np.nan))
+
+
+@pt.no_grad()
+def sr(wf=None, sampling_result: SamplingResult = None, config: SRConfig = None):
+    """SR:88-136.  Preconditions the gradient g with the quantum geometric tensor S = O^dagger O of the max_indices_num most
+    frequent samples, O = diag(sqrt f) conj(J - <J>), J the per-sample log-Jacobian (wf.compute_cat_log_jac):
+      regularised:  g <- (g - O^dagger (1 + eps T)^-1 (O g)) / eps  with T = O O^dagger / eps^2  (Woodbury form of (S + eps)^-1 g)
+      otherwise:    g <- O^dagger T^+ T^+ O g  (pseudo-inverse through an SVD).
+    Returns (new real gradient, SRMetrics, seconds) like the reference's @timed function."""
+    import time
+    t0 = time.time()
+    config = config if config is not None else SRConfig()
+    metrics = SRMetrics()
+    g = wf.cat_grad
+    g = pt.complex(g, pt.zeros_like(g))
+    if config.use_theor_freqs:
+        amps = wf.amplitude(sampling_result.indices)
+        freqs = pt.conj(amps) * amps
+    else:
+        freqs = sampling_result.counts
+    freqs = freqs / pt.sum(freqs)
+    _, order = pt.sort(freqs.real, descending=True)
+    top = order[:config.max_indices_num]
+    f = freqs[top]
+    f = f / pt.sum(f)
+    idx = sampling_result.indices[top]
+    amps = wf.amplitude(idx)
+    metrics.sr_unq_num = amps.shape[0]
+    metrics.sr_sampled_prob = pt.dot(pt.conj(amps), amps).real.item()
+    metrics.sr_max_amp, metrics.sr_min_amp = amps[0].item(), amps[-1].item()
+    J = wf.compute_cat_log_jac(idx)
+    J = J - (J.T * f).sum(dim=-1, keepdim=True).T
+    if config.use_reg:
+        inv_eps = 1.0 / config.reg_eps
+        O = inv_eps * pt.sqrt(f).unsqueeze(1) * J.conj()
+        T = O @ O.conj().T
+        T_reg = pt.eye(T.shape[0], dtype=T.dtype, device=T.device) + config.reg_eps * T
+        g = inv_eps * g - O.conj().T @ pt.linalg.solve(T_reg, O @ g)
+    else:
+        O = pt.sqrt(f).unsqueeze(1) * J.conj()
+        T = O @ O.conj().T
+        u, sv, vh = pt.linalg.svd(T, full_matrices=True)
+        sv_inv = pt.where(pt.isclose(sv, pt.zeros_like(sv)), pt.zeros_like(sv), 1.0 / sv)
+        T_inv = vh.conj().T @ pt.diag(sv_inv.type(T.dtype)) @ u.conj().T
+        g = O.conj().T @ (T_inv.conj().T @ (T_inv @ (O @ g)))
+    return g.real, metrics, time.time() - t0
+
+
+class ProcessGradConfig:
+    """PG:20-34."""
+
+    def __init__(self, *args, use_sr: bool = True, sr_config: SRConfig = None, clip_grad_norm: bool = True,
+                 clip_grad_norm_value: float = 1.0, renorm_grad: bool = False, **kwargs):
+        self.use_sr = use_sr
+        self.sr_config = sr_config if sr_config is not None else SRConfig()
+        self.clip_grad_norm, self.clip_grad_norm_value, self.renorm_grad = clip_grad_norm, clip_grad_norm_value, renorm_grad
+
+
+class ProcessGradMetrics:
+    def __init__(self):
+        self.sr_metrics, self.proc_grad_time = SRMetrics(), np.nan
+
+
+def process_grad(wf=None, sampling_result: SamplingResult = None, config: ProcessGradConfig = None):
+    """PG:55-70."""
+    config = config if config is not None else ProcessGradConfig()
+    metrics = ProcessGradMetrics()
+    if config.use_sr:
+        wf.cat_grad, metrics.sr_metrics, sr_time = sr(wf=wf, sampling_result=sampling_result, config=config.sr_config)
+        metrics.sr_metrics.sr_time = sr_time
+    if config.clip_grad_norm:
+        wf.clip_grad_norm(config.clip_grad_norm_value)
+    if config.renorm_grad:
+        wf.cat_grad = wf.cat_grad / pt.linalg.norm(wf.cat_grad)
+    return metrics

@@ -360,6 +360,19 @@ def _vmc_case(name, n, n_el, n_irreps, sample_num, seed):
         out.update(amps=amps.detach().numpy(), eloc=est.values.numpy(), energy_mean=complex(est.mean), energy_var=complex(est.var),
                    loss=float(loss), grad_proj=proj @ grad, grad_norm=float(np.linalg.norm(grad)), grad_head=grad[:64].copy(),
                    grad_tail=grad[-64:].copy())
+        # gradient post-processing (PG:55-70): stochastic reconfiguration on the top-25 samples (SR:88-136) + clipping
+        jac = wf.compute_cat_log_jac(indices[:8])
+        jproj = np.random.default_rng(seed + 5).standard_normal((grad.shape[0], 4))
+        out.update(log_jac_proj=(jac.detach().numpy() @ jproj), log_jac_head=jac.detach().numpy()[:, :32].copy())
+        ref.process_grad(wf=wf, sampling_result=sr, config=ref.ProcessGradConfig())
+        g_sr = wf.cat_grad.numpy()
+        out.update(sr_grad_proj=proj @ g_sr, sr_grad_norm=float(np.linalg.norm(g_sr)), sr_grad_head=g_sr[:64].copy())
+        # the same without regularisation (pseudo-inverse branch) on a fresh gradient
+        wf.cat_grad = torch.from_numpy(grad.copy())
+        ref.process_grad(wf=wf, sampling_result=sr, config=ref.ProcessGradConfig(sr_config=ref.SRConfig(use_reg=False, max_indices_num=10),
+                                                                                clip_grad_norm=False, renorm_grad=True))
+        g_sr2 = wf.cat_grad.numpy()
+        out.update(sr2_grad_proj=proj @ g_sr2, sr2_grad_norm=float(np.linalg.norm(g_sr2)))
         # the full (not sample-aware) local energy through the old code path (CLE:117-163 -> PO:326-393, 992-1105)
         cfg_old = ref.LocalEnergyCalculationConfig(use_tree_for_candidates='ham', code_version='old')
         le_full, metrics = ref.compute_local_energies(wf=wf, sampling_result=sr, sampled_amps=amps.detach(), ham=ham, config=cfg_old,

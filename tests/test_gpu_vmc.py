@@ -12,7 +12,7 @@ from conftest import load_golden
 from anqs_quantum_chemistry_b200 import (HilbertSpace, PauliObservable, PauliArraysOperator, ParticleNumberSymmetry,
                                          SpinHalfProjectionSymmetry, LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig,
                                          SamplingConfig, SamplingResult, sample, LocalEnergyCalculationConfig,
-                                         compute_local_energies, vmc_loss, synthetic)
+                                         compute_local_energies, vmc_loss, synthetic, SRConfig, ProcessGradConfig, process_grad)
 from oracle.make_golden import made_weights
 
 pytestmark = pytest.mark.gpu
@@ -69,6 +69,23 @@ def test_vmc_iteration_matches_reference(name):
     assert abs(np.linalg.norm(grad) - float(g['grad_norm'])) < 1e-10 * gs
     assert np.abs(proj @ grad - g['grad_proj']).max() < 1e-9 * gs
     assert np.abs(grad[:64] - g['grad_head']).max() < 1e-10 * gs and np.abs(grad[-64:] - g['grad_tail']).max() < 1e-10 * gs
+    # gradient post-processing (PG:55-70): per-sample log-Jacobian, SR on the top-25 samples, clipping
+    jac = wf.compute_cat_log_jac(indices[:8]).cpu().numpy()
+    jproj = np.random.default_rng(int(g['weight_seed']) + 5).standard_normal((grad.shape[0], 4))
+    assert np.abs(jac[:, :32] - g['log_jac_head']).max() < 1e-10
+    assert np.abs(jac @ jproj - g['log_jac_proj']).max() < 1e-9 * max(1.0, np.abs(g['log_jac_proj']).max())
+    raw = wf.cat_grad.clone()
+    process_grad(wf=wf, sampling_result=sr, config=ProcessGradConfig())
+    g_sr = wf.cat_grad.cpu().numpy()
+    assert abs(np.linalg.norm(g_sr) - float(g['sr_grad_norm'])) < 1e-8
+    assert np.abs(proj @ g_sr - g['sr_grad_proj']).max() < 1e-7 * max(1.0, np.abs(g['sr_grad_proj']).max())
+    assert np.abs(g_sr[:64] - g['sr_grad_head']).max() < 1e-7
+    wf.cat_grad = raw
+    process_grad(wf=wf, sampling_result=sr, config=ProcessGradConfig(sr_config=SRConfig(use_reg=False, max_indices_num=10),
+                                                                      clip_grad_norm=False, renorm_grad=True))
+    g_sr2 = wf.cat_grad.cpu().numpy()
+    assert abs(np.linalg.norm(g_sr2) - 1.0) < 1e-12
+    assert np.abs(proj @ g_sr2 - g['sr2_grad_proj']).max() < 1e-6 * max(1.0, np.abs(g['sr2_grad_proj']).max())
     # the full (not sample-aware) local energy: de-duplicated non-sampled x', amplitudes from the network (PO:992-1105)
     for version in ('old', 'new'):
         le_full, metrics = compute_local_energies(wf=wf, sampling_result=sr, sampled_amps=amps.detach(), ham=ham,
