@@ -28,6 +28,10 @@ _SIGNATURES = {
     'anqs_scan_workspace': (ctypes.c_size_t, [_c_i64]),
     'anqs_exclusive_scan_i64': (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
     'anqs_k1_emit': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),
+    'anqs_k1_enum_tiles': (_c_int, [_vp]),
+    'anqs_k1_enum_workspace': (ctypes.c_size_t, [_vp, _c_i64]),
+    'anqs_k1_enum_filter': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp]),
+    'anqs_k1_enum_emit': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_matrix_elements': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
     'anqs_hash_capacity': (_c_i64, [_c_i64]),
     'anqs_hash_bytes': (ctypes.c_size_t, [_c_i64]),

@@ -130,7 +130,7 @@ constexpr uint32_t PROD_SINGLE_MAX = 2;         // rows with <= this many member
 
 struct HostProd {
     std::vector<ProdTile> tiles;
-    std::vector<uint8_t> blob;
+    std::vector<uint8_t> blob, blob_u;  // blob_u: the same records with the mask index u in place of the hashes
     std::vector<uint32_t> row_u, mem_u;
     uint32_t tile_bytes_max = 0;
 };
@@ -191,20 +191,23 @@ static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostP
         tile.n_single = (uint32_t)ts.size();
         tile.row_base = row_base;
         tile.member_base = member_base;
-        std::vector<RowRec> rows;
-        std::vector<MemRec> mems;
+        std::vector<RowRec> rows, rows_u;
+        std::vector<MemRec> mems, mems_u;
         for (auto &c : tm) {
             const uint32_t pa = ms[c.begin].pa;
             rows.push_back({pa, lin_host(LIN_LINE, pa), (uint32_t)mems.size(), (uint32_t)(c.end - c.begin)});
+            rows_u.push_back(rows.back());
             out.row_u.push_back(0);
             for (size_t k = c.begin; k < c.end; ++k) {
                 mems.push_back({ms[k].mb, ms[k].hash});
+                mems_u.push_back({ms[k].mb, ms[k].u});
                 out.mem_u.push_back(ms[k].u);
             }
         }
         for (auto &c : ts) {
             const M &m = ms[c.begin];
             rows.push_back({m.pa, lin_host(LIN_LINE, m.pa), m.mb, m.hash});
+            rows_u.push_back({m.pa, 0u, m.mb, m.u});
             out.row_u.push_back(m.u);
         }
         tile.n_members = (uint32_t)mems.size();
@@ -214,6 +217,9 @@ static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostP
         out.blob.resize(off + nbytes, 0);
         std::memcpy(out.blob.data() + off, rows.data(), rows.size() * sizeof(RowRec));
         std::memcpy(out.blob.data() + off + rows.size() * sizeof(RowRec), mems.data(), mems.size() * sizeof(MemRec));
+        out.blob_u.resize(off + nbytes, 0);
+        std::memcpy(out.blob_u.data() + off, rows_u.data(), rows_u.size() * sizeof(RowRec));
+        std::memcpy(out.blob_u.data() + off + rows_u.size() * sizeof(RowRec), mems_u.data(), mems_u.size() * sizeof(MemRec));
         tile.blob_off = (uint32_t)off;
         tile.blob_bytes = (uint32_t)nbytes;
         out.tile_bytes_max = std::max(out.tile_bytes_max, tile.blob_bytes);
@@ -222,6 +228,151 @@ static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostP
         member_base += (uint32_t)mems.size();
     }
     if (out.mem_u.empty()) out.mem_u.push_back(0);
+}
+
+// ---- enumeration tiles (Tables::enum_*, consumed by k1_enum.cu) -----------------------------------------------
+constexpr uint32_t ENUM_TILE_MAX = 188 * 1024;  // bytes of shared memory one enumeration tile may take
+
+struct HostEnum {
+    std::vector<EnumTile> tiles;
+    std::vector<uint8_t> blob;
+    uint32_t tile_bytes_max = 0;
+    bool ok = true;
+};
+
+// Pattern-type analysis of one YZ group (see EnumTile in common.cuh).  Returns nbits (0 = generic) and fills pos / zbase /
+// table (2^nbits entries, re and im).
+static int analyse_group(uint64_t xy, const int64_t *yz, const double *wre, const double *wim, int num, int pos[3],
+                         uint64_t *zbase, std::vector<double> &tre, std::vector<double> &tim) {
+    const uint64_t EVEN = 0x5555555555555555ULL;
+    const int ka = __builtin_popcountll(xy & EVEN), kb = __builtin_popcountll(xy & ~EVEN);
+    if (num < 1 || num > ENUM_PATTERN_MAX_TERMS || ka + kb == 0 || ka + kb > 4 || (ka & 1) || (kb & 1)) return 0;
+    for (int t = 0; t < num; ++t)
+        if (((uint64_t)yz[t] ^ (uint64_t)yz[0]) & ~xy) return 0;
+    *zbase = (uint64_t)yz[0] & ~xy;
+    // index positions: every position of the mask except the highest of each spin part
+    std::vector<int> pa, pb, idxpos;
+    for (int b = 0; b < 64; ++b)
+        if ((xy >> b) & 1) ((b & 1) ? pb : pa).push_back(b);
+    for (size_t i = 0; i + 1 < pa.size(); ++i) idxpos.push_back(pa[i]);
+    for (size_t i = 0; i + 1 < pb.size(); ++i) idxpos.push_back(pb[i]);
+    const int nbits = (int)idxpos.size();  // 1 (2,0) | 2 (2,2) | 3 (4,0)
+    for (int i = 0; i < 3; ++i) pos[i] = i < nbits ? idxpos[i] : 0;
+    tre.assign((size_t)1 << nbits, 0.0);
+    tim.assign((size_t)1 << nbits, 0.0);
+    for (int idx = 0; idx < (1 << nbits); ++idx) {
+        uint64_t b = 0;
+        for (int i = 0; i < nbits; ++i)
+            if ((idx >> i) & 1) b |= 1ULL << idxpos[i];
+        bool valid = true;
+        for (const std::vector<int> *part : {&pa, &pb}) {
+            if (part->empty()) continue;
+            int occ = 0;
+            for (size_t i = 0; i + 1 < part->size(); ++i) occ += (int)((b >> (*part)[i]) & 1);
+            const int top = (int)part->size() / 2 - occ;  // implied occupation of the highest position
+            if (top < 0 || top > 1) valid = false;
+            else if (top) b |= 1ULL << part->back();
+        }
+        if (!valid) continue;  // never addressed by a sample of the sector
+        double sr = 0.0, si = 0.0;
+        for (int t = 0; t < num; ++t) {
+            const double sgn = (__builtin_popcountll(b & (uint64_t)yz[t] & xy) & 1) ? -1.0 : 1.0;
+            sr += sgn * wre[t];
+            si += sgn * wim[t];
+        }
+        tre[idx] = sr;
+        tim[idx] = si;
+    }
+    return nbits;
+}
+
+static void build_enum_tiles(const std::vector<uint64_t> &xy, const std::vector<int2> &grp, int64_t U_pad,
+                             const int64_t *h_yz, const std::vector<double> &wre, const std::vector<double> &wim, bool real,
+                             HostEnum &out) {
+    // per-mask analysis
+    struct MaskInfo { int nbits; int pos[3]; uint64_t zbase; std::vector<double> tre, tim; };
+    std::vector<MaskInfo> info((size_t)U_pad);
+    std::vector<size_t> mask_bytes((size_t)U_pad);
+    for (int64_t u = 0; u < U_pad; ++u) {
+        MaskInfo &mi = info[u];
+        mi.zbase = 0;
+        mi.nbits = analyse_group(xy[u], h_yz + grp[u].x, wre.data() + grp[u].x, wim.data() + grp[u].x, grp[u].y, mi.pos, &mi.zbase,
+                                 mi.tre, mi.tim);
+        if (grp[u].y > ENUM_MAX_GROUP) out.ok = false;
+        mask_bytes[u] = 24 + (mi.nbits ? ((size_t)8 << mi.nbits) * (real ? 1 : 2) : (size_t)grp[u].y * (real ? 16 : 24));
+    }
+    const int64_t nblocks = U_pad / 32;
+    std::vector<size_t> block_bytes((size_t)nblocks);
+    size_t total = 0;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        size_t bytes = 0;
+        for (int64_t u = b * 32; u < b * 32 + 32; ++u) bytes += mask_bytes[u];
+        block_bytes[b] = bytes;
+        if (bytes + 128 > ENUM_TILE_MAX) out.ok = false;
+        total += bytes;
+    }
+    if (!out.ok) return;
+    const size_t budget = ENUM_TILE_MAX - 128;
+    const size_t n_tiles = std::max<size_t>(1, (total + budget - 4096 - 1) / (budget - 4096));
+    const size_t target = (total + n_tiles - 1) / n_tiles;
+    int64_t b = 0;
+    while (b < nblocks) {
+        const int64_t b0 = b;
+        size_t bytes = 0;
+        while (b < nblocks && (b == b0 || (bytes < target && bytes + block_bytes[b] <= budget))) bytes += block_bytes[b++];
+        EnumTile tile{};
+        tile.u0 = (uint32_t)(b0 * 32);
+        tile.n_masks = (uint32_t)((b - b0) * 32);
+        tile.word0 = (uint32_t)b0;
+        tile.n_words = (uint32_t)(b - b0);
+        std::vector<uint64_t> txy(tile.n_masks), tzb(tile.n_masks);
+        std::vector<uint2> tdesc(tile.n_masks);
+        std::vector<double> tab_re, tab_im, tim;
+        std::vector<ulonglong2> trec;
+        for (uint32_t k = 0; k < tile.n_masks; ++k) {
+            const int64_t u = (int64_t)tile.u0 + k;
+            const MaskInfo &mi = info[u];
+            txy[k] = xy[u];
+            tzb[k] = mi.zbase;
+            if (mi.nbits) {
+                tdesc[k] = make_uint2((uint32_t)tab_re.size(),
+                                      (uint32_t)mi.nbits | ((uint32_t)mi.pos[0] << 2) | ((uint32_t)mi.pos[1] << 8) | ((uint32_t)mi.pos[2] << 14));
+                tab_re.insert(tab_re.end(), mi.tre.begin(), mi.tre.end());
+                if (!real) tab_im.insert(tab_im.end(), mi.tim.begin(), mi.tim.end());
+            } else {
+                tdesc[k] = make_uint2((uint32_t)trec.size(), (uint32_t)grp[u].y << 2);
+                for (int j = grp[u].x; j < grp[u].x + grp[u].y; ++j) {
+                    unsigned long long bits;
+                    std::memcpy(&bits, &wre[j], 8);
+                    trec.push_back(make_ulonglong2((unsigned long long)h_yz[j], bits));
+                    if (!real) tim.push_back(wim[j]);
+                }
+            }
+        }
+        tile.n_tab = (uint32_t)tab_re.size();
+        tile.n_terms = (uint32_t)trec.size();
+        auto align16 = [](size_t v) { return (v + 15) / 16 * 16; };
+        const size_t tab_off = (size_t)tile.n_masks * 24;
+        const size_t term_off = align16(tab_off + (tab_re.size() + tab_im.size()) * 8);
+        const size_t nbytes = align16(term_off + trec.size() * 16 + tim.size() * 8);
+        tile.tab_off = (uint32_t)tab_off;
+        tile.term_off = (uint32_t)term_off;
+        if (nbytes > ENUM_TILE_MAX) out.ok = false;
+        const size_t off = (out.blob.size() + 127) / 128 * 128;
+        out.blob.resize(off + nbytes, 0);
+        uint8_t *base = out.blob.data() + off;
+        std::memcpy(base, txy.data(), txy.size() * 8);
+        std::memcpy(base + txy.size() * 8, tzb.data(), tzb.size() * 8);
+        std::memcpy(base + txy.size() * 16, tdesc.data(), tdesc.size() * 8);
+        if (!tab_re.empty()) std::memcpy(base + tab_off, tab_re.data(), tab_re.size() * 8);
+        if (!tab_im.empty()) std::memcpy(base + tab_off + tab_re.size() * 8, tab_im.data(), tab_im.size() * 8);
+        if (!trec.empty()) std::memcpy(base + term_off, trec.data(), trec.size() * 16);
+        if (!tim.empty()) std::memcpy(base + term_off + trec.size() * 16, tim.data(), tim.size() * 8);
+        tile.blob_off = (uint32_t)off;
+        tile.blob_bytes = (uint32_t)nbytes;
+        out.tile_bytes_max = std::max(out.tile_bytes_max, tile.blob_bytes);
+        out.tiles.push_back(tile);
+    }
 }
 
 }  // namespace anqs
@@ -360,6 +511,15 @@ int anqs_tables_create(anqs_tables_t **out, int qubit_num, int64_t U, int64_t T,
     if (e == cudaSuccess) e = up((void **)&t->prod_blob, prod.blob.data(), prod.blob.size());
     if (e == cudaSuccess) e = up((void **)&t->prod_row_u, prod.row_u.data(), prod.row_u.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = up((void **)&t->prod_mem_u, prod.mem_u.data(), prod.mem_u.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = up((void **)&t->prod_blob_u, prod.blob_u.data(), prod.blob_u.size());
+    HostEnum en;
+    build_enum_tiles(xy, grp, t->U_pad, h_yz, wre, wim, real, en);
+    if (en.ok) {
+        t->n_enum_tiles = (int)en.tiles.size();
+        t->enum_tile_bytes_max = (int)en.tile_bytes_max;
+        if (e == cudaSuccess) e = up((void **)&t->enum_tiles, en.tiles.data(), en.tiles.size() * sizeof(EnumTile));
+        if (e == cudaSuccess) e = up((void **)&t->enum_blob, en.blob.data(), en.blob.size());
+    }
     if (e != cudaSuccess) {
         anqs_tables_destroy((anqs_tables_t *)t);
         set_error(std::string("anqs_tables_create: device upload failed: ") + cudaGetErrorString(e));
@@ -383,6 +543,9 @@ int anqs_tables_destroy(anqs_tables_t *h) {
     cudaFree(t->prod_blob);
     cudaFree(t->prod_row_u);
     cudaFree(t->prod_mem_u);
+    cudaFree(t->prod_blob_u);
+    cudaFree(t->enum_tiles);
+    cudaFree(t->enum_blob);
     delete t;
     return 0;
 }

@@ -51,7 +51,31 @@ struct MemRec {            // 8 bytes
     uint32_t mb;           // beta part
     uint32_t hash;         // lin(LIN_POSA, pa) ^ lin(LIN_POSB, mb)
 };
-
+// Enumeration tile (k1_enum.cu): a contiguous range of XY masks [u0, u0 + n_masks) with everything their matrix elements
+// need, sized to live in shared memory.  Blob layout (one bulk copy), every section 16-byte aligned:
+//   [xy: n_masks x 8 B][zbase: n_masks x 8 B][desc: n_masks x 8 B]
+//   [pattern tables: n_tab x 8 B (re)][n_tab x 8 B (im) when weights are complex]
+//   [term records: n_terms x 16 B = {yz (original bit order), bits(w_re)}][w_im: n_terms x 8 B when complex]
+// A YZ group is of PATTERN type when all its terms differ only on the XY positions of its mask (true for every
+// four-position group of a Jordan-Wigner molecular Hamiltonian): then
+//   H_{x,x'} = (-1)^popcount(x' & zbase) * G[idx],   idx = the bits of x' at <= 3 "index positions" of the mask,
+// with G precomputed at table-build time - one 8-byte load and one POPC per connection instead of one 16-byte record and
+// one POPC per term.  idx leaves out the highest alpha and the highest beta position of the mask: for a sample inside the
+// (N_alpha, N_beta) sector those bits are implied by the electron counts (the kernel checks the sample and falls back to
+// the term records in global memory otherwise).
+//   desc.x = first table entry (pattern) | first term record (generic), tile-local
+//   desc.y = nbits (2 bits; 0 = generic) | pattern: p0 << 2 | p1 << 8 | p2 << 14 | generic: num << 2
+struct EnumTile {
+    uint32_t blob_off;     // byte offset in enum_blob (multiple of 128)
+    uint32_t blob_bytes;   // multiple of 16
+    uint32_t u0, n_masks;  // u0 and n_masks are multiples of 32
+    uint32_t n_tab, n_terms;
+    uint32_t tab_off, term_off;  // byte offsets inside the tile
+    uint32_t word0, n_words;     // the tile's slice of a bitmap row
+    uint32_t pad0, pad1;
+};
+constexpr int ENUM_MAX_GROUP = (1 << 24) - 1;  // longest YZ group the tiled path handles (it also has to fit a tile)
+constexpr int ENUM_PATTERN_MAX_TERMS = 64;     // longer groups stay generic (their tables would not save anything)
 // Device-resident Hamiltonian tables (reference tensors PO:103-115, re-laid-out for the kernels).
 struct Tables {
     int qubit_num;
@@ -82,6 +106,14 @@ struct Tables {
     uint8_t *prod_blob;       // tile blobs, each 128-byte aligned (device)
     uint32_t *prod_row_u;     // [total rows]    mask index u of a singleton row (device)
     uint32_t *prod_mem_u;     // [total members] mask index u of a member (device)
+
+    // ---- enumeration layouts (k1_enum.cu) ------------------------------------------------------------------
+    uint8_t *prod_blob_u;     // same tiles as prod_blob with the mask index u in place of the hashes
+                              // (MemRec::hash and the singleton RowRec::b)
+    int n_enum_tiles;         // 0: the tiled enumeration is unavailable for this table (a YZ group does not fit)
+    int enum_tile_bytes_max;
+    EnumTile *enum_tiles;     // [n_enum_tiles] directory (device)
+    uint8_t *enum_blob;       // tile blobs, each 128-byte aligned (device)
 };
 
 // ---- sampled-set lookup table (kernel family 2) ------------------------------------------------------

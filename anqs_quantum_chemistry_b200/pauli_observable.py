@@ -166,7 +166,14 @@ class PauliObservable(AbstractHilbertSpaceObject):
             self._tables = handle
             self.weights_real = bool(info[3].value)
             self.bitmap_row_words = int(info[4].value)
+            self._enum_tiles = int(_lib.lib().anqs_k1_enum_tiles(handle))
         return self._tables
+
+    @property
+    def enum_tiles(self) -> int:
+        """Number of shared-memory tiles of the tiled enumeration (k1_enum.cu); 0 = the table does not fit it."""
+        self.tables
+        return self._enum_tiles
 
     def __del__(self):
         try:
@@ -178,18 +185,30 @@ class PauliObservable(AbstractHilbertSpaceObject):
 
     # ---- kernel 1: connected configurations -------------------------------------------------------------
     def connected_configurations(self, samples: pt.Tensor, alpha_num: int, beta_num: int, with_dest: bool = True,
-                                 with_xy_ptr: bool = True, matrix_elements: str = None):
+                                 with_xy_ptr: bool = True, matrix_elements: str = None, tiled: bool = None):
         """Connected list of a batch of packed samples [n] int64, lexicographic in (dest, xy_ptr) like
         PO:527-567.  matrix_elements in (None, 'real', 'complex').  Returns a dict with offsets [n+1] int64,
-        dest int32 [M], xprime int64 [M], xy_ptr int32 [M], H."""
+        dest int32 [M], xprime int64 [M], xy_ptr int32 [M], H.
+        tiled: None = the tile-resident kernels (k1_enum.cu) whenever the table fits them, else the untiled pair
+        (k1_connected.cu); True / False force one or the other.  Both give the same list bit for bit."""
         tables = self.tables
         dev = self.device
         samples = samples.contiguous().view(-1)
         n = samples.shape[0]
         lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        if tiled is None:
+            tiled = self.enum_tiles > 0
+        elif tiled and self.enum_tiles == 0:
+            raise RuntimeError('the tiled enumeration is unavailable for this Hamiltonian table')
         counts = pt.empty(n, dtype=pt.int64, device=dev)
         bitmap = pt.empty(n * self.bitmap_row_words, dtype=pt.int32, device=dev)
-        _lib.check(lib.anqs_k1_filter(tables, _lib.dptr(samples), n, alpha_num, beta_num, _lib.dptr(counts), _lib.dptr(bitmap), sp))
+        enum_work = None
+        if tiled:
+            enum_work = pt.empty(max(1, (int(lib.anqs_k1_enum_workspace(tables, n)) + 3) // 4), dtype=pt.int32, device=dev)
+            _lib.check(lib.anqs_k1_enum_filter(tables, _lib.dptr(samples), n, alpha_num, beta_num, _lib.dptr(counts), _lib.dptr(bitmap),
+                                               _lib.dptr(enum_work), sp))
+        else:
+            _lib.check(lib.anqs_k1_filter(tables, _lib.dptr(samples), n, alpha_num, beta_num, _lib.dptr(counts), _lib.dptr(bitmap), sp))
         offsets = pt.empty(n + 1, dtype=pt.int64, device=dev)
         work = pt.empty(max(1, int(lib.anqs_scan_workspace(n)) // 8), dtype=pt.int64, device=dev)
         _lib.check(lib.anqs_exclusive_scan_i64(_lib.dptr(counts), _lib.dptr(offsets), n, _lib.dptr(work), sp))
@@ -207,8 +226,12 @@ class PauliObservable(AbstractHilbertSpaceObject):
         h_ptr = _lib.dptr(pt.view_as_real(out['H'])) if hc == 2 else _lib.dptr(out['H'])
         if m == 0:
             return out
-        _lib.check(lib.anqs_k1_emit(tables, _lib.dptr(samples), n, _lib.dptr(bitmap), _lib.dptr(offsets), _lib.dptr(out['dest']),
-                                    _lib.dptr(out['xprime']), _lib.dptr(out['xy_ptr']), h_ptr, hc, sp))
+        if tiled:
+            _lib.check(lib.anqs_k1_enum_emit(tables, _lib.dptr(samples), n, alpha_num, beta_num, _lib.dptr(bitmap), _lib.dptr(offsets), _lib.dptr(enum_work),
+                                             _lib.dptr(out['dest']), _lib.dptr(out['xprime']), _lib.dptr(out['xy_ptr']), h_ptr, hc, sp))
+        else:
+            _lib.check(lib.anqs_k1_emit(tables, _lib.dptr(samples), n, _lib.dptr(bitmap), _lib.dptr(offsets), _lib.dptr(out['dest']),
+                                        _lib.dptr(out['xprime']), _lib.dptr(out['xy_ptr']), h_ptr, hc, sp))
         return out
 
     # ---- reference method surface -----------------------------------------------------------------------

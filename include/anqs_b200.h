@@ -81,6 +81,22 @@ int anqs_k1_emit(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, co
                  const int64_t *d_offsets, int32_t *d_dest, int64_t *d_xprime, int32_t *d_xy_ptr,
                  double *d_H, int h_components, void *stream);
 
+/* ---- A2+A3+A6  kernel 1, tiled variant: the same ordered list at HBM-write speed (PO:527-567 + PO:256-324) ---------
+ * Same bitmap, counts and output rows as anqs_k1_filter / anqs_k1_emit (the two pairs are interchangeable bit for bit); the
+ * masks are cut into "enumeration tiles" (contiguous mask ranges with the term records of their YZ groups) that a CTA keeps
+ * resident in shared memory, so matrix-element sums never go to L2.  anqs_k1_enum_tiles() == 0 means the table does not
+ * fit the tiled layout (a YZ group larger than a tile, or bitmap rows too long for shared memory): use the pair above.
+ * d_work: anqs_k1_enum_workspace(t, n) bytes, 128-byte aligned, written by the filter (the rank of every tile's first
+ * connection inside each sample) and consumed by the emit; both calls must be ordered on the same stream.
+ * d_counts and d_bitmap are mandatory here; d_offsets = exclusive scan of d_counts (anqs_exclusive_scan_i64). */
+int anqs_k1_enum_tiles(const anqs_tables_t *t);
+size_t anqs_k1_enum_workspace(const anqs_tables_t *t, int64_t n);
+int anqs_k1_enum_filter(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
+                        int64_t *d_counts, uint32_t *d_bitmap, void *d_work, void *stream);
+int anqs_k1_enum_emit(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
+                      const uint32_t *d_bitmap, const int64_t *d_offsets, void *d_work, int32_t *d_dest, int64_t *d_xprime, int32_t *d_xy_ptr,
+                      double *d_H, int h_components, void *stream);
+
 /* ---- A6  PauliObservable.compute_matrix_elements (PO:256-324) on an arbitrary (x', xy_ptr) list ------ */
 int anqs_matrix_elements(const anqs_tables_t *t, const int64_t *d_xprime, const int64_t *d_xy_ptr, int64_t m,
                          double *d_H /* m complex128 */, void *stream);
