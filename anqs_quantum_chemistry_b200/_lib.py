@@ -29,6 +29,7 @@ _SIGNATURES = {
     'anqs_exclusive_scan_i64': (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
     'anqs_k1_emit': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_k1_enum_tiles': (_c_int, [_vp]),
+    'anqs_k1_enum_force_product_filter': (None, [_c_int]),
     'anqs_k1_enum_workspace': (ctypes.c_size_t, [_vp, _c_i64]),
     'anqs_k1_enum_filter': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp]),
     'anqs_k1_enum_emit': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),

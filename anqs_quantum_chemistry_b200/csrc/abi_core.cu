@@ -231,7 +231,6 @@ static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostP
 }
 
 // ---- enumeration tiles (Tables::enum_*, consumed by k1_enum.cu) -----------------------------------------------
-constexpr uint32_t ENUM_TILE_MAX = 188 * 1024;  // bytes of shared memory one enumeration tile may take
 
 struct HostEnum {
     std::vector<EnumTile> tiles;
@@ -512,6 +511,24 @@ int anqs_tables_create(anqs_tables_t **out, int qubit_num, int64_t U, int64_t T,
     if (e == cudaSuccess) e = up((void **)&t->prod_row_u, prod.row_u.data(), prod.row_u.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = up((void **)&t->prod_mem_u, prod.mem_u.data(), prod.mem_u.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = up((void **)&t->prod_blob_u, prod.blob_u.data(), prod.blob_u.size());
+    {   // bit-sliced filter positions
+        const uint64_t EVEN = 0x5555555555555555ULL;
+        std::vector<uint2> bs((size_t)t->U_pad, make_uint2(0x40404040u, 0x40404040u));
+        t->bs_ok = 1;
+        auto part = [&](uint64_t bits) -> uint32_t {
+            const int k = __builtin_popcountll(bits);
+            if (k & 1) return 0x40404040u;   // can never hold half of its positions occupied
+            if (k > 4) { t->bs_ok = 0; return 0x40404040u; }
+            uint32_t b[4] = {64, 64, 65, 65};
+            int i = 0;
+            for (int pos = 0; pos < 64; ++pos)
+                if ((bits >> pos) & 1) b[i++] = (uint32_t)pos;
+            if (k == 2) { b[2] = 64; b[3] = 65; }
+            return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        };
+        for (int64_t u = 0; u < U; ++u) bs[u] = make_uint2(part(xy[u] & EVEN), part(xy[u] & ~EVEN));
+        if (e == cudaSuccess) e = up((void **)&t->bs_pos, bs.data(), bs.size() * sizeof(uint2));
+    }
     HostEnum en;
     build_enum_tiles(xy, grp, t->U_pad, h_yz, wre, wim, real, en);
     if (en.ok) {
@@ -544,6 +561,7 @@ int anqs_tables_destroy(anqs_tables_t *h) {
     cudaFree(t->prod_row_u);
     cudaFree(t->prod_mem_u);
     cudaFree(t->prod_blob_u);
+    cudaFree(t->bs_pos);
     cudaFree(t->enum_tiles);
     cudaFree(t->enum_blob);
     delete t;

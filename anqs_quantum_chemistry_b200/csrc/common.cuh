@@ -74,6 +74,12 @@ struct EnumTile {
     uint32_t word0, n_words;     // the tile's slice of a bitmap row
     uint32_t pad0, pad1;
 };
+// shared-memory budget of enum_emit_kernel: per-warp queues of tile-local mask indices + one resident tile
+constexpr int ENUM_EMIT_WARPS = 32;
+constexpr int ENUM_STEP_WORDS = 32;                        // bitmap words expanded per step
+constexpr int ENUM_QCAP = ENUM_STEP_WORDS * 32 + 32;       // queued indices per warp
+constexpr int ENUM_QUEUE_BYTES = ENUM_EMIT_WARPS * ENUM_QCAP * 2;
+constexpr uint32_t ENUM_TILE_MAX = 227 * 1024 - ENUM_QUEUE_BYTES - 1024;  // bytes one enumeration tile may take
 constexpr int ENUM_MAX_GROUP = (1 << 24) - 1;  // longest YZ group the tiled path handles (it also has to fit a tile)
 constexpr int ENUM_PATTERN_MAX_TERMS = 64;     // longer groups stay generic (their tables would not save anything)
 // Device-resident Hamiltonian tables (reference tensors PO:103-115, re-laid-out for the kernels).
@@ -110,6 +116,11 @@ struct Tables {
     // ---- enumeration layouts (k1_enum.cu) ------------------------------------------------------------------
     uint8_t *prod_blob_u;     // same tiles as prod_blob with the mask index u in place of the hashes
                               // (MemRec::hash and the singleton RowRec::b)
+    // Bit-sliced filter: per mask the bit positions (in x) of its alpha part (4 bytes) and beta part (4 bytes), padded with
+    // the constant slices 64 (all zeros) / 65 (all ones) so that "exactly two of the four slices set" is the electron-count
+    // test of every part of weight 0, 2 or 4 (weight 0: {0,0,1,1}; weight 2: {p,q,0,1}; odd weights: {0,0,0,0} = never).
+    uint2 *bs_pos;            // [U_pad]
+    int bs_ok;                // 0: some part has an even weight > 4, the bit-sliced filter does not apply
     int n_enum_tiles;         // 0: the tiled enumeration is unavailable for this table (a YZ group does not fit)
     int enum_tile_bytes_max;
     EnumTile *enum_tiles;     // [n_enum_tiles] directory (device)

@@ -144,10 +144,127 @@ enum_filter_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int
     }
 }
 
+// ---- pass 1, bit-sliced: 32 samples per lane-operation -------------------------------------------------------------------
+// For a sample inside the (N_alpha, N_beta) sector, x' = x ^ xy keeps the electron counts iff exactly half of the positions of
+// the alpha part of the mask, and half of those of its beta part, are occupied in x.  With the samples of a group of 32
+// BIT-SLICED (slice i = bit i of the 32 samples, one ballot each), that test is a boolean function of <= 8 slices evaluated
+// for 32 samples at once: one lane = one mask, ~20 LOP3 and no POPC per 32 (sample, mask) pairs.  A 32 x 32 bit transpose
+// across the warp turns the 32 result words (mask-major) into the bitmap words of the 32 samples.  Samples outside the
+// sector (never produced by the masked samplers, but legal input) get their rows recomputed with the plain popcount test.
+constexpr int BS_THREADS = 512;
+constexpr int BS_WARPS = BS_THREADS / 32;
+
+__device__ __forceinline__ uint32_t exactly_two(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return ~(a ^ b ^ c ^ d) & ~(a & b & c & d) & (a | b | c | d);
+}
+
+// lane l holds row l of a 32 x 32 bit matrix; afterwards lane l holds column l
+__device__ __forceinline__ uint32_t transpose32(uint32_t w) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        const uint32_t mk = k == 16 ? 0x0000FFFFu : k == 8 ? 0x00FF00FFu : k == 4 ? 0x0F0F0F0Fu : k == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t p = __shfl_xor_sync(0xffffffffu, w, k);
+        w = (lane & k) ? ((w & ~mk) | ((p >> k) & mk)) : ((w & mk) | ((p & mk) << k));
+    }
+    return w;
+}
+
+__global__ void __launch_bounds__(BS_THREADS, 2)
+enum_filter_bitsliced_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int alpha, int beta,
+                             int64_t *__restrict__ counts, uint32_t *__restrict__ bitmap, int32_t *__restrict__ tile_prefix) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint32_t X[66];
+    __shared__ uint64_t s_x[32];
+    __shared__ uint32_t s_bad, s_valid;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int row_words = (int)t.row_words, stride = row_words | 1;  // odd stride: the 32 rows of a column hit 32 banks
+    uint32_t *rows = reinterpret_cast<uint32_t *>(smem_raw);
+    const int64_t ngroups = (n + 31) >> 5;
+    for (int64_t group = blockIdx.x; group < ngroups; group += gridDim.x) {
+        {   // slices: every warp reads the 32 samples and builds 64 / BS_WARPS of the slices
+            const int64_t r = group * 32 + lane;
+            const bool valid = r < n;
+            const uint64_t x = valid ? (uint64_t)samples[r] : 0ull;
+            constexpr int PER = 64 / BS_WARPS;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (x >> (warp * PER + i)) & 1ull);
+                if (lane == i) mine = b;
+            }
+            if (lane < PER) X[warp * PER + lane] = mine;
+            if (warp == 0) {
+                const bool insec = __popcll(x & 0x5555555555555555ULL) == alpha && __popcll(x & 0xAAAAAAAAAAAAAAAAULL) == beta;
+                s_x[lane] = x;
+                const uint32_t bad = __ballot_sync(0xffffffffu, valid && !insec), val = __ballot_sync(0xffffffffu, valid);
+                if (lane == 0) {
+                    X[64] = 0u;
+                    X[65] = 0xffffffffu;
+                    s_bad = bad;
+                    s_valid = val;
+                }
+            }
+        }
+        __syncthreads();
+        for (int j0 = warp; j0 < row_words; j0 += BS_WARPS * 4) {
+            uint2 pos[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = j0 + k * BS_WARPS;
+                pos[k] = j < row_words ? __ldg(t.bs_pos + (size_t)j * 32 + lane) : make_uint2(0x40404040u, 0x40404040u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = j0 + k * BS_WARPS;
+                if (j >= row_words) break;
+                const uint32_t fa = exactly_two(X[pos[k].x & 0xff], X[(pos[k].x >> 8) & 0xff], X[(pos[k].x >> 16) & 0xff], X[pos[k].x >> 24]);
+                const uint32_t fb = exactly_two(X[pos[k].y & 0xff], X[(pos[k].y >> 8) & 0xff], X[(pos[k].y >> 16) & 0xff], X[pos[k].y >> 24]);
+                rows[lane * stride + j] = transpose32(fa & fb);
+            }
+        }
+        __syncthreads();
+        const uint32_t bad = s_bad, valid = s_valid;
+        if (bad) {  // plain popcount test for the samples outside the sector (whole warp per sample)
+            for (int sidx = warp; sidx < 32; sidx += BS_WARPS) {
+                if (!((bad >> sidx) & 1u)) continue;
+                const uint64_t x = s_x[sidx];
+                const uint32_t xa = compress_even_bits(x), xb = compress_even_bits(x >> 1);
+                for (int j = 0; j < row_words; ++j) {
+                    const uint2 m = __ldg(t.mab + (size_t)j * 32 + lane);
+                    const bool p = (int64_t)j * 32 + lane < t.U && __popc(xa ^ m.x) == alpha && __popc(xb ^ m.y) == beta;
+                    const uint32_t b = __ballot_sync(0xffffffffu, p);
+                    if (lane == 0) rows[sidx * stride + j] = b;
+                }
+            }
+            __syncthreads();
+        }
+        for (int sidx = warp; sidx < 32; sidx += BS_WARPS) {
+            if (!((valid >> sidx) & 1u)) continue;
+            const int64_t r = group * 32 + sidx;
+            const uint32_t *bm = rows + sidx * stride;
+            int total = 0;
+            for (int e = 0; e < t.n_enum_tiles; ++e) {
+                const int w0 = (int)__ldg(&t.enum_tiles[e].word0), nw = (int)__ldg(&t.enum_tiles[e].n_words);
+                int c = 0;
+                for (int j = w0 + lane; j < w0 + nw; j += 32) c += __popc(bm[j]);
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0) tile_prefix[r * t.n_enum_tiles + e] = total;
+                total += c;
+            }
+            if (lane == 0) counts[r] = total;
+            uint32_t *row = bitmap + r * t.row_words;
+            for (int j = lane; j < row_words; j += 32) row[j] = bm[j];
+        }
+        __syncthreads();
+    }
+}
+
 // ---- pass 2: tile-resident ordered emit ------------------------------------------------------------------------------
-constexpr int ET_STEP_WORDS = 16;                 // bitmap words expanded per step
-constexpr int ET_QCAP = ET_STEP_WORDS * 32 + 32;  // queued tile-local mask indices per warp
-constexpr int ET_QUEUE_BYTES = EN_WARPS * ET_QCAP * 2;
+constexpr int ET_STEP_WORDS = ENUM_STEP_WORDS;
+constexpr int ET_QCAP = ENUM_QCAP;
+constexpr int ET_QUEUE_BYTES = ENUM_QUEUE_BYTES;
+static_assert(EN_WARPS == ENUM_EMIT_WARPS, "queue budget");
 constexpr uint32_t ET_BIG = 24;                   // YZ groups longer than this are summed by the whole warp
 
 struct EtTile {
@@ -302,25 +419,23 @@ enum_emit_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int a
             for (int j = 0; j < n_words; j += 32) {
                 const uint32_t wfull = wnext;
                 wnext = (j + 32 + lane < n_words) ? __ldg(row + j + 32 + lane) : 0u;
-#pragma unroll
-                for (int half = 0; half < 32; half += ET_STEP_WORDS) {
-                    uint32_t w = __shfl_sync(0xffffffffu, wfull, (lane + half) & 31);
-                    if (lane >= ET_STEP_WORDS) w = 0u;
+                {
+                    uint32_t w = wfull;
                     const int c = __popc(w);
                     int inc = c;
 #pragma unroll
-                    for (int d = 1; d < ET_STEP_WORDS; d <<= 1) {
+                    for (int d = 1; d < 32; d <<= 1) {
                         const int o = __shfl_up_sync(0xffffffffu, inc, d);
                         if (lane >= d) inc += o;
                     }
-                    const int total = __shfl_sync(0xffffffffu, inc, ET_STEP_WORDS - 1);
+                    const int total = __shfl_sync(0xffffffffu, inc, 31);
                     if (total == 0) continue;
-                    int p = qlen + inc - c;
-                    const uint32_t base = (uint32_t)(j + half + lane) << 5;
+                    uint16_t *qp = q + (qlen + inc - c);
+                    uint32_t base = (uint32_t)(j + lane) << 5;
                     while (w) {
                         const int bit = __ffs(w) - 1;
                         w &= w - 1;
-                        q[p++] = (uint16_t)(base + bit);
+                        *qp++ = (uint16_t)(base + bit);
                     }
                     __syncwarp();
                     qlen += total;
@@ -355,9 +470,15 @@ static int filter_warps(const Tables *t) {
     return (int)(w & ~3ll);
 }
 
+static size_t bitsliced_smem(const Tables *t) { return (size_t)32 * (size_t)(t->row_words | 1) * 4; }
+static bool bitsliced_available(const Tables *t) { return t->bs_ok && bitsliced_smem(t) + 1024 <= (size_t)EN_SMEM_MAX; }
+
 static bool tiled_available(const Tables *t) {
-    return t->n_enum_tiles > 0 && filter_warps(t) >= 4 && ET_QUEUE_BYTES + t->enum_tile_bytes_max + 256 <= EN_SMEM_MAX;
+    return t->n_enum_tiles > 0 && (bitsliced_available(t) || filter_warps(t) >= 4) &&
+           ET_QUEUE_BYTES + t->enum_tile_bytes_max + 256 <= EN_SMEM_MAX;
 }
+
+static bool g_force_product_filter = false;  // test hook (anqs_k1_enum_force_product_filter)
 
 static size_t counters_bytes(const Tables *t) { return ((size_t)t->n_enum_tiles * 4 + 127) / 128 * 128; }
 
@@ -373,6 +494,8 @@ int anqs_k1_enum_tiles(const anqs_tables_t *h) {
     return tiled_available(t) ? t->n_enum_tiles : 0;
 }
 
+void anqs_k1_enum_force_product_filter(int on) { g_force_product_filter = on != 0; }
+
 size_t anqs_k1_enum_workspace(const anqs_tables_t *h, int64_t n) {
     if (!h || n < 0) return 0;
     const Tables *t = (const Tables *)h;
@@ -387,6 +510,17 @@ int anqs_k1_enum_filter(const anqs_tables_t *h, const int64_t *d_samples, int64_
     const Tables *t = (const Tables *)h;
     ANQS_REQUIRE(tiled_available(t), "the tiled enumeration is unavailable for this table (anqs_k1_enum_tiles() == 0): use anqs_k1_filter / anqs_k1_emit");
     ANQS_REQUIRE(d_samples && d_counts && d_bitmap && d_work, "null pointer");
+    if (bitsliced_available(t) && !g_force_product_filter) {
+        const size_t smem = bitsliced_smem(t);
+        ANQS_CUDA(cudaFuncSetAttribute(enum_filter_bitsliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(EN_SMEM_MAX - 1024) / (smem + 1024)));
+        const int grid = (int)std::min<int64_t>((n + 31) / 32, (int64_t)sm_count_of_current_device() * per_sm);
+        int32_t *tile_prefix = reinterpret_cast<int32_t *>((unsigned char *)d_work + counters_bytes(t));
+        enum_filter_bitsliced_kernel<<<grid, BS_THREADS, smem, (cudaStream_t)stream>>>(*t, d_samples, n, alpha_num, beta_num, d_counts,
+                                                                                       d_bitmap, tile_prefix);
+        ANQS_LAUNCH_CHECK();
+        return 0;
+    }
     const int warps = filter_warps(t);
     const uint32_t bm_bytes = (uint32_t)(((size_t)warps * t->row_words * 4 + 127) / 128 * 128);
     const size_t smem = (size_t)bm_bytes + (size_t)t->tile_bytes_max;

@@ -187,18 +187,30 @@ def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     m = int(conn['xprime'].shape[0])
     counts, offsets, bitmap_words = conn['counts'], conn['offsets'], ham.bitmap_row_words
     bitmap = torch.empty(n * bitmap_words, dtype=torch.int32, device=dev)
-    t_filter = _time_ms(lambda: _lib.check(lib.anqs_k1_filter(ham.tables, _lib.dptr(rows), n, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), sp)))
-    t_emit = _time_ms(lambda: _lib.check(lib.anqs_k1_emit(ham.tables, _lib.dptr(rows), n, _lib.dptr(bitmap), _lib.dptr(offsets),
-                                                          _lib.dptr(conn['dest']), _lib.dptr(conn['xprime']), _lib.dptr(None),
-                                                          _lib.dptr(conn['H']), 1, sp)))
-    t_emit_noh = _time_ms(lambda: _lib.check(lib.anqs_k1_emit(ham.tables, _lib.dptr(rows), n, _lib.dptr(bitmap), _lib.dptr(offsets),
-                                                              _lib.dptr(conn['dest']), _lib.dptr(conn['xprime']), _lib.dptr(None),
-                                                              _lib.dptr(None), 0, sp)))
+    t_filter0 = _time_ms(lambda: _lib.check(lib.anqs_k1_filter(ham.tables, _lib.dptr(rows), n, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), sp)))
+    t_emit0 = _time_ms(lambda: _lib.check(lib.anqs_k1_emit(ham.tables, _lib.dptr(rows), n, _lib.dptr(bitmap), _lib.dptr(offsets),
+                                                           _lib.dptr(conn['dest']), _lib.dptr(conn['xprime']), _lib.dptr(None),
+                                                           _lib.dptr(conn['H']), 1, sp)))
     algo = 20.0 * m + 8.0 * n + 4.0 * bitmap_words * n * 2
-    out['enumeration'] = {'rows': n, 'connections': m, 'filter_ms': t_filter, 'emit_ms': t_emit, 'emit_without_H_ms': t_emit_noh,
-                          'connections_per_s': m / ((t_filter + t_emit) * 1e-3), 'achieved_gbs': algo / ((t_filter + t_emit) * 1e-3) / 1e9,
-                          'algorithmic_bytes': '20 B per emitted connection (x\' 8 + H 8 + dest 4) + bitmap write and read + 8 B per row',
-                          'bound': 'hbm'}
+    enum = {'rows': n, 'connections': m, 'untiled_filter_ms': t_filter0, 'untiled_emit_ms': t_emit0,
+            'algorithmic_bytes': '20 B per emitted connection (x\' 8 + H 8 + dest 4) + bitmap write and read + 8 B per row', 'bound': 'hbm'}
+    t_filter, t_emit = t_filter0, t_emit0
+    if ham.enum_tiles > 0:
+        work = torch.empty((int(lib.anqs_k1_enum_workspace(ham.tables, n)) + 3) // 4, dtype=torch.int32, device=dev)
+        t_filter = _time_ms(lambda: _lib.check(lib.anqs_k1_enum_filter(ham.tables, _lib.dptr(rows), n, na, nb, _lib.dptr(counts), _lib.dptr(bitmap),
+                                                                       _lib.dptr(work), sp)))
+        t_emit = _time_ms(lambda: _lib.check(lib.anqs_k1_enum_emit(ham.tables, _lib.dptr(rows), n, na, nb, _lib.dptr(bitmap), _lib.dptr(offsets),
+                                                                   _lib.dptr(work), _lib.dptr(conn['dest']), _lib.dptr(conn['xprime']), _lib.dptr(None),
+                                                                   _lib.dptr(conn['H']), 1, sp)))
+        t_emit_noh = _time_ms(lambda: _lib.check(lib.anqs_k1_enum_emit(ham.tables, _lib.dptr(rows), n, na, nb, _lib.dptr(bitmap), _lib.dptr(offsets),
+                                                                       _lib.dptr(work), _lib.dptr(conn['dest']), _lib.dptr(conn['xprime']),
+                                                                       _lib.dptr(None), _lib.dptr(None), 0, sp)))
+        enum.update({'enum_tiles': ham.enum_tiles, 'emit_without_H_ms': t_emit_noh,
+                     'kernels': 'enum_filter_bitsliced_kernel + enum_emit_kernel (k1_enum.cu); untiled pair timed beside'})
+        del work
+    enum.update({'filter_ms': t_filter, 'emit_ms': t_emit, 'connections_per_s': m / ((t_filter + t_emit) * 1e-3),
+                 'achieved_gbs': algo / ((t_filter + t_emit) * 1e-3) / 1e9})
+    out['enumeration'] = enum
     del conn, bitmap
     # ---- MADE amplitudes (fp64) and the count-splitting sampler at this qubit count
     masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=na + nb),

@@ -90,6 +90,9 @@ int anqs_k1_emit(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, co
  * connection inside each sample) and consumed by the emit; both calls must be ordered on the same stream.
  * d_counts and d_bitmap are mandatory here; d_offsets = exclusive scan of d_counts (anqs_exclusive_scan_i64). */
 int anqs_k1_enum_tiles(const anqs_tables_t *t);
+/* Test hook: the filter has two implementations, a bit-sliced one (32 samples per lane operation; needs every spin part of
+ * every mask to have weight <= 4) and a product-layout one (any table); on != 0 forces the second. */
+void anqs_k1_enum_force_product_filter(int on);
 size_t anqs_k1_enum_workspace(const anqs_tables_t *t, int64_t n);
 int anqs_k1_enum_filter(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
                         int64_t *d_counts, uint32_t *d_bitmap, void *d_work, void *stream);

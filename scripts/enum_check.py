@@ -32,8 +32,12 @@ def run(n, n_el, irreps, rows, timing=False, complex_w=False, off_sector=False):
         me = 'real' if ham.weights_real else 'complex'
         a = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=False)
         b = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True)
+        _lib.lib().anqs_k1_enum_force_product_filter(1)
+        c = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True)
+        _lib.lib().anqs_k1_enum_force_product_filter(0)
         for k in ('counts', 'offsets', 'dest', 'xprime', 'xy_ptr'):
             assert torch.equal(a[k], b[k]), k
+            assert torch.equal(a[k], c[k]), k
         err = float((a['H'] - b['H']).abs().max()) if a['H'].numel() else 0.0
         print('  bit-equal lists; max |H_tiled - H_untiled| =', err, ' M =', a['xprime'].shape[0])
         assert err < 1e-11
@@ -45,6 +49,9 @@ def run(n, n_el, irreps, rows, timing=False, complex_w=False, off_sector=False):
             work = torch.empty((int(lib.anqs_k1_enum_workspace(ham.tables, nrows)) + 3) // 4, dtype=torch.int32, device=dev)
             counts, offsets = b['counts'], b['offsets']
             t_f = tm(lambda: _lib.check(lib.anqs_k1_enum_filter(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), _lib.dptr(work), sp)))
+            _lib.lib().anqs_k1_enum_force_product_filter(1)
+            t_fp = tm(lambda: _lib.check(lib.anqs_k1_enum_filter(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), _lib.dptr(work), sp)))
+            _lib.lib().anqs_k1_enum_force_product_filter(0)
             t_f0 = tm(lambda: _lib.check(lib.anqs_k1_filter(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), sp)))
             _lib.check(lib.anqs_k1_enum_filter(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), _lib.dptr(work), sp))
             hptr = _lib.dptr(torch.view_as_real(b['H'])) if me == 'complex' else _lib.dptr(b['H'])
@@ -56,7 +63,7 @@ def run(n, n_el, irreps, rows, timing=False, complex_w=False, off_sector=False):
             t_e0 = tm(lambda: _lib.check(lib.anqs_k1_emit(ham.tables, _lib.dptr(s), nrows, _lib.dptr(bitmap), _lib.dptr(offsets),
                                                           _lib.dptr(b['dest']), _lib.dptr(b['xprime']), _lib.dptr(None), hptr, hc, sp)))
             by = (12 + 8 * hc) * m
-            print(f'  filter tiled {t_f:.3f} ms (untiled {t_f0:.3f}); emit tiled {t_e:.3f} ms (no H {t_e_noh:.3f}; untiled {t_e0:.3f}); '
+            print(f'  filter bit-sliced {t_f:.3f} ms (product {t_fp:.3f}, untiled {t_f0:.3f}); emit tiled {t_e:.3f} ms (no H {t_e_noh:.3f}; untiled {t_e0:.3f}); '
                   f'{by / ((t_f + t_e) * 1e-3) / 1e9:.0f} GB/s filter+emit, {by / (t_e * 1e-3) / 1e9:.0f} GB/s emit only')
 
 run(12, 4, 1, 200)

@@ -257,3 +257,49 @@ def test_edge_cases(tmp_path):
     # an electron count nobody satisfies: no connections at all
     conn = ham.connected_configurations(_dev(g['samples']), 3, 1)
     assert conn['xprime'].numel() == 0 and int(conn['counts'].sum().item()) == 0
+
+
+@pytest.mark.parametrize('qubits,electrons,irreps,rows,complex_w,off_sector', [
+    (12, 4, 1, 200, False, False), (20, 14, 1, 1500, False, False), (20, 14, 1, 400, True, False),
+    (20, 14, 1, 600, False, True), (12, 4, 1, 150, True, True), (36, 12, 8, 700, False, False), (56, 14, 8, 600, False, False)])
+def test_tiled_enumeration_equals_untiled(qubits, electrons, irreps, rows, complex_w, off_sector, tmp_path):
+    """The tile-resident kernels (bit-sliced or product-layout filter, pattern-table matrix elements; k1_enum.cu) and the
+    untiled pair (k1_connected.cu) emit the same ordered list bit for bit, and matrix elements that agree to 1e-12 —
+    also for complex weights and for samples outside the (N_alpha, N_beta) sector, where the pattern tables do not apply."""
+    from anqs_quantum_chemistry_b200 import _lib
+    xy, yz, w = synthetic.synthetic_hamiltonian(qubits, n_irreps=irreps, seed=5)
+    if complex_w:
+        w = w.astype(np.complex128) * np.exp(0.3j)
+    na = nb = electrons // 2
+    samples = synthetic.random_physical_samples(qubits, na, nb, rows, seed=11)
+    if off_sector:
+        other = synthetic.random_physical_samples(qubits, na + 1, nb - 1, rows, seed=12)
+        samples = np.unique(np.concatenate((samples[: rows // 2], other[: rows // 2])))
+    hs = HilbertSpace(qubit_num=qubits, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, qubits))
+    assert ham.enum_tiles > 0
+    s = _dev(samples.view(np.int64))
+    me = 'complex' if complex_w else 'real'
+    ref = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=False)
+    outs = [ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True)]
+    _lib.lib().anqs_k1_enum_force_product_filter(1)
+    try:
+        outs.append(ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True))
+    finally:
+        _lib.lib().anqs_k1_enum_force_product_filter(0)
+    assert ref['xprime'].shape[0] > 0
+    for out in outs:
+        for k in ('counts', 'offsets', 'dest', 'xprime', 'xy_ptr'):
+            assert torch.equal(ref[k], out[k]), k
+        scale = max(1.0, float(ref['H'].abs().max()))
+        assert float((ref['H'] - out['H']).abs().max()) < 1e-12 * scale
+    # against the CPU oracle as well (first rows)
+    sub = min(64, samples.shape[0])
+    tab = orc.Tables(xy, yz, w)
+    dest, xp, ptr = orc.candidates_ham(samples, 0, sub, tab, na, nb)
+    m = xp.shape[0]
+    np.testing.assert_array_equal(outs[0]['xprime'][:m].cpu().numpy(), xp)
+    np.testing.assert_array_equal(outs[0]['xy_ptr'][:m].cpu().numpy(), ptr)
+    H = orc.matrix_elements(xp, ptr, tab)
+    got = outs[0]['H'][:m].cpu().numpy()
+    assert np.abs(got - (H if complex_w else H.real)).max() < 1e-10 * max(1.0, np.abs(H).max())
