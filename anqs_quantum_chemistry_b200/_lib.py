@@ -41,6 +41,7 @@ _SIGNATURES = {
     'anqs_hash_filter_info': (_c_int, [_vp, _c_i64, _vp, _vp, _vp]),
     'anqs_hash_probe': (_c_int, [_vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp]),
     'anqs_local_energy_sample_aware': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _vp]),
+    'anqs_local_energy_force_per_sample_kernel': (None, [_c_int]),
     'anqs_accumulate_rows': (_c_int, [_vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_made_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_made_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),

@@ -131,9 +131,26 @@ constexpr uint32_t PROD_SINGLE_MAX = 2;         // rows with <= this many member
 struct HostProd {
     std::vector<ProdTile> tiles;
     std::vector<uint8_t> blob, blob_u;  // blob_u: the same records with the mask index u in place of the hashes
+    std::vector<uint8_t> blob_bs;       // the same records with slice positions in place of the part words (k1_fused_bs.cu)
+    bool bs_ok = true;
     std::vector<uint32_t> row_u, mem_u;
     uint32_t tile_bytes_max = 0;
 };
+
+// Slice positions of one spin part (de-interleaved, bits 0..31) for the bit-sliced electron-count test: four bytes, padded
+// with the constant slices 32 (all zeros) / 33 (all ones) so that "exactly two of the four slices set" is the test for
+// weights 0, 2 and 4; odd weights can never pass ({32,32,32,32}); even weights > 4 are not representable (ok = false).
+static uint32_t part_positions(uint32_t bits, bool *ok) {
+    const int k = __builtin_popcount(bits);
+    if (k & 1) return 0x20202020u;
+    if (k > 4) { *ok = false; return 0x20202020u; }
+    uint32_t b[4] = {32, 32, 33, 33};
+    int i = 0;
+    for (int pos = 0; pos < 32; ++pos)
+        if ((bits >> pos) & 1) b[i++] = (uint32_t)pos;
+    if (k == 2) { b[2] = 32; b[3] = 33; }
+    return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+}
 
 static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostProd &out) {
     // masks sorted by (alpha part, spread bits of the member hash, beta part)
@@ -191,16 +208,18 @@ static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostP
         tile.n_single = (uint32_t)ts.size();
         tile.row_base = row_base;
         tile.member_base = member_base;
-        std::vector<RowRec> rows, rows_u;
-        std::vector<MemRec> mems, mems_u;
+        std::vector<RowRec> rows, rows_u, rows_bs;
+        std::vector<MemRec> mems, mems_u, mems_bs;
         for (auto &c : tm) {
             const uint32_t pa = ms[c.begin].pa;
             rows.push_back({pa, lin_host(LIN_LINE, pa), (uint32_t)mems.size(), (uint32_t)(c.end - c.begin)});
             rows_u.push_back(rows.back());
+            rows_bs.push_back({part_positions(pa, &out.bs_ok), rows.back().hline, rows.back().a, rows.back().b});
             out.row_u.push_back(0);
             for (size_t k = c.begin; k < c.end; ++k) {
                 mems.push_back({ms[k].mb, ms[k].hash});
                 mems_u.push_back({ms[k].mb, ms[k].u});
+                mems_bs.push_back({part_positions(ms[k].mb, &out.bs_ok), ms[k].hash});
                 out.mem_u.push_back(ms[k].u);
             }
         }
@@ -208,6 +227,7 @@ static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostP
             const M &m = ms[c.begin];
             rows.push_back({m.pa, lin_host(LIN_LINE, m.pa), m.mb, m.hash});
             rows_u.push_back({m.pa, 0u, m.mb, m.u});
+            rows_bs.push_back({part_positions(m.pa, &out.bs_ok), lin_host(LIN_LINE, m.pa), part_positions(m.mb, &out.bs_ok), m.hash});
             out.row_u.push_back(m.u);
         }
         tile.n_members = (uint32_t)mems.size();
@@ -217,6 +237,9 @@ static void build_product_layout(const std::vector<uint2> &mab, int64_t U, HostP
         out.blob.resize(off + nbytes, 0);
         std::memcpy(out.blob.data() + off, rows.data(), rows.size() * sizeof(RowRec));
         std::memcpy(out.blob.data() + off + rows.size() * sizeof(RowRec), mems.data(), mems.size() * sizeof(MemRec));
+        out.blob_bs.resize(off + nbytes, 0);
+        std::memcpy(out.blob_bs.data() + off, rows_bs.data(), rows_bs.size() * sizeof(RowRec));
+        std::memcpy(out.blob_bs.data() + off + rows_bs.size() * sizeof(RowRec), mems_bs.data(), mems_bs.size() * sizeof(MemRec));
         out.blob_u.resize(off + nbytes, 0);
         std::memcpy(out.blob_u.data() + off, rows_u.data(), rows_u.size() * sizeof(RowRec));
         std::memcpy(out.blob_u.data() + off + rows_u.size() * sizeof(RowRec), mems_u.data(), mems_u.size() * sizeof(MemRec));
@@ -511,6 +534,8 @@ int anqs_tables_create(anqs_tables_t **out, int qubit_num, int64_t U, int64_t T,
     if (e == cudaSuccess) e = up((void **)&t->prod_row_u, prod.row_u.data(), prod.row_u.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = up((void **)&t->prod_mem_u, prod.mem_u.data(), prod.mem_u.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = up((void **)&t->prod_blob_u, prod.blob_u.data(), prod.blob_u.size());
+    if (e == cudaSuccess) e = up((void **)&t->prod_blob_bs, prod.blob_bs.data(), prod.blob_bs.size());
+    t->prod_bs_ok = prod.bs_ok ? 1 : 0;
     {   // bit-sliced filter positions
         const uint64_t EVEN = 0x5555555555555555ULL;
         std::vector<uint2> bs((size_t)t->U_pad, make_uint2(0x40404040u, 0x40404040u));
@@ -561,6 +586,7 @@ int anqs_tables_destroy(anqs_tables_t *h) {
     cudaFree(t->prod_row_u);
     cudaFree(t->prod_mem_u);
     cudaFree(t->prod_blob_u);
+    cudaFree(t->prod_blob_bs);
     cudaFree(t->bs_pos);
     cudaFree(t->enum_tiles);
     cudaFree(t->enum_blob);

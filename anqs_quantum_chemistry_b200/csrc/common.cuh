@@ -116,6 +116,9 @@ struct Tables {
     // ---- enumeration layouts (k1_enum.cu) ------------------------------------------------------------------
     uint8_t *prod_blob_u;     // same tiles as prod_blob with the mask index u in place of the hashes
                               // (MemRec::hash and the singleton RowRec::b)
+    uint8_t *prod_blob_bs;    // same tiles with slice positions (part_positions in abi_core.cu) in place of RowRec::pa,
+                              // the singleton RowRec::a and MemRec::mb: the records of the bit-sliced fused kernel
+    int prod_bs_ok;           // 0: a spin part of some mask has an even weight > 4 (the bit-sliced kernels do not apply)
     // Bit-sliced filter: per mask the bit positions (in x) of its alpha part (4 bytes) and beta part (4 bytes), padded with
     // the constant slices 64 (all zeros) / 65 (all ones) so that "exactly two of the four slices set" is the electron-count
     // test of every part of weight 0, 2 or 4 (weight 0: {0,0,1,1}; weight 2: {p,q,0,1}; odd weights: {0,0,0,0} = never).
@@ -159,6 +162,10 @@ struct HashView {
     uint32_t capmask;        // capacity - 1
     uint32_t linemask;       // nlines - 1, nlines = capacity * FILTER_BYTES_PER_SLOT / 128
 };
+struct Tables;
+// k1_fused_bs.cu: launches the bit-sliced fused local-energy kernel; 1 = launched, 0 = does not apply, < 0 = CUDA error
+int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, const double *d_amps, int64_t row_start,
+                        int64_t row_len, int alpha_num, int beta_num, double *d_eloc, cudaStream_t s);
 inline HashView make_hash_view(const void *d_table, int64_t capacity) {
     HashView hv;
     hv.slots = (const HashSlot *)d_table;

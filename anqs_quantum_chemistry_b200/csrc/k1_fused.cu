@@ -287,6 +287,14 @@ int anqs_local_energy_sample_aware(const anqs_tables_t *h, const int64_t *d_samp
     const int64_t ngroups = (row_len + FZ_WARPS - 1) / FZ_WARPS;
     const int grid = (int)std::min<int64_t>(ngroups, sm_count_of_current_device());
     cudaStream_t s = (cudaStream_t)stream;
+    {   // bit-sliced kernel (k1_fused_bs.cu) whenever the table allows it
+        const int rc = fused_bs_try_launch(t, hv, d_samples, d_amps, row_start, row_len, alpha_num, beta_num, d_eloc, s);
+        ANQS_REQUIRE(rc >= 0, "cudaFuncSetAttribute failed for the bit-sliced kernel");
+        if (rc == 1) {
+            ANQS_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (t->weights_real) {
         auto kern = fused_eloc_kernel<true>;
         ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,398 @@
+// Fused sample-aware local energy, bit-sliced variant (same contract and results as fused_eloc_kernel in k1_fused.cu;
+// reference PO:396-487 with coupling 'ham').
+//
+// The untiled kernel gives one warp one sample and spends most of its instructions on the electron-count tests (a POPC pair
+// per mask, A + 0.4 U of them per sample) and on per-row bookkeeping, with ~15 % of the lanes alive at the filter probe.
+// Here a warp owns a GROUP OF 32 SAMPLES:
+//
+//  * BIT-SLICED TESTS.  Slice i of the group = bit i of its 32 samples (one ballot).  For a sample inside the
+//    (N_alpha, N_beta) sector, x' = x ^ mask keeps the electron counts iff exactly half of the positions of the alpha part
+//    of the mask and half of those of its beta part are occupied in x: a boolean function of <= 8 slices that one lane
+//    evaluates for 32 samples at once (~12 LOP3, no POPC).  The product layout factorises it: the alpha factor is computed
+//    once per row, the beta factor once per member.
+//  * SAMPLE-SYNCHRONOUS PROBES.  For every sample of the group that has a passing member in the current row step, the warp
+//    probes the presence filter for that one sample: all lanes address the same 128-byte line (the line depends on the
+//    sample and the row only), so the line-blocked filter keeps its one-wavefront-per-step property.  The probe address
+//    and the two bit positions are XOR-linear in (sample hash, member hash): one LOP3 each per lane.
+//  * Singleton rows (one member per alpha part, e.g. the same-spin double excitations) have no line to share; there each
+//    lane walks the set bits of its own result word.
+//  * Filter positives (true members + ~0.3 % false positives) are queued per warp as (key, mask reference, sample) and
+//    resolved 32 at a time against the slot table; hits add H * psi(x') to the group's per-sample accumulators in shared
+//    memory.
+//  * Samples outside the sector (never produced by the symmetry-masked samplers, but legal input) take a plain path: popcount
+//    tests over the flat mask table and a direct slot-table lookup per passing mask.
+//
+// When there are fewer groups than warps on the chip (small batches), R = 2^k warps share one group and split its row steps.
+#include <algorithm>
+
+#include "common.cuh"
+#include "matrix_elements.cuh"
+
+namespace anqs {
+
+constexpr int FB_THREADS = 1024;
+constexpr int FB_WARPS = FB_THREADS / 32;
+constexpr int FB_QCAP = 64;                            // queued filter positives per warp
+constexpr int FB_QUEUE_BYTES = FB_WARPS * FB_QCAP * 16;  // uint4 {ka, kb, uref, sample}
+constexpr uint32_t FB_UREF_ROW = 0x80000000u;          // uref flag: index into prod_row_u instead of prod_mem_u
+constexpr uint32_t FB_BULK_CHUNK = 64 * 1024;
+constexpr uint32_t FB_NEVER = 0x20202020u;             // four ZERO slices: the test is false for every sample
+
+struct __align__(16) FbSlot {   // one group of 32 samples (shared memory)
+    uint32_t Xa[34], Xb[34];    // slices of the alpha / beta halves; [32] = all zeros, [33] = all ones
+    uint2 hs[32];               // per sample: {line hash, probe constants (offset part | bit part << 16)}
+    uint32_t xa[32], xb[32];
+    double acc[64];             // (re, im) of sum H psi(x') per sample
+    uint32_t valid, slow, pad0, pad1;
+};
+
+// XOR-linear pieces of the filter address: h = hash(sample) ^ hash(member)
+//   byte offset inside the (line ^ spread) group: spread bits -> line bits 7.., word bits -> 2..6
+//   the key's two bits of that word, packed 5 + 5
+__device__ __forceinline__ uint32_t fb_off(uint32_t h, uint32_t gmask) { return (((h >> 15) & gmask) << 7) | ((h >> 3) & 0x7Cu); }
+__device__ __forceinline__ uint32_t fb_bits(uint32_t h) { return (h & 31u) | (((h >> 10) & 31u) << 5); }
+
+__device__ __forceinline__ uint32_t fb_exactly_two(const uint32_t *X, uint32_t pos) {
+    const uint32_t a = X[pos & 0xff], b = X[(pos >> 8) & 0xff], c = X[(pos >> 16) & 0xff], d = X[pos >> 24];
+    return ~(a ^ b ^ c ^ d) & ~(a & b & c & d) & (a | b | c | d);
+}
+
+__device__ __forceinline__ uint32_t fb_mask_from_pos(uint32_t pos) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t p = (pos >> (8 * i)) & 0xffu;
+        if (p < 32u) m |= 1u << p;
+    }
+    return m;
+}
+
+// both bits of the key present in the filter word
+__device__ __forceinline__ uint32_t fb_test(uint32_t word, uint32_t hb) {
+    return __funnelshift_r(word, 0u, hb) & __funnelshift_r(word, 0u, hb >> 5) & 1u;
+}
+
+struct FbWarp {
+    FbSlot *sl;
+    uint4 *q;
+    int qlen;
+    const uint8_t *filter;
+    uint32_t linemask, gmask;
+};
+
+template <bool REAL>
+__device__ __forceinline__ void fb_resolve(const Tables &t, const HashView &hv, FbWarp &w, bool active, uint4 e) {
+    const uint64_t key = (uint64_t)e.x | ((uint64_t)e.y << 32);
+    long long j = -1;
+    double ar = 0.0, ai = 0.0;
+    int2 g = make_int2(0, 0);
+    if (active) {
+        j = hash_lookup(hv, key, ar, ai);
+        if (j >= 0) {
+            const uint32_t u = (e.z & FB_UREF_ROW) ? __ldg(t.prod_row_u + (e.z & ~FB_UREF_ROW)) : __ldg(t.prod_mem_u + e.z);
+            g = __ldg(t.grp + u);
+        }
+    }
+    const bool hit = active && j >= 0;
+    if (__any_sync(0xffffffffu, hit)) {
+        double hr, hi;
+        warp_matrix_elements<REAL>(t, hit, g, key, hr, hi);
+        if (hit) {
+            double *acc = w.sl->acc + 2 * e.w;
+            if (REAL) {
+                atomicAdd(acc, hr * ar);
+                atomicAdd(acc + 1, hr * ai);
+            } else {
+                atomicAdd(acc, hr * ar - hi * ai);
+                atomicAdd(acc + 1, hr * ai + hi * ar);
+            }
+        }
+    }
+}
+
+// Queues the lanes flagged in `positive` (ballot b != 0); resolves a batch once 32 are waiting.
+template <bool REAL>
+__device__ __forceinline__ void fb_push(const Tables &t, const HashView &hv, FbWarp &w, unsigned b, bool positive, uint32_t s,
+                                        uint32_t apos, uint32_t bpos, uint32_t uref) {
+    const int lane = lane_id();
+    if (positive) {
+        const int p = w.qlen + __popc(b & lanemask_lt());
+        w.q[p] = make_uint4(w.sl->xa[s] ^ fb_mask_from_pos(apos), w.sl->xb[s] ^ fb_mask_from_pos(bpos), uref, s);
+    }
+    w.qlen += __popc(b);
+    __syncwarp();
+    if (w.qlen >= 32) {
+        const uint4 e0 = w.q[lane];
+        const int rem = w.qlen - 32;
+        uint4 e1 = make_uint4(0, 0, 0, 0);
+        if (lane < rem) e1 = w.q[32 + lane];
+        __syncwarp();
+        if (lane < rem) w.q[lane] = e1;
+        __syncwarp();
+        w.qlen = rem;
+        fb_resolve<REAL>(t, hv, w, true, e0);
+    }
+}
+
+template <bool REAL>
+__device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView &hv, FbWarp &w, const ProdTile &tile,
+                                                const unsigned char *smem_tile, int k, int R) {
+    const int lane = lane_id();
+    const FbSlot &sl = *w.sl;
+    const uint32_t valid = sl.valid;
+    const uint4 *rows = reinterpret_cast<const uint4 *>(smem_tile);
+    const uint2 *mems = reinterpret_cast<const uint2 *>(smem_tile + (size_t)(tile.n_multi + tile.n_single) * sizeof(RowRec));
+    // ---- multi-member rows: alpha factor per row, beta factor per member, one probe step per (row step, passing sample) ----
+    for (uint32_t r = 0; r < tile.n_multi; ++r) {
+        const uint4 rec = rows[r];  // {alpha positions, line hash of the alpha part, first member, member count}
+        const uint32_t nsteps = (rec.w + 63u) >> 6;
+        uint32_t j = (uint32_t)(k - (int)r) & (uint32_t)(R - 1);
+        if (j >= nsteps) continue;
+        const uint32_t fa = fb_exactly_two(sl.Xa, rec.x) & valid;
+        if (!fa) continue;
+        for (; j < nsteps; j += R) {
+            const uint32_t j1 = j * 64u + lane, j2 = j1 + 32u;
+            uint2 m1 = make_uint2(FB_NEVER, 0u), m2 = make_uint2(FB_NEVER, 0u);
+            if (j1 < rec.w) m1 = mems[rec.z + j1];
+            if (j2 < rec.w) m2 = mems[rec.z + j2];
+            const uint32_t w1 = fa & fb_exactly_two(sl.Xb, m1.x), w2 = fa & fb_exactly_two(sl.Xb, m2.x);
+            uint32_t any = __reduce_or_sync(0xffffffffu, w1 | w2);
+            if (!any) continue;
+            const uint32_t mo1 = fb_off(m1.y, w.gmask), mo2 = fb_off(m2.y, w.gmask), mh1 = fb_bits(m1.y), mh2 = fb_bits(m2.y);
+            while (any) {
+                const uint32_t s = __ffs(any) - 1;
+                any &= any - 1;
+                const uint2 hs = sl.hs[s];  // uniform address
+                const uint32_t u = (((hs.x ^ rec.y) & w.linemask) << 7) ^ (hs.y & 0xFFFFu);
+                const uint32_t sb = hs.y >> 16;
+                uint32_t word1 = 0, word2 = 0;
+                if ((w1 >> s) & 1u) word1 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (u ^ mo1)));
+                if ((w2 >> s) & 1u) word2 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (u ^ mo2)));
+                const bool f1 = fb_test(word1, sb ^ mh1), f2 = fb_test(word2, sb ^ mh2);
+                if (__any_sync(0xffffffffu, f1 | f2)) {
+                    const unsigned b1 = __ballot_sync(0xffffffffu, f1);
+                    if (b1) fb_push<REAL>(t, hv, w, b1, f1, s, rec.x, m1.x, tile.member_base + rec.z + j1);
+                    const unsigned b2 = __ballot_sync(0xffffffffu, f2);
+                    if (b2) fb_push<REAL>(t, hv, w, b2, f2, s, rec.x, m2.x, tile.member_base + rec.z + j2);
+                }
+            }
+        }
+    }
+    // ---- singleton rows: one row per lane, every lane walks the set bits (samples) of its own result word --------------
+    const uint4 *srows = rows + tile.n_multi;
+    for (uint32_t r0 = (uint32_t)k * 32u; r0 < tile.n_single; r0 += 32u * (uint32_t)R) {
+        const uint32_t r = r0 + lane;
+        uint4 c = make_uint4(FB_NEVER, 0u, FB_NEVER, 0u);  // {alpha positions, line hash, beta positions, member hash}
+        if (r < tile.n_single) c = srows[r];
+        uint32_t ww = valid & fb_exactly_two(sl.Xa, c.x) & fb_exactly_two(sl.Xb, c.z);
+        const uint32_t mo = fb_off(c.w, w.gmask), mh = fb_bits(c.w);
+        while (__any_sync(0xffffffffu, ww != 0u)) {
+            const bool act = ww != 0u;
+            const uint32_t s = act ? __ffs(ww) - 1 : 0u;
+            ww &= ww - 1;  // 0 stays 0
+            const uint2 hs = sl.hs[s];
+            const uint32_t off = ((((hs.x ^ c.y) & w.linemask) << 7) ^ (hs.y & 0xFFFFu)) ^ mo;
+            uint32_t word = 0;
+            if (act) word = __ldg(reinterpret_cast<const uint32_t *>(w.filter + off));
+            const bool f = fb_test(word, (hs.y >> 16) ^ mh);
+            const unsigned b = __ballot_sync(0xffffffffu, f);
+            if (b) fb_push<REAL>(t, hv, w, b, f, s, c.x, c.z, FB_UREF_ROW | (tile.row_base + tile.n_multi + r));
+        }
+    }
+}
+
+// Plain path for one sample outside the sector: popcount tests over the flat mask table, direct slot lookups.
+template <bool REAL>
+__device__ __forceinline__ void fb_slow_sample(const Tables &t, const HashView &hv, uint32_t xa, uint32_t xb, int alpha, int beta,
+                                               double &er, double &ei) {
+    const int lane = lane_id();
+    double sr = 0.0, si = 0.0;
+    for (int64_t u0 = 0; u0 < t.U; u0 += 32) {
+        const int64_t u = u0 + lane;
+        uint2 m = make_uint2(0u, 0u);
+        if (u < t.U) m = __ldg(t.mab + u);
+        const bool pass = u < t.U && __popc(xa ^ m.x) == alpha && __popc(xb ^ m.y) == beta;
+        const uint64_t key = (uint64_t)(xa ^ m.x) | ((uint64_t)(xb ^ m.y) << 32);
+        long long j = -1;
+        double ar = 0.0, ai = 0.0;
+        if (pass) j = hash_lookup(hv, key, ar, ai);
+        const bool hit = pass && j >= 0;
+        if (__any_sync(0xffffffffu, hit)) {
+            int2 g = make_int2(0, 0);
+            if (hit) g = __ldg(t.grp + u);
+            double hr, hi;
+            warp_matrix_elements<REAL>(t, hit, g, key, hr, hi);
+            if (hit) {
+                if (REAL) {
+                    sr += hr * ar;
+                    si += hr * ai;
+                } else {
+                    sr += hr * ar - hi * ai;
+                    si += hr * ai + hi * ar;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, d);
+        si += __shfl_xor_sync(0xffffffffu, si, d);
+    }
+    er = sr;
+    ei = si;
+}
+
+template <bool REAL>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples, const double2 *__restrict__ amps,
+                     int64_t row_start, int64_t row_len, int alpha, int beta, double2 *__restrict__ eloc, int R) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ ProdTile s_tile;
+    FbSlot *slots = reinterpret_cast<FbSlot *>(smem_raw);
+    uint4 *queues = reinterpret_cast<uint4 *>(smem_raw + FB_WARPS * sizeof(FbSlot));
+    unsigned char *tile_buf = smem_raw + FB_WARPS * sizeof(FbSlot) + FB_QUEUE_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int S = FB_WARPS / R, slot = warp / R, k = warp & (R - 1);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    uint32_t parity = 0;
+    FbWarp w;
+    w.sl = slots + slot;
+    w.q = queues + warp * FB_QCAP;
+    w.filter = hv.filter;
+    w.linemask = hv.linemask;
+    w.gmask = __ldg(&hv.header->gmask);
+    FbSlot &sl = *w.sl;
+
+    const bool resident = t.n_tiles == 1;
+    bool loaded = false;
+    const int64_t ngroups = (row_len + 31) >> 5;
+    const int64_t per_iter = (int64_t)gridDim.x * S;
+    for (int64_t g0 = (int64_t)blockIdx.x * S; g0 < ngroups; g0 += per_iter) {
+        const int64_t g = g0 + slot;
+        const bool have = g < ngroups;
+        __syncthreads();  // the previous groups are finished with the slots
+        if (k == 0) {
+            const int64_t r = g * 32 + lane;
+            const bool ok = have && r < row_len;
+            const uint64_t x = ok ? (uint64_t)samples[row_start + r] : 0ull;
+            const uint32_t xa = compress_even_bits(x), xb = compress_even_bits(x >> 1);
+            const bool insec = __popc(xa) == alpha && __popc(xb) == beta;
+            uint32_t ma = 0, mb = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t ba = __ballot_sync(0xffffffffu, (xa >> i) & 1u), bb = __ballot_sync(0xffffffffu, (xb >> i) & 1u);
+                if (lane == i) {
+                    ma = ba;
+                    mb = bb;
+                }
+            }
+            sl.Xa[lane] = ma;
+            sl.Xb[lane] = mb;
+            if (lane < 2) {
+                sl.Xa[32 + lane] = lane ? 0xffffffffu : 0u;
+                sl.Xb[32 + lane] = lane ? 0xffffffffu : 0u;
+            }
+            const uint32_t hl = lin_dev(LIN_LINE, xa);
+            const uint32_t hp = (lin_dev(LIN_POSA, xa) & POSA_MASK) ^ (lin_dev(LIN_POSB, xb) & POSB_MASK);
+            sl.hs[lane] = make_uint2(hl, fb_off(hp, w.gmask) | (fb_bits(hp) << 16));
+            sl.xa[lane] = xa;
+            sl.xb[lane] = xb;
+            sl.acc[2 * lane] = 0.0;
+            sl.acc[2 * lane + 1] = 0.0;
+            const uint32_t valid = __ballot_sync(0xffffffffu, ok && insec), slow = __ballot_sync(0xffffffffu, ok && !insec);
+            if (lane == 0) {
+                sl.valid = valid;
+                sl.slow = slow;
+            }
+        }
+        __syncthreads();
+        w.qlen = 0;
+        for (int ti = 0; ti < t.n_tiles; ++ti) {
+            if (!resident || !loaded) {
+                __syncthreads();  // everyone is done with the previous contents of tile_buf / s_tile
+                if (threadIdx.x == 0) {
+                    const ProdTile pt = t.prod_tiles[ti];
+                    s_tile = pt;
+                    mbar_arrive_expect_tx(&bar, pt.blob_bytes);
+                    for (uint32_t off = 0; off < pt.blob_bytes; off += FB_BULK_CHUNK)
+                        bulk_copy_g2s(tile_buf + off, t.prod_blob_bs + pt.blob_off + off, min(FB_BULK_CHUNK, pt.blob_bytes - off), &bar);
+                }
+                __syncthreads();
+                mbar_wait(&bar, parity);
+                parity ^= 1u;
+                loaded = true;
+            }
+            const ProdTile tile = s_tile;
+            if (sl.valid) fb_process_tile<REAL>(t, hv, w, tile, tile_buf, k, R);
+        }
+        __syncwarp();
+        if (w.qlen > 0) {
+            const bool act = lane < w.qlen;
+            const uint4 e = act ? w.q[lane] : make_uint4(0, 0, 0, 0);
+            fb_resolve<REAL>(t, hv, w, act, e);
+            w.qlen = 0;
+        }
+        __syncthreads();  // every contribution to the accumulators of this CTA's groups has landed
+        if (k == 0 && have) {
+            uint32_t slow = sl.slow;
+            while (slow) {
+                const uint32_t s = __ffs(slow) - 1;
+                slow &= slow - 1;
+                double er, ei;
+                fb_slow_sample<REAL>(t, hv, sl.xa[s], sl.xb[s], alpha, beta, er, ei);
+                if (lane == 0) {
+                    sl.acc[2 * s] = er;
+                    sl.acc[2 * s + 1] = ei;
+                }
+            }
+            __syncwarp();
+            if (((sl.valid | sl.slow) >> lane) & 1u) {
+                const int64_t r = g * 32 + lane;
+                const double sr = sl.acc[2 * lane], si = sl.acc[2 * lane + 1];
+                const double2 a = amps[row_start + r];
+                const double den = a.x * a.x + a.y * a.y;
+                eloc[r] = make_double2((sr * a.x + si * a.y) / den, (si * a.x - sr * a.y) / den);
+            }
+        }
+    }
+}
+
+static bool g_force_untiled_fused = false;  // test hook (anqs_local_energy_force_per_sample_kernel)
+
+// returns 1 when it launched, 0 when the bit-sliced kernel does not apply (the caller falls back), < 0 on error
+int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, const double *d_amps, int64_t row_start,
+                        int64_t row_len, int alpha_num, int beta_num, double *d_eloc, cudaStream_t s) {
+    if (g_force_untiled_fused || !t->prod_bs_ok) return 0;
+    const size_t smem = (size_t)FB_WARPS * sizeof(FbSlot) + FB_QUEUE_BYTES + (size_t)t->tile_bytes_max;
+    if (smem + 256 > 227 * 1024) return 0;
+    const int sms = sm_count_of_current_device();
+    const int64_t ngroups = (row_len + 31) / 32;
+    int R = 1;
+    while (R < FB_WARPS && ngroups * (R * 2) <= (int64_t)sms * FB_WARPS) R *= 2;
+    const int S = FB_WARPS / R;
+    const int grid = (int)std::min<int64_t>((ngroups + S - 1) / S, sms);
+    cudaError_t e;
+    if (t->weights_real) {
+        auto kern = fused_eloc_bs_kernel<true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -1;
+        kern<<<grid, FB_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num, beta_num,
+                                            (double2 *)d_eloc, R);
+    } else {
+        auto kern = fused_eloc_bs_kernel<false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -1;
+        kern<<<grid, FB_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num, beta_num,
+                                            (double2 *)d_eloc, R);
+    }
+    return 1;
+}
+
+}  // namespace anqs
+
+extern "C" void anqs_local_energy_force_per_sample_kernel(int on) { anqs::g_force_untiled_fused = on != 0; }

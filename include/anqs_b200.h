@@ -135,6 +135,10 @@ int anqs_local_energy_sample_aware(const anqs_tables_t *t, const int64_t *d_samp
                                    int64_t n_total, int64_t row_start, int64_t row_len, const void *d_table,
                                    int64_t capacity, int alpha_num, int beta_num, double *d_eloc, void *stream);
 
+/* Test hook: the call above runs a bit-sliced kernel (a warp per group of 32 samples; needs every spin part of every mask
+ * to have weight <= 4) and falls back to a warp-per-sample kernel otherwise; on != 0 forces the second. */
+void anqs_local_energy_force_per_sample_kernel(int on);
+
 /* ---- A7  scatter of the materialised list (PO:453-478 / PO:1048-1057): E[dest] += H * psi(src) -------
  * d_src_ptr[r] = index of x'_r in the sampled set or -1 (skipped).  Rows must be grouped by dest through
  * d_offsets (CSR).  d_eloc[i] = sum / psi(x_i) when d_amps_dest != NULL, else the raw sum. */
