@@ -32,6 +32,7 @@ namespace anqs {
 
 constexpr int FB_THREADS = 1024;
 constexpr int FB_WARPS = FB_THREADS / 32;
+static_assert(FB_WARPS % 8 == 0, "R (warps per group, <= 8) must divide the warp count");
 constexpr int FB_QCAP = 64;                            // queued filter positives per warp
 constexpr int FB_QUEUE_BYTES = FB_WARPS * FB_QCAP * 16;  // uint4 {ka, kb, uref, sample}
 constexpr uint32_t FB_UREF_ROW = 0x80000000u;          // uref flag: index into prod_row_u instead of prod_mem_u
@@ -160,20 +161,33 @@ __device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView 
             if (!any) continue;
             const uint32_t mo1 = fb_off(m1.y, w.gmask), mo2 = fb_off(m2.y, w.gmask), mh1 = fb_bits(m1.y), mh2 = fb_bits(m2.y);
             while (any) {
-                const uint32_t s = __ffs(any) - 1;
+                // two samples per iteration: four independent filter loads in flight per lane
+                const uint32_t sa = __ffs(any) - 1;
                 any &= any - 1;
-                const uint2 hs = sl.hs[s];  // uniform address
-                const uint32_t u = (((hs.x ^ rec.y) & w.linemask) << 7) ^ (hs.y & 0xFFFFu);
-                const uint32_t sb = hs.y >> 16;
-                uint32_t word1 = 0, word2 = 0;
-                if ((w1 >> s) & 1u) word1 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (u ^ mo1)));
-                if ((w2 >> s) & 1u) word2 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (u ^ mo2)));
-                const bool f1 = fb_test(word1, sb ^ mh1), f2 = fb_test(word2, sb ^ mh2);
-                if (__any_sync(0xffffffffu, f1 | f2)) {
-                    const unsigned b1 = __ballot_sync(0xffffffffu, f1);
-                    if (b1) fb_push<REAL>(t, hv, w, b1, f1, s, rec.x, m1.x, tile.member_base + rec.z + j1);
-                    const unsigned b2 = __ballot_sync(0xffffffffu, f2);
-                    if (b2) fb_push<REAL>(t, hv, w, b2, f2, s, rec.x, m2.x, tile.member_base + rec.z + j2);
+                const bool two = any != 0u;
+                const uint32_t sb = two ? __ffs(any) - 1 : sa;
+                any &= any - 1;  // 0 stays 0
+                const uint2 ha = sl.hs[sa], hb = sl.hs[sb];  // uniform addresses
+                const uint32_t ua = (((ha.x ^ rec.y) & w.linemask) << 7) ^ (ha.y & 0xFFFFu);
+                const uint32_t ub = (((hb.x ^ rec.y) & w.linemask) << 7) ^ (hb.y & 0xFFFFu);
+                const uint32_t bita = 1u << sa, bitb = two ? 1u << sb : 0u;
+                uint32_t wa1 = 0, wa2 = 0, wb1 = 0, wb2 = 0;
+                if (w1 & bita) wa1 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (ua ^ mo1)));
+                if (w2 & bita) wa2 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (ua ^ mo2)));
+                if (w1 & bitb) wb1 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (ub ^ mo1)));
+                if (w2 & bitb) wb2 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (ub ^ mo2)));
+                const uint32_t ka = ha.y >> 16, kb = hb.y >> 16;
+                const bool fa1 = fb_test(wa1, ka ^ mh1), fa2 = fb_test(wa2, ka ^ mh2);
+                const bool fb1 = fb_test(wb1, kb ^ mh1), fb2 = fb_test(wb2, kb ^ mh2);
+                if (__any_sync(0xffffffffu, fa1 | fa2 | fb1 | fb2)) {
+                    unsigned b = __ballot_sync(0xffffffffu, fa1);
+                    if (b) fb_push<REAL>(t, hv, w, b, fa1, sa, rec.x, m1.x, tile.member_base + rec.z + j1);
+                    b = __ballot_sync(0xffffffffu, fa2);
+                    if (b) fb_push<REAL>(t, hv, w, b, fa2, sa, rec.x, m2.x, tile.member_base + rec.z + j2);
+                    b = __ballot_sync(0xffffffffu, fb1);
+                    if (b) fb_push<REAL>(t, hv, w, b, fb1, sb, rec.x, m1.x, tile.member_base + rec.z + j1);
+                    b = __ballot_sync(0xffffffffu, fb2);
+                    if (b) fb_push<REAL>(t, hv, w, b, fb2, sb, rec.x, m2.x, tile.member_base + rec.z + j2);
                 }
             }
         }
@@ -187,16 +201,26 @@ __device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView 
         uint32_t ww = valid & fb_exactly_two(sl.Xa, c.x) & fb_exactly_two(sl.Xb, c.z);
         const uint32_t mo = fb_off(c.w, w.gmask), mh = fb_bits(c.w);
         while (__any_sync(0xffffffffu, ww != 0u)) {
-            const bool act = ww != 0u;
-            const uint32_t s = act ? __ffs(ww) - 1 : 0u;
+            // two of the lane's own samples per iteration
+            const bool acta = ww != 0u;
+            const uint32_t sa = acta ? __ffs(ww) - 1 : 0u;
             ww &= ww - 1;  // 0 stays 0
-            const uint2 hs = sl.hs[s];
-            const uint32_t off = ((((hs.x ^ c.y) & w.linemask) << 7) ^ (hs.y & 0xFFFFu)) ^ mo;
-            uint32_t word = 0;
-            if (act) word = __ldg(reinterpret_cast<const uint32_t *>(w.filter + off));
-            const bool f = fb_test(word, (hs.y >> 16) ^ mh);
-            const unsigned b = __ballot_sync(0xffffffffu, f);
-            if (b) fb_push<REAL>(t, hv, w, b, f, s, c.x, c.z, FB_UREF_ROW | (tile.row_base + tile.n_multi + r));
+            const bool actb = ww != 0u;
+            const uint32_t sb = actb ? __ffs(ww) - 1 : 0u;
+            ww &= ww - 1;
+            const uint2 ha = sl.hs[sa], hb = sl.hs[sb];
+            const uint32_t offa = ((((ha.x ^ c.y) & w.linemask) << 7) ^ (ha.y & 0xFFFFu)) ^ mo;
+            const uint32_t offb = ((((hb.x ^ c.y) & w.linemask) << 7) ^ (hb.y & 0xFFFFu)) ^ mo;
+            uint32_t worda = 0, wordb = 0;
+            if (acta) worda = __ldg(reinterpret_cast<const uint32_t *>(w.filter + offa));
+            if (actb) wordb = __ldg(reinterpret_cast<const uint32_t *>(w.filter + offb));
+            const bool fa = fb_test(worda, (ha.y >> 16) ^ mh), fb = fb_test(wordb, (hb.y >> 16) ^ mh);
+            if (__any_sync(0xffffffffu, fa | fb)) {
+                unsigned b = __ballot_sync(0xffffffffu, fa);
+                if (b) fb_push<REAL>(t, hv, w, b, fa, sa, c.x, c.z, FB_UREF_ROW | (tile.row_base + tile.n_multi + r));
+                b = __ballot_sync(0xffffffffu, fb);
+                if (b) fb_push<REAL>(t, hv, w, b, fb, sb, c.x, c.z, FB_UREF_ROW | (tile.row_base + tile.n_multi + r));
+            }
         }
     }
 }
@@ -362,18 +386,20 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
     }
 }
 
-static bool g_force_untiled_fused = false;  // test hook (anqs_local_energy_force_per_sample_kernel)
+static int g_fused_choice = 0;  // test hook (anqs_local_energy_force_per_sample_kernel): 0 = by batch size, 1 = per-sample, 2 = bit-sliced
 
 // returns 1 when it launched, 0 when the bit-sliced kernel does not apply (the caller falls back), < 0 on error
 int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, const double *d_amps, int64_t row_start,
                         int64_t row_len, int alpha_num, int beta_num, double *d_eloc, cudaStream_t s) {
-    if (g_force_untiled_fused || !t->prod_bs_ok) return 0;
+    if (g_fused_choice == 1 || !t->prod_bs_ok) return 0;
     const size_t smem = (size_t)FB_WARPS * sizeof(FbSlot) + FB_QUEUE_BYTES + (size_t)t->tile_bytes_max;
     if (smem + 256 > 227 * 1024) return 0;
     const int sms = sm_count_of_current_device();
     const int64_t ngroups = (row_len + 31) / 32;
+    // small batches leave most SMs without a group: the warp-per-sample kernel spreads them better
+    if (g_fused_choice == 0 && ngroups < (int64_t)sms * 8) return 0;
     int R = 1;
-    while (R < FB_WARPS && ngroups * (R * 2) <= (int64_t)sms * FB_WARPS) R *= 2;
+    while (R < 8 && ngroups * (R * 2) <= (int64_t)sms * FB_WARPS) R *= 2;  // R divides FB_WARPS
     const int S = FB_WARPS / R;
     const int grid = (int)std::min<int64_t>((ngroups + S - 1) / S, sms);
     cudaError_t e;
@@ -395,4 +421,4 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
 
 }  // namespace anqs
 
-extern "C" void anqs_local_energy_force_per_sample_kernel(int on) { anqs::g_force_untiled_fused = on != 0; }
+extern "C" void anqs_local_energy_force_per_sample_kernel(int on) { anqs::g_fused_choice = on; }

@@ -48,7 +48,7 @@ def ncu_traffic(n_unq, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture of
     this exact configuration (profiles/traffic.json); None when the configuration was not captured."""
     try:
-        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))['fused_eloc_kernel']
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))['fused_eloc_bs_kernel']
         if world == 1 and int(t['n_unq_per_gpu']) == int(n_unq):
             return float(t['dram_bytes_read']) + float(t['dram_bytes_write'])
     except Exception:
@@ -416,6 +416,8 @@ def main():
 
     extras = secondary_measurements(ham, hs, d_idx, na, nb, dev) if (rank == 0 and not args.no_extras) else None
 
+    # which fused kernel the C ABI picks for this batch (k1_fused_bs.cu: >= 256 rows per SM and every spin part of weight <= 4)
+    kernel_name = 'fused_eloc_bs_kernel' if (rows + 31) // 32 >= 8 * torch.cuda.get_device_properties(dev).multi_processor_count else 'fused_eloc_kernel'
     if rank == 0:
         peak, peak_src = load_peaks()
         U, T = ham.unq_xy_masks_num, ham.term_num
@@ -432,12 +434,16 @@ def main():
             'e2e': {'value': n_set * len(e2e_ms) / (e2e_total * 1e-3), 'unit': 'E_loc/s', 'h2d_bytes_per_step': int(24 * rows),
                     'd2h_bytes_per_step': int(16 * rows)},
             'gpu_launches': 2 * args.steps,
-            'kernel': {'name': 'fused_eloc_kernel', 'ms': kernel_ms, 'share_of_step': kernel_ms / (total_ms / args.steps),
+            'step_ms_each': [round(v, 3) for v in step_ms],
+            'kernel': {'name': kernel_name, 'ms': kernel_ms, 'share_of_step': kernel_ms / (total_ms / args.steps),
                        'filter_tests_per_s': rows * U / (kernel_ms * 1e-3), 'probes_per_s': m_probe / (kernel_ms * 1e-3)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(args.n_unq, world),
                          'peak_source': peak_src,
                          'algorithmic_bytes': '32 B per probed candidate + 24 B per table sample + 16 B per row + 8U + 16T',
-                         'note': 'probe bandwidth as SURVEY 8(d) defines it for the fused kernel; the probes are 4-byte loads served by L1/L2 (line-blocked filter), so DRAM traffic is ~1 % of the algorithmic bytes and the kernel is bound by instruction issue (ncu: profiles/r1e_*)'},
+                         'note': 'probe bandwidth as SURVEY 8(d) defines it for the fused kernel (one notional 32-byte slot sector per probed candidate). The kernel '
+                                 'answers ~99.7 % of the probes from a 4-byte word of an L1/L2-resident presence filter, so its DRAM traffic (`traffic`) is ~1 % of '
+                                 'these bytes and the fraction can pass 1: the real limiter is instruction issue and L2->L1 latency (ncu: profiles/r1f_*). The '
+                                 'HBM-bound kernel of the path is the materialising enumeration, secondary.enumeration.frac_of_hbm_peak'},
             'clocks': clock_info,
         }
         if extras is not None:

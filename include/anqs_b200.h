@@ -136,7 +136,8 @@ int anqs_local_energy_sample_aware(const anqs_tables_t *t, const int64_t *d_samp
                                    int64_t capacity, int alpha_num, int beta_num, double *d_eloc, void *stream);
 
 /* Test hook: the call above runs a bit-sliced kernel (a warp per group of 32 samples; needs every spin part of every mask
- * to have weight <= 4) and falls back to a warp-per-sample kernel otherwise; on != 0 forces the second. */
+ * to have weight <= 4) for batches of >= 256 rows per SM and a warp-per-sample kernel otherwise.
+ * on = 1 forces the warp-per-sample kernel, 2 the bit-sliced one (where it applies), 0 restores the choice by size. */
 void anqs_local_energy_force_per_sample_kernel(int on);
 
 /* ---- A7  scatter of the materialised list (PO:453-478 / PO:1048-1057): E[dest] += H * psi(src) -------

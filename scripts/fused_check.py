@@ -38,6 +38,7 @@ def run(n, n_el, irreps, rows, timing=False, complex_w=False, off_sector=False, 
         def go():
             return ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
                                                       alpha_num=na, beta_num=nb, table=table)[0]
+        lib.anqs_local_energy_force_per_sample_kernel(2)
         e_new = go()
         lib.anqs_local_energy_force_per_sample_kernel(1)
         e_old = go()
@@ -46,7 +47,7 @@ def run(n, n_el, irreps, rows, timing=False, complex_w=False, off_sector=False, 
         assert err <= 1e-11 * max(1.0, scale)
         if timing:
             t_old = tm(go)
-            lib.anqs_local_energy_force_per_sample_kernel(0)
+            lib.anqs_local_energy_force_per_sample_kernel(2)
             t_new = tm(go)
             print(f'  per-sample kernel {t_old:.3f} ms, bit-sliced {t_new:.3f} ms  ({s.shape[0] / t_new / 1e3:.3e} E_loc/s)')
         lib.anqs_local_energy_force_per_sample_kernel(0)

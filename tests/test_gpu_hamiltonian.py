@@ -303,3 +303,44 @@ def test_tiled_enumeration_equals_untiled(qubits, electrons, irreps, rows, compl
     H = orc.matrix_elements(xp, ptr, tab)
     got = outs[0]['H'][:m].cpu().numpy()
     assert np.abs(got - (H if complex_w else H.real)).max() < 1e-10 * max(1.0, np.abs(H).max())
+
+
+@pytest.mark.parametrize('qubits,electrons,irreps,rows,complex_w,off_sector,clustered', [
+    (12, 4, 1, 200, False, False, False), (20, 14, 1, 3000, False, False, False), (20, 14, 1, 5000, False, False, True),
+    (20, 14, 1, 500, True, False, False), (20, 14, 1, 1000, False, True, False), (36, 12, 8, 1500, False, False, False),
+    (56, 14, 8, 3000, False, False, True), (56, 14, 8, 40000, False, False, False)])
+def test_bit_sliced_local_energy_equals_per_sample_kernel(qubits, electrons, irreps, rows, complex_w, off_sector, clustered, tmp_path):
+    """The two fused sample-aware kernels (a warp per group of 32 samples with bit-sliced electron-count tests, k1_fused_bs.cu;
+    a warp per sample, k1_fused.cu) and the CPU oracle give the same local energies to 1e-10, also for complex weights, for
+    clustered sample sets (many hits, loaded filter lines), samples outside the sector, and when several warps share a group."""
+    from anqs_quantum_chemistry_b200 import _lib
+    xy, yz, w = synthetic.synthetic_hamiltonian(qubits, n_irreps=irreps, seed=3)
+    if complex_w:
+        w = w.astype(np.complex128) * np.exp(0.3j)
+    na = nb = electrons // 2
+    if clustered:
+        samples = synthetic.clustered_physical_samples(qubits, na, nb, rows, seed=7, mean_rank=2.0)
+    else:
+        samples = synthetic.random_physical_samples(qubits, na, nb, rows, seed=13)
+    if off_sector:
+        other = synthetic.random_physical_samples(qubits, na + 1, nb - 1, rows, seed=14)
+        samples = np.unique(np.concatenate((samples[: rows // 2], other[: rows // 2])))
+    amps = synthetic.random_amplitudes(samples.shape[0], seed=15)
+    hs = HilbertSpace(qubit_num=qubits, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, qubits))
+    s, a = _dev(samples.view(np.int64)).view(-1, 1), _dev(amps)
+    table = SampleTable(s.view(-1), a)
+    res = {}
+    try:
+        for choice in (1, 2, 0):
+            _lib.lib().anqs_local_energy_force_per_sample_kernel(choice)
+            res[choice] = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
+                                                             alpha_num=na, beta_num=nb, table=table)[0].cpu().numpy()
+    finally:
+        _lib.lib().anqs_local_energy_force_per_sample_kernel(0)
+    scale = max(1.0, np.abs(res[1]).max())
+    assert np.abs(res[2] - res[1]).max() < 1e-11 * scale
+    assert np.abs(res[0] - res[1]).max() < 1e-11 * scale
+    if samples.shape[0] <= 6000:
+        e_ref = orc.local_energy_sample_aware(samples, amps, orc.Tables(xy, yz, w), na, nb)
+        assert np.abs(res[2] - e_ref).max() < 1e-10 * scale
