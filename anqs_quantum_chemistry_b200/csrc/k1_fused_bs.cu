@@ -118,7 +118,8 @@ __device__ __forceinline__ void fb_push(const Tables &t, const HashView &hv, FbW
     const int lane = lane_id();
     if (positive) {
         const int p = w.qlen + __popc(b & lanemask_lt());
-        w.q[p] = make_uint4(w.sl->xa[s] ^ fb_mask_from_pos(apos), w.sl->xb[s] ^ fb_mask_from_pos(bpos), uref, s);
+        const uint32_t ka = w.sl->xa[s] ^ fb_mask_from_pos(apos), kb = w.sl->xb[s] ^ fb_mask_from_pos(bpos);
+        w.q[p] = make_uint4(ka, kb, uref, s);
     }
     w.qlen += __popc(b);
     __syncwarp();

@@ -1,0 +1,21 @@
+"""Times SampleTable builds (k2_hash.cu) at the key counts of the 1..8-GPU bench."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from anqs_quantum_chemistry_b200 import SampleTable, synthetic, dist as adist
+dev = torch.device('cuda:0')
+def tm(fn, reps=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+for n in (1 << 20, 1 << 23):
+    s = synthetic.random_physical_samples(56, 7, 7, n, seed=1)
+    a = synthetic.random_amplitudes(s.shape[0], seed=2)
+    ds, da = torch.from_numpy(s.view(np.int64)).to(dev), torch.from_numpy(a).to(dev)
+    print(n, 'keys: build', round(tm(lambda: SampleTable(ds, da)), 3), 'ms')
+    e = torch.randn(n // 8 if n > (1 << 20) else n, dtype=torch.complex128, device=dev)
+    print('   stats', round(tm(lambda: adist.local_energy_stats(e, da[:e.shape[0]])), 3), 'ms')
