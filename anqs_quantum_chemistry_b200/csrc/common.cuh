@@ -132,7 +132,7 @@ struct Tables {
 
 // ---- sampled-set lookup table (kernel family 2) ------------------------------------------------------
 // Memory layout of the caller-allocated buffer (128-byte aligned):
-//   [capacity slots of 32 bytes][dedicated slot for the all-ones key, 32 bytes][header, 96 bytes][filter]
+//   [capacity slots of 32 bytes][dedicated slot for the all-ones key, 32 bytes][header, 96 bytes][pad to an 8 KB boundary][filter]
 // The filter is a line-blocked presence filter of 2*capacity bytes (32..64 bits per key, TWO bits of one word per key):
 // the 128-byte line is chosen by the ALPHA half of the key (lin LIN_LINE), optionally spread over 2^G lines by
 // G hash bits of the beta half, and the bit inside the line by both halves (LIN_POSA ^ LIN_POSB).  All the hashes
@@ -144,6 +144,7 @@ constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;  // de-interleaving maps a
 constexpr int FILTER_MAX_SPREAD_BITS = 6;
 constexpr int FILTER_BYTES_PER_SLOT = 2;  // filter size = 2 * capacity bytes: 32..64 bits per key, TWO bits of one word per key (~0.3 % false positives)
 constexpr uint32_t POSA_MASK = 0x7FFFu, POSB_MASK = 0x1FFFFFu;  // widths of the two position hashes
+constexpr size_t FILTER_ALIGN = 8192;  // > every member part of a probe offset: 6 spread bits << 7 | 5 word bits << 2
 struct __align__(32) HashSlot {
     uint64_t key;    // de-interleaved configuration
     long long idx;   // position in the key array (-1 = empty)
@@ -170,7 +171,9 @@ inline HashView make_hash_view(const void *d_table, int64_t capacity) {
     HashView hv;
     hv.slots = (const HashSlot *)d_table;
     hv.header = (const FilterHeader *)(hv.slots + capacity + 1);
-    hv.filter = (const uint8_t *)(hv.slots + capacity) + 128;
+    // the filter starts at the first FILTER_ALIGN boundary behind the header: the fused kernels form probe addresses as
+    // (filter + sample part) ^ (member part < FILTER_ALIGN), which equals filter + (sample part ^ member part) only then
+    hv.filter = (const uint8_t *)(((uintptr_t)(hv.slots + capacity) + 128 + (FILTER_ALIGN - 1)) & ~(uintptr_t)(FILTER_ALIGN - 1));
     hv.capmask = (uint32_t)(capacity - 1);
     hv.linemask = (uint32_t)(capacity * FILTER_BYTES_PER_SLOT / 128 - 1);
     return hv;

@@ -173,10 +173,12 @@ __device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView 
                 const uint32_t ub = (((hb.x ^ rec.y) & w.linemask) << 7) ^ (hb.y & 0xFFFFu);
                 const uint32_t bita = 1u << sa, bitb = two ? 1u << sb : 0u;
                 uint32_t wa1 = 0, wa2 = 0, wb1 = 0, wb2 = 0;
-                if (w1 & bita) wa1 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (ua ^ mo1)));
-                if (w2 & bita) wa2 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (ua ^ mo2)));
-                if (w1 & bitb) wb1 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (ub ^ mo1)));
-                if (w2 & bitb) wb2 = __ldg(reinterpret_cast<const uint32_t *>(w.filter + (ub ^ mo2)));
+                // filter is FILTER_ALIGN-aligned and mo < FILTER_ALIGN: (filter + u) ^ mo == filter + (u ^ mo), one LOP3 per probe
+                const uintptr_t pa = (uintptr_t)(w.filter + ua), pb = (uintptr_t)(w.filter + ub);
+                if (w1 & bita) wa1 = __ldg(reinterpret_cast<const uint32_t *>(pa ^ mo1));
+                if (w2 & bita) wa2 = __ldg(reinterpret_cast<const uint32_t *>(pa ^ mo2));
+                if (w1 & bitb) wb1 = __ldg(reinterpret_cast<const uint32_t *>(pb ^ mo1));
+                if (w2 & bitb) wb2 = __ldg(reinterpret_cast<const uint32_t *>(pb ^ mo2));
                 const uint32_t ka = ha.y >> 16, kb = hb.y >> 16;
                 const bool fa1 = fb_test(wa1, ka ^ mh1), fa2 = fb_test(wa2, ka ^ mh2);
                 const bool fb1 = fb_test(wb1, kb ^ mh1), fb2 = fb_test(wb2, kb ^ mh2);

@@ -137,7 +137,8 @@ static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, v
     const uint32_t nlines = hv.linemask + 1;
     // 0xFF over the slots: key = EMPTY, idx = -1; zero header and filter
     ANQS_CUDA(cudaMemsetAsync(slots, 0xFF, (size_t)(capacity + 1) * sizeof(HashSlot), s));
-    ANQS_CUDA(cudaMemsetAsync(hdr, 0, 96 + (size_t)FILTER_BYTES_PER_SLOT * capacity, s));
+    ANQS_CUDA(cudaMemsetAsync(hdr, 0, 96, s));
+    ANQS_CUDA(cudaMemsetAsync(filter_words, 0, (size_t)FILTER_BYTES_PER_SLOT * capacity, s));
     if (n == 0) return 0;
     ANQS_REQUIRE(d_keys, "null key array");
     int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 16);
@@ -162,7 +163,9 @@ int64_t anqs_hash_capacity(int64_t n) {
     return cap;
 }
 
-size_t anqs_hash_bytes(int64_t capacity) { return (size_t)capacity * sizeof(HashSlot) + 128 + (size_t)FILTER_BYTES_PER_SLOT * capacity; }
+size_t anqs_hash_bytes(int64_t capacity) {
+    return (size_t)capacity * sizeof(HashSlot) + 128 + FILTER_ALIGN + (size_t)FILTER_BYTES_PER_SLOT * capacity;
+}
 
 int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                     void *stream) {

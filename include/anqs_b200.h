@@ -106,8 +106,9 @@ int anqs_matrix_elements(const anqs_tables_t *t, const int64_t *d_xprime, const 
 
 /* ---- A5  kernel 2: membership join, HilbertSpace.find_a_in_b (HS:263-284) -----------------------------
  * Open-addressing table in one caller-allocated, 128-byte aligned buffer of anqs_hash_bytes(capacity) bytes:
- * capacity 32-byte slots {key, index, amp.re, amp.im}, one dedicated slot for the all-ones key, a 96-byte header, and
- * a presence filter of 4*capacity bytes (one bit per key; the 128-byte line is chosen by a GF(2)-linear hash of the
+ * capacity 32-byte slots {key, index, amp.re, amp.im}, one dedicated slot for the all-ones key, a 96-byte header, padding
+ * to the next 8 KB address boundary, and a presence filter of 2*capacity bytes (two bits of one 32-bit word per key; the
+ * 128-byte line is chosen by a GF(2)-linear hash of the
  * alpha half of the key, so all the candidates of one sample that share the alpha part of their mask test the same
  * line).  Keys are stored de-interleaved (even bits | odd bits << 32).  capacity: power of two >=
  * anqs_hash_capacity(n).  d_amps may be NULL.  The build is stream-ordered (no host synchronisation); it picks the
