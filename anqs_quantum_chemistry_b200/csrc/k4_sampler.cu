@@ -285,7 +285,36 @@ gumbel_level_kernel(const double *__restrict__ cond, int DM, int k, const double
     }
 }
 
+// ---- survivors of one Gumbel top-k level (ANQS:733-776) -------------------------------------------------------------------
+// sorted_idx[r] = flat (parent * D + outcome) index of the r-th largest perturbed log-probability (the per-level global sort
+// stays a library call).  Row r < keep becomes a node of the next level: prefix | outcome << qudit_start, the next memo
+// index, its log-probability and its Gumbel.  Masked children carry gumbel = -inf and sort last: n_alive counts the rows
+// in front of them, and the caller keeps [0, n_alive).
+__global__ void __launch_bounds__(256)
+gumbel_select_kernel(const int64_t *__restrict__ sorted_idx, const double *__restrict__ sorted_gumbel, int64_t keep, int k,
+                     int qudit_start, const int64_t *__restrict__ prefix, const int32_t *__restrict__ memo_idx,
+                     const int32_t *__restrict__ next_memo_q, const double *__restrict__ level_log_prob,
+                     int64_t *__restrict__ out_prefix, int32_t *__restrict__ out_memo, double *__restrict__ out_log_prob,
+                     double *__restrict__ out_gumbel, int *__restrict__ n_alive) {
+    const int D = 1 << k;
+    int alive_here = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < keep; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t flat = sorted_idx[r];
+        const double g = sorted_gumbel[r];
+        const int64_t parent = flat >> k;
+        const int outcome = (int)(flat & (D - 1));
+        out_prefix[r] = prefix[parent] | ((int64_t)outcome << qudit_start);
+        out_memo[r] = next_memo_q[(int64_t)memo_idx[parent] * D + outcome];
+        out_log_prob[r] = level_log_prob[flat];
+        out_gumbel[r] = g;
+        alive_here += g > -INFINITY ? 1 : 0;
+    }
+    alive_here = __reduce_add_sync(0xffffffffu, alive_here);
+    if ((threadIdx.x & 31) == 0 && alive_here) atomicAdd(n_alive, alive_here);
+}
+
 }  // namespace anqs
+
 
 using namespace anqs;
 
@@ -342,6 +371,26 @@ int anqs_sampler_gumbel_level(const double *d_cond, int max_qudit_dim, int qubit
     gumbel_level_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d_cond, max_qudit_dim, qubits_in_qudit, d_parent_log_prob, d_parent_gumbel, d_memo_idx,
         (const unsigned long long *)d_cont_mask_q, memo_size, n, level, seed, parent_offset, d_uniforms, d_out_log_prob, d_out_gumbel);
+    ANQS_LAUNCH_CHECK();
+    return 0;
+}
+
+int anqs_sampler_gumbel_select(const int64_t *d_sorted_idx, const double *d_sorted_gumbel, int64_t keep, int qubits_in_qudit,
+                               int qudit_start, const int64_t *d_prefix, const int32_t *d_memo_idx, const int32_t *d_next_memo_q,
+                               const double *d_level_log_prob, int64_t *d_out_prefix, int32_t *d_out_memo_idx,
+                               double *d_out_log_prob, double *d_out_gumbel, int32_t *d_n_alive, void *stream) {
+    ANQS_REQUIRE(keep >= 0, "negative row count");
+    ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6, "qudit must have 1..6 qubits");
+    ANQS_REQUIRE(d_n_alive, "null counter");
+    cudaStream_t s = (cudaStream_t)stream;
+    ANQS_CUDA(cudaMemsetAsync(d_n_alive, 0, sizeof(int32_t), s));
+    if (keep == 0) return 0;
+    ANQS_REQUIRE(d_sorted_idx && d_sorted_gumbel && d_prefix && d_memo_idx && d_next_memo_q && d_level_log_prob && d_out_prefix &&
+                     d_out_memo_idx && d_out_log_prob && d_out_gumbel, "null pointer");
+    const int grid = (int)std::min<int64_t>((keep + 255) / 256, (int64_t)sm_count_of_current_device() * 8);
+    gumbel_select_kernel<<<grid, 256, 0, s>>>(d_sorted_idx, d_sorted_gumbel, keep, qubits_in_qudit, qudit_start, d_prefix, d_memo_idx,
+                                              d_next_memo_q, d_level_log_prob, d_out_prefix, d_out_memo_idx, d_out_log_prob, d_out_gumbel,
+                                              d_n_alive);
     ANQS_LAUNCH_CHECK();
     return 0;
 }

@@ -142,13 +142,17 @@ class AutoregressiveSamplerMixin:
             flat_g = out_g.view(-1)
             keep = min(sample_num, flat_g.shape[0])
             top_g, top_i = pt.sort(flat_g, descending=True, stable=True)   # ANQS:733
-            top_g, top_i = top_g[:keep], top_i[:keep]
-            alive = top_g > -math.inf                                       # masked children (ANQS:804-809 phys_mask)
-            top_g, top_i = top_g[alive], top_i[alive]
-            parent, outcome = top_i // D, top_i % D
-            prefix = prefix[parent] | (outcome << qg.qudit_starts[q])
-            memo = next_q.view(-1)[memo[parent].to(pt.int64) * D + outcome]
-            log_prob, gumbel = out_lp.view(-1)[top_i], top_g
+            # ANQS:735-776 in one kernel: children of the kept rows; masked children (gumbel = -inf, ANQS:804-809) sort last
+            new_prefix = pt.empty(keep, dtype=pt.int64, device=dev)
+            new_memo = pt.empty(keep, dtype=pt.int32, device=dev)
+            new_lp = pt.empty(keep, dtype=pt.float64, device=dev)
+            new_g = pt.empty(keep, dtype=pt.float64, device=dev)
+            n_alive = pt.empty(1, dtype=pt.int32, device=dev)
+            _lib.check(lib.anqs_sampler_gumbel_select(_lib.dptr(top_i), _lib.dptr(top_g), keep, k, qg.qudit_starts[q], _lib.dptr(prefix),
+                                                      _lib.dptr(memo), _lib.dptr(next_q), _lib.dptr(out_lp), _lib.dptr(new_prefix),
+                                                      _lib.dptr(new_memo), _lib.dptr(new_lp), _lib.dptr(new_g), _lib.dptr(n_alive), sp))
+            alive = int(n_alive.item())  # the next level's size has to come back to the host
+            prefix, memo, log_prob, gumbel = new_prefix[:alive], new_memo[:alive], new_lp[:alive], new_g[:alive]
         log_prob = log_prob - pt.logsumexp(log_prob, dim=0)
         return prefix.view(-1, 1), pt.exp(log_prob)
 

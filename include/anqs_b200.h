@@ -273,6 +273,17 @@ int anqs_sampler_gumbel_level(const double *d_cond, int max_qudit_dim, int qubit
                               int64_t parent_offset, const double *d_uniforms, double *d_out_log_prob,
                               double *d_out_gumbel, void *stream);
 
+/* Survivors of one Gumbel top-k level (ANQS:733-776).  d_sorted_idx / d_sorted_gumbel = the level's [n*D] perturbed
+ * log-probabilities sorted in descending order (flat index parent * D + outcome; the global sort itself is a library call).
+ * Rows r < keep become the nodes of the next level: d_out_prefix[r] = d_prefix[parent] | outcome << qudit_start,
+ * d_out_memo_idx[r] = d_next_memo_q[memo_idx[parent] * D + outcome], d_out_log_prob[r] = d_level_log_prob[flat],
+ * d_out_gumbel[r] = d_sorted_gumbel[r].  Masked children carry -inf and sort last; *d_n_alive (device int32) = number of
+ * rows in front of them, the caller keeps [0, *d_n_alive). */
+int anqs_sampler_gumbel_select(const int64_t *d_sorted_idx, const double *d_sorted_gumbel, int64_t keep, int qubits_in_qudit,
+                               int qudit_start, const int64_t *d_prefix, const int32_t *d_memo_idx, const int32_t *d_next_memo_q,
+                               const double *d_level_log_prob, int64_t *d_out_prefix, int32_t *d_out_memo_idx,
+                               double *d_out_log_prob, double *d_out_gumbel, int32_t *d_n_alive, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
