@@ -164,10 +164,23 @@ class PauliObservable(AbstractHilbertSpaceObject):
                 info = [_lib.ctypes.c_int(), _lib.ctypes.c_int64(), _lib.ctypes.c_int64(), _lib.ctypes.c_int(), _lib.ctypes.c_int64()]
                 _lib.check(_lib.lib().anqs_tables_info(handle, *[_lib.ctypes.byref(i) for i in info]))
             self._tables = handle
-            self.weights_real = bool(info[3].value)
-            self.bitmap_row_words = int(info[4].value)
+            self._weights_real = bool(info[3].value)
+            self._bitmap_row_words = int(info[4].value)
             self._enum_tiles = int(_lib.lib().anqs_k1_enum_tiles(handle))
         return self._tables
+
+    # properties of the device tables: asking for one creates the tables (they used to be plain attributes that only
+    # existed after the first kernel call)
+    @property
+    def weights_real(self) -> bool:
+        """True when every Pauli weight has zero imaginary part (real-integral molecules): 8-byte matrix elements."""
+        self.tables
+        return self._weights_real
+
+    @property
+    def bitmap_row_words(self) -> int:
+        self.tables
+        return self._bitmap_row_words
 
     @property
     def enum_tiles(self) -> int:

@@ -344,3 +344,30 @@ def test_bit_sliced_local_energy_equals_per_sample_kernel(qubits, electrons, irr
     if samples.shape[0] <= 6000:
         e_ref = orc.local_energy_sample_aware(samples, amps, orc.Tables(xy, yz, w), na, nb)
         assert np.abs(res[2] - e_ref).max() < 1e-10 * scale
+
+
+def test_full_local_energy_on_a_fresh_observable(tmp_path):
+    """compute_local_energies(sample_aware=False) as the first call on a new PauliObservable (the device tables and their
+    properties are created on demand) agrees with the dense-matrix local energy H psi / psi over the whole sector."""
+    from anqs_quantum_chemistry_b200 import ParticleNumberSymmetry, SpinHalfProjectionSymmetry, LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig
+    n, n_el = 12, 4
+    xy, yz, w = synthetic.synthetic_hamiltonian(n, n_irreps=1, seed=0)
+    hs = HilbertSpace(qubit_num=n, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, n))
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=n_el),
+                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    torch.manual_seed(0)
+    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='MADE'))
+    sector = synthetic.random_physical_samples(n, n_el // 2, n_el // 2, 10 ** 4, seed=1)  # all 225 states of the sector
+    assert sector.shape[0] == 225
+    sub = sector[::3].copy()
+    with torch.no_grad():
+        psi = wf.amplitude(_dev(sector.view(np.int64)).view(-1, 1)).cpu().numpy()
+        a = wf.amplitude(_dev(sub.view(np.int64)).view(-1, 1))
+        full, aware, metrics = ham.compute_local_energies(wf=wf, sampled_indices=_dev(sub.view(np.int64)).view(-1, 1), sampled_amps=a,
+                                                          sample_aware=False)
+    tab = orc.Tables(xy, yz, w)
+    e_all = orc.local_energy_sample_aware(sector, psi, tab, n_el // 2, n_el // 2)  # every connected state is in the set: exact H psi / psi
+    pos = np.searchsorted(sector, sub)
+    assert np.abs(full.cpu().numpy() - e_all[pos]).max() < 1e-10 * max(1.0, np.abs(e_all).max())
+    assert metrics.non_sampled_unq_x_primes_num > 0
