@@ -98,18 +98,59 @@ class ShardedLocalEnergy:
         self.beta_num = beta_num
         self.group = group
 
-    @pt.no_grad()
     def __call__(self, local_idx: pt.Tensor, local_amps: pt.Tensor):
         """local_idx [n_r] or [n_r,1] int64, local_amps [n_r] complex128: this rank's shard.
         Returns (E_loc of the local rows, mean, var) with mean/var over the global batch."""
+        return self.stats(local_idx, local_amps)[:3]
+
+    @pt.no_grad()
+    def stats(self, local_idx: pt.Tensor, local_amps: pt.Tensor):
+        """As __call__, plus the global normalisation sum |psi|^2: (E_loc local, mean, var, norm)."""
         from .hilbert_space import SampleTable
         g_idx, g_amps, lo, hi = all_gather_shards(local_idx, local_amps, self.group, self.sizes)
         table = SampleTable(g_idx, g_amps)
         eloc, _, _ = self.ham.compute_var_local_energy_proxy(
             unq_batch_as_base_indices=g_idx.view(-1, 1), unq_batch_as_amps=g_amps, coupling_method='ham',
             alpha_num=self.alpha_num, beta_num=self.beta_num, row_start=lo, row_len=hi - lo, table=table)
-        mean, var, _ = reduce_energy_stats(local_energy_stats(eloc, g_amps[lo:hi]), self.group)
-        return eloc, mean, var
+        mean, var, norm = reduce_energy_stats(local_energy_stats(eloc, g_amps[lo:hi]), self.group)
+        return eloc, mean, var, norm
+
+
+class ShardedEnergyGradient:
+    """Energy gradient of a batch that is sharded over the ranks of `group`.
+
+    The loss of the reference (EXP:609), L = 2 Re sum_i f_i log(conj psi_i) (E_i - <E>) with theoretical frequencies
+    f_i = |psi_i|^2 / sum_j |psi_j|^2 (CLE:107-113), is a sum over samples once <E> and the normalisation are known; both
+    come out of the energy pass already reduced over the ranks.  Every rank back-propagates its own terms through its
+    own shard and the flat parameter gradients are summed with ONE all-reduce; parameters are replicated, so all ranks
+    take the same optimiser step.  `local_energy` is a callable (local_idx, local_amps) -> (E_loc local, mean, var, norm)
+    with global mean / var / norm, e.g. ShardedLocalEnergy(ham, n_alpha, n_beta).stats."""
+
+    def __init__(self, wf, local_energy, group=None):
+        self.wf, self.local_energy, self.group = wf, local_energy, group
+
+    def __call__(self, local_idx: pt.Tensor):
+        """Leaves the global gradient in p.grad of every parameter of wf; returns (mean, var, loss) over the global batch."""
+        wf = self.wf
+        params = [p for p in wf.parameters() if p.requires_grad]
+        for p in params:
+            p.grad = None
+        amps = wf.amplitude(local_idx)
+        eloc, mean, var, norm = self.local_energy(local_idx, amps.detach())
+        with pt.no_grad():
+            a = amps.detach()
+            seed = (a.real * a.real + a.imag * a.imag) / norm * (eloc - mean)   # f_i (E_i - <E>)
+        loss = 2 * (seed * pt.log(pt.conj(amps))).sum().real
+        loss.backward()
+        flat = pt.cat([(p.grad if p.grad is not None else pt.zeros_like(p)).reshape(-1) for p in params] + [loss.detach().reshape(1)])
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(flat, group=self.group)
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.grad = flat[off:off + n].view_as(p).clone()
+            off += n
+        return mean, var, flat[-1]
 
 
 @pt.no_grad()

@@ -79,3 +79,61 @@ def test_all_gather_and_reduce_world_size_2(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 1001, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / 'ok0') and os.path.exists(tmp_path / 'ok1')
+
+
+class _ToyWF(torch.nn.Module):
+    """psi(x) = exp(sum_k theta_k phi_k(x) + i sum_k eta_k phi_k(x)) on CPU: enough to exercise the gradient exchange."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.theta = torch.nn.Parameter(torch.randn(5, dtype=torch.float64) * 0.3)
+        self.eta = torch.nn.Parameter(torch.randn(5, dtype=torch.float64) * 0.3)
+
+    def amplitude(self, idx):
+        x = idx.view(-1, 1).to(torch.float64)
+        phi = torch.cos(x * torch.arange(1, 6, dtype=torch.float64) * 1e-3)
+        return torch.exp(torch.complex(phi @ self.theta, phi @ self.eta))
+
+
+def _toy_energy(idx):
+    x = idx.view(-1).to(torch.float64)
+    return torch.complex(torch.sin(x * 7e-3), 0.1 * torch.cos(x * 3e-3))
+
+
+def _grad_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        idx = torch.arange(0, 4000, 13, dtype=torch.int64)
+        lo, hi = [0, idx.shape[0] // 3, idx.shape[0]][rank:rank + 2]
+
+        def local_energy(local_idx, local_amps):
+            eloc = _toy_energy(local_idx)
+            mean, var, norm = adist.reduce_energy_stats(adist.local_energy_stats(eloc, local_amps))
+            return eloc, mean, var, norm
+
+        wf = _ToyWF()
+        mean, var, loss = adist.ShardedEnergyGradient(wf, local_energy)(idx[lo:hi])
+        # single-process reference on the whole batch: EXP:609 with theoretical frequencies
+        ref = _ToyWF()
+        amps = ref.amplitude(idx)
+        est = MonteCarloEstimator(values=_toy_energy(idx), counts=(amps.detach().conj() * amps.detach()))
+        from anqs_quantum_chemistry_b200.calculations import vmc_loss
+        ref_loss = vmc_loss(amps, est)
+        ref_loss.backward()
+        assert abs(complex(mean) - complex(est.mean)) < 1e-12
+        assert abs(float(loss) - float(ref_loss)) < 1e-12
+        for p, q in zip(wf.parameters(), ref.parameters()):
+            assert float((p.grad - q.grad).abs().max()) < 1e-12
+        open(os.path.join(out_dir, f'grad_ok{rank}'), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_energy_gradient_world_size_2(tmp_path):
+    """Both ranks end up with the gradient of the reference's loss over the WHOLE batch (one all-reduce of the flat gradient)."""
+    port = _free_port()
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / 'grad_ok0') and os.path.exists(tmp_path / 'grad_ok1')
