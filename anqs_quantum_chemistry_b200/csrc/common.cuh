@@ -155,6 +155,7 @@ struct FilterHeader {  // lives in the 96 bytes behind the dedicated slot
     uint32_t gmask;         // (1 << G) - 1
     uint32_t overloaded[FILTER_MAX_SPREAD_BITS + 1];  // keys in lines holding more than 128 << g keys, per candidate g
     uint32_t n_keys;
+    // bytes 40..95 of the header region: seven 64-bit accumulators of the overload sums while the table is being built
 };
 struct HashView {
     const HashSlot *slots;

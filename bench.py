@@ -123,16 +123,18 @@ def _time_ms(fn, reps=5, warm=2):
     return float(np.mean(ts))
 
 
-def vmc_iteration_rate(dev, n=20, n_el=14, sample_num=10 ** 4, iters=20):
+def vmc_iteration_rate(dev, n=20, n_el=14, sample_num=10 ** 4, iters=20, with_sr=False):
     """VMC iterations/s (the second half of BASELINE.json's metric) on the C3 shape the reference was timed on in
     BASELINE.md section 2: 20 qubits, 14 electrons, dense synthetic H (T = 14 251), MADE LogAbsPhaseANQS, Gumbel unique
-    sampling of 1e4 configurations, sample-aware local energies, loss EXP:609, backward, Adam step (EXP:626-679 without
-    stochastic reconfiguration, which is out of scope this round)."""
+    sampling of 1e4 configurations, sample-aware local energies, loss EXP:609, backward, [with_sr: process_grad = stochastic
+    reconfiguration on the 25 most frequent samples (SR:88-136) + gradient clipping, the reference's defaults,] Adam step
+    (EXP:626-679)."""
     import torch
     from anqs_quantum_chemistry_b200 import (HilbertSpace, PauliObservable, PauliArraysOperator, ParticleNumberSymmetry,
                                              SpinHalfProjectionSymmetry, LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig,
                                              SamplingConfig, SamplingResult, sample, LocalEnergyCalculationConfig,
                                              compute_local_energies, vmc_loss, synthetic)
+    from anqs_quantum_chemistry_b200.calculations import process_grad, ProcessGradConfig
     xy, yz, w = synthetic.synthetic_hamiltonian(n, n_irreps=1, seed=0)
     hs = HilbertSpace(qubit_num=n, device=dev, parent_dir=tempfile.mkdtemp(prefix='anqs_vmc_'), rng_seed=0)
     ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, n))
@@ -155,6 +157,8 @@ def vmc_iteration_rate(dev, n=20, n_el=14, sample_num=10 ** 4, iters=20):
         est = le.sample_aware_e_loc_mc_est
         loss = vmc_loss(amps, est)
         loss.backward()
+        if with_sr:
+            process_grad(wf=wf, sampling_result=SamplingResult(indices=indices, counts=res.counts[perm]), config=ProcessGradConfig())
         opt.step()
         return est.mean, indices.shape[0]
 
@@ -168,6 +172,7 @@ def vmc_iteration_rate(dev, n=20, n_el=14, sample_num=10 ** 4, iters=20):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     return {'iters_per_s': iters / dt, 'ms_per_iter': 1e3 * dt / iters, 'n_unq': int(n_unq), 'qubits': n, 'electrons': n_el,
+            'stochastic_reconfiguration': bool(with_sr),
             'terms': int(ham.term_num), 'energy_first': float(energies[0].real), 'energy_last': float(energies[-1].real),
             'note': 'reference on 8 CPU threads: 0.17 it/s (MADE, ham) to 0.37 it/s (NADE, trie) at this size, incl. SR (BASELINE.md section 2)'}
 
@@ -240,6 +245,7 @@ def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     out['sample_stats'] = {'samples': 10 ** 6, 'unique': int(idx.shape[0]), 'seconds': dt, 'unique_per_s': idx.shape[0] / dt,
                            'note': 'untrained MADE (near-uniform): the reference needs 105.7 s for this call on 8 CPU threads (BASELINE.md)'}
     out['vmc_iteration'] = vmc_iteration_rate(dev)
+    out['vmc_iteration_with_sr'] = vmc_iteration_rate(dev, with_sr=True)
     wf.set_inference_precision('tf32')
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -433,7 +439,8 @@ def main():
                        'l2': 'flushed between timed iterations (256 MiB write)', 'parallelism': f'dp{world} (rows sharded, table replicated)'},
             'e2e': {'value': n_set * len(e2e_ms) / (e2e_total * 1e-3), 'unit': 'E_loc/s', 'h2d_bytes_per_step': int(24 * rows),
                     'd2h_bytes_per_step': int(16 * rows)},
-            'gpu_launches': 2 * args.steps,
+            # our kernels per step: filter_count, filter_overload, filter_pick_spread, hash_build (k2_hash.cu) + the fused local-energy kernel
+            'gpu_launches': 5 * args.steps,
             'step_ms_each': [round(v, 3) for v in step_ms],
             'kernel': {'name': kernel_name, 'ms': kernel_ms, 'share_of_step': kernel_ms / (total_ms / args.steps),
                        'filter_tests_per_s': rows * U / (kernel_ms * 1e-3), 'probes_per_s': m_probe / (kernel_ms * 1e-3)},
