@@ -62,7 +62,15 @@ class ClockSampler:
               'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def wait_ready(self, timeout=5.0):
+        """Blocks until nvidia-smi has delivered its first row (its start-up holds driver locks for tens of milliseconds and
+        would otherwise land inside a timed step), then marks where the timed region begins."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -86,7 +94,7 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], [], set()
         names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for r in self.rows:
+        for r in self.rows[self.first:] or self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(names, r[2:6]):
@@ -365,13 +373,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-
     clocks = ClockSampler(local_rank)
     if rank == 0:
-        clocks.start()
+        clocks.start()  # before the warm-up: it must be up and sampling, not starting, when the timed region begins
+    for _ in range(args.warmup):
+        step()
+    if rank == 0:
+        clocks.wait_ready()
+    barrier()
     step_ms = []
     for _ in range(args.steps):
         flush.fill_(1)  # evict L2 between timed iterations
