@@ -1,0 +1,54 @@
+"""BASELINE config 3 (C3): 20 qubits, 14 electrons, dense synthetic H, transformer wave function (dim 64, depth 2, 4 heads) with
+particle-number / S_z masks: amplitudes/s of the hand-written kernel, unique samples/s of both samplers, VMC iterations/s."""
+import sys, os, tempfile, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from anqs_quantum_chemistry_b200 import (HilbertSpace, PauliObservable, PauliArraysOperator, ParticleNumberSymmetry, SpinHalfProjectionSymmetry,
+                                         LocallyDecomposableMasker, SamplingConfig, SamplingResult, sample, LocalEnergyCalculationConfig,
+                                         compute_local_energies, vmc_loss, synthetic)
+from anqs_quantum_chemistry_b200.transformer_anqs import TransformerANQS, TransformerANQSConfig
+dev = torch.device('cuda:0')
+n, n_el = 20, 14
+xy, yz, w = synthetic.synthetic_hamiltonian(n, n_irreps=1, seed=0)
+hs = HilbertSpace(qubit_num=n, device=dev, parent_dir=tempfile.mkdtemp(prefix='anqs_c3_'), rng_seed=0)
+ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, n))
+masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=n_el),
+                                                                 SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+torch.manual_seed(0)
+wf = TransformerANQS(hilbert_space=hs, masker=masker, config=TransformerANQSConfig(dim=64, depth=2, head_num=4))
+out = {'config': 'C3: 20 qubits, 14 e-, dense synthetic H (T = %d), TransformerANQS dim 64 depth 2 heads 4' % ham.term_num}
+
+def wall(fn, reps=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(reps): r = fn()
+    torch.cuda.synchronize()
+    return r, (time.perf_counter() - t0) / reps
+
+sector = torch.from_numpy(synthetic.random_physical_samples(n, n_el // 2, n_el // 2, 10 ** 6, seed=1).view('int64')).to(dev)
+with torch.no_grad():
+    big = sector.repeat(20)[: 1 << 18].contiguous()
+    _, t = wall(lambda: wf.log_psi_kernel(big))
+    out['amplitudes_per_s_kernel_f64'] = big.shape[0] / t
+    (idx, cnt), t = wall(lambda: wf.sample_stats(10 ** 7, seed=1), reps=3, warm=1)
+    out['count_splitting_1e7_samples'] = {'unique': int(idx.shape[0]), 'seconds': t, 'unique_per_s': idx.shape[0] / t}
+    (idx, f), t = wall(lambda: wf.sample_indices_gumbel(10 ** 4), reps=5, warm=2)
+    out['gumbel_1e4'] = {'unique': int(idx.shape[0]), 'seconds': t}
+opt = torch.optim.Adam(wf.parameters(), lr=1e-3)
+cfg_s, cfg_e = SamplingConfig(sample_indices=True, sample_num=10 ** 4), LocalEnergyCalculationConfig(use_tree_for_candidates='ham')
+energies = []
+def one_iter():
+    opt.zero_grad()
+    res, _, _, _ = sample(wf=wf, config=cfg_s)
+    indices, perm = wf.sort_base_idx(res.indices)
+    amps = wf.amplitude(indices)
+    le, _ = compute_local_energies(wf=wf, sampling_result=SamplingResult(indices=indices, counts=res.counts[perm]), sampled_amps=amps.detach(),
+                                   ham=ham, config=cfg_e, sample_aware=True)
+    est = le.sample_aware_e_loc_mc_est
+    vmc_loss(amps, est).backward()
+    opt.step()
+    energies.append(float(est.mean.real))
+_, t = wall(one_iter, reps=20, warm=3)
+out['vmc_iteration'] = {'ms_per_iter': t * 1e3, 'iters_per_s': 1 / t, 'n_unq': 10 ** 4, 'energy_first': energies[0], 'energy_last': energies[-1],
+                        'note': 'forward with gradients runs through the mirrored torch module (library autograd); sampler and E_loc on the hand-written kernels'}
+print(json.dumps(out))
