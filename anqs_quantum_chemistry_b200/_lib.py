@@ -45,6 +45,7 @@ _SIGNATURES = {
     'anqs_accumulate_rows': (_c_int, [_vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_made_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_made_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
+    'anqs_made_backward_chain': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'anqs_nade_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_nade_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
     'anqs_made_tc_packed_bytes': (ctypes.c_size_t, [_vp]),

@@ -122,6 +122,9 @@ class MLP(nn.Module):
                 layer.weight.data.mul_(mask.to(layer.weight.device))
 
 
+_MADE_BWD_SCRATCH_BYTES = 1 << 30  # scratch of one backward launch (dY, da, x); larger batches are processed in chunks
+
+
 class _MadeLogPsi(pt.autograd.Function):
     """log psi(x) of a batch of packed configurations; backward by hand from the saved activations."""
 
@@ -135,50 +138,49 @@ class _MadeLogPsi(pt.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        """The per-sample chain runs in made_backward_kernel (k3_made_bwd.cu); what is left here are the reductions over the
+        batch: grad W_out = dY^T h_last, grad W_l = da_l^T (h_{l-1} | x) and the bias sums, batched over both sub-networks."""
         wf, idx = ctx.wf, ctx.idx
-        save_h, save_p = ctx.saved
-        B, Q, DM, depth = idx.shape[0], wf.qudit_num, wf.max_qudit_dim, wf.depth
-        g_re, g_im = grad_out.real.contiguous(), grad_out.imag.contiguous()
-        x = (1.0 - 2.0 * ((idx.view(-1, 1) >> wf.hilbert_space.shifts) & 1).to(pt.float64))  # [B, n]
-        chosen = wf.chosen_outcomes(idx)                                                    # [B, Q]
-        rows = chosen + DM * pt.arange(Q, device=idx.device).view(1, -1)                    # row of the output layer
+        save_h, save_p = ctx.saved                      # [2, depth, B, width], [B, Q, DM]
+        B, Q, DM, depth, n = idx.shape[0], wf.qudit_num, wf.max_qudit_dim, wf.depth, wf.qubit_num
+        dev = idx.device
+        g = grad_out.to(pt.complex128).contiguous()
+        desc = wf._descriptor()
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        QD, width = Q * DM, wf.width
+        chunk = max(1, min(B, _MADE_BWD_SCRATCH_BYTES // (16 * QD + 16 * depth * width + 8 * n)))
+        gW_out = gb_out = gW0 = gWm = gb_h = None
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            m = hi - lo
+            dY = pt.empty((2, m, QD), dtype=pt.float64, device=dev)
+            da = pt.empty((2, depth, m, width), dtype=pt.float64, device=dev)
+            x = pt.empty((m, n), dtype=pt.float64, device=dev)
+            h = save_h if m == B else save_h[:, :, lo:hi].contiguous()
+            p = save_p if m == B else save_p[lo:hi]
+            _lib.check(lib.anqs_made_backward_chain(ctypes.byref(desc), _lib.dptr(idx[lo:hi]), m, _lib.dptr(pt.view_as_real(g[lo:hi])),
+                                                    _lib.dptr(h), _lib.dptr(p), _lib.dptr(dY), _lib.dptr(da), _lib.dptr(x), sp))
+            parts = (pt.bmm(dY.transpose(1, 2), h[:, depth - 1]),                      # [2, QD, width]
+                     dY.sum(1),                                                        # [2, QD]
+                     pt.matmul(da[:, 0].transpose(1, 2), x),                           # [2, width, n]
+                     pt.matmul(da[:, 1:].transpose(2, 3), h[:, :depth - 1]) if depth > 1 else None,   # [2, depth-1, width, width]
+                     da.sum(2))                                                        # [2, depth, width]
+            if gW_out is None:
+                gW_out, gb_out, gW0, gWm, gb_h = parts
+            else:
+                gW_out, gb_out, gW0, gb_h = gW_out + parts[0], gb_out + parts[1], gW0 + parts[2], gb_h + parts[4]
+                gWm = gWm + parts[3] if depth > 1 else None
         n_layer = depth + 1
         per_net = 2 * n_layer if wf.use_bias else n_layer
         grads = [None] * (2 * per_net)
-
-        def put(net, layer, gw, gb):
-            base = net * per_net
-            if wf.use_bias:
-                grads[base + 2 * layer], grads[base + 2 * layer + 1] = gw, gb
-            else:
-                grads[base + layer] = gw
-
         for net in range(2):
-            W = [ctx.weights[net * per_net + (2 * l if wf.use_bias else l)] for l in range(n_layer)]
-            h = [save_h[net, l] for l in range(depth)]  # [B, width] each
-            if net == 0:
-                # d log|psi| / d y_qd = [d == chosen] - p_qd (the mean subtraction drops out: the entries sum to zero)
-                dY = -(g_re.view(-1, 1, 1) * save_p)
-                dY.view(B, Q * DM).scatter_add_(1, rows, g_re.view(-1, 1).expand(B, Q))
-                dY = dY.view(B, Q * DM)
-                gw, gb = dY.t() @ h[-1], dY.sum(0)
-                dh = dY @ W[depth]
-            else:
-                coeff = (math.pi * g_im).view(-1, 1)                                        # arg psi = pi * sum_q y[q, chosen]
-                gw = pt.zeros_like(W[depth])
-                gw.index_add_(0, rows.reshape(-1), (coeff * h[-1]).unsqueeze(1).expand(B, Q, h[-1].shape[1]).reshape(B * Q, -1))
-                gb = pt.zeros(W[depth].shape[0], dtype=pt.float64, device=idx.device)
-                gb.index_add_(0, rows.reshape(-1), coeff.expand(B, Q).reshape(-1))
-                dh = coeff * W[depth][rows.reshape(-1)].view(B, Q, -1).sum(1)
-            put(net, depth, gw, gb)
-            for l in range(depth - 1, -1, -1):
-                da = dh * (1.0 - h[l] * h[l])
-                inp = x if l == 0 else h[l - 1]
-                put(net, l, da.t() @ inp, da.sum(0))
-                if l > 0:
-                    dh = da @ W[l]
-                    if wf.use_res:
-                        dh = dh + da
+            for l in range(n_layer):
+                gw = gW0[net] if l == 0 else (gW_out[net] if l == depth else gWm[net, l - 1])
+                if wf.use_bias:
+                    grads[net * per_net + 2 * l] = gw
+                    grads[net * per_net + 2 * l + 1] = gb_out[net] if l == depth else gb_h[net, l]
+                else:
+                    grads[net * per_net + l] = gw
         return (None, None) + tuple(grads)
 
 

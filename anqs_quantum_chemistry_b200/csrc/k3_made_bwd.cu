@@ -1,0 +1,184 @@
+// Kernel family 3, backward: the per-sample chain of the MADE wave function's gradient (reference: autograd through
+// ANQS:407-485 / LAP:63-163 / MLP:217-246).
+//
+// d log psi / d theta splits into a per-sample chain (output-layer gradient -> hidden-layer gradients, 64-wide, needs the saved
+// activations and conditional probabilities of the forward pass) and reductions over the batch (outer products summed over
+// samples).  made_backward_kernel does the whole chain for both sub-networks in one launch and writes exactly the operands
+// of the batch reductions, which are plain GEMMs / column sums and stay library calls:
+//   dY[net][B][Q*DM]   gradient w.r.t. the output layer's pre-activations
+//                        log-abs network:  g_re * ([d == chosen] - p_qd)   (the mean subtraction drops out: the entries sum to 0)
+//                        phase network:    pi * g_im * [d == chosen]
+//   da[net][l][B][64]  gradient w.r.t. the pre-activation of hidden layer l: dh * (1 - h_l^2),
+//                        dh_{l-1} = da_l W_l (+ da_l on the residual connection, MLP:237-239)
+//   x[B][n]            the 1 - 2 bit input encoding (MLP:205-215)
+// so that  grad W_out = dY^T h_last, grad b_out = sum_s dY, grad W_l = da_l^T (h_{l-1} | x), grad b_l = sum_s da_l.
+// Same 64-sample x 64-output DFMA tiles as the forward kernel.
+#include <algorithm>
+
+#include "common.cuh"
+#include "made_common.cuh"
+
+namespace anqs {
+
+constexpr size_t MDB_SMEM = (size_t)2 * 64 * MD_S * sizeof(double) + 64 * sizeof(uint64_t) + 64 * sizeof(double2);
+
+// acc[ss][jj] += sum_k act[k][ty*4+ss] * wt[k][tx+16*jj]
+__device__ __forceinline__ void gemm_tile_acc(const double *act, const double *wt, int K, int tx, int ty, double (&acc)[4][4]) {
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const double2 a01 = *reinterpret_cast<const double2 *>(act + k * MD_S + ty * 4);
+        const double2 a23 = *reinterpret_cast<const double2 *>(act + k * MD_S + ty * 4 + 2);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+        double w[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) w[jj] = wt[k * MD_S + tx + 16 * jj];
+#pragma unroll
+        for (int ss = 0; ss < 4; ++ss)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[ss][jj] = fma(a[ss], w[jj], acc[ss][jj]);
+    }
+}
+
+__global__ void __launch_bounds__(MD_THREADS, 2)
+made_backward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in, int64_t B, const double2 *__restrict__ grad_out,
+                     const double *__restrict__ save_h, const double *__restrict__ save_p, double *__restrict__ dY,
+                     double *__restrict__ da_out, double *__restrict__ x_out) {
+    extern __shared__ __align__(16) unsigned char md_smem[];
+    double *act = reinterpret_cast<double *>(md_smem);
+    double *wt = act + 64 * MD_S;
+    uint64_t *s_idx = reinterpret_cast<uint64_t *>(wt + 64 * MD_S);
+    double2 *s_g = reinterpret_cast<double2 *>(s_idx + 64);
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n = P.qubit_num, Q = P.qudit_num, DM = P.max_qudit_dim, depth = P.depth;
+    const size_t QD = (size_t)Q * DM;
+    const int64_t ntiles = (B + MD_TB - 1) / MD_TB;
+    const double PI = 3.14159265358979323846;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * MD_TB;
+        __syncthreads();
+        if (tid < 64) {
+            const bool ok = base + tid < B;
+            s_idx[tid] = ok ? (uint64_t)idx_in[base + tid] : 0ull;
+            s_g[tid] = ok ? grad_out[base + tid] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        for (int e = tid; e < 64 * n; e += MD_THREADS) {  // input encoding, [sample][qubit]
+            const int s = e / n, k = e - s * n;
+            if (base + s < B) x_out[(size_t)(base + s) * n + k] = 1.0 - 2.0 * (double)((s_idx[s] >> k) & 1ull);
+        }
+        for (int net = 0; net < 2; ++net) {
+            const double *const *Ws = net == 0 ? P.w_abs : P.w_phase;
+            double dh[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dh[a][b] = 0.0;
+            double *dYn = dY + (size_t)net * (size_t)B * QD;
+            if (net == 0) {
+                // output layer of the log-abs network: dY tile per qudit, dh += dY_q W_out[q]
+                for (int q = 0; q < Q; ++q) {
+                    const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start;
+                    __syncthreads();  // the previous GEMM is done with act / wt
+                    for (int e = tid; e < 64 * 64; e += MD_THREADS) {
+                        const int s = e >> 6, d = e & 63;
+                        double v = 0.0;
+                        if (d < DM && base + s < B) {
+                            const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
+                            const double p = __ldg(save_p + ((size_t)(base + s) * Q + q) * DM + d);
+                            v = s_g[s].x * ((d == chosen ? 1.0 : 0.0) - p);
+                            dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = v;
+                        }
+                        act[d * MD_S + s] = v;
+                        const int dd = e >> 6, j = e & 63;  // weight rows of this qudit, as they lie: wt[d][j] = W[(q DM + d)][j]
+                        wt[dd * MD_S + j] = dd < DM ? __ldg(Ws[depth] + ((size_t)q * DM + dd) * MD_W + j) : 0.0;
+                    }
+                    __syncthreads();
+                    gemm_tile_acc(act, wt, DM, tx, ty, dh);
+                }
+            } else {
+                // phase network: only the chosen outcome of every qudit carries a gradient (arg psi = pi * sum_q y[q, chosen])
+                for (int q = 0; q < Q; ++q) {
+                    const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start;
+                    for (int e = tid; e < 64 * 64; e += MD_THREADS) {
+                        const int s = e >> 6, d = e & 63;
+                        if (d < DM && base + s < B) {
+                            const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
+                            dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = d == chosen ? PI * s_g[s].y : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int ss = 0; ss < 4; ++ss) {
+                        const int s = ty * 4 + ss;
+                        const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
+                        const double *w = Ws[depth] + ((size_t)q * DM + chosen) * MD_W;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) dh[ss][jj] += __ldg(w + tx + 16 * jj);
+                    }
+                }
+#pragma unroll
+                for (int ss = 0; ss < 4; ++ss)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) dh[ss][jj] *= PI * s_g[ty * 4 + ss].y;
+            }
+            // hidden layers, last to first
+            for (int l = depth - 1; l >= 0; --l) {
+                double da[4][4];
+#pragma unroll
+                for (int ss = 0; ss < 4; ++ss) {
+                    const int64_t row = base + ty * 4 + ss;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = tx + 16 * jj;
+                        double v = 0.0;
+                        if (row < B) {
+                            const double h = __ldg(save_h + (((size_t)net * depth + l) * (size_t)B + (size_t)row) * MD_W + j);
+                            v = dh[ss][jj] * (1.0 - h * h);
+                            da_out[(((size_t)net * depth + l) * (size_t)B + (size_t)row) * MD_W + j] = v;
+                        }
+                        da[ss][jj] = v;
+                    }
+                }
+                if (l > 0) {
+                    __syncthreads();
+#pragma unroll
+                    for (int ss = 0; ss < 4; ++ss)
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) act[(tx + 16 * jj) * MD_S + ty * 4 + ss] = da[ss][jj];
+                    for (int e = tid; e < 64 * 64; e += MD_THREADS) {
+                        const int j = e >> 6, i = e & 63;
+                        wt[j * MD_S + i] = __ldg(Ws[l] + (size_t)j * MD_W + i);
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) dh[a][b] = P.use_res ? da[a][b] : 0.0;  // residual connection (MLP:237-239)
+                    gemm_tile_acc(act, wt, MD_W, tx, ty, dh);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace anqs
+
+using namespace anqs;
+
+extern "C" int anqs_made_backward_chain(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                                        const double *d_save_h, const double *d_save_p, double *d_dY, double *d_da, double *d_x,
+                                        void *stream) {
+    ANQS_REQUIRE(desc, "null network descriptor");
+    ANQS_REQUIRE(desc->width == MD_W && desc->max_qudit_dim <= 64 && desc->depth >= 1 && desc->depth <= 4, "unsupported network shape");
+    ANQS_REQUIRE(n >= 0, "negative sample count");
+    if (n == 0) return 0;
+    ANQS_REQUIRE(d_idx && d_grad_out && d_save_h && d_save_p && d_dY && d_da && d_x, "null pointer");
+    ANQS_CUDA(cudaFuncSetAttribute(made_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MDB_SMEM));
+    const int64_t ntiles = (n + MD_TB - 1) / MD_TB;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count_of_current_device() * 2);
+    made_backward_kernel<<<grid, MD_THREADS, MDB_SMEM, (cudaStream_t)stream>>>(*desc, d_idx, n, (const double2 *)d_grad_out, d_save_h,
+                                                                              d_save_p, d_dY, d_da, d_x);
+    ANQS_LAUNCH_CHECK();
+    return 0;
+}

@@ -180,6 +180,18 @@ int anqs_made_log_psi(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_
 int anqs_made_cond_log_abs(const anqs_made_desc_t *desc, int qudit_idx, const int64_t *d_prefix, int64_t n,
                            double *d_cond, void *stream);
 
+/* Backward of anqs_made_log_psi: the per-sample chain of d log psi / d parameters for both sub-networks, from the
+ * activations (d_save_h) and conditional probabilities (d_save_p) the forward call saved and the upstream gradient
+ * d_grad_out[n] (complex128: .re multiplies d log|psi|, .im multiplies d arg psi).  Writes the operands of the batch
+ * reductions, which are plain GEMMs / column sums and are left to the caller:
+ *   d_dY[2][n][qudit_num * max_qudit_dim]  gradient w.r.t. the output layer's pre-activations (net 0 = log-abs, 1 = phase)
+ *   d_da[2][depth][n][width]               gradient w.r.t. the pre-activation of hidden layer l
+ *   d_x[n][qubit_num]                      the 1 - 2 bit input encoding
+ * grad W_out = dY^T h_last, grad b_out = sum_s dY, grad W_l = da_l^T (h_{l-1} | x), grad b_l = sum_s da_l. */
+int anqs_made_backward_chain(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                             const double *d_save_h, const double *d_save_p, double *d_dY, double *d_da, double *d_x,
+                             void *stream);
+
 /* ---- A9  kernel 3, NADE mode (ANQS:410-428, LAP:24-42): one (log-abs, phase) MLP pair per qudit --------------------------
  * Same scalar fields as anqs_made_desc_t.  d_ptrs is a DEVICE array of 2 * qudit_num * (depth + 1) * 2 device pointers:
  * entry ((net * qudit_num + q) * (depth + 1) + layer) * 2 + {0: weight [out][in], 1: bias or NULL}; net 0 =
