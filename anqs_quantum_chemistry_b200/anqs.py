@@ -496,19 +496,29 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
 
         blocks = []
         if self.de_mode == 'MADE':
-            DM = self.max_qudit_dim
-            out_rows = chosen + DM * pt.arange(Q, device=dev).view(1, -1)
-            for net, sub in enumerate((self.log_abs_subnet, self.phase_subnet)):
-                W = [layer.weight.data for layer in sub.layers]
-                h = [save_h[net, l] for l in range(depth)]
-                if net == 0:   # d Re log psi / d y_qd = [d == chosen] - p_qd
-                    dY = -save_p.clone()
-                    dY.view(B, Q * DM).scatter_add_(1, out_rows, pt.ones((B, Q), dtype=pt.float64, device=dev))
-                    dY = dY.view(B, Q * DM)
-                else:          # d Im log psi / d y_qd = pi [d == chosen]
-                    dY = pt.zeros((B, Q * DM), dtype=pt.float64, device=dev)
-                    dY.scatter_(1, out_rows, math.pi)
-                blocks.append(flat(mlp_rows(bits, h, W, dY), imag=net == 1))
+            # the per-sample chain of both sub-networks in one launch (k3_made_bwd.cu) with unit upstream gradients; the rows of
+            # the Jacobian are the per-sample outer products of its outputs with the saved activations
+            QD, width, n = Q * self.max_qudit_dim, self.width, self.qubit_num
+            dY = pt.empty((2, B, QD), dtype=pt.float64, device=dev)
+            da = pt.empty((2, depth, B, width), dtype=pt.float64, device=dev)
+            x = pt.empty((B, n), dtype=pt.float64, device=dev)
+            ones = pt.ones((B, 2), dtype=pt.float64, device=dev)
+            desc = self._descriptor()
+            _lib.check(_lib.lib().anqs_made_backward_chain(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(ones), _lib.dptr(save_h),
+                                                           _lib.dptr(save_p), _lib.dptr(dY), _lib.dptr(da), _lib.dptr(x),
+                                                           _lib.stream_ptr(dev)))
+            for net in range(2):
+                cols = []
+                for l in range(depth + 1):
+                    if l == depth:
+                        g_out, inp = dY[net], save_h[net, depth - 1]
+                    else:
+                        g_out, inp = da[net, l], (x if l == 0 else save_h[net, l - 1])
+                    cols.append((g_out.unsqueeze(2) * inp.unsqueeze(1)).reshape(B, -1))
+                    if self.use_bias:
+                        cols.append(g_out)
+                g = pt.cat(cols, dim=1)
+                blocks.append(pt.complex(zero.expand_as(g), -g) if net == 1 else pt.complex(g, zero.expand_as(g)))
         else:
             for net, subs in enumerate((self.log_abs_subnet, self.phase_subnet)):
                 for q, mlp in enumerate(subs):

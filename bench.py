@@ -44,6 +44,17 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def ncu_pipes(n_unq, world):
+    """ALU-pipe and issue utilisation of the dominant kernel from the same committed ncu capture (None when not captured)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))['fused_eloc_bs_kernel']
+        if world == 1 and int(t['n_unq_per_gpu']) == int(n_unq):
+            return {'alu_pipe_busy': t['alu_pipe_busy'], 'issue_active': t['issue_active'], 'warp_instructions_per_row': t['warp_instructions'] / n_unq}
+    except Exception:
+        pass
+    return None
+
+
 def ncu_traffic(n_unq, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture of
     this exact configuration (profiles/traffic.json); None when the configuration was not captured."""
@@ -454,7 +465,8 @@ def main():
             'kernel': {'name': kernel_name, 'ms': kernel_ms, 'share_of_step': kernel_ms / (total_ms / args.steps),
                        'filter_tests_per_s': rows * U / (kernel_ms * 1e-3), 'probes_per_s': m_probe / (kernel_ms * 1e-3)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(args.n_unq, world),
-                         'peak_source': peak_src,
+                         'peak_source': peak_src, 'real_limiter': ncu_pipes(args.n_unq, world),
+                         'achieved_dram_gbs': (ncu_traffic(args.n_unq, world) or 0.0) / (kernel_ms * 1e-3) / 1e9,
                          'algorithmic_bytes': '32 B per probed candidate + 24 B per table sample + 16 B per row + 8U + 16T',
                          'note': 'probe bandwidth as SURVEY 8(d) defines it for the fused kernel (one notional 32-byte slot sector per probed candidate). The kernel '
                                  'answers ~99.7 % of the probes from a 4-byte word of an L1/L2-resident presence filter, so its DRAM traffic (`traffic`) is ~1 % of '
