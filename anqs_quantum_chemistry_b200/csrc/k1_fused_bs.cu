@@ -406,6 +406,28 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
     const int S = FB_WARPS / R;
     const int grid = (int)std::min<int64_t>((ngroups + S - 1) / S, sms);
     cudaError_t e;
+    // Presence filters beyond ~24 MB fall out of L2 under their own single-sector random traffic (profiles/README.md):
+    // ask for the filter to be kept as persisting L2 lines for this launch.  Best effort - every call may be refused.
+    const size_t filter_bytes = ((size_t)hv.linemask + 1) * 128;
+    bool window = false;
+    if (filter_bytes > ((size_t)16 << 20)) {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (max_persist > 0 && max_window > 0) {
+            const size_t want = std::min<size_t>(filter_bytes, (size_t)max_persist);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr = {};
+            attr.accessPolicyWindow.base_ptr = const_cast<uint8_t *>(hv.filter);
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(filter_bytes, (size_t)max_window);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)filter_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            window = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+        }
+        cudaGetLastError();  // refusals are not errors of this call
+    }
     if (t->weights_real) {
         auto kern = fused_eloc_bs_kernel<true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -418,6 +440,12 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
         if (e != cudaSuccess) return -1;
         kern<<<grid, FB_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num, beta_num,
                                             (double2 *)d_eloc, R);
+    }
+    if (window) {  // the window applies to the launches issued while it is set: clear it again
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
     }
     return 1;
 }
