@@ -197,42 +197,57 @@ class _NadeLogPsi(pt.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
+        """The per-sample chains of all 2 Q MLPs run in nade_backward_kernel (k3_made_bwd.cu); the reductions over the batch
+        are batched GEMMs / column sums over (sub-network, qudit)."""
         wf, idx = ctx.wf, ctx.idx
         save_h, save_p = ctx.saved                      # [2, Q, depth, B, width], [B, Q, DM]
-        B, Q, depth = idx.shape[0], wf.qudit_num, wf.depth
-        g_re, g_im = grad_out.real.contiguous(), grad_out.imag.contiguous()
-        bits = (1.0 - 2.0 * ((idx.view(-1, 1) >> wf.hilbert_space.shifts) & 1).to(pt.float64))   # [B, n]
-        chosen = wf.chosen_outcomes(idx)                                                          # [B, Q]
+        B, Q, DM, depth, n, width = idx.shape[0], wf.qudit_num, wf.max_qudit_dim, wf.depth, wf.qubit_num, wf.width
+        dev = idx.device
+        g = grad_out.to(pt.complex128).contiguous()
+        desc = wf._descriptor()
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        QD = Q * DM
+        chunk = max(1, min(B, _MADE_BWD_SCRATCH_BYTES // (32 * QD + 16 * Q * depth * width + 8 * n)))
+        acc = None
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            m = hi - lo
+            dY = pt.empty((2, m, QD), dtype=pt.float64, device=dev)
+            da = pt.empty((2, Q, depth, m, width), dtype=pt.float64, device=dev)
+            x = pt.empty((m, n), dtype=pt.float64, device=dev)
+            h = save_h if m == B else save_h[:, :, :, lo:hi].contiguous()
+            p = save_p if m == B else save_p[lo:hi]
+            _lib.check(lib.anqs_nade_backward_chain(ctypes.byref(desc), _lib.dptr(idx[lo:hi]), m, _lib.dptr(pt.view_as_real(g[lo:hi])),
+                                                    _lib.dptr(h), _lib.dptr(p), _lib.dptr(dY), _lib.dptr(da), _lib.dptr(x), sp))
+            dYq = dY.view(2, m, Q, DM).permute(0, 2, 3, 1)                                # [2, Q, DM, m]
+            parts = [pt.matmul(dYq, h[:, :, depth - 1]),                                  # [2, Q, DM, width]
+                     dY.sum(1).view(2, Q, DM),                                            # [2, Q, DM]
+                     pt.matmul(da[:, :, 0].transpose(2, 3), x),                           # [2, Q, width, n]
+                     da.sum(3)]                                                           # [2, Q, depth, width]
+            if depth > 1:
+                parts.append(pt.matmul(da[:, :, 1:].transpose(3, 4), h[:, :, :depth - 1]))   # [2, Q, depth-1, width, width]
+            acc = parts if acc is None else [a + b for a, b in zip(acc, parts)]
+        gW_out, gb_out, gW0, gb_h = acc[:4]
+        gWm = acc[4] if depth > 1 else None
         n_layer = depth + 1
         per_mlp = 2 * n_layer if wf.use_bias else n_layer
         grads = [None] * len(ctx.weights)
-        rows = pt.arange(B, device=idx.device)
         for net in range(2):
             for q in range(Q):
                 base = (net * Q + q) * per_mlp
-                W = [ctx.weights[base + (2 * l if wf.use_bias else l)] for l in range(n_layer)]
-                h = [save_h[net, q, l] for l in range(depth)]
                 start, D = wf.qudit_starts[q], wf.qubit_grouping.qudit_dims_host[q]
-                x = bits[:, :start] if start > 0 else pt.zeros((B, 1), dtype=pt.float64, device=idx.device)
-                if net == 0:
-                    dY = -(g_re.view(-1, 1) * save_p[:, q, :D])
-                    dY[rows, chosen[:, q]] += g_re
-                else:
-                    dY = pt.zeros((B, D), dtype=pt.float64, device=idx.device)
-                    dY[rows, chosen[:, q]] = math.pi * g_im
-                out = [(dY.t() @ h[-1], dY.sum(0))]
-                dh = dY @ W[depth]
-                for l in range(depth - 1, -1, -1):
-                    da = dh * (1.0 - h[l] * h[l])
-                    inp = x if l == 0 else h[l - 1]
-                    out.append((da.t() @ inp, da.sum(0)))
-                    if l > 0:
-                        dh = da @ W[l]
-                        if wf.use_res:
-                            dh = dh + da
-                for l, (gw, gb) in zip(range(depth, -1, -1), out):
+                for l in range(n_layer):
+                    if l == 0:   # LAP:26: the first qudit's network sees one constant-zero input
+                        gw = gW0[net, q, :, :start] if start > 0 else pt.zeros((width, 1), dtype=pt.float64, device=dev)
+                    elif l == depth:
+                        gw = gW_out[net, q, :D]
+                    else:
+                        gw = gWm[net, q, l - 1]
+                    if l == depth and depth == 0:
+                        gw = gW_out[net, q, :D]
                     if wf.use_bias:
-                        grads[base + 2 * l], grads[base + 2 * l + 1] = gw, gb
+                        grads[base + 2 * l] = gw
+                        grads[base + 2 * l + 1] = gb_out[net, q, :D] if l == depth else gb_h[net, q, l]
                     else:
                         grads[base + l] = gw
         return (None, None) + tuple(grads)
@@ -461,39 +476,13 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
     @pt.no_grad()
     def compute_cat_log_jac(self, indices: pt.Tensor) -> pt.Tensor:
         """ANQS:820-839: [B, param_num] complex128, row b = d log(conj psi(x_b)) / d theta with the parameters concatenated in
-        .parameters() order.  One forward launch with saved activations, then the per-sample chain rule as batched outer
-        products - no loop over samples (the reference vmaps autograd over the <= 50 samples SR uses, SR:20-32)."""
+        .parameters() order.  One forward launch with saved activations, one launch of the backward chain kernel with unit
+        upstream gradients, then per-sample outer products - no loop over samples (the reference vmaps autograd over the
+        <= 50 samples SR uses, SR:20-32)."""
         idx = indices.contiguous().view(-1)
         B, Q, depth, dev = idx.shape[0], self.qudit_num, self.depth, idx.device
         _, (save_h, save_p) = self._launch_log_psi(idx, save=True)
-        bits = (1.0 - 2.0 * ((idx.view(-1, 1) >> self.hilbert_space.shifts) & 1).to(pt.float64))
-        chosen = self.chosen_outcomes(idx)
-        rows = pt.arange(B, device=dev)
         zero = pt.zeros((), dtype=pt.float64, device=dev)
-
-        def mlp_rows(x, h, W, dY):
-            """Per-sample gradients of one MLP: [(gW [B, out, in], gb [B, out])] for layers 0..depth given dY = d f / d output."""
-            out = [(dY.unsqueeze(2) * h[-1].unsqueeze(1), dY)]
-            dh = dY @ W[depth]
-            for l in range(depth - 1, -1, -1):
-                da = dh * (1.0 - h[l] * h[l])
-                inp = x if l == 0 else h[l - 1]
-                out.append((da.unsqueeze(2) * inp.unsqueeze(1), da))
-                if l > 0:
-                    dh = da @ W[l]
-                    if self.use_res:
-                        dh = dh + da
-            return out[::-1]
-
-        def flat(per_layer, imag):
-            cols = []
-            for gW, gb in per_layer:
-                cols.append(gW.reshape(B, -1))
-                if self.use_bias:
-                    cols.append(gb)
-            g = pt.cat(cols, dim=1)
-            return pt.complex(zero.expand_as(g), -g) if imag else pt.complex(g, zero.expand_as(g))
-
         blocks = []
         if self.de_mode == 'MADE':
             # the per-sample chain of both sub-networks in one launch (k3_made_bwd.cu) with unit upstream gradients; the rows of
@@ -520,19 +509,34 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
                 g = pt.cat(cols, dim=1)
                 blocks.append(pt.complex(zero.expand_as(g), -g) if net == 1 else pt.complex(g, zero.expand_as(g)))
         else:
-            for net, subs in enumerate((self.log_abs_subnet, self.phase_subnet)):
-                for q, mlp in enumerate(subs):
-                    W = [layer.weight.data for layer in mlp.layers]
-                    h = [save_h[net, q, l] for l in range(depth)]
+            # NADE: the chains of all 2 Q MLPs in one launch, then per-sample outer products in .parameters() order
+            DM, width, n = self.max_qudit_dim, self.width, self.qubit_num
+            dY = pt.empty((2, B, Q * DM), dtype=pt.float64, device=dev)
+            da = pt.empty((2, Q, depth, B, width), dtype=pt.float64, device=dev)
+            x = pt.empty((B, n), dtype=pt.float64, device=dev)
+            ones = pt.ones((B, 2), dtype=pt.float64, device=dev)
+            desc = self._descriptor()
+            _lib.check(_lib.lib().anqs_nade_backward_chain(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(ones), _lib.dptr(save_h),
+                                                           _lib.dptr(save_p), _lib.dptr(dY), _lib.dptr(da), _lib.dptr(x),
+                                                           _lib.stream_ptr(dev)))
+            dYq = dY.view(2, B, Q, DM)
+            for net in range(2):
+                cols = []
+                for q in range(Q):
                     start, D = self.qudit_starts[q], self.qubit_grouping.qudit_dims_host[q]
-                    x = bits[:, :start] if start > 0 else pt.zeros((B, 1), dtype=pt.float64, device=dev)
-                    if net == 0:
-                        dY = -save_p[:, q, :D].clone()
-                        dY[rows, chosen[:, q]] += 1.0
-                    else:
-                        dY = pt.zeros((B, D), dtype=pt.float64, device=dev)
-                        dY[rows, chosen[:, q]] = math.pi
-                    blocks.append(flat(mlp_rows(x, h, W, dY), imag=net == 1))
+                    for l in range(depth + 1):
+                        if l == depth:
+                            g_out, inp = dYq[net, :, q, :D], save_h[net, q, depth - 1]
+                        elif l == 0:
+                            g_out = da[net, q, 0]
+                            inp = x[:, :start] if start > 0 else pt.zeros((B, 1), dtype=pt.float64, device=dev)
+                        else:
+                            g_out, inp = da[net, q, l], save_h[net, q, l - 1]
+                        cols.append((g_out.unsqueeze(2) * inp.unsqueeze(1)).reshape(B, -1))
+                        if self.use_bias:
+                            cols.append(g_out)
+                g = pt.cat(cols, dim=1)
+                blocks.append(pt.complex(zero.expand_as(g), -g) if net == 1 else pt.complex(g, zero.expand_as(g)))
         return pt.cat(blocks, dim=1)
 
     @staticmethod

@@ -162,6 +162,107 @@ made_backward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_i
     }
 }
 
+// NADE mode: the same chain for every (sub-network, qudit) MLP (LAP:24-42): output width D_q = 2^bits of the qudit, first layer
+// fed by the qubits before the qudit.  Outputs: dY[2][B][Q*DM] (entries d >= D_q are zero), da[2][Q][depth][B][64], x[B][n].
+__global__ void __launch_bounds__(MD_THREADS, 2)
+nade_backward_kernel(const anqs_nade_desc_t P, const int64_t *__restrict__ idx_in, int64_t B, const double2 *__restrict__ grad_out,
+                     const double *__restrict__ save_h, const double *__restrict__ save_p, double *__restrict__ dY,
+                     double *__restrict__ da_out, double *__restrict__ x_out) {
+    extern __shared__ __align__(16) unsigned char md_smem[];
+    double *act = reinterpret_cast<double *>(md_smem);
+    double *wt = act + 64 * MD_S;
+    uint64_t *s_idx = reinterpret_cast<uint64_t *>(wt + 64 * MD_S);
+    double2 *s_g = reinterpret_cast<double2 *>(s_idx + 64);
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n = P.qubit_num, Q = P.qudit_num, DM = P.max_qudit_dim, depth = P.depth;
+    const size_t QD = (size_t)Q * DM;
+    const int64_t ntiles = (B + MD_TB - 1) / MD_TB;
+    const double PI = 3.14159265358979323846;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * MD_TB;
+        __syncthreads();
+        if (tid < 64) {
+            const bool ok = base + tid < B;
+            s_idx[tid] = ok ? (uint64_t)idx_in[base + tid] : 0ull;
+            s_g[tid] = ok ? grad_out[base + tid] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        for (int e = tid; e < 64 * n; e += MD_THREADS) {
+            const int s = e / n, k = e - s * n;
+            if (base + s < B) x_out[(size_t)(base + s) * n + k] = 1.0 - 2.0 * (double)((s_idx[s] >> k) & 1ull);
+        }
+        for (int net = 0; net < 2; ++net) {
+            double *dYn = dY + (size_t)net * (size_t)B * QD;
+            for (int q = 0; q < Q; ++q) {
+                const double *const *tab = P.ptrs + ((size_t)(net * Q + q) * (depth + 1)) * 2;
+                const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start, D = 1 << bits;
+                const double *W_out = tab[2 * depth];
+                double dh[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) dh[a][b] = 0.0;
+                __syncthreads();  // the previous GEMM is done with act / wt
+                for (int e = tid; e < 64 * 64; e += MD_THREADS) {
+                    const int s = e >> 6, d = e & 63;
+                    double v = 0.0;
+                    if (d < DM && base + s < B) {
+                        const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
+                        if (d < D)
+                            v = net == 0 ? s_g[s].x * ((d == chosen ? 1.0 : 0.0) - __ldg(save_p + ((size_t)(base + s) * Q + q) * DM + d))
+                                         : (d == chosen ? PI * s_g[s].y : 0.0);
+                        dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = v;
+                    }
+                    act[d * MD_S + s] = v;
+                    const int dd = e >> 6, j = e & 63;
+                    wt[dd * MD_S + j] = dd < D ? __ldg(W_out + (size_t)dd * MD_W + j) : 0.0;
+                }
+                __syncthreads();
+                gemm_tile_acc(act, wt, D, tx, ty, dh);
+                for (int l = depth - 1; l >= 0; --l) {
+                    double da[4][4];
+#pragma unroll
+                    for (int ss = 0; ss < 4; ++ss) {
+                        const int64_t row = base + ty * 4 + ss;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = tx + 16 * jj;
+                            double v = 0.0;
+                            if (row < B) {
+                                const size_t off = ((((size_t)net * Q + q) * depth + l) * (size_t)B + (size_t)row) * MD_W + j;
+                                const double h = __ldg(save_h + off);
+                                v = dh[ss][jj] * (1.0 - h * h);
+                                da_out[off] = v;
+                            }
+                            da[ss][jj] = v;
+                        }
+                    }
+                    if (l > 0) {
+                        __syncthreads();
+#pragma unroll
+                        for (int ss = 0; ss < 4; ++ss)
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) act[(tx + 16 * jj) * MD_S + ty * 4 + ss] = da[ss][jj];
+                        const double *W = tab[2 * l];
+                        for (int e = tid; e < 64 * 64; e += MD_THREADS) {
+                            const int j = e >> 6, i = e & 63;
+                            wt[j * MD_S + i] = __ldg(W + (size_t)j * MD_W + i);
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) dh[a][b] = P.use_res ? da[a][b] : 0.0;
+                        gemm_tile_acc(act, wt, MD_W, tx, ty, dh);
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace anqs
 
 using namespace anqs;
@@ -178,6 +279,23 @@ extern "C" int anqs_made_backward_chain(const anqs_made_desc_t *desc, const int6
     const int64_t ntiles = (n + MD_TB - 1) / MD_TB;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count_of_current_device() * 2);
     made_backward_kernel<<<grid, MD_THREADS, MDB_SMEM, (cudaStream_t)stream>>>(*desc, d_idx, n, (const double2 *)d_grad_out, d_save_h,
+                                                                              d_save_p, d_dY, d_da, d_x);
+    ANQS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int anqs_nade_backward_chain(const anqs_nade_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                                        const double *d_save_h, const double *d_save_p, double *d_dY, double *d_da, double *d_x,
+                                        void *stream) {
+    ANQS_REQUIRE(desc, "null network descriptor");
+    ANQS_REQUIRE(desc->width == MD_W && desc->max_qudit_dim <= 64 && desc->depth >= 1 && desc->depth <= 4 && desc->ptrs, "unsupported network shape");
+    ANQS_REQUIRE(n >= 0, "negative sample count");
+    if (n == 0) return 0;
+    ANQS_REQUIRE(d_idx && d_grad_out && d_save_h && d_save_p && d_dY && d_da && d_x, "null pointer");
+    ANQS_CUDA(cudaFuncSetAttribute(nade_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MDB_SMEM));
+    const int64_t ntiles = (n + MD_TB - 1) / MD_TB;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count_of_current_device() * 2);
+    nade_backward_kernel<<<grid, MD_THREADS, MDB_SMEM, (cudaStream_t)stream>>>(*desc, d_idx, n, (const double2 *)d_grad_out, d_save_h,
                                                                               d_save_p, d_dY, d_da, d_x);
     ANQS_LAUNCH_CHECK();
     return 0;

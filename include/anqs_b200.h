@@ -211,6 +211,11 @@ int anqs_nade_log_psi(const anqs_nade_desc_t *desc, const int64_t *d_idx, int64_
                       double *d_save_p, void *stream);
 int anqs_nade_cond_log_abs(const anqs_nade_desc_t *desc, int qudit_idx, const int64_t *d_prefix, int64_t n, double *d_cond,
                            void *stream);
+/* Backward chain of anqs_nade_log_psi, as anqs_made_backward_chain but per (sub-network, qudit) MLP:
+ * d_dY[2][n][qudit_num * max_qudit_dim] (entries beyond the qudit's own outcomes are zero), d_da[2][qudit_num][depth][n][width],
+ * d_x[n][qubit_num]; d_save_h / d_save_p as anqs_nade_log_psi saved them. */
+int anqs_nade_backward_chain(const anqs_nade_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                             const double *d_save_h, const double *d_save_p, double *d_dY, double *d_da, double *d_x, void *stream);
 
 /* ---- A9  kernel 3, tensor-core mode: the same two functions with every GEMM on tcgen05 (kind::tf32, fp32 accumulate in
  * TMEM) and fp32 epilogue math.  Inference only (no activations are saved); agreement with the fp64 entry points above
