@@ -303,11 +303,14 @@ gumbel_select_kernel(const int64_t *__restrict__ sorted_idx, const double *__res
         const double g = sorted_gumbel[r];
         const int64_t parent = flat >> k;
         const int outcome = (int)(flat & (D - 1));
+        const bool alive = g > -INFINITY;
         out_prefix[r] = prefix[parent] | ((int64_t)outcome << qudit_start);
-        out_memo[r] = next_memo_q[(int64_t)memo_idx[parent] * D + outcome];
-        out_log_prob[r] = level_log_prob[flat];
+        // dead rows (masked children, children of dead rows) may be carried to the next level: they get no memo index, which
+        // masks all of their own children
+        out_memo[r] = alive ? next_memo_q[(int64_t)memo_idx[parent] * D + outcome] : -1;
+        out_log_prob[r] = alive ? level_log_prob[flat] : -INFINITY;
         out_gumbel[r] = g;
-        alive_here += g > -INFINITY ? 1 : 0;
+        alive_here += alive ? 1 : 0;
     }
     alive_here = __reduce_add_sync(0xffffffffu, alive_here);
     if ((threadIdx.x & 31) == 0 && alive_here) atomicAdd(n_alive, alive_here);

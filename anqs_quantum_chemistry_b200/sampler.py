@@ -116,10 +116,16 @@ class AutoregressiveSamplerMixin:
         return prefix.view(-1, 1), counts.to(BASE_COMPLEX_TYPE)
 
     @pt.no_grad()
-    def sample_indices_gumbel(self, sample_num: int, seed: int = None, uniforms=None):
+    def sample_indices_gumbel(self, sample_num: int, seed: int = None, uniforms=None, compact_levels: bool = None):
         """ANQS:778-818: stochastic-beam (Gumbel top-k) sampling without replacement.  Returns (indices [N,1],
         freqs [N] = model probabilities renormalised over the kept set).  `uniforms`, if given, is a callable
-        (level, B, D) -> [B, D] float64 tensor of U(0,1) variates (parity tests)."""
+        (level, B, D) -> [B, D] float64 tensor of U(0,1) variates (parity tests).
+        compact_levels: drop the masked children after every level like the reference does (one host read per level) instead
+        of carrying them on as dead rows and dropping them once at the end.  Both give the same samples - the counter-based
+        draws are keyed by the row index, and the alive rows keep theirs - so the default compacts only when `uniforms` are
+        injected, whose shapes follow the reference's compacted levels."""
+        if compact_levels is None:
+            compact_levels = uniforms is not None
         dev = _lib.require_cuda(self.device)
         lib, sp = _lib.lib(), _lib.stream_ptr(dev)
         qg = self.qubit_grouping
@@ -151,8 +157,16 @@ class AutoregressiveSamplerMixin:
             _lib.check(lib.anqs_sampler_gumbel_select(_lib.dptr(top_i), _lib.dptr(top_g), keep, k, qg.qudit_starts[q], _lib.dptr(prefix),
                                                       _lib.dptr(memo), _lib.dptr(next_q), _lib.dptr(out_lp), _lib.dptr(new_prefix),
                                                       _lib.dptr(new_memo), _lib.dptr(new_lp), _lib.dptr(new_g), _lib.dptr(n_alive), sp))
-            alive = int(n_alive.item())  # the next level's size has to come back to the host
-            prefix, memo, log_prob, gumbel = new_prefix[:alive], new_memo[:alive], new_lp[:alive], new_g[:alive]
+            if compact_levels:
+                alive = int(n_alive.item())
+                prefix, memo, log_prob, gumbel = new_prefix[:alive], new_memo[:alive], new_lp[:alive], new_g[:alive]
+            else:
+                # no host read here: masked children are carried on as dead rows (they sort last at every level and mask all
+                # of their own children) and dropped once after the last level
+                prefix, memo, log_prob, gumbel = new_prefix, new_memo, new_lp, new_g
+        if not compact_levels:
+            alive = int(n_alive.item())
+            prefix, log_prob = prefix[:alive], log_prob[:alive]
         log_prob = log_prob - pt.logsumexp(log_prob, dim=0)
         return prefix.view(-1, 1), pt.exp(log_prob)
 

@@ -295,7 +295,8 @@ int anqs_sampler_gumbel_level(const double *d_cond, int max_qudit_dim, int qubit
  * Rows r < keep become the nodes of the next level: d_out_prefix[r] = d_prefix[parent] | outcome << qudit_start,
  * d_out_memo_idx[r] = d_next_memo_q[memo_idx[parent] * D + outcome], d_out_log_prob[r] = d_level_log_prob[flat],
  * d_out_gumbel[r] = d_sorted_gumbel[r].  Masked children carry -inf and sort last; *d_n_alive (device int32) = number of
- * rows in front of them, the caller keeps [0, *d_n_alive). */
+ * rows in front of them.  The caller may keep [0, *d_n_alive) or carry all `keep` rows on: dead rows come out with memo
+ * index -1 and log-probability -inf, so every level below masks them again (one host read at the end instead of one per level). */
 int anqs_sampler_gumbel_select(const int64_t *d_sorted_idx, const double *d_sorted_gumbel, int64_t keep, int qubits_in_qudit,
                                int qudit_start, const int64_t *d_prefix, const int32_t *d_memo_idx, const int32_t *d_next_memo_q,
                                const double *d_level_log_prob, int64_t *d_out_prefix, int32_t *d_out_memo_idx,
