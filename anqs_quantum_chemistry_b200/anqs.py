@@ -285,6 +285,8 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
             self.phase_subnet = per_qudit(aux)
         self._ptr_table = None
         self._ptr_key = None
+        self._desc_cache = None        # (parameter pointers, descriptor): rebuilt only when a parameter is re-allocated
+        self._param_list = None
         self.to(self.device)
         self._param_num = None
         self._masked_key = None        # parameter versions right after the MADE masks were last applied
@@ -307,11 +309,22 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         assert precision == 'fp64' or self.de_mode == 'MADE', 'the tensor-core kernels implement MADE mode'
         self.inference_precision = precision
 
+    def _params(self):
+        """The parameters as a plain list: nn.Module.parameters() walks the module tree on every call (~70 us here), and this is
+        asked for on every kernel launch."""
+        if self._param_list is None:
+            self._param_list = list(self.parameters())
+        return self._param_list
+
     def _param_key(self):
-        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+        return tuple((p._version, p.data_ptr()) for p in self._params())
 
     def _nade_descriptor(self) -> _lib.NadeDesc:
         dev = _lib.require_cuda(self.device)
+        # the descriptor holds device POINTERS: it stays valid while no parameter is re-allocated (in-place updates keep them)
+        ptr_key = tuple(p.data_ptr() for p in self._params())
+        if self._desc_cache is not None and self._desc_cache[0] == ptr_key:
+            return self._desc_cache[1]
         d = _lib.NadeDesc()
         qg = self.qubit_grouping
         d.qubit_num, d.qudit_num, d.max_qudit_dim = self.qubit_num, qg.qudit_num, self.max_qudit_dim
@@ -340,6 +353,7 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         d.cont_mask = qg.cont_mask_words.data_ptr()
         d.memo_size = self.masker.memo_size
         d._keep = keep
+        self._desc_cache = (ptr_key, d)
         return d
 
     def _descriptor(self):
@@ -351,6 +365,9 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
             self.log_abs_subnet.apply_made_masks_()
             self.phase_subnet.apply_made_masks_()
             self._masked_key = self._param_key()
+        ptr_key = tuple(k[1] for k in self._masked_key)
+        if self._desc_cache is not None and self._desc_cache[0] == ptr_key:
+            return self._desc_cache[1]  # pointers unchanged: the descriptor built earlier is still right
         d = _lib.MadeDesc()
         qg = self.qubit_grouping
         d.qubit_num, d.qudit_num, d.max_qudit_dim = self.qubit_num, qg.qudit_num, self.max_qudit_dim
@@ -374,6 +391,7 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         d.cont_mask = qg.cont_mask_words.data_ptr()
         d.memo_size = self.masker.memo_size
         d._keep = keep
+        self._desc_cache = (ptr_key, d)
         return d
 
     def _launch_log_psi(self, idx: pt.Tensor, save: bool):
@@ -427,10 +445,10 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
     def log_psi_of_indices(self, base_idx: pt.Tensor) -> pt.Tensor:
         idx = base_idx.contiguous().view(-1)
         if self.de_mode == 'NADE':
-            return _NadeLogPsi.apply(self, idx, *list(self.parameters()))
+            return _NadeLogPsi.apply(self, idx, *self._params())
         if self.inference_precision == 'tf32' and not pt.is_grad_enabled():
             return self.log_psi_tc(idx)
-        return _MadeLogPsi.apply(self, idx, *list(self.parameters()))
+        return _MadeLogPsi.apply(self, idx, *self._params())
 
     def log_psi(self, base_vec: pt.Tensor, just_return: bool = False) -> pt.Tensor:
         """ANQS:407-481 (argument is the unpacked bit matrix, as in the reference)."""
