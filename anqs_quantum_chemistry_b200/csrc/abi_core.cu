@@ -124,7 +124,7 @@ __global__ void scan_apply(const int64_t *__restrict__ in, int64_t n, const int6
 
 
 // ---- product layout of the XY masks (Tables::prod_*, consumed by k1_fused.cu) --------------------------------
-constexpr uint32_t PROD_TILE_MAX = 200 * 1024;  // bytes of shared memory one tile may take
+constexpr uint32_t PROD_TILE_MAX = 150 * 1024;  // bytes of shared memory one tile may take (the bit-sliced fused kernel keeps 75 KB of per-group state beside it)
 constexpr uint32_t PROD_ROW_CHUNK = 2048;       // longer rows are split so that tiles pack evenly
 constexpr uint32_t PROD_SINGLE_MAX = 2;         // rows with <= this many members become singleton records
 

@@ -308,7 +308,7 @@ def test_tiled_enumeration_equals_untiled(qubits, electrons, irreps, rows, compl
 @pytest.mark.parametrize('qubits,electrons,irreps,rows,complex_w,off_sector,clustered', [
     (12, 4, 1, 200, False, False, False), (20, 14, 1, 3000, False, False, False), (20, 14, 1, 5000, False, False, True),
     (20, 14, 1, 500, True, False, False), (20, 14, 1, 1000, False, True, False), (36, 12, 8, 1500, False, False, False),
-    (56, 14, 8, 3000, False, False, True), (56, 14, 8, 40000, False, False, False)])
+    (56, 14, 8, 3000, False, False, True), (56, 14, 8, 40000, False, False, False), (36, 12, 1, 1200, False, False, False)])
 def test_bit_sliced_local_energy_equals_per_sample_kernel(qubits, electrons, irreps, rows, complex_w, off_sector, clustered, tmp_path):
     """The two fused sample-aware kernels (a warp per group of 32 samples with bit-sliced electron-count tests, k1_fused_bs.cu;
     a warp per sample, k1_fused.cu) and the CPU oracle give the same local energies to 1e-10, also for complex weights, for
