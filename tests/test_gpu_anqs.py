@@ -333,3 +333,22 @@ def test_gumbel_dead_rows_equal_compaction(n, ne, num):
     assert torch.equal(a_idx, b_idx) and torch.equal(a_f, b_f)
     assert a_idx.shape[0] == min(num, a_idx.shape[0]) and abs(float(a_f.sum()) - 1.0) < 1e-12
     assert torch.unique(a_idx).shape[0] == a_idx.shape[0]
+
+
+def test_count_splitting_at_full_size():
+    """BASELINE config 4's size (36 qubits, 12 electrons, 1e7 samples): the counts add up to the number of samples drawn, every
+    configuration is physical ((N, S_z) sector) and occurs once, the call is reproducible, and the sub-tree sharded sampler
+    (emulated ranks) returns the same set."""
+    from anqs_quantum_chemistry_b200 import dist as adist
+    n, ne, num = 36, 12, 10 ** 7
+    hs, masker, wf = build(n, ne)
+    idx, cnt = wf.sample_stats(num, seed=5)
+    assert float(cnt.real.sum()) == float(num) and float(cnt.imag.abs().max()) == 0.0 and float(cnt.real.min()) >= 1.0
+    flat = idx.view(-1)
+    even = torch.tensor(0x5555555555555555, dtype=torch.int64, device=DEV)
+    assert bool((hs.popcount(flat & even) == ne // 2).all()) and bool((hs.popcount(flat & ~even) == ne // 2).all())
+    assert torch.unique(flat).shape[0] == flat.shape[0] > 10 ** 6
+    idx2, cnt2 = wf.sample_stats(num, seed=5)
+    assert torch.equal(idx, idx2) and torch.equal(cnt, cnt2)
+    parts = [adist.sharded_sample_stats(wf, num, seed=5, world_size=4, rank=r, gather=False) for r in range(4)]
+    assert torch.equal(torch.cat([p[0] for p in parts]), idx) and torch.equal(torch.cat([p[1] for p in parts]), cnt)

@@ -371,3 +371,70 @@ def test_full_local_energy_on_a_fresh_observable(tmp_path):
     pos = np.searchsorted(sector, sub)
     assert np.abs(full.cpu().numpy() - e_all[pos]).max() < 1e-10 * max(1.0, np.abs(e_all).max())
     assert metrics.non_sampled_unq_x_primes_num > 0
+
+
+def test_full_size_properties(tmp_path):
+    """BASELINE.json's full size (C5: 56 qubits, T = 114 305, 2^20 unique samples), where no CPU oracle finishes: properties that
+    do not depend on the size.  Local energies: scale invariance E_loc[c psi] = E_loc[psi], hermiticity of the restricted
+    Hamiltonian (sum conj(psi) H psi real), a row window equals the slice of the whole, the two fused kernels agree.
+    Enumeration (65 536 rows, 2.5e8 connections): every x' has the sector's electron counts, x' ^ x[dest] is exactly the mask
+    xy_ptr names, xy_ptr rises strictly inside every sample, counts / offsets are consistent, and the three filters agree."""
+    from anqs_quantum_chemistry_b200 import _lib
+    n, na, nb = 56, 7, 7
+    xy, yz, w = synthetic.synthetic_hamiltonian(n, n_irreps=8, seed=0)
+    samples = synthetic.random_physical_samples(n, na, nb, 1 << 20, seed=1)
+    amps = synthetic.random_amplitudes(samples.shape[0], seed=2)
+    hs = HilbertSpace(qubit_num=n, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, n))
+    assert ham.term_num == 114305 and ham.unq_xy_masks_num == 23157
+    s, a = _dev(samples.view(np.int64)).view(-1, 1), _dev(amps)
+    assert s.shape[0] == 1 << 20
+
+    def eloc(amps_t, **kw):
+        return ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=amps_t, coupling_method='ham',
+                                                  alpha_num=na, beta_num=nb, **kw)[0]
+
+    e = eloc(a)
+    scale = float(e.abs().max())
+    assert torch.isfinite(torch.view_as_real(e)).all()
+    # homogeneous of degree zero in psi
+    e_c = eloc(a * (0.37 - 1.2j))
+    assert float((e_c - e).abs().max()) < 1e-11 * max(1.0, scale)
+    # <psi|H|psi> restricted to the sampled set is real
+    hpsi = (a.conj() * (e * a)).sum()
+    assert abs(float(hpsi.imag)) < 1e-9 * max(1.0, abs(float(hpsi.real)))
+    # a row window is the slice of the whole (same table)
+    table = SampleTable(s.view(-1), a)
+    lo, ln = 123457, 300001
+    e_win = eloc(a, table=table, row_start=lo, row_len=ln)
+    assert torch.equal(e_win, e[lo:lo + ln])
+    # the warp-per-sample kernel agrees with the bit-sliced one at this size
+    try:
+        _lib.lib().anqs_local_energy_force_per_sample_kernel(1)
+        e_ps = eloc(a, table=table)
+    finally:
+        _lib.lib().anqs_local_energy_force_per_sample_kernel(0)
+    assert float((e_ps - e).abs().max()) < 1e-11 * max(1.0, scale)
+    del e_c, e_win, e_ps, table
+
+    rows = s.view(-1)[: 1 << 16].contiguous()
+    conn = ham.connected_configurations(rows, na, nb, matrix_elements='real')
+    m = conn['xprime'].shape[0]
+    assert m == int(conn['counts'].sum()) == int(conn['offsets'][-1]) and m > 2.4e8
+    assert torch.equal(conn['offsets'][1:] - conn['offsets'][:-1], conn['counts'])
+    xp, dest, ptr = conn['xprime'], conn['dest'].long(), conn['xy_ptr'].long()
+    even = torch.tensor(0x5555555555555555, dtype=torch.int64, device=DEV)
+    assert bool((hs.popcount(xp & even) == na).all()) and bool((hs.popcount(xp & ~even) == nb).all())
+    assert torch.equal(xp ^ rows[dest], ham.unq_xy_masks.to(DEV).view(-1)[ptr])
+    same = dest[1:] == dest[:-1]
+    assert bool((dest[1:] >= dest[:-1]).all()) and bool((ptr[1:][same] > ptr[:-1][same]).all())
+    assert torch.isfinite(conn['H']).all()
+    counts_ref = conn['counts'].clone()
+    del conn, xp, dest, ptr, same
+    for tiled, force in ((True, 1), (False, 0)):   # product-layout filter, flat popcount filter
+        _lib.lib().anqs_k1_enum_force_product_filter(force)
+        try:
+            other = ham.connected_configurations(rows[:8192], na, nb, with_dest=False, with_xy_ptr=False, tiled=tiled)
+        finally:
+            _lib.lib().anqs_k1_enum_force_product_filter(0)
+        assert torch.equal(other['counts'], counts_ref[:8192])
