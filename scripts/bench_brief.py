@@ -1,3 +1,4 @@
+"""One-line summary of a bench.py log (value, e2e, ms/step, kernel share, roofline fraction)."""
 import json, sys
 for line in open(sys.argv[1]):
     if line.startswith('{'):

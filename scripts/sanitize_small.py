@@ -1,5 +1,5 @@
-"""Small invocations of every new kernel (tiled enumeration with both filters, bit-sliced and per-sample fused local energy,
-Gumbel select) for compute-sanitizer --tool memcheck."""
+"""Small invocations of the round-1 kernels (tiled enumeration with both filters, bit-sliced and per-sample fused local energy,
+Gumbel select) on awkward sizes - meant for `compute-sanitizer --tool memcheck` (closed on this pool, so it only ran plain)."""
 import sys, os, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
