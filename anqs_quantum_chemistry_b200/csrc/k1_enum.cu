@@ -172,13 +172,17 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t w) {
 
 __global__ void __launch_bounds__(BS_THREADS, 2)
 enum_filter_bitsliced_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int alpha, int beta,
-                             int64_t *__restrict__ counts, uint32_t *__restrict__ bitmap, int32_t *__restrict__ tile_prefix) {
+                             int64_t *__restrict__ counts, uint32_t *__restrict__ bitmap, int32_t *__restrict__ tile_prefix,
+                             int chunk_words) {
+    // The bitmap rows of the 32 samples are built chunk_words words at a time in shared memory (one chunk when the whole row
+    // fits, as for every BASELINE table; tables with very many masks take several).
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t X[66];
     __shared__ uint64_t s_x[32];
     __shared__ uint32_t s_bad, s_valid;
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int row_words = (int)t.row_words, stride = row_words | 1;  // odd stride: the 32 rows of a column hit 32 banks
+    const int row_words = (int)t.row_words, stride = chunk_words | 1;  // odd stride: the 32 rows of a column hit 32 banks
+    const int n_tiles = t.n_enum_tiles;
     uint32_t *rows = reinterpret_cast<uint32_t *>(smem_raw);
     const int64_t ngroups = (n + 31) >> 5;
     for (int64_t group = blockIdx.x; group < ngroups; group += gridDim.x) {
@@ -207,54 +211,82 @@ enum_filter_bitsliced_kernel(Tables t, const int64_t *__restrict__ samples, int6
             }
         }
         __syncthreads();
-        for (int j0 = warp; j0 < row_words; j0 += BS_WARPS * 4) {
-            uint2 pos[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = j0 + k * BS_WARPS;
-                pos[k] = j < row_words ? __ldg(t.bs_pos + (size_t)j * 32 + lane) : make_uint2(0x40404040u, 0x40404040u);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = j0 + k * BS_WARPS;
-                if (j >= row_words) break;
-                const uint32_t fa = exactly_two(X[pos[k].x & 0xff], X[(pos[k].x >> 8) & 0xff], X[(pos[k].x >> 16) & 0xff], X[pos[k].x >> 24]);
-                const uint32_t fb = exactly_two(X[pos[k].y & 0xff], X[(pos[k].y >> 8) & 0xff], X[(pos[k].y >> 16) & 0xff], X[pos[k].y >> 24]);
-                rows[lane * stride + j] = transpose32(fa & fb);
-            }
-        }
-        __syncthreads();
         const uint32_t bad = s_bad, valid = s_valid;
-        if (bad) {  // plain popcount test for the samples outside the sector (whole warp per sample)
-            for (int sidx = warp; sidx < 32; sidx += BS_WARPS) {
-                if (!((bad >> sidx) & 1u)) continue;
-                const uint64_t x = s_x[sidx];
-                const uint32_t xa = compress_even_bits(x), xb = compress_even_bits(x >> 1);
-                for (int j = 0; j < row_words; ++j) {
-                    const uint2 m = __ldg(t.mab + (size_t)j * 32 + lane);
-                    const bool p = (int64_t)j * 32 + lane < t.U && __popc(xa ^ m.x) == alpha && __popc(xb ^ m.y) == beta;
-                    const uint32_t b = __ballot_sync(0xffffffffu, p);
-                    if (lane == 0) rows[sidx * stride + j] = b;
+        int e_first = 0;  // first enumeration tile that reaches into the current chunk
+        for (int c0 = 0; c0 < row_words; c0 += chunk_words) {
+            const int c1 = min(c0 + chunk_words, row_words);
+            for (int j0 = c0 + warp; j0 < c1; j0 += BS_WARPS * 4) {
+                uint2 pos[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = j0 + k * BS_WARPS;
+                    pos[k] = j < c1 ? __ldg(t.bs_pos + (size_t)j * 32 + lane) : make_uint2(0x40404040u, 0x40404040u);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = j0 + k * BS_WARPS;
+                    if (j >= c1) break;
+                    const uint32_t fa = exactly_two(X[pos[k].x & 0xff], X[(pos[k].x >> 8) & 0xff], X[(pos[k].x >> 16) & 0xff], X[pos[k].x >> 24]);
+                    const uint32_t fb = exactly_two(X[pos[k].y & 0xff], X[(pos[k].y >> 8) & 0xff], X[(pos[k].y >> 16) & 0xff], X[pos[k].y >> 24]);
+                    rows[lane * stride + (j - c0)] = transpose32(fa & fb);
                 }
             }
             __syncthreads();
+            if (bad) {  // plain popcount test for the samples outside the sector (whole warp per sample)
+                for (int sidx = warp; sidx < 32; sidx += BS_WARPS) {
+                    if (!((bad >> sidx) & 1u)) continue;
+                    const uint64_t x = s_x[sidx];
+                    const uint32_t xa = compress_even_bits(x), xb = compress_even_bits(x >> 1);
+                    for (int j = c0; j < c1; ++j) {
+                        const uint2 m = __ldg(t.mab + (size_t)j * 32 + lane);
+                        const bool p = (int64_t)j * 32 + lane < t.U && __popc(xa ^ m.x) == alpha && __popc(xb ^ m.y) == beta;
+                        const uint32_t b = __ballot_sync(0xffffffffu, p);
+                        if (lane == 0) rows[sidx * stride + (j - c0)] = b;
+                    }
+                }
+                __syncthreads();
+            }
+            while (e_first < n_tiles && (int)(__ldg(&t.enum_tiles[e_first].word0) + __ldg(&t.enum_tiles[e_first].n_words)) <= c0) ++e_first;
+            for (int sidx = warp; sidx < 32; sidx += BS_WARPS) {
+                if (!((valid >> sidx) & 1u)) continue;
+                const int64_t r = group * 32 + sidx;
+                const uint32_t *bm = rows + sidx * stride - c0;  // bm[j] = word j of the row, c0 <= j < c1
+                // connections of every enumeration tile that overlaps this chunk (raw counts for now, scanned below)
+                for (int e = e_first; e < n_tiles; ++e) {
+                    const int w0 = (int)__ldg(&t.enum_tiles[e].word0), w1 = w0 + (int)__ldg(&t.enum_tiles[e].n_words);
+                    if (w0 >= c1) break;
+                    int c = 0;
+                    for (int j = max(w0, c0) + lane; j < min(w1, c1); j += 32) c += __popc(bm[j]);
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (lane == 0) {
+                        int32_t *slot = tile_prefix + r * n_tiles + e;
+                        *slot = w0 >= c0 ? c : *slot + c;  // a tile that started in an earlier chunk already has a partial count
+                    }
+                }
+                uint32_t *row = bitmap + r * t.row_words;
+                for (int j = c0 + lane; j < c1; j += 32) row[j] = bm[j];
+            }
+            __syncthreads();
         }
+        // per-tile counts -> rank of every tile's first connection inside the sample (exclusive scan), total -> counts
         for (int sidx = warp; sidx < 32; sidx += BS_WARPS) {
             if (!((valid >> sidx) & 1u)) continue;
             const int64_t r = group * 32 + sidx;
-            const uint32_t *bm = rows + sidx * stride;
-            int total = 0;
-            for (int e = 0; e < t.n_enum_tiles; ++e) {
-                const int w0 = (int)__ldg(&t.enum_tiles[e].word0), nw = (int)__ldg(&t.enum_tiles[e].n_words);
-                int c = 0;
-                for (int j = w0 + lane; j < w0 + nw; j += 32) c += __popc(bm[j]);
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (lane == 0) tile_prefix[r * t.n_enum_tiles + e] = total;
-                total += c;
+            int32_t *tp = tile_prefix + r * n_tiles;
+            int carry = 0;
+            for (int e0 = 0; e0 < n_tiles; e0 += 32) {
+                const int e = e0 + lane;
+                const int v = e < n_tiles ? tp[e] : 0;
+                int inc = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                if (e < n_tiles) tp[e] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
             }
-            if (lane == 0) counts[r] = total;
-            uint32_t *row = bitmap + r * t.row_words;
-            for (int j = lane; j < row_words; j += 32) row[j] = bm[j];
+            if (lane == 0) counts[r] = carry;
         }
         __syncthreads();
     }
@@ -470,8 +502,14 @@ static int filter_warps(const Tables *t) {
     return (int)(w & ~3ll);
 }
 
-static size_t bitsliced_smem(const Tables *t) { return (size_t)32 * (size_t)(t->row_words | 1) * 4; }
-static bool bitsliced_available(const Tables *t) { return t->bs_ok && bitsliced_smem(t) + 1024 <= (size_t)EN_SMEM_MAX; }
+// bitmap words of the 32 samples' rows kept in shared memory at a time: the whole row when it fits beside a second CTA
+constexpr int BS_CHUNK_MAX = 894;  // 32 * 895 * 4 B = 112 KB
+static int bitsliced_chunk(const Tables *t) {
+    const int64_t nchunks = (t->row_words + BS_CHUNK_MAX - 1) / BS_CHUNK_MAX;
+    return (int)((t->row_words + nchunks - 1) / nchunks);
+}
+static size_t bitsliced_smem(const Tables *t) { return (size_t)32 * (size_t)(bitsliced_chunk(t) | 1) * 4; }
+static bool bitsliced_available(const Tables *t) { return t->bs_ok != 0; }
 
 static bool tiled_available(const Tables *t) {
     return t->n_enum_tiles > 0 && (bitsliced_available(t) || filter_warps(t) >= 4) &&
@@ -517,7 +555,7 @@ int anqs_k1_enum_filter(const anqs_tables_t *h, const int64_t *d_samples, int64_
         const int grid = (int)std::min<int64_t>((n + 31) / 32, (int64_t)sm_count_of_current_device() * per_sm);
         int32_t *tile_prefix = reinterpret_cast<int32_t *>((unsigned char *)d_work + counters_bytes(t));
         enum_filter_bitsliced_kernel<<<grid, BS_THREADS, smem, (cudaStream_t)stream>>>(*t, d_samples, n, alpha_num, beta_num, d_counts,
-                                                                                       d_bitmap, tile_prefix);
+                                                                                       d_bitmap, tile_prefix, bitsliced_chunk(t));
         ANQS_LAUNCH_CHECK();
         return 0;
     }

@@ -261,7 +261,8 @@ def test_edge_cases(tmp_path):
 
 @pytest.mark.parametrize('qubits,electrons,irreps,rows,complex_w,off_sector', [
     (12, 4, 1, 200, False, False), (20, 14, 1, 1500, False, False), (20, 14, 1, 400, True, False),
-    (20, 14, 1, 600, False, True), (12, 4, 1, 150, True, True), (36, 12, 8, 700, False, False), (56, 14, 8, 600, False, False)])
+    (20, 14, 1, 600, False, True), (12, 4, 1, 150, True, True), (36, 12, 8, 700, False, False), (56, 14, 8, 600, False, False),
+    (36, 12, 1, 300, False, False), (36, 12, 1, 200, False, True)])   # dense 36 qubits: 933 bitmap words = two filter chunks
 def test_tiled_enumeration_equals_untiled(qubits, electrons, irreps, rows, complex_w, off_sector, tmp_path):
     """The tile-resident kernels (bit-sliced or product-layout filter, pattern-table matrix elements; k1_enum.cu) and the
     untiled pair (k1_connected.cu) emit the same ordered list bit for bit, and matrix elements that agree to 1e-12 —
