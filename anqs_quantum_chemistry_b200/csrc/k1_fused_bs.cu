@@ -22,7 +22,7 @@
 //  * Samples outside the sector (never produced by the symmetry-masked samplers, but legal input) take a plain path: popcount
 //    tests over the flat mask table and a direct slot-table lookup per passing mask.
 //
-// When there are fewer groups than warps on the chip (small batches), R = 2^k warps share one group and split its row steps.
+// When there are fewer groups than warps on the chip (small batches), R warps share one group and split its row steps.
 #include <algorithm>
 
 #include "common.cuh"
@@ -32,7 +32,6 @@ namespace anqs {
 
 constexpr int FB_THREADS = 1024;
 constexpr int FB_WARPS = FB_THREADS / 32;
-static_assert(FB_WARPS % 8 == 0, "R (warps per group, <= 8) must divide the warp count");
 constexpr int FB_QCAP = 64;                            // queued filter positives per warp
 constexpr int FB_QUEUE_BYTES = FB_WARPS * FB_QCAP * 16;  // uint4 {ka, kb, uref, sample}
 constexpr uint32_t FB_UREF_ROW = 0x80000000u;          // uref flag: index into prod_row_u instead of prod_mem_u
@@ -145,10 +144,12 @@ __device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView 
     const uint4 *rows = reinterpret_cast<const uint4 *>(smem_tile);
     const uint2 *mems = reinterpret_cast<const uint2 *>(smem_tile + (size_t)(tile.n_multi + tile.n_single) * sizeof(RowRec));
     // ---- multi-member rows: alpha factor per row, beta factor per member, one probe step per (row step, passing sample) ----
-    for (uint32_t r = 0; r < tile.n_multi; ++r) {
+    // warp k of the group takes the steps j of row r with (r + j) % R == k; jrot = (k - r) mod R, kept without divisions
+    uint32_t jrot = (uint32_t)k;
+    for (uint32_t r = 0; r < tile.n_multi; ++r, jrot = jrot ? jrot - 1u : (uint32_t)R - 1u) {
         const uint4 rec = rows[r];  // {alpha positions, line hash of the alpha part, first member, member count}
         const uint32_t nsteps = (rec.w + 63u) >> 6;
-        uint32_t j = (uint32_t)(k - (int)r) & (uint32_t)(R - 1);
+        uint32_t j = jrot;
         if (j >= nsteps) continue;
         const uint32_t fa = fb_exactly_two(sl.Xa, rec.x) & valid;
         if (!fa) continue;
@@ -269,10 +270,13 @@ __device__ __forceinline__ void fb_slow_sample(const Tables &t, const HashView &
     ei = si;
 }
 
-template <bool REAL>
+// SPLIT = false: every warp owns a group (S = FB_WARPS, R = 1 at compile time: the shape of large batches, kept free of the
+// bookkeeping of the general case); SPLIT = true: S groups per CTA iteration, R warps per group, both run-time.
+template <bool REAL, bool SPLIT>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples, const double2 *__restrict__ amps,
-                     int64_t row_start, int64_t row_len, int alpha, int beta, double2 *__restrict__ eloc, int R) {
+                     int64_t row_start, int64_t row_len, int alpha, int beta, double2 *__restrict__ eloc, int S_arg, int R_arg) {
+    const int S = SPLIT ? S_arg : FB_WARPS, R = SPLIT ? R_arg : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ ProdTile s_tile;
@@ -281,7 +285,9 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
     unsigned char *tile_buf = smem_raw + FB_WARPS * sizeof(FbSlot) + FB_QUEUE_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int S = FB_WARPS / R, slot = warp / R, k = warp & (R - 1);
+    // S groups per CTA iteration, R warps per group (S * R <= FB_WARPS; the warps left over only take part in the barriers)
+    const bool live = SPLIT ? warp < S * R : true;
+    const int slot = SPLIT ? (live ? warp / R : 0) : warp, k = SPLIT ? warp - (warp / R) * R : 0;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -301,9 +307,9 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
     const int64_t per_iter = (int64_t)gridDim.x * S;
     for (int64_t g0 = (int64_t)blockIdx.x * S; g0 < ngroups; g0 += per_iter) {
         const int64_t g = g0 + slot;
-        const bool have = g < ngroups;
+        const bool have = live && g < ngroups;
         __syncthreads();  // the previous groups are finished with the slots
-        if (k == 0) {
+        if (k == 0 && live) {
             const int64_t r = g * 32 + lane;
             const bool ok = have && r < row_len;
             const uint64_t x = ok ? (uint64_t)samples[row_start + r] : 0ull;
@@ -355,7 +361,7 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
                 loaded = true;
             }
             const ProdTile tile = s_tile;
-            if (sl.valid) fb_process_tile<REAL>(t, hv, w, tile, tile_buf, k, R);
+            if (have && sl.valid) fb_process_tile<REAL>(t, hv, w, tile, tile_buf, k, R);
         }
         __syncwarp();
         if (w.qlen > 0) {
@@ -401,9 +407,9 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
     const int64_t ngroups = (row_len + 31) / 32;
     // small batches leave most SMs without a group: the warp-per-sample kernel spreads them better
     if (g_fused_choice == 0 && ngroups < (int64_t)sms * 8) return 0;
-    int R = 1;
-    while (R < 8 && ngroups * (R * 2) <= (int64_t)sms * FB_WARPS) R *= 2;  // R divides FB_WARPS
-    const int S = FB_WARPS / R;
+    // S groups per CTA iteration, R = FB_WARPS / S warps per group: as few groups per CTA as spreads them over all the SMs
+    const int S = (int)std::min<int64_t>(FB_WARPS, (ngroups + sms - 1) / sms);
+    const int R = FB_WARPS / S;
     const int grid = (int)std::min<int64_t>((ngroups + S - 1) / S, sms);
     cudaError_t e;
     // Presence filters beyond ~24 MB fall out of L2 under their own single-sector random traffic (profiles/README.md):
@@ -428,19 +434,12 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
         }
         cudaGetLastError();  // refusals are not errors of this call
     }
-    if (t->weights_real) {
-        auto kern = fused_eloc_bs_kernel<true>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return -1;
-        kern<<<grid, FB_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num, beta_num,
-                                            (double2 *)d_eloc, R);
-    } else {
-        auto kern = fused_eloc_bs_kernel<false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return -1;
-        kern<<<grid, FB_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num, beta_num,
-                                            (double2 *)d_eloc, R);
-    }
+    auto kern = t->weights_real ? (S == FB_WARPS ? fused_eloc_bs_kernel<true, false> : fused_eloc_bs_kernel<true, true>)
+                                : (S == FB_WARPS ? fused_eloc_bs_kernel<false, false> : fused_eloc_bs_kernel<false, true>);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1;
+    kern<<<grid, FB_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num, beta_num,
+                                        (double2 *)d_eloc, S, R);
     if (window) {  // the window applies to the launches issued while it is set: clear it again
         cudaStreamAttrValue attr = {};
         attr.accessPolicyWindow.num_bytes = 0;
