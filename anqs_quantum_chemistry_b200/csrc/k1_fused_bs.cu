@@ -423,7 +423,9 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
         if (max_persist > 0 && max_window > 0) {
             const size_t want = std::min<size_t>(filter_bytes, (size_t)max_persist);
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            static size_t limit_set[64] = {0};  // per device: the set-aside only ever grows, and is not touched again once large enough
+            if (dev >= 0 && dev < 64 && limit_set[dev] < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+                limit_set[dev] = want;
             cudaStreamAttrValue attr = {};
             attr.accessPolicyWindow.base_ptr = const_cast<uint8_t *>(hv.filter);
             attr.accessPolicyWindow.num_bytes = std::min<size_t>(filter_bytes, (size_t)max_window);
