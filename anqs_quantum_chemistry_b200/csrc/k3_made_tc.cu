@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace anqs {
 
@@ -56,11 +57,6 @@ __host__ __device__ inline TcPacked tc_layout(int qubit_num, int qudit_num, int 
     return L;
 }
 
-// byte offset of element (row, k) of an [rows x K] operand in the canonical no-swizzle K-major layout
-__host__ __device__ __forceinline__ uint32_t canon_off(uint32_t row, uint32_t k, uint32_t K) {
-    return (row >> 3) * (K / 4 * 128) + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4;
-}
-
 __global__ void made_tc_pack_kernel(const anqs_made_desc_t P, TcPacked L, unsigned char *out) {
     const int Q = P.qudit_num, DM = P.max_qudit_dim, n = P.qubit_num, depth = P.depth;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -92,57 +88,6 @@ __global__ void made_tc_pack_kernel(const anqs_made_desc_t P, TcPacked L, unsign
     }
 }
 
-// ---- tcgen05 / TMEM primitives ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address, bits [0,14)
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;      // leading-dimension byte offset, bits [16,30)
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;      // stride-dimension byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                                 // descriptor version 1 (sm_100); layout type 0 = no swizzle
-    return d;
-}
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128
-__device__ __forceinline__ constexpr uint32_t idesc_tf32(uint32_t N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
-    uint32_t r[64];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
-          "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
-          "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
-          "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 __device__ __forceinline__ long long tc_floor_div(long long a, long long b) {
     long long q = a / b, r = a % b;
     return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
@@ -159,14 +104,6 @@ __device__ __forceinline__ long long tc_memo_index(const anqs_made_desc_t &P, ui
         idx += tc_floor_div(e * d[3] + d[4], d[5]) * d[6];
     }
     return idx;
-}
-
-// K / 8 tf32 MMAs: D[128 x 64] (+)= A[128 x K] * B[64 x K]^T
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, uint32_t K) {
-    const uint32_t sbo = K / 4 * 128;
-    const uint32_t idesc = idesc_tf32(64);
-    for (uint32_t k = 0; k < K; k += 8)
-        umma_tf32(tmem_d, smem_desc(a_saddr + (k >> 2) * 128, 128, sbo), smem_desc(b_saddr + (k >> 2) * 128, 128, sbo), idesc, k > 0);
 }
 
 // mode 0: log psi of whole configurations; mode 1: normalised conditional log|psi| of qudit level_q for prefixes.

@@ -68,13 +68,45 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
                                                 head_num=self.config.head_num, dtype=self.dtype)
         self.to(self.device)
         self._param_num = None
+        self._param_list = None
+        self._desc_cache = None          # (parameter pointers, descriptor)
+        self._packed_tc = None           # parameters in the tensor cores' operand layout (k5_transformer_tc.cu)
+        self._packed_key = None
+        self.inference_precision = 'fp64'   # 'tf32': no-grad amplitudes and the samplers' conditionals run on tcgen05
         self._init_sampler()
 
     qudit_num = property(lambda self: self.qubit_grouping.qudit_num)
 
+    def set_inference_precision(self, precision: str):
+        """'fp64' (default, parity mode) or 'tf32': no-grad log psi / amplitudes and the conditionals the samplers ask for run
+        through the tensor-core kernels.  Gradients always run in fp64."""
+        assert precision in ('fp64', 'tf32')
+        if precision == 'tf32':
+            assert self.config.head_num in (4, 8, 16), 'the tensor-core mode needs a head dimension <= 16'
+        self.inference_precision = precision
+
+    def _params(self):
+        if self._param_list is None:
+            self._param_list = list(self.parameters())
+        return self._param_list
+
+    def _packed_weights(self, desc):
+        """Parameters packed for the tensor-core kernels; repacked when one of them changed."""
+        key = tuple((p._version, p.data_ptr()) for p in self._params())
+        if self._packed_tc is None or self._packed_key != key:
+            nbytes = int(_lib.lib().anqs_transformer_tc_packed_bytes(ctypes.byref(desc)))
+            if self._packed_tc is None or self._packed_tc.numel() * 8 < nbytes:
+                self._packed_tc = pt.empty((nbytes + 7) // 8, dtype=pt.int64, device=self.device)
+            _lib.check(_lib.lib().anqs_transformer_tc_pack(ctypes.byref(desc), _lib.dptr(self._packed_tc), _lib.stream_ptr(self.device)))
+            self._packed_key = key
+        return self._packed_tc
+
     # ---- kernel plumbing ---------------------------------------------------------------------------------------------------
     def _descriptor(self) -> _lib.TransformerDesc:
         dev = _lib.require_cuda(self.device)
+        ptr_key = tuple(p.data_ptr() for p in self._params())
+        if self._desc_cache is not None and self._desc_cache[0] == ptr_key:
+            return self._desc_cache[1]  # the descriptor holds pointers: valid while no parameter is re-allocated
         net = self.transformer_made
         d = _lib.TransformerDesc()
         d.qubit_num, d.dim, d.depth, d.head_num, d.sym_num = self.qubit_num, net.dim, net.depth, net.head_num, self.masker.sym_num
@@ -104,17 +136,23 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         d.cont_mask = self.qubit_grouping.cont_mask_words.data_ptr()
         d.memo_size = self.masker.memo_size
         d._keep = keep
+        self._desc_cache = (ptr_key, d)
         return d
 
     @pt.no_grad()
-    def log_psi_kernel(self, base_idx: pt.Tensor) -> pt.Tensor:
+    def log_psi_kernel(self, base_idx: pt.Tensor, precision: str = None) -> pt.Tensor:
         dev = _lib.require_cuda(self.device)
         idx = base_idx.contiguous().view(-1)
         B = idx.shape[0]
         out = pt.empty(B, dtype=pt.complex128, device=dev)
         desc = self._descriptor()
-        _lib.check(_lib.lib().anqs_transformer_log_psi(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(out)),
-                                                       _lib.stream_ptr(dev)))
+        if (precision or self.inference_precision) == 'tf32':
+            packed = self._packed_weights(desc)
+            _lib.check(_lib.lib().anqs_transformer_log_psi_tc(ctypes.byref(desc), _lib.dptr(packed), _lib.dptr(idx), B,
+                                                              _lib.dptr(pt.view_as_real(out)), _lib.stream_ptr(dev)))
+        else:
+            _lib.check(_lib.lib().anqs_transformer_log_psi(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(out)),
+                                                           _lib.stream_ptr(dev)))
         return out
 
     def log_psi_torch(self, base_idx: pt.Tensor) -> pt.Tensor:
@@ -163,6 +201,11 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         B = prefix_idx.shape[0]
         out = pt.empty((B, 2), dtype=pt.float64, device=dev)
         desc = self._descriptor()
-        _lib.check(_lib.lib().anqs_transformer_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
-                                                            _lib.stream_ptr(dev)))
+        if self.inference_precision == 'tf32':
+            packed = self._packed_weights(desc)
+            _lib.check(_lib.lib().anqs_transformer_cond_log_abs_tc(ctypes.byref(desc), _lib.dptr(packed), qudit_idx, _lib.dptr(prefix_idx), B,
+                                                                   _lib.dptr(out), _lib.stream_ptr(dev)))
+        else:
+            _lib.check(_lib.lib().anqs_transformer_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
+                                                                _lib.stream_ptr(dev)))
         return out

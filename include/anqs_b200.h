@@ -259,6 +259,18 @@ int anqs_transformer_log_psi(const anqs_transformer_desc_t *desc, const int64_t 
 int anqs_transformer_cond_log_abs(const anqs_transformer_desc_t *desc, int qubit_idx, const int64_t *d_prefix, int64_t n,
                                   double *d_cond, void *stream);
 
+/* Tensor-core mode of the two functions above: every projection on tcgen05 (kind::tf32, fp32 accumulation in TMEM), attention,
+ * LayerNorm and the masked normalisation in fp32.  Inference only; agreement with the fp64 entry points is a stated
+ * tolerance (tests/test_gpu_transformer.py).  The parameters are first packed into the tensor cores' operand layout:
+ * anqs_transformer_tc_pack must be called again whenever one changes.  d_packed: anqs_transformer_tc_packed_bytes(desc)
+ * bytes, 128-byte aligned.  head_num must be 4, 8 or 16. */
+size_t anqs_transformer_tc_packed_bytes(const anqs_transformer_desc_t *desc);
+int anqs_transformer_tc_pack(const anqs_transformer_desc_t *desc, void *d_packed, void *stream);
+int anqs_transformer_log_psi_tc(const anqs_transformer_desc_t *desc, const void *d_packed, const int64_t *d_idx, int64_t n,
+                                double *d_log_psi, void *stream);
+int anqs_transformer_cond_log_abs_tc(const anqs_transformer_desc_t *desc, const void *d_packed, int qubit_idx, const int64_t *d_prefix,
+                                     int64_t n, double *d_cond, void *stream);
+
 /* ---- A11  kernel 4: one level of the count-splitting batch sampler (ANQS:593-662) ----------------------
  * Parents i = 0..n-1 carry a packed prefix, a count (double, exact below 2^53), and a memo index.
  * split:  d_child_counts[i][D] (D = 2^qubits_in_qudit) = exact multinomial split of d_counts[i] with
