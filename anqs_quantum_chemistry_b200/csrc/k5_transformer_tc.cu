@@ -26,7 +26,7 @@ constexpr int TFC_D = 64;
 constexpr uint32_t TFC_MAT = 64 * 64 * 4;             // one packed weight matrix
 constexpr uint32_t TFC_VEC_FLOATS = 640;              // bq bk bv | bo | b1 | b2 | ln1w ln1b ln2w ln2b
 constexpr uint32_t TFC_LAYER_BYTES = 6 * TFC_MAT + TFC_VEC_FLOATS * 4;
-constexpr int TFC_KV_STRIDE = 65;                     // floats per staged K / V row (odd: rows of different samples hit different banks)
+constexpr int TFC_KV_STRIDE = 68;                     // floats per staged K / V row: 16-byte aligned rows for float4 reads, 4-bank skew between rows
 
 struct TfcLayout {
     uint32_t layer[4];     // per layer: [Wq Wk Wv Wo W1 W2][vectors]
@@ -214,15 +214,28 @@ transformer_tc_kernel(const anqs_transformer_desc_t P, const TfcLayout L, const 
 #pragma unroll
                 for (int d = 0; d < HD; ++d) o[d] = 0.f;
                 for (int tp = 0; tp <= t; ++tp) {
-                    const float *kr = Ks + (r0 + tp) * TFC_KV_STRIDE + h * HD, *vr = Vs + (r0 + tp) * TFC_KV_STRIDE + h * HD;
+                    const float4 *kr = reinterpret_cast<const float4 *>(Ks + (r0 + tp) * TFC_KV_STRIDE + h * HD);
+                    const float4 *vr = reinterpret_cast<const float4 *>(Vs + (r0 + tp) * TFC_KV_STRIDE + h * HD);
                     float sc = 0.f;
 #pragma unroll
-                    for (int d = 0; d < HD; ++d) sc = fmaf(q[h * HD + d], kr[d], sc);
+                    for (int d4 = 0; d4 < HD / 4; ++d4) {
+                        const float4 kk = kr[d4];
+                        sc = fmaf(q[h * HD + 4 * d4], kk.x, sc);
+                        sc = fmaf(q[h * HD + 4 * d4 + 1], kk.y, sc);
+                        sc = fmaf(q[h * HD + 4 * d4 + 2], kk.z, sc);
+                        sc = fmaf(q[h * HD + 4 * d4 + 3], kk.w, sc);
+                    }
                     const float m_new = fmaxf(m_run, sc);
                     const float corr = __expf(m_run - m_new), pw = __expf(sc - m_new);
                     den = den * corr + pw;
 #pragma unroll
-                    for (int d = 0; d < HD; ++d) o[d] = o[d] * corr + pw * vr[d];
+                    for (int d4 = 0; d4 < HD / 4; ++d4) {
+                        const float4 vv = vr[d4];
+                        o[4 * d4] = o[4 * d4] * corr + pw * vv.x;
+                        o[4 * d4 + 1] = o[4 * d4 + 1] * corr + pw * vv.y;
+                        o[4 * d4 + 2] = o[4 * d4 + 2] * corr + pw * vv.z;
+                        o[4 * d4 + 3] = o[4 * d4 + 3] * corr + pw * vv.w;
+                    }
                     m_run = m_new;
                 }
                 const float inv = 1.0f / den;

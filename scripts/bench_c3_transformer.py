@@ -28,12 +28,17 @@ def wall(fn, reps=5, warm=2):
 sector = torch.from_numpy(synthetic.random_physical_samples(n, n_el // 2, n_el // 2, 10 ** 6, seed=1).view('int64')).to(dev)
 with torch.no_grad():
     big = sector.repeat(20)[: 1 << 18].contiguous()
-    _, t = wall(lambda: wf.log_psi_kernel(big))
-    out['amplitudes_per_s_kernel_f64'] = big.shape[0] / t
-    (idx, cnt), t = wall(lambda: wf.sample_stats(10 ** 7, seed=1), reps=3, warm=1)
-    out['count_splitting_1e7_samples'] = {'unique': int(idx.shape[0]), 'seconds': t, 'unique_per_s': idx.shape[0] / t}
-    (idx, f), t = wall(lambda: wf.sample_indices_gumbel(10 ** 4), reps=5, warm=2)
-    out['gumbel_1e4'] = {'unique': int(idx.shape[0]), 'seconds': t}
+    for prec in ('fp64', 'tf32'):
+        wf.set_inference_precision(prec)
+        _, t = wall(lambda: wf.log_psi_kernel(big))
+        out[f'amplitudes_per_s_kernel_{prec}'] = big.shape[0] / t
+        (idx, cnt), t = wall(lambda: wf.sample_stats(10 ** 7, seed=1), reps=3, warm=1)
+        out[f'count_splitting_1e7_samples_{prec}'] = {'unique': int(idx.shape[0]), 'seconds': t, 'unique_per_s': idx.shape[0] / t}
+        (idx, f), t = wall(lambda: wf.sample_indices_gumbel(10 ** 4), reps=5, warm=2)
+        out[f'gumbel_1e4_{prec}'] = {'unique': int(idx.shape[0]), 'seconds': t}
+    ref = wf.log_psi_kernel(sector[:5000], precision='fp64'); tc = wf.log_psi_kernel(sector[:5000], precision='tf32')
+    out['tf32_max_abs_err'] = {'log_abs': float((ref.real - tc.real).abs().max()), 'phase': float((ref.imag - tc.imag).abs().max())}
+wf.set_inference_precision('tf32')   # the VMC iteration below samples through the tensor-core conditionals
 opt = torch.optim.Adam(wf.parameters(), lr=1e-3)
 cfg_s, cfg_e = SamplingConfig(sample_indices=True, sample_num=10 ** 4), LocalEnergyCalculationConfig(use_tree_for_candidates='ham')
 energies = []
@@ -50,5 +55,5 @@ def one_iter():
     energies.append(float(est.mean.real))
 _, t = wall(one_iter, reps=20, warm=3)
 out['vmc_iteration'] = {'ms_per_iter': t * 1e3, 'iters_per_s': 1 / t, 'n_unq': 10 ** 4, 'energy_first': energies[0], 'energy_last': energies[-1],
-                        'note': 'forward with gradients runs through the mirrored torch module (library autograd); sampler and E_loc on the hand-written kernels'}
+                        'note': 'sampler on the tcgen05 conditionals, E_loc on the fused kernel; the forward with gradients runs through the mirrored torch module (library autograd)'}
 print(json.dumps(out))

@@ -132,3 +132,48 @@ def test_vmc_iterations_lower_the_energy():
         energies.append(float(est.mean.real))
     assert energies[-1] < energies[0] - 1e-3
     assert abs(float(est.mean.imag)) < 1e-9
+
+
+@pytest.mark.parametrize('n,ne,heads,depth', [(12, 4, 4, 2), (20, 14, 4, 2), (20, 14, 8, 1), (14, 10, 16, 3)])
+def test_tensor_core_mode_within_tolerance(n, ne, heads, depth):
+    """tcgen05 (tf32) inference mode against the fp64 kernel: the same symmetry masks exactly (an unphysical configuration is
+    -inf in both), log|psi| within 2e-2 and the phase within 5e-2 rad (tf32 products carry 10 mantissa bits; measured 3e-3 /
+    7e-3), conditionals within 1e-2, and sampling through it stays physical and normalised."""
+    from anqs_quantum_chemistry_b200 import synthetic
+    hs = HilbertSpace(qubit_num=n, device=DEV, parent_dir=tempfile.mkdtemp(prefix='anqs_tfm_tc_'), rng_seed=0)
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=ne),
+                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    torch.manual_seed(1)
+    wf = TransformerANQS(hilbert_space=hs, masker=masker, config=TransformerANQSConfig(dim=64, depth=depth, head_num=heads))
+    phys = torch.from_numpy(synthetic.random_physical_samples(n, ne // 2, ne // 2, 3000, seed=1).view('int64')).to(DEV)
+    unphys = torch.from_numpy(synthetic.random_physical_samples(n, ne // 2 + 1, ne // 2 - 1, 50, seed=2).view('int64')).to(DEV)
+    idx = torch.cat((phys, unphys))
+    with torch.no_grad():
+        ref = wf.log_psi_kernel(idx, precision='fp64')
+        tc = wf.log_psi_kernel(idx, precision='tf32')
+    fin = torch.isfinite(ref.real)
+    assert torch.equal(fin, torch.isfinite(tc.real)) and int(fin.sum()) == phys.shape[0]
+    assert float((tc.real[fin] - ref.real[fin]).abs().max()) < 2e-2
+    assert float((tc.imag[fin] - ref.imag[fin]).abs().max()) < 5e-2
+    for q in (0, n // 2, n - 1):
+        wf.set_inference_precision('fp64')
+        c0 = wf.cond_log_abs(qudit_idx=q, prefix_idx=phys)
+        wf.set_inference_precision('tf32')
+        c1 = wf.cond_log_abs(qudit_idx=q, prefix_idx=phys)
+        f = torch.isfinite(c0)
+        assert torch.equal(f, torch.isfinite(c1))
+        assert float((c0[f] - c1[f]).abs().max()) < 1e-2
+    # samplers on the tensor-core conditionals
+    s_idx, s_cnt = wf.sample_stats(10 ** 5, seed=3)
+    assert float(s_cnt.real.sum()) == 1e5
+    even = torch.tensor(0x5555555555555555, dtype=torch.int64, device=DEV)
+    assert bool((hs.popcount(s_idx.view(-1) & even) == ne // 2).all()) and bool((hs.popcount(s_idx.view(-1) & ~even) == ne // 2).all())
+    g_idx, g_f = wf.sample_indices_gumbel(min(200, phys.shape[0]))
+    assert abs(float(g_f.sum()) - 1.0) < 1e-12 and torch.unique(g_idx).shape[0] == g_idx.shape[0]
+    # a parameter update is picked up (the packed weights are rebuilt)
+    with torch.no_grad():
+        for p in wf.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+        ref2 = wf.log_psi_kernel(phys, precision='fp64')
+        tc2 = wf.log_psi_kernel(phys, precision='tf32')
+    assert float((tc2.real - ref2.real).abs().max()) < 2e-2 and float((ref2.real - ref.real[fin]).abs().max()) > 1e-3
