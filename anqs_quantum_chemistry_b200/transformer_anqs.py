@@ -25,6 +25,18 @@ from .qubit_grouping import QubitGrouping, QubitGroupingConfig
 from .sampler import AutoregressiveSamplerMixin, ParameterVectorMixin
 
 
+class _ElementwiseLayerNorm(nn.LayerNorm):
+    """nn.LayerNorm with the same parameters and state_dict keys whose forward is written out in elementwise operations:
+    torch's fused fp64 layer_norm kernel takes 1.8 ms per call on a [2e5, 64] input on B200 (RowwiseMomentsCUDAKernel<double>),
+    7 ms of a 30 ms VMC iteration; the arithmetic below is the same function (biased variance, eps inside the square root)."""
+
+    def forward(self, x: pt.Tensor) -> pt.Tensor:
+        mu = x.mean(dim=-1, keepdim=True)
+        xc = x - mu
+        var = (xc * xc).mean(dim=-1, keepdim=True)
+        return xc * pt.rsqrt(var + self.eps) * self.weight + self.bias
+
+
 class TransformerMADE(nn.Module):
     """Token + positional embedding, causal post-norm encoder, linear decoder.  Construction order (and therefore the
     initial weights under a given torch seed) follows transformer_made.py:26-41."""
@@ -37,6 +49,12 @@ class TransformerMADE(nn.Module):
         self.embedding = nn.Embedding(3, dim, dtype=dtype)
         layer = nn.TransformerEncoderLayer(d_model=dim, nhead=head_num, dim_feedforward=dim, dropout=0.0, batch_first=True, dtype=dtype)
         self.transformer = nn.TransformerEncoder(encoder_layer=layer, num_layers=depth, enable_nested_tensor=False)
+        for enc in self.transformer.layers:  # same parameters (names, values, order), elementwise forward
+            for name in ('norm1', 'norm2'):
+                old = getattr(enc, name)
+                new = _ElementwiseLayerNorm(old.normalized_shape, eps=old.eps, dtype=dtype)
+                new.weight, new.bias = old.weight, old.bias
+                setattr(enc, name, new)
         self.decoder = nn.Linear(dim, out_dim, dtype=dtype)
 
     def forward(self, x: pt.Tensor) -> pt.Tensor:
