@@ -49,6 +49,10 @@ _SIGNATURES = {
     'anqs_nade_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_nade_backward_chain': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'anqs_nade_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
+    'anqs_nade_tc_packed_bytes': (ctypes.c_size_t, [_vp]),
+    'anqs_nade_tc_pack': (_c_int, [_vp, _vp, _vp]),
+    'anqs_nade_log_psi_tc': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
+    'anqs_nade_cond_log_abs_tc': (_c_int, [_vp, _vp, _c_int, _vp, _c_i64, _vp, _vp]),
     'anqs_made_tc_packed_bytes': (ctypes.c_size_t, [_vp]),
     'anqs_made_tc_pack': (_c_int, [_vp, _vp, _vp]),
     'anqs_made_log_psi_tc': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),

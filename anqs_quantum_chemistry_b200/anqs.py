@@ -306,7 +306,6 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         """'fp64' (default; the reference's precision, every path) or 'tf32' (tcgen05 tensor cores for evaluations that do
         not need gradients: amplitudes of non-sampled configurations, the samplers' conditional probabilities)."""
         assert precision in ('fp64', 'tf32')
-        assert precision == 'fp64' or self.de_mode == 'MADE', 'the tensor-core kernels implement MADE mode'
         self.inference_precision = precision
 
     def _params(self):
@@ -414,12 +413,16 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
     def _packed_weights(self, desc):
         """Weights packed for the tensor-core kernels; repacked when a parameter changed."""
         dev = self.device
-        if self._packed_tc is None or self._packed_key != self._masked_key:
-            nbytes = int(_lib.lib().anqs_made_tc_packed_bytes(ctypes.byref(desc)))
+        nade = self.de_mode == 'NADE'
+        key = self._param_key() if nade else self._masked_key
+        if self._packed_tc is None or self._packed_key != key:
+            lib = _lib.lib()
+            nbytes = int((lib.anqs_nade_tc_packed_bytes if nade else lib.anqs_made_tc_packed_bytes)(ctypes.byref(desc)))
             if self._packed_tc is None or self._packed_tc.numel() * 8 < nbytes:
                 self._packed_tc = pt.empty((nbytes + 7) // 8, dtype=pt.int64, device=dev)
-            _lib.check(_lib.lib().anqs_made_tc_pack(ctypes.byref(desc), _lib.dptr(self._packed_tc), _lib.stream_ptr(dev)))
-            self._packed_key = self._masked_key
+            _lib.check((lib.anqs_nade_tc_pack if nade else lib.anqs_made_tc_pack)(ctypes.byref(desc), _lib.dptr(self._packed_tc),
+                                                                                  _lib.stream_ptr(dev)))
+            self._packed_key = key
         return self._packed_tc
 
     @pt.no_grad()
@@ -431,8 +434,8 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         out = pt.empty(B, dtype=pt.complex128, device=dev)
         desc = self._descriptor()
         packed = self._packed_weights(desc)
-        _lib.check(_lib.lib().anqs_made_log_psi_tc(ctypes.byref(desc), _lib.dptr(packed), _lib.dptr(idx), B,
-                                                   _lib.dptr(pt.view_as_real(out)), _lib.stream_ptr(dev)))
+        fn = _lib.lib().anqs_nade_log_psi_tc if self.de_mode == 'NADE' else _lib.lib().anqs_made_log_psi_tc
+        _lib.check(fn(ctypes.byref(desc), _lib.dptr(packed), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(out)), _lib.stream_ptr(dev)))
         return out
 
     def chosen_outcomes(self, idx: pt.Tensor) -> pt.Tensor:
@@ -444,10 +447,10 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
     # ---- reference surface ---------------------------------------------------------------------------------------
     def log_psi_of_indices(self, base_idx: pt.Tensor) -> pt.Tensor:
         idx = base_idx.contiguous().view(-1)
-        if self.de_mode == 'NADE':
-            return _NadeLogPsi.apply(self, idx, *self._params())
         if self.inference_precision == 'tf32' and not pt.is_grad_enabled():
             return self.log_psi_tc(idx)
+        if self.de_mode == 'NADE':
+            return _NadeLogPsi.apply(self, idx, *self._params())
         return _MadeLogPsi.apply(self, idx, *self._params())
 
     def log_psi(self, base_vec: pt.Tensor, just_return: bool = False) -> pt.Tensor:
@@ -478,13 +481,13 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         B = prefix_idx.shape[0]
         out = pt.empty((B, self.max_qudit_dim), dtype=pt.float64, device=dev)
         desc = self._descriptor()
-        if self.de_mode == 'NADE':
+        if self.inference_precision == 'tf32':
+            packed = self._packed_weights(desc)
+            fn = _lib.lib().anqs_nade_cond_log_abs_tc if self.de_mode == 'NADE' else _lib.lib().anqs_made_cond_log_abs_tc
+            _lib.check(fn(ctypes.byref(desc), _lib.dptr(packed), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out), _lib.stream_ptr(dev)))
+        elif self.de_mode == 'NADE':
             _lib.check(_lib.lib().anqs_nade_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
                                                          _lib.stream_ptr(dev)))
-        elif self.inference_precision == 'tf32':
-            packed = self._packed_weights(desc)
-            _lib.check(_lib.lib().anqs_made_cond_log_abs_tc(ctypes.byref(desc), _lib.dptr(packed), qudit_idx, _lib.dptr(prefix_idx), B,
-                                                            _lib.dptr(out), _lib.stream_ptr(dev)))
         else:
             _lib.check(_lib.lib().anqs_made_cond_log_abs(ctypes.byref(desc), qudit_idx, _lib.dptr(prefix_idx), B, _lib.dptr(out),
                                                          _lib.stream_ptr(dev)))

@@ -217,6 +217,16 @@ int anqs_nade_cond_log_abs(const anqs_nade_desc_t *desc, int qudit_idx, const in
 int anqs_nade_backward_chain(const anqs_nade_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
                              const double *d_save_h, const double *d_save_p, double *d_dY, double *d_da, double *d_x, void *stream);
 
+/* NADE mode on the tensor cores (k3_nade_tc.cu): as the MADE tensor-core entry points below, for the per-qudit MLP pairs.
+ * anqs_nade_tc_pack must be called again whenever a parameter changes; d_packed: anqs_nade_tc_packed_bytes(desc) bytes,
+ * 128-byte aligned.  Inference only, stated tolerance (tests/test_gpu_nade.py). */
+size_t anqs_nade_tc_packed_bytes(const anqs_nade_desc_t *desc);
+int anqs_nade_tc_pack(const anqs_nade_desc_t *desc, void *d_packed, void *stream);
+int anqs_nade_log_psi_tc(const anqs_nade_desc_t *desc, const void *d_packed, const int64_t *d_idx, int64_t n, double *d_log_psi,
+                         void *stream);
+int anqs_nade_cond_log_abs_tc(const anqs_nade_desc_t *desc, const void *d_packed, int qudit_idx, const int64_t *d_prefix, int64_t n,
+                              double *d_cond, void *stream);
+
 /* ---- A9  kernel 3, tensor-core mode: the same two functions with every GEMM on tcgen05 (kind::tf32, fp32 accumulate in
  * TMEM) and fp32 epilogue math.  Inference only (no activations are saved); agreement with the fp64 entry points above
  * is ~1e-3 in log|psi| and ~1e-2 rad in the phase (tf32 products carry 10 mantissa bits), see tests/test_gpu_anqs.py.

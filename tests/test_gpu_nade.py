@@ -77,3 +77,48 @@ def test_log_jacobian_matches_autograd():
         g_im = torch.autograd.grad(lp.imag.sum(), params)
         row = torch.complex(torch.cat([x.reshape(-1) for x in g_re]), -torch.cat([x.reshape(-1) for x in g_im]))
         assert (jac[b] - row).abs().max() < 1e-12
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_tensor_core_mode_within_tolerance(name):
+    """NADE on the tensor cores (tcgen05 tf32, k3_nade_tc.cu) against the fp64 kernel: identical masks, log|psi| within 2e-2,
+    phase within 1e-1 rad, conditionals within 2e-2; sampling through it conserves counts and stays physical; a parameter update
+    is picked up."""
+    g = load_golden(name)
+    wf = build(g, device=DEV)
+    n, ne = int(g['qubit_num']), int(g['particle_num'])
+    s = _dev(g['samples']).view(-1, 1)
+    unphys = torch.full((3, 1), (1 << n) - 1, dtype=torch.int64, device=DEV)   # all orbitals occupied: outside the sector
+    idx = torch.cat((s, unphys))
+    with torch.no_grad():
+        ref = wf.log_psi_of_indices(idx)
+        wf.set_inference_precision('tf32')
+        tc = wf.log_psi_of_indices(idx)
+    fin = torch.isfinite(ref.real)
+    assert torch.equal(fin, torch.isfinite(tc.real)) and 0 < int(fin.sum()) <= s.shape[0]   # the golden samples hold unphysical ones too
+    assert float((tc.real[fin] - ref.real[fin]).abs().max()) < 2e-2
+    assert float((tc.imag[fin] - ref.imag[fin]).abs().max()) < 1e-1
+    for q in range(wf.qudit_num):
+        wf.set_inference_precision('fp64')
+        c0 = wf.cond_log_abs(qudit_idx=q, prefix_idx=s.view(-1))
+        wf.set_inference_precision('tf32')
+        c1 = wf.cond_log_abs(qudit_idx=q, prefix_idx=s.view(-1))
+        f = torch.isfinite(c0)
+        assert torch.equal(f, torch.isfinite(c1))
+        assert float((c0[f] - c1[f]).abs().max()) < 2e-2
+    si, sc = wf.sample_stats(10 ** 5, seed=3)
+    assert float(sc.real.sum()) == 1e5
+    even = torch.tensor(0x5555555555555555, dtype=torch.int64, device=DEV)
+    assert bool((wf.hilbert_space.popcount(si.view(-1) & even) == ne // 2).all())
+    with torch.no_grad():
+        for p in wf.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+        tc2 = wf.log_psi_of_indices(s)
+        wf.set_inference_precision('fp64')
+        ref2 = wf.log_psi_of_indices(s)
+    f2 = torch.isfinite(ref2.real)
+    assert float((tc2.real[f2] - ref2.real[f2]).abs().max()) < 2e-2 and float((ref2.real[f2] - ref.real[:s.shape[0]][f2]).abs().max()) > 1e-3
+    # gradients never take the tensor-core path
+    wf.set_inference_precision('tf32')
+    lp = wf.log_psi_of_indices(s[:4])
+    assert lp.requires_grad and torch.equal(lp.detach(), ref2[:4])
