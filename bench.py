@@ -272,6 +272,34 @@ def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out['sample_stats_tcgen05'] = {'samples': 10 ** 6, 'unique': int(idx.shape[0]), 'seconds': dt, 'unique_per_s': idx.shape[0] / dt}
+    # ---- the other two ansatz families: NADE (the reference's default mode) at this qubit count, transformer on the C3 shape
+    def both_precisions(w, xs):
+        res, ref = {}, None
+        with torch.no_grad():
+            for prec in ('fp64', 'tf32'):
+                w.set_inference_precision(prec)
+                t = _time_ms(lambda: w.amplitude(xs.view(-1, 1)), reps=3, warm=1)
+                lp = w.log_psi_of_indices(xs) if hasattr(w, 'log_psi_tc') else w.log_psi_kernel(xs)
+                res[prec + '_amplitudes_per_s'] = xs.shape[0] / (t * 1e-3)
+                if prec == 'fp64':
+                    ref = lp
+                else:
+                    res['tf32_max_abs_err_log_abs'] = float((lp.real - ref.real).abs().max())
+                    res['tf32_max_abs_err_phase'] = float((lp.imag - ref.imag).abs().max())
+            w.set_inference_precision('fp64')
+        return res
+    torch.manual_seed(0)
+    nade = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='NADE'))
+    out['amplitudes_nade'] = dict(batch=b, qubits=wf.qubit_num, params=nade.param_num, **both_precisions(nade, x))
+    from anqs_quantum_chemistry_b200 import HilbertSpace, synthetic
+    from anqs_quantum_chemistry_b200.transformer_anqs import TransformerANQS, TransformerANQSConfig
+    hs3 = HilbertSpace(qubit_num=20, device=dev, parent_dir=tempfile.mkdtemp(prefix='anqs_c3_'), rng_seed=0)
+    masker3 = LocallyDecomposableMasker(hilbert_space=hs3, symmetries=(ParticleNumberSymmetry(hilbert_space=hs3, particle_num=14),
+                                                                       SpinHalfProjectionSymmetry(hilbert_space=hs3, spin=0)))
+    torch.manual_seed(0)
+    tfm = TransformerANQS(hilbert_space=hs3, masker=masker3, config=TransformerANQSConfig(dim=64, depth=2, head_num=4))
+    x3 = torch.from_numpy(synthetic.random_physical_samples(20, 7, 7, 10 ** 6, seed=1).view(np.int64)).to(dev).repeat(20)[: 1 << 17].contiguous()
+    out['amplitudes_transformer'] = dict(batch=int(x3.shape[0]), qubits=20, config='dim 64, depth 2, 4 heads', **both_precisions(tfm, x3))
     return out
 
 
