@@ -46,6 +46,8 @@ _SIGNATURES = {
     'anqs_made_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_made_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
     'anqs_made_backward_chain': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'anqs_batch_reduce_workspace': (_c_i64, [_vp, _c_int, _c_i64]),
+    'anqs_batch_reduce_gemm': (_c_int, [_vp, _c_int, _c_i64, _c_int, _vp, _c_i64, _vp]),
     'anqs_nade_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_nade_backward_chain': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'anqs_nade_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
@@ -105,6 +107,33 @@ class TransformerDesc(ctypes.Structure):
 
 # entry points added by later kernel families register themselves here (name -> (restype, argtypes))
 OPTIONAL_SIGNATURES = {}
+
+class BrgProblem(ctypes.Structure):
+    """anqs_brg_problem_t (include/anqs_b200.h): C[M][N] (+)= A^T B, colsum[M] (+)= column sums of A."""
+    _fields_ = [('A', _vp), ('B', _vp), ('C', _vp), ('colsum', _vp),
+                ('lda', ctypes.c_int32), ('ldb', ctypes.c_int32), ('ldc', ctypes.c_int32), ('M', ctypes.c_int32), ('N', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
+
+
+_brg_workspace = {}
+
+
+def batch_reduce(problems, K: int, accumulate: bool, device):
+    """problems: list of (A, lda, M, B, ldb, N, C, ldc, colsum or None) with device addresses (ints).  One call of
+    anqs_batch_reduce_gemm on the current stream; the workspace is kept per device and grows on demand."""
+    import torch as pt
+    arr = (BrgProblem * len(problems))()
+    for i, (A, lda, M, B, ldb, N, C, ldc, colsum) in enumerate(problems):
+        arr[i] = BrgProblem(A, B, C, colsum, lda, ldb, ldc, M, N, 0)
+    need = lib().anqs_batch_reduce_workspace(arr, len(problems), K)
+    if need < 0:
+        raise RuntimeError('anqs_batch_reduce_workspace: bad problem description')
+    ws = _brg_workspace.get(device)
+    if ws is None or ws.numel() * 8 < need:
+        ws = _brg_workspace[device] = pt.empty((need + 7) // 8, dtype=pt.float64, device=device)
+    check(lib().anqs_batch_reduce_gemm(arr, len(problems), K, int(bool(accumulate)), ctypes.c_void_p(ws.data_ptr()), ws.numel() * 8,
+                                       stream_ptr(device)))
+
 
 _lib = None
 

@@ -138,8 +138,9 @@ class _MadeLogPsi(pt.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        """The per-sample chain runs in made_backward_kernel (k3_made_bwd.cu); what is left here are the reductions over the
-        batch: grad W_out = dY^T h_last, grad W_l = da_l^T (h_{l-1} | x) and the bias sums, batched over both sub-networks."""
+        """The per-sample chain runs in made_backward_kernel (k3_made_bwd.cu), the reductions over the batch - grad W_out =
+        dY^T h_last, grad W_l = da_l^T (h_{l-1} | x) and the bias sums of both sub-networks - in batch_reduce_gemm_kernel
+        (k3_batch_reduce.cu)."""
         wf, idx = ctx.wf, ctx.idx
         save_h, save_p = ctx.saved                      # [2, depth, B, width], [B, Q, DM]
         B, Q, DM, depth, n = idx.shape[0], wf.qudit_num, wf.max_qudit_dim, wf.depth, wf.qubit_num
@@ -149,27 +150,30 @@ class _MadeLogPsi(pt.autograd.Function):
         lib, sp = _lib.lib(), _lib.stream_ptr(dev)
         QD, width = Q * DM, wf.width
         chunk = max(1, min(B, _MADE_BWD_SCRATCH_BYTES // (16 * QD + 16 * depth * width + 8 * n)))
-        gW_out = gb_out = gW0 = gWm = gb_h = None
+        f64 = dict(dtype=pt.float64, device=dev)
+        alloc = pt.zeros if B == 0 else pt.empty
+        gW_out, gb_out = alloc((2, QD, width), **f64), alloc((2, QD), **f64)
+        gW0, gb_h = alloc((2, width, n), **f64), alloc((2, depth, width), **f64)
+        gWm = alloc((2, depth - 1, width, width), **f64) if depth > 1 else None
         for lo in range(0, B, chunk):
             hi = min(B, lo + chunk)
             m = hi - lo
-            dY = pt.empty((2, m, QD), dtype=pt.float64, device=dev)
-            da = pt.empty((2, depth, m, width), dtype=pt.float64, device=dev)
-            x = pt.empty((m, n), dtype=pt.float64, device=dev)
+            dY = pt.empty((2, m, QD), **f64)
+            da = pt.empty((2, depth, m, width), **f64)
+            x = pt.empty((m, n), **f64)
             h = save_h if m == B else save_h[:, :, lo:hi].contiguous()
             p = save_p if m == B else save_p[lo:hi]
             _lib.check(lib.anqs_made_backward_chain(ctypes.byref(desc), _lib.dptr(idx[lo:hi]), m, _lib.dptr(pt.view_as_real(g[lo:hi])),
                                                     _lib.dptr(h), _lib.dptr(p), _lib.dptr(dY), _lib.dptr(da), _lib.dptr(x), sp))
-            parts = (pt.bmm(dY.transpose(1, 2), h[:, depth - 1]),                      # [2, QD, width]
-                     dY.sum(1),                                                        # [2, QD]
-                     pt.matmul(da[:, 0].transpose(1, 2), x),                           # [2, width, n]
-                     pt.matmul(da[:, 1:].transpose(2, 3), h[:, :depth - 1]) if depth > 1 else None,   # [2, depth-1, width, width]
-                     da.sum(2))                                                        # [2, depth, width]
-            if gW_out is None:
-                gW_out, gb_out, gW0, gWm, gb_h = parts
-            else:
-                gW_out, gb_out, gW0, gb_h = gW_out + parts[0], gb_out + parts[1], gW0 + parts[2], gb_h + parts[4]
-                gWm = gWm + parts[3] if depth > 1 else None
+            problems = []
+            for net in range(2):   # k3_batch_reduce.cu: all batch reductions of both sub-networks in one launch pair
+                problems.append((dY[net].data_ptr(), QD, QD, h[net, depth - 1].data_ptr(), width, width,
+                                 gW_out[net].data_ptr(), width, gb_out[net].data_ptr()))
+                problems.append((da[net, 0].data_ptr(), width, width, x.data_ptr(), n, n, gW0[net].data_ptr(), n, gb_h[net, 0].data_ptr()))
+                for l in range(1, depth):
+                    problems.append((da[net, l].data_ptr(), width, width, h[net, l - 1].data_ptr(), width, width,
+                                     gWm[net, l - 1].data_ptr(), width, gb_h[net, l].data_ptr()))
+            _lib.batch_reduce(problems, m, lo > 0, dev)
         n_layer = depth + 1
         per_net = 2 * n_layer if wf.use_bias else n_layer
         grads = [None] * (2 * per_net)

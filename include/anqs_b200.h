@@ -211,6 +211,19 @@ int anqs_nade_log_psi(const anqs_nade_desc_t *desc, const int64_t *d_idx, int64_
                       double *d_save_p, void *stream);
 int anqs_nade_cond_log_abs(const anqs_nade_desc_t *desc, int qudit_idx, const int64_t *d_prefix, int64_t n, double *d_cond,
                            void *stream);
+/* The reductions over the batch that finish a backward pass (reference: torch's addmm backward under MLP:217-246):
+ * for every problem  C[M][N] (+)= A^T B  and, when colsum is not null,  colsum[M] (+)= column sums of A,  with A [K][M]
+ * (leading dimension lda) and B [K][N] (ldb) sample-major and N <= 64.  All problems share K.  Deterministic: partial tiles
+ * go to `workspace` (anqs_batch_reduce_workspace bytes) and are added in a fixed order.  accumulate != 0 adds to C / colsum. */
+typedef struct {
+    const double *A, *B;
+    double *C, *colsum;
+    int32_t lda, ldb, ldc, M, N, reserved;
+} anqs_brg_problem_t;
+int64_t anqs_batch_reduce_workspace(const anqs_brg_problem_t *problems, int n_problems, int64_t K);
+int anqs_batch_reduce_gemm(const anqs_brg_problem_t *problems, int n_problems, int64_t K, int accumulate, void *workspace,
+                           int64_t workspace_bytes, void *stream);
+
 /* Backward chain of anqs_nade_log_psi, as anqs_made_backward_chain but per (sub-network, qudit) MLP:
  * d_dY[2][n][qudit_num * max_qudit_dim] (entries beyond the qudit's own outcomes are zero), d_da[2][qudit_num][depth][n][width],
  * d_x[n][qubit_num]; d_save_h / d_save_p as anqs_nade_log_psi saved them. */

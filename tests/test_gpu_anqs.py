@@ -352,3 +352,33 @@ def test_count_splitting_at_full_size():
     assert torch.equal(idx, idx2) and torch.equal(cnt, cnt2)
     parts = [adist.sharded_sample_stats(wf, num, seed=5, world_size=4, rank=r, gather=False) for r in range(4)]
     assert torch.equal(torch.cat([p[0] for p in parts]), idx) and torch.equal(torch.cat([p[1] for p in parts]), cnt)
+
+
+@pytest.mark.parametrize('K', [1, 17, 1000, 100003])
+def test_batch_reduce_gemm_matches_matmul(K):
+    """k3_batch_reduce.cu (the batch reductions of the backward pass, torch's addmm backward under MLP:217-246) against
+    float64 matmul on ragged problems: partial output tiles, odd leading dimensions, with and without column sums, accumulate."""
+    from anqs_quantum_chemistry_b200 import _lib
+    dev = torch.device('cuda:0')
+    gen = torch.Generator(device='cpu').manual_seed(K)
+    shapes = [(640, 64, 640, 64), (200, 56, 201, 57), (64, 64, 64, 64), (1, 1, 3, 5), (129, 7, 131, 7)]   # M, N, lda, ldb
+    ops, problems = [], []
+    for M, N, lda, ldb in shapes:
+        A = torch.randn(K, lda, generator=gen, dtype=torch.float64).to(dev)
+        Bm = torch.randn(K, ldb, generator=gen, dtype=torch.float64).to(dev)
+        C = torch.full((M, N + 2), 7.0, dtype=torch.float64, device=dev)
+        cs = torch.full((M,), 7.0, dtype=torch.float64, device=dev) if M != 64 else None
+        ops.append((A, Bm, C, cs, M, N))
+        problems.append((A.data_ptr(), lda, M, Bm.data_ptr(), ldb, N, C.data_ptr(), N + 2, cs.data_ptr() if cs is not None else None))
+    _lib.batch_reduce(problems, K, False, dev)
+    for A, Bm, C, cs, M, N in ops:
+        ref = A[:, :M].T @ Bm[:, :N]
+        scale = max(1.0, float(ref.abs().max()))
+        assert float((C[:, :N] - ref).abs().max()) < 1e-12 * scale * max(1, K) ** 0.5
+        assert bool((C[:, N:] == 7.0).all())                       # outside the problem: untouched
+        if cs is not None:
+            assert float((cs - A[:, :M].sum(0)).abs().max()) < 1e-12 * max(1, K) ** 0.5 * scale
+    first = [op[2].clone() for op in ops]
+    _lib.batch_reduce(problems, K, True, dev)                      # accumulate: exactly twice the first result (deterministic)
+    for (A, Bm, C, cs, M, N), f in zip(ops, first):
+        assert torch.equal(C[:, :N], 2 * f[:, :N])
