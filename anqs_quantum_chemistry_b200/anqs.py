@@ -201,8 +201,8 @@ class _NadeLogPsi(pt.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        """The per-sample chains of all 2 Q MLPs run in nade_backward_kernel (k3_made_bwd.cu); the reductions over the batch
-        are batched GEMMs / column sums over (sub-network, qudit)."""
+        """The per-sample chains of all 2 Q MLPs run in nade_backward_kernel (k3_made_bwd.cu), the reductions over the batch
+        of every (sub-network, qudit, layer) in batch_reduce_gemm_kernel (k3_batch_reduce.cu)."""
         wf, idx = ctx.wf, ctx.idx
         save_h, save_p = ctx.saved                      # [2, Q, depth, B, width], [B, Q, DM]
         B, Q, DM, depth, n, width = idx.shape[0], wf.qudit_num, wf.max_qudit_dim, wf.depth, wf.qubit_num, wf.width
@@ -212,27 +212,32 @@ class _NadeLogPsi(pt.autograd.Function):
         lib, sp = _lib.lib(), _lib.stream_ptr(dev)
         QD = Q * DM
         chunk = max(1, min(B, _MADE_BWD_SCRATCH_BYTES // (32 * QD + 16 * Q * depth * width + 8 * n)))
-        acc = None
+        f64 = dict(dtype=pt.float64, device=dev)
+        alloc = pt.zeros if B == 0 else pt.empty
+        gW_out, gb_out = alloc((2, Q, DM, width), **f64), alloc((2, Q, DM), **f64)
+        gW0, gb_h = alloc((2, Q, width, n), **f64), alloc((2, Q, depth, width), **f64)
+        gWm = alloc((2, Q, depth - 1, width, width), **f64) if depth > 1 else None
         for lo in range(0, B, chunk):
             hi = min(B, lo + chunk)
             m = hi - lo
-            dY = pt.empty((2, m, QD), dtype=pt.float64, device=dev)
-            da = pt.empty((2, Q, depth, m, width), dtype=pt.float64, device=dev)
-            x = pt.empty((m, n), dtype=pt.float64, device=dev)
+            dY = pt.empty((2, m, QD), **f64)
+            da = pt.empty((2, Q, depth, m, width), **f64)
+            x = pt.empty((m, n), **f64)
             h = save_h if m == B else save_h[:, :, :, lo:hi].contiguous()
             p = save_p if m == B else save_p[lo:hi]
             _lib.check(lib.anqs_nade_backward_chain(ctypes.byref(desc), _lib.dptr(idx[lo:hi]), m, _lib.dptr(pt.view_as_real(g[lo:hi])),
                                                     _lib.dptr(h), _lib.dptr(p), _lib.dptr(dY), _lib.dptr(da), _lib.dptr(x), sp))
-            dYq = dY.view(2, m, Q, DM).permute(0, 2, 3, 1)                                # [2, Q, DM, m]
-            parts = [pt.matmul(dYq, h[:, :, depth - 1]),                                  # [2, Q, DM, width]
-                     dY.sum(1).view(2, Q, DM),                                            # [2, Q, DM]
-                     pt.matmul(da[:, :, 0].transpose(2, 3), x),                           # [2, Q, width, n]
-                     da.sum(3)]                                                           # [2, Q, depth, width]
-            if depth > 1:
-                parts.append(pt.matmul(da[:, :, 1:].transpose(3, 4), h[:, :, :depth - 1]))   # [2, Q, depth-1, width, width]
-            acc = parts if acc is None else [a + b for a, b in zip(acc, parts)]
-        gW_out, gb_out, gW0, gb_h = acc[:4]
-        gWm = acc[4] if depth > 1 else None
+            problems = []
+            for net in range(2):   # k3_batch_reduce.cu: every (sub-network, qudit, layer) reduction in one call
+                for q in range(Q):
+                    problems.append((dY[net].data_ptr() + 8 * q * DM, QD, DM, h[net, q, depth - 1].data_ptr(), width, width,
+                                     gW_out[net, q].data_ptr(), width, gb_out[net, q].data_ptr()))
+                    problems.append((da[net, q, 0].data_ptr(), width, width, x.data_ptr(), n, n, gW0[net, q].data_ptr(), n,
+                                     gb_h[net, q, 0].data_ptr()))
+                    for l in range(1, depth):
+                        problems.append((da[net, q, l].data_ptr(), width, width, h[net, q, l - 1].data_ptr(), width, width,
+                                         gWm[net, q, l - 1].data_ptr(), width, gb_h[net, q, l].data_ptr()))
+            _lib.batch_reduce(problems, m, lo > 0, dev)
         n_layer = depth + 1
         per_mlp = 2 * n_layer if wf.use_bias else n_layer
         grads = [None] * len(ctx.weights)
