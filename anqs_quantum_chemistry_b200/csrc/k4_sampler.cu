@@ -14,6 +14,8 @@
 // parents are distributed over warps, launches or GPUs - which is what lets sub-trees be sharded with no
 // communication.  draw_mode 0 replaces the binomial draw by its rounded mean rint(n p): the deterministic mode
 // the parity tests use against the reference with torch.distributions.Binomial patched the same way.
+// A node that carries a single sample takes one categorical draw by inversion instead of k binomial rounds (a multinomial
+// with one trial), which is what most nodes of the deep levels of a large sparse batch are.
 #include <algorithm>
 
 #include "common.cuh"
@@ -130,19 +132,51 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
         cum[1 + lane] = p0;
         cum[33 + lane] = p1;
         __syncwarp();
-        if (lane == 0) {  // sequential prefix sum, like a cumsum along the row (ANQS:562-565)
-            double acc = 0.0;
-            cum[0] = 0.0;
-            for (int d = 1; d <= D; ++d) {
-                acc += cum[d];
-                cum[d] = acc;
-            }
-        }
-        __syncwarp();
-        // binomial tree, most significant outcome bit first (ANQS:568-585)
         double cnt = counts[b];  // count of tree node `lane` (valid for lane < 2^j in round j)
         double c_even = 0.0, c_odd = 0.0;
-        for (int j = 0; j < k; ++j) {
+        if (draw_mode == 0) {
+            if (lane == 0) {  // sequential prefix sum, like a cumsum along the row (ANQS:562-565): the order the goldens were made with
+                double acc = 0.0;
+                cum[0] = 0.0;
+                for (int d = 1; d <= D; ++d) {
+                    acc += cum[d];
+                    cum[d] = acc;
+                }
+            }
+        } else {              // random draws: any summation order is as good, take the warp scan
+            double s0 = p0, s1 = p1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double t0 = __shfl_up_sync(0xffffffffu, s0, d), t1 = __shfl_up_sync(0xffffffffu, s1, d);
+                if (lane >= d) s0 += t0, s1 += t1;
+            }
+            s1 += __shfl_sync(0xffffffffu, s0, 31);
+            cum[1 + lane] = s0;
+            cum[33 + lane] = s1;
+            if (lane == 0) cum[0] = 0.0;
+        }
+        __syncwarp();
+        const bool single = draw_mode != 0 && cnt == 1.0;   // warp-uniform
+        if (single) {
+            // a multinomial with one trial is one categorical draw: invert the cumulative distribution with one uniform
+            // instead of walking the binomial tree with k of them (most nodes of a deep level carry a single sample)
+            const uint64_t parent = rng_keys ? (uint64_t)rng_keys[b] : (uint64_t)(parent_offset + b);
+            Philox g(seed, (uint32_t)parent, (uint32_t)(parent >> 32), ((uint32_t)level << 16) | 0xFF00u, 0u);
+            const uint4 r = g();
+            const double t = u01(r.x, r.y) * cum[D];
+            const bool le0 = lane + 1 <= D && cum[lane + 1] <= t, le1 = lane + 33 <= D && cum[lane + 33] <= t;
+            int d = __popc(__ballot_sync(0xffffffffu, le0)) + __popc(__ballot_sync(0xffffffffu, le1));
+            d = min(d, D - 1);
+            // rounding at the upper end can land on an outcome of probability zero: step down to the nearest possible one
+            const unsigned pos0 = __ballot_sync(0xffffffffu, p0 > 0.0), pos1 = __ballot_sync(0xffffffffu, p1 > 0.0);
+            const unsigned long long pos = ((unsigned long long)pos1 << 32) | pos0;
+            const unsigned long long below = pos & (d == 63 ? ~0ull : ((1ull << (d + 1)) - 1ull));
+            if (below) d = 63 - __clzll(below);
+            c_even = (d == 2 * lane) ? 1.0 : 0.0;
+            c_odd = (d == 2 * lane + 1) ? 1.0 : 0.0;
+        }
+        // binomial tree, most significant outcome bit first (ANQS:568-585)
+        for (int j = 0; j < (single ? 0 : k); ++j) {
             const int nodes = 1 << j, span = D >> j;
             double left = 0.0;
             if (lane < nodes) {
