@@ -196,6 +196,41 @@ def vmc_iteration_rate(dev, n=20, n_el=14, sample_num=10 ** 4, iters=20, with_sr
             'note': 'reference on 8 CPU threads: 0.17 it/s (MADE, ham) to 0.37 it/s (NADE, trie) at this size, incl. SR (BASELINE.md section 2)'}
 
 
+def vmc_iteration_c5(ham, wf, dev, n_el, sample_num=10 ** 6, iters=5):
+    """VMC iterations/s on the C5 shape itself (this GPU only; scripts/bench_vmc_sharded.py shards the same iteration over
+    1/2/4/8 GPUs): count-splitting sampler of 1e6 samples (tf32 conditionals) -> float64 amplitudes with the graph ->
+    sample-aware local energy -> loss EXP:609 -> float64 backward -> Adam."""
+    import torch
+    from anqs_quantum_chemistry_b200 import dist as adist
+    prec = wf.inference_precision
+    wf.set_inference_precision('tf32')
+    opt = torch.optim.Adam(wf.parameters(), lr=1e-3)
+    step = adist.ShardedEnergyGradient(wf, adist.ShardedLocalEnergy(ham, n_el // 2, n_el // 2).stats)
+    n_unq = 0
+
+    def one_iter(it):
+        idx, _ = adist.sharded_sample_stats(wf, sample_num, seed=100 + it, world_size=1, rank=0, gather=False)
+        mean, _, _ = step(idx)
+        opt.step()
+        return idx.shape[0], mean
+    for it in range(2):
+        one_iter(it)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(iters):
+        n_unq, mean = one_iter(2 + it)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    wf.set_inference_precision(prec)
+    for p_ in wf.parameters():
+        p_.grad = None
+    return {'iters_per_s': 1e3 / ms, 'ms_per_iter': ms, 'samples': sample_num, 'n_unq_last': int(n_unq), 'qubits': int(wf.qubit_num),
+            'sampler': 'count splitting (ANQS:494-525), tf32 conditionals', 'gradient': 'float64', 'energy_last': float(mean.real),
+            'multi_gpu': 'profiles/r1_vmc_c5_{1,2,4,8}gpu.json (scripts/bench_vmc_sharded.py)'}
+
+
 def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     """The other kernels of the path on the same workload (not part of `value`): ordered term enumeration with matrix
     elements (the materialising path of the full local energy), MADE amplitudes and the count-splitting sampler."""
@@ -272,6 +307,7 @@ def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out['sample_stats_tcgen05'] = {'samples': 10 ** 6, 'unique': int(idx.shape[0]), 'seconds': dt, 'unique_per_s': idx.shape[0] / dt}
+    out['vmc_iteration_c5'] = vmc_iteration_c5(ham, wf, dev, na + nb)
     # ---- the other two ansatz families: NADE (the reference's default mode) at this qubit count, transformer on the C3 shape
     def both_precisions(w, xs):
         res, ref = {}, None

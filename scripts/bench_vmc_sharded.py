@@ -22,6 +22,7 @@ ap.add_argument('--steps', type=int, default=10)
 ap.add_argument('--warmup', type=int, default=3)
 ap.add_argument('--qubits', type=int, default=56)
 ap.add_argument('--electrons', type=int, default=14)
+ap.add_argument('--profile', action='store_true', help='after the timed run: one iteration under the torch profiler (rank 0 prints the tables)')
 ap.add_argument('--f64-sampler', action='store_true', help='conditional probabilities of the sampler in float64 instead of tf32')
 args = ap.parse_args()
 rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
@@ -102,5 +103,14 @@ if rank == 0:
                                                   'optimizer': float(t[3])},
                       'unique_rows_per_s': float(r) / args.steps / ms * 1e3,
                       'energy_mean_last': [float(mean.real), float(mean.imag)]}), flush=True)
+if args.profile:
+    from torch.profiler import profile, ProfilerActivity
+    barrier()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        iteration(10 ** 6)
+        torch.cuda.synchronize()
+    if rank == 0:
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=30, max_name_column_width=60))
+        print(prof.key_averages().table(sort_by='self_cpu_time_total', row_limit=25, max_name_column_width=60))
 if world > 1:
     dist.destroy_process_group()

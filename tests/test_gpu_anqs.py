@@ -382,3 +382,37 @@ def test_batch_reduce_gemm_matches_matmul(K):
     _lib.batch_reduce(problems, K, True, dev)                      # accumulate: exactly twice the first result (deterministic)
     for (A, Bm, C, cs, M, N), f in zip(ops, first):
         assert torch.equal(C[:, :N], 2 * f[:, :N])
+
+
+@pytest.mark.parametrize('count', [1.0, 2.0, 37.0])
+def test_split_level_draws_follow_the_conditional_distribution(count):
+    """Exactness of the random mode of split_level_kernel (ANQS:557-591 draws a multinomial): 2e5 parents with the same
+    conditional row and distinct keys; the histogram of their children against count * p by chi-square (63 - 6 masked outcomes
+    => 56 degrees of freedom).  count = 1 exercises the single-draw path, 2 the inversion binomial, 37 both binomial samplers."""
+    from anqs_quantum_chemistry_b200 import _lib
+    import ctypes
+    dev = torch.device('cuda:0')
+    B, D = 200000, 64
+    gen = torch.Generator().manual_seed(5)
+    logits = torch.randn(D, generator=gen, dtype=torch.float64) * 1.5
+    logits[[3, 17, 31, 32, 60, 63]] = -float('inf')                # masked outcomes (cond = -inf), incl. the last one
+    p = torch.softmax(logits, 0)
+    cond = (0.5 * torch.log(p)).repeat(B, 1).contiguous().to(dev)   # the kernel takes log|psi| conditionals: p = softmax(2 cond)
+    counts = torch.full((B,), count, dtype=torch.float64, device=dev)
+    memo = torch.zeros(B, dtype=torch.int32, device=dev)
+    cont = torch.tensor([-1], dtype=torch.int64, device=dev)        # every continuation allowed by the symmetry table
+    keys = (torch.arange(B, dtype=torch.int64, device=dev) * 2654435761 + 12345)
+    child = torch.empty((B, D), dtype=torch.float64, device=dev)
+    n_child = torch.empty(B, dtype=torch.int64, device=dev)
+    _lib.check(_lib.lib().anqs_sampler_split_level(_lib.dptr(cond), D, 6, _lib.dptr(counts), _lib.dptr(memo), _lib.dptr(cont), 1, B,
+                                                   3, 1, 99, 0, _lib.dptr(keys), _lib.dptr(child), _lib.dptr(n_child),
+                                                   _lib.stream_ptr(dev)))
+    child = child.cpu()
+    assert bool((child.sum(1) == count).all())                      # every parent's samples are conserved
+    assert bool((child == child.round()).all()) and bool((child >= 0).all())
+    hist = child.sum(0)
+    assert float(hist[p == 0].sum()) == 0.0                         # impossible outcomes never drawn
+    expect = B * count * p[p > 0]
+    chi2 = float(((hist[p > 0] - expect) ** 2 / expect).sum())
+    assert chi2 < 57 + 6 * (2 * 57) ** 0.5, chi2                    # mean dof, six sigma
+    assert int(n_child.sum()) == int((child > 0).sum())
