@@ -124,11 +124,12 @@ nade_forward_kernel(const anqs_nade_desc_t P, const int64_t *__restrict__ idx_in
                             if (d < D && ((mw >> d) & 1ull)) mx = fmax(mx, z[jj]);
                         }
                         mx = row_max16(mx);
-                        double se = 0.0;
+                        double se = 0.0, ez[4];
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             const int d = tx + 16 * jj;
-                            if (d < D && ((mw >> d) & 1ull)) se += exp(2.0 * (z[jj] - mx));
+                            ez[jj] = (d < D && ((mw >> d) & 1ull)) ? exp(2.0 * (z[jj] - mx)) : 0.0;
+                            se += ez[jj];
                         }
                         se = row_sum16(se);
                         const double L = mx + 0.5 * log(se);
@@ -145,13 +146,14 @@ nade_forward_kernel(const anqs_nade_desc_t P, const int64_t *__restrict__ idx_in
                             }
                         } else {
                             double pick = 0.0;
+                            const double inv_se = 1.0 / se;   // p_d = exp(2 (z_d - max)) / sum: no second exponential
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
                                 const int d = tx + 16 * jj;
                                 const bool allowed = any && d < D && ((mw >> d) & 1ull);
                                 if (d == chosen) pick = allowed ? z[jj] - L : -INFINITY;
                                 if (save_p && d < DM && base + s < B)
-                                    save_p[((size_t)(base + s) * Q + q) * DM + d] = allowed ? exp(2.0 * (z[jj] - L)) : 0.0;
+                                    save_p[((size_t)(base + s) * Q + q) * DM + d] = allowed ? ez[jj] * inv_se : 0.0;
                             }
                             out_re[ss] += row_sum16(pick);
                         }

@@ -32,10 +32,15 @@ __device__ __forceinline__ long long memo_index(const anqs_made_desc_t &P, uint6
 }
 
 // wt[k][j] = W[(row0 + j) * K + k] for j < rows, 0 otherwise  (nn.Linear layout [out][in])
+// A warp moves 8 rows x 4 consecutive k at a time: every row contributes one full 32-byte sector of W, and the 32 stores
+// land on (4 k + j) mod 16 = every 8-byte bank pair exactly twice (MD_S = 68 = 4 mod 16), the two-wavefront minimum.
 __device__ __forceinline__ void load_weights_t(double *wt, const double *__restrict__ W, int row0, int rows, int K) {
-    for (int e = threadIdx.x; e < 64 * K; e += MD_THREADS) {
-        int j = e / K, k = e - j * K;
-        wt[k * MD_S + j] = j < rows ? __ldg(W + (size_t)(row0 + j) * K + k) : 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kq = lane & 3, jo = lane >> 2;
+    const int steps = 8 * ((K + 3) >> 2);
+    for (int t = warp; t < steps; t += MD_THREADS / 32) {
+        const int j = (t & 7) * 8 + jo, k = (t >> 3) * 4 + kq;
+        if (k < K) wt[k * MD_S + j] = j < rows ? __ldg(W + (size_t)(row0 + j) * K + k) : 0.0;
     }
 }
 
