@@ -4,8 +4,8 @@
 // Every one of them is C[M x N] (+)= A^T B with A [K x M] and B [K x N] both stored sample-major (one row per sample), K = the
 // batch (10^5..10^6), M <= 640, N <= 64: a tiny output and an enormous reduction dimension.  Library fp64 GEMMs pick
 // 32x32 tiles for that shape (measured 5 TFLOP/s on B200); here the output is cut into 128 x 64 tiles, the batch into S
-// slices so that tiles x S is one wave of two CTAs per SM, and each CTA keeps its whole output tile in registers (8 x 8 per
-// thread) while its slice of A and B streams through a double-buffered shared-memory tile by cp.async — 8 LDS.128 per
+// slices so that all CTAs together are one wave (a 128-row tile gets 3/2 of the slices of a 64-row tile, which runs 4 x 8
+// per thread), and each CTA keeps its whole output tile in registers (8 x 8 per thread) while its slice of A and B streams through a double-buffered shared-memory tile by cp.async — 8 LDS.128 per
 // 64 DFMA, so the FP64 pipe and not the shared-memory pipe is the limit.  The column sums of A (bias gradients) ride along
 // from the same shared-memory tile.  Partial tiles go to a caller-supplied workspace and a second small kernel adds them up
 // in a fixed order: the result is deterministic.
@@ -17,7 +17,7 @@
 
 namespace anqs {
 
-constexpr int BR_MT = 128, BR_NT = 64, BR_KT = 16, BR_THREADS = 128, BR_MAX_TILES = 32;
+constexpr int BR_MT = 128, BR_NT = 64, BR_KT = 16, BR_THREADS = 128, BR_MAX_TILES = 64;
 constexpr int BR_TILE_DOUBLES = BR_MT * BR_NT + BR_MT;   // partial C tile + partial column sums
 
 struct BrTile {
@@ -27,6 +27,7 @@ struct BrTile {
 };
 struct BrBatch {
     BrTile t[BR_MAX_TILES];
+    int first[BR_MAX_TILES + 1];   // CTAs first[i] .. first[i + 1] - 1 are the K slices of tile i
 };
 
 // 8-byte asynchronous copy global -> shared, zero-filled when !ok (src-size 0): no registers held across the compute phase
@@ -36,35 +37,35 @@ __device__ __forceinline__ void br_cp_async8(double *dst, const double *src, boo
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(BR_THREADS, 2)
-batch_reduce_gemm_kernel(const BrBatch P, int64_t K, int64_t k_per_split, double *__restrict__ ws) {
-    __shared__ __align__(16) double As[2][BR_KT][BR_MT];
-    __shared__ __align__(16) double Bs[2][BR_KT][BR_NT];
-    const int tile = blockIdx.y;
-    const double *const tA = P.t[tile].A, *const tB = P.t[tile].B;
-    const int lda = P.t[tile].lda, ldb = P.t[tile].ldb, M = P.t[tile].M, N = P.t[tile].N;
-    const bool want_sums = P.t[tile].colsum != nullptr;
+// One K slice of one output tile with MT (128 or 64) rows: thread = (MT / 16) x 8 outputs.
+template <int MT>
+__device__ __forceinline__ void br_slice(const BrTile &T, int64_t k0, int64_t k1, double (*As)[BR_KT][BR_MT], double (*Bs)[BR_KT][BR_NT],
+                                         double *__restrict__ out) {
+    constexpr int RJ = MT / 32;              // row blocks of 32 per thread: rows 2 og + {0,1} + 32 j, j < RJ
+    const int lda = T.lda, ldb = T.ldb, M = T.M, N = T.N;
+    const bool want_sums = T.colsum != nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ig = lane & 7;                 // 8 column groups: columns 2 ig + {0,1} + 16 j, j < 4
-    const int og = warp * 4 + (lane >> 3);   // 16 row groups:   rows    2 og + {0,1} + 32 j, j < 4
-    const int64_t k0 = (int64_t)blockIdx.x * k_per_split, k1 = min(K, k0 + k_per_split);
+    const int og = warp * 4 + (lane >> 3);   // 16 row groups
     const int b_col = tid & (BR_NT - 1), b_row = tid >> 6;   // B tile: 8 elements per thread, rows b_row + 2 j
     const bool a_ok = tid < M, b_ok = b_col < N;             // A tile: 16 elements per thread, column tid, rows j
-    const double *Ap = tA + (a_ok ? tid : 0), *Bp = tB + (b_ok ? b_col : 0);
+    const double *Ap = T.A + (a_ok ? tid : 0), *Bp = T.B + (b_ok ? b_col : 0);
 
-    double acc[8][8];
+    double acc[2 * RJ][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 2 * RJ; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
     double csum = 0.0;
 
     auto fetch = [&](int64_t kb, int buf) {
+        if (MT == 128 || tid < 64) {
 #pragma unroll
-        for (int j = 0; j < BR_KT; ++j) {
-            const int64_t k = kb + j;
-            const bool ok = a_ok && k < k1;
-            br_cp_async8(&As[buf][j][tid], Ap + (ok ? k : k0) * lda, ok);
+            for (int j = 0; j < BR_KT; ++j) {
+                const int64_t k = kb + j;
+                const bool ok = a_ok && k < k1;
+                br_cp_async8(&As[buf][j][tid], Ap + (ok ? k : k0) * lda, ok);
+            }
         }
 #pragma unroll
         for (int j = 0; j < BR_KT / 2; ++j) {
@@ -83,43 +84,64 @@ batch_reduce_gemm_kernel(const BrBatch P, int64_t K, int64_t k_per_split, double
         if (kb + BR_KT < k1) fetch(kb + BR_KT, buf ^ 1);
 #pragma unroll
         for (int kk = 0; kk < BR_KT; ++kk) {
-            double a[8], b[8];
+            double a[2 * RJ], b[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < RJ; ++j) {
                 const double2 v = *reinterpret_cast<const double2 *>(&As[buf][kk][2 * og + 32 * j]);
                 a[2 * j] = v.x;
                 a[2 * j + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
                 const double2 w = *reinterpret_cast<const double2 *>(&Bs[buf][kk][2 * ig + 16 * j]);
                 b[2 * j] = w.x;
                 b[2 * j + 1] = w.y;
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 2 * RJ; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
-        if (want_sums) {
+        if (want_sums && tid < MT) {
 #pragma unroll
             for (int kk = 0; kk < BR_KT; ++kk) csum += As[buf][kk][tid];
         }
     }
 
-    double *out = ws + ((size_t)tile * gridDim.x + blockIdx.x) * BR_TILE_DOUBLES;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 2 * RJ; ++i) {
         const int r = 2 * og + (i & 1) + 32 * (i >> 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             *reinterpret_cast<double2 *>(out + r * BR_NT + 2 * ig + 16 * j) = make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
     }
-    out[BR_MT * BR_NT + tid] = csum;
+    if (tid < MT) out[BR_MT * BR_NT + tid] = csum;
 }
 
-// C (+)= sum over the S partial tiles, in slice order; eight CTAs per tile.
+// MT_MAX = 128: tiles of either height in one launch, two CTAs per SM; MT_MAX = 64: every tile has <= 64 rows, three CTAs per SM.
+template <int MT_MAX>
+__global__ void __launch_bounds__(BR_THREADS, MT_MAX == 128 ? 2 : 3)
+batch_reduce_gemm_kernel(const BrBatch P, int n_tiles, int64_t K, double *__restrict__ ws) {
+    __shared__ __align__(16) double As[2][BR_KT][BR_MT];
+    __shared__ __align__(16) double Bs[2][BR_KT][BR_NT];
+    int tile = 0;
+    while (tile + 1 < n_tiles && (int)blockIdx.x >= P.first[tile + 1]) ++tile;
+    const int S = P.first[tile + 1] - P.first[tile], split = (int)blockIdx.x - P.first[tile];
+    const int64_t kps = ((K + S - 1) / S + BR_KT - 1) / BR_KT * BR_KT;
+    const int64_t k0 = split * kps, k1 = min(K, k0 + kps);
+    double *out = ws + (size_t)blockIdx.x * BR_TILE_DOUBLES;
+    if (MT_MAX == 64 || P.t[tile].M <= 64)
+        br_slice<64>(P.t[tile], k0, k1, As, Bs, out);
+    else
+        br_slice<128>(P.t[tile], k0, k1, As, Bs, out);
+}
+
+// C (+)= sum over the partial tiles of the K slices, in slice order; eight CTAs per tile.
 __global__ void __launch_bounds__(256)
-batch_reduce_finish_kernel(const BrBatch P, int S, int accumulate, const double *__restrict__ ws) {
+batch_reduce_finish_kernel(const BrBatch P, int accumulate, const double *__restrict__ ws) {
     const BrTile T = P.t[blockIdx.y];
-    const double *base = ws + (size_t)blockIdx.y * S * BR_TILE_DOUBLES;
+    const int S = P.first[blockIdx.y + 1] - P.first[blockIdx.y];
+    const double *base = ws + (size_t)P.first[blockIdx.y] * BR_TILE_DOUBLES;
     for (int e = blockIdx.x * 256 + threadIdx.x; e < BR_TILE_DOUBLES; e += gridDim.x * 256) {
         const bool is_sum = e >= BR_MT * BR_NT;
         const int r = is_sum ? e - BR_MT * BR_NT : e / BR_NT, c = is_sum ? 0 : e % BR_NT;
@@ -131,7 +153,14 @@ batch_reduce_finish_kernel(const BrBatch P, int S, int accumulate, const double 
     }
 }
 
-static int br_plan(const anqs_brg_problem_t *p, int n, int64_t K, std::vector<BrTile> &tiles, int &S, int64_t &k_per_split) {
+// Cuts the problems into tiles and the tiles into launches of <= BR_MAX_TILES; every launch is one wave: a 128-row tile
+// gets 3/2 of the K slices of a 64-row tile, so that all CTAs of the launch take about the same time.
+struct BrLaunch {
+    BrBatch b;
+    int n_tiles, n_ctas, all_half;
+};
+static int br_plan(const anqs_brg_problem_t *p, int n, int64_t K, std::vector<BrLaunch> &launches) {
+    std::vector<BrTile> tiles;
     for (int i = 0; i < n; ++i) {
         if (!(p[i].A && p[i].B && p[i].C && p[i].M > 0 && p[i].N > 0 && p[i].N <= BR_NT && p[i].lda >= p[i].M && p[i].ldb >= p[i].N &&
               p[i].ldc >= p[i].N))
@@ -147,12 +176,33 @@ static int br_plan(const anqs_brg_problem_t *p, int n, int64_t K, std::vector<Br
             tiles.push_back(t);
         }
     }
-    const int64_t want = 2 * (int64_t)sm_count_of_current_device() / (int64_t)tiles.size();   // one wave of two CTAs per SM
+    const int sms = sm_count_of_current_device();
     const int64_t most = std::max<int64_t>(1, K / (4 * BR_KT));   // at least four K tiles per CTA
-    S = (int)std::max<int64_t>(1, std::min(want, most));
-    k_per_split = ((K + S - 1) / S + BR_KT - 1) / BR_KT * BR_KT;
-    S = (int)((K + k_per_split - 1) / k_per_split);
+    for (size_t t0 = 0; t0 < tiles.size(); t0 += BR_MAX_TILES) {
+        BrLaunch L;
+        L.n_tiles = (int)std::min<size_t>(BR_MAX_TILES, tiles.size() - t0);
+        int units = 0, n_half = 0;   // measured cost of a K row: 64-row tile : 128-row tile = 2 : 3 (same fixed work per K tile)
+        for (int i = 0; i < L.n_tiles; ++i) {
+            units += tiles[t0 + i].M <= 64 ? 2 : 3;
+            n_half += tiles[t0 + i].M <= 64;
+        }
+        L.all_half = n_half == L.n_tiles;
+        const int64_t slots = (int64_t)sms * (L.all_half ? 3 : 2);
+        L.b.first[0] = 0;
+        for (int i = 0; i < L.n_tiles; ++i) {
+            L.b.t[i] = tiles[t0 + i];
+            const int64_t s = std::max<int64_t>(1, std::min(most, (tiles[t0 + i].M <= 64 ? 2 : 3) * slots / units));
+            L.b.first[i + 1] = L.b.first[i] + (int)s;
+        }
+        L.n_ctas = L.b.first[L.n_tiles];
+        launches.push_back(L);
+    }
     return 0;
+}
+static int64_t br_workspace(const std::vector<BrLaunch> &launches) {
+    int64_t ctas = 0;
+    for (const BrLaunch &L : launches) ctas += L.n_ctas;
+    return ctas * BR_TILE_DOUBLES * (int64_t)sizeof(double);
 }
 
 }  // namespace anqs
@@ -161,30 +211,26 @@ using namespace anqs;
 
 extern "C" int64_t anqs_batch_reduce_workspace(const anqs_brg_problem_t *problems, int n_problems, int64_t K) {
     if (!problems || n_problems <= 0 || K <= 0) return 0;
-    std::vector<BrTile> tiles;
-    int S;
-    int64_t kps;
-    if (br_plan(problems, n_problems, K, tiles, S, kps)) return -1;
-    return (int64_t)tiles.size() * S * BR_TILE_DOUBLES * (int64_t)sizeof(double);
+    std::vector<BrLaunch> launches;
+    if (br_plan(problems, n_problems, K, launches)) return -1;
+    return br_workspace(launches);
 }
 
 extern "C" int anqs_batch_reduce_gemm(const anqs_brg_problem_t *problems, int n_problems, int64_t K, int accumulate, void *workspace,
                                       int64_t workspace_bytes, void *stream) {
     ANQS_REQUIRE(problems && n_problems > 0, "no problems");
     ANQS_REQUIRE(K > 0, "empty batch");
-    std::vector<BrTile> tiles;
-    int S;
-    int64_t kps;
-    ANQS_REQUIRE(br_plan(problems, n_problems, K, tiles, S, kps) == 0, "bad problem (null pointer, N > 64 or leading dimension too small)");
-    ANQS_REQUIRE(workspace && workspace_bytes >= (int64_t)tiles.size() * S * BR_TILE_DOUBLES * (int64_t)sizeof(double), "workspace too small");
+    std::vector<BrLaunch> launches;
+    ANQS_REQUIRE(br_plan(problems, n_problems, K, launches) == 0, "bad problem (null pointer, N > 64 or leading dimension too small)");
+    ANQS_REQUIRE(workspace && workspace_bytes >= br_workspace(launches), "workspace too small");
     double *ws = (double *)workspace;
-    for (size_t t0 = 0; t0 < tiles.size(); t0 += BR_MAX_TILES) {
-        const int nt = (int)std::min<size_t>(BR_MAX_TILES, tiles.size() - t0);
-        BrBatch b;
-        for (int i = 0; i < nt; ++i) b.t[i] = tiles[t0 + i];
-        double *w = ws + t0 * S * BR_TILE_DOUBLES;
-        batch_reduce_gemm_kernel<<<dim3(S, nt), BR_THREADS, 0, (cudaStream_t)stream>>>(b, K, kps, w);
-        batch_reduce_finish_kernel<<<dim3(8, nt), 256, 0, (cudaStream_t)stream>>>(b, S, accumulate, w);
+    for (const BrLaunch &L : launches) {
+        if (L.all_half)
+            batch_reduce_gemm_kernel<64><<<L.n_ctas, BR_THREADS, 0, (cudaStream_t)stream>>>(L.b, L.n_tiles, K, ws);
+        else
+            batch_reduce_gemm_kernel<128><<<L.n_ctas, BR_THREADS, 0, (cudaStream_t)stream>>>(L.b, L.n_tiles, K, ws);
+        batch_reduce_finish_kernel<<<dim3(8, L.n_tiles), 256, 0, (cudaStream_t)stream>>>(L.b, accumulate, ws);
+        ws += (size_t)L.n_ctas * BR_TILE_DOUBLES;
     }
     ANQS_CUDA(cudaGetLastError());
     return 0;
