@@ -81,18 +81,31 @@ made_backward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_i
                 for (int q = 0; q < Q; ++q) {
                     const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start;
                     __syncthreads();  // the previous GEMM is done with act / wt
-                    for (int e = tid; e < 64 * 64; e += MD_THREADS) {
-                        const int s = e >> 6, d = e & 63;
-                        double v = 0.0;
-                        if (d < DM && base + s < B) {
-                            const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
-                            const double p = __ldg(save_p + ((size_t)(base + s) * Q + q) * DM + d);
-                            v = s_g[s].x * ((d == chosen ? 1.0 : 0.0) - p);
-                            dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = v;
+                    // A warp moves 4 samples x 8 outcomes at a time (full 64-byte runs of save_p / dY; the transposed stores hit
+                    // (4 d + s) mod 16 = every bank pair twice), all sixteen loads of a thread in flight before the first use.
+                    {
+                        const int lane = tid & 31, warp = tid >> 5, dq = lane & 7, sq = lane >> 3;
+                        double pv[16], wv[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int t = warp + 8 * i, s = (t >> 3) * 4 + sq, d = (t & 7) * 8 + dq;
+                            pv[i] = (d < DM && base + s < B) ? __ldg(save_p + ((size_t)(base + s) * Q + q) * DM + d) : 0.0;
+                            const int e = tid + MD_THREADS * i, dd = e >> 6, j = e & 63;  // wt[d][j] = W[(q DM + d)][j], as the rows lie
+                            wv[i] = dd < DM ? __ldg(Ws[depth] + ((size_t)q * DM + dd) * MD_W + j) : 0.0;
                         }
-                        act[d * MD_S + s] = v;
-                        const int dd = e >> 6, j = e & 63;  // weight rows of this qudit, as they lie: wt[d][j] = W[(q DM + d)][j]
-                        wt[dd * MD_S + j] = dd < DM ? __ldg(Ws[depth] + ((size_t)q * DM + dd) * MD_W + j) : 0.0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int t = warp + 8 * i, s = (t >> 3) * 4 + sq, d = (t & 7) * 8 + dq;
+                            double v = 0.0;
+                            if (d < DM && base + s < B) {
+                                const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
+                                v = s_g[s].x * ((d == chosen ? 1.0 : 0.0) - pv[i]);
+                                dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = v;
+                            }
+                            act[d * MD_S + s] = v;
+                            const int e = tid + MD_THREADS * i;
+                            wt[(e >> 6) * MD_S + (e & 63)] = wv[i];
+                        }
                     }
                     __syncthreads();
                     gemm_tile_acc(act, wt, DM, tx, ty, dh);
@@ -205,19 +218,30 @@ nade_backward_kernel(const anqs_nade_desc_t P, const int64_t *__restrict__ idx_i
 #pragma unroll
                     for (int b = 0; b < 4; ++b) dh[a][b] = 0.0;
                 __syncthreads();  // the previous GEMM is done with act / wt
-                for (int e = tid; e < 64 * 64; e += MD_THREADS) {
-                    const int s = e >> 6, d = e & 63;
-                    double v = 0.0;
-                    if (d < DM && base + s < B) {
-                        const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
-                        if (d < D)
-                            v = net == 0 ? s_g[s].x * ((d == chosen ? 1.0 : 0.0) - __ldg(save_p + ((size_t)(base + s) * Q + q) * DM + d))
-                                         : (d == chosen ? PI * s_g[s].y : 0.0);
-                        dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = v;
+                {   // same staging as made_backward_kernel: 4 samples x 8 outcomes per warp step, loads first
+                    const int lane = tid & 31, warp = tid >> 5, dq = lane & 7, sq = lane >> 3;
+                    double pv[16], wv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int t = warp + 8 * i, s = (t >> 3) * 4 + sq, d = (t & 7) * 8 + dq;
+                        pv[i] = (net == 0 && d < D && base + s < B) ? __ldg(save_p + ((size_t)(base + s) * Q + q) * DM + d) : 0.0;
+                        const int e = tid + MD_THREADS * i, dd = e >> 6, j = e & 63;
+                        wv[i] = dd < D ? __ldg(W_out + (size_t)dd * MD_W + j) : 0.0;
                     }
-                    act[d * MD_S + s] = v;
-                    const int dd = e >> 6, j = e & 63;
-                    wt[dd * MD_S + j] = dd < D ? __ldg(W_out + (size_t)dd * MD_W + j) : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int t = warp + 8 * i, s = (t >> 3) * 4 + sq, d = (t & 7) * 8 + dq;
+                        double v = 0.0;
+                        if (d < DM && base + s < B) {
+                            const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
+                            if (d < D)
+                                v = net == 0 ? s_g[s].x * ((d == chosen ? 1.0 : 0.0) - pv[i]) : (d == chosen ? PI * s_g[s].y : 0.0);
+                            dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = v;
+                        }
+                        act[d * MD_S + s] = v;
+                        const int e = tid + MD_THREADS * i;
+                        wt[(e >> 6) * MD_S + (e & 63)] = wv[i];
+                    }
                 }
                 __syncthreads();
                 gemm_tile_acc(act, wt, D, tx, ty, dh);
