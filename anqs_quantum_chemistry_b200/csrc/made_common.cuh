@@ -37,10 +37,17 @@ __device__ __forceinline__ long long memo_index(const anqs_made_desc_t &P, uint6
 __device__ __forceinline__ void load_weights_t(double *wt, const double *__restrict__ W, int row0, int rows, int K) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kq = lane & 3, jo = lane >> 2;
-    const int steps = 8 * ((K + 3) >> 2);
-    for (int t = warp; t < steps; t += MD_THREADS / 32) {
-        const int j = (t & 7) * 8 + jo, k = (t >> 3) * 4 + kq;
-        if (k < K) wt[k * MD_S + j] = j < rows ? __ldg(W + (size_t)(row0 + j) * K + k) : 0.0;
+    // K <= 64: at most 16 steps per warp; all loads of a thread are issued before the first store
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int t = warp + (MD_THREADS / 32) * i, j = (t & 7) * 8 + jo, k = (t >> 3) * 4 + kq;
+        v[i] = (k < K && j < rows) ? __ldg(W + (size_t)(row0 + j) * K + k) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int t = warp + (MD_THREADS / 32) * i, j = (t & 7) * 8 + jo, k = (t >> 3) * 4 + kq;
+        if (k < K) wt[k * MD_S + j] = v[i];
     }
 }
 
