@@ -57,3 +57,4 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(5): one_iter(False)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=25, max_name_column_width=60))
+print(prof.key_averages().table(sort_by='self_cpu_time_total', row_limit=30, max_name_column_width=60))
