@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(K4_WARPS * 32)
 split_level_kernel(const double *__restrict__ cond, int DM, int k, const double *__restrict__ counts,
                    const int32_t *__restrict__ memo_idx, const unsigned long long *__restrict__ cont_mask_q,
                    int64_t memo_size, int64_t B, int level, int draw_mode, uint64_t seed, int64_t parent_offset,
-                   const int64_t *__restrict__ rng_keys, double *__restrict__ child_counts, int64_t *__restrict__ n_children) {
+                   const int64_t *__restrict__ rng_keys, double *__restrict__ child_counts, int64_t *__restrict__ n_children,
+                   signed char *__restrict__ single_out) {
     __shared__ double cum_all[K4_WARPS][66];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *cum = cum_all[warp];
@@ -125,13 +126,16 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
         const double mx = warp_max(fmax(l0, l1));
         double e0 = lane < D ? exp(l0 - mx) : 0.0, e1 = lane + 32 < D ? exp(l1 - mx) : 0.0;
         if (!(mx > -INFINITY)) e0 = e1 = 0.0;
-        const double sum = warp_sum(e0 + e1);
-        double p0 = e0 / sum, p1 = e1 / sum;
-        if (!(sum > 0.0)) p0 = p1 = 0.0;
-        __syncwarp();
-        cum[1 + lane] = p0;
-        cum[33 + lane] = p1;
-        __syncwarp();
+        double p0 = e0, p1 = e1;   // random mode: unnormalised weights do (every use below is a ratio of partial sums)
+        if (draw_mode == 0) {
+            const double sum = warp_sum(e0 + e1);
+            p0 = e0 / sum, p1 = e1 / sum;
+            if (!(sum > 0.0)) p0 = p1 = 0.0;
+            __syncwarp();
+            cum[1 + lane] = p0;
+            cum[33 + lane] = p1;
+            __syncwarp();
+        }
         double cnt = counts[b];  // count of tree node `lane` (valid for lane < 2^j in round j)
         double c_even = 0.0, c_odd = 0.0;
         if (draw_mode == 0) {
@@ -151,6 +155,7 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
                 if (lane >= d) s0 += t0, s1 += t1;
             }
             s1 += __shfl_sync(0xffffffffu, s0, 31);
+            __syncwarp();
             cum[1 + lane] = s0;
             cum[33 + lane] = s1;
             if (lane == 0) cum[0] = 0.0;
@@ -209,11 +214,17 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
         if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];
         const bool s_even = lane < half && ((mw >> (2 * lane)) & 1ull) && c_even > 0.0;
         const bool s_odd = lane < half && ((mw >> (2 * lane + 1)) & 1ull) && c_odd > 0.0;
-        if (lane < half) {
-            child_counts[b * D + 2 * lane] = c_even;
-            child_counts[b * D + 2 * lane + 1] = c_odd;
-        }
         const unsigned be = __ballot_sync(0xffffffffu, s_even), bo = __ballot_sync(0xffffffffu, s_odd);
+        if (single_out != nullptr && single) {
+            // the one child (or none, when the symmetry table forbids it) goes out as a byte: no dense row for this parent
+            if (lane == 0) single_out[b] = be ? (signed char)(2 * (__ffs(be) - 1)) : bo ? (signed char)(2 * (__ffs(bo) - 1) + 1) : (signed char)-1;
+        } else {
+            if (lane < half) {
+                child_counts[b * D + 2 * lane] = c_even;
+                child_counts[b * D + 2 * lane + 1] = c_odd;
+            }
+            if (single_out != nullptr && lane == 0) single_out[b] = (signed char)-2;
+        }
         if (lane == 0) n_children[b] = __popc(be) + __popc(bo);
     }
 }
@@ -222,13 +233,25 @@ __global__ void __launch_bounds__(K4_WARPS * 32)
 emit_children_kernel(const double *__restrict__ child_counts, int k, int start, const int64_t *__restrict__ prefix,
                      const int32_t *__restrict__ memo_idx, const unsigned long long *__restrict__ cont_mask_q,
                      const int32_t *__restrict__ next_memo_q, int64_t memo_size, int64_t B,
-                     const int64_t *__restrict__ offsets, int64_t *__restrict__ out_prefix,
-                     double *__restrict__ out_counts, int32_t *__restrict__ out_memo) {
+                     const int64_t *__restrict__ offsets, const signed char *__restrict__ single_in,
+                     int64_t *__restrict__ out_prefix, double *__restrict__ out_counts, int32_t *__restrict__ out_memo) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = lanemask_lt();
     const int D = 1 << k, half = D >> 1;
     for (int64_t b = (int64_t)blockIdx.x * K4_WARPS + warp; b < B; b += (int64_t)gridDim.x * K4_WARPS) {
         const int mi = memo_idx[b];
+        if (single_in != nullptr) {
+            const int sd = single_in[b];
+            if (sd != -2) {   // single-sample parent: the split already named its child
+                if (sd >= 0 && lane == 0) {
+                    const int64_t r = offsets[b];
+                    out_prefix[r] = (int64_t)((uint64_t)prefix[b] | ((uint64_t)sd << start));
+                    out_counts[r] = 1.0;
+                    out_memo[r] = next_memo_q[(size_t)mi * D + sd];
+                }
+                continue;
+            }
+        }
         unsigned long long mw = 0ull;
         if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];
         double c_even = 0.0, c_odd = 0.0;
@@ -360,7 +383,7 @@ extern "C" {
 int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits_in_qudit, const double *d_counts,
                              const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n,
                              int level, int draw_mode, uint64_t seed, int64_t parent_offset, const int64_t *d_rng_keys,
-                             double *d_child_counts, int64_t *d_n_children, void *stream) {
+                             double *d_child_counts, int64_t *d_n_children, int8_t *d_single, void *stream) {
     ANQS_REQUIRE(n >= 0, "negative parent count");
     ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6 && (1 << qubits_in_qudit) <= max_qudit_dim && max_qudit_dim <= 64,
                  "qudit must have 1..6 qubits and fit max_qudit_dim <= 64");
@@ -370,7 +393,7 @@ int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits
     int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
     split_level_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d_cond, max_qudit_dim, qubits_in_qudit, d_counts, d_memo_idx, (const unsigned long long *)d_cont_mask_q, memo_size, n,
-        level, draw_mode, seed, parent_offset, d_rng_keys, d_child_counts, d_n_children);
+        level, draw_mode, seed, parent_offset, d_rng_keys, d_child_counts, d_n_children, (signed char *)d_single);
     ANQS_LAUNCH_CHECK();
     return 0;
 }
@@ -378,7 +401,8 @@ int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits
 int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit, int qudit_start,
                                const int64_t *d_prefix, const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q,
                                const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,
-                               int64_t *d_out_prefix, double *d_out_counts, int32_t *d_out_memo_idx, void *stream) {
+                               const int8_t *d_single, int64_t *d_out_prefix, double *d_out_counts, int32_t *d_out_memo_idx,
+                               void *stream) {
     ANQS_REQUIRE(n >= 0, "negative parent count");
     ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6, "qudit must have 1..6 qubits");
     ANQS_REQUIRE(qudit_start >= 0 && qudit_start + qubits_in_qudit <= 64, "qudit outside the 64-bit word");
@@ -388,7 +412,7 @@ int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit
     int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
     emit_children_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d_child_counts, qubits_in_qudit, qudit_start, d_prefix, d_memo_idx, (const unsigned long long *)d_cont_mask_q,
-        d_next_memo_q, memo_size, n, d_offsets, d_out_prefix, d_out_counts, d_out_memo_idx);
+        d_next_memo_q, memo_size, n, d_offsets, (const signed char *)d_single, d_out_prefix, d_out_counts, d_out_memo_idx);
     ANQS_LAUNCH_CHECK();
     return 0;
 }

@@ -81,9 +81,10 @@ class AutoregressiveSamplerMixin:
         cond = self.cond_log_abs(qudit_idx=q, prefix_idx=prefix)
         child = pt.empty((B, D), dtype=pt.float64, device=dev)
         n_child = pt.empty(B, dtype=pt.int64, device=dev)
+        single = pt.empty(B, dtype=pt.int8, device=dev)   # single-sample parents hand their child over as one byte
         _lib.check(lib.anqs_sampler_split_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(counts), _lib.dptr(memo),
                                                 _lib.dptr(cont_q), self.masker.memo_size, B, q, mode, seed, 0, _lib.dptr(prefix),
-                                                _lib.dptr(child), _lib.dptr(n_child), sp))
+                                                _lib.dptr(child), _lib.dptr(n_child), _lib.dptr(single), sp))
         offsets = pt.empty(B + 1, dtype=pt.int64, device=dev)
         work = pt.empty(max(1, int(lib.anqs_scan_workspace(B)) // 8), dtype=pt.int64, device=dev)
         _lib.check(lib.anqs_exclusive_scan_i64(_lib.dptr(n_child), _lib.dptr(offsets), B, _lib.dptr(work), sp))
@@ -94,7 +95,7 @@ class AutoregressiveSamplerMixin:
         if total > 0:
             _lib.check(lib.anqs_sampler_emit_children(_lib.dptr(child), k, qg.qudit_starts[q], _lib.dptr(prefix), _lib.dptr(memo),
                                                       _lib.dptr(cont_q), _lib.dptr(next_q), self.masker.memo_size, B,
-                                                      _lib.dptr(offsets), _lib.dptr(new_prefix), _lib.dptr(new_counts),
+                                                      _lib.dptr(offsets), _lib.dptr(single), _lib.dptr(new_prefix), _lib.dptr(new_counts),
                                                       _lib.dptr(new_memo), sp))
         return new_prefix, new_counts, new_memo
 

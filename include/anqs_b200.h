@@ -304,16 +304,20 @@ int anqs_transformer_cond_log_abs_tc(const anqs_transformer_desc_t *desc, const 
  *         draw_mode 1: Philox4x32-10 binomial variates keyed by (seed; key_i, level, round, node) with key_i =
  *         d_rng_keys[i] when given (pass the packed prefixes: the draws then do not depend on how the nodes of a level are
  *         split over launches, ranks or GPUs) else parent_offset + i.
+ *         d_single (optional, int8[n]): a parent that carries one sample in draw_mode 1 then gets its child as a byte
+ *         (outcome, or -1 when the symmetry table forbids it) INSTEAD of a row of d_child_counts; all other parents get -2
+ *         and their dense row.  Pass the same array to emit.  NULL: every parent gets its dense row.
  * emit:   writes the surviving children in (parent, outcome) order at d_offsets[i] (exclusive scan of
  *         d_n_children): prefix | outcome << qudit_start, count, next memo index (QG:99-108 tables as int32). */
 int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits_in_qudit, const double *d_counts,
                              const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n,
                              int level, int draw_mode, uint64_t seed, int64_t parent_offset, const int64_t *d_rng_keys,
-                             double *d_child_counts, int64_t *d_n_children, void *stream);
+                             double *d_child_counts, int64_t *d_n_children, int8_t *d_single, void *stream);
 int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit, int qudit_start,
                                const int64_t *d_prefix, const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q,
                                const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,
-                               int64_t *d_out_prefix, double *d_out_counts, int32_t *d_out_memo_idx, void *stream);
+                               const int8_t *d_single, int64_t *d_out_prefix, double *d_out_counts, int32_t *d_out_memo_idx,
+                               void *stream);
 
 /* ---- A12  one level of Gumbel top-k (stochastic beam) sampling (ANQS:676-688, 718-731) -----------------
  * d_out_log_prob[i][D] = d_parent_log_prob[i] + 2*d_cond[i][:D]; d_out_gumbel[i][D] = Gumbel(log_prob)

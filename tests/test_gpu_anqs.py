@@ -405,8 +405,20 @@ def test_split_level_draws_follow_the_conditional_distribution(count):
     child = torch.empty((B, D), dtype=torch.float64, device=dev)
     n_child = torch.empty(B, dtype=torch.int64, device=dev)
     _lib.check(_lib.lib().anqs_sampler_split_level(_lib.dptr(cond), D, 6, _lib.dptr(counts), _lib.dptr(memo), _lib.dptr(cont), 1, B,
-                                                   3, 1, 99, 0, _lib.dptr(keys), _lib.dptr(child), _lib.dptr(n_child),
+                                                   3, 1, 99, 0, _lib.dptr(keys), _lib.dptr(child), _lib.dptr(n_child), _lib.dptr(None),
                                                    _lib.stream_ptr(dev)))
+    # the byte path for single-sample parents names the same child as the dense row (and leaves the dense rows of others alone)
+    child2 = torch.full((B, D), -5.0, dtype=torch.float64, device=dev)
+    n_child2 = torch.empty(B, dtype=torch.int64, device=dev)
+    single = torch.empty(B, dtype=torch.int8, device=dev)
+    _lib.check(_lib.lib().anqs_sampler_split_level(_lib.dptr(cond), D, 6, _lib.dptr(counts), _lib.dptr(memo), _lib.dptr(cont), 1, B,
+                                                   3, 1, 99, 0, _lib.dptr(keys), _lib.dptr(child2), _lib.dptr(n_child2), _lib.dptr(single),
+                                                   _lib.stream_ptr(dev)))
+    assert torch.equal(n_child, n_child2)
+    if count == 1.0:
+        assert torch.equal(single.long(), child.argmax(1)) and bool((child2 == -5.0).all())
+    else:
+        assert bool((single == -2).all()) and torch.equal(child, child2)
     child = child.cpu()
     assert bool((child.sum(1) == count).all())                      # every parent's samples are conserved
     assert bool((child == child.round()).all()) and bool((child >= 0).all())
