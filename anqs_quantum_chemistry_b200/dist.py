@@ -26,12 +26,24 @@ def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None, sizes=None):
+def group_world_size(group=None, world_size: int = None) -> int:
+    """Number of ranks a collective of this module spans.  An explicit `world_size` wins over the process group: a caller that
+    runs on ONE rank inside an initialised multi-rank job (rank-0-only diagnostics, a single-GPU side computation) passes
+    world_size=1 and no collective is issued - a collective entered by one rank alone blocks until the NCCL watchdog aborts."""
+    if world_size is not None:
+        assert world_size == 1 or (dist.is_initialized() and world_size == dist.get_world_size(group)), \
+            'world_size must be 1 (local mode) or the size of the process group'
+        return int(world_size)
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None, sizes=None, world_size: int = None):
     """Concatenation over ranks (in rank order) of the per-rank shards.
     Returns (global_idx [N] int64, global_amps [N] complex128, lo, hi) with [lo, hi) this rank's rows.
     `sizes` (shard length of every rank, identical on all ranks) skips the size exchange and its host
-    synchronisation; equal shards are gathered straight into the result with no staging copies."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    synchronisation; equal shards are gathered straight into the result with no staging copies.
+    world_size=1 forces the local (no collective) mode, see group_world_size."""
+    world = group_world_size(group, world_size)
     local_idx = local_idx.contiguous().view(-1)
     local_amps = local_amps.contiguous().view(-1)
     if world == 1:
@@ -76,11 +88,11 @@ def local_energy_stats(eloc: pt.Tensor, amps: pt.Tensor) -> pt.Tensor:
     return pt.stack((w.sum(), we.real.sum(), we.imag.sum(), wee.real.sum(), wee.imag.sum()))
 
 
-def reduce_energy_stats(stats: pt.Tensor, group=None):
+def reduce_energy_stats(stats: pt.Tensor, group=None, world_size: int = None):
     """all_reduce of the packed sums, then MonteCarloEstimator semantics with theoretical frequencies
     f = |psi|^2 / sum |psi|^2 (compute_local_energies.py:48-62, 107-113):
     mean = sum f E,  var = sum f (E - mean)^2 = sum f E^2 - mean^2 (complex square, as in the reference)."""
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
+    if group_world_size(group, world_size) > 1:
         dist.all_reduce(stats, group=group)
     norm = stats[0]
     mean = pt.complex(stats[1], stats[2]) / norm
@@ -91,8 +103,9 @@ def reduce_energy_stats(stats: pt.Tensor, group=None):
 class ShardedLocalEnergy:
     """Sample-aware local energies of a batch that is sharded over the ranks of `group`."""
 
-    def __init__(self, ham, alpha_num: int, beta_num: int, group=None, sizes=None):
+    def __init__(self, ham, alpha_num: int, beta_num: int, group=None, sizes=None, world_size: int = None):
         self.sizes = sizes
+        self.world_size = world_size
         self.ham = ham
         self.alpha_num = alpha_num
         self.beta_num = beta_num
@@ -107,12 +120,12 @@ class ShardedLocalEnergy:
     def stats(self, local_idx: pt.Tensor, local_amps: pt.Tensor):
         """As __call__, plus the global normalisation sum |psi|^2: (E_loc local, mean, var, norm)."""
         from .hilbert_space import SampleTable
-        g_idx, g_amps, lo, hi = all_gather_shards(local_idx, local_amps, self.group, self.sizes)
+        g_idx, g_amps, lo, hi = all_gather_shards(local_idx, local_amps, self.group, self.sizes, self.world_size)
         table = SampleTable(g_idx, g_amps)
         eloc, _, _ = self.ham.compute_var_local_energy_proxy(
             unq_batch_as_base_indices=g_idx.view(-1, 1), unq_batch_as_amps=g_amps, coupling_method='ham',
             alpha_num=self.alpha_num, beta_num=self.beta_num, row_start=lo, row_len=hi - lo, table=table)
-        mean, var, norm = reduce_energy_stats(local_energy_stats(eloc, g_amps[lo:hi]), self.group)
+        mean, var, norm = reduce_energy_stats(local_energy_stats(eloc, g_amps[lo:hi]), self.group, self.world_size)
         return eloc, mean, var, norm
 
 
@@ -126,8 +139,8 @@ class ShardedEnergyGradient:
     take the same optimiser step.  `local_energy` is a callable (local_idx, local_amps) -> (E_loc local, mean, var, norm)
     with global mean / var / norm, e.g. ShardedLocalEnergy(ham, n_alpha, n_beta).stats."""
 
-    def __init__(self, wf, local_energy, group=None):
-        self.wf, self.local_energy, self.group = wf, local_energy, group
+    def __init__(self, wf, local_energy, group=None, world_size: int = None):
+        self.wf, self.local_energy, self.group, self.world_size = wf, local_energy, group, world_size
 
     def __call__(self, local_idx: pt.Tensor):
         """Leaves the global gradient in p.grad of every parameter of wf; returns (mean, var, loss) over the global batch."""
@@ -143,7 +156,7 @@ class ShardedEnergyGradient:
         loss = 2 * (seed * pt.log(pt.conj(amps))).sum().real
         loss.backward()
         flat = pt.cat([(p.grad if p.grad is not None else pt.zeros_like(p)).reshape(-1) for p in params] + [loss.detach().reshape(1)])
-        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if group_world_size(self.group, self.world_size) > 1:
             dist.all_reduce(flat, group=self.group)
         off = 0
         for p in params:
@@ -165,6 +178,7 @@ def sharded_sample_stats(wf, sample_num: int, seed: int, world_size: int = None,
     same order (sub-trees of a contiguous slice stay contiguous).  With gather=True the (index, count) shards are
     all-gathered (one collective of 16 B per unique sample) and every rank returns the whole set; otherwise the local shard.
     world_size / rank default to the process group's (pass them explicitly to emulate ranks in one process)."""
+    explicit = world_size is not None
     if world_size is None:
         world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -180,7 +194,7 @@ def sharded_sample_stats(wf, sample_num: int, seed: int, world_size: int = None,
     if not sharded:  # the tree never got wide enough: every rank holds everything, keep a slice
         lo, hi = shard_bounds(prefix.shape[0], world_size, rank)
         prefix, counts = prefix[lo:hi].contiguous(), counts[lo:hi].contiguous()
-    if gather and world_size > 1 and dist.is_initialized():
+    if gather and world_size > 1 and dist.is_initialized() and (not explicit or world_size == dist.get_world_size(group)):
         g_idx, g_cnt, _, _ = all_gather_shards(prefix, pt.complex(counts, pt.zeros_like(counts)), group)
         return g_idx.view(-1, 1), g_cnt
     return prefix.view(-1, 1), counts.to(pt.complex128)

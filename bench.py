@@ -44,27 +44,31 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def ncu_pipes(n_unq, world):
-    """ALU-pipe and issue utilisation of the dominant kernel from the same committed ncu capture (None when not captured)."""
+def _ncu_record(kernel, size, world, key='n_unq_per_gpu'):
+    """The committed ncu capture of `kernel` at exactly this configuration (profiles/traffic.json), else None."""
     try:
-        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))['fused_eloc_bs_kernel']
-        if world == 1 and int(t['n_unq_per_gpu']) == int(n_unq):
-            return {'alu_pipe_busy': t['alu_pipe_busy'], 'issue_active': t['issue_active'], 'warp_instructions_per_row': t['warp_instructions'] / n_unq}
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))[kernel]
+        if world == 1 and int(t[key]) == int(size):
+            return t
     except Exception:
         pass
     return None
 
 
-def ncu_traffic(n_unq, world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture of
-    this exact configuration (profiles/traffic.json); None when the configuration was not captured."""
-    try:
-        t = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))['fused_eloc_bs_kernel']
-        if world == 1 and int(t['n_unq_per_gpu']) == int(n_unq):
-            return float(t['dram_bytes_read']) + float(t['dram_bytes_write'])
-    except Exception:
-        pass
-    return None
+def ncu_pipes(kernel, n_unq, world):
+    """ALU-pipe / issue utilisation and the warp-instruction count of one launch of the dominant kernel, from the ncu capture."""
+    t = _ncu_record(kernel, n_unq, world)
+    if t is None or 'warp_instructions' not in t:
+        return None
+    return {'alu_pipe_busy': t.get('alu_pipe_busy'), 'issue_active': t.get('issue_active'), 'warp_instructions': t['warp_instructions'],
+            'warp_instructions_per_row': t['warp_instructions'] / n_unq, 'source': t.get('source')}
+
+
+def ncu_traffic(kernel, size, world, key='n_unq_per_gpu'):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this exact
+    configuration (profiles/traffic.json); None when the configuration was not captured."""
+    t = _ncu_record(kernel, size, world, key)
+    return None if t is None else float(t['dram_bytes_read']) + float(t['dram_bytes_write'])
 
 
 class ClockSampler:
@@ -205,7 +209,8 @@ def vmc_iteration_c5(ham, wf, dev, n_el, sample_num=10 ** 6, iters=5):
     prec = wf.inference_precision
     wf.set_inference_precision('tf32')
     opt = torch.optim.Adam(wf.parameters(), lr=1e-3)
-    step = adist.ShardedEnergyGradient(wf, adist.ShardedLocalEnergy(ham, n_el // 2, n_el // 2).stats)
+    # world_size=1: this runs on one rank only and must never enter a collective (dist.group_world_size)
+    step = adist.ShardedEnergyGradient(wf, adist.ShardedLocalEnergy(ham, n_el // 2, n_el // 2, world_size=1).stats, world_size=1)
     n_unq = 0
 
     def one_iter(it):
@@ -339,52 +344,230 @@ def secondary_measurements(ham, hs, d_idx, na, nb, dev):
     return out
 
 
+def shared_config(args, world, terms, unique_xy_masks):
+    """The `config` object of the JSON line: identical for both arms (ours / reference), so the driver can match them."""
+    return {'workload': WORKLOAD, 'n_unq_per_gpu': args.n_unq, 'sampled_set': args.n_unq * world, 'terms': int(terms),
+            'unique_xy_masks': int(unique_xy_masks), 'mode': 'sample-aware local energies, coupling "ham" (PO:396-487)',
+            'l2': 'flushed between timed iterations (256 MiB write)', 'parallelism': f'dp{world} (rows sharded, table replicated)'}
+
+
+def cpu_reference_measurements(xy, yz, w, samples, amps, na, nb, rows, steps, warmup, budget_s=None):
+    """The CPU arm, shared by `--impl reference` and the `cpu_baseline` leg (rank 0, host cores only).
+
+    kind "reference": the UNMODIFIED reference (oracle/_ref, shipped by build()) through its own public call
+    PauliObservable.compute_var_local_energy_proxy on torch CPU threads = os.cpu_count(), coupling 'ham' (the algorithm the GPU
+    kernel implements; its cost per row does not depend on the size of the sampled set) and 'trie' (the reference's fastest
+    path on small sets; its cost per row grows with the set), each on a bounded sample: the first `rows` samples of the
+    workload are both the destination rows and the sampled set (the reference's call has no row window).
+    kind "port": the C/pthreads restatement (oracle/anqs_oracle.c) on `rows`-row windows against the FULL sampled set, the
+    {configuration -> position} map built ONCE (as the GPU arm builds its table once per batch).
+    Returns (value, per-step seconds of the headline method, cpu_baseline dict)."""
+    from oracle import hamiltonian_oracle as orc
+    from oracle import reference_arm
+    n_set = samples.shape[0]
+    rows = min(rows, n_set)
+    out = {'unit': 'E_loc/s', 'os_cpu_count': os.cpu_count()}
+    # ---- the C port: whole-set map built once, windows of `rows` rows
+    tab = orc.Tables(xy, yz, w)
+    t0 = time.perf_counter()
+    sset = orc.SampledSet(samples)
+    map_s = time.perf_counter() - t0
+    port_times = []
+    for it in range(warmup + steps):
+        lo = (it * rows) % max(1, n_set - rows + 1)
+        t0 = time.perf_counter()
+        orc.local_energy_sample_aware(samples, amps, tab, na, nb, row_start=lo, row_len=rows, sampled_set=sset)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            port_times.append(dt)
+        if budget_s is not None and sum(port_times) > budget_s / 3 and len(port_times) >= 2:
+            break
+    port_value = rows * len(port_times) / sum(port_times)
+    out['port'] = {'value': port_value, 'cores': orc.num_threads(), 'map_build_s_once': map_s,
+                   'sample': f'{len(port_times)} windows of {rows} destination rows against the full {n_set}-sample set (map built once), coupling "ham"'}
+    del sset
+    # ---- the reference itself
+    if reference_arm.reference_root() is None:
+        out.update({'value': port_value, 'cores': orc.num_threads(), 'kind': 'port', 'sample': out['port']['sample'],
+                    'reference_unavailable': 'oracle/_ref not shipped (run __graft_entry__.build() in the build container)'})
+        return port_value, port_times, out
+    import torch
+    arm = reference_arm.ReferenceLocalEnergy(xy, yz, w, QUBITS)
+    s_ref, a_ref = samples[:rows], amps[:rows]
+    ham_times, trie_times, e_ref = [], [], None
+    t_begin = time.perf_counter()
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        e_ref = arm(s_ref, a_ref, na, nb, 'ham')
+        t1 = time.perf_counter()
+        arm(s_ref, a_ref, na, nb, 'trie')
+        t2 = time.perf_counter()
+        if it >= warmup:
+            ham_times.append(t1 - t0)
+            trie_times.append(t2 - t1)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s and len(ham_times) >= 1:
+            break
+    arm.close()
+    e_port = orc.local_energy_sample_aware(s_ref, a_ref, tab, na, nb)
+    ham_v, trie_v = rows * len(ham_times) / sum(ham_times), rows * len(trie_times) / sum(trie_times)
+    out.update({'value': ham_v, 'cores': arm.threads, 'kind': 'reference', 'torch_num_threads': torch.get_num_threads(),
+                'method_of_value': 'ham', 'reference_ham': ham_v, 'reference_trie_on_this_sample': trie_v,
+                'max_abs_diff_reference_vs_port': float(np.abs(e_ref - e_port).max()),
+                'sample': f'{len(ham_times)} calls of the reference\'s compute_var_local_energy_proxy on the first {rows} samples of the workload '
+                          f'(rows = sampled set), coupling "ham" (= value: its cost per row does not depend on the size of the sampled set, so the '
+                          f'bounded sample is representative of the full {n_set}-sample workload) and "trie" (reported beside it: its cost per row '
+                          f'GROWS with the set - 14.1k / 7.5k / 3.7k E_loc/s at 1 024 / 8 192 / 65 536 samples on 8 threads in the build container - '
+                          f'so its figure on a {rows}-sample set overstates what it would reach on the full set)'})
+    return ham_v, ham_times, out
+
+
 def run_reference(args, rank, world):
-    """Reference arm: the reference is Python/PyTorch-CPU and cannot travel to the GPU box, so this times the
-    oracle port of its 'ham' local-energy path (oracle/anqs_oracle.c, all host threads) on a bounded sample."""
+    """Reference arm: rank 0 times the reference's own CPU implementation of the path on the box's host cores (see
+    cpu_reference_measurements); the other ranks exit without work."""
     if rank != 0:
         return
-    from oracle import hamiltonian_oracle as orc
     n_set = args.n_unq * args.gpus
     xy, yz, w, samples, amps = make_workload(n_set)
-    tab = orc.Tables(xy, yz, w)
-    rows = args.cpu_rows
     na = nb = ELECTRONS // 2
-    times = []
-    for it in range(args.warmup + args.steps):
-        lo = (it * rows) % max(1, n_set - rows)
-        t0 = time.perf_counter()
-        orc.local_energy_sample_aware(samples, amps, tab, na, nb, row_start=lo, row_len=rows)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
-    total = sum(times)
-    value = rows * len(times) / total
-    cores = orc.num_threads()
+    value, times, base = cpu_reference_measurements(xy, yz, w, samples, amps, na, nb, args.cpu_rows, args.steps, args.warmup)
+    U = int(np.unique(np.asarray(xy)).shape[0])
     line = {
         'impl': 'reference', 'metric': 'local_energies_per_sec', 'value': value, 'unit': 'E_loc/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True,
+        'steps': len(times), 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(times) / len(times), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'n_unq_per_gpu': args.n_unq, 'sampled_set': n_set, 'terms': int(tab.term_num),
-                   'unique_xy_masks': int(tab.unq_xy_masks_num)},
-        'cpu_baseline': {'value': value, 'unit': 'E_loc/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{rows} destination rows per step against the full {n_set}-sample table, coupling "ham"'},
+        'config': shared_config(args, args.gpus, len(w), U),
+        'cpu_baseline': base,
         'e2e': {'value': value, 'unit': 'E_loc/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def main():
+class DeviceClock:
+    """Marks on the launching stream (CUDA events); wall clock for the CPU stand-in engine of the gloo control-flow test."""
+
+    def __init__(self, dev):
+        import torch
+        self.torch, self.cuda = torch, dev.type == 'cuda'
+
+    def mark(self):
+        if self.cuda:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        return time.perf_counter()
+
+    def ms(self, a, b):
+        return a.elapsed_time(b) if self.cuda else (b - a) * 1e3
+
+    def sync(self):
+        if self.cuda:
+            self.torch.cuda.synchronize()
+
+
+class GpuEngine:
+    """Everything of the bench that touches the GPU.  tests/test_bench_flow.py swaps in a CPU stand-in with the same methods
+    to run main()'s control flow (collectives included) at world size 2 on gloo."""
+    backend = 'nccl'
+
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        from anqs_quantum_chemistry_b200 import HilbertSpace, PauliObservable, PauliArraysOperator, _lib
+        from anqs_quantum_chemistry_b200 import dist as adist
+        assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+        torch.cuda.set_device(local_rank)
+        self.torch, self.adist, self._lib = torch, adist, _lib
+        self.args, self.rank, self.world = args, rank, world
+        self.device = dev = torch.device('cuda', local_rank)
+        self.na = self.nb = ELECTRONS // 2
+
+    def setup(self):
+        """After init_process_group: workload, tables, resident inputs."""
+        torch, adist, _lib, args, world, rank, dev = self.torch, self.adist, self._lib, self.args, self.world, self.rank, self.device
+        from anqs_quantum_chemistry_b200 import HilbertSpace, PauliObservable, PauliArraysOperator
+        self.n_set = args.n_unq * world
+        self.xy, self.yz, self.w, self.samples, self.amps = make_workload(self.n_set)
+        self.tmp = tempfile.mkdtemp(prefix=f'anqs_bench_r{rank}_')
+        self.hs = HilbertSpace(qubit_num=QUBITS, device=dev, parent_dir=self.tmp, rng_seed=0)
+        self.ham = PauliObservable(hilbert_space=self.hs, of_qubit_operator=PauliArraysOperator(self.xy, self.yz, self.w, QUBITS))
+        self.lib, self.tables = _lib.lib(), self.ham.tables
+        self.U, self.T = self.ham.unq_xy_masks_num, self.ham.term_num
+        lo, hi = adist.shard_bounds(self.n_set, world, rank)
+        self.rows = hi - lo
+        self.shard_sizes = [adist.shard_bounds(self.n_set, world, r)[1] - adist.shard_bounds(self.n_set, world, r)[0] for r in range(world)]
+        self.h_idx = torch.from_numpy(self.samples.view(np.int64)[lo:hi].copy()).pin_memory()
+        self.h_amps = torch.from_numpy(self.amps[lo:hi].copy()).pin_memory()
+        self.d_idx, self.d_amps = self.h_idx.to(dev), self.h_amps.to(dev)
+        self.h_out = torch.empty(self.rows, dtype=torch.complex128).pin_memory()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        self.sle = adist.ShardedLocalEnergy(self.ham, self.na, self.nb, sizes=self.shard_sizes) if world > 1 else None
+        # which fused kernel the C ABI picks for this batch (k1_fused_bs.cu: >= 256 rows per SM and every spin part of weight <= 4)
+        self.kernel_name = ('fused_eloc_bs_kernel' if (self.rows + 31) // 32 >= 8 * torch.cuda.get_device_properties(dev).multi_processor_count
+                            else 'fused_eloc_kernel')
+        self.launches_per_step = 5  # filter_count, filter_overload, filter_pick_spread, hash_build (k2_hash.cu) + the fused kernel
+
+    def flush_l2(self):
+        self.flush.fill_(1)
+
+    def step(self, clock=None):
+        """One pass with the inputs resident: [all_gather] -> table build -> fused kernel on this rank's rows -> statistics
+        [all_reduce].  Returns (E_loc, mean, (mark before, mark after) the fused kernel or None)."""
+        torch, adist, _lib = self.torch, self.adist, self._lib
+        from anqs_quantum_chemistry_b200 import SampleTable
+        g_idx, g_amps, glo, ghi = adist.all_gather_shards(self.d_idx, self.d_amps, sizes=self.shard_sizes)
+        table = SampleTable(g_idx, g_amps)
+        eloc = torch.empty(ghi - glo, dtype=torch.complex128, device=self.device)
+        sp = _lib.stream_ptr(self.device)
+        m0 = clock.mark() if clock else None
+        _lib.check(self.lib.anqs_local_energy_sample_aware(self.tables, _lib.dptr(g_idx), _lib.dptr(torch.view_as_real(g_amps)), g_idx.shape[0],
+                                                           glo, ghi - glo, _lib.dptr(table.slots), table.capacity, self.na, self.nb,
+                                                           _lib.dptr(torch.view_as_real(eloc)), sp))
+        m1 = clock.mark() if clock else None
+        mean, var, _ = adist.reduce_energy_stats(adist.local_energy_stats(eloc, g_amps[glo:ghi]))
+        return eloc, mean, (m0, m1) if clock else None
+
+    def e2e_step(self):
+        """The same pass through the public API with HOST (pinned) inputs and the E_loc vector read back to the host."""
+        dev = self.device
+        idx_d = self.h_idx.to(dev, non_blocking=True)
+        amps_d = self.h_amps.to(dev, non_blocking=True)
+        if self.sle is not None:
+            e, m, v = self.sle(idx_d, amps_d)
+        else:
+            e, _, _ = self.ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=idx_d.view(-1, 1), unq_batch_as_amps=amps_d,
+                                                              coupling_method='ham', alpha_num=self.na, beta_num=self.nb)
+        self.h_out.copy_(e, non_blocking=True)
+
+    e2e_bytes = property(lambda self: (int(24 * self.rows), int(16 * self.rows)))
+
+    def conn_per_row(self):
+        torch, _lib = self.torch, self._lib
+        counts = torch.empty(min(self.rows, 1 << 16), dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.anqs_k1_filter(self.tables, _lib.dptr(self.d_idx), counts.shape[0], self.na, self.nb, _lib.dptr(counts), _lib.dptr(None),
+                                           _lib.stream_ptr(self.device)))
+        return float(counts.double().mean().item())
+
+    def extras_local(self):
+        """Rank 0 only, AFTER the process group is gone: the other kernels of the path on this GPU."""
+        return secondary_measurements(self.ham, self.hs, self.d_idx, self.na, self.nb, self.device)
+
+    def cpu_baseline(self):
+        return cpu_reference_measurements(self.xy, self.yz, self.w, self.samples, self.amps, self.na, self.nb, self.args.cpu_rows,
+                                          steps=3, warmup=0, budget_s=20.0)[2]
+
+
+def main(argv=None, engine_cls=GpuEngine):
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n-unq', type=int, default=1 << 20, help='unique samples (rows) per GPU')
-    ap.add_argument('--cpu-rows', type=int, default=4096, help='rows per CPU-baseline step')
+    ap.add_argument('--cpu-rows', type=int, default=2048, help='rows per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary kernel measurements')
-    args = ap.parse_args()
+    ap.add_argument('--extras-at-any-world', action='store_true',
+                    help='run the rank-0-only secondary measurements at world > 1 too (after the process group is destroyed; the other GPUs idle)')
+    args = ap.parse_args(argv)
     assert args.warmup >= 3 or args.impl == 'reference' or os.environ.get('ANQS_BENCH_ALLOW_SHORT'), 'need >= 3 warm-up steps'
 
     rank = int(os.environ.get('RANK', '0'))
@@ -394,169 +577,126 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import datetime
     import torch
     import torch.distributed as dist
-    from anqs_quantum_chemistry_b200 import HilbertSpace, PauliObservable, PauliArraysOperator, SampleTable, _lib
-    from anqs_quantum_chemistry_b200 import dist as adist
 
-    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run'
-
-    na = nb = ELECTRONS // 2
-    n_set = args.n_unq * world
-    xy, yz, w, samples, amps = make_workload(n_set)
-    tmp = tempfile.mkdtemp(prefix=f'anqs_bench_r{rank}_')
-    hs = HilbertSpace(qubit_num=QUBITS, device=dev, parent_dir=tmp, rng_seed=0)
-    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, QUBITS))
-    lib = _lib.lib()
-    tables = ham.tables
-    lo, hi = adist.shard_bounds(n_set, world, rank)
-    rows = hi - lo
-    shard_sizes = [adist.shard_bounds(n_set, world, r)[1] - adist.shard_bounds(n_set, world, r)[0] for r in range(world)]
-
-    h_idx = torch.from_numpy(samples.view(np.int64)[lo:hi].copy()).pin_memory()
-    h_amps = torch.from_numpy(amps[lo:hi].copy()).pin_memory()
-    d_idx = h_idx.to(dev)
-    d_amps = h_amps.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    kern_ms = []
-
-    def step(time_kernel=False):
-        g_idx, g_amps, glo, ghi = adist.all_gather_shards(d_idx, d_amps, sizes=shard_sizes)
-        table = SampleTable(g_idx, g_amps)
-        eloc = torch.empty(ghi - glo, dtype=torch.complex128, device=dev)
-        sp = _lib.stream_ptr(dev)
-        if time_kernel:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        _lib.check(lib.anqs_local_energy_sample_aware(tables, _lib.dptr(g_idx), _lib.dptr(torch.view_as_real(g_amps)), g_idx.shape[0],
-                                                      glo, ghi - glo, _lib.dptr(table.slots), table.capacity, na, nb,
-                                                      _lib.dptr(torch.view_as_real(eloc)), sp))
-        if time_kernel:
-            e1.record()
-            kern_ms.append((e0, e1))
-        mean, var, _ = adist.reduce_energy_stats(adist.local_energy_stats(eloc, g_amps[glo:ghi]))
-        return eloc, mean
+    eng = engine_cls(args, rank, local_rank, world)
+    dev = eng.device
+    if world > 1:
+        # a collective that one rank never enters must fail in minutes, not hang the node until the watchdog default
+        kw = {'device_id': dev} if dev.type == 'cuda' else {}
+        dist.init_process_group(eng.backend, timeout=datetime.timedelta(seconds=180), **kw)
+    eng.setup()
+    clock = DeviceClock(dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        clock.sync()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     clocks = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and dev.type == 'cuda':
         clocks.start()  # before the warm-up: it must be up and sampling, not starting, when the timed region begins
     for _ in range(args.warmup):
-        step()
+        eng.step()
     if rank == 0:
         clocks.wait_ready()
     barrier()
-    step_ms = []
+    step_ms, kern = [], []
     for _ in range(args.steps):
-        flush.fill_(1)  # evict L2 between timed iterations
+        eng.flush_l2()  # evict L2 between timed iterations
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        eloc, mean = step(time_kernel=True)
-        e1.record()
+        m0 = clock.mark()
+        eloc, mean, km = eng.step(clock)
+        m1 = clock.mark()
         barrier()
-        step_ms.append(e0.elapsed_time(e1))
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ms]))
+        step_ms.append(clock.ms(m0, m1))
+        kern.append(clock.ms(*km))
+    total_ms = max_over_ranks(sum(step_ms))
+    kernel_ms = float(np.mean(kern))
 
-    # end to end through the public API with host buffers (N=1 semantics per rank; shards gathered on device)
+    # end to end through the public API with host buffers (copies inside the timed region)
     e2e_ms = []
-    h_out = torch.empty(rows, dtype=torch.complex128).pin_memory()
     for it in range(args.warmup + args.steps):
-        flush.fill_(1)
+        eng.flush_l2()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        idx_d = h_idx.to(dev, non_blocking=True)
-        amps_d = h_amps.to(dev, non_blocking=True)
-        if world > 1:
-            sle = adist.ShardedLocalEnergy(ham, na, nb, sizes=shard_sizes)
-            e, m, v = sle(idx_d, amps_d)
-        else:
-            e, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=idx_d.view(-1, 1), unq_batch_as_amps=amps_d,
-                                                         coupling_method='ham', alpha_num=na, beta_num=nb)
-        h_out.copy_(e, non_blocking=True)
-        e1.record()
+        m0 = clock.mark()
+        eng.e2e_step()
+        m1 = clock.mark()
         barrier()
         if it >= args.warmup:
-            e2e_ms.append(e0.elapsed_time(e1))
-    e2e_total = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
-    e2e_total = float(e2e_total.item())
+            e2e_ms.append(clock.ms(m0, m1))
+    e2e_total = max_over_ranks(sum(e2e_ms))
     clock_info = clocks.stop() if rank == 0 else None
+    conn_per_row = eng.conn_per_row()
 
-    # algorithmic traffic of the dominant (fused) kernel: one 32-byte slot per probed candidate
-    counts = torch.empty(min(rows, 1 << 16), dtype=torch.int64, device=dev)
-    _lib.check(lib.anqs_k1_filter(tables, _lib.dptr(d_idx), counts.shape[0], na, nb, _lib.dptr(counts), _lib.dptr(None), _lib.stream_ptr(dev)))
-    conn_per_row = float(counts.double().mean().item())
-
-    extras = secondary_measurements(ham, hs, d_idx, na, nb, dev) if (rank == 0 and not args.no_extras) else None
-
-    # which fused kernel the C ABI picks for this batch (k1_fused_bs.cu: >= 256 rows per SM and every spin part of weight <= 4)
-    kernel_name = 'fused_eloc_bs_kernel' if (rows + 31) // 32 >= 8 * torch.cuda.get_device_properties(dev).multi_processor_count else 'fused_eloc_kernel'
-    if rank == 0:
-        peak, peak_src = load_peaks()
-        U, T = ham.unq_xy_masks_num, ham.term_num
-        m_probe = conn_per_row * rows
-        algo_bytes = 32.0 * m_probe + 24.0 * n_set + 16.0 * rows + 8.0 * U + 16.0 * T
-        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-        line = {
-            'metric': 'local_energies_per_sec', 'value': n_set * args.steps / (total_ms * 1e-3), 'unit': 'E_loc/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'n_unq_per_gpu': args.n_unq, 'sampled_set': n_set, 'terms': int(T), 'unique_xy_masks': int(U),
-                       'connections_per_sample': conn_per_row, 'mode': 'sample-aware (coupling "ham")',
-                       'l2': 'flushed between timed iterations (256 MiB write)', 'parallelism': f'dp{world} (rows sharded, table replicated)'},
-            'e2e': {'value': n_set * len(e2e_ms) / (e2e_total * 1e-3), 'unit': 'E_loc/s', 'h2d_bytes_per_step': int(24 * rows),
-                    'd2h_bytes_per_step': int(16 * rows)},
-            # our kernels per step: filter_count, filter_overload, filter_pick_spread, hash_build (k2_hash.cu) + the fused local-energy kernel
-            'gpu_launches': 5 * args.steps,
-            'step_ms_each': [round(v, 3) for v in step_ms],
-            'kernel': {'name': kernel_name, 'ms': kernel_ms, 'share_of_step': kernel_ms / (total_ms / args.steps),
-                       'filter_tests_per_s': rows * U / (kernel_ms * 1e-3), 'probes_per_s': m_probe / (kernel_ms * 1e-3)},
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(args.n_unq, world),
-                         'peak_source': peak_src, 'real_limiter': ncu_pipes(args.n_unq, world),
-                         'achieved_dram_gbs': (ncu_traffic(args.n_unq, world) or 0.0) / (kernel_ms * 1e-3) / 1e9,
-                         'algorithmic_bytes': '32 B per probed candidate + 24 B per table sample + 16 B per row + 8U + 16T',
-                         'note': 'probe bandwidth as SURVEY 8(d) defines it for the fused kernel (one notional 32-byte slot sector per probed candidate). The kernel '
-                                 'answers ~99.7 % of the probes from a 4-byte word of an L1/L2-resident presence filter, so its DRAM traffic (`traffic`) is ~1 % of '
-                                 'these bytes and the fraction can pass 1: the real limiter is instruction issue and L2->L1 latency (ncu: profiles/r1f_*). The '
-                                 'HBM-bound kernel of the path is the materialising enumeration, secondary.enumeration.frac_of_hbm_peak'},
-            'clocks': clock_info,
-        }
-        if extras is not None:
-            for v in extras.values():
-                if isinstance(v, dict) and 'achieved_gbs' in v:
-                    v['frac_of_hbm_peak'] = v['achieved_gbs'] / peak
-            line['secondary'] = extras
-        if not args.no_cpu_baseline:
-            from oracle import hamiltonian_oracle as orc
-            tab = orc.Tables(xy, yz, w)
-            t0 = time.perf_counter()
-            done = 0
-            while time.perf_counter() - t0 < 10.0:
-                orc.local_energy_sample_aware(samples, amps, tab, na, nb, row_start=done % max(1, n_set - args.cpu_rows), row_len=args.cpu_rows)
-                done += args.cpu_rows
-            dt = time.perf_counter() - t0
-            line['cpu_baseline'] = {'value': done / dt, 'unit': 'E_loc/s', 'cores': orc.num_threads(), 'kind': 'port',
-                                    'sample': f'{done} destination rows ({dt:.1f} s) against the same {n_set}-sample table and Hamiltonian'}
-        print(json.dumps(line), flush=True)
+    # ---- every collective of this program is above this line.  Rank-0-only work (secondary kernels, CPU baseline) must never
+    # run inside a live process group: a collective entered by one rank alone hangs until the watchdog aborts the job.
     if world > 1:
+        barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return
+    run_extras = not args.no_extras and (world == 1 or args.extras_at_any_world)
+    extras = eng.extras_local() if run_extras else None
+    peak, peak_src = load_peaks()
+    U, T, rows, n_set = eng.U, eng.T, eng.rows, eng.n_set
+    m_probe = conn_per_row * rows
+    algo_bytes = 32.0 * m_probe + 24.0 * n_set + 16.0 * rows + 8.0 * U + 16.0 * T
+    notional = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic, pipes = ncu_traffic(eng.kernel_name, args.n_unq, world), ncu_pipes(eng.kernel_name, args.n_unq, world)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == 'cuda' else 1
+    sm_mhz = (clock_info or {}).get('sm_mhz') or 1965.0
+    issue_peak = sm_count * 4 * sm_mhz * 1e6 / 1e9          # G warp-instructions / s: 4 schedulers per SM, one issue per clock each
+    roofline = {'bound': 'alu', 'unit': 'Gwarp-inst/s', 'peak': issue_peak, 'achieved': None, 'frac': None, 'traffic': traffic,
+                'peak_source': f'{sm_count} SMs x 4 issue slots/clk x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)',
+                'note': 'The dominant kernel answers ~99.7 % of its probes from an L1/L2-resident presence filter: its DRAM traffic (`traffic`) is ~0.4 % of the '
+                        'notional probe bytes, so it is bound by instruction issue, not by HBM.  achieved = warp instructions of one launch (ncu '
+                        'smsp__inst_executed.sum of this exact configuration, profiles/traffic.json; the count is a property of the workload) / the launch '
+                        'duration measured live.  hbm_notional keeps the probe-bandwidth figure SURVEY 8(d) defines (32 B per probed candidate).  The '
+                        'HBM-bound kernel of the path is the materialising enumeration: roofline_enumeration.'}
+    if pipes is not None:
+        roofline['achieved'] = pipes['warp_instructions'] / (kernel_ms * 1e-3) / 1e9
+        roofline['frac'] = roofline['achieved'] / issue_peak
+        roofline['ncu'] = pipes
+    roofline['hbm_notional'] = {'bound': 'hbm', 'achieved': notional, 'peak': peak, 'unit': 'GB/s', 'frac': notional / peak, 'peak_source': peak_src,
+                                'algorithmic_bytes': '32 B per probed candidate + 24 B per table sample + 16 B per row + 8U + 16T',
+                                'achieved_dram_gbs': (traffic or 0.0) / (kernel_ms * 1e-3) / 1e9}
+    h2d, d2h = eng.e2e_bytes
+    line = {
+        'metric': 'local_energies_per_sec', 'value': n_set * args.steps / (total_ms * 1e-3), 'unit': 'E_loc/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64+f64', 'data': 'synthetic',
+        'config': shared_config(args, world, T, U),
+        'e2e': {'value': n_set * len(e2e_ms) / (e2e_total * 1e-3), 'unit': 'E_loc/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': eng.launches_per_step * args.steps,
+        'step_ms_each': [round(v, 3) for v in step_ms],
+        'kernel': {'name': eng.kernel_name, 'ms': kernel_ms, 'share_of_step': kernel_ms / (total_ms / args.steps),
+                   'connections_per_sample': conn_per_row,
+                   'filter_tests_per_s': rows * U / (kernel_ms * 1e-3), 'probes_per_s': m_probe / (kernel_ms * 1e-3)},
+        'roofline': roofline,
+        'clocks': clock_info,
+    }
+    if extras is not None:
+        enum = extras.get('enumeration')
+        if enum is not None:
+            enum['frac_of_hbm_peak'] = enum['achieved_gbs'] / peak
+            line['roofline_enumeration'] = {'bound': 'hbm', 'achieved': enum['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
+                                            'frac': enum['achieved_gbs'] / peak, 'peak_source': peak_src,
+                                            'traffic': ncu_traffic('enum_emit_kernel', enum['rows'], 1, key='rows'),
+                                            'kernels': enum.get('kernels'), 'algorithmic_bytes': enum['algorithmic_bytes']}
+        line['secondary'] = extras
+    if not args.no_cpu_baseline and world == 1:
+        line['cpu_baseline'] = eng.cpu_baseline()
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == '__main__':

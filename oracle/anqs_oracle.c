@@ -244,6 +244,28 @@ static void le_rows(int64_t lo, int64_t hi, void *vc) {
         c->eloc[2 * i + 1] = (ei * dr - er * di) / den;
     }
 }
+/* The sampled-set map as an object, so that a caller evaluating many row windows against one sampled set builds it
+ * once (the GPU arm builds its table once per batch too). */
+void *orc_map_create(const int64_t *samples, int64_t N) {
+    map_t *m = (map_t *)malloc(sizeof(map_t));
+    *m = map_build(samples, N);
+    return m;
+}
+void orc_map_free(void *vm) {
+    map_t *m = (map_t *)vm;
+    if (!m) return;
+    free(m->keys); free(m->vals); free(m);
+}
+void orc_local_energy_sample_aware_map(const int64_t *samples, const double *amps, int64_t N, const void *map,
+                                       int64_t row_start, int64_t row_len,
+                                       const int64_t *unq_xy, int64_t U,
+                                       const int64_t *yz_start, const int64_t *yz_num,
+                                       const int64_t *re_yz, const double *re_w,
+                                       int64_t alpha_num, int64_t beta_num, double *eloc /* [2*row_len] */) {
+    (void)N;
+    le_ctx c = { samples, amps, row_start, unq_xy, U, yz_start, yz_num, re_yz, re_w, alpha_num, beta_num, eloc, (const map_t *)map };
+    parallel_for(row_len, 8, le_rows, &c);
+}
 void orc_local_energy_sample_aware(const int64_t *samples, const double *amps, int64_t N,
                                    int64_t row_start, int64_t row_len,
                                    const int64_t *unq_xy, int64_t U,
@@ -251,8 +273,8 @@ void orc_local_energy_sample_aware(const int64_t *samples, const double *amps, i
                                    const int64_t *re_yz, const double *re_w,
                                    int64_t alpha_num, int64_t beta_num, double *eloc /* [2*row_len] */) {
     map_t map = map_build(samples, N);
-    le_ctx c = { samples, amps, row_start, unq_xy, U, yz_start, yz_num, re_yz, re_w, alpha_num, beta_num, eloc, &map };
-    parallel_for(row_len, 8, le_rows, &c);
+    orc_local_energy_sample_aware_map(samples, amps, N, &map, row_start, row_len, unq_xy, U, yz_start, yz_num, re_yz, re_w,
+                                      alpha_num, beta_num, eloc);
     free(map.keys); free(map.vals);
 }
 

@@ -127,17 +127,39 @@ def matrix_elements(xprime, xy_ptr, tab: Tables):
     return H
 
 
-def local_energy_sample_aware(samples, amps, tab: Tables, alpha_num, beta_num, row_start=0, row_len=None):
-    s = _i64(samples).reshape(-1)
+class SampledSet:
+    """The {configuration -> position} map of a sampled set, built once and reused by every row window evaluated
+    against it (oracle/anqs_oracle.c orc_map_create)."""
+
+    def __init__(self, samples):
+        self.samples = _i64(samples).reshape(-1)
+        lib().orc_map_create.restype = ctypes.c_void_p
+        self.handle = ctypes.c_void_p(lib().orc_map_create(_p(self.samples, _i64p), ctypes.c_int64(self.samples.size)))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().orc_map_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def local_energy_sample_aware(samples, amps, tab: Tables, alpha_num, beta_num, row_start=0, row_len=None, sampled_set: SampledSet = None):
+    s = _i64(samples).reshape(-1) if sampled_set is None else sampled_set.samples
     a = np.ascontiguousarray(amps, dtype=np.complex128).reshape(-1)
     row_len = s.size - row_start if row_len is None else row_len
     e = np.empty(row_len, np.complex128)
-    lib().orc_local_energy_sample_aware(
-        _p(s, _i64p), _p(a.view(np.float64), _f64p), ctypes.c_int64(s.size), ctypes.c_int64(row_start),
-        ctypes.c_int64(row_len), _p(tab.unq_xy_masks, _i64p), ctypes.c_int64(tab.unq_xy_masks_num),
-        _p(tab.unq_xy_to_yz_start, _i64p), _p(tab.unq_xy_to_yz_num, _i64p), _p(tab.rearranged_yz, _i64p),
-        _p(tab.rearranged_weights.view(np.float64), _f64p), ctypes.c_int64(alpha_num), ctypes.c_int64(beta_num),
-        _p(e.view(np.float64), _f64p))
+    head = (_p(s, _i64p), _p(a.view(np.float64), _f64p), ctypes.c_int64(s.size))
+    tail = (ctypes.c_int64(row_start),
+            ctypes.c_int64(row_len), _p(tab.unq_xy_masks, _i64p), ctypes.c_int64(tab.unq_xy_masks_num),
+            _p(tab.unq_xy_to_yz_start, _i64p), _p(tab.unq_xy_to_yz_num, _i64p), _p(tab.rearranged_yz, _i64p),
+            _p(tab.rearranged_weights.view(np.float64), _f64p), ctypes.c_int64(alpha_num), ctypes.c_int64(beta_num),
+            _p(e.view(np.float64), _f64p))
+    if sampled_set is None:
+        lib().orc_local_energy_sample_aware(*head, *tail)
+    else:
+        lib().orc_local_energy_sample_aware_map(*head, sampled_set.handle, *tail)
     return e
 
 
