@@ -146,13 +146,22 @@ class SampleTable:
 
     def __init__(self, keys: pt.Tensor, amps: pt.Tensor = None, spread_bits: int = None):
         dev = _lib.require_cuda(keys.device)
-        assert keys.dtype == pt.int64 and keys.dim() == 1 and keys.is_contiguous()
         n = keys.shape[0]
-        self.n = n
         self.capacity = int(_lib.lib().anqs_hash_capacity(n))
         nbytes = int(_lib.lib().anqs_hash_bytes(self.capacity))
         self.slots = pt.empty(((nbytes + 7) // 8,), dtype=pt.int64, device=dev)  # slots + header + filter
         assert self.slots.data_ptr() % 128 == 0
+        self.rebuild(keys, amps, spread_bits)
+
+    def rebuild(self, keys: pt.Tensor, amps: pt.Tensor = None, spread_bits: int = None):
+        """(Re)builds the table in place for a new key set that needs the same capacity: an iteration loop keeps one table
+        object and pays no allocation per batch (stream-ordered: four kernels and three memsets, no host synchronisation)."""
+        dev = _lib.require_cuda(keys.device)
+        assert keys.dtype == pt.int64 and keys.dim() == 1 and keys.is_contiguous() and keys.device == self.slots.device
+        n = keys.shape[0]
+        if int(_lib.lib().anqs_hash_capacity(n)) != self.capacity:
+            raise ValueError(f'SampleTable.rebuild: {n} keys need capacity {int(_lib.lib().anqs_hash_capacity(n))}, this table has {self.capacity}')
+        self.n = n
         amps_real = None
         if amps is not None:
             assert amps.dtype == pt.complex128 and amps.shape[0] == n
@@ -164,6 +173,7 @@ class SampleTable:
         else:
             _lib.check(_lib.lib().anqs_hash_build_spread(_lib.dptr(keys), _lib.dptr(amps_real), n, _lib.dptr(self.slots),
                                                          self.capacity, int(spread_bits), _lib.stream_ptr(dev)))
+        return self
 
     def filter_info(self):
         """(G, overloaded[0..6]): the spread chosen by the build and the line-occupancy statistic behind it."""

@@ -503,6 +503,7 @@ class GpuEngine:
         # which fused kernel the C ABI picks for this batch (k1_fused_bs.cu: >= 256 rows per SM and every spin part of weight <= 4)
         self.kernel_name = ('fused_eloc_bs_kernel' if (self.rows + 31) // 32 >= 8 * torch.cuda.get_device_properties(dev).multi_processor_count
                             else 'fused_eloc_kernel')
+        self.table = self.eloc = None
         self.launches_per_step = 5  # filter_count, filter_overload, filter_pick_spread, hash_build (k2_hash.cu) + the fused kernel
 
     def flush_l2(self):
@@ -514,8 +515,14 @@ class GpuEngine:
         torch, adist, _lib = self.torch, self.adist, self._lib
         from anqs_quantum_chemistry_b200 import SampleTable
         g_idx, g_amps, glo, ghi = adist.all_gather_shards(self.d_idx, self.d_amps, sizes=self.shard_sizes)
-        table = SampleTable(g_idx, g_amps)
-        eloc = torch.empty(ghi - glo, dtype=torch.complex128, device=self.device)
+        # table storage and the output vector live across steps (an iteration loop would keep them too): no allocation, hence
+        # no cudaMalloc stall, inside a step
+        if self.table is None:
+            self.table = SampleTable(g_idx, g_amps)
+            self.eloc = torch.empty(ghi - glo, dtype=torch.complex128, device=self.device)
+        else:
+            self.table.rebuild(g_idx, g_amps)
+        table, eloc = self.table, self.eloc
         sp = _lib.stream_ptr(self.device)
         m0 = clock.mark() if clock else None
         _lib.check(self.lib.anqs_local_energy_sample_aware(self.tables, _lib.dptr(g_idx), _lib.dptr(torch.view_as_real(g_amps)), g_idx.shape[0],
