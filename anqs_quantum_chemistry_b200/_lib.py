@@ -29,9 +29,9 @@ _SIGNATURES = {
     'anqs_exclusive_scan_i64': (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
     'anqs_k1_emit': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_k1_enum_tiles': (_c_int, [_vp]),
-    'anqs_k1_enum_force_product_filter': (None, [_c_int]),
     'anqs_k1_enum_workspace': (ctypes.c_size_t, [_vp, _c_i64]),
     'anqs_k1_enum_filter': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp]),
+    'anqs_k1_enum_filter_variant': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_k1_enum_emit': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_matrix_elements': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
     'anqs_hash_capacity': (_c_i64, [_c_i64]),
@@ -41,7 +41,7 @@ _SIGNATURES = {
     'anqs_hash_filter_info': (_c_int, [_vp, _c_i64, _vp, _vp, _vp]),
     'anqs_hash_probe': (_c_int, [_vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp]),
     'anqs_local_energy_sample_aware': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _vp]),
-    'anqs_local_energy_force_per_sample_kernel': (None, [_c_int]),
+    'anqs_local_energy_sample_aware_variant': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _c_int, _vp]),
     'anqs_accumulate_rows': (_c_int, [_vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_made_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_made_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),

@@ -41,24 +41,103 @@ class LocalSamplingConfig:
         return (self.strategy,) * (qudit_num - self.masking_depth) + ('DU',) * self.masking_depth
 
 
-class MLPConfig:
-    """MLP:83-99 with the uniform width / bias / activation patterns of MLP:13-70 flattened into plain fields."""
+class _PatternConfig:
+    """PatternConfig of the reference (infrastructure/nested_data.py:97-125): a per-layer pattern; only 'uniform' exists there
+    apart from ActivationConfig's 'sanqs_paper'."""
+    UNIFORM_PATTERN_FIELD = None
 
-    def __init__(self, *args, depth: int = 2, width: int = 64, use_res: bool = True, use_bias: bool = True,
-                 activation=nn.Tanh, activate_last_layer: bool = False, **kwargs):
-        self.depth, self.width, self.use_res, self.use_bias = depth, width, use_res, use_bias
-        self.activation, self.activate_last_layer = activation, activate_last_layer
+    def __init__(self, *args, pattern_type: str = 'uniform', **kwargs):
+        if args or kwargs:
+            raise TypeError(f'{type(self).__name__}: unexpected arguments {args} {sorted(kwargs)}')
+        if pattern_type != 'uniform':
+            raise NotImplementedError(f"{type(self).__name__}: pattern_type '{pattern_type}' is not implemented by the sm_100a kernels "
+                                      f"(uniform layers only)")
+        self.pattern_type = pattern_type
+
+    def create_pattern(self, depth):
+        return (getattr(self, self.UNIFORM_PATTERN_FIELD),) * depth
+
+
+class WidthConfig(_PatternConfig):
+    """MLP:13-23."""
+    UNIFORM_PATTERN_FIELD = 'width'
+
+    def __init__(self, *args, width: int = 64, **kwargs):
+        self.width = width
+        super().__init__(*args, **kwargs)
+
+
+class BiasConfig(_PatternConfig):
+    """MLP:26-36."""
+    UNIFORM_PATTERN_FIELD = 'use_bias'
+
+    def __init__(self, *args, use_bias: bool = True, **kwargs):
+        self.use_bias = use_bias
+        super().__init__(*args, **kwargs)
+
+
+class ActivationConfig(_PatternConfig):
+    """MLP:49-70."""
+    UNIFORM_PATTERN_FIELD = 'activation'
+
+    def __init__(self, *args, activation=nn.Tanh, **kwargs):
+        self.activation = activation
+        super().__init__(*args, **kwargs)
+
+
+class MLPConfig:
+    """MLP:83-99, same keywords: depth, width_config, use_res, bias_config, activation_config, activate_last_layer.  What the
+    kernels do not implement raises NotImplementedError instead of silently building a different network: hidden width other
+    than 64 (made_common.cuh MD_W), non-uniform patterns, an activation other than tanh, an activated last layer.  Unknown
+    keywords raise TypeError.  `width=` / `use_bias=` / `activation=` are accepted as shorthands for the three sub-configs."""
+
+    def __init__(self, *args, depth: int = 2, width_config: WidthConfig = None, use_res: bool = True, bias_config: BiasConfig = None,
+                 activation_config: ActivationConfig = None, activate_last_layer: bool = False,
+                 width: int = None, use_bias: bool = None, activation=None, **kwargs):
+        if args or kwargs:
+            raise TypeError(f'MLPConfig: unexpected arguments {args} {sorted(kwargs)}')
+        for name, short, full in (('width', width, width_config), ('use_bias', use_bias, bias_config), ('activation', activation, activation_config)):
+            if short is not None and full is not None:
+                raise TypeError(f'MLPConfig: give either {name}= or its config object, not both')
+        self.depth = depth
+        self.width_config = width_config if width_config is not None else WidthConfig(**({} if width is None else {'width': width}))
+        self.use_res = use_res
+        self.bias_config = bias_config if bias_config is not None else BiasConfig(**({} if use_bias is None else {'use_bias': use_bias}))
+        self.activation_config = (activation_config if activation_config is not None
+                                  else ActivationConfig(**({} if activation is None else {'activation': activation})))
+        self.activate_last_layer = activate_last_layer
+        if not 1 <= self.depth <= 4:
+            raise NotImplementedError('MLPConfig: depth must be in [1, 4] (anqs_made_desc_t holds five layers)')
+        if self.width != 64:
+            raise NotImplementedError(f'MLPConfig: hidden width {self.width} is not implemented (the sm_100a kernels are built for width 64, '
+                                      f'the reference default)')
+        if self.activation is not nn.Tanh:
+            raise NotImplementedError('MLPConfig: only nn.Tanh hidden activations are implemented')
+        if self.activate_last_layer:
+            raise NotImplementedError('MLPConfig: activate_last_layer=True is not implemented (identity output layer only)')
+
+    # flat views used by the modules
+    width = property(lambda self: self.width_config.width)
+    use_bias = property(lambda self: self.bias_config.use_bias)
+    activation = property(lambda self: self.activation_config.activation)
 
 
 class ANQSConfig:
-    """ANQS:68-109.  The reference's default de_mode is 'NADE' (one MLP pair per qudit); the default here is 'MADE' (one masked
-    network), the mode BASELINE.json's configurations name.  Both are implemented."""
+    """ANQS:68-109, same keywords and the same defaults: de_mode='NADE' (one MLP pair per qudit, ANQS:90); 'MADE' (one masked
+    network, the mode BASELINE.json's configurations name) has to be asked for, as in the reference."""
     ALLOWED_DE_MODES = ('MADE', 'NADE')
 
-    def __init__(self, *args, dtype=BASE_REAL_TYPE, de_mode: str = 'MADE', qubit_grouping_config: QubitGroupingConfig = None,
+    def __init__(self, *args, dtype=BASE_REAL_TYPE, de_mode: str = 'NADE', qubit_grouping_config: QubitGroupingConfig = None,
                  local_sampling_config: LocalSamplingConfig = None, subtract_mean: bool = True,
                  main_subnet_config: MLPConfig = None, aux_subnet_config: MLPConfig = None,
-                 use_sign_structure: bool = False, **kwargs):
+                 use_sign_structure: bool = False, spin_flip_symmetry_config=None, **kwargs):
+        if args or kwargs:
+            raise TypeError(f'ANQSConfig: unexpected arguments {args} {sorted(kwargs)}')
+        assert de_mode in self.ALLOWED_DE_MODES
+        if use_sign_structure:
+            raise NotImplementedError('ANQSConfig: use_sign_structure=True is not implemented')
+        if spin_flip_symmetry_config is not None and (getattr(spin_flip_symmetry_config, 'abs', False) or getattr(spin_flip_symmetry_config, 'phase', False)):
+            raise NotImplementedError('ANQSConfig: spin-flip symmetrisation is broken in the reference (ANQS:160-190) and not implemented')
         self.dtype = dtype
         self.de_mode = de_mode
         self.qubit_grouping_config = qubit_grouping_config if qubit_grouping_config is not None else QubitGroupingConfig()
@@ -67,6 +146,7 @@ class ANQSConfig:
         self.main_subnet_config = main_subnet_config if main_subnet_config is not None else MLPConfig()
         self.aux_subnet_config = aux_subnet_config if aux_subnet_config is not None else MLPConfig()
         self.use_sign_structure = use_sign_structure
+        self.spin_flip_symmetry_config = spin_flip_symmetry_config
 
 
 class MLP(nn.Module):

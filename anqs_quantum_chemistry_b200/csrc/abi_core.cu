@@ -262,134 +262,235 @@ struct HostEnum {
     bool ok = true;
 };
 
-// Pattern-type analysis of one YZ group (see EnumTile in common.cuh).  Returns nbits (0 = generic) and fills pos / zbase /
-// table (2^nbits entries, re and im).
-static int analyse_group(uint64_t xy, const int64_t *yz, const double *wre, const double *wim, int num, int pos[3],
-                         uint64_t *zbase, std::vector<double> &tre, std::vector<double> &tim) {
-    const uint64_t EVEN = 0x5555555555555555ULL;
-    const int ka = __builtin_popcountll(xy & EVEN), kb = __builtin_popcountll(xy & ~EVEN);
-    if (num < 1 || num > ENUM_PATTERN_MAX_TERMS || ka + kb == 0 || ka + kb > 4 || (ka & 1) || (kb & 1)) return 0;
-    for (int t = 0; t < num; ++t)
-        if (((uint64_t)yz[t] ^ (uint64_t)yz[0]) & ~xy) return 0;
-    *zbase = (uint64_t)yz[0] & ~xy;
-    // index positions: every position of the mask except the highest of each spin part
-    std::vector<int> pa, pb, idxpos;
-    for (int b = 0; b < 64; ++b)
-        if ((xy >> b) & 1) ((b & 1) ? pb : pa).push_back(b);
-    for (size_t i = 0; i + 1 < pa.size(); ++i) idxpos.push_back(pa[i]);
-    for (size_t i = 0; i + 1 < pb.size(); ++i) idxpos.push_back(pb[i]);
-    const int nbits = (int)idxpos.size();  // 1 (2,0) | 2 (2,2) | 3 (4,0)
-    for (int i = 0; i < 3; ++i) pos[i] = i < nbits ? idxpos[i] : 0;
-    tre.assign((size_t)1 << nbits, 0.0);
-    tim.assign((size_t)1 << nbits, 0.0);
-    for (int idx = 0; idx < (1 << nbits); ++idx) {
-        uint64_t b = 0;
-        for (int i = 0; i < nbits; ++i)
-            if ((idx >> i) & 1) b |= 1ULL << idxpos[i];
-        bool valid = true;
-        for (const std::vector<int> *part : {&pa, &pb}) {
-            if (part->empty()) continue;
-            int occ = 0;
-            for (size_t i = 0; i + 1 < part->size(); ++i) occ += (int)((b >> (*part)[i]) & 1);
-            const int top = (int)part->size() / 2 - occ;  // implied occupation of the highest position
-            if (top < 0 || top > 1) valid = false;
-            else if (top) b |= 1ULL << part->back();
-        }
-        if (!valid) continue;  // never addressed by a sample of the sector
-        double sr = 0.0, si = 0.0;
-        for (int t = 0; t < num; ++t) {
-            const double sgn = (__builtin_popcountll(b & (uint64_t)yz[t] & xy) & 1) ? -1.0 : 1.0;
-            sr += sgn * wre[t];
-            si += sgn * wim[t];
-        }
-        tre[idx] = sr;
-        tim[idx] = si;
+// Analysis of one YZ group for the tile-resident emit kernel (see EnumTile in common.cuh).
+//   kind 1 (pattern):    every term has the same Z part outside the mask; table G[slot].
+//   kind 2 (one extra):  the Z parts outside the mask differ from a common zbase by at most ONE position r (one-body
+//                        excitations dressed with number operators): H = sign * (A[slot] + sum_{r occupied in x'} D[r][slot]).
+//   kind 3 (diagonal):   xy = 0 and every term has at most two Z positions: H = K + sum_i a_i n_i + sum_{j<i} b_ij n_i n_j.
+//   kind 4 (pattern, explicit sign): a pattern group whose zbase is NOT the Jordan-Wigner string the kernel derives from the
+//                        mask itself (see below): evaluated like kind 1, but on the deferred path with its own zbase.
+//   kind 0:              none of these; the kernel sums the term records from global memory.
+// Derived sign: with S = the exclusive prefix parity of the SAMPLE x (bit i of S = parity of the bits of x below i), the
+// kernel takes the sign of a kind-1 connection as parity(S & xy) = parity(x & W), W = XOR over the positions i of the mask of
+// the bits below i (the union of the ranges between the 1st and 2nd, and the 3rd and 4th position, lower ends included).
+// That equals parity(x & zbase) up to bits of x ON the mask's positions whenever (zbase ^ W) lies inside the mask - true for
+// every Jordan-Wigner excitation string - and those bits are a function of the occupation pattern, so they are folded into
+// the table.  The mask records then carry no zbase at all: one 16-byte shared-memory load per connection instead of 24.
+struct GroupInfo {
+    int kind = 0, nbits = 0;
+    uint32_t mult = 0;
+    uint64_t zbase = 0;
+    std::vector<double> re, im;  // kind 1: 2^nbits | kind 2: (1 + n) * 2^nbits (A then D[r]) | kind 3: 1 + n + n * n
+    size_t block_bytes(bool real) const {  // bytes of the occupation block of kinds 2 / 3 / 4 (16-byte header + tables)
+        return kind >= 2 ? 16 + re.size() * 8 * (real ? 1 : 2) : 0;
     }
-    return nbits;
+};
+
+static inline uint32_t enum_slot(uint64_t v, uint32_t mult) {
+    return ((((uint32_t)(v >> 32)) * ENUM_FOLD + (uint32_t)v) * mult) >> 29;
 }
 
-static void build_enum_tiles(const std::vector<uint64_t> &xy, const std::vector<int2> &grp, int64_t U_pad,
+static void analyse_group(int n, uint64_t xy, const int64_t *yz, const double *wre, const double *wim, int num, GroupInfo &out) {
+    const uint64_t EVEN = 0x5555555555555555ULL;
+    out = GroupInfo();
+    if (num < 1) return;
+    if (xy == 0) {  // diagonal
+        for (int t = 0; t < num; ++t)
+            if (__builtin_popcountll((uint64_t)yz[t]) > 2) return;
+        out.kind = 3;
+        out.re.assign((size_t)1 + n + (size_t)n * n, 0.0);
+        out.im.assign(out.re.size(), 0.0);
+        for (int pass = 0; pass < 2; ++pass) {
+            const double *w = pass ? wim : wre;
+            std::vector<double> &tab = pass ? out.im : out.re;
+            double *K = &tab[0], *a = &tab[1], *b = &tab[1 + n];
+            for (int t = 0; t < num; ++t) {
+                const uint64_t z = (uint64_t)yz[t];
+                const int pc = __builtin_popcountll(z);
+                *K += w[t];
+                if (pc == 1) a[__builtin_ctzll(z)] += -2.0 * w[t];
+                if (pc == 2) {
+                    const int j = __builtin_ctzll(z), i = 63 - __builtin_clzll(z);  // j < i
+                    a[i] += -2.0 * w[t];
+                    a[j] += -2.0 * w[t];
+                    b[(size_t)i * n + j] += 4.0 * w[t];
+                }
+            }
+        }
+        return;
+    }
+    const int ka = __builtin_popcountll(xy & EVEN), kb = __builtin_popcountll(xy & ~EVEN);
+    if (ka + kb > 4 || (ka & 1) || (kb & 1)) return;
+    // occupation patterns of x' on the mask's positions that a sample of the sector can produce: exactly half of the alpha
+    // positions and half of the beta positions occupied
+    std::vector<int> pos;
+    for (int b = 0; b < 64; ++b)
+        if ((xy >> b) & 1) pos.push_back(b);
+    std::vector<uint64_t> pats;
+    for (int m = 0; m < (1 << pos.size()); ++m) {
+        uint64_t b = 0;
+        for (size_t i = 0; i < pos.size(); ++i)
+            if ((m >> i) & 1) b |= 1ULL << pos[i];
+        if (__builtin_popcountll(b & EVEN) * 2 == ka && __builtin_popcountll(b & ~EVEN) * 2 == kb) pats.push_back(b);
+    }
+    // common Z part outside the mask
+    uint64_t zbase = (uint64_t)yz[0] & ~xy;
+    int kind = 1;
+    for (int t = 0; t < num && kind == 1; ++t)
+        if (((uint64_t)yz[t] & ~xy) != zbase) kind = 0;
+    if (kind == 0) {  // one extra position at most, relative to E_0 or to E_0 with one position toggled
+        const uint64_t e0 = (uint64_t)yz[0] & ~xy;
+        for (int c = -1; c < n && kind == 0; ++c) {
+            if (c >= 0 && ((xy >> c) & 1)) continue;
+            const uint64_t cand = c < 0 ? e0 : e0 ^ (1ULL << c);
+            bool good = true;
+            for (int t = 0; t < num && good; ++t) good = __builtin_popcountll(((uint64_t)yz[t] & ~xy) ^ cand) <= 1;
+            if (good) { kind = 2; zbase = cand; }
+        }
+        if (kind == 0) return;
+    }
+    int nbits = 0;
+    while ((size_t)(1 << nbits) < pats.size()) ++nbits;
+    if (nbits == 0) nbits = 1;
+    // multiplier search: a deterministic sequence of odd candidates; the patterns must land on distinct slots < 2^nbits
+    uint32_t mult = 0;
+    for (; nbits <= 3; ++nbits) {
+        uint32_t cand = 0x2545F491u;
+        for (int tries = 0; tries < 200000 && !mult; ++tries) {
+            cand = cand * 0x9E3779B1u + 0x7F4A7C15u;
+            const uint32_t m = cand | 1u;
+            uint32_t seen = 0;
+            bool good = true;
+            for (uint64_t b : pats) {
+                const uint32_t sl = enum_slot(b, m);
+                if (sl >= (1u << nbits) || ((seen >> sl) & 1u)) { good = false; break; }
+                seen |= 1u << sl;
+            }
+            if (good) mult = m;
+        }
+        if (mult) break;
+    }
+    if (!mult) return;  // kind 0
+    uint64_t W = 0;  // XOR over the mask's positions i of the bits below i
+    for (int i = 0; i < 64; ++i)
+        if ((xy >> i) & 1) W ^= (i == 0 ? 0ull : (~0ull >> (64 - i)));
+    const bool derived = ((zbase ^ W) & ~xy) == 0;
+    if (kind == 1 && !derived) kind = 4;
+    out.kind = kind;
+    out.nbits = nbits;
+    out.mult = mult;
+    out.zbase = zbase;
+    const size_t ns = (size_t)1 << nbits;
+    const size_t rows = kind == 2 ? (size_t)1 + n : 1;  // row 0: G or A; row 1 + r: D[r]
+    out.re.assign(rows * ns, 0.0);
+    out.im.assign(rows * ns, 0.0);
+    for (uint64_t b : pats) {
+        const uint32_t sl = enum_slot(b, mult);
+        for (int t = 0; t < num; ++t) {
+            double sgn = (__builtin_popcountll(b & (uint64_t)yz[t] & xy) & 1) ? -1.0 : 1.0;
+            // kind 1: the kernel's sign is parity(x & W) instead of parity(x & zbase); the difference lives on the mask's
+            // positions, where x = b ^ xy
+            if (kind == 1 && (__builtin_popcountll((b ^ xy) & xy & W) & 1)) sgn = -sgn;
+            const uint64_t extra = ((uint64_t)yz[t] & ~xy) ^ zbase;  // 0 or one bit
+            out.re[sl] += sgn * wre[t];
+            out.im[sl] += sgn * wim[t];
+            if (extra) {  // w (-1)^{n_r} = w - 2 w n_r
+                const int r = __builtin_ctzll(extra);
+                out.re[(size_t)(1 + r) * ns + sl] += -2.0 * sgn * wre[t];
+                out.im[(size_t)(1 + r) * ns + sl] += -2.0 * sgn * wim[t];
+            }
+        }
+    }
+}
+
+static void build_enum_tiles(int n, const std::vector<uint64_t> &xy, const std::vector<int2> &grp, int64_t U_pad,
                              const int64_t *h_yz, const std::vector<double> &wre, const std::vector<double> &wim, bool real,
                              HostEnum &out) {
-    // per-mask analysis
-    struct MaskInfo { int nbits; int pos[3]; uint64_t zbase; std::vector<double> tre, tim; };
-    std::vector<MaskInfo> info((size_t)U_pad);
+    std::vector<GroupInfo> info((size_t)U_pad);
     std::vector<size_t> mask_bytes((size_t)U_pad);
     for (int64_t u = 0; u < U_pad; ++u) {
-        MaskInfo &mi = info[u];
-        mi.zbase = 0;
-        mi.nbits = analyse_group(xy[u], h_yz + grp[u].x, wre.data() + grp[u].x, wim.data() + grp[u].x, grp[u].y, mi.pos, &mi.zbase,
-                                 mi.tre, mi.tim);
-        if (grp[u].y > ENUM_MAX_GROUP) out.ok = false;
-        mask_bytes[u] = 24 + (mi.nbits ? ((size_t)8 << mi.nbits) * (real ? 1 : 2) : (size_t)grp[u].y * (real ? 16 : 24));
+        analyse_group(n, xy[u], h_yz + grp[u].x, wre.data() + grp[u].x, wim.data() + grp[u].x, grp[u].y, info[u]);
+        mask_bytes[u] = 17 + (info[u].kind == 1 ? info[u].re.size() * 8 * (real ? 1 : 2) : info[u].block_bytes(real));
     }
-    const int64_t nblocks = U_pad / 32;
+    const int64_t nblocks = U_pad / 32;  // one block = one bitmap word = 32 masks
     std::vector<size_t> block_bytes((size_t)nblocks);
-    size_t total = 0;
     for (int64_t b = 0; b < nblocks; ++b) {
         size_t bytes = 0;
         for (int64_t u = b * 32; u < b * 32 + 32; ++u) bytes += mask_bytes[u];
         block_bytes[b] = bytes;
-        if (bytes + 128 > ENUM_TILE_MAX) out.ok = false;
-        total += bytes;
     }
-    if (!out.ok) return;
-    const size_t budget = ENUM_TILE_MAX - 128;
-    const size_t n_tiles = std::max<size_t>(1, (total + budget - 4096 - 1) / (budget - 4096));
-    const size_t target = (total + n_tiles - 1) / n_tiles;
+    // Tiles of a whole number of expansion steps (ENUM_STEP_WORDS bitmap words) whenever that many words fit: a step that is
+    // only partly filled costs the emit kernel as much as a full one.
+    const size_t budget = ENUM_TILE_MAX - 256;
     int64_t b = 0;
     while (b < nblocks) {
         const int64_t b0 = b;
         size_t bytes = 0;
-        while (b < nblocks && (b == b0 || (bytes < target && bytes + block_bytes[b] <= budget))) bytes += block_bytes[b++];
+        int64_t fit = b0;  // one past the last block that fits
+        while (fit < nblocks && bytes + block_bytes[fit] <= budget) bytes += block_bytes[fit++];
+        if (fit == b0) { out.ok = false; return; }  // a single word of masks does not fit (a diagonal block of a huge n)
+        int64_t take = fit - b0;
+        if (fit < nblocks && take > ENUM_STEP_WORDS) take -= take % ENUM_STEP_WORDS;
+        b = b0 + take;
         EnumTile tile{};
         tile.u0 = (uint32_t)(b0 * 32);
-        tile.n_masks = (uint32_t)((b - b0) * 32);
+        tile.n_masks = (uint32_t)(take * 32);
         tile.word0 = (uint32_t)b0;
-        tile.n_words = (uint32_t)(b - b0);
-        std::vector<uint64_t> txy(tile.n_masks), tzb(tile.n_masks);
-        std::vector<uint2> tdesc(tile.n_masks);
-        std::vector<double> tab_re, tab_im, tim;
-        std::vector<ulonglong2> trec;
-        for (uint32_t k = 0; k < tile.n_masks; ++k) {
-            const int64_t u = (int64_t)tile.u0 + k;
-            const MaskInfo &mi = info[u];
-            txy[k] = xy[u];
-            tzb[k] = mi.zbase;
-            if (mi.nbits) {
-                tdesc[k] = make_uint2((uint32_t)tab_re.size(),
-                                      (uint32_t)mi.nbits | ((uint32_t)mi.pos[0] << 2) | ((uint32_t)mi.pos[1] << 8) | ((uint32_t)mi.pos[2] << 14));
-                tab_re.insert(tab_re.end(), mi.tre.begin(), mi.tre.end());
-                if (!real) tab_im.insert(tab_im.end(), mi.tim.begin(), mi.tim.end());
-            } else {
-                tdesc[k] = make_uint2((uint32_t)trec.size(), (uint32_t)grp[u].y << 2);
-                for (int j = grp[u].x; j < grp[u].x + grp[u].y; ++j) {
-                    unsigned long long bits;
-                    std::memcpy(&bits, &wre[j], 8);
-                    trec.push_back(make_ulonglong2((unsigned long long)h_yz[j], bits));
-                    if (!real) tim.push_back(wim[j]);
-                }
+        tile.n_words = (uint32_t)take;
+        const size_t desc_off = (size_t)tile.n_masks * 16;  // (no separate descriptor section any more: kept for the directory)
+        const size_t tab_off = desc_off;
+        struct Rec { uint64_t xy; uint32_t mult, off; };
+        std::vector<Rec> rec(tile.n_masks);
+        std::vector<double> tab_re, tab_im;
+        for (uint32_t k = 0; k < tile.n_masks; ++k) {  // pattern tables first: [re of all][im of all]
+            const GroupInfo &gi = info[(size_t)tile.u0 + k];
+            rec[k] = Rec{xy[(size_t)tile.u0 + k], 0u, 0u};
+            if (gi.kind == 1) {
+                rec[k].mult = gi.mult;
+                rec[k].off = (uint32_t)(tab_off + tab_re.size() * 8);
+                tab_re.insert(tab_re.end(), gi.re.begin(), gi.re.end());
+                if (!real) tab_im.insert(tab_im.end(), gi.im.begin(), gi.im.end());
             }
         }
         tile.n_tab = (uint32_t)tab_re.size();
-        tile.n_terms = (uint32_t)trec.size();
-        auto align16 = [](size_t v) { return (v + 15) / 16 * 16; };
-        const size_t tab_off = (size_t)tile.n_masks * 24;
-        const size_t term_off = align16(tab_off + (tab_re.size() + tab_im.size()) * 8);
-        const size_t nbytes = align16(term_off + trec.size() * 16 + tim.size() * 8);
+        tile.desc_off = (uint32_t)desc_off;
         tile.tab_off = (uint32_t)tab_off;
-        tile.term_off = (uint32_t)term_off;
-        if (nbytes > ENUM_TILE_MAX) out.ok = false;
+        // occupation blocks of the generic groups: [mult u32][kind | nbits << 8 u32][zbase u64][re tables][im tables when complex]
+        std::vector<uint8_t> blocks;
+        const size_t blocks_off = tab_off + (tab_re.size() + tab_im.size()) * 8;
+        for (uint32_t k = 0; k < tile.n_masks; ++k) {
+            const GroupInfo &gi = info[(size_t)tile.u0 + k];
+            if (gi.kind == 1 || (size_t)tile.u0 + k >= (size_t)U_pad || grp[(size_t)tile.u0 + k].y == 0) continue;
+            tile.n_generic++;
+            if (gi.kind < 2) continue;  // kind 0: desc.y = 0 -> term records from global memory
+            rec[k].off = (uint32_t)(blocks_off + blocks.size());
+            const uint32_t hdr[2] = {gi.mult, (uint32_t)gi.kind | ((uint32_t)gi.nbits << 8)};
+            const size_t at = blocks.size();
+            blocks.resize(at + gi.block_bytes(real));
+            std::memcpy(&blocks[at], hdr, 8);
+            std::memcpy(&blocks[at + 8], &gi.zbase, 8);
+            std::memcpy(&blocks[at + 16], gi.re.data(), gi.re.size() * 8);
+            if (!real) std::memcpy(&blocks[at + 16 + gi.re.size() * 8], gi.im.data(), gi.im.size() * 8);
+        }
+        auto align16 = [](size_t v) { return (v + 15) / 16 * 16; };
+        // bitmap of the generic masks, one word per bitmap word of the tile
+        std::vector<uint32_t> genmask(tile.n_words, 0u);
+        for (uint32_t k = 0; k < tile.n_masks; ++k)
+            if (rec[k].mult == 0u && grp[(size_t)tile.u0 + k].y > 0) genmask[k >> 5] |= 1u << (k & 31u);
+        const size_t gen_off = align16(blocks_off + blocks.size());
+        tile.gen_off = (uint32_t)gen_off;
+        // + 64: slack behind the last table (a slot is always < 8, whatever the table size)
+        const size_t nbytes = align16(gen_off + genmask.size() * 4) + 64;
+        if (nbytes > ENUM_TILE_MAX) { out.ok = false; return; }
         const size_t off = (out.blob.size() + 127) / 128 * 128;
         out.blob.resize(off + nbytes, 0);
         uint8_t *base = out.blob.data() + off;
-        std::memcpy(base, txy.data(), txy.size() * 8);
-        std::memcpy(base + txy.size() * 8, tzb.data(), tzb.size() * 8);
-        std::memcpy(base + txy.size() * 16, tdesc.data(), tdesc.size() * 8);
+        static_assert(sizeof(Rec) == 16, "mask record");
+        std::memcpy(base, rec.data(), rec.size() * 16);
         if (!tab_re.empty()) std::memcpy(base + tab_off, tab_re.data(), tab_re.size() * 8);
         if (!tab_im.empty()) std::memcpy(base + tab_off + tab_re.size() * 8, tab_im.data(), tab_im.size() * 8);
-        if (!trec.empty()) std::memcpy(base + term_off, trec.data(), trec.size() * 16);
-        if (!tim.empty()) std::memcpy(base + term_off + trec.size() * 16, tim.data(), tim.size() * 8);
+        if (!blocks.empty()) std::memcpy(base + blocks_off, blocks.data(), blocks.size());
+        std::memcpy(base + gen_off, genmask.data(), genmask.size() * 4);
         tile.blob_off = (uint32_t)off;
         tile.blob_bytes = (uint32_t)nbytes;
         out.tile_bytes_max = std::max(out.tile_bytes_max, tile.blob_bytes);
@@ -555,12 +656,21 @@ int anqs_tables_create(anqs_tables_t **out, int qubit_num, int64_t U, int64_t T,
         if (e == cudaSuccess) e = up((void **)&t->bs_pos, bs.data(), bs.size() * sizeof(uint2));
     }
     HostEnum en;
-    build_enum_tiles(xy, grp, t->U_pad, h_yz, wre, wim, real, en);
+    build_enum_tiles(qubit_num, xy, grp, t->U_pad, h_yz, wre, wim, real, en);
     if (en.ok) {
         t->n_enum_tiles = (int)en.tiles.size();
         t->enum_tile_bytes_max = (int)en.tile_bytes_max;
         if (e == cudaSuccess) e = up((void **)&t->enum_tiles, en.tiles.data(), en.tiles.size() * sizeof(EnumTile));
         if (e == cudaSuccess) e = up((void **)&t->enum_blob, en.blob.data(), en.blob.size());
+    }
+    if (e == cudaSuccess) {
+        t->dev_copy = nullptr;
+        Tables *dc = nullptr;
+        e = cudaMalloc((void **)&dc, sizeof(Tables));
+        if (e == cudaSuccess) {
+            t->dev_copy = dc;
+            e = cudaMemcpy(dc, t, sizeof(Tables), cudaMemcpyHostToDevice);
+        }
     }
     if (e != cudaSuccess) {
         anqs_tables_destroy((anqs_tables_t *)t);
@@ -588,6 +698,7 @@ int anqs_tables_destroy(anqs_tables_t *h) {
     cudaFree(t->prod_blob_u);
     cudaFree(t->prod_blob_bs);
     cudaFree(t->bs_pos);
+    cudaFree(t->dev_copy);
     cudaFree(t->enum_tiles);
     cudaFree(t->enum_blob);
     delete t;

@@ -51,36 +51,49 @@ struct MemRec {            // 8 bytes
     uint32_t mb;           // beta part
     uint32_t hash;         // lin(LIN_POSA, pa) ^ lin(LIN_POSB, mb)
 };
-// Enumeration tile (k1_enum.cu): a contiguous range of XY masks [u0, u0 + n_masks) with everything their matrix elements
-// need, sized to live in shared memory.  Blob layout (one bulk copy), every section 16-byte aligned:
-//   [xy: n_masks x 8 B][zbase: n_masks x 8 B][desc: n_masks x 8 B]
+// Enumeration tile (k1_enum.cu): a contiguous range of XY masks [u0, u0 + n_masks) with everything the matrix elements of
+// its PATTERN groups need, sized to live in shared memory.  Blob layout (one bulk copy), every section 16-byte aligned:
+//   [rec:  n_masks x 16 B = {xy, mult, off}]   one LDS.128 per connection
 //   [pattern tables: n_tab x 8 B (re)][n_tab x 8 B (im) when weights are complex]
-//   [term records: n_terms x 16 B = {yz (original bit order), bits(w_re)}][w_im: n_terms x 8 B when complex]
+//   [occupation blocks of the generic groups]
+//   [generic-mask bitmap: n_words x 4 B, bit b of word j = mask 32 j + b is generic]
 // A YZ group is of PATTERN type when all its terms differ only on the XY positions of its mask (true for every
 // four-position group of a Jordan-Wigner molecular Hamiltonian): then
-//   H_{x,x'} = (-1)^popcount(x' & zbase) * G[idx],   idx = the bits of x' at <= 3 "index positions" of the mask,
-// with G precomputed at table-build time - one 8-byte load and one POPC per connection instead of one 16-byte record and
-// one POPC per term.  idx leaves out the highest alpha and the highest beta position of the mask: for a sample inside the
-// (N_alpha, N_beta) sector those bits are implied by the electron counts (the kernel checks the sample and falls back to
-// the term records in global memory otherwise).
-//   desc.x = first table entry (pattern) | first term record (generic), tile-local
-//   desc.y = nbits (2 bits; 0 = generic) | pattern: p0 << 2 | p1 << 8 | p2 << 14 | generic: num << 2
+//   H_{x,x'} = (-1)^parity(x & zbase) * G[slot],   slot = (((v.hi * ENUM_FOLD + v.lo) * mult) >> 29),  v = x' & xy,
+// with G summed at table-build time and `mult` an odd 32-bit multiplier searched per mask so that the occupation patterns a
+// sample of the (N_alpha, N_beta) sector can show on the mask's positions (exactly half of the alpha positions and half of
+// the beta positions occupied: 2, 4 or 6 patterns) land on distinct slots of a table of 2, 4 or 8 doubles - five integer
+// instructions instead of three variable bit extractions.  `off` is the byte offset of G inside the tile.  zbase itself is
+// not stored: for a Jordan-Wigner string parity(x & zbase) = parity(S & xy) up to a pattern-dependent sign folded into G,
+// S = the exclusive prefix parity of the sample, computed once per (sample, tile) unit (analyse_group in abi_core.cu).
+// Generic groups (the diagonal, one-body excitations dressed with number operators; ~1 % of the connections) and pattern
+// groups whose zbase is not of that form have mult = 0; `off` then points at an OCCUPATION BLOCK in the tile,
+// [mult u32][kind | nbits << 8 u32][zbase u64][tables]:
+//   kind 2: the Z parts of the terms outside the mask differ from zbase by at most one position r:
+//           H = sign * (A[slot] + sum over the occupied positions r of x' of D[r][slot]),  tables A[2^nbits], D[n][2^nbits]
+//   kind 3: xy = 0 and at most two Z positions per term:  H = K + sum_i n_i (a_i + sum_{j<i} n_j b_ij),  tables K, a[n], b[n][n]
+//   kind 4: a pattern group with an explicit zbase:  H = sign * G[slot]
+// (complex weights: the imaginary tables follow the real ones), or off = 0 when the group is none of these: its term records
+// are then summed from the global arrays.  Generic connections are deferred by the emit kernel (a per-warp list in global
+// memory) and evaluated 32 at a time, one connection per lane.  Samples outside the (N_alpha, N_beta) sector, for which no
+// table applies, take a separate slow path through the global term arrays.
 struct EnumTile {
     uint32_t blob_off;     // byte offset in enum_blob (multiple of 128)
     uint32_t blob_bytes;   // multiple of 16
     uint32_t u0, n_masks;  // u0 and n_masks are multiples of 32
-    uint32_t n_tab, n_terms;
-    uint32_t tab_off, term_off;  // byte offsets inside the tile
+    uint32_t n_tab, n_generic;
+    uint32_t desc_off, tab_off;  // byte offsets inside the tile
     uint32_t word0, n_words;     // the tile's slice of a bitmap row
-    uint32_t pad0, pad1;
+    uint32_t gen_off, pad1;      // gen_off: byte offset of the per-word bitmaps of the generic masks (n_words x 4 B)
 };
-// shared-memory budget of enum_emit_kernel: per-warp queues of tile-local mask indices + one resident tile
+constexpr uint32_t ENUM_FOLD = 0x9E3779B1u;  // folds the two words of x' & xy into one before the per-mask multiplier
+// shared-memory budget of enum_emit_kernel: per-warp queues of tile-local mask indices, one resident tile
 constexpr int ENUM_EMIT_WARPS = 32;
 constexpr int ENUM_STEP_WORDS = 32;                        // bitmap words expanded per step
 constexpr int ENUM_QCAP = ENUM_STEP_WORDS * 32 + 32;       // queued indices per warp
 constexpr int ENUM_QUEUE_BYTES = ENUM_EMIT_WARPS * ENUM_QCAP * 2;
+constexpr int ENUM_DEFER_CAP = 64;                         // deferred connections per warp (global workspace, 16 B each)
 constexpr uint32_t ENUM_TILE_MAX = 227 * 1024 - ENUM_QUEUE_BYTES - 1024;  // bytes one enumeration tile may take
-constexpr int ENUM_MAX_GROUP = (1 << 24) - 1;  // longest YZ group the tiled path handles (it also has to fit a tile)
 constexpr int ENUM_PATTERN_MAX_TERMS = 64;     // longer groups stay generic (their tables would not save anything)
 // Device-resident Hamiltonian tables (reference tensors PO:103-115, re-laid-out for the kernels).
 struct Tables {
@@ -124,10 +137,11 @@ struct Tables {
     // test of every part of weight 0, 2 or 4 (weight 0: {0,0,1,1}; weight 2: {p,q,0,1}; odd weights: {0,0,0,0} = never).
     uint2 *bs_pos;            // [U_pad]
     int bs_ok;                // 0: some part has an even weight > 4, the bit-sliced filter does not apply
-    int n_enum_tiles;         // 0: the tiled enumeration is unavailable for this table (a YZ group does not fit)
+    int n_enum_tiles;         // 0: the tiled enumeration is unavailable for this table
     int enum_tile_bytes_max;
     EnumTile *enum_tiles;     // [n_enum_tiles] directory (device)
     uint8_t *enum_blob;       // tile blobs, each 128-byte aligned (device)
+    Tables *dev_copy;         // this struct in device memory: what rarely-taken non-inlined device functions read the table pointers from
 };
 
 // ---- sampled-set lookup table (kernel family 2) ------------------------------------------------------
@@ -167,7 +181,7 @@ struct HashView {
 struct Tables;
 // k1_fused_bs.cu: launches the bit-sliced fused local-energy kernel; 1 = launched, 0 = does not apply, < 0 = CUDA error
 int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, const double *d_amps, int64_t row_start,
-                        int64_t row_len, int alpha_num, int beta_num, double *d_eloc, cudaStream_t s);
+                        int64_t row_len, int alpha_num, int beta_num, double *d_eloc, int variant, cudaStream_t s);
 inline HashView make_hash_view(const void *d_table, int64_t capacity) {
     HashView hv;
     hv.slots = (const HashSlot *)d_table;

@@ -19,6 +19,7 @@
 // Algorithmic HBM traffic: 20 B written per emitted connection (x' 8, H 8, dest 4; +4 with xy_ptr, +8 with complex H), the
 // bitmap row (U/8 B) written once and read once per sample, 8 B per sample in, 4 B per (sample, tile) of ranks.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "matrix_elements.cuh"
@@ -293,129 +294,248 @@ enum_filter_bitsliced_kernel(Tables t, const int64_t *__restrict__ samples, int6
 }
 
 // ---- pass 2: tile-resident ordered emit ------------------------------------------------------------------------------
+// A warp owns one (sample, tile) unit at a time.  The tile's slice of the sample's bitmap row is expanded ENUM_STEP_WORDS words
+// at a time into a queue of tile-local mask indices (ascending = output order); every 32 queued indices are one batch, one
+// connection per lane: one LDS.128 {xy, mult, table offset} + one LDS.64 table entry, ~25 integer
+// instructions, three coalesced streaming stores.  Generic connections (mult = 0, ~1 %) are appended to the warp's deferred
+// list (global workspace, L2) and evaluated 32 at a time from the occupation blocks of the tile; samples outside the sector
+// take et_unit_slow.
 constexpr int ET_STEP_WORDS = ENUM_STEP_WORDS;
 constexpr int ET_QCAP = ENUM_QCAP;
 constexpr int ET_QUEUE_BYTES = ENUM_QUEUE_BYTES;
 static_assert(EN_WARPS == ENUM_EMIT_WARPS, "queue budget");
-constexpr uint32_t ET_BIG = 24;                   // YZ groups longer than this are summed by the whole warp
-
-struct EtTile {
-    const uint64_t *xy, *zb;
-    const uint2 *desc;
-    const double *tab;   // pattern tables: [n_tab] re, then [n_tab] im when weights are complex
-    const uint4 *term;   // {yz.lo, yz.hi, w.lo, w.hi}
-    const double *wim;
-    uint32_t u0, n_tab;
-};
 
 __device__ __forceinline__ double flip_hi(double w, uint32_t sign) {
     return __hiloint2double(__double2hiint(w) ^ (int)sign, __double2loint(w));
 }
-
-template <bool REAL>
-__device__ __forceinline__ void et_term(const uint4 rec, const double *wim, uint32_t k, uint32_t xlo, uint32_t xhi, double &hr,
-                                        double &hi) {
-    const uint32_t sign = (uint32_t)__popc((xlo & rec.x) ^ (xhi & rec.y)) << 31;
-    hr += __hiloint2double((int)(rec.w ^ sign), (int)rec.z);
-    if (!REAL) hi += flip_hi(wim[k], sign);
+// shared-memory loads by 32-bit shared address (no generic-to-shared conversion in the inner loop); the tile is read-only
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
 }
 
-// One connection per lane: x' = x ^ xy[u], H_{x,x'} and the stores.  Must be called by the whole warp.
-template <bool REAL, int HC>
-__device__ __forceinline__ void et_emit_batch(const Tables &t, const EtTile &tl, uint64_t x, bool in_sector, int s, bool active,
-                                              uint32_t ul, int64_t r, int32_t *dest, int64_t *xprime, int32_t *xy_ptr, double *H) {
-    uint64_t xp = 0;
-    double hr = 0.0, hi = 0.0;
-    if (active) xp = x ^ tl.xy[ul];
-    if (HC && in_sector) {
-        uint2 d = make_uint2(0u, 0u);
-        uint64_t zb = 0;
-        if (active) {
-            d = tl.desc[ul];
-            zb = tl.zb[ul];
-        }
-        const uint32_t xlo = (uint32_t)xp, xhi = (uint32_t)(xp >> 32);
-        const uint32_t nbits = d.y & 3u;
-        const uint32_t num = nbits ? 0u : d.y >> 2;
-        if (nbits) {
-            // pattern group: sign from the Z string outside the mask, magnitude from the table
-            const uint32_t sign = (uint32_t)__popc((xlo & (uint32_t)zb) ^ (xhi & (uint32_t)(zb >> 32))) << 31;
-            uint32_t idx = (uint32_t)(xp >> ((d.y >> 2) & 63u)) & 1u;
-            idx |= ((uint32_t)(xp >> ((d.y >> 8) & 63u)) & 1u) << 1;
-            idx |= ((uint32_t)(xp >> ((d.y >> 14) & 63u)) & 1u) << 2;
-            idx = (idx & ((1u << nbits) - 1u)) + d.x;
-            hr = flip_hi(tl.tab[idx], sign);
-            if (!REAL) hi = flip_hi(tl.tab[tl.n_tab + idx], sign);
-        } else if (num <= ET_BIG) {
-            double h2 = 0.0, i2 = 0.0;
-            uint32_t k = d.x;
-            const uint32_t end = d.x + num;
-            for (; k + 1 < end; k += 2) {
-                et_term<REAL>(tl.term[k], tl.wim, k, xlo, xhi, hr, hi);
-                et_term<REAL>(tl.term[k + 1], tl.wim, k + 1, xlo, xhi, h2, i2);
-            }
-            if (k < end) et_term<REAL>(tl.term[k], tl.wim, k, xlo, xhi, hr, hi);
-            hr += h2;
-            hi += i2;
-        }
-        unsigned bigmask = __ballot_sync(0xffffffffu, num > ET_BIG);
-        while (bigmask) {  // long generic groups (the diagonal, one-body excitations): the whole warp sums one group
-            const int src = __ffs(bigmask) - 1;
-            bigmask &= bigmask - 1;
-            const uint32_t st = __shfl_sync(0xffffffffu, d.x, src), end = st + __shfl_sync(0xffffffffu, num, src);
-            const uint32_t slo = __shfl_sync(0xffffffffu, xlo, src), shi = __shfl_sync(0xffffffffu, xhi, src);
-            double sr = 0.0, si = 0.0;
-            for (uint32_t k = st + lane_id(); k < end; k += 32) et_term<REAL>(tl.term[k], tl.wim, k, slo, shi, sr, si);
+struct EtOut {  // per-lane output cursors of the unit being emitted
+    int32_t *dest;
+    long long *xprime;
+    int32_t *xy_ptr;
+    double *H;
+};
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+
+// Inclusive warp scan of the per-lane popcounts of one step of bitmap words and expansion of the set bits into the queue
+// (ascending; q_s = shared address of the warp's queue).  Returns the number of indices appended.
+__device__ __forceinline__ int et_expand(uint32_t q_s, int qlen, uint32_t w, int j, int &lane_start) {
+    const int lane = lane_id();
+    const int c = __popc(w);
+    int inc = c;
 #pragma unroll
-            for (int dd = 16; dd > 0; dd >>= 1) {
-                sr += __shfl_xor_sync(0xffffffffu, sr, dd);
-                if (!REAL) si += __shfl_xor_sync(0xffffffffu, si, dd);
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    lane_start = qlen + inc - c;  // queue position of the lane's first index
+    if (total == 0) return 0;
+    // the lane's indices go to q[qlen + inc - c .. qlen + inc): written from the highest bit down (one FLO per bit)
+    uint32_t qa = q_s + 2u * (uint32_t)(qlen + inc);
+    const uint32_t base = (uint32_t)(j + lane) << 5;
+    while (w) {
+        const uint32_t bit = 31u - (uint32_t)__clz((int)w);
+        qa -= 2u;
+        sts_u16(qa, base + bit);
+        w ^= 1u << bit;
+    }
+    __syncwarp();
+    return total;
+}
+
+// Matrix elements of up to 32 deferred connections of the resident tile, one per lane (whole warp).
+// ent.x = x', ent.y = (output position << 16) | tile-local mask index.
+template <bool REAL, int HC>
+__device__ __noinline__ void et_eval_deferred(const Tables *td, uint32_t tile_s, uint32_t u0, ulonglong2 ent, bool active,
+                                              double *H) {
+    const Tables &t = *td;
+    const int lane = lane_id(), n = t.qubit_num;
+    const uint32_t k = (uint32_t)ent.y & 0xffffu;
+    const uint32_t plo = (uint32_t)ent.x, phi = (uint32_t)(ent.x >> 32);
+    uint4 r4 = make_uint4(0u, 0u, 0u, 0u);  // {xy.lo, xy.hi, mult (0 here), block offset}
+    uint2 hdr = make_uint2(0u, 0u), zb = make_uint2(0u, 0u);
+    if (active) {
+        r4 = lds128(tile_s + k * 16u);
+        if (r4.w) {
+            hdr = lds64(tile_s + r4.w);
+            zb = lds64(tile_s + r4.w + 8u);
+        }
+    }
+    const uint32_t kind = hdr.y & 0xffu, nbits = hdr.y >> 8;
+    const uint32_t sign = (uint32_t)__popc((plo & zb.x) ^ (phi & zb.y)) << 31;
+    double hr = 0.0, hi = 0.0;
+    if (kind == 2u || kind == 4u) {  // A[slot] (+ sum over the occupied positions of x' of D[r][slot] for kind 2)
+        const uint32_t slot = (((phi & r4.y) * ENUM_FOLD + (plo & r4.x)) * hdr.x) >> 29;
+        const uint32_t a0 = tile_s + r4.w + 16u + slot * 8u, im_delta = (uint32_t)(kind == 2u ? 1 + n : 1) << (nbits + 3u);
+        hr = lds_f64(a0);
+        if (!REAL) hi = lds_f64(a0 + im_delta);
+        if (kind == 2u) {
+            for (uint32_t w = plo; w; w &= w - 1u) {
+                const uint32_t a = a0 + ((uint32_t)__ffs(w) << (nbits + 3u));  // row 1 + r
+                hr += lds_f64(a);
+                if (!REAL) hi += lds_f64(a + im_delta);
             }
-            if (lane_id() == src) {
-                hr = sr;
-                hi = si;
+            for (uint32_t w = phi; w; w &= w - 1u) {
+                const uint32_t a = a0 + ((uint32_t)(32 + __ffs(w)) << (nbits + 3u));
+                hr += lds_f64(a);
+                if (!REAL) hi += lds_f64(a + im_delta);
             }
         }
-    } else if (HC) {
-        // sample outside the (N_alpha, N_beta) sector: the pattern tables do not apply; PO:256-324 on the untiled term arrays
+        hr = flip_hi(hr, sign);
+        if (!REAL) hi = flip_hi(hi, sign);
+    }
+    unsigned dmask = __ballot_sync(0xffffffffu, kind == 3u);
+    while (dmask) {  // diagonal: K + sum_i n_i (a_i + sum_{j<i} n_j b_ij), orbitals i over the lanes
+        const int src = __ffs(dmask) - 1;
+        dmask &= dmask - 1;
+        const uint64_t xs = __shfl_sync(0xffffffffu, (unsigned long long)ent.x, src);
+        const uint32_t blk = tile_s + __shfl_sync(0xffffffffu, r4.w, src) + 16u;
+        const uint32_t im_delta = (uint32_t)(1 + n + n * n) * 8u;
+        double pr = 0.0, pi = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            if (!((xs >> i) & 1ull)) continue;
+            double ir = lds_f64(blk + 8u + (uint32_t)i * 8u), ii = REAL ? 0.0 : lds_f64(blk + 8u + (uint32_t)i * 8u + im_delta);
+            const uint32_t row = blk + 8u + (uint32_t)n * 8u + (uint32_t)(i * n) * 8u;
+            for (uint64_t w = xs & ((1ull << i) - 1ull); w; w &= w - 1ull) {
+                const uint32_t a = row + (uint32_t)(__ffsll((long long)w) - 1) * 8u;
+                ir += lds_f64(a);
+                if (!REAL) ii += lds_f64(a + im_delta);
+            }
+            pr += ir;
+            pi += ii;
+        }
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) {
+            pr += __shfl_xor_sync(0xffffffffu, pr, dd);
+            if (!REAL) pi += __shfl_xor_sync(0xffffffffu, pi, dd);
+        }
+        if (lane == src) {
+            hr = lds_f64(blk) + pr;
+            if (!REAL) hi = lds_f64(blk + im_delta) + pi;
+        }
+    }
+    const bool fb = active && kind == 0u;  // neither table applies: term records from global memory
+    if (__any_sync(0xffffffffu, fb)) {
         int2 g = make_int2(0, 0);
-        if (active) g = __ldg(t.grp + tl.u0 + ul);
-        warp_matrix_elements<REAL>(t, active, g, deinterleave(xp), hr, hi);
+        if (fb) g = __ldg(t.grp + u0 + k);
+        double gr, gi;
+        warp_matrix_elements<REAL>(t, fb, g, deinterleave(ent.x), gr, gi);
+        if (fb) {
+            hr = gr;
+            hi = gi;
+        }
     }
     if (active) {
-        if (dest) __stcs(dest + r, s);
-        __stcs(reinterpret_cast<long long *>(xprime) + r, (long long)xp);
-        if (xy_ptr) __stcs(xy_ptr + r, (int32_t)(tl.u0 + ul));
+        const int64_t r = (int64_t)(ent.y >> 16);
         if (HC == 1) __stcs(H + r, hr);
         if (HC == 2) __stcs(reinterpret_cast<double2 *>(H) + r, make_double2(hr, hi));
     }
 }
 
+// One unit of a sample OUTSIDE the (N_alpha, N_beta) sector (never produced by the masked samplers, but legal input): the
+// tables do not apply, every matrix element comes from the term arrays in global memory (PO:256-324 as written).
 template <bool REAL, int HC>
+__device__ __noinline__ void et_unit_slow(const Tables *td, uint32_t tile_s, uint32_t u0, int n_words, uint32_t q_s, int64_t s, uint64_t x,
+                                          const uint32_t *row, int64_t out, int32_t *dest, int64_t *xprime, int32_t *xy_ptr, double *H) {
+    const Tables &t = *td;
+    const int lane = lane_id();
+    for (int j = 0; j < n_words; j += ET_STEP_WORDS) {
+        const uint32_t w = (j + lane < n_words) ? __ldg(row + j + lane) : 0u;
+        int lane_start;
+        const int qlen = et_expand(q_s, 0, w, j, lane_start);
+        for (int done = 0; done < qlen; done += 32) {
+            const bool active = done + lane < qlen;
+            const uint32_t k = active ? lds_u16(q_s + 2u * (uint32_t)(done + lane)) : 0u;
+            const uint2 m = lds64(tile_s + k * 16u);
+            const uint64_t xp = x ^ (((uint64_t)m.y << 32) | m.x);
+            double hr = 0.0, hi = 0.0;
+            if (HC) {
+                int2 g = make_int2(0, 0);
+                if (active) g = __ldg(t.grp + u0 + k);
+                warp_matrix_elements<REAL>(t, active, g, deinterleave(xp), hr, hi);
+            }
+            if (active) {
+                const int64_t r = out + done + lane;
+                if (dest) dest[r] = (int32_t)s;
+                xprime[r] = (int64_t)xp;
+                if (xy_ptr) xy_ptr[r] = (int32_t)(u0 + k);
+                if (HC == 1) H[r] = hr;
+                if (HC == 2) reinterpret_cast<double2 *>(H)[r] = make_double2(hr, hi);
+            }
+        }
+        out += qlen;
+        __syncwarp();
+    }
+}
+
+// FLAGS: bit 0 = dest is written, bit 1 = xy_ptr is written
+template <bool REAL, int HC, int FLAGS>
 __global__ void __launch_bounds__(EN_THREADS, 1)
 enum_emit_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int alpha, int beta, const uint32_t *__restrict__ bitmap,
                  const int64_t *__restrict__ offsets, const int32_t *__restrict__ tile_prefix, uint32_t *__restrict__ counters,
-                 int32_t *__restrict__ dest, int64_t *__restrict__ xprime, int32_t *__restrict__ xy_ptr, double *__restrict__ H) {
+                 int64_t band_rows, int grab, ulonglong2 *__restrict__ defer_ws, int32_t *__restrict__ dest, int64_t *__restrict__ xprime, int32_t *__restrict__ xy_ptr,
+                 double *__restrict__ H) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ EnumTile s_tile;
     __shared__ int s_skip;
+    constexpr bool WITH_DEST = (FLAGS & 1) != 0, WITH_PTR = (FLAGS & 2) != 0;
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    uint16_t *q = reinterpret_cast<uint16_t *>(smem_raw) + warp * ET_QCAP;
+    const uint32_t q_s = smem_u32(smem_raw) + (uint32_t)warp * ET_QCAP * 2u + 2u * (uint32_t)lane;  // the lane's own slot of the warp's queue
     unsigned char *tile_buf = smem_raw + ET_QUEUE_BYTES;
+    const uint32_t tile_s = smem_u32(tile_buf);
+    ulonglong2 *dq = defer_ws + ((size_t)blockIdx.x * EN_WARPS + warp) * ENUM_DEFER_CAP;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
     uint32_t parity = 0;
     const int n_tiles = t.n_enum_tiles;
-    int ti = (int)(blockIdx.x % (unsigned)n_tiles);
-    for (int tried = 0; tried < n_tiles; ++tried, ti = (ti + 1 == n_tiles) ? 0 : ti + 1) {
+    // Samples are processed in BANDS of band_rows: all the tiles of one band before the next band.  The twelve or so tile
+    // regions of one sample's output rows are then written within a short time of each other (whatever the relative speed of
+    // the tiles), so they meet in L2 and go to HBM as long contiguous runs instead of 2-3 KB pieces.
+    const int64_t n_bands = (n + band_rows - 1) / band_rows;
+    int resident = -1;  // tile in shared memory (the same value in every thread of the CTA)
+    for (int64_t band = 0; band < n_bands; ++band)
+    for (int tried = 0; tried < n_tiles; ++tried) {
+        const int ti = (int)((blockIdx.x + (unsigned)tried) % (unsigned)n_tiles);
+        const int64_t band0 = band * band_rows, band_len = min(band_rows, n - band0);
+        uint32_t *counter = counters + band * n_tiles + ti;
         __syncthreads();  // every warp is done with the tile that is resident now
         if (threadIdx.x == 0) {
-            const uint32_t taken = *reinterpret_cast<volatile uint32_t *>(counters + ti);
-            s_skip = taken >= (uint64_t)n;
-            if (!s_skip) {
+            const uint32_t taken = *reinterpret_cast<volatile uint32_t *>(counter);
+            s_skip = (int64_t)taken >= band_len;
+            if (!s_skip && ti != resident) {
                 const EnumTile et = t.enum_tiles[ti];
                 s_tile = et;
                 stage_blob(tile_buf, t.enum_blob + et.blob_off, et.blob_bytes, &bar);
@@ -423,74 +543,167 @@ enum_emit_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int a
         }
         __syncthreads();
         if (s_skip) continue;
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
-        const EnumTile et = s_tile;
-        EtTile tl;
-        tl.xy = reinterpret_cast<const uint64_t *>(tile_buf);
-        tl.zb = tl.xy + et.n_masks;
-        tl.desc = reinterpret_cast<const uint2 *>(tl.zb + et.n_masks);
-        tl.tab = reinterpret_cast<const double *>(tile_buf + et.tab_off);
-        tl.term = reinterpret_cast<const uint4 *>(tile_buf + et.term_off);
-        tl.wim = reinterpret_cast<const double *>(tile_buf + et.term_off + (size_t)et.n_terms * 16);
-        tl.u0 = et.u0;
-        tl.n_tab = et.n_tab;
-        const int n_words = (int)et.n_words;
-        for (;;) {
-            uint32_t s32 = 0;
-            if (lane == 0) s32 = atomicAdd(counters + ti, 1u);
-            s32 = __shfl_sync(0xffffffffu, s32, 0);
-            if ((int64_t)s32 >= n) break;
-            const int64_t s = (int64_t)s32;
-            const uint64_t x = (uint64_t)samples[s];
-            const bool in_sector = __popcll(x & 0x5555555555555555ULL) == alpha && __popcll(x & 0xAAAAAAAAAAAAAAAAULL) == beta;
-            int64_t out = offsets[s] + tile_prefix[s * n_tiles + ti];
-            const uint32_t *row = bitmap + s * t.row_words + et.word0;
-            int qlen = 0;
-            uint32_t wnext = lane < n_words ? __ldg(row + lane) : 0u;
-            for (int j = 0; j < n_words; j += 32) {
-                const uint32_t wfull = wnext;
-                wnext = (j + 32 + lane < n_words) ? __ldg(row + j + 32 + lane) : 0u;
-                {
-                    uint32_t w = wfull;
-                    const int c = __popc(w);
-                    int inc = c;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int o = __shfl_up_sync(0xffffffffu, inc, d);
-                        if (lane >= d) inc += o;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, inc, 31);
-                    if (total == 0) continue;
-                    uint16_t *qp = q + (qlen + inc - c);
-                    uint32_t base = (uint32_t)(j + lane) << 5;
-                    while (w) {
-                        const int bit = __ffs(w) - 1;
-                        w &= w - 1;
-                        *qp++ = (uint16_t)(base + bit);
-                    }
-                    __syncwarp();
-                    qlen += total;
-                    int done = 0;
-                    while (qlen - done >= 32) {
-                        et_emit_batch<REAL, HC>(t, tl, x, in_sector, (int)s, true, q[done + lane], out + done + lane, dest, xprime, xy_ptr, H);
-                        done += 32;
-                    }
-                    if (done > 0) {
-                        const int rem = qlen - done;
-                        const uint16_t v = lane < rem ? q[done + lane] : (uint16_t)0;
-                        __syncwarp();
-                        if (lane < rem) q[lane] = v;
-                        __syncwarp();
-                        out += done;
-                        qlen = rem;
-                    }
+        const bool fresh = ti != resident;
+        resident = ti;
+        const uint32_t u0 = s_tile.u0, im_delta = s_tile.n_tab * 8u, word0 = s_tile.word0, gen_s = tile_s + s_tile.gen_off;
+        const int n_words = (int)s_tile.n_words;
+        // Units are taken `grab` at a time: lane i of the warp loads the sample, output offset and tile rank of unit i in one
+        // round trip, the units are then processed in turn with their values broadcast from the lanes.  The next group's
+        // ticket is requested one group ahead and its per-unit values are loaded while the last unit of the current group is
+        // processed; the bitmap words of every step are loaded one step ahead, across unit and group boundaries.  Nothing
+        // of a unit waits on global memory except the very first group of a tile.
+        auto take = [&]() -> uint32_t {  // lane 0 holds the result
+            uint32_t v = 0;
+            if (lane == 0) v = atomicAdd(counter, (uint32_t)grab);
+            return v;
+        };
+        auto load_meta = [&](uint32_t base, uint64_t &xs, int64_t &os) {
+            xs = 0ull;
+            os = 0;
+            const int64_t sidx = band0 + (int64_t)base + lane;
+            if (lane < grab && (int64_t)base + lane < band_len) {
+                xs = (uint64_t)__ldg(samples + sidx);
+                os = __ldg(offsets + sidx) + __ldg(tile_prefix + sidx * n_tiles + ti);
+            }
+        };
+        uint32_t base = take();
+        if (fresh) {
+            mbar_wait(&bar, parity);
+            parity ^= 1u;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t nbase = take();  // lane 0; read one group later
+        uint64_t xs;
+        int64_t os;
+        load_meta(base, xs, os);
+        uint32_t wnext = 0u;
+        if ((int64_t)base < band_len && lane < n_words) wnext = __ldg(bitmap + (band0 + (int64_t)base) * t.row_words + word0 + lane);
+        int ndef = 0;  // deferred connections of this warp for the resident tile
+        while ((int64_t)base < band_len) {
+          const int cnt = (int)min((int64_t)grab, band_len - (int64_t)base);
+          uint32_t base2 = 0xffffffffu, nbase2 = 0u;
+          uint64_t xs2 = 0ull;
+          int64_t os2 = 0;
+          for (int ui = 0; ui < cnt; ++ui) {
+            const int64_t s = band0 + (int64_t)base + ui;
+            const bool last_unit = ui == cnt - 1;
+            if (last_unit) {  // the next group: its ticket has been in flight for a whole group
+                base2 = __shfl_sync(0xffffffffu, nbase, 0);
+                if ((int64_t)base2 < band_len) {
+                    nbase2 = take();
+                    load_meta(base2, xs2, os2);
                 }
             }
-            if (qlen > 0)
-                et_emit_batch<REAL, HC>(t, tl, x, in_sector, (int)s, lane < qlen, lane < qlen ? q[lane] : (uint16_t)0, out + lane, dest, xprime,
-                                        xy_ptr, H);
+            const uint64_t x = __shfl_sync(0xffffffffu, (unsigned long long)xs, ui);
+            const int64_t out0 = (int64_t)__shfl_sync(0xffffffffu, (unsigned long long)os, ui);
+            const uint32_t *row = bitmap + s * t.row_words + word0;
+            // first words of the unit that follows this one (next unit of the group, or first unit of the next group)
+            const uint32_t *row_after = last_unit ? (((int64_t)base2 < band_len) ? bitmap + (band0 + (int64_t)base2) * t.row_words + word0 : nullptr)
+                                                  : row + t.row_words;
+            if (__popcll(x & 0x5555555555555555ULL) != alpha || __popcll(x & 0xAAAAAAAAAAAAAAAAULL) != beta) {
+                et_unit_slow<REAL, HC>(t.dev_copy, tile_s, u0, n_words, q_s - 2u * (uint32_t)lane, s, x, row, out0, WITH_DEST ? dest : nullptr, xprime, WITH_PTR ? xy_ptr : nullptr, H);
+                wnext = (row_after && lane < n_words) ? __ldg(row_after + lane) : 0u;
+                continue;
+            }
+            const uint32_t xlo = (uint32_t)x, xhi = (uint32_t)(x >> 32);
+            // exclusive prefix parity of the sample: bit i = parity of the bits of x below i (the Jordan-Wigner sign of a
+            // pattern connection is parity(S & xy), see analyse_group in abi_core.cu)
+            uint64_t S = x;
+            S ^= S << 1; S ^= S << 2; S ^= S << 4; S ^= S << 8; S ^= S << 16; S ^= S << 32;
+            S <<= 1;
+            const uint32_t slo = (uint32_t)S, shi = (uint32_t)(S >> 32);
+            EtOut o;
+            o.dest = WITH_DEST ? dest + out0 + lane : nullptr;
+            o.xprime = reinterpret_cast<long long *>(xprime) + out0 + lane;
+            o.xy_ptr = WITH_PTR ? xy_ptr + out0 + lane : nullptr;
+            o.H = HC ? H + (int64_t)HC * (out0 + lane) : nullptr;
+            int emitted = 0;  // connections of this unit already handed to a batch
+            int qlen = 0;
+
+            // one batch: the connection of lane l is queue entry `from + l`
+            auto batch = [&](int from, bool active) {
+                const uint32_t k = active ? lds_u16(q_s + 2u * (uint32_t)from) : 0u;
+                const uint4 r4 = lds128(tile_s + k * 16u);
+                const uint32_t plo = xlo ^ r4.x, phi = xhi ^ r4.y;
+                const uint64_t xp = ((uint64_t)phi << 32) | plo;
+                if (active) {
+                    if (WITH_DEST) __stcs(o.dest, (int32_t)s);
+                    __stcs(o.xprime, (long long)xp);
+                    if (WITH_PTR) __stcs(o.xy_ptr, (int32_t)(u0 + k));
+                }
+                if (WITH_DEST) o.dest += 32;
+                o.xprime += 32;
+                if (WITH_PTR) o.xy_ptr += 32;
+                if (HC) {  // generic connections (mult = 0) were put on the deferred list when their bits were expanded
+                    const uint32_t sign = (uint32_t)__popc((slo & r4.x) ^ (shi & r4.y)) << 31;
+                    const uint32_t slot = (((phi & r4.y) * ENUM_FOLD + (plo & r4.x)) * r4.z) >> 29;
+                    const uint32_t g = tile_s + r4.w + slot * 8u;
+                    const double hr = flip_hi(lds_f64(g), sign);
+                    if (active && r4.z != 0u) {
+                        if (HC == 1) __stcs(o.H, hr);
+                        if (HC == 2) __stcs(reinterpret_cast<double2 *>(o.H), make_double2(hr, REAL ? 0.0 : flip_hi(lds_f64(g + im_delta), sign)));
+                    }
+                    o.H += 32 * HC;
+                }
+                emitted += 32;
+            };
+
+            for (int j = 0; j < n_words; j += ET_STEP_WORDS) {
+                const uint32_t w = wnext;
+                if (j + ET_STEP_WORDS < n_words) wnext = (j + ET_STEP_WORDS + lane < n_words) ? __ldg(row + j + ET_STEP_WORDS + lane) : 0u;
+                else wnext = (row_after && lane < n_words) ? __ldg(row_after + lane) : 0u;
+                int lane_start;
+                const int added = et_expand(q_s - 2u * (uint32_t)lane, qlen, w, j, lane_start);
+                if (HC) {  // bits of generic masks in this step: onto the deferred list, with their output positions
+                    uint32_t gw = (j + lane < n_words) ? (w & lds32(gen_s + 4u * (uint32_t)(j + lane))) : 0u;
+                    unsigned dm = __ballot_sync(0xffffffffu, gw != 0u);
+                    while (dm) {
+                        if (gw) {
+                            const uint32_t bit = (uint32_t)__ffs(gw) - 1u;
+                            gw &= gw - 1u;
+                            const uint32_t k = ((uint32_t)(j + lane) << 5) + bit;
+                            const uint2 m = lds64(tile_s + k * 16u);
+                            const int64_t p = out0 + emitted + lane_start + __popc(w & ((1u << bit) - 1u));
+                            dq[ndef + __popc(dm & lanemask_lt())] =
+                                make_ulonglong2((((uint64_t)(xhi ^ m.y)) << 32) | (xlo ^ m.x), ((unsigned long long)p << 16) | k);
+                        }
+                        ndef += __popc(dm);
+                        __syncwarp();
+                        if (ndef >= 32) {
+                            const ulonglong2 ent = __ldcg(dq + lane);
+                            et_eval_deferred<REAL, HC>(t.dev_copy, tile_s, u0, ent, true, H);
+                            const ulonglong2 mv = (32 + lane < ndef) ? __ldcg(dq + 32 + lane) : make_ulonglong2(0ull, 0ull);
+                            __syncwarp();
+                            if (32 + lane < ndef) dq[lane] = mv;
+                            ndef -= 32;
+                            __syncwarp();
+                        }
+                        dm = __ballot_sync(0xffffffffu, gw != 0u);
+                    }
+                }
+                qlen += added;
+                int done = 0;
+                for (; qlen - done >= 32; done += 32) batch(done, true);
+                if (done > 0) {  // move the remainder (< 32 entries) to the front of the queue
+                    const int rem = qlen - done;
+                    const uint32_t v = lane < rem ? lds_u16(q_s + 2u * (uint32_t)done) : 0u;
+                    __syncwarp();
+                    if (lane < rem) sts_u16(q_s, v);
+                    __syncwarp();
+                    qlen = rem;
+                }
+            }
+            if (qlen > 0) batch(0, lane < qlen);
             __syncwarp();
+          }
+          base = base2;
+          nbase = nbase2;
+          xs = xs2;
+          os = os2;
+        }
+        if (HC && ndef > 0) {  // what is left of the deferred list before the tile goes away
+            const ulonglong2 ent = lane < ndef ? __ldcg(dq + lane) : make_ulonglong2(0ull, 0ull);
+            et_eval_deferred<REAL, HC>(t.dev_copy, tile_s, u0, ent, lane < ndef, H);
         }
     }
 }
@@ -516,9 +729,24 @@ static bool tiled_available(const Tables *t) {
            ET_QUEUE_BYTES + t->enum_tile_bytes_max + 256 <= EN_SMEM_MAX;
 }
 
-static bool g_force_product_filter = false;  // test hook (anqs_k1_enum_force_product_filter)
-
-static size_t counters_bytes(const Tables *t) { return ((size_t)t->n_enum_tiles * 4 + 127) / 128 * 128; }
+// rows per band of the emit kernel (see enum_emit_kernel); ANQS_ENUM_BAND_ROWS overrides it for experiments
+static int64_t emit_band_rows() {
+    static int64_t cached = 0;
+    if (cached == 0) {
+        const char *e = getenv("ANQS_ENUM_BAND_ROWS");
+        const long long v = e ? atoll(e) : 0;
+        cached = v >= 32 ? (int64_t)v : ((int64_t)1 << 40);
+    }
+    return cached;
+}
+static int64_t emit_bands(int64_t n) { return std::max<int64_t>(1, (n + emit_band_rows() - 1) / emit_band_rows()); }
+static size_t counters_bytes(const Tables *t, int64_t n) {
+    return ((size_t)emit_bands(n) * (size_t)std::max(1, t->n_enum_tiles) * 4 + 127) / 128 * 128;
+}
+static size_t prefix_bytes(const Tables *t, int64_t n) {
+    return ((size_t)n * (size_t)std::max(1, t->n_enum_tiles) * sizeof(int32_t) + 127) / 128 * 128;
+}
+static size_t defer_bytes() { return (size_t)sm_count_of_current_device() * EN_WARPS * ENUM_DEFER_CAP * sizeof(ulonglong2); }
 
 }  // namespace anqs
 
@@ -532,28 +760,33 @@ int anqs_k1_enum_tiles(const anqs_tables_t *h) {
     return tiled_available(t) ? t->n_enum_tiles : 0;
 }
 
-void anqs_k1_enum_force_product_filter(int on) { g_force_product_filter = on != 0; }
-
 size_t anqs_k1_enum_workspace(const anqs_tables_t *h, int64_t n) {
     if (!h || n < 0) return 0;
     const Tables *t = (const Tables *)h;
-    return counters_bytes(t) + (size_t)n * (size_t)std::max(1, t->n_enum_tiles) * sizeof(int32_t);
+    // [tile counters][tile_prefix: n x n_tiles int32][deferred lists of the emit kernel: one per warp]
+    return counters_bytes(t, n) + prefix_bytes(t, n) + defer_bytes();
 }
 
 int anqs_k1_enum_filter(const anqs_tables_t *h, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
                         int64_t *d_counts, uint32_t *d_bitmap, void *d_work, void *stream) {
+    return anqs_k1_enum_filter_variant(h, d_samples, n, alpha_num, beta_num, d_counts, d_bitmap, d_work, 0, stream);
+}
+
+int anqs_k1_enum_filter_variant(const anqs_tables_t *h, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
+                                int64_t *d_counts, uint32_t *d_bitmap, void *d_work, int variant, void *stream) {
     ANQS_REQUIRE(h, "null tables handle");
+    ANQS_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (automatic) or 1 (product-layout filter)");
     ANQS_REQUIRE(n >= 0, "negative sample count");
     if (n == 0) return 0;
     const Tables *t = (const Tables *)h;
     ANQS_REQUIRE(tiled_available(t), "the tiled enumeration is unavailable for this table (anqs_k1_enum_tiles() == 0): use anqs_k1_filter / anqs_k1_emit");
     ANQS_REQUIRE(d_samples && d_counts && d_bitmap && d_work, "null pointer");
-    if (bitsliced_available(t) && !g_force_product_filter) {
+    if (bitsliced_available(t) && variant != 1) {
         const size_t smem = bitsliced_smem(t);
         ANQS_CUDA(cudaFuncSetAttribute(enum_filter_bitsliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(EN_SMEM_MAX - 1024) / (smem + 1024)));
         const int grid = (int)std::min<int64_t>((n + 31) / 32, (int64_t)sm_count_of_current_device() * per_sm);
-        int32_t *tile_prefix = reinterpret_cast<int32_t *>((unsigned char *)d_work + counters_bytes(t));
+        int32_t *tile_prefix = reinterpret_cast<int32_t *>((unsigned char *)d_work + counters_bytes(t, n));
         enum_filter_bitsliced_kernel<<<grid, BS_THREADS, smem, (cudaStream_t)stream>>>(*t, d_samples, n, alpha_num, beta_num, d_counts,
                                                                                        d_bitmap, tile_prefix, bitsliced_chunk(t));
         ANQS_LAUNCH_CHECK();
@@ -565,7 +798,7 @@ int anqs_k1_enum_filter(const anqs_tables_t *h, const int64_t *d_samples, int64_
     ANQS_CUDA(cudaFuncSetAttribute(enum_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t ngroups = (n + warps - 1) / warps;
     const int grid = (int)std::min<int64_t>(ngroups, sm_count_of_current_device());
-    int32_t *tile_prefix = reinterpret_cast<int32_t *>((unsigned char *)d_work + counters_bytes(t));
+    int32_t *tile_prefix = reinterpret_cast<int32_t *>((unsigned char *)d_work + counters_bytes(t, n));
     enum_filter_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(*t, d_samples, n, alpha_num, beta_num, d_counts, d_bitmap,
                                                                           tile_prefix, bm_bytes);
     ANQS_LAUNCH_CHECK();
@@ -587,22 +820,40 @@ int anqs_k1_enum_emit(const anqs_tables_t *h, const int64_t *d_samples, int64_t 
     ANQS_REQUIRE(!(hc == 1 && !t->weights_real), "real matrix elements requested but the Hamiltonian weights are complex");
     cudaStream_t s = (cudaStream_t)stream;
     uint32_t *counters = reinterpret_cast<uint32_t *>(d_work);
-    const int32_t *tile_prefix = reinterpret_cast<const int32_t *>((unsigned char *)d_work + counters_bytes(t));
-    ANQS_CUDA(cudaMemsetAsync(counters, 0, counters_bytes(t), s));
+    const int32_t *tile_prefix = reinterpret_cast<const int32_t *>((unsigned char *)d_work + counters_bytes(t, n));
+    ANQS_CUDA(cudaMemsetAsync(counters, 0, counters_bytes(t, n), s));
+    ulonglong2 *defer_ws = reinterpret_cast<ulonglong2 *>((unsigned char *)d_work + counters_bytes(t, n) + prefix_bytes(t, n));
     const size_t smem = (size_t)ET_QUEUE_BYTES + (size_t)t->enum_tile_bytes_max;
     const int grid = sm_count_of_current_device();
+    const int flags = (d_dest ? 1 : 0) | (d_xy_ptr ? 2 : 0);
+    // units a warp takes per ticket (<= 32): about a sixth of its share of one band of one tile, so the tail stays short
+    int grab = 1;
+    {
+        const int64_t warps_per_tile = std::max<int64_t>(1, (int64_t)grid * EN_WARPS / std::max(1, t->n_enum_tiles));
+        const int64_t share = std::min<int64_t>(n, emit_band_rows()) / (warps_per_tile * 6);
+        while (grab * 2 <= share && grab < 32) grab *= 2;
+        if (const char *e = getenv("ANQS_ENUM_GRAB")) grab = std::max(1, std::min(32, atoi(e)));
+    }
+#define ANQS_ENUM_EMIT_F(REAL, HC, FLAGS)                                                                                     \
+    do {                                                                                                                      \
+        auto kern = enum_emit_kernel<REAL, HC, FLAGS>;                                                                        \
+        ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+        kern<<<grid, EN_THREADS, smem, s>>>(*t, d_samples, n, alpha_num, beta_num, d_bitmap, d_offsets, tile_prefix, counters, emit_band_rows(), grab, defer_ws, d_dest,   \
+                                            d_xprime, d_xy_ptr, d_H);                                                         \
+    } while (0)
 #define ANQS_ENUM_EMIT(REAL, HC)                                                                                              \
     do {                                                                                                                      \
-        auto kern = enum_emit_kernel<REAL, HC>;                                                                               \
-        ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
-        kern<<<grid, EN_THREADS, smem, s>>>(*t, d_samples, n, alpha_num, beta_num, d_bitmap, d_offsets, tile_prefix, counters, d_dest, d_xprime,   \
-                                            d_xy_ptr, d_H);                                                                   \
+        if (flags == 0) ANQS_ENUM_EMIT_F(REAL, HC, 0);                                                                        \
+        else if (flags == 1) ANQS_ENUM_EMIT_F(REAL, HC, 1);                                                                   \
+        else if (flags == 2) ANQS_ENUM_EMIT_F(REAL, HC, 2);                                                                   \
+        else ANQS_ENUM_EMIT_F(REAL, HC, 3);                                                                                   \
     } while (0)
     if (hc == 0) ANQS_ENUM_EMIT(true, 0);
     else if (t->weights_real && hc == 1) ANQS_ENUM_EMIT(true, 1);
     else if (t->weights_real && hc == 2) ANQS_ENUM_EMIT(true, 2);
     else ANQS_ENUM_EMIT(false, 2);
 #undef ANQS_ENUM_EMIT
+#undef ANQS_ENUM_EMIT_F
     ANQS_LAUNCH_CHECK();
     return 0;
 }

@@ -276,7 +276,15 @@ extern "C" {
 int anqs_local_energy_sample_aware(const anqs_tables_t *h, const int64_t *d_samples, const double *d_amps,
                                    int64_t n_total, int64_t row_start, int64_t row_len, const void *d_table,
                                    int64_t capacity, int alpha_num, int beta_num, double *d_eloc, void *stream) {
+    return anqs_local_energy_sample_aware_variant(h, d_samples, d_amps, n_total, row_start, row_len, d_table, capacity, alpha_num, beta_num,
+                                                  d_eloc, 0, stream);
+}
+
+int anqs_local_energy_sample_aware_variant(const anqs_tables_t *h, const int64_t *d_samples, const double *d_amps,
+                                           int64_t n_total, int64_t row_start, int64_t row_len, const void *d_table,
+                                           int64_t capacity, int alpha_num, int beta_num, double *d_eloc, int variant, void *stream) {
     ANQS_REQUIRE(h, "null tables handle");
+    ANQS_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0 (automatic), 1 (warp-per-sample kernel) or 2 (bit-sliced kernel)");
     ANQS_REQUIRE(row_start >= 0 && row_len >= 0 && row_start + row_len <= n_total, "row window out of range");
     if (row_len == 0) return 0;
     ANQS_REQUIRE(d_samples && d_amps && d_table && d_eloc, "null pointer");
@@ -288,7 +296,7 @@ int anqs_local_energy_sample_aware(const anqs_tables_t *h, const int64_t *d_samp
     const int grid = (int)std::min<int64_t>(ngroups, sm_count_of_current_device());
     cudaStream_t s = (cudaStream_t)stream;
     {   // bit-sliced kernel (k1_fused_bs.cu) whenever the table allows it
-        const int rc = fused_bs_try_launch(t, hv, d_samples, d_amps, row_start, row_len, alpha_num, beta_num, d_eloc, s);
+        const int rc = fused_bs_try_launch(t, hv, d_samples, d_amps, row_start, row_len, alpha_num, beta_num, d_eloc, variant, s);
         ANQS_REQUIRE(rc >= 0, "cudaFuncSetAttribute failed for the bit-sliced kernel");
         if (rc == 1) {
             ANQS_LAUNCH_CHECK();

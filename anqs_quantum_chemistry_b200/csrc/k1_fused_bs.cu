@@ -395,18 +395,17 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
     }
 }
 
-static int g_fused_choice = 0;  // test hook (anqs_local_energy_force_per_sample_kernel): 0 = by batch size, 1 = per-sample, 2 = bit-sliced
-
 // returns 1 when it launched, 0 when the bit-sliced kernel does not apply (the caller falls back), < 0 on error
+// variant: 0 = chosen by batch size, 1 = never (the caller's warp-per-sample kernel), 2 = always when the table allows it
 int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, const double *d_amps, int64_t row_start,
-                        int64_t row_len, int alpha_num, int beta_num, double *d_eloc, cudaStream_t s) {
-    if (g_fused_choice == 1 || !t->prod_bs_ok) return 0;
+                        int64_t row_len, int alpha_num, int beta_num, double *d_eloc, int variant, cudaStream_t s) {
+    if (variant == 1 || !t->prod_bs_ok) return 0;
     const size_t smem = (size_t)FB_WARPS * sizeof(FbSlot) + FB_QUEUE_BYTES + (size_t)t->tile_bytes_max;
     if (smem + 256 > 227 * 1024) return 0;
     const int sms = sm_count_of_current_device();
     const int64_t ngroups = (row_len + 31) / 32;
     // small batches leave most SMs without a group: the warp-per-sample kernel spreads them better
-    if (g_fused_choice == 0 && ngroups < (int64_t)sms * 8) return 0;
+    if (variant == 0 && ngroups < (int64_t)sms * 8) return 0;
     // S groups per CTA iteration, R = FB_WARPS / S warps per group: as few groups per CTA as spreads them over all the SMs
     const int S = (int)std::min<int64_t>(FB_WARPS, (ngroups + sms - 1) / sms);
     const int R = FB_WARPS / S;
@@ -416,6 +415,7 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
     // ask for the filter to be kept as persisting L2 lines for this launch.  Best effort - every call may be refused.
     const size_t filter_bytes = ((size_t)hv.linemask + 1) * 128;
     bool window = false;
+    cudaStreamAttrValue prev_attr = {};
     if (filter_bytes > ((size_t)16 << 20)) {
         int dev = 0, max_persist = 0, max_window = 0;
         cudaGetDevice(&dev);
@@ -432,6 +432,8 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
             attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)filter_bytes);
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            // the caller's own window (if any) is put back after the launch
+            if (cudaStreamGetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &prev_attr) != cudaSuccess) prev_attr = cudaStreamAttrValue{};
             window = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
         }
         cudaGetLastError();  // refusals are not errors of this call
@@ -442,10 +444,8 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
     if (e != cudaSuccess) return -1;
     kern<<<grid, FB_THREADS, smem, s>>>(*t, hv, d_samples, (const double2 *)d_amps, row_start, row_len, alpha_num, beta_num,
                                         (double2 *)d_eloc, S, R);
-    if (window) {  // the window applies to the launches issued while it is set: clear it again
-        cudaStreamAttrValue attr = {};
-        attr.accessPolicyWindow.num_bytes = 0;
-        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+    if (window) {  // the window applies to the launches issued while it is set: restore what the stream had before
+        cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &prev_attr);
         cudaGetLastError();
     }
     return 1;
@@ -453,4 +453,3 @@ int fused_bs_try_launch(const Tables *t, HashView hv, const int64_t *d_samples, 
 
 }  // namespace anqs
 
-extern "C" void anqs_local_energy_force_per_sample_kernel(int on) { anqs::g_fused_choice = on; }

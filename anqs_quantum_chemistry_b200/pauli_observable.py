@@ -198,12 +198,13 @@ class PauliObservable(AbstractHilbertSpaceObject):
 
     # ---- kernel 1: connected configurations -------------------------------------------------------------
     def connected_configurations(self, samples: pt.Tensor, alpha_num: int, beta_num: int, with_dest: bool = True,
-                                 with_xy_ptr: bool = True, matrix_elements: str = None, tiled: bool = None):
+                                 with_xy_ptr: bool = True, matrix_elements: str = None, tiled: bool = None, filter_variant: int = 0):
         """Connected list of a batch of packed samples [n] int64, lexicographic in (dest, xy_ptr) like
         PO:527-567.  matrix_elements in (None, 'real', 'complex').  Returns a dict with offsets [n+1] int64,
         dest int32 [M], xprime int64 [M], xy_ptr int32 [M], H.
         tiled: None = the tile-resident kernels (k1_enum.cu) whenever the table fits them, else the untiled pair
-        (k1_connected.cu); True / False force one or the other.  Both give the same list bit for bit."""
+        (k1_connected.cu); True / False force one or the other.  Both give the same list bit for bit.
+        filter_variant (tiled path): 0 = bit-sliced filter when the table allows it, 1 = product-layout filter."""
         tables = self.tables
         dev = self.device
         samples = samples.contiguous().view(-1)
@@ -218,8 +219,8 @@ class PauliObservable(AbstractHilbertSpaceObject):
         enum_work = None
         if tiled:
             enum_work = pt.empty(max(1, (int(lib.anqs_k1_enum_workspace(tables, n)) + 3) // 4), dtype=pt.int32, device=dev)
-            _lib.check(lib.anqs_k1_enum_filter(tables, _lib.dptr(samples), n, alpha_num, beta_num, _lib.dptr(counts), _lib.dptr(bitmap),
-                                               _lib.dptr(enum_work), sp))
+            _lib.check(lib.anqs_k1_enum_filter_variant(tables, _lib.dptr(samples), n, alpha_num, beta_num, _lib.dptr(counts), _lib.dptr(bitmap),
+                                                       _lib.dptr(enum_work), int(filter_variant), sp))
         else:
             _lib.check(lib.anqs_k1_filter(tables, _lib.dptr(samples), n, alpha_num, beta_num, _lib.dptr(counts), _lib.dptr(bitmap), sp))
         offsets = pt.empty(n + 1, dtype=pt.int64, device=dev)
@@ -296,10 +297,11 @@ class PauliObservable(AbstractHilbertSpaceObject):
                                        chunk_size: int = 20000, alpha_num: int = None, beta_num: int = None,
                                        matrix_element_chunk_size: int = np.inf,
                                        row_start: int = 0, row_len: int = None,
-                                       table: SampleTable = None) -> Tuple[pt.Tensor, pt.Tensor, LocalEnergyMetrics]:
+                                       table: SampleTable = None, kernel_variant: int = 0) -> Tuple[pt.Tensor, pt.Tensor, LocalEnergyMetrics]:
         """PO:396-487.  Sample-aware local energies of the whole batch in one fused launch; `chunk_size` and
         `matrix_element_chunk_size` are accepted for signature compatibility (nothing is materialised, so
-        there is nothing to chunk).  row_start/row_len/table are extensions used by the multi-GPU shard path."""
+        there is nothing to chunk).  row_start/row_len/table are extensions used by the multi-GPU shard path;
+        kernel_variant: 0 = kernel chosen by batch size, 1 = warp-per-sample kernel, 2 = bit-sliced kernel."""
         assert coupling_method in self.ALLOWED_COUPLING_METHODS
         if coupling_method == 'hamming_ball':
             raise NotImplementedError("coupling_method='hamming_ball' is broken in the reference (pauli_observable.py:698)")
@@ -312,9 +314,10 @@ class PauliObservable(AbstractHilbertSpaceObject):
         if table is None:
             table = SampleTable(samples, amps)
         eloc = pt.empty(row_len, dtype=pt.complex128, device=dev)
-        _lib.check(_lib.lib().anqs_local_energy_sample_aware(
+        _lib.check(_lib.lib().anqs_local_energy_sample_aware_variant(
             self.tables, _lib.dptr(samples), _lib.dptr(pt.view_as_real(amps)), n, row_start, row_len,
-            _lib.dptr(table.slots), table.capacity, alpha_num, beta_num, _lib.dptr(pt.view_as_real(eloc)), _lib.stream_ptr(dev)))
+            _lib.dptr(table.slots), table.capacity, alpha_num, beta_num, _lib.dptr(pt.view_as_real(eloc)), int(kernel_variant),
+            _lib.stream_ptr(dev)))
         return eloc, eloc, LocalEnergyMetrics()
 
     @pt.no_grad()

@@ -83,19 +83,22 @@ int anqs_k1_emit(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, co
 
 /* ---- A2+A3+A6  kernel 1, tiled variant: the same ordered list at HBM-write speed (PO:527-567 + PO:256-324) ---------
  * Same bitmap, counts and output rows as anqs_k1_filter / anqs_k1_emit (the two pairs are interchangeable bit for bit); the
- * masks are cut into "enumeration tiles" (contiguous mask ranges with the term records of their YZ groups) that a CTA keeps
- * resident in shared memory, so matrix-element sums never go to L2.  anqs_k1_enum_tiles() == 0 means the table does not
- * fit the tiled layout (a YZ group larger than a tile, or bitmap rows too long for shared memory): use the pair above.
+ * masks are cut into "enumeration tiles" (contiguous mask ranges with the matrix-element tables of their YZ groups) that a
+ * CTA keeps resident in shared memory, so matrix elements never go to L2.  anqs_k1_enum_tiles() == 0 means the table does
+ * not fit the tiled layout (bitmap rows too long for shared memory): use the pair above.
  * d_work: anqs_k1_enum_workspace(t, n) bytes, 128-byte aligned, written by the filter (the rank of every tile's first
  * connection inside each sample) and consumed by the emit; both calls must be ordered on the same stream.
  * d_counts and d_bitmap are mandatory here; d_offsets = exclusive scan of d_counts (anqs_exclusive_scan_i64). */
 int anqs_k1_enum_tiles(const anqs_tables_t *t);
-/* Test hook: the filter has two implementations, a bit-sliced one (32 samples per lane operation; needs every spin part of
- * every mask to have weight <= 4) and a product-layout one (any table); on != 0 forces the second. */
-void anqs_k1_enum_force_product_filter(int on);
 size_t anqs_k1_enum_workspace(const anqs_tables_t *t, int64_t n);
 int anqs_k1_enum_filter(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
                         int64_t *d_counts, uint32_t *d_bitmap, void *d_work, void *stream);
+/* Same with the implementation picked by an ARGUMENT (no process-global state; safe from any number of host threads): the
+ * filter has a bit-sliced implementation (32 samples per lane operation; needs every spin part of every mask to have
+ * weight <= 4) and a product-layout one (any table).  variant 0 = the bit-sliced one when it applies (what the call above
+ * does), 1 = the product-layout one.  Both produce the same bytes. */
+int anqs_k1_enum_filter_variant(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
+                                int64_t *d_counts, uint32_t *d_bitmap, void *d_work, int variant, void *stream);
 int anqs_k1_enum_emit(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
                       const uint32_t *d_bitmap, const int64_t *d_offsets, void *d_work, int32_t *d_dest, int64_t *d_xprime, int32_t *d_xy_ptr,
                       double *d_H, int h_components, void *stream);
@@ -136,10 +139,14 @@ int anqs_local_energy_sample_aware(const anqs_tables_t *t, const int64_t *d_samp
                                    int64_t n_total, int64_t row_start, int64_t row_len, const void *d_table,
                                    int64_t capacity, int alpha_num, int beta_num, double *d_eloc, void *stream);
 
-/* Test hook: the call above runs a bit-sliced kernel (a warp per group of 32 samples; needs every spin part of every mask
- * to have weight <= 4) for batches of >= 256 rows per SM and a warp-per-sample kernel otherwise.
- * on = 1 forces the warp-per-sample kernel, 2 the bit-sliced one (where it applies), 0 restores the choice by size. */
-void anqs_local_energy_force_per_sample_kernel(int on);
+/* Same with the kernel picked by an ARGUMENT (no process-global state): the call above runs a bit-sliced kernel (a warp per
+ * group of 32 samples; needs every spin part of every mask to have weight <= 4) for batches of >= 256 rows per SM and a
+ * warp-per-sample kernel otherwise.  variant 0 = that choice, 1 = the warp-per-sample kernel, 2 = the bit-sliced one
+ * wherever the table allows it.  All give the same local energies (order of the fp64 additions aside). */
+int anqs_local_energy_sample_aware_variant(const anqs_tables_t *t, const int64_t *d_samples, const double *d_amps,
+                                           int64_t n_total, int64_t row_start, int64_t row_len, const void *d_table,
+                                           int64_t capacity, int alpha_num, int beta_num, double *d_eloc, int variant,
+                                           void *stream);
 
 /* ---- A7  scatter of the materialised list (PO:453-478 / PO:1048-1057): E[dest] += H * psi(src) -------
  * d_src_ptr[r] = index of x'_r in the sampled set or -1 (skipped).  Rows must be grouped by dest through

@@ -40,12 +40,10 @@ with tempfile.TemporaryDirectory() as tmp:
     table = SampleTable(s, a)
     res = {}
     for choice in (1, 2):
-        lib.anqs_local_energy_force_per_sample_kernel(choice)
-        f = lambda: ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s.view(-1, 1), unq_batch_as_amps=a, coupling_method='ham',
-                                                       alpha_num=na, beta_num=nb, table=table)[0]
+        f = lambda choice=choice: ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s.view(-1, 1), unq_batch_as_amps=a, coupling_method='ham',
+                                                                     alpha_num=na, beta_num=nb, table=table, kernel_variant=choice)[0]
         res[choice] = f()
         print(('per-sample' if choice == 1 else 'bit-sliced'), f'fused kernel, {s.shape[0]} rows: {tm(f):.2f} ms', flush=True)
-    lib.anqs_local_energy_force_per_sample_kernel(0)
     err = float((res[1] - res[2]).abs().max())
     print(f'fused kernels agree to {err:.2e} (scale {float(res[1].abs().max()):.2e})')
     assert err < 1e-11 * max(1.0, float(res[1].abs().max()))

@@ -32,9 +32,7 @@ def run(n, n_el, irreps, rows, timing=False, complex_w=False, off_sector=False):
         me = 'real' if ham.weights_real else 'complex'
         a = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=False)
         b = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True)
-        _lib.lib().anqs_k1_enum_force_product_filter(1)
-        c = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True)
-        _lib.lib().anqs_k1_enum_force_product_filter(0)
+        c = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True, filter_variant=1)
         for k in ('counts', 'offsets', 'dest', 'xprime', 'xy_ptr'):
             assert torch.equal(a[k], b[k]), k
             assert torch.equal(a[k], c[k]), k
@@ -49,9 +47,7 @@ def run(n, n_el, irreps, rows, timing=False, complex_w=False, off_sector=False):
             work = torch.empty((int(lib.anqs_k1_enum_workspace(ham.tables, nrows)) + 3) // 4, dtype=torch.int32, device=dev)
             counts, offsets = b['counts'], b['offsets']
             t_f = tm(lambda: _lib.check(lib.anqs_k1_enum_filter(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), _lib.dptr(work), sp)))
-            _lib.lib().anqs_k1_enum_force_product_filter(1)
-            t_fp = tm(lambda: _lib.check(lib.anqs_k1_enum_filter(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), _lib.dptr(work), sp)))
-            _lib.lib().anqs_k1_enum_force_product_filter(0)
+            t_fp = tm(lambda: _lib.check(lib.anqs_k1_enum_filter_variant(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), _lib.dptr(work), 1, sp)))
             t_f0 = tm(lambda: _lib.check(lib.anqs_k1_filter(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), sp)))
             _lib.check(lib.anqs_k1_enum_filter(ham.tables, _lib.dptr(s), nrows, na, nb, _lib.dptr(counts), _lib.dptr(bitmap), _lib.dptr(work), sp))
             hptr = _lib.dptr(torch.view_as_real(b['H'])) if me == 'complex' else _lib.dptr(b['H'])

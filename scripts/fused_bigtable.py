@@ -20,10 +20,9 @@ with tempfile.TemporaryDirectory() as tmp:
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sp = _lib.stream_ptr(dev)
     def go():
-        _lib.check(lib.anqs_local_energy_sample_aware(ham.tables, _lib.dptr(s), _lib.dptr(torch.view_as_real(a)), s.shape[0], 0, rows,
-                                                      _lib.dptr(table.slots), table.capacity, 7, 7, _lib.dptr(torch.view_as_real(eloc)), sp))
+        _lib.check(lib.anqs_local_energy_sample_aware_variant(ham.tables, _lib.dptr(s), _lib.dptr(torch.view_as_real(a)), s.shape[0], 0, rows,
+                                                              _lib.dptr(table.slots), table.capacity, 7, 7, _lib.dptr(torch.view_as_real(eloc)), choice, sp))
     for choice in (2, 1):
-        lib.anqs_local_energy_force_per_sample_kernel(choice)
         ts = []
         for _ in range(6):
             flush.fill_(1); torch.cuda.synchronize()

@@ -35,22 +35,18 @@ def run(n, n_el, irreps, rows, timing=False, complex_w=False, off_sector=False, 
         s = torch.from_numpy(samples.view(np.int64)).to(dev).view(-1, 1)
         a = torch.from_numpy(amps).to(dev)
         table = SampleTable(s.view(-1), a)
-        def go():
+        def go(variant):
             return ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
-                                                      alpha_num=na, beta_num=nb, table=table)[0]
-        lib.anqs_local_energy_force_per_sample_kernel(2)
-        e_new = go()
-        lib.anqs_local_energy_force_per_sample_kernel(1)
-        e_old = go()
+                                                      alpha_num=na, beta_num=nb, table=table, kernel_variant=variant)[0]
+        e_new = go(2)
+        e_old = go(1)
         err = float((e_new - e_old).abs().max()); scale = float(e_old.abs().max())
         print(f'n={n} rows={s.shape[0]} complex={complex_w} off_sector={off_sector} clustered={clustered}: max|dE| = {err:.3e} (scale {scale:.3e})')
         assert err <= 1e-11 * max(1.0, scale)
         if timing:
-            t_old = tm(go)
-            lib.anqs_local_energy_force_per_sample_kernel(2)
-            t_new = tm(go)
+            t_old = tm(lambda: go(1))
+            t_new = tm(lambda: go(2))
             print(f'  per-sample kernel {t_old:.3f} ms, bit-sliced {t_new:.3f} ms  ({s.shape[0] / t_new / 1e3:.3e} E_loc/s)')
-        lib.anqs_local_energy_force_per_sample_kernel(0)
 
 run(12, 4, 1, 200)
 run(20, 14, 1, 3000)

@@ -20,17 +20,13 @@ for n, n_el, irreps, rows, off in ((12, 4, 1, 70, False), (20, 14, 1, 333, True)
         s = torch.from_numpy(samples.view(np.int64)).to(dev)
         a = torch.from_numpy(amps).to(dev)
         for force in (0, 1):
-            lib.anqs_k1_enum_force_product_filter(force)
-            c = ham.connected_configurations(s, na, nb, matrix_elements='real', tiled=True)
-        lib.anqs_k1_enum_force_product_filter(0)
+            c = ham.connected_configurations(s, na, nb, matrix_elements='real', tiled=True, filter_variant=force)
         c0 = ham.connected_configurations(s, na, nb, matrix_elements='real', tiled=False)
         assert torch.equal(c['xprime'], c0['xprime'])
         table = SampleTable(s, a)
         for choice in (1, 2):
-            lib.anqs_local_energy_force_per_sample_kernel(choice)
             e = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s.view(-1, 1), unq_batch_as_amps=a, coupling_method='ham',
-                                                   alpha_num=na, beta_num=nb, table=table)[0]
-        lib.anqs_local_energy_force_per_sample_kernel(0)
+                                                   alpha_num=na, beta_num=nb, table=table, kernel_variant=choice)[0]
         torch.cuda.synchronize()
         print('ok', n, samples.shape[0], c['xprime'].shape[0], complex(e.sum()))
 n, n_el = 12, 4

@@ -282,12 +282,8 @@ def test_tiled_enumeration_equals_untiled(qubits, electrons, irreps, rows, compl
     s = _dev(samples.view(np.int64))
     me = 'complex' if complex_w else 'real'
     ref = ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=False)
-    outs = [ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True)]
-    _lib.lib().anqs_k1_enum_force_product_filter(1)
-    try:
-        outs.append(ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True))
-    finally:
-        _lib.lib().anqs_k1_enum_force_product_filter(0)
+    outs = [ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True),
+            ham.connected_configurations(s, na, nb, matrix_elements=me, tiled=True, filter_variant=1)]  # product-layout filter
     assert ref['xprime'].shape[0] > 0
     for out in outs:
         for k in ('counts', 'offsets', 'dest', 'xprime', 'xy_ptr'):
@@ -332,13 +328,9 @@ def test_bit_sliced_local_energy_equals_per_sample_kernel(qubits, electrons, irr
     s, a = _dev(samples.view(np.int64)).view(-1, 1), _dev(amps)
     table = SampleTable(s.view(-1), a)
     res = {}
-    try:
-        for choice in (1, 2, 0):
-            _lib.lib().anqs_local_energy_force_per_sample_kernel(choice)
-            res[choice] = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
-                                                             alpha_num=na, beta_num=nb, table=table)[0].cpu().numpy()
-    finally:
-        _lib.lib().anqs_local_energy_force_per_sample_kernel(0)
+    for choice in (1, 2, 0):
+        res[choice] = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
+                                                         alpha_num=na, beta_num=nb, table=table, kernel_variant=choice)[0].cpu().numpy()
     scale = max(1.0, np.abs(res[1]).max())
     assert np.abs(res[2] - res[1]).max() < 1e-11 * scale
     assert np.abs(res[0] - res[1]).max() < 1e-11 * scale
@@ -410,11 +402,7 @@ def test_full_size_properties(tmp_path):
     e_win = eloc(a, table=table, row_start=lo, row_len=ln)
     assert torch.equal(e_win, e[lo:lo + ln])
     # the warp-per-sample kernel agrees with the bit-sliced one at this size
-    try:
-        _lib.lib().anqs_local_energy_force_per_sample_kernel(1)
-        e_ps = eloc(a, table=table)
-    finally:
-        _lib.lib().anqs_local_energy_force_per_sample_kernel(0)
+    e_ps = eloc(a, table=table, kernel_variant=1)
     assert float((e_ps - e).abs().max()) < 1e-11 * max(1.0, scale)
     del e_c, e_win, e_ps, table
 
@@ -433,9 +421,5 @@ def test_full_size_properties(tmp_path):
     counts_ref = conn['counts'].clone()
     del conn, xp, dest, ptr, same
     for tiled, force in ((True, 1), (False, 0)):   # product-layout filter, flat popcount filter
-        _lib.lib().anqs_k1_enum_force_product_filter(force)
-        try:
-            other = ham.connected_configurations(rows[:8192], na, nb, with_dest=False, with_xy_ptr=False, tiled=tiled)
-        finally:
-            _lib.lib().anqs_k1_enum_force_product_filter(0)
+        other = ham.connected_configurations(rows[:8192], na, nb, with_dest=False, with_xy_ptr=False, tiled=tiled, filter_variant=force)
         assert torch.equal(other['counts'], counts_ref[:8192])
