@@ -252,20 +252,24 @@ enum_filter_bitsliced_kernel(Tables t, const int64_t *__restrict__ samples, int6
                 if (!((valid >> sidx) & 1u)) continue;
                 const int64_t r = group * 32 + sidx;
                 const uint32_t *bm = rows + sidx * stride - c0;  // bm[j] = word j of the row, c0 <= j < c1
-                // connections of every enumeration tile that overlaps this chunk (raw counts for now, scanned below)
+                uint32_t *row = bitmap + r * t.row_words;
+                // one pass over the row's words: written out to the bitmap and counted per enumeration tile that overlaps this
+                // chunk (raw counts for now, scanned below); the tiles cover every word of a row
                 for (int e = e_first; e < n_tiles; ++e) {
                     const int w0 = (int)__ldg(&t.enum_tiles[e].word0), w1 = w0 + (int)__ldg(&t.enum_tiles[e].n_words);
                     if (w0 >= c1) break;
                     int c = 0;
-                    for (int j = max(w0, c0) + lane; j < min(w1, c1); j += 32) c += __popc(bm[j]);
+                    for (int j = max(w0, c0) + lane; j < min(w1, c1); j += 32) {
+                        const uint32_t v = bm[j];
+                        row[j] = v;
+                        c += __popc(v);
+                    }
                     c = __reduce_add_sync(0xffffffffu, c);
                     if (lane == 0) {
                         int32_t *slot = tile_prefix + r * n_tiles + e;
                         *slot = w0 >= c0 ? c : *slot + c;  // a tile that started in an earlier chunk already has a partial count
                     }
                 }
-                uint32_t *row = bitmap + r * t.row_words;
-                for (int j = c0 + lane; j < c1; j += 32) row[j] = bm[j];
             }
             __syncthreads();
         }
@@ -360,14 +364,22 @@ __device__ __forceinline__ int et_expand(uint32_t q_s, int qlen, uint32_t w, int
     const int total = __shfl_sync(0xffffffffu, inc, 31);
     lane_start = qlen + inc - c;  // queue position of the lane's first index
     if (total == 0) return 0;
-    // the lane's indices go to q[qlen + inc - c .. qlen + inc): written from the highest bit down (one FLO per bit)
-    uint32_t qa = q_s + 2u * (uint32_t)(qlen + inc);
+    // The lane's indices go to q[qlen + inc - c .. qlen + inc), two per iteration: the lowest remaining bit from the front, the
+    // highest from the back (for an odd count the middle one is written twice, to the same slot).  The trip count is the
+    // warp's maximum, so the loop branch is uniform and the body predicated: no reconvergence bookkeeping per iteration.
+    uint32_t qa_lo = q_s + 2u * (uint32_t)(qlen + inc - c), qa_hi = q_s + 2u * (uint32_t)(qlen + inc);
     const uint32_t base = (uint32_t)(j + lane) << 5;
-    while (w) {
-        const uint32_t bit = 31u - (uint32_t)__clz((int)w);
-        qa -= 2u;
-        sts_u16(qa, base + bit);
-        w ^= 1u << bit;
+    const int trips = (__reduce_max_sync(0xffffffffu, c) + 1) >> 1;
+    for (int it = 0; it < trips; ++it) {
+        if (w) {
+            const uint32_t hb = 31u - (uint32_t)__clz((int)w), lb = (uint32_t)__ffs((int)w) - 1u;
+            qa_hi -= 2u;
+            sts_u16(qa_hi, base + hb);
+            sts_u16(qa_lo, base + lb);
+            qa_lo += 2u;
+            w &= ~(1u << hb);
+            w &= w - 1u;
+        }
     }
     __syncwarp();
     return total;
@@ -510,8 +522,13 @@ enum_emit_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int a
     __shared__ EnumTile s_tile;
     __shared__ int s_skip;
     constexpr bool WITH_DEST = (FLAGS & 1) != 0, WITH_PTR = (FLAGS & 2) != 0;
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t q_s = smem_u32(smem_raw) + (uint32_t)warp * ET_QCAP * 2u + 2u * (uint32_t)lane;  // the lane's own slot of the warp's queue
+    // lane, warp and the queue address are pinned in registers (volatile asm): left alone, the compiler re-derives them from
+    // %tid.x at every use - a tenth of the instructions of this kernel
+    int lane, warp;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("shr.u32 %0, %1, 5;" : "=r"(warp) : "r"(threadIdx.x));
+    uint32_t q_s = smem_u32(smem_raw) + (uint32_t)warp * ET_QCAP * 2u + 2u * (uint32_t)lane;  // the lane's own slot of the warp's queue
+    asm volatile("" : "+r"(q_s));
     unsigned char *tile_buf = smem_raw + ET_QUEUE_BYTES;
     const uint32_t tile_s = smem_u32(tile_buf);
     ulonglong2 *dq = defer_ws + ((size_t)blockIdx.x * EN_WARPS + warp) * ENUM_DEFER_CAP;
@@ -612,17 +629,24 @@ enum_emit_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int a
             S ^= S << 1; S ^= S << 2; S ^= S << 4; S ^= S << 8; S ^= S << 16; S ^= S << 32;
             S <<= 1;
             const uint32_t slo = (uint32_t)S, shi = (uint32_t)(S >> 32);
+            // Every warp store covers one 32-row block of the output arrays that starts on a multiple of 32 rows (128 bytes of
+            // dest, 256 of x' and H): lane l always writes row (block start + l).  Stores that straddle those blocks, as a
+            // unit's natural start out0 would make all of them, run at half the rate (partial 32-byte sectors at both ends of
+            // every store, measured in scripts/microbench_write2.cu: 3.5 instead of 6.3 TB/s).  So the first batch of a unit
+            // is a partial one on lanes [shift, 32), shift = out0 mod 32, and the last one a partial one on the low lanes.
+            const int shift = (int)(out0 & 31);
             EtOut o;
-            o.dest = WITH_DEST ? dest + out0 + lane : nullptr;
-            o.xprime = reinterpret_cast<long long *>(xprime) + out0 + lane;
-            o.xy_ptr = WITH_PTR ? xy_ptr + out0 + lane : nullptr;
-            o.H = HC ? H + (int64_t)HC * (out0 + lane) : nullptr;
+            o.dest = WITH_DEST ? dest + (out0 - shift) + lane : nullptr;
+            o.xprime = reinterpret_cast<long long *>(xprime) + (out0 - shift) + lane;
+            o.xy_ptr = WITH_PTR ? xy_ptr + (out0 - shift) + lane : nullptr;
+            o.H = HC ? H + (int64_t)HC * ((out0 - shift) + lane) : nullptr;
             int emitted = 0;  // connections of this unit already handed to a batch
             int qlen = 0;
 
-            // one batch: the connection of lane l is queue entry `from + l`
-            auto batch = [&](int from, bool active) {
-                const uint32_t k = active ? lds_u16(q_s + 2u * (uint32_t)from) : 0u;
+            // one batch: lanes [a, a + cnt) take queue entries [from, from + cnt)
+            auto batch = [&](int from, int a, int cnt) {
+                const bool active = lane >= a && lane < a + cnt;
+                const uint32_t k = active ? lds_u16(q_s + 2u * (uint32_t)(from - a)) : 0u;
                 const uint4 r4 = lds128(tile_s + k * 16u);
                 const uint32_t plo = xlo ^ r4.x, phi = xhi ^ r4.y;
                 const uint64_t xp = ((uint64_t)phi << 32) | plo;
@@ -645,7 +669,7 @@ enum_emit_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int a
                     }
                     o.H += 32 * HC;
                 }
-                emitted += 32;
+                emitted += cnt;
             };
 
             for (int j = 0; j < n_words; j += ET_STEP_WORDS) {
@@ -682,8 +706,12 @@ enum_emit_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int a
                     }
                 }
                 qlen += added;
-                int done = 0;
-                for (; qlen - done >= 32; done += 32) batch(done, true);
+                int done = 0, a = (emitted + shift) & 31;  // a != 0 only before the first batch of the unit
+                while (qlen - done >= 32 - a) {
+                    batch(done, a, 32 - a);
+                    done += 32 - a;
+                    a = 0;
+                }
                 if (done > 0) {  // move the remainder (< 32 entries) to the front of the queue
                     const int rem = qlen - done;
                     const uint32_t v = lane < rem ? lds_u16(q_s + 2u * (uint32_t)done) : 0u;
@@ -693,7 +721,7 @@ enum_emit_kernel(Tables t, const int64_t *__restrict__ samples, int64_t n, int a
                     qlen = rem;
                 }
             }
-            if (qlen > 0) batch(0, lane < qlen);
+            if (qlen > 0) batch(0, (emitted + shift) & 31, qlen);
             __syncwarp();
           }
           base = base2;

@@ -9,6 +9,7 @@
 // MODE 3: as MODE 0 but the chunk index is scrambled (chunks in random order)
 // MODE 4: the emit kernel's pattern without its per-warp tickets: a CTA stays on tile blockIdx % n_tiles and takes 32 consecutive
 //         samples per ticket (one per warp); warp w writes the chunk (sample, tile): 32 chunks at a stride of one sample row
+template <int MIS>
 __global__ void __launch_bounds__(1024, 1) wr4(int32_t *dest, long long *xp, double *H, long long n_samples, int ch, int n_tiles, unsigned *counters) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ unsigned s_t;
@@ -21,8 +22,9 @@ __global__ void __launch_bounds__(1024, 1) wr4(int32_t *dest, long long *xp, dou
             const long long s = (long long)s_t * 32 + warp;
             if ((long long)s_t * 32 >= n_samples) break;
             if (s >= n_samples) continue;
-            const long long o0 = (s * n_tiles + ti) * ch;
-            for (int k = lane; k < ch; k += 32) {
+            // MIS: every chunk starts MIS rows later and is MIS... rows shorter, so no warp store is 128-byte aligned
+            const long long o0 = (s * n_tiles + ti) * ch + (MIS ? (MIS + (s * 7 + ti * 3) % 9) : 0);
+            for (int k = lane; k < ch - 16; k += 32) {
                 const long long r = o0 + k;
                 __stcs(dest + r, (int)s); __stcs(xp + r, r ^ 0x5555); __stcs(H + r, (double)k);
             }
@@ -79,17 +81,17 @@ int main() {
     for (int ch : {320, 1280, 3840}) run("warp per chunk, scrambled order", wr<3>, ch, 1);
     for (int ch : {160, 320, 640}) run("CTA takes 32 consecutive chunks", wr<1>, ch, 1);
     for (int nt : {6, 12, 24}) run("CTA: 32 samples, chunks in turn + sync", wr<2>, 3840 / nt, nt);
-    for (int nt : {6, 12, 24}) {
+    for (int mis : {0, 1}) for (int nt : {6, 12, 24}) {
         const int ch = 3840 / nt;
         float best = 1e9f;
         for (int it = 0; it < 5; ++it) {
             cudaMemset(c, 0, 4096);
             cudaEventRecord(e0);
-            wr4<<<148, 1024>>>(d, x, h, M / 3840, ch, nt, c);
+            if (mis) wr4<5><<<148, 1024>>>(d, x, h, M / 3840, ch, nt, c); else wr4<0><<<148, 1024>>>(d, x, h, M / 3840, ch, nt, c);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (it > 0 && ms < best) best = ms;
         }
-        printf("%-40s chunk %5d rows: %.3f ms  %.0f GB/s  (%s)\n", "CTA on one tile, 32 samples at a stride", ch, best, 20.0 * M / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+        printf("%-40s chunk %5d rows: %.3f ms  %.0f GB/s  (%s)\n", mis ? "same, chunk starts misaligned" : "CTA on one tile, 32 samples at a stride", ch, best, 20.0 * (M / 3840) * nt * (ch - 16) / best / 1e6, cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }
