@@ -40,6 +40,12 @@ _SIGNATURES = {
     'anqs_hash_build_spread': (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _c_int, _vp]),
     'anqs_hash_filter_info': (_c_int, [_vp, _c_i64, _vp, _vp, _vp]),
     'anqs_hash_probe': (_c_int, [_vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp]),
+    'anqs_sort_workspace': (ctypes.c_size_t, [_c_i64]),
+    'anqs_sort_pairs_u64': (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, ctypes.c_uint64, _vp, _vp]),
+    'anqs_unique_workspace': (ctypes.c_size_t, [_c_i64]),
+    'anqs_unique_i64': (_c_int, [_vp, _c_i64, _c_int, _vp, _vp, _vp, _vp, _vp]),
+    'anqs_topk_workspace': (ctypes.c_size_t, [_c_i64, _c_i64]),
+    'anqs_topk_f64': (_c_int, [_vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_local_energy_sample_aware': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _vp]),
     'anqs_local_energy_sample_aware_variant': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _c_int, _vp]),
     'anqs_accumulate_rows': (_c_int, [_vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
@@ -179,6 +185,53 @@ def dptr(t):
     if not t.is_contiguous():
         raise RuntimeError('expected a contiguous tensor')
     return _vp(t.data_ptr())
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(1, (int(nbytes) + 7) // 8), dtype=torch.int64, device=device)
+
+
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor = None, begin_bit: int = 0, end_bit: int = 64, key_kind: int = 0, xor_mask: int = 0):
+    """(sorted keys, payloads) through anqs_sort_pairs_u64; keys int64 or float64 [n] on a CUDA device, vals int64 [n] or None
+    (payload = position, i.e. the permutation)."""
+    dev = require_cuda(keys.device)
+    keys = keys.contiguous()
+    n = keys.shape[0]
+    out_k, out_v = torch.empty_like(keys), torch.empty(n, dtype=torch.int64, device=dev)
+    if n == 0:
+        return out_k, out_v
+    work = _workspace(lib().anqs_sort_workspace(n), dev)
+    check(lib().anqs_sort_pairs_u64(dptr(keys), dptr(vals.contiguous() if vals is not None else None), dptr(out_k), dptr(out_v), n,
+                                    int(begin_bit), int(end_bit), int(key_kind), ctypes.c_uint64(xor_mask & 0xFFFFFFFFFFFFFFFF), dptr(work),
+                                    stream_ptr(dev)))
+    return out_k, out_v
+
+
+def unique_i64(x: torch.Tensor, end_bit: int = 64, return_inverse: bool = True):
+    """Sorted (signed) unique values of an int64 vector and the inverse map (anqs_unique_i64); one host read for the count."""
+    dev = require_cuda(x.device)
+    x = x.contiguous().view(-1)
+    n = x.shape[0]
+    unq = torch.empty(n, dtype=torch.int64, device=dev)
+    inv = torch.empty(n, dtype=torch.int64, device=dev) if return_inverse else None
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    if n > 0:
+        work = _workspace(lib().anqs_unique_workspace(n), dev)
+        check(lib().anqs_unique_i64(dptr(x), n, int(end_bit), dptr(unq), dptr(inv), dptr(cnt), dptr(work), stream_ptr(dev)))
+    return unq[:int(cnt.item())], inv
+
+
+def topk_f64(vals: torch.Tensor, k: int):
+    """First k rows of a stable descending sort of a float64 vector: (values, positions) through anqs_topk_f64."""
+    dev = require_cuda(vals.device)
+    vals = vals.contiguous().view(-1)
+    n = vals.shape[0]
+    top_v = torch.empty(k, dtype=torch.float64, device=dev)
+    top_i = torch.empty(k, dtype=torch.int64, device=dev)
+    if k > 0:
+        work = _workspace(lib().anqs_topk_workspace(n, k), dev)
+        check(lib().anqs_topk_f64(dptr(vals), n, int(k), dptr(top_v), dptr(top_i), dptr(work), stream_ptr(dev)))
+    return top_v, top_i
 
 
 def require_cuda(device):

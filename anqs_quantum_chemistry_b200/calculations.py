@@ -12,6 +12,8 @@ reference (EnergyOptExp.iter, energy_opt_exp.py:626-679) runs unchanged on the B
 import numpy as np
 import torch as pt
 
+from . import _lib
+
 
 class SamplingConfig:
     """SMP:18-36."""
@@ -51,7 +53,7 @@ def sample(wf=None, config: SamplingConfig = None, starting_sample_num: int = No
             repetition_num += 1
             next_rep_sample_num *= config.upscale_factor
         actual_unq_num = indices.shape[0]
-        counts, order = pt.sort(counts.real, descending=True)
+        counts, order = _lib.sort_pairs(counts.real.contiguous(), None, 0, 64, key_kind=1, xor_mask=-1)  # descending, stable
         indices = indices[order[:config.sample_num]]
     else:
         indices, counts = wf.sample_stats(sample_num=config.sample_num, **sampler_kwargs)
@@ -169,7 +171,7 @@ def sr(wf=None, sampling_result: SamplingResult = None, config: SRConfig = None)
     else:
         freqs = sampling_result.counts
     freqs = freqs / pt.sum(freqs)
-    _, order = pt.sort(freqs.real, descending=True)
+    _, order = _lib.sort_pairs(freqs.real.contiguous(), None, 0, 64, key_kind=1, xor_mask=-1)  # descending, stable
     top = order[:config.max_indices_num]
     f = freqs[top]
     f = f / pt.sum(f)

@@ -109,21 +109,24 @@ class HilbertSpace:
         return self.popcount(base_idx)
 
     # ---- unique / sort / join (HS:200-284) -----------------------------------------------------------
+    @property
+    def _key_bits(self) -> int:
+        """Bits of a packed index that can differ between two configurations (all of them at 64 qubits)."""
+        return 64 if self.qubit_num >= 64 else self.qubit_num
+
     def compute_unique_indices(self, base_idx):
-        """Sorted (signed) unique rows and the inverse map (HS:215-228)."""
+        """Sorted (signed) unique rows and the inverse map (HS:215-228): radix sort + head flags + scan (k2_sort.cu)."""
         assert len(base_idx.shape) == 2
         assert base_idx.shape[-1] == self.int_per_idx
-        unq, inv = pt.unique(base_idx[..., 0], return_inverse=True)
+        unq, inv = _lib.unique_i64(base_idx[..., 0], end_bit=self._key_bits)
         return unq.reshape(-1, 1), inv
 
     def sort_base_idx(self, base_idx: pt.Tensor = None, descending: bool = False):
-        """Ascending in UNSIGNED order with a stable permutation (HS:239-261)."""
+        """Ascending in UNSIGNED order with a stable permutation (HS:239-261): LSD radix sort over the qubit_num low bits."""
         if descending:
             raise NotImplementedError
-        # unsigned order = signed order of (x xor 2^63)
-        flipped = base_idx[:, 0] ^ (-(2 ** 63))
-        _, perm = pt.sort(flipped, stable=True)
-        return base_idx[perm], perm
+        srt, perm = _lib.sort_pairs(base_idx[:, 0], None, 0, self._key_bits)
+        return srt.view(-1, 1), perm
 
     def find_a_in_b(self, a: pt.Tensor, b: pt.Tensor):
         """(mask, ptr): position of each row of `a` in `b`, -1 when absent (HS:263-284)."""

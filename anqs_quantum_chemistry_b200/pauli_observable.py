@@ -365,7 +365,7 @@ class PauliObservable(AbstractHilbertSpaceObject):
             cur.sampled_x_primes_num = int((~missing).sum().item())
             cur.non_sampled_x_primes_num = m - cur.sampled_x_primes_num
             if cur.non_sampled_x_primes_num > 0:
-                unq, inv = pt.unique(xp[missing], return_inverse=True)
+                unq, inv = _lib.unique_i64(xp[missing], end_bit=self.hilbert_space._key_bits)  # PO:1016-1040 (k2_sort.cu)
                 cur.non_sampled_unq_x_primes_num = unq.shape[0]
                 t0 = time.time()
                 unq_amps = pt.cat([wf.amplitude(unq[a:a + amps_chunk_size].view(-1, 1)).detach()

@@ -148,7 +148,7 @@ class AutoregressiveSamplerMixin:
                                                      _lib.dptr(u), _lib.dptr(out_lp), _lib.dptr(out_g), sp))
             flat_g = out_g.view(-1)
             keep = min(sample_num, flat_g.shape[0])
-            top_g, top_i = pt.sort(flat_g, descending=True, stable=True)   # ANQS:733
+            top_g, top_i = _lib.topk_f64(flat_g, keep)   # ANQS:733: the first `keep` rows of the stable descending sort (radix select)
             # ANQS:735-776 in one kernel: children of the kept rows; masked children (gumbel = -inf, ANQS:804-809) sort last
             new_prefix = pt.empty(keep, dtype=pt.int64, device=dev)
             new_memo = pt.empty(keep, dtype=pt.int32, device=dev)

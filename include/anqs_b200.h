@@ -130,6 +130,31 @@ int anqs_hash_filter_info(const void *d_table, int64_t capacity, int *spread_bit
 int anqs_hash_probe(const void *d_table, int64_t capacity, const int64_t *d_queries, int64_t m,
                     int64_t *d_ptr, uint8_t *d_mask, void *stream);
 
+/* ---- A5 / A12  ordering: sort, unique, top-k (HS:215-261, ANQS:733, PO:1016-1040) -------------------------------------
+ * The reference calls torch.sort / torch.unique; these are hand-written radix kernels (k2_sort.cu).  All stream-ordered, no
+ * host synchronisation; d_work: the matching *_workspace() bytes, 256-byte aligned.
+ *
+ * anqs_sort_pairs_u64: stable ascending sort of (key, payload) pairs by the bits [begin_bit, end_bit) of
+ * transform(key) ^ xor_mask, transform = identity (key_kind 0) or the order-preserving map of IEEE doubles (key_kind 1).
+ * d_vals_in == NULL means payload = position (the permutation comes out in d_vals_out).  xor_mask = 0: unsigned ascending
+ * (HilbertSpace.sort_base_idx, HS:239-261); 1 << 63: signed ascending; ~0: descending (ties keep their order: the same rows
+ * as torch.sort(descending=True, stable=True)).  Keys come out untransformed.  Not in place. */
+size_t anqs_sort_workspace(int64_t n);
+int anqs_sort_pairs_u64(const uint64_t *d_keys_in, const int64_t *d_vals_in, uint64_t *d_keys_out, int64_t *d_vals_out, int64_t n,
+                        int begin_bit, int end_bit, int key_kind, uint64_t xor_mask, void *d_work, void *stream);
+/* HilbertSpace.compute_unique_indices (HS:215-228) for single-word indices: d_unq[0 .. *d_n_unique) = the distinct values of
+ * d_in in SIGNED ascending order (torch.unique), d_inv[i] = position of d_in[i] in d_unq (may be NULL).  end_bit: bits at and
+ * above it are equal in all inputs (qubit_num, or 64). d_unq must hold n values; *d_n_unique is a device scalar. */
+size_t anqs_unique_workspace(int64_t n);
+int anqs_unique_i64(const int64_t *d_in, int64_t n, int end_bit, int64_t *d_unq, int64_t *d_inv, int64_t *d_n_unique, void *d_work,
+                    void *stream);
+/* The k largest of n doubles, descending, ties by position: d_top_vals / d_top_idx = the first k rows of
+ * torch.sort(vals, descending=True, stable=True) (ANQS:733 keeps exactly those).  An 8-bit radix select finds the k-th value
+ * from histograms alone, the survivors are compacted in order and only they are sorted.  -inf (masked children) sort last;
+ * NaNs are not expected. */
+size_t anqs_topk_workspace(int64_t n, int64_t k);
+int anqs_topk_f64(const double *d_vals, int64_t n, int64_t k, double *d_top_vals, int64_t *d_top_idx, void *d_work, void *stream);
+
 /* ---- A2+A3+A5+A6+A7  fused sample-aware local energy --------------------------------------------------
  * PauliObservable.compute_var_local_energy_proxy(coupling_method='ham') (PO:396-487, non-symmetric branch):
  *   E_loc[i] = ( sum_{x' in sampled set, x' = x_i ^ xy[u] physical} H_{x_i,x'} psi(x') ) / psi(x_i)
