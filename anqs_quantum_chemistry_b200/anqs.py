@@ -547,8 +547,12 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         return self.log_psi_of_indices(self.base_vec2base_idx(base_vec))
 
     def amplitude(self, base_idx: pt.Tensor) -> pt.Tensor:
-        """ANQS:483-485."""
-        return pt.exp(self.log_psi_of_indices(base_idx))
+        """ANQS:483-485.  The returned tensor carries the log psi it was exponentiated from (`amps.log_psi`, same autograd
+        graph) so that calculations.vmc_loss can skip the exp -> log round trip of the reference."""
+        lp = self.log_psi_of_indices(base_idx)
+        amps = pt.exp(lp)
+        amps.log_psi = lp
+        return amps
 
     def phase(self, base_idx: pt.Tensor) -> pt.Tensor:
         return self.log_psi_of_indices(base_idx).imag

@@ -130,9 +130,25 @@ def compute_local_energies(wf=None, sampling_result: SamplingResult = None, samp
                              sample_aware_e_loc_mc_est=MonteCarloEstimator(values=aware, counts=theor_freqs)), metrics
 
 
+def log_conj_psi(sampled_amps: pt.Tensor) -> pt.Tensor:
+    """log(conj psi_i) of the loss EXP:609.  The reference exponentiates log psi in `amplitude`
+    (ANQS:485) and takes the logarithm again in the loss, so the backward pass runs through exp and log (a division by psi)
+    for nothing.  The wave functions of this package attach the log psi they computed to the amplitudes they return
+    (`amps.log_psi`, same autograd graph); when it is there the loss is built on it directly: conj(log psi), with the
+    imaginary part brought back to the principal branch by a constant (no gradient) multiple of 2 pi so that the VALUE of the
+    loss equals the reference's log(conj(psi)) too.  Amplitudes from anywhere else take the reference's route."""
+    lp = getattr(sampled_amps, 'log_psi', None)
+    if lp is None or lp.shape != sampled_amps.shape:
+        return pt.log(pt.conj(sampled_amps))
+    a = -lp.imag
+    with pt.no_grad():
+        wrap = -2.0 * np.pi * pt.round(a / (2.0 * np.pi))
+    return pt.complex(lp.real, a + wrap)
+
+
 def vmc_loss(sampled_amps: pt.Tensor, estimator: MonteCarloEstimator) -> pt.Tensor:
     """EXP:609: 2 Re sum_i f_i log(conj psi_i) (E_i - <E>); its gradient is the energy gradient."""
-    return 2 * (estimator.freqs * pt.log(pt.conj(sampled_amps)) * (estimator.values - estimator.mean)).sum().real
+    return 2 * (estimator.freqs * log_conj_psi(sampled_amps) * (estimator.values - estimator.mean)).sum().real
 
 
 # ---- gradient post-processing (SURVEY.md section 8(f) rank 2) ------------------------------------------------------------------

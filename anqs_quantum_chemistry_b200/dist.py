@@ -153,7 +153,8 @@ class ShardedEnergyGradient:
         with pt.no_grad():
             a = amps.detach()
             seed = (a.real * a.real + a.imag * a.imag) / norm * (eloc - mean)   # f_i (E_i - <E>)
-        loss = 2 * (seed * pt.log(pt.conj(amps))).sum().real
+        from .calculations import log_conj_psi
+        loss = 2 * (seed * log_conj_psi(amps)).sum().real   # no exp -> log round trip when amps carry their log psi
         loss.backward()
         flat = pt.cat([(p.grad if p.grad is not None else pt.zeros_like(p)).reshape(-1) for p in params] + [loss.detach().reshape(1)])
         if group_world_size(self.group, self.world_size) > 1:

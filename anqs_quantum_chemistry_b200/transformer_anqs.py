@@ -202,7 +202,10 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         return self.log_psi_of_indices(self.base_vec2base_idx(base_vec))
 
     def amplitude(self, base_idx: pt.Tensor) -> pt.Tensor:
-        return pt.exp(self.log_psi_of_indices(base_idx))
+        lp = self.log_psi_of_indices(base_idx)
+        amps = pt.exp(lp)
+        amps.log_psi = lp   # calculations.vmc_loss builds the loss on it (no exp -> log round trip)
+        return amps
 
     def forward(self, base_idx: pt.Tensor) -> pt.Tensor:
         return self.amplitude(base_idx)

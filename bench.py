@@ -553,6 +553,54 @@ class GpuEngine:
                                            _lib.stream_ptr(self.device)))
         return float(counts.double().mean().item())
 
+    def vmc_collective(self, iters=5, warm=2, sample_num=10 ** 6):
+        """ALL ranks, inside the live process group: VMC iterations/s (the second half of BASELINE.json's metric) on the C5 shape
+        with the whole iteration sharded over the ranks - sub-tree sharded count-splitting sampler of 1e6 samples, float64
+        amplitudes of the local rows, all-gather of (index, amplitude), sample-aware local energies of the local rows, all-reduce
+        of the energy statistics, loss EXP:609, backward through the local rows, ONE all-reduce of the flat gradient, Adam on
+        the replicated parameters.  Strong scaling: the samples per iteration are fixed.  Device time, max over ranks."""
+        import torch.distributed as dist
+        torch, adist, dev, world = self.torch, self.adist, self.device, self.world
+        from anqs_quantum_chemistry_b200 import (ParticleNumberSymmetry, SpinHalfProjectionSymmetry, LocallyDecomposableMasker,
+                                                 LogAbsPhaseANQS, ANQSConfig)
+        hs = self.hs
+        masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=ELECTRONS),
+                                                                         SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+        torch.manual_seed(0)
+        wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='MADE'))
+        wf.set_inference_precision('tf32')   # the sampler's conditionals only; amplitudes with a graph stay float64
+        opt = torch.optim.Adam(wf.parameters(), lr=1e-3)
+        step = adist.ShardedEnergyGradient(wf, adist.ShardedLocalEnergy(self.ham, self.na, self.nb).stats)
+        rows = 0
+
+        def one_iter(it):
+            idx, _ = adist.sharded_sample_stats(wf, sample_num, seed=1000 + it, gather=False)
+            mean, _, _ = step(idx)
+            opt.step()
+            return idx.shape[0], mean
+        for it in range(warm):
+            one_iter(it)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(iters):
+            n_rows, mean = one_iter(warm + it)
+            rows += n_rows
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1), 0.0], dtype=torch.float64, device=dev)
+        r = torch.tensor([float(rows)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(r)
+        ms = float(t[0]) / iters
+        return {'iters_per_s': 1e3 / ms, 'ms_per_iter': ms, 'n_gpus': world, 'samples_per_iteration': sample_num, 'scaling': 'strong',
+                'unique_per_iteration': float(r) / iters, 'qubits': QUBITS, 'params': int(wf.param_num),
+                'sampler': 'count splitting sharded by sub-tree (ANQS:494-525), tf32 conditionals', 'gradient': 'float64',
+                'energy_last': float(mean.real)}
+
     def extras_local(self):
         """Rank 0 only, AFTER the process group is gone: the other kernels of the path on this GPU."""
         return secondary_measurements(self.ham, self.hs, self.d_idx, self.na, self.nb, self.device)
@@ -644,6 +692,8 @@ def main(argv=None, engine_cls=GpuEngine):
     e2e_total = max_over_ranks(sum(e2e_ms))
     clock_info = clocks.stop() if rank == 0 else None
     conn_per_row = eng.conn_per_row()
+    # VMC iterations/s with the iteration sharded over the ranks: a collective measurement, so every rank takes part
+    vmc_sharded = eng.vmc_collective() if (world > 1 and not args.no_extras and hasattr(eng, 'vmc_collective')) else None
 
     # ---- every collective of this program is above this line.  Rank-0-only work (secondary kernels, CPU baseline) must never
     # run inside a live process group: a collective entered by one rank alone hangs until the watchdog aborts the job.
@@ -692,7 +742,11 @@ def main(argv=None, engine_cls=GpuEngine):
         'roofline': roofline,
         'clocks': clock_info,
     }
+    if vmc_sharded is not None:
+        line['secondary'] = {'vmc_iteration_c5_sharded': vmc_sharded}
     if extras is not None:
+        if vmc_sharded is not None:
+            extras['vmc_iteration_c5_sharded'] = vmc_sharded
         enum = extras.get('enumeration')
         if enum is not None:
             enum['frac_of_hbm_peak'] = enum['achieved_gbs'] / peak

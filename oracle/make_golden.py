@@ -179,13 +179,15 @@ class _RintBinomial:
         return torch.minimum(self.n, torch.clamp(torch.round(self.n * self.p), min=0.0))
 
 
-def _anqs_case(name, n, n_el, sample_count, stats_num, gumbel_num, seed):
+def _anqs_case(name, n, n_el, sample_count, stats_num, gumbel_num, seed, z2=(), masking_depth=0):
     tmp = tempfile.mkdtemp(prefix='anqs_golden_')
     try:
-        o = ref_shim.build_reference_objects(None, n, n_el, tmp)
+        o = ref_shim.build_reference_objects(None, n, n_el, tmp, z2=z2, masking_depth=masking_depth)
         wf, masker, qg = o.wf, o.masker, o.wf.qubit_grouping
         Q, DM = qg.qudit_num, int(max(qg.qudit_dims))
-        out = dict(qubit_num=n, particle_num=n_el, weight_seed=seed, qudit_num=Q, max_qudit_dim=DM)
+        out = dict(qubit_num=n, particle_num=n_el, weight_seed=seed, qudit_num=Q, max_qudit_dim=DM, masking_depth=masking_depth,
+                   z2_values=np.array([v for v, _ in z2], dtype=np.int64),
+                   z2_masks=np.array([sum(1 << int(p) for p in pos) for _, pos in z2], dtype=np.int64))
         # initial weights under pt.manual_seed(0) (build_reference_objects seeds before constructing the ansatz)
         out['init_checksums'] = np.array([[float(p.sum()), float((p * p).sum()), float(p.reshape(-1)[0]), float(p.reshape(-1)[-1])]
                                           for p in wf.parameters()])
@@ -323,6 +325,9 @@ def make_anqs():
     _anqs_case('anqs_n20', 20, 14, 200, 10 ** 6, 300, seed=1)
     _anqs_case('anqs_n56', 56, 14, 200, 3000, 200, seed=2)
     _anqs_case('anqs_n14', 14, 10, 100, 10 ** 5, 500, seed=3)
+    # the reference's default masker level ('z2': Z2 generators on top of N and S_z) and a non-zero masking depth
+    _anqs_case('anqs_z2_n12', 12, 4, 100, 10 ** 4, 40, seed=4, z2=((1, (0, 3, 5, 8)), (-1, (1, 2, 10))))
+    _anqs_case('anqs_md1_n20', 20, 14, 100, 10 ** 5, 100, seed=5, masking_depth=1)
 
 
 # ---- one whole VMC iteration (EXP:626-679 without SR): sample -> amplitudes -> local energies -> loss -> backward ----

@@ -84,6 +84,7 @@ def load_reference():
     from nqs.base.qubit_grouping import QubitGrouping, QubitGroupingConfig
     from nqs.stochastic.observables.pauli_observable import PauliObservable
     from nqs.stochastic.symmetries import ParticleNumberSymmetry, SpinHalfProjectionSymmetry
+    from nqs.stochastic.symmetries.z2_symmetry import Z2Symmetry
     from nqs.stochastic.maskers import LocallyDecomposableMasker
     from nqs.stochastic.ansatzes.anqs import ANQSConfig, LogAbsPhaseANQS, LogPsiANQS
     from nqs.stochastic.ansatzes.anqs.abstract_anqs import AbstractANQS, LocalSamplingConfig
@@ -95,7 +96,7 @@ def load_reference():
     _LOADED.update(dict(
         HilbertSpace=HilbertSpace, QubitGrouping=QubitGrouping, QubitGroupingConfig=QubitGroupingConfig,
         PauliObservable=PauliObservable, ParticleNumberSymmetry=ParticleNumberSymmetry,
-        SpinHalfProjectionSymmetry=SpinHalfProjectionSymmetry,
+        SpinHalfProjectionSymmetry=SpinHalfProjectionSymmetry, Z2Symmetry=Z2Symmetry,
         LocallyDecomposableMasker=LocallyDecomposableMasker, ANQSConfig=ANQSConfig,
         LogAbsPhaseANQS=LogAbsPhaseANQS, LogPsiANQS=LogPsiANQS, AbstractANQS=AbstractANQS,
         LocalSamplingConfig=LocalSamplingConfig, MLP=MLP, MLPConfig=MLPConfig,
@@ -107,7 +108,7 @@ def load_reference():
 
 
 def build_reference_objects(terms: dict, qubit_num: int, particle_num: int, parent_dir: str,
-                            de_mode: str = 'MADE', rng_seed: int = 0, spin: int = 0):
+                            de_mode: str = 'MADE', rng_seed: int = 0, spin: int = 0, z2=(), masking_depth: int = 0):
     """Wires HilbertSpace -> PauliObservable -> masker -> LogAbsPhaseANQS exactly like
     energy_opt_exp.py:348-376 with the 'e_num_spin' masker level (create_masker.py:61-65)."""
     ref = load_reference()
@@ -116,9 +117,13 @@ def build_reference_objects(terms: dict, qubit_num: int, particle_num: int, pare
                           rng_seed=rng_seed, popcount_mode='memory_efficient')
     hs.init_perm()
     ham = ref.PauliObservable(hilbert_space=hs, of_qubit_operator=ref.QubitOperator(terms)) if terms is not None else None
-    masker = ref.LocallyDecomposableMasker(hilbert_space=hs, symmetries=(
-        ref.ParticleNumberSymmetry(hilbert_space=hs, particle_num=particle_num),
-        ref.SpinHalfProjectionSymmetry(hilbert_space=hs, spin=spin)))
+    # z2: ((value, pauli_z_positions), ...) -> Z2Symmetry generators on top of the two additive symmetries (the reference's
+    # default masker level 'z2', create_masker.py:18-24, 58-69); masking_depth: LocalSamplingConfig (ANQS:29-50)
+    syms = (ref.ParticleNumberSymmetry(hilbert_space=hs, particle_num=particle_num),
+            ref.SpinHalfProjectionSymmetry(hilbert_space=hs, spin=spin))
+    syms += tuple(ref.Z2Symmetry(hilbert_space=hs, value=v, pauli_z_positions=torch.tensor(list(pos), dtype=torch.int64)) for v, pos in z2)
+    masker = ref.LocallyDecomposableMasker(hilbert_space=hs, symmetries=syms)
     torch.manual_seed(rng_seed)
-    wf = ref.LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ref.ANQSConfig(de_mode=de_mode))
+    wf = ref.LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ref.ANQSConfig(
+        de_mode=de_mode, local_sampling_config=ref.LocalSamplingConfig(masking_depth=masking_depth)))
     return types.SimpleNamespace(ref=ref, hs=hs, ham=ham, masker=masker, wf=wf)

@@ -10,16 +10,19 @@ from conftest import load_golden
 from anqs_quantum_chemistry_b200 import (HilbertSpace, ParticleNumberSymmetry, SpinHalfProjectionSymmetry, Z2Symmetry,
                                          LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig)
 
-CASES = ['anqs_n12', 'anqs_n14', 'anqs_n20', 'anqs_n56']
+CASES = ['anqs_n12', 'anqs_n14', 'anqs_n20', 'anqs_n56', 'anqs_z2_n12', 'anqs_md1_n20']
 
 
-def build(n, ne, device='cpu', seed=0):
+def build(n, ne, device='cpu', seed=0, z2=(), masking_depth=0):
+    from anqs_quantum_chemistry_b200 import Z2Symmetry, LocalSamplingConfig
     tmp = tempfile.mkdtemp(prefix='anqs_test_')
     hs = HilbertSpace(qubit_num=n, device=device, parent_dir=tmp, rng_seed=seed)
-    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=ne),
-                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    syms = (ParticleNumberSymmetry(hilbert_space=hs, particle_num=ne), SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0))
+    syms += tuple(Z2Symmetry(hilbert_space=hs, value=int(v), pauli_z_positions=[i for i in range(n) if (int(m) >> i) & 1]) for v, m in z2)
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=syms)
     torch.manual_seed(seed)
-    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='MADE'))
+    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker,
+                         config=ANQSConfig(de_mode='MADE', local_sampling_config=LocalSamplingConfig(masking_depth=masking_depth)))
     return hs, masker, wf
 
 
@@ -27,7 +30,8 @@ def build(n, ne, device='cpu', seed=0):
 def test_tables_and_init_match_reference(name):
     g = load_golden(name)
     n, ne = int(g['qubit_num']), int(g['particle_num'])
-    hs, masker, wf = build(n, ne)
+    z2 = tuple(zip(g['z2_values'].tolist(), g['z2_masks'].tolist()))
+    hs, masker, wf = build(n, ne, z2=z2, masking_depth=int(g['masking_depth']))
     memo_ref = np.unpackbits(g['memo'])[:(n + 1) * masker.memo_size].reshape(n + 1, masker.memo_size).astype(bool)
     assert np.array_equal(masker.memo_host, memo_ref)
     qg = wf.qubit_grouping
@@ -77,3 +81,30 @@ def test_no_cpu_fallback():
         wf.amplitude(torch.zeros((4, 1), dtype=torch.int64))
     with pytest.raises(RuntimeError, match='no CPU path'):
         wf.sample_stats(100)
+
+
+def test_loss_on_attached_log_psi_equals_the_reference_loss():
+    """calculations.vmc_loss with `amps.log_psi` attached (no exp -> log round trip) gives the value and the gradient of the
+    reference's 2 Re sum f log(conj psi) (E - <E>) (EXP:609), phases beyond (-pi, pi] included."""
+    import torch
+    from anqs_quantum_chemistry_b200.calculations import vmc_loss, MonteCarloEstimator
+    torch.manual_seed(1)
+    n = 200
+    theta = torch.randn(n, dtype=torch.float64, requires_grad=True)
+    phi = (7.0 * torch.randn(n, dtype=torch.float64)).requires_grad_(True)       # many phases outside the principal branch
+    eloc = torch.complex(torch.randn(n, dtype=torch.float64), 0.3 * torch.randn(n, dtype=torch.float64))
+
+    def run(attach):
+        lp = torch.complex(theta * 0.5, phi)
+        amps = torch.exp(lp)
+        if attach:
+            amps.log_psi = lp
+        est = MonteCarloEstimator(values=eloc, counts=(amps.detach().conj() * amps.detach()))
+        loss = vmc_loss(amps, est)
+        g = torch.autograd.grad(loss, (theta, phi))
+        return loss.detach(), g
+    l0, g0 = run(False)
+    l1, g1 = run(True)
+    assert abs(float(l0) - float(l1)) < 1e-12 * max(1.0, abs(float(l0)))
+    for a, b in zip(g0, g1):
+        assert float((a - b).abs().max()) < 1e-12

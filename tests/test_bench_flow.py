@@ -83,6 +83,17 @@ class StubEngine:
     def conn_per_row(self):
         return 3.0
 
+    def vmc_collective(self):
+        # the sharded VMC iteration of the real engine: collectives entered by EVERY rank, inside the live group
+        assert dist.is_initialized() and dist.get_world_size() == self.world
+
+        def local_energy(local_idx, local_amps):
+            eloc = _fake_energy(local_idx)
+            mean, var, norm = adist.reduce_energy_stats(adist.local_energy_stats(eloc, local_amps))
+            return eloc, mean, var, norm
+        mean, var, loss = adist.ShardedEnergyGradient(_ToyWF(), local_energy)(self.d_idx)
+        return {'iters_per_s': 1.0, 'n_gpus': self.world, 'energy_last': float(mean.real)}
+
     def extras_local(self):
         # round 1's failure mode: rank-0-only code that goes through dist.py.  It must find no live group here ...
         assert not dist.is_initialized(), 'rank-0-only extras must run after destroy_process_group()'
@@ -125,6 +136,7 @@ def test_bench_main_control_flow_world_size_2(tmp_path):
     assert line['n_gpus'] == 2 and line['steps'] == 2 and line['warmup'] == 3
     assert line['config']['sampled_set'] == 1000 and line['scaling'] == 'weak'
     assert line['value'] > 0 and line['e2e']['value'] > 0 and 'secondary' in line
+    assert line['secondary']['vmc_iteration_c5_sharded']['n_gpus'] == 2
     assert 'cpu_baseline' not in line  # N = 1 only
 
 

@@ -9,23 +9,28 @@ import pytest
 import torch
 
 from conftest import load_golden
-from anqs_quantum_chemistry_b200 import (HilbertSpace, ParticleNumberSymmetry, SpinHalfProjectionSymmetry,
-                                         LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig, synthetic)
+from anqs_quantum_chemistry_b200 import (HilbertSpace, ParticleNumberSymmetry, SpinHalfProjectionSymmetry, Z2Symmetry,
+                                         LocallyDecomposableMasker, LogAbsPhaseANQS, ANQSConfig, LocalSamplingConfig, synthetic)
 from oracle import anqs_numpy as onp
 from oracle.make_golden import made_weights
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device('cuda:0')
 CASES = ['anqs_n12', 'anqs_n14', 'anqs_n20', 'anqs_n56']
+# the reference's default symmetry level (Z2 generators on top of N and S_z, create_masker.py:18-24) and a non-zero
+# masking depth (the last qudit sampled unmasked, ANQS:417-418, 605-606) reach the kernels through the same descriptors
+CASES_SYM = CASES + ['anqs_z2_n12', 'anqs_md1_n20']
 
 
-def build(n, ne, nets=None, seed=0):
+def build(n, ne, nets=None, seed=0, z2=(), masking_depth=0):
     tmp = tempfile.mkdtemp(prefix='anqs_gpu_test_')
     hs = HilbertSpace(qubit_num=n, device=DEV, parent_dir=tmp, rng_seed=seed)
-    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=(ParticleNumberSymmetry(hilbert_space=hs, particle_num=ne),
-                                                                     SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0)))
+    syms = (ParticleNumberSymmetry(hilbert_space=hs, particle_num=ne), SpinHalfProjectionSymmetry(hilbert_space=hs, spin=0))
+    syms += tuple(Z2Symmetry(hilbert_space=hs, value=int(v), pauli_z_positions=[i for i in range(n) if (int(m) >> i) & 1]) for v, m in z2)
+    masker = LocallyDecomposableMasker(hilbert_space=hs, symmetries=syms)
     torch.manual_seed(seed)
-    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker, config=ANQSConfig(de_mode='MADE'))
+    wf = LogAbsPhaseANQS(hilbert_space=hs, masker=masker,
+                         config=ANQSConfig(de_mode='MADE', local_sampling_config=LocalSamplingConfig(masking_depth=masking_depth)))
     if nets is not None:
         sd = {}
         for name, layers in zip(('log_abs_subnet', 'phase_subnet'), nets):
@@ -40,8 +45,9 @@ def setup_case(name):
     g = load_golden(name)
     n, ne = int(g['qubit_num']), int(g['particle_num'])
     masks = onp.NumberSpinMasks(n, ne)
-    nets = made_weights(n, masks.Q, masks.DM, seed=int(g['weight_seed']))
-    hs, masker, wf = build(n, ne, nets)
+    nets = made_weights(n, int(g['qudit_num']), int(g['max_qudit_dim']), seed=int(g['weight_seed']))
+    z2 = tuple(zip(g['z2_values'].tolist(), g['z2_masks'].tolist())) if 'z2_values' in g else ()
+    hs, masker, wf = build(n, ne, nets, z2=z2, masking_depth=int(g['masking_depth']) if 'masking_depth' in g else 0)
     return g, masks, nets, wf
 
 
@@ -49,7 +55,7 @@ def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES_SYM)
 def test_log_psi_and_amplitude_match_reference(name):
     g, masks, nets, wf = setup_case(name)
     s = _dev(g['samples']).view(-1, 1)
@@ -65,7 +71,7 @@ def test_log_psi_and_amplitude_match_reference(name):
     assert np.array_equal(lp_vec, lp)
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES_SYM)
 def test_cond_log_abs_matches_reference(name):
     g, masks, nets, wf = setup_case(name)
     nphys = int(g['n_phys'])
@@ -83,7 +89,7 @@ def test_cond_log_abs_matches_reference(name):
         assert np.array_equal(c2, c)
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES_SYM)
 def test_gradients_match_reference_autograd(name):
     g, masks, nets, wf = setup_case(name)
     nphys = int(g['n_phys'])
@@ -110,7 +116,7 @@ def test_gradients_match_reference_autograd(name):
     assert np.abs(proj @ ga - g['grad_amp_proj']).max() < 1e-10 * max(1.0, np.abs(g['grad_amp_proj']).max())
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES_SYM)
 def test_sample_stats_rint_matches_reference(name):
     g, masks, nets, wf = setup_case(name)
     idx, cnt = wf.sample_stats(int(g['stats_num']), draw_mode='rint')
@@ -120,7 +126,7 @@ def test_sample_stats_rint_matches_reference(name):
     assert float(cnt.real.sum()) == float(g['stats_num'])
 
 
-@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('name', CASES_SYM)
 def test_gumbel_matches_reference(name):
     g, masks, nets, wf = setup_case(name)
     urng = np.random.default_rng(int(g['weight_seed']) + 4)
