@@ -40,6 +40,8 @@ _SIGNATURES = {
     'anqs_hash_build_spread': (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _c_int, _vp]),
     'anqs_hash_filter_info': (_c_int, [_vp, _c_i64, _vp, _vp, _vp]),
     'anqs_hash_probe': (_c_int, [_vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp]),
+    'anqs_pair_join_workspace': (ctypes.c_size_t, [_c_i64, _c_i64]),
+    'anqs_local_energy_pair_join': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp]),
     'anqs_sort_workspace': (ctypes.c_size_t, [_c_i64]),
     'anqs_sort_pairs_u64': (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_int, _c_int, _c_int, ctypes.c_uint64, _vp, _vp]),
     'anqs_unique_workspace': (ctypes.c_size_t, [_c_i64]),

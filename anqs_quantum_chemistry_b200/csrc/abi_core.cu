@@ -598,6 +598,8 @@ int anqs_tables_create(anqs_tables_t **out, int qubit_num, int64_t U, int64_t T,
         max_group = std::max(max_group, (int)h_yz_num[u]);
     }
     t->max_group = max_group;
+    t->max_xy_weight = 0;
+    for (int64_t u = 0; u < U; ++u) t->max_xy_weight = std::max(t->max_xy_weight, __builtin_popcountll((unsigned long long)h_unq_xy[u]));
     bool real = true;
     std::vector<double> wre(T), wim(T);
     std::vector<ulonglong2> rec(T);

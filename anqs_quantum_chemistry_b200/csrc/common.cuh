@@ -104,6 +104,7 @@ struct Tables {
     int64_t U_pad;           // U rounded up to a multiple of 1024 (32 bitmap words)
     int64_t row_words;       // U_pad / 32
     int max_group;           // largest YZ group
+    int max_xy_weight;       // largest popcount of an XY mask (the pair-join kernel's pruning radius)
     uint64_t *xy;            // [U_pad]  unique XY masks, ascending (signed order, as torch.unique gives)
     uint2 *mab;              // [U_pad]  de-interleaved masks: .x = even (alpha) bits, .y = odd (beta) bits
     int2 *grp;               // [U_pad]  (start, num) of the YZ group of each XY mask

@@ -97,12 +97,21 @@ hash_build_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ 
             }
             sl = slots + h;
         }
-        // duplicates: the largest position wins, which is what a sequential scatter_ leaves behind
+        // duplicates: the largest position wins, which is what a sequential scatter_ leaves behind.  The amplitude has to follow
+        // the position: a thread that raised idx writes its amplitude, then re-reads idx and, if a larger position has arrived
+        // meanwhile, writes THAT position's amplitude - so whichever store lands last carries the amplitude of the final idx.
         long long old = atomicMax(&sl->idx, (long long)j);
         if (old < j && amps) {
-            double2 a = amps[j];
-            sl->re = a.x;
-            sl->im = a.y;
+            long long cur = j;
+            for (;;) {
+                const double2 a = amps[cur];
+                sl->re = a.x;
+                sl->im = a.y;
+                __threadfence();
+                const long long now = *reinterpret_cast<volatile long long *>(&sl->idx);
+                if (now == cur) break;
+                cur = now;
+            }
         }
     }
 }

@@ -101,7 +101,12 @@ made_forward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in
                         const uint64_t prefix = start == 0 ? 0ull : (x & ((1ull << start) - 1ull));
                         uint64_t mw;
                         if (P.du[q]) {
-                            mw = DM >= 64 ? ~0ull : ((1ull << DM) - 1ull);
+                            // Unmasked qudit.  The reference is not consistent about how wide "unmasked" is in MADE mode, and both
+                            // widths are reproduced: log psi / amplitudes unmask all max_qudit_dim output columns (the mask is
+                            // padded first and replaced by ones afterwards, ANQS:434-441), the samplers' conditionals only the
+                            // qudit's own 2^bits outcomes (ones first, padding afterwards, ANQS:605-613, 708-716).
+                            const int dq = MODE == MADE_COND ? (1 << (P.qudit_starts[q + 1] - start)) : DM;
+                            mw = dq >= 64 ? ~0ull : ((1ull << dq) - 1ull);
                         } else {
                             long long mi = memo_index(P, prefix);
                             mw = (mi >= 0 && mi < P.memo_size) ? __ldg(P.cont_mask + (size_t)q * P.memo_size + mi) : 0ull;

@@ -257,8 +257,9 @@ made_tc_kernel(const anqs_made_desc_t P, const TcPacked L, const unsigned char *
                     const int DM = P.max_qudit_dim;
                     if (net == 0) {
                         uint64_t mw;
-                        if (P.du[q]) {
-                            mw = DM >= 64 ? ~0ull : ((1ull << DM) - 1ull);
+                        if (P.du[q]) {  // unmasked qudit: max_qudit_dim columns for log psi, the qudit's own 2^bits for the samplers (k3_made.cu)
+                            const int dq = MODE == 1 ? (1 << bits) : DM;
+                            mw = dq >= 64 ? ~0ull : ((1ull << dq) - 1ull);
                         } else {
                             const uint64_t prefix = start == 0 ? 0ull : (x & ((1ull << start) - 1ull));
                             const long long mi = tc_memo_index(P, prefix);

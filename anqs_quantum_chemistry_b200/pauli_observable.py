@@ -11,8 +11,10 @@ compute goes through the sm_100a kernels of libanqs_b200.so:
                                      de-duplicated non-sampled configurations, anqs_accumulate_rows
 
 The three working coupling methods of the reference ('ham', 'all_to_all', 'trie') produce the same numbers
-(SURVEY.md §4); they all map to the fused kernel here.  'hamming_ball' is broken in the reference
-(PO:698) and is rejected.
+(SURVEY.md §4).  'ham' enumerates the U connected configurations of every sample and probes the sampled set (fused
+kernel); 'trie' / 'all_to_all' join the sampled configurations pairwise (k1_pairs.cu: N^2 XOR + POPC tests, survivors looked
+up among the unique masks) while the batch is small enough for that to be the cheaper algorithm, and fall back to the fused
+kernel beyond.  'hamming_ball' is broken in the reference (PO:698) and is rejected.
 """
 import os
 import time
@@ -56,24 +58,32 @@ def parse_of_qubit_operator_arrays(of_qubit_operator, qubit_num: int):
         xy, yz, w = arrays
         return (np.ascontiguousarray(w, dtype=np.complex128), np.ascontiguousarray(xy).view(np.int64).copy(),
                 np.ascontiguousarray(yz).view(np.int64).copy())
+    # one walk over the dict to flatten it, everything else vectorised (the reference loops in python over every Pauli of
+    # every term with tensor indexing, PO:150-183)
+    import itertools
+    from operator import itemgetter
     terms = of_qubit_operator.terms
     T = len(terms)
-    w = np.zeros(T, np.complex128)
+    keys = list(terms.keys())
+    w = np.fromiter(terms.values(), dtype=np.complex128, count=T)
+    lens = np.fromiter(map(len, keys), dtype=np.int64, count=T)
+    flat = list(itertools.chain.from_iterable(keys))
+    m = len(flat)
     xy = np.zeros(T, np.uint64)
     yz = np.zeros(T, np.uint64)
-    i_pow = (1.0 + 0j, 1j, -1.0 + 0j, -1j)
-    for t, (qubit_ops, weight) in enumerate(terms.items()):
-        x = z = ny = 0
-        for q, p in qubit_ops:
-            bit = 1 << (qubit_num - 1 - q)
-            if p == 'X' or p == 'Y':
-                x |= bit
-            if p == 'Y' or p == 'Z':
-                z |= bit
-            if p == 'Y':
-                ny += 1
-        xy[t], yz[t] = x, z
-        w[t] = (weight + 0j) * i_pow[ny & 3]
+    ny = np.zeros(T, np.int64)
+    if m:
+        q = np.fromiter(map(itemgetter(0), flat), dtype=np.int64, count=m)
+        p = np.fromiter(map(ord, map(itemgetter(1), flat)), dtype=np.int64, count=m)
+        bit = np.left_shift(np.uint64(1), (qubit_num - 1 - q).astype(np.uint64))
+        is_y = p == ord('Y')
+        is_x, is_z = (p == ord('X')) | is_y, (p == ord('Z')) | is_y
+        ne = lens > 0
+        starts = (np.cumsum(lens) - lens)[ne]
+        xy[ne] = np.bitwise_or.reduceat(np.where(is_x, bit, np.uint64(0)), starts)
+        yz[ne] = np.bitwise_or.reduceat(np.where(is_z, bit, np.uint64(0)), starts)
+        ny[ne] = np.add.reduceat(is_y.astype(np.int64), starts)
+    w = w * np.array([1.0 + 0j, 1j, -1.0 + 0j, -1j])[ny & 3]
     return w, xy.view(np.int64), yz.view(np.int64)
 
 
@@ -108,6 +118,7 @@ class PauliArraysOperator:
 class PauliObservable(AbstractHilbertSpaceObject):
     ALLOWED_COUPLING_METHODS = ('ham', 'all_to_all', 'hamming_ball', 'trie')
     MEMORY_MAGIC_CONSTANT = 25
+    PAIR_JOIN_MAX_SAMPLES = 1 << 16   # above this the N^2 pair tests of the pair-join kernel lose to enumerate-and-probe
 
     def __init__(self, *args, of_qubit_operator=None, **kwargs):
         super().__init__(*args, **kwargs)
@@ -123,7 +134,10 @@ class PauliObservable(AbstractHilbertSpaceObject):
             host = {name: np.load(path) for name, path in self.tensor_name2tensor_path.items()}
         else:
             weights, xy_masks, yz_masks = parse_of_qubit_operator_arrays(of_qubit_operator, self.qubit_num)
-            host = self.compute_local_energy_structures_host(xy_masks, yz_masks, weights)
+            if self.device.type == 'cuda':  # sort / segment on the GPU (k2_sort.cu)
+                host = self.compute_local_energy_structures_device(xy_masks, yz_masks, weights, self.device, self.hilbert_space._key_bits)
+            else:  # host-side logic without a GPU (table tests, cache writers)
+                host = self.compute_local_energy_structures_host(xy_masks, yz_masks, weights)
             os.makedirs(self.hilbert_space.parent_dir, exist_ok=True)
             for name, path in self.tensor_name2tensor_path.items():
                 np.save(path, host[name])
@@ -148,6 +162,26 @@ class PauliObservable(AbstractHilbertSpaceObject):
                     rearranged_yz=yz_masks[order].reshape(-1, 1).astype(np.int64),
                     rearranged_weights=np.ascontiguousarray(weights[order], dtype=np.complex128))
 
+    @staticmethod
+    def compute_local_energy_structures_device(xy_masks, yz_masks, weights, device, key_bits: int = 64):
+        """The same six tensors built on the GPU (reference PO:131-142 + PO:185-211, two python
+        loops with `.item()` per term): radix sort of the XY masks with head flags + scan for the unique masks and the inverse
+        map (anqs_unique_i64), a stable radix sort of the inverse map for the regrouping permutation (terms of a group keep
+        their original order), segment lengths from the sorted inverse map.  Returned as host arrays (they are cached as
+        `.npy` files and handed to anqs_tables_create)."""
+        dev = _lib.require_cuda(device)
+        xy = pt.from_numpy(np.ascontiguousarray(xy_masks)).to(dev)
+        yz = pt.from_numpy(np.ascontiguousarray(yz_masks)).to(dev)
+        w = pt.from_numpy(np.ascontiguousarray(weights, dtype=np.complex128)).to(dev)
+        unq, inv = _lib.unique_i64(xy, end_bit=key_bits)
+        U = unq.shape[0]
+        _, order = _lib.sort_pairs(inv, None, 0, max(1, int(U - 1).bit_length()))   # stable: original term order inside a group
+        num = pt.bincount(inv, minlength=U)
+        start = pt.cumsum(num, 0) - num
+        return dict(unq_xy_masks=unq.reshape(-1, 1).cpu().numpy(), unq_xy_masks_inv=inv.cpu().numpy(),
+                    unq_xy_to_yz_num=num.cpu().numpy(), unq_xy_to_yz_start=start.cpu().numpy(),
+                    rearranged_yz=yz[order].reshape(-1, 1).cpu().numpy(), rearranged_weights=w[order].cpu().numpy())
+
     # ---- device handle ----------------------------------------------------------------------------------
     @property
     def tables(self):
@@ -171,6 +205,13 @@ class PauliObservable(AbstractHilbertSpaceObject):
 
     # properties of the device tables: asking for one creates the tables (they used to be plain attributes that only
     # existed after the first kernel call)
+    @property
+    def mask_table(self) -> SampleTable:
+        """Hash table {XY mask -> its index u} over the unique masks, for the pair-join kernel (built once)."""
+        if getattr(self, '_mask_table', None) is None:
+            self._mask_table = SampleTable(self.unq_xy_masks.to(self.device).contiguous().view(-1), None)
+        return self._mask_table
+
     @property
     def weights_real(self) -> bool:
         """True when every Pauli weight has zero imaginary part (real-integral molecules): 8-byte matrix elements."""
@@ -301,7 +342,8 @@ class PauliObservable(AbstractHilbertSpaceObject):
         """PO:396-487.  Sample-aware local energies of the whole batch in one fused launch; `chunk_size` and
         `matrix_element_chunk_size` are accepted for signature compatibility (nothing is materialised, so
         there is nothing to chunk).  row_start/row_len/table are extensions used by the multi-GPU shard path;
-        kernel_variant: 0 = kernel chosen by batch size, 1 = warp-per-sample kernel, 2 = bit-sliced kernel."""
+        kernel_variant: 0 = chosen from coupling_method and batch size, 1 = warp-per-sample kernel, 2 = bit-sliced kernel,
+        3 = pair-join kernel (k1_pairs.cu)."""
         assert coupling_method in self.ALLOWED_COUPLING_METHODS
         if coupling_method == 'hamming_ball':
             raise NotImplementedError("coupling_method='hamming_ball' is broken in the reference (pauli_observable.py:698)")
@@ -311,9 +353,20 @@ class PauliObservable(AbstractHilbertSpaceObject):
         n = samples.shape[0]
         assert amps.shape[0] == n
         row_len = n - row_start if row_len is None else row_len
+        eloc = pt.empty(row_len, dtype=pt.complex128, device=dev)
+        # 'trie' / 'all_to_all' couple the sampled configurations with each other (PO:602-696): the pair-join kernel, N^2 pair
+        # tests instead of N x U filter tests, while that is the smaller number; 'ham' (and large batches) enumerate and probe
+        pair_join = kernel_variant == 3 or (kernel_variant == 0 and coupling_method in ('trie', 'all_to_all')
+                                            and n <= self.PAIR_JOIN_MAX_SAMPLES and n <= 4 * self.unq_xy_masks_num)
+        if pair_join:
+            mt = self.mask_table
+            work = _lib._workspace(_lib.lib().anqs_pair_join_workspace(row_len, n), dev)
+            _lib.check(_lib.lib().anqs_local_energy_pair_join(
+                self.tables, _lib.dptr(samples), _lib.dptr(pt.view_as_real(amps)), n, row_start, row_len, _lib.dptr(mt.slots), mt.capacity,
+                alpha_num, beta_num, _lib.dptr(pt.view_as_real(eloc)), _lib.dptr(work), _lib.stream_ptr(dev)))
+            return eloc, eloc, LocalEnergyMetrics()
         if table is None:
             table = SampleTable(samples, amps)
-        eloc = pt.empty(row_len, dtype=pt.complex128, device=dev)
         _lib.check(_lib.lib().anqs_local_energy_sample_aware_variant(
             self.tables, _lib.dptr(samples), _lib.dptr(pt.view_as_real(amps)), n, row_start, row_len,
             _lib.dptr(table.slots), table.capacity, alpha_num, beta_num, _lib.dptr(pt.view_as_real(eloc)), int(kernel_variant),

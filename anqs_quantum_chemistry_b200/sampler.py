@@ -54,6 +54,14 @@ class AutoregressiveSamplerMixin:
         qg = self.qubit_grouping
         if self._next_memo is None:
             self._next_memo = [pt.from_numpy(np.ascontiguousarray(t.astype(np.int32))).to(self.device) for t in qg.next_memo_host]
+        pattern = getattr(self, 'local_sampling_pattern', None)
+        if pattern is not None and pattern[q] == 'DU':
+            # An unmasked qudit (masking_depth > 0; the reference default is 0).  The reference's samplers draw such a level from
+            # the unmasked conditionals and THEN throw the unphysical children away, with the samples they carry (ANQS:605-606 +
+            # 653-655; ANQS:708-709 + 804-809) - a different level kernel.  Amplitudes, conditionals and gradients of such wave
+            # functions are implemented and tested against the reference; sampling from them is not.
+            raise NotImplementedError('sampling with LocalSamplingConfig(masking_depth > 0) is not implemented by the sm_100a sampler '
+                                      'kernels (amplitude / log_psi / cond_log_abs / gradients are)')
         return qg.cont_mask_words[q], self._next_memo[q]
 
     def _start_memo_idx(self) -> int:

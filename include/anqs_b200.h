@@ -173,6 +173,16 @@ int anqs_local_energy_sample_aware_variant(const anqs_tables_t *t, const int64_t
                                            int64_t capacity, int alpha_num, int beta_num, double *d_eloc, int variant,
                                            void *stream);
 
+/* ---- pair-join coupling ('trie' / 'all_to_all' of the reference, PO:602-696, TRIE:8-125) --------------------------------
+ * The same sample-aware local energies from the coupled PAIRS of the sampled set: N^2 XOR + POPC tests, survivors look
+ * x_i ^ x_j up among the unique XY masks.  d_mask_table: anqs_hash_build over the U unique XY masks (keys = the masks, no
+ * amplitudes), capacity >= anqs_hash_capacity(U).  Independent of U; the better algorithm while the sampled set is smaller
+ * than the mask list.  d_work: anqs_pair_join_workspace(row_len, n_total) bytes.  Same results as the call above. */
+size_t anqs_pair_join_workspace(int64_t row_len, int64_t n_total);
+int anqs_local_energy_pair_join(const anqs_tables_t *t, const int64_t *d_samples, const double *d_amps, int64_t n_total,
+                                int64_t row_start, int64_t row_len, const void *d_mask_table, int64_t mask_capacity, int alpha_num,
+                                int beta_num, double *d_eloc, void *d_work, void *stream);
+
 /* ---- A7  scatter of the materialised list (PO:453-478 / PO:1048-1057): E[dest] += H * psi(src) -------
  * d_src_ptr[r] = index of x'_r in the sampled set or -1 (skipped).  Rows must be grouped by dest through
  * d_offsets (CSR).  d_eloc[i] = sum / psi(x_i) when d_amps_dest != NULL, else the raw sum. */

@@ -202,7 +202,12 @@ def _anqs_case(name, n, n_el, sample_count, stats_num, gumbel_num, seed, z2=(), 
         out['next_memo_masked_sum'] = np.array([int((qg.qudit_idx2memo_idx_mul_table[q] * qg.qudit_idx2cont_mask_mul_table[q]).sum())
                                                 for q in range(Q)])
         na = nb = n_el // 2
-        phys = synthetic.random_physical_samples(n, na, nb, sample_count, seed=seed + 1)
+        phys = synthetic.random_physical_samples(n, na, nb, sample_count * (8 if z2 else 1), seed=seed + 1)
+        for v, pos in z2:  # keep the configurations every Z2 generator accepts
+            zmask = np.uint64(sum(1 << int(p) for p in pos))
+            par = np.array([bin(int(x & zmask)).count('1') & 1 for x in phys])
+            phys = phys[(1 - 2 * par) == v]
+        phys = phys[:sample_count]
         rng = np.random.default_rng(seed + 2)
         unphys = rng.integers(0, 2 ** min(n, 62), size=8, dtype=np.int64).astype(np.uint64)
         samples = np.concatenate((phys, unphys))
@@ -218,6 +223,8 @@ def _anqs_case(name, n, n_el, sample_count, stats_num, gumbel_num, seed, z2=(), 
                 prefix_vec = base_vec[:phys.shape[0], :qg.qudit_starts[q]]
                 rolling = masker.compute_rolling_acc_eigs(prefix_vec)[-1]
                 mask = qg.qudit_idx2cont_mask_mul_table[q][masker.acc_eigs2memo_idx(rolling)]
+                if wf.local_sampling_pattern[q] == 'DU':  # the mask the reference's own callers pass for such a qudit (ANQS:417-418)
+                    mask = torch.ones_like(mask)
                 full = torch.zeros((mask.shape[0], DM), dtype=torch.bool)
                 full[:, :mask.shape[1]] = mask
                 out[f'cond_log_abs_q{q}'] = wf.cond_log_abs(qudit_idx=q, base_vec=prefix_vec, mask=full).numpy()
@@ -271,7 +278,12 @@ def _nade_case(name, n, n_el, sample_count, stats_num, gumbel_num, seed):
                    param_names=np.array([k for k, _ in wf.named_parameters()]),
                    init_checksums=np.array([[float(p.sum()), float((p * p).sum())] for p in wf.parameters()]))
         na = nb = n_el // 2
-        phys = synthetic.random_physical_samples(n, na, nb, sample_count, seed=seed + 1)
+        phys = synthetic.random_physical_samples(n, na, nb, sample_count * (8 if z2 else 1), seed=seed + 1)
+        for v, pos in z2:  # keep the configurations every Z2 generator accepts
+            zmask = np.uint64(sum(1 << int(p) for p in pos))
+            par = np.array([bin(int(x & zmask)).count('1') & 1 for x in phys])
+            phys = phys[(1 - 2 * par) == v]
+        phys = phys[:sample_count]
         rng = np.random.default_rng(seed + 2)
         samples = np.concatenate((phys, rng.integers(0, 2 ** min(n, 62), size=8, dtype=np.int64).astype(np.uint64)))
         s_t = _t(samples.view(np.int64)).reshape(-1, 1)

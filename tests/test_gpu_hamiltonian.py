@@ -71,9 +71,12 @@ def test_local_energy_matches_reference(case, tmp_path):
     # a window of rows (the multi-GPU shard path) equals the same rows of the full evaluation
     n = s.shape[0]
     lo, ln = n // 3, n // 2
-    w, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
-                                                 alpha_num=na, beta_num=nb, row_start=lo, row_len=ln)
-    assert torch.equal(w, e[lo:lo + ln])
+    for method in ('ham', 'trie'):   # the fused kernel and the pair-join kernel
+        e = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method=method,
+                                               alpha_num=na, beta_num=nb)[0]
+        w, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method=method,
+                                                     alpha_num=na, beta_num=nb, row_start=lo, row_len=ln)
+        assert torch.equal(w, e[lo:lo + ln])
 
 
 @pytest.mark.parametrize('case', HAM_CASES_WITH_LISTS)
@@ -334,6 +337,14 @@ def test_bit_sliced_local_energy_equals_per_sample_kernel(qubits, electrons, irr
     scale = max(1.0, np.abs(res[1]).max())
     assert np.abs(res[2] - res[1]).max() < 1e-11 * scale
     assert np.abs(res[0] - res[1]).max() < 1e-11 * scale
+    if samples.shape[0] <= 40000:  # the pair-join kernel (what 'trie' / 'all_to_all' run on small batches): same energies
+        e_pj = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='trie',
+                                                  alpha_num=na, beta_num=nb, kernel_variant=3)[0].cpu().numpy()
+        assert np.abs(e_pj - res[1]).max() < 1e-11 * scale
+        lo, ln = samples.shape[0] // 4, samples.shape[0] // 2   # a row window (the multi-GPU shard path)
+        e_win = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='trie', alpha_num=na,
+                                                   beta_num=nb, kernel_variant=3, row_start=lo, row_len=ln)[0].cpu().numpy()
+        assert np.array_equal(e_win, e_pj[lo:lo + ln])
     if samples.shape[0] <= 6000:
         e_ref = orc.local_energy_sample_aware(samples, amps, orc.Tables(xy, yz, w), na, nb)
         assert np.abs(res[2] - e_ref).max() < 1e-10 * scale

@@ -71,3 +71,44 @@ def test_hilbert_space_methods_use_the_kernels(tmp_path):
     assert torch.equal(unq[:, 0], ref_u) and torch.equal(inv, ref_inv)
     srt, perm = hs.sort_base_idx(keys)
     assert torch.equal(srt, keys[perm]) and bool((srt[1:, 0] >= srt[:-1, 0]).all())
+
+
+def test_sort_and_unique_match_the_reference_golden(tmp_path):
+    """HS:239-261 / HS:215-228 outputs of the unmodified reference (tests/golden/hilbert.npz), 64-qubit indices with bit 63 set."""
+    from conftest import load_golden
+    from anqs_quantum_chemistry_b200 import HilbertSpace
+    g = load_golden('hilbert')
+    hs64 = HilbertSpace(qubit_num=64, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    dup = torch.from_numpy(g['dup']).to(DEV).view(-1, 1)
+    s, p = hs64.sort_base_idx(dup)
+    np.testing.assert_array_equal(s.cpu().numpy().reshape(-1), g['sorted'])
+    np.testing.assert_array_equal(p.cpu().numpy(), g['sort_perm'])
+    if 'unq' in g:
+        u, inv = hs64.compute_unique_indices(dup)
+        np.testing.assert_array_equal(u.cpu().numpy().reshape(-1), g['unq'])
+        np.testing.assert_array_equal(inv.cpu().numpy(), g['unq_inv'])
+
+
+@pytest.mark.parametrize('name', ['ham_n8_dense', 'ham_n12_dense', 'ham_n20_dense', 'ham_n56_sparse', 'ham_n64_sparse'])
+def test_gpu_table_builder_matches_reference_tables(name, tmp_path):
+    """the six local-energy structure tensors built on the GPU (radix sort / unique / segment) equal
+    the reference's (PO:131-211), from the arrays and from the `.terms` dictionary."""
+    from conftest import load_golden
+    from anqs_quantum_chemistry_b200 import HilbertSpace, PauliObservable, PauliArraysOperator
+    g = load_golden(name)
+    n = int(g['qubit_num'])
+    op = PauliArraysOperator(g['in_xy'], g['in_yz'], g['in_w'], n)
+
+    class FromTerms:
+        terms = op.terms
+    for sub, operator in (('a', op), ('t', FromTerms())):
+        hs = HilbertSpace(qubit_num=n, device=DEV, parent_dir=str(tmp_path / sub), rng_seed=0)
+        ham = PauliObservable(hilbert_space=hs, of_qubit_operator=operator)
+        for key in ham.local_energy_structure_tensor_names:
+            ref = g[key].reshape(-1)
+            got = getattr(ham, key).cpu().numpy().reshape(-1)
+            assert got.shape == ref.shape, key
+            if key == 'rearranged_weights':
+                assert np.abs(got - ref).max() == 0.0
+            else:
+                assert np.array_equal(got, ref), key
