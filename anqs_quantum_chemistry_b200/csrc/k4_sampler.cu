@@ -17,6 +17,7 @@
 // A node that carries a single sample takes one categorical draw by inversion instead of k binomial rounds (a multinomial
 // with one trial), which is what most nodes of the deep levels of a large sparse batch are.
 #include <algorithm>
+#include <cstdint>
 
 #include "common.cuh"
 
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32)
 emit_children_kernel(const double *__restrict__ child_counts, int k, int start, const int64_t *__restrict__ prefix,
                      const int32_t *__restrict__ memo_idx, const unsigned long long *__restrict__ cont_mask_q,
                      const int32_t *__restrict__ next_memo_q, int64_t memo_size, int64_t B,
-                     const int64_t *__restrict__ offsets, const signed char *__restrict__ single_in,
+                     const int64_t *__restrict__ offsets, const signed char *__restrict__ single_in, int64_t out_cap,
                      int64_t *__restrict__ out_prefix, double *__restrict__ out_counts, int32_t *__restrict__ out_memo) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = lanemask_lt();
@@ -243,7 +244,7 @@ emit_children_kernel(const double *__restrict__ child_counts, int k, int start, 
         if (single_in != nullptr) {
             const int sd = single_in[b];
             if (sd != -2) {   // single-sample parent: the split already named its child
-                if (sd >= 0 && lane == 0) {
+                if (sd >= 0 && lane == 0 && offsets[b] < out_cap) {
                     const int64_t r = offsets[b];
                     out_prefix[r] = (int64_t)((uint64_t)prefix[b] | ((uint64_t)sd << start));
                     out_counts[r] = 1.0;
@@ -265,14 +266,14 @@ emit_children_kernel(const double *__restrict__ child_counts, int k, int start, 
         const int64_t base = offsets[b];
         const uint64_t px = (uint64_t)prefix[b];
         const int before = __popc(be & lt) + __popc(bo & lt);
-        if (s_even) {
+        if (s_even && base + before < out_cap) {
             const int64_t r = base + before;
             const int d = 2 * lane;
             out_prefix[r] = (int64_t)(px | ((uint64_t)d << start));
             out_counts[r] = c_even;
             out_memo[r] = next_memo_q[(size_t)mi * D + d];
         }
-        if (s_odd) {
+        if (s_odd && base + before + (s_even ? 1 : 0) < out_cap) {
             const int64_t r = base + before + (s_even ? 1 : 0);
             const int d = 2 * lane + 1;
             out_prefix[r] = (int64_t)(px | ((uint64_t)d << start));
@@ -403,7 +404,17 @@ int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit
                                const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,
                                const int8_t *d_single, int64_t *d_out_prefix, double *d_out_counts, int32_t *d_out_memo_idx,
                                void *stream) {
+    return anqs_sampler_emit_children_capped(d_child_counts, qubits_in_qudit, qudit_start, d_prefix, d_memo_idx, d_cont_mask_q, d_next_memo_q,
+                                             memo_size, n, d_offsets, d_single, INT64_MAX, d_out_prefix, d_out_counts, d_out_memo_idx, stream);
+}
+
+int anqs_sampler_emit_children_capped(const double *d_child_counts, int qubits_in_qudit, int qudit_start,
+                                      const int64_t *d_prefix, const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q,
+                                      const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,
+                                      const int8_t *d_single, int64_t out_capacity, int64_t *d_out_prefix, double *d_out_counts,
+                                      int32_t *d_out_memo_idx, void *stream) {
     ANQS_REQUIRE(n >= 0, "negative parent count");
+    ANQS_REQUIRE(out_capacity >= 0, "negative output capacity");
     ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6, "qudit must have 1..6 qubits");
     ANQS_REQUIRE(qudit_start >= 0 && qudit_start + qubits_in_qudit <= 64, "qudit outside the 64-bit word");
     if (n == 0) return 0;
@@ -412,7 +423,7 @@ int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit
     int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
     emit_children_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d_child_counts, qubits_in_qudit, qudit_start, d_prefix, d_memo_idx, (const unsigned long long *)d_cont_mask_q,
-        d_next_memo_q, memo_size, n, d_offsets, (const signed char *)d_single, d_out_prefix, d_out_counts, d_out_memo_idx);
+        d_next_memo_q, memo_size, n, d_offsets, (const signed char *)d_single, out_capacity, d_out_prefix, d_out_counts, d_out_memo_idx);
     ANQS_LAUNCH_CHECK();
     return 0;
 }

@@ -183,6 +183,8 @@ def sharded_sample_stats(wf, sample_num: int, seed: int, world_size: int = None,
     if world_size is None:
         world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world_size == 1:  # nothing to shard: the wave function's own call (one host read per call in steady state)
+        return wf.sample_stats(sample_num, draw_mode=draw_mode, seed=seed)
     mode = {'rint': 0, 'philox': 1}[draw_mode]
     prefix, counts, memo = wf.sample_stats_root(sample_num)
     sharded = world_size == 1

@@ -113,16 +113,73 @@ class AutoregressiveSamplerMixin:
                 pt.tensor([self._start_memo_idx()], dtype=pt.int32, device=dev))
 
     @pt.no_grad()
-    def sample_stats(self, sample_num: int, draw_mode: str = 'philox', seed: int = None) -> Tuple[pt.Tensor, pt.Tensor]:
+    def sample_stats(self, sample_num: int, draw_mode: str = 'philox', seed: int = None, exact_levels: bool = False) -> Tuple[pt.Tensor, pt.Tensor]:
         """ANQS:494-525: breadth-first count splitting.  Returns (unique indices [N,1] int64, counts [N] complex128).
         draw_mode 'philox' draws binomials from the counter-based generator (seeded by hilbert_space.rng_seed and a
-        per-call counter); 'rint' replaces every draw by its rounded mean (deterministic)."""
+        per-call counter); 'rint' replaces every draw by its rounded mean (deterministic).
+        The first call for a given sample_num reads every level's size back to the host (one synchronisation per qudit); later
+        calls size the levels from the previous call's sizes (+25 %) and read the host ONCE, after the last level - the same
+        samples either way, because the draws are keyed by the node's prefix and dead rows carry a zero count.  A level that
+        outgrows its predicted size makes the call fall back to the exact path (exact_levels=True forces it)."""
         seed = self._sampler_seed(seed)
         mode = {'rint': 0, 'philox': 1}[draw_mode]
+        if getattr(self, '_level_hints', None) is None:
+            self._level_hints = {}
+        hints = self._level_hints.get(sample_num)
+        if hints is not None and not exact_levels:
+            out = self._sample_stats_predicted(sample_num, mode, seed, hints)
+            if out is not None:
+                return out
         prefix, counts, memo = self.sample_stats_root(sample_num)
+        sizes = []
         for q in range(self.qubit_grouping.qudit_num):
             prefix, counts, memo = self.sample_stats_level(q, prefix, counts, memo, mode, seed)
+            sizes.append(int(prefix.shape[0]))
+        self._level_hints[sample_num] = sizes
         return prefix.view(-1, 1), counts.to(BASE_COMPLEX_TYPE)
+
+    def _sample_stats_predicted(self, sample_num: int, mode: int, seed: int, hints):
+        """All levels with capacities predicted from `hints`, one host read at the end; None when a level overflowed."""
+        dev = _lib.require_cuda(self.device)
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        qg = self.qubit_grouping
+        Q = qg.qudit_num
+        prefix, counts, memo = self.sample_stats_root(sample_num)
+        totals = pt.zeros(Q, dtype=pt.int64, device=dev)
+        caps = []
+        for q in range(Q):
+            B = prefix.shape[0]
+            k, D = qg.qubits_per_qudit[q], qg.qudit_dims_host[q]
+            # every live node carries at least one sample, so a level never holds more than sample_num nodes
+            cap = max(1, min(B * D, sample_num, int(hints[q] * 1.25) + 1024))
+            caps.append(cap)
+            cont_q, next_q = self._level_tables(q)
+            cond = self.cond_log_abs(qudit_idx=q, prefix_idx=prefix)
+            child = pt.empty((B, D), dtype=pt.float64, device=dev)
+            n_child = pt.empty(B, dtype=pt.int64, device=dev)
+            single = pt.empty(B, dtype=pt.int8, device=dev)
+            _lib.check(lib.anqs_sampler_split_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(counts), _lib.dptr(memo),
+                                                    _lib.dptr(cont_q), self.masker.memo_size, B, q, mode, seed, 0, _lib.dptr(prefix),
+                                                    _lib.dptr(child), _lib.dptr(n_child), _lib.dptr(single), sp))
+            offsets = pt.empty(B + 1, dtype=pt.int64, device=dev)
+            work = pt.empty(max(1, int(lib.anqs_scan_workspace(B)) // 8), dtype=pt.int64, device=dev)
+            _lib.check(lib.anqs_exclusive_scan_i64(_lib.dptr(n_child), _lib.dptr(offsets), B, _lib.dptr(work), sp))
+            totals[q:q + 1].copy_(offsets[B:B + 1])
+            # rows beyond the level's true size stay dead: count 0 (no children), prefix 0, memo 0
+            new_prefix = pt.zeros(cap, dtype=pt.int64, device=dev)
+            new_counts = pt.zeros(cap, dtype=pt.float64, device=dev)
+            new_memo = pt.zeros(cap, dtype=pt.int32, device=dev)
+            _lib.check(lib.anqs_sampler_emit_children_capped(_lib.dptr(child), k, qg.qudit_starts[q], _lib.dptr(prefix), _lib.dptr(memo),
+                                                             _lib.dptr(cont_q), _lib.dptr(next_q), self.masker.memo_size, B,
+                                                             _lib.dptr(offsets), _lib.dptr(single), cap, _lib.dptr(new_prefix),
+                                                             _lib.dptr(new_counts), _lib.dptr(new_memo), sp))
+            prefix, counts, memo = new_prefix, new_counts, new_memo
+        sizes = totals.cpu().tolist()   # the one host read of the call
+        if any(sz > cap for sz, cap in zip(sizes, caps)):
+            return None
+        self._level_hints[sample_num] = sizes
+        n = sizes[-1]
+        return prefix[:n].view(-1, 1), counts[:n].to(BASE_COMPLEX_TYPE)
 
     @pt.no_grad()
     def sample_indices_gumbel(self, sample_num: int, seed: int = None, uniforms=None, compact_levels: bool = None):

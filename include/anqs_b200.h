@@ -360,6 +360,14 @@ int anqs_sampler_emit_children(const double *d_child_counts, int qubits_in_qudit
                                const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,
                                const int8_t *d_single, int64_t *d_out_prefix, double *d_out_counts, int32_t *d_out_memo_idx,
                                void *stream);
+/* Same with a bound on the output rows: children that would land at or beyond out_capacity are not written.  Lets a caller
+ * size the next level from a prediction (the previous call's level sizes) instead of reading every level's size back to the
+ * host: it checks all the d_offsets totals once, after the last level, and repeats the call exactly if one exceeded its bound. */
+int anqs_sampler_emit_children_capped(const double *d_child_counts, int qubits_in_qudit, int qudit_start,
+                                      const int64_t *d_prefix, const int32_t *d_memo_idx, const uint64_t *d_cont_mask_q,
+                                      const int32_t *d_next_memo_q, int64_t memo_size, int64_t n, const int64_t *d_offsets,
+                                      const int8_t *d_single, int64_t out_capacity, int64_t *d_out_prefix, double *d_out_counts,
+                                      int32_t *d_out_memo_idx, void *stream);
 
 /* ---- A12  one level of Gumbel top-k (stochastic beam) sampling (ANQS:676-688, 718-731) -----------------
  * d_out_log_prob[i][D] = d_parent_log_prob[i] + 2*d_cond[i][:D]; d_out_gumbel[i][D] = Gumbel(log_prob)

@@ -442,3 +442,22 @@ def test_split_level_draws_follow_the_conditional_distribution(count):
     chi2 = float(((hist[p > 0] - expect) ** 2 / expect).sum())
     assert chi2 < 57 + 6 * (2 * 57) ** 0.5, chi2                    # mean dof, six sigma
     assert int(n_child.sum()) == int((child > 0).sum())
+
+
+def test_predicted_level_sizes_give_the_same_samples():
+    """sample_stats sizes its levels from the previous call (one host read per call): same configurations and counts as the
+    exact path that reads every level's size back, for the same seed; an under-predicted level falls back to the exact path."""
+    hs, masker, wf = build(20, 14)
+    N = 10 ** 6
+    i0, c0 = wf.sample_stats(N, seed=7)                       # first call: exact, records the level sizes
+    assert wf._level_hints[N][-1] == i0.shape[0]
+    i1, c1 = wf.sample_stats(N, seed=7)                       # predicted capacities
+    assert torch.equal(i0, i1) and torch.equal(c0, c1)
+    i2, c2 = wf.sample_stats(N, seed=8)
+    i3, c3 = wf.sample_stats(N, seed=8, exact_levels=True)
+    assert torch.equal(i2, i3) and torch.equal(c2, c3)
+    assert float(c2.real.sum()) == float(N)
+    wf._level_hints[N] = [1] * len(wf._level_hints[N])        # hopeless prediction: every level overflows -> exact fallback
+    wf._level_hints[N][0] = -10 ** 9
+    i4, c4 = wf.sample_stats(N, seed=8)
+    assert torch.equal(i4, i3) and torch.equal(c4, c3)
