@@ -47,7 +47,7 @@ _SIGNATURES = {
     'anqs_unique_workspace': (ctypes.c_size_t, [_c_i64]),
     'anqs_unique_i64': (_c_int, [_vp, _c_i64, _c_int, _vp, _vp, _vp, _vp, _vp]),
     'anqs_topk_workspace': (ctypes.c_size_t, [_c_i64, _c_i64]),
-    'anqs_topk_f64': (_c_int, [_vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp]),
+    'anqs_topk_f64': (_c_int, [_vp, _c_i64, _c_i64, _c_int, _vp, _vp, _vp, _vp]),
     'anqs_local_energy_sample_aware': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _vp]),
     'anqs_local_energy_sample_aware_variant': (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _c_int, _vp]),
     'anqs_accumulate_rows': (_c_int, [_vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _vp]),
@@ -80,6 +80,8 @@ _SIGNATURES = {
     'anqs_sampler_gumbel_select': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'anqs_sampler_gumbel_level': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, ctypes.c_uint64,
                                            _c_i64, _vp, _vp, _vp, _vp]),
+    'anqs_sampler_gumbel_level_keyed': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, ctypes.c_uint64,
+                                                 _c_i64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -176,6 +178,14 @@ def check(rc: int):
 
 
 def stream_ptr(device=None):
+    """The current stream of `device` as a void*.  Every launch of the library goes to the CURRENT CUDA device (grid sizes come
+    from its SM count, handles and workspaces live on it), so a tensor on another device is refused here with a clear message
+    instead of an 'invalid resource handle' from the driver: one process (or one `with torch.cuda.device(...)` block) per GPU."""
+    if device is not None:
+        device = torch.device(device)
+        if device.type == 'cuda' and device.index is not None and device.index != torch.cuda.current_device():
+            raise RuntimeError(f'anqs_b200: tensors live on {device} but the current CUDA device is cuda:{torch.cuda.current_device()}; '
+                               f'call torch.cuda.set_device({device.index}) or wrap the call in `with torch.cuda.device({device.index}):`')
     return _vp(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -224,8 +234,9 @@ def unique_i64(x: torch.Tensor, end_bit: int = 64, return_inverse: bool = True):
     return unq[:int(cnt.item())], inv
 
 
-def topk_f64(vals: torch.Tensor, k: int):
-    """First k rows of a stable descending sort of a float64 vector: (values, positions) through anqs_topk_f64."""
+def topk_f64(vals: torch.Tensor, k: int, sorted: bool = True):
+    """The k largest entries of a float64 vector through anqs_topk_f64: (values, positions), as the first k rows of a stable
+    descending sort (sorted=True) or the same set in position order (sorted=False)."""
     dev = require_cuda(vals.device)
     vals = vals.contiguous().view(-1)
     n = vals.shape[0]
@@ -233,7 +244,7 @@ def topk_f64(vals: torch.Tensor, k: int):
     top_i = torch.empty(k, dtype=torch.int64, device=dev)
     if k > 0:
         work = _workspace(lib().anqs_topk_workspace(n, k), dev)
-        check(lib().anqs_topk_f64(dptr(vals), n, int(k), dptr(top_v), dptr(top_i), dptr(work), stream_ptr(dev)))
+        check(lib().anqs_topk_f64(dptr(vals), n, int(k), int(bool(sorted)), dptr(top_v), dptr(top_i), dptr(work), stream_ptr(dev)))
     return top_v, top_i
 
 

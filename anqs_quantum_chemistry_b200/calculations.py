@@ -187,8 +187,8 @@ def sr(wf=None, sampling_result: SamplingResult = None, config: SRConfig = None)
     else:
         freqs = sampling_result.counts
     freqs = freqs / pt.sum(freqs)
-    _, order = _lib.sort_pairs(freqs.real.contiguous(), None, 0, 64, key_kind=1, xor_mask=-1)  # descending, stable
-    top = order[:config.max_indices_num]
+    # SR:96-101 sorts all the frequencies and keeps the first max_indices_num: the radix select finds them without the full sort
+    _, top = _lib.topk_f64(freqs.real.contiguous(), min(int(config.max_indices_num), freqs.shape[0]), sorted=True)
     f = freqs[top]
     f = f / pt.sum(f)
     idx = sampling_result.indices[top]

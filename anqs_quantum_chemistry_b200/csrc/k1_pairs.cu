@@ -22,7 +22,40 @@
 
 namespace anqs {
 
-constexpr int PJ_ROWS = 128, PJ_COLS = 512;
+constexpr int PJ_ROWS = 128, PJ_COLS = 512, PJ_WARPS = PJ_ROWS / 32;
+constexpr int PJ_LIST = 64;   // pending coupled pairs per warp (flushed at 32)
+
+struct PjHit {   // a coupled pair waiting for its matrix element
+    uint64_t xj;
+    int32_t u;       // index of the XY mask x_i ^ x_j
+    int16_t row;     // lane that owns row i
+    int16_t col;     // column slot in the staged chunk (its amplitude)
+};
+
+// Matrix elements of up to 32 pending pairs of one warp, one per lane, and their accumulation into the owning lanes (in list
+// order, which is column order for every row: deterministic).
+template <bool REAL>
+__device__ __forceinline__ void pj_flush(const Tables &t, PjHit *list, double2 *contrib, int cnt, const double2 *s_a, double &er, double &ei) {
+    const int lane = threadIdx.x & 31;
+    const bool active = lane < cnt;
+    PjHit h = list[lane];
+    double hr = 0.0, hi = 0.0;
+    int2 g = make_int2(0, 0);
+    if (active) g = __ldg(t.grp + h.u);
+    warp_matrix_elements<REAL>(t, active, g, deinterleave(h.xj), hr, hi);
+    if (active) {
+        const double2 a = s_a[h.col];
+        contrib[lane] = make_double2(hr * a.x - hi * a.y, hr * a.y + hi * a.x);
+    }
+    __syncwarp();
+    for (int e = 0; e < cnt; ++e) {
+        if (list[e].row == lane) {
+            er += contrib[e].x;
+            ei += contrib[e].y;
+        }
+    }
+    __syncwarp();
+}
 
 template <bool REAL>
 __global__ void __launch_bounds__(PJ_ROWS) pair_join_kernel(Tables t, HashView masks, const int64_t *__restrict__ samples,
@@ -32,37 +65,62 @@ __global__ void __launch_bounds__(PJ_ROWS) pair_join_kernel(Tables t, HashView m
     __shared__ uint64_t s_x[PJ_COLS];
     __shared__ double2 s_a[PJ_COLS];
     __shared__ uint8_t s_ok[PJ_COLS];
+    __shared__ PjHit s_list[PJ_WARPS][PJ_LIST];
+    __shared__ double2 s_contrib[PJ_WARPS][32];
+    __shared__ int s_cnt[PJ_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * PJ_ROWS + threadIdx.x;
     const bool have = r < row_len;
     const uint64_t xi = have ? (uint64_t)samples[row_start + r] : 0ull;
     const int64_t c_lo = (int64_t)blockIdx.y * cols_per_slice, c_hi = min(n_total, c_lo + cols_per_slice);
     double er = 0.0, ei = 0.0;
+    if (lane == 0) s_cnt[warp] = 0;
     for (int64_t c0 = c_lo; c0 < c_hi; c0 += PJ_COLS) {
         const int cnt = (int)min((int64_t)PJ_COLS, c_hi - c0);
         __syncthreads();
         for (int k = threadIdx.x; k < cnt; k += PJ_ROWS) {
             const uint64_t xj = (uint64_t)samples[c0 + k];
             // columns outside the (N_alpha, N_beta) sector never couple (the 'ham' path drops them with its electron-count filter)
-            const bool ok = __popcll(xj & 0x5555555555555555ULL) == alpha && __popcll(xj & 0xAAAAAAAAAAAAAAAAULL) == beta;
             s_x[k] = xj;
-            s_ok[k] = ok ? 1 : 0;
+            s_ok[k] = (__popcll(xj & 0x5555555555555555ULL) == alpha && __popcll(xj & 0xAAAAAAAAAAAAAAAAULL) == beta) ? 1 : 0;
             s_a[k] = amps[c0 + k];
         }
         __syncthreads();
-        if (!have) continue;
+        // every lane tests its row against the same column (broadcast reads); the rare survivors look their mask up and go onto
+        // the warp's pending list, which is evaluated 32 pairs at a time, one per lane - so a hit costs the warp one lane's
+        // work, not a divergent excursion of the whole warp
         for (int k = 0; k < cnt; ++k) {
             const uint64_t xj = s_x[k];
             const uint64_t m = xi ^ xj;
-            if (__popcll(m) > max_weight || !s_ok[k]) continue;
-            double dr, di;
-            const long long u = hash_lookup(masks, deinterleave(m), dr, di);
-            if (u < 0) continue;
-            const int2 g = __ldg(t.grp + u);
-            double hr, hi;
-            group_sum_lane<REAL>(t, g.x, g.y, deinterleave(xj), hr, hi);
-            const double2 a = s_a[k];
-            er += hr * a.x - hi * a.y;
-            ei += hr * a.y + hi * a.x;
+            if (have && __popcll(m) <= max_weight && s_ok[k]) {
+                double dr, di;
+                const long long u = hash_lookup(masks, deinterleave(m), dr, di);
+                if (u >= 0) {
+                    const int pos = atomicAdd(&s_cnt[warp], 1);
+                    PjHit h;
+                    h.xj = xj;
+                    h.u = (int32_t)u;
+                    h.row = (int16_t)lane;
+                    h.col = (int16_t)k;
+                    s_list[warp][pos] = h;
+                }
+            }
+            __syncwarp();
+            const int pending = *reinterpret_cast<volatile int *>(&s_cnt[warp]);
+            if (pending >= 32) {
+                pj_flush<REAL>(t, s_list[warp], s_contrib[warp], 32, s_a, er, ei);
+                if (lane < pending - 32) s_list[warp][lane] = s_list[warp][32 + lane];
+                __syncwarp();
+                if (lane == 0) s_cnt[warp] = pending - 32;
+                __syncwarp();
+            }
+        }
+        // the amplitudes of this chunk go away with it: evaluate what is pending
+        const int pending = *reinterpret_cast<volatile int *>(&s_cnt[warp]);
+        if (pending > 0) {
+            pj_flush<REAL>(t, s_list[warp], s_contrib[warp], pending, s_a, er, ei);
+            if (lane == 0) s_cnt[warp] = 0;
+            __syncwarp();
         }
     }
     if (have) partial[(size_t)blockIdx.y * row_len + r] = make_double2(er, ei);
@@ -83,11 +141,11 @@ __global__ void pair_join_finish_kernel(const double2 *__restrict__ partial, int
     }
 }
 
+// Column slices: a function of the size of the sampled set ONLY, so that a window of rows (the multi-GPU shard path) adds the
+// same partial sums in the same order as the full evaluation and comes out bit-identical.
 static int pj_slices(int64_t row_len, int64_t n_total) {
-    const int64_t row_blocks = (row_len + PJ_ROWS - 1) / PJ_ROWS;
-    const int64_t want = std::max<int64_t>(1, (4 * (int64_t)sm_count_of_current_device() + row_blocks - 1) / row_blocks);
-    const int64_t max_slices = std::max<int64_t>(1, (n_total + PJ_COLS - 1) / PJ_COLS);
-    return (int)std::min<int64_t>(std::min<int64_t>(want, max_slices), 1024);
+    (void)row_len;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(64, (n_total + 63) / 64));
 }
 
 }  // namespace anqs
@@ -114,7 +172,7 @@ int anqs_local_energy_pair_join(const anqs_tables_t *h, const int64_t *d_samples
     cudaStream_t s = (cudaStream_t)stream;
     HashView masks = make_hash_view(d_mask_table, mask_capacity);
     const int slices = pj_slices(row_len, n_total);
-    const int64_t cols = ((n_total + slices - 1) / slices + PJ_COLS - 1) / PJ_COLS * PJ_COLS;
+    const int64_t cols = ((n_total + slices - 1) / slices + 31) / 32 * 32;
     dim3 grid((unsigned)((row_len + PJ_ROWS - 1) / PJ_ROWS), (unsigned)slices);
     if (t->weights_real)
         pair_join_kernel<true><<<grid, PJ_ROWS, 0, s>>>(*t, masks, d_samples, (const double2 *)d_amps, n_total, row_start, row_len, alpha_num,

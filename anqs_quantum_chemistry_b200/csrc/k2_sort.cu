@@ -115,6 +115,81 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t *
     }
 }
 
+// Small inputs (n <= RS_SMALL_MAX): every pass in ONE launch of ONE CTA - counts, scan and stable scatter separated by
+// __syncthreads(), ping-pong between the caller's output and the workspace.  A VMC iteration at 1e4 samples sorts a handful of
+// such arrays; at three launches per pass they would cost more in launch latency than all its other kernels together.
+constexpr int RS_SMALL_THREADS = 1024, RS_SMALL_WARPS = RS_SMALL_THREADS / 32, RS_SMALL_MAX = 1 << 14;
+
+__global__ void __launch_bounds__(RS_SMALL_THREADS) rs_small_kernel(const uint64_t *__restrict__ keys_in, const int64_t *__restrict__ vals_in,
+                                                                    uint64_t *keys_out, int64_t *vals_out, uint64_t *tmp_k, int64_t *tmp_v, int n,
+                                                                    int begin_bit, int end_bit, int kind, uint64_t xor_mask) {
+    __shared__ uint32_t wh[RS_SMALL_WARPS][256];   // per-warp digit bases of the chunk being scattered
+    __shared__ uint32_t base[256];                 // running global base per digit
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npass = (end_bit - begin_bit + 7) / 8;
+    const uint64_t *src_k = keys_in;
+    const int64_t *src_v = vals_in;
+    for (int p = 0; p < npass; ++p) {
+        const bool to_out = ((npass - 1 - p) & 1) == 0;
+        uint64_t *dst_k = to_out ? keys_out : tmp_k;
+        int64_t *dst_v = to_out ? vals_out : tmp_v;
+        const int shift = begin_bit + 8 * p;
+        const uint32_t mask = (uint32_t)((1u << min(8, end_bit - shift)) - 1u);
+        // digit histogram of the whole array -> exclusive scan = first output position of every digit
+        if (threadIdx.x < 256) base[threadIdx.x] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += RS_SMALL_THREADS) atomicAdd(&base[digit_of(sort_key(src_k[i], kind, xor_mask), shift, mask)], 1u);
+        __syncthreads();
+        if (warp == 0) {  // 256 bins, 8 per lane
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i] = base[lane * 8 + i]; sum += v[i]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { base[lane * 8 + i] = run; run += v[i]; }
+        }
+        __syncthreads();
+        // stable scatter, 1024 elements (32 per warp) at a time, in order
+        for (int c0 = 0; c0 < n; c0 += RS_SMALL_THREADS) {
+            for (int i = threadIdx.x; i < RS_SMALL_WARPS * 256; i += RS_SMALL_THREADS) (&wh[0][0])[i] = 0u;
+            __syncthreads();
+            const int j = c0 + threadIdx.x;
+            const bool ok = j < n;
+            const uint64_t bits = ok ? src_k[j] : 0ull;
+            const uint32_t d = ok ? digit_of(sort_key(bits, kind, xor_mask), shift, mask) : 256u + (uint32_t)lane;
+            const unsigned m = __match_any_sync(0xffffffffu, d);
+            const uint32_t below = (uint32_t)__popc(m & ((1u << lane) - 1u));
+            if (ok && below == 0u) wh[warp][d] = (uint32_t)__popc(m);
+            __syncthreads();
+            if (threadIdx.x < 256) {  // per digit: this chunk's warps in order behind the running base
+                uint32_t run = base[threadIdx.x];
+                for (int w = 0; w < RS_SMALL_WARPS; ++w) {
+                    const uint32_t c = wh[w][threadIdx.x];
+                    wh[w][threadIdx.x] = run;
+                    run += c;
+                }
+                base[threadIdx.x] = run;
+            }
+            __syncthreads();
+            if (ok) {
+                const uint32_t pos = wh[warp][d] + below;
+                dst_k[pos] = bits;
+                dst_v[pos] = src_v ? src_v[j] : (int64_t)j;
+            }
+            __syncthreads();
+        }
+        src_k = dst_k;
+        src_v = dst_v;
+        __syncthreads();
+    }
+}
+
 __global__ void copy_pairs_kernel(const uint64_t *__restrict__ keys_in, const int64_t *__restrict__ vals_in, uint64_t *__restrict__ keys_out,
                                   int64_t *__restrict__ vals_out, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -141,6 +216,10 @@ static int sort_pairs(const uint64_t *keys_in, const int64_t *vals_in, uint64_t 
     uint64_t *tmp_k = (uint64_t *)w;
     int64_t *tmp_v = (int64_t *)(w + align256((size_t)n * 8));
     uint32_t *counts = (uint32_t *)(w + 2 * align256((size_t)n * 8));
+    if (n <= RS_SMALL_MAX) {
+        rs_small_kernel<<<1, RS_SMALL_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, tmp_k, tmp_v, (int)n, begin_bit, end_bit, kind, xor_mask);
+        return cudaGetLastError() == cudaSuccess ? 0 : 2;
+    }
     const int nblocks = (int)rs_blocks(n);
     const uint64_t *src_k = keys_in;
     const int64_t *src_v = vals_in;
@@ -181,6 +260,8 @@ struct SelectState {
     uint64_t prefix;        // digits of the k-th smallest transformed key decided so far
     uint64_t decided_mask;  // which bits of prefix are decided
     int64_t k_rem;          // how many of the elements that match the prefix are still wanted
+    uint32_t done_blocks;   // blocks of the current digit's launch that have added their histogram
+    uint32_t pad;
     uint32_t hist[256];
 };
 
@@ -189,12 +270,16 @@ __global__ void sel_init_kernel(SelectState *st, int64_t k) {
         st->prefix = 0ull;
         st->decided_mask = 0ull;
         st->k_rem = k;
+        st->done_blocks = 0u;
     }
     st->hist[threadIdx.x] = 0u;
 }
-__global__ void __launch_bounds__(256) sel_hist_kernel(const uint64_t *__restrict__ vals, int64_t n, int kind, uint64_t xor_mask, int shift,
-                                                      SelectState *st) {
+// one digit of the selection: histogram of the digit over the elements that match the prefix decided so far; the block that
+// finishes last reads the histogram, picks the bucket of the k-th smallest key and extends the prefix (no second launch)
+__global__ void __launch_bounds__(256) sel_digit_kernel(const uint64_t *__restrict__ vals, int64_t n, int kind, uint64_t xor_mask, int shift,
+                                                       SelectState *st) {
     __shared__ uint32_t hist[256];
+    __shared__ bool s_last;
     hist[threadIdx.x] = 0u;
     __syncthreads();
     const uint64_t prefix = st->prefix, dmask = st->decided_mask;
@@ -204,23 +289,26 @@ __global__ void __launch_bounds__(256) sel_hist_kernel(const uint64_t *__restric
     }
     __syncthreads();
     if (hist[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], hist[threadIdx.x]);
-}
-__global__ void sel_step_kernel(SelectState *st, int shift) {  // one block of 256 threads
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = st->hist[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&st->done_blocks, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    hist[threadIdx.x] = *reinterpret_cast<volatile uint32_t *>(&st->hist[threadIdx.x]);
     __syncthreads();
     if (threadIdx.x == 0) {
         int64_t k = st->k_rem, before = 0;
         int b = 0;
         for (; b < 255; ++b) {
-            if (before + (int64_t)h[b] >= k) break;
-            before += h[b];
+            if (before + (int64_t)hist[b] >= k) break;
+            before += hist[b];
         }
-        st->prefix |= (uint64_t)b << shift;
-        st->decided_mask |= 0xffull << shift;
+        st->prefix = prefix | ((uint64_t)b << shift);
+        st->decided_mask = dmask | (0xffull << shift);
         st->k_rem = k - before;
+        st->done_blocks = 0u;
     }
-    __syncthreads();
     st->hist[threadIdx.x] = 0u;
 }
 // packed flags: (key < T) << 32 | (key == T); their scan gives both ranks at once
@@ -317,7 +405,7 @@ static size_t topk_ws_bytes(int64_t n, int64_t k) {
 }
 size_t anqs_topk_workspace(int64_t n, int64_t k) { return (n < 0 || k < 0) ? 0 : topk_ws_bytes(n, k); }
 
-int anqs_topk_f64(const double *d_vals, int64_t n, int64_t k, double *d_top_vals, int64_t *d_top_idx, void *d_work, void *stream) {
+int anqs_topk_f64(const double *d_vals, int64_t n, int64_t k, int sorted, double *d_top_vals, int64_t *d_top_idx, void *d_work, void *stream) {
     ANQS_REQUIRE(n >= 0 && n < ((int64_t)1 << 31), "element count out of range");
     ANQS_REQUIRE(k >= 0 && k <= n, "need 0 <= k <= n");
     if (k == 0) return 0;
@@ -338,22 +426,28 @@ int anqs_topk_f64(const double *d_vals, int64_t n, int64_t k, double *d_top_vals
     void *scan_ws = w;
     w += align256(anqs_scan_workspace(n));
     const uint64_t *bits = (const uint64_t *)d_vals;
-    if (n <= 2 * k || n <= 4096) {  // nothing to gain from selecting first
-        ANQS_REQUIRE(sort_pairs(bits, nullptr, (uint64_t *)flags, excl, n, 0, 64, 1, desc, w, s) == 0,
-                     "kernel launch failed");
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    if (k == n && !sorted) {  // everything is kept and no order is asked for
+        copy_pairs_kernel<<<grid, 256, 0, s>>>(bits, nullptr, (uint64_t *)d_top_vals, d_top_idx, n);
+        ANQS_LAUNCH_CHECK();
+        return 0;
+    }
+    if (sorted && (n <= 2 * k || n <= RS_SMALL_MAX)) {  // nothing to gain from selecting first (small inputs sort in one launch)
+        ANQS_REQUIRE(sort_pairs(bits, nullptr, (uint64_t *)flags, excl, n, 0, 64, 1, desc, w, s) == 0, "kernel launch failed");
         ANQS_CUDA(cudaMemcpyAsync(d_top_vals, flags, (size_t)k * 8, cudaMemcpyDeviceToDevice, s));
         ANQS_CUDA(cudaMemcpyAsync(d_top_idx, excl, (size_t)k * 8, cudaMemcpyDeviceToDevice, s));
         return 0;
     }
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
     sel_init_kernel<<<1, 256, 0, s>>>(st, k);
-    for (int shift = 56; shift >= 0; shift -= 8) {
-        sel_hist_kernel<<<grid, 256, 0, s>>>(bits, n, 1, desc, shift, st);
-        sel_step_kernel<<<1, 256, 0, s>>>(st, shift);
-    }
+    for (int shift = 56; shift >= 0; shift -= 8) sel_digit_kernel<<<grid, 256, 0, s>>>(bits, n, 1, desc, shift, st);
     sel_flags_kernel<<<grid, 256, 0, s>>>(bits, n, 1, desc, st, flags);
     ANQS_LAUNCH_CHECK();
     if (anqs_exclusive_scan_i64(flags, excl, n, scan_ws, stream) != 0) return 2;
+    if (!sorted) {  // survivors in position order: a valid top-k set, one sort cheaper
+        sel_compact_kernel<<<grid, 256, 0, s>>>(bits, n, 1, desc, st, excl, (uint64_t *)d_top_vals, d_top_idx);
+        ANQS_LAUNCH_CHECK();
+        return 0;
+    }
     sel_compact_kernel<<<grid, 256, 0, s>>>(bits, n, 1, desc, st, excl, kept_bits, kept_idx);
     ANQS_LAUNCH_CHECK();
     ANQS_REQUIRE(sort_pairs(kept_bits, kept_idx, (uint64_t *)d_top_vals, d_top_idx, k, 0, 64, 1, desc, w, s) == 0, "kernel launch failed");

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(K4_WARPS * 32)
 gumbel_level_kernel(const double *__restrict__ cond, int DM, int k, const double *__restrict__ parent_log_prob,
                     const double *__restrict__ parent_gumbel, const int32_t *__restrict__ memo_idx,
                     const unsigned long long *__restrict__ cont_mask_q, int64_t memo_size, int64_t B, int level,
-                    uint64_t seed, int64_t parent_offset, const double *__restrict__ uniforms,
+                    uint64_t seed, int64_t parent_offset, const int64_t *__restrict__ rng_keys, const double *__restrict__ uniforms,
                     double *__restrict__ out_log_prob, double *__restrict__ out_gumbel) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = 1 << k;
@@ -321,7 +321,9 @@ gumbel_level_kernel(const double *__restrict__ cond, int DM, int k, const double
                 if (uniforms) {
                     u = uniforms[b * D + d];
                 } else {
-                    const uint64_t parent = (uint64_t)(parent_offset + b);
+                    // keyed by the node's own identity (its packed prefix) when given: the draws then do not depend on the order or
+                    // the position of the rows of a level
+                    const uint64_t parent = rng_keys ? (uint64_t)rng_keys[b] : (uint64_t)(parent_offset + b);
                     Philox rng(seed, (uint32_t)parent, (uint32_t)(parent >> 32), ((uint32_t)level << 16) | (uint32_t)d, 0x47u);
                     uint4 r = rng();
                     u = u01(r.x, r.y);
@@ -433,6 +435,15 @@ int anqs_sampler_gumbel_level(const double *d_cond, int max_qudit_dim, int qubit
                               const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n, int level, uint64_t seed,
                               int64_t parent_offset, const double *d_uniforms, double *d_out_log_prob,
                               double *d_out_gumbel, void *stream) {
+    return anqs_sampler_gumbel_level_keyed(d_cond, max_qudit_dim, qubits_in_qudit, d_parent_log_prob, d_parent_gumbel, d_memo_idx, d_cont_mask_q,
+                                           memo_size, n, level, seed, parent_offset, nullptr, d_uniforms, d_out_log_prob, d_out_gumbel, stream);
+}
+
+int anqs_sampler_gumbel_level_keyed(const double *d_cond, int max_qudit_dim, int qubits_in_qudit,
+                                    const double *d_parent_log_prob, const double *d_parent_gumbel, const int32_t *d_memo_idx,
+                                    const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n, int level, uint64_t seed,
+                                    int64_t parent_offset, const int64_t *d_rng_keys, const double *d_uniforms, double *d_out_log_prob,
+                                    double *d_out_gumbel, void *stream) {
     ANQS_REQUIRE(n >= 0, "negative parent count");
     ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6 && (1 << qubits_in_qudit) <= max_qudit_dim && max_qudit_dim <= 64,
                  "qudit must have 1..6 qubits and fit max_qudit_dim <= 64");
@@ -442,7 +453,8 @@ int anqs_sampler_gumbel_level(const double *d_cond, int max_qudit_dim, int qubit
     int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
     gumbel_level_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d_cond, max_qudit_dim, qubits_in_qudit, d_parent_log_prob, d_parent_gumbel, d_memo_idx,
-        (const unsigned long long *)d_cont_mask_q, memo_size, n, level, seed, parent_offset, d_uniforms, d_out_log_prob, d_out_gumbel);
+        (const unsigned long long *)d_cont_mask_q, memo_size, n, level, seed, parent_offset, d_rng_keys, d_uniforms, d_out_log_prob,
+        d_out_gumbel);
     ANQS_LAUNCH_CHECK();
     return 0;
 }

@@ -186,10 +186,12 @@ class AutoregressiveSamplerMixin:
         """ANQS:778-818: stochastic-beam (Gumbel top-k) sampling without replacement.  Returns (indices [N,1],
         freqs [N] = model probabilities renormalised over the kept set).  `uniforms`, if given, is a callable
         (level, B, D) -> [B, D] float64 tensor of U(0,1) variates (parity tests).
-        compact_levels: drop the masked children after every level like the reference does (one host read per level) instead
-        of carrying them on as dead rows and dropping them once at the end.  Both give the same samples - the counter-based
-        draws are keyed by the row index, and the alive rows keep theirs - so the default compacts only when `uniforms` are
-        injected, whose shapes follow the reference's compacted levels."""
+        compact_levels: drop the masked children after every level like the reference does (sorted top-k and one host read per
+        level) instead of carrying them on as dead rows and dropping them once at the end (unsorted top-k - a radix select and an
+        ordered compaction, no sort - and one host read per call).  Both give the same SET of samples with the same
+        frequencies: the counter-based draws are keyed by the row's packed prefix, not by its position.  The default compacts
+        only when `uniforms` are injected, whose shapes follow the reference's compacted, sorted levels; the rows then come
+        back in the reference's order (descending Gumbel), otherwise in the order of the last level's candidates."""
         if compact_levels is None:
             compact_levels = uniforms is not None
         dev = _lib.require_cuda(self.device)
@@ -208,12 +210,13 @@ class AutoregressiveSamplerMixin:
             out_lp = pt.empty((B, D), dtype=pt.float64, device=dev)
             out_g = pt.empty((B, D), dtype=pt.float64, device=dev)
             u = uniforms(q, B, D).to(dev).contiguous() if uniforms is not None else None
-            _lib.check(lib.anqs_sampler_gumbel_level(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(log_prob), _lib.dptr(gumbel),
-                                                     _lib.dptr(memo), _lib.dptr(cont_q), self.masker.memo_size, B, q, seed, 0,
-                                                     _lib.dptr(u), _lib.dptr(out_lp), _lib.dptr(out_g), sp))
+            _lib.check(lib.anqs_sampler_gumbel_level_keyed(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(log_prob), _lib.dptr(gumbel),
+                                                           _lib.dptr(memo), _lib.dptr(cont_q), self.masker.memo_size, B, q, seed, 0,
+                                                           _lib.dptr(prefix), _lib.dptr(u), _lib.dptr(out_lp), _lib.dptr(out_g), sp))
             flat_g = out_g.view(-1)
             keep = min(sample_num, flat_g.shape[0])
-            top_g, top_i = _lib.topk_f64(flat_g, keep)   # ANQS:733: the first `keep` rows of the stable descending sort (radix select)
+            # ANQS:733: the `keep` largest Gumbels; as the head of the stable descending sort only where the order matters
+            top_g, top_i = _lib.topk_f64(flat_g, keep, sorted=compact_levels)
             # ANQS:735-776 in one kernel: children of the kept rows; masked children (gumbel = -inf, ANQS:804-809) sort last
             new_prefix = pt.empty(keep, dtype=pt.int64, device=dev)
             new_memo = pt.empty(keep, dtype=pt.int32, device=dev)
@@ -231,8 +234,10 @@ class AutoregressiveSamplerMixin:
                 # of their own children) and dropped once after the last level
                 prefix, memo, log_prob, gumbel = new_prefix, new_memo, new_lp, new_g
         if not compact_levels:
+            # dead rows (Gumbel = -inf) are scattered among the alive ones: one stable 1-bit radix pass puts the alive rows first
+            _, order = _lib.sort_pairs(pt.isinf(gumbel).to(pt.int64), None, 0, 1)
             alive = int(n_alive.item())
-            prefix, log_prob = prefix[:alive], log_prob[:alive]
+            prefix, log_prob = prefix[order[:alive]], log_prob[order[:alive]]
         log_prob = log_prob - pt.logsumexp(log_prob, dim=0)
         return prefix.view(-1, 1), pt.exp(log_prob)
 

@@ -108,6 +108,26 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
             self._param_list = list(self.parameters())
         return self._param_list
 
+    def invalidate_caches(self):
+        """Forget everything derived from the parameter VALUES: the MADE re-masking mark, the tensor-core packed weights, the
+        kernel descriptors.  The caches are keyed on (tensor version, data pointer), which in-place writes through `p.data`
+        (`p.data.copy_()`, EMA updates, weight surgery - the reference's own idiom) do not change: call this after such a
+        write.  load_state_dict() and .to() / .double() / ... call it themselves; optimiser steps and `p.copy_()` under
+        no_grad bump the version and need nothing."""
+        for name in ('_masked_key', '_packed_key', '_desc_cache', '_ptr_key', '_param_list'):
+            if hasattr(self, name):
+                setattr(self, name, None)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_caches()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_caches()
+        return out
+
     def _packed_weights(self, desc):
         """Parameters packed for the tensor-core kernels; repacked when one of them changed."""
         key = tuple((p._version, p.data_ptr()) for p in self._params())

@@ -148,12 +148,15 @@ int anqs_sort_pairs_u64(const uint64_t *d_keys_in, const int64_t *d_vals_in, uin
 size_t anqs_unique_workspace(int64_t n);
 int anqs_unique_i64(const int64_t *d_in, int64_t n, int end_bit, int64_t *d_unq, int64_t *d_inv, int64_t *d_n_unique, void *d_work,
                     void *stream);
-/* The k largest of n doubles, descending, ties by position: d_top_vals / d_top_idx = the first k rows of
- * torch.sort(vals, descending=True, stable=True) (ANQS:733 keeps exactly those).  An 8-bit radix select finds the k-th value
- * from histograms alone, the survivors are compacted in order and only they are sorted.  -inf (masked children) sort last;
- * NaNs are not expected. */
+/* The k largest of n doubles.  sorted != 0: descending, ties by position - d_top_vals / d_top_idx = the first k rows of
+ * torch.sort(vals, descending=True, stable=True) (ANQS:733 keeps exactly those).  sorted == 0: the same SET in position order
+ * (ties at the cut still go to the lower positions), which is all a stochastic-beam level needs when its draws are keyed by
+ * the row's own identity; saves the final sort.  An 8-bit radix select finds the k-th value from histograms alone (one launch
+ * per digit, the last block of each extends the prefix), the survivors are compacted in order and only they are sorted.
+ * -inf (masked children) rank last; NaNs are not expected. */
 size_t anqs_topk_workspace(int64_t n, int64_t k);
-int anqs_topk_f64(const double *d_vals, int64_t n, int64_t k, double *d_top_vals, int64_t *d_top_idx, void *d_work, void *stream);
+int anqs_topk_f64(const double *d_vals, int64_t n, int64_t k, int sorted, double *d_top_vals, int64_t *d_top_idx, void *d_work,
+                  void *stream);
 
 /* ---- A2+A3+A5+A6+A7  fused sample-aware local energy --------------------------------------------------
  * PauliObservable.compute_var_local_energy_proxy(coupling_method='ham') (PO:396-487, non-symmetric branch):
@@ -378,6 +381,13 @@ int anqs_sampler_gumbel_level(const double *d_cond, int max_qudit_dim, int qubit
                               const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n, int level, uint64_t seed,
                               int64_t parent_offset, const double *d_uniforms, double *d_out_log_prob,
                               double *d_out_gumbel, void *stream);
+/* Same with the Philox draws keyed by d_rng_keys[i] (pass the packed prefixes) instead of parent_offset + i: a level then
+ * gives the same children whatever the order or position of its rows, so the per-level top-k need not be sorted. */
+int anqs_sampler_gumbel_level_keyed(const double *d_cond, int max_qudit_dim, int qubits_in_qudit,
+                                    const double *d_parent_log_prob, const double *d_parent_gumbel, const int32_t *d_memo_idx,
+                                    const uint64_t *d_cont_mask_q, int64_t memo_size, int64_t n, int level, uint64_t seed,
+                                    int64_t parent_offset, const int64_t *d_rng_keys, const double *d_uniforms, double *d_out_log_prob,
+                                    double *d_out_gumbel, void *stream);
 
 /* Survivors of one Gumbel top-k level (ANQS:733-776).  d_sorted_idx / d_sorted_gumbel = the level's [n*D] perturbed
  * log-probabilities sorted in descending order (flat index parent * D + outcome; the global sort itself is a library call).

@@ -339,12 +339,15 @@ def test_sub_tree_sharded_sampling_is_identical(n, ne, samples):
 
 @pytest.mark.parametrize('n,ne,num', [(12, 4, 100), (20, 14, 5000), (14, 10, 10 ** 4)])
 def test_gumbel_dead_rows_equal_compaction(n, ne, num):
-    """Production Gumbel sampling carries masked children on as dead rows and reads the host once; compacting after every
-    level (what the reference does, and what the parity mode with injected uniforms does) gives the same samples bit for bit."""
+    """Production Gumbel sampling carries masked children on as dead rows, takes an UNSORTED top-k per level and reads the host
+    once; compacting and sorting after every level (what the reference does, and what the parity mode with injected uniforms
+    does) gives the same set of samples with the same frequencies - the draws are keyed by the rows' prefixes, not positions."""
     hs, masker, wf = build(n, ne)
     a_idx, a_f = wf.sample_indices_gumbel(num, seed=123, compact_levels=False)
     b_idx, b_f = wf.sample_indices_gumbel(num, seed=123, compact_levels=True)
-    assert torch.equal(a_idx, b_idx) and torch.equal(a_f, b_f)
+    pa, pb = torch.argsort(a_idx.view(-1)), torch.argsort(b_idx.view(-1))
+    assert torch.equal(a_idx.view(-1)[pa], b_idx.view(-1)[pb])
+    assert float((a_f[pa] - b_f[pb]).abs().max()) < 1e-14
     assert a_idx.shape[0] == min(num, a_idx.shape[0]) and abs(float(a_f.sum()) - 1.0) < 1e-12
     assert torch.unique(a_idx).shape[0] == a_idx.shape[0]
 

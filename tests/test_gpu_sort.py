@@ -53,6 +53,9 @@ def test_topk_is_the_head_of_a_stable_descending_sort(n, k):
     top_v, top_i = _lib.topk_f64(v, k)
     ref_v, ref_i = torch.sort(v, descending=True, stable=True)
     assert torch.equal(top_v, ref_v[:k]) and torch.equal(top_i, ref_i[:k])
+    # unsorted variant: the same set, in position order
+    set_v, set_i = _lib.topk_f64(v, k, sorted=False)
+    assert torch.equal(set_i, torch.sort(ref_i[:k]).values) and torch.equal(set_v, v[set_i])
 
 
 def test_descending_float_sort_with_negative_zero_and_infinities():
