@@ -65,17 +65,21 @@ def test_local_energy_matches_reference(case, tmp_path):
                                                             coupling_method=method, chunk_size=20000, alpha_num=na, beta_num=nb)
         assert e.dtype == torch.complex128 and tuple(e.shape) == (s.shape[0],)
         assert np.abs(e.cpu().numpy() - g[f'eloc_{method}']).max() < 1e-10 * scale
+    # the pair-join kernel (what 'trie' / 'all_to_all' run for large mask lists and small batches) against the reference's trie path
+    e_pj = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='trie',
+                                              alpha_num=na, beta_num=nb, kernel_variant=3)[0]
+    assert np.abs(e_pj.cpu().numpy() - g['eloc_trie']).max() < 1e-10 * scale
     with pytest.raises(NotImplementedError):
         ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='hamming_ball',
                                            alpha_num=na, beta_num=nb)
     # a window of rows (the multi-GPU shard path) equals the same rows of the full evaluation
     n = s.shape[0]
     lo, ln = n // 3, n // 2
-    for method in ('ham', 'trie'):   # the fused kernel and the pair-join kernel
-        e = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method=method,
-                                               alpha_num=na, beta_num=nb)[0]
-        w, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method=method,
-                                                     alpha_num=na, beta_num=nb, row_start=lo, row_len=ln)
+    for variant in (0, 3):   # the fused kernel and the pair-join kernel
+        e = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
+                                               alpha_num=na, beta_num=nb, kernel_variant=variant)[0]
+        w, _, _ = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
+                                                     alpha_num=na, beta_num=nb, row_start=lo, row_len=ln, kernel_variant=variant)
         assert torch.equal(w, e[lo:lo + ln])
 
 
