@@ -69,6 +69,8 @@ _SIGNATURES = {
     'anqs_made_cond_log_abs_tc': (_c_int, [_vp, _vp, _c_int, _vp, _c_i64, _vp, _vp]),
     'anqs_transformer_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
     'anqs_transformer_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
+    'anqs_transformer_backward_workspace': (_c_i64, [_vp, _vp, _c_i64]),
+    'anqs_transformer_backward': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp]),
     'anqs_transformer_tc_packed_bytes': (ctypes.c_size_t, [_vp]),
     'anqs_transformer_tc_pack': (_c_int, [_vp, _vp, _vp]),
     'anqs_transformer_log_psi_tc': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),
@@ -114,6 +116,16 @@ class TransformerDesc(ctypes.Structure):
                 ('ln1_b', ctypes.c_void_p * 4), ('ln2_w', ctypes.c_void_p * 4), ('ln2_b', ctypes.c_void_p * 4),
                 ('dec_w', ctypes.c_void_p), ('dec_b', ctypes.c_void_p), ('cont_mask', ctypes.c_void_p),
                 ('memo_size', ctypes.c_int64), ('ln_eps', ctypes.c_double)]
+
+
+class TransformerGrads(ctypes.Structure):
+    """anqs_transformer_grads_t (include/anqs_b200.h): destinations of the parameter gradients."""
+    _fields_ = [('tok_emb', ctypes.c_void_p), ('pos_emb', ctypes.c_void_p),
+                ('in_proj_w', ctypes.c_void_p * 4), ('in_proj_b', ctypes.c_void_p * 4), ('out_proj_w', ctypes.c_void_p * 4),
+                ('out_proj_b', ctypes.c_void_p * 4), ('lin1_w', ctypes.c_void_p * 4), ('lin1_b', ctypes.c_void_p * 4),
+                ('lin2_w', ctypes.c_void_p * 4), ('lin2_b', ctypes.c_void_p * 4), ('ln1_w', ctypes.c_void_p * 4),
+                ('ln1_b', ctypes.c_void_p * 4), ('ln2_w', ctypes.c_void_p * 4), ('ln2_b', ctypes.c_void_p * 4),
+                ('dec_w', ctypes.c_void_p), ('dec_b', ctypes.c_void_p)]
 
 
 # entry points added by later kernel families register themselves here (name -> (restype, argtypes))

@@ -7,9 +7,10 @@ of outcome 1.  The reference's legacy ANQS scaffolding around it is not construc
 plugs into the live framework instead: one qubit per qudit, continuation masks from the LocallyDecomposableMasker
 (QG:199-213), masked normalisation re -= 0.5 logsumexp(2 re) (ANQS:392-405), samplers of AbstractANQS (ANQS:494-818).
 
-Compute: inference (amplitudes without gradients, the samplers' conditionals) runs in the hand-written fp64 kernel
-k5_transformer.cu.  When gradients are needed the forward pass is evaluated through the torch module so that autograd can
-differentiate it; both paths agree to 1e-10 (tests/test_gpu_transformer.py).
+Compute: amplitudes and the samplers' conditionals run in the hand-written fp64 kernel k5_transformer.cu; the gradient
+with respect to the parameters in k5_transformer_bwd.cu (per-sample chain with the forward pass recomputed per tile) plus
+the batch reductions of k3_batch_reduce.cu, wired into autograd by _TransformerLogPsi below.  `log_psi_torch` - the same
+function through the torch module - is kept only as the fp64 cross-check of both (tests/test_gpu_transformer.py, 1e-10).
 """
 import ctypes
 import math
@@ -66,6 +67,56 @@ class TransformerMADE(nn.Module):
         return self.decoder(self.transformer(h, mask=causal, is_causal=True))
 
 
+_BWD_SCRATCH_BYTES = 2 << 30   # per-row workspace of one backward chunk
+
+
+class _TransformerLogPsi(pt.autograd.Function):
+    """log psi of the transformer wave function with a hand-written backward (include/anqs_b200.h: anqs_transformer_backward)."""
+
+    @staticmethod
+    def forward(ctx, wf, idx, *params):
+        ctx.wf, ctx.idx = wf, idx
+        return wf.log_psi_kernel(idx, precision='fp64')
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        wf, idx = ctx.wf, ctx.idx
+        dev = idx.device
+        B = idx.shape[0]
+        g = grad_out.to(pt.complex128).contiguous()
+        names = [n for n, _ in wf.named_parameters()]
+        params = wf._params()
+        alloc = pt.zeros if B == 0 else pt.empty
+        grads = {n: alloc(p.shape, dtype=pt.float64, device=dev) for n, p in zip(names, params)}
+        desc = wf._descriptor()
+        gd = _lib.TransformerGrads()
+        pre = 'transformer_made.'
+        gd.tok_emb, gd.pos_emb = grads[pre + 'embedding.weight'].data_ptr(), grads[pre + 'pos_embedding.weight'].data_ptr()
+        gd.dec_w, gd.dec_b = grads[pre + 'decoder.weight'].data_ptr(), grads[pre + 'decoder.bias'].data_ptr()
+        for l in range(wf.config.depth):
+            lp = f'{pre}transformer.layers.{l}.'
+            for field, name in (('in_proj_w', 'self_attn.in_proj_weight'), ('in_proj_b', 'self_attn.in_proj_bias'),
+                                ('out_proj_w', 'self_attn.out_proj.weight'), ('out_proj_b', 'self_attn.out_proj.bias'),
+                                ('lin1_w', 'linear1.weight'), ('lin1_b', 'linear1.bias'), ('lin2_w', 'linear2.weight'),
+                                ('lin2_b', 'linear2.bias'), ('ln1_w', 'norm1.weight'), ('ln1_b', 'norm1.bias'),
+                                ('ln2_w', 'norm2.weight'), ('ln2_b', 'norm2.bias')):
+                getattr(gd, field)[l] = grads[lp + name].data_ptr()
+        lib, sp = _lib.lib(), _lib.stream_ptr(dev)
+        if B > 0:
+            per_sample = max(1, int(lib.anqs_transformer_backward_workspace(ctypes.byref(desc), ctypes.byref(gd), 1024)) // 1024)
+            chunk = max(1, min(B, _BWD_SCRATCH_BYTES // per_sample))
+            need = int(lib.anqs_transformer_backward_workspace(ctypes.byref(desc), ctypes.byref(gd), chunk))
+            if need < 0:
+                raise RuntimeError('anqs_transformer_backward_workspace: unsupported network shape')
+            work = wf._bwd_workspace(need)
+            for lo in range(0, B, chunk):
+                m = min(B, lo + chunk) - lo
+                _lib.check(lib.anqs_transformer_backward(ctypes.byref(desc), ctypes.byref(gd), _lib.dptr(idx[lo:lo + m]), m,
+                                                         _lib.dptr(pt.view_as_real(g[lo:lo + m])), _lib.dptr(work), work.numel() * 8,
+                                                         int(lo > 0), sp))
+        return (None, None) + tuple(grads[n] for n in names)
+
+
 class TransformerANQSConfig:
     def __init__(self, *args, dim: int = 64, depth: int = 2, head_num: int = 4, dtype=BASE_REAL_TYPE, **kwargs):
         self.dim, self.depth, self.head_num, self.dtype = dim, depth, head_num, dtype
@@ -91,6 +142,7 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         self._packed_tc = None           # parameters in the tensor cores' operand layout (k5_transformer_tc.cu)
         self._packed_key = None
         self.inference_precision = 'fp64'   # 'tf32': no-grad amplitudes and the samplers' conditionals run on tcgen05
+        self._bwd_work = None            # workspace of the backward kernel, kept between iterations
         self._init_sampler()
 
     qudit_num = property(lambda self: self.qubit_grouping.qudit_num)
@@ -138,6 +190,12 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
             _lib.check(_lib.lib().anqs_transformer_tc_pack(ctypes.byref(desc), _lib.dptr(self._packed_tc), _lib.stream_ptr(self.device)))
             self._packed_key = key
         return self._packed_tc
+
+    def _bwd_workspace(self, nbytes: int) -> pt.Tensor:
+        if self._bwd_work is None or self._bwd_work.numel() * 8 < nbytes:
+            self._bwd_work = None
+            self._bwd_work = pt.empty((nbytes + 7) // 8, dtype=pt.float64, device=self.device)
+        return self._bwd_work
 
     # ---- kernel plumbing ---------------------------------------------------------------------------------------------------
     def _descriptor(self) -> _lib.TransformerDesc:
@@ -214,8 +272,9 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
 
     # ---- reference-style surface -------------------------------------------------------------------------------------------------
     def log_psi_of_indices(self, base_idx: pt.Tensor) -> pt.Tensor:
-        if pt.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return self.log_psi_torch(base_idx)
+        if pt.is_grad_enabled() and any(p.requires_grad for p in self._params()):
+            _lib.require_cuda(self.device)
+            return _TransformerLogPsi.apply(self, base_idx.contiguous().view(-1), *self._params())
         return self.log_psi_kernel(base_idx)
 
     def log_psi(self, base_vec: pt.Tensor, just_return: bool = False) -> pt.Tensor:

@@ -70,21 +70,46 @@ def test_conditionals_match_reference_logits(name):
 
 
 @pytest.mark.parametrize('name', CASES)
-def test_kernel_matches_torch_path_and_gradients_flow(name):
+def test_kernel_matches_torch_path_and_backward_kernel_matches_autograd(name):
+    """Forward: k5_transformer.cu against the torch module.  Backward: k5_transformer_bwd.cu + k3_batch_reduce.cu (what
+    log_psi_of_indices differentiates through) against autograd through the torch module, every parameter, 1e-10 relative
+    to the largest gradient entry; per-sample weights on both log|psi| and arg psi so that no term cancels."""
+    import anqs_quantum_chemistry_b200.transformer_anqs as tfm
     g, masks, wf = case(name)
     n, ne = masks.n, masks.particle_num
-    x = _dev(synthetic.random_physical_samples(n, ne // 2, ne // 2, 200, seed=5).view(np.int64)).view(-1, 1)
+    B = 203
+    x = _dev(synthetic.random_physical_samples(n, ne // 2, ne // 2, B, seed=5).view(np.int64)).view(-1, 1)
+    gen = torch.Generator().manual_seed(11)
+    a, b = torch.randn(B, generator=gen, dtype=torch.float64).to(DEV), torch.randn(B, generator=gen, dtype=torch.float64).to(DEV)
     lp_k = wf.log_psi_kernel(x)
-    lp_t = wf.log_psi_of_indices(x)            # grad mode on -> torch module
-    assert lp_t.requires_grad
+    lp_t = wf.log_psi_torch(x)
     assert (lp_k - lp_t.detach()).abs().max() < 1e-10
     wf.zero_grad()
-    (lp_t.real.sum() + 0.3 * lp_t.imag.sum()).backward()
+    (a * lp_t.real + b * lp_t.imag).sum().backward()
+    ref = {k: p.grad.clone() for k, p in wf.named_parameters()}
+    for scratch in (8 * 2 ** 20, tfm._BWD_SCRATCH_BYTES):               # several chunks that accumulate; one chunk
+        old, tfm._BWD_SCRATCH_BYTES = tfm._BWD_SCRATCH_BYTES, scratch
+        try:
+            wf.zero_grad()
+            lp_c = wf.log_psi_of_indices(x)        # grad mode on -> _TransformerLogPsi
+            assert lp_c.requires_grad and torch.equal(lp_c.detach(), lp_k)
+            (a * lp_c.real + b * lp_c.imag).sum().backward()
+        finally:
+            tfm._BWD_SCRATCH_BYTES = old
+        for k, p in wf.named_parameters():
+            scale = float(ref[k].abs().max()) + 1e-300
+            assert float((p.grad - ref[k]).abs().max()) <= 1e-10 * max(scale, 1.0), (k, float((p.grad - ref[k]).abs().max()), scale)
     g2 = wf.cat_grad
     assert g2.shape[0] == wf.param_num and bool(torch.isfinite(g2).all()) and float(g2.abs().max()) > 0
+    # the same call (one chunk) twice gives the same bits (fixed-order reductions)
+    first = g2.clone()
+    wf.zero_grad()
+    lp_c = wf.log_psi_of_indices(x)
+    (a * lp_c.real + b * lp_c.imag).sum().backward()
+    assert torch.equal(wf.cat_grad, first)
     # tile boundaries: any batch size gives the same numbers
-    for b in (1, 2, 3, 4, 61):
-        assert torch.equal(wf.log_psi_kernel(x[:b]), lp_k[:b])
+    for bsz in (1, 2, 3, 4, 61):
+        assert torch.equal(wf.log_psi_kernel(x[:bsz]), lp_k[:bsz])
     assert wf.log_psi_kernel(x[:0]).shape[0] == 0
 
 
