@@ -69,8 +69,9 @@ _SIGNATURES = {
     'anqs_made_cond_log_abs_tc': (_c_int, [_vp, _vp, _c_int, _vp, _c_i64, _vp, _vp]),
     'anqs_transformer_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
     'anqs_transformer_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
-    'anqs_transformer_backward_workspace': (_c_i64, [_vp, _vp, _c_i64]),
-    'anqs_transformer_backward': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _vp]),
+    'anqs_transformer_backward_workspace': (_c_i64, [_vp, _c_i64]),
+    'anqs_transformer_log_psi_saving': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _c_i64, _vp]),
+    'anqs_transformer_backward': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp, _c_i64, _c_int, _c_int, _vp]),
     'anqs_transformer_tc_packed_bytes': (ctypes.c_size_t, [_vp]),
     'anqs_transformer_tc_pack': (_c_int, [_vp, _vp, _vp]),
     'anqs_transformer_log_psi_tc': (_c_int, [_vp, _vp, _vp, _c_i64, _vp, _vp]),

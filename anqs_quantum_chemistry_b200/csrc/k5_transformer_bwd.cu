@@ -34,16 +34,21 @@ struct TfBwdPtrs {   // per-row workspace of one chunk of samples (R = samples *
     int P;
 };
 
+// Tile <-> workspace rows.  A warp moves blocks of 4 rows x 8 columns: lane = (column 0..7) * 4 + (row 0..3), so that a
+// half-warp touches 16 different shared-memory bank pairs (stride MD_S = 68 doubles between columns: 4 * column + row) and
+// every 32-byte sector it touches in global memory is fully used.
 // dst[j][r] = src[(row0 + r) * 64 + j], zero beyond `rows`
 __device__ __forceinline__ void load_rows(double *dst, const double *__restrict__ src, int64_t row0, int rows) {
-    for (int e = threadIdx.x; e < 64 * 64; e += MD_THREADS) {
-        const int r = e >> 6, j = e & 63;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, rl = lane & 3, jl = lane >> 2;
+    for (int b = warp; b < 128; b += MD_THREADS / 32) {
+        const int r = (b >> 3) * 4 + rl, j = (b & 7) * 8 + jl;
         dst[j * MD_S + r] = r < rows ? src[(row0 + r) * 64 + j] : 0.0;
     }
 }
 __device__ __forceinline__ void store_rows(const double *src, double *__restrict__ dst, int64_t row0, int rows, int ld = 64, int col0 = 0) {
-    for (int e = threadIdx.x; e < 64 * 64; e += MD_THREADS) {
-        const int r = e >> 6, j = e & 63;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, rl = lane & 3, jl = lane >> 2;
+    for (int b = warp; b < 128; b += MD_THREADS / 32) {
+        const int r = (b >> 3) * 4 + rl, j = (b & 7) * 8 + jl;
         if (r < rows) dst[(row0 + r) * ld + col0 + j] = src[j * MD_S + r];
     }
 }
@@ -149,15 +154,19 @@ __device__ __forceinline__ void store_acc(double *out, const double (&acc)[4][4]
     for (int jj = 0; jj < 4; ++jj) {
         const int j = tx + 16 * jj;
         const double b = bias ? __ldg(bias + j) : 0.0;
-#pragma unroll
-        for (int ss = 0; ss < 4; ++ss) out[j * MD_S + ty * 4 + ss] = acc[ss][jj] + b;
+        double2 *o2 = reinterpret_cast<double2 *>(out + j * MD_S + ty * 4);
+        o2[0] = make_double2(acc[0][jj] + b, acc[1][jj] + b);
+        o2[1] = make_double2(acc[2][jj] + b, acc[3][jj] + b);
     }
 }
 
-template <int HD>
+// PHASE 0: forward pass that keeps the activations in the workspace and writes log psi (what autograd's forward runs);
+// PHASE 1: backward pass from a workspace PHASE 0 filled for the same samples; PHASE 2: both in one launch per chunk of
+// samples (the forward pass recomputed - for batches whose activations exceed the caller's workspace).
+template <int HD, int PHASE>
 __global__ void __launch_bounds__(MD_THREADS, 1)
 transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__restrict__ idx_in, int64_t B, const double2 *__restrict__ grad_out,
-                            TfBwdPtrs ws) {
+                            double2 *__restrict__ log_psi, TfBwdPtrs ws) {
     extern __shared__ __align__(16) unsigned char tb_smem[];
     double *buf[5];
     buf[0] = reinterpret_cast<double *>(tb_smem);
@@ -186,6 +195,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
         if (tid < S) s_idx[tid] = base + tid < B ? (uint64_t)idx_in[base + tid] : 0ull;
         __syncthreads();
         // =========================== forward pass of the tile, keeping what the backward needs ===========================
+        if (PHASE != 1) {
         for (int e = tid; e < 64 * 64; e += MD_THREADS) {
             const int k = e >> 6, r = e & 63;
             double v = 0.0;
@@ -214,7 +224,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             store_rows(Vb, ws.v[l], row0, live);
             __syncthreads();
             for (int pair = tid; pair < rows * H; pair += MD_THREADS) {   // causal attention; the output overwrites the query slice
-                const int r = pair / H, h = pair - r * H;
+                const int h = pair / rows, r = pair - h * rows;            // lanes run over rows: K / V reads of a sample broadcast
                 const int s = r / T, t = r - s * T, r0 = s * T;
                 double q[HD], o[HD];
                 _Pragma("unroll") for (int d = 0; d < hd; ++d) q[d] = Qb[(h * hd + d) * MD_S + r] * scale;
@@ -256,8 +266,9 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = tx + 16 * jj;
                     const double b = P.lin1_b[l] ? __ldg(P.lin1_b[l] + j) : 0.0;
-#pragma unroll
-                    for (int ss = 0; ss < 4; ++ss) Kb[j * MD_S + ty * 4 + ss] = fmax(acc[ss][jj] + b, 0.0);
+                    double2 *o2 = reinterpret_cast<double2 *>(Kb + j * MD_S + ty * 4);
+                    o2[0] = make_double2(fmax(acc[0][jj] + b, 0.0), fmax(acc[1][jj] + b, 0.0));
+                    o2[1] = make_double2(fmax(acc[2][jj] + b, 0.0), fmax(acc[3][jj] + b, 0.0));
                 }
             }
             __syncthreads();
@@ -280,29 +291,64 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             s_dec[r * 4 + c] = acc;
         }
         __syncthreads();
-        // =========================== gradient of log psi with respect to the decoder outputs ===============================
-        // per position: re = z_bit - L, L = 0.5 logsumexp(2 z) over the allowed outcomes; im = the chosen outcome's phase
-        if (tid < S) {
-            const bool real_sample = base + tid < B;
-            const uint64_t x = s_idx[tid];
-            const double2 g = real_sample ? grad_out[base + tid] : make_double2(0.0, 0.0);
-            for (int t = 0; t < T; ++t) {
-                double *o = s_dec + (tid * T + t) * 4;  // (re0, im0, re1, im1) -> their gradients
+        if (PHASE == 0) {   // log psi: one thread per position, then one per sample adds the positions up in order
+            for (int e = tid; e < live * 4; e += MD_THREADS) ws.gdec[row0 * 4 + e] = s_dec[e];   // PHASE 1 starts from these
+            if (tid < rows) {
+                const int sm = tid / T, t = tid - sm * T;
+                const uint64_t x = s_idx[sm];
+                const double *o = s_dec + tid * 4;  // (re0, im0, re1, im1)
                 const uint64_t prefix = t == 0 ? 0ull : (x & ((1ull << t) - 1ull));
                 const long long mi = memo_index_of(P.sym_num, P.sym, prefix);
                 const uint64_t mw = (mi >= 0 && mi < P.memo_size) ? __ldg(P.cont_mask + (size_t)t * P.memo_size + mi) : 0ull;
                 const bool a0 = mw & 1ull, a1 = (mw >> 1) & 1ull;
                 const double z0 = a0 ? o[0] : -INFINITY, z1 = a1 ? o[2] : -INFINITY;
                 const double mx = fmax(z0, z1);
-                const double e0 = a0 ? exp(2.0 * (z0 - mx)) : 0.0, e1 = a1 ? exp(2.0 * (z1 - mx)) : 0.0;
-                const double p0 = (a0 || a1) ? e0 / (e0 + e1) : 0.0, p1 = (a0 || a1) ? e1 / (e0 + e1) : 0.0;
+                const double Ln = mx + 0.5 * log((a0 ? exp(2.0 * (z0 - mx)) : 0.0) + (a1 ? exp(2.0 * (z1 - mx)) : 0.0));
                 const int bit = (int)((x >> t) & 1ull);
-                const bool chosen_ok = bit ? a1 : a0;
-                o[0] = a0 ? g.x * (((bit == 0 && chosen_ok) ? 1.0 : 0.0) - p0) : 0.0;
-                o[2] = a1 ? g.x * (((bit == 1 && chosen_ok) ? 1.0 : 0.0) - p1) : 0.0;
-                o[1] = bit == 0 ? g.y : 0.0;
-                o[3] = bit == 1 ? g.y : 0.0;
+                const bool ok = bit ? a1 : a0;
+                st_mx[tid] = ok ? (bit ? z1 : z0) - Ln : 0.0;
+                st_den[tid] = ok ? (bit ? o[3] : o[1]) : 0.0;
+                st_d[tid] = ok ? 0.0 : 1.0;
             }
+            __syncthreads();
+            if (tid < S && base + tid < B) {
+                double re = 0.0, im = 0.0;
+                bool dead = false;
+                for (int t = 0; t < T; ++t) {
+                    re += st_mx[tid * T + t];
+                    im += st_den[tid * T + t];
+                    dead |= st_d[tid * T + t] != 0.0;
+                }
+                log_psi[base + tid] = dead ? make_double2(-INFINITY, 0.0) : make_double2(re, im);
+            }
+        }
+        }   // PHASE != 1
+        if (PHASE == 0) continue;
+        // =========================== gradient of log psi with respect to the decoder outputs ===============================
+        // per position: re = z_bit - L, L = 0.5 logsumexp(2 z) over the allowed outcomes; im = the chosen outcome's phase
+        if (PHASE == 1) {
+            for (int e = tid; e < 64 * 4; e += MD_THREADS) s_dec[e] = e < live * 4 ? ws.gdec[row0 * 4 + e] : 0.0;
+            __syncthreads();
+        }
+        if (tid < rows) {
+            const int sm = tid / T, t = tid - sm * T;
+            const uint64_t x = s_idx[sm];
+            const double2 g = base + sm < B ? grad_out[base + sm] : make_double2(0.0, 0.0);
+            double *o = s_dec + tid * 4;  // (re0, im0, re1, im1) -> their gradients
+            const uint64_t prefix = t == 0 ? 0ull : (x & ((1ull << t) - 1ull));
+            const long long mi = memo_index_of(P.sym_num, P.sym, prefix);
+            const uint64_t mw = (mi >= 0 && mi < P.memo_size) ? __ldg(P.cont_mask + (size_t)t * P.memo_size + mi) : 0ull;
+            const bool a0 = mw & 1ull, a1 = (mw >> 1) & 1ull;
+            const double z0 = a0 ? o[0] : -INFINITY, z1 = a1 ? o[2] : -INFINITY;
+            const double mx = fmax(z0, z1);
+            const double e0 = a0 ? exp(2.0 * (z0 - mx)) : 0.0, e1 = a1 ? exp(2.0 * (z1 - mx)) : 0.0;
+            const double p0 = (a0 || a1) ? e0 / (e0 + e1) : 0.0, p1 = (a0 || a1) ? e1 / (e0 + e1) : 0.0;
+            const int bit = (int)((x >> t) & 1ull);
+            const bool chosen_ok = bit ? a1 : a0;
+            o[0] = a0 ? g.x * (((bit == 0 && chosen_ok) ? 1.0 : 0.0) - p0) : 0.0;
+            o[2] = a1 ? g.x * (((bit == 1 && chosen_ok) ? 1.0 : 0.0) - p1) : 0.0;
+            o[1] = bit == 0 ? g.y : 0.0;
+            o[3] = bit == 1 ? g.y : 0.0;
         }
         __syncthreads();
         for (int e = tid; e < live * 4; e += MD_THREADS) ws.gdec[row0 * 4 + e] = s_dec[e];
@@ -332,11 +378,12 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
                 gemm_tile(G, W, TB_D, tx, ty, acc);               // dHf = dy2 * W2
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int ss = 0; ss < 4; ++ss) {
-                        const int a = (tx + 16 * jj) * MD_S + ty * 4 + ss;
-                        B1[a] = B2[a] > 0.0 ? acc[ss][jj] : 0.0;  // through the ReLU
-                    }
+                {
+                    const int a = (tx + 16 * jj) * MD_S + ty * 4;
+                    const double2 h01 = *reinterpret_cast<const double2 *>(B2 + a), h23 = *reinterpret_cast<const double2 *>(B2 + a + 2);
+                    *reinterpret_cast<double2 *>(B1 + a) = make_double2(h01.x > 0.0 ? acc[0][jj] : 0.0, h01.y > 0.0 ? acc[1][jj] : 0.0);   // ReLU
+                    *reinterpret_cast<double2 *>(B1 + a + 2) = make_double2(h23.x > 0.0 ? acc[2][jj] : 0.0, h23.y > 0.0 ? acc[3][jj] : 0.0);
+                }
             }
             __syncthreads();
             store_rows(B1, ws.ghp[l], row0, live);
@@ -346,9 +393,12 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
                 double acc[4][4];
                 gemm_tile(B1, W, TB_D, tx, ty, acc);              // dX1 = dy2 (residual) + dHpre * W1
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int ss = 0; ss < 4; ++ss) G[(tx + 16 * jj) * MD_S + ty * 4 + ss] += acc[ss][jj];
+                for (int jj = 0; jj < 4; ++jj) {
+                    double2 *g2 = reinterpret_cast<double2 *>(G + (tx + 16 * jj) * MD_S + ty * 4);
+                    const double2 u = g2[0], v = g2[1];
+                    g2[0] = make_double2(u.x + acc[0][jj], u.y + acc[1][jj]);
+                    g2[1] = make_double2(v.x + acc[2][jj], v.y + acc[3][jj]);
+                }
             }
             __syncthreads();
             // ---- LayerNorm 1 ------------------------------------------------------------------------------------------------
@@ -370,8 +420,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             load_rows(B2, ws.k[l], row0, live);
             load_rows(G, ws.v[l], row0, live);
             __syncthreads();
-            for (int pair = tid; pair < rows * H; pair += MD_THREADS) {   // pass 1, per (query row, head): statistics and dQ
-                const int r = pair / H, h = pair - r * H;
+            for (int pair = tid; pair < rows * H; pair += MD_THREADS) {   // pass 1, per (head, query row): statistics and dQ
+                const int h = pair / rows, r = pair - h * rows;
                 const int s = r / T, t = r - s * T, r0 = s * T;
                 double q[HD], da[HD], dq[HD];
                 _Pragma("unroll") for (int d = 0; d < hd; ++d) {
@@ -415,8 +465,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             for (int e = tid; e < 64 * 64; e += MD_THREADS)
                 if ((e & 63) >= rows) W[(e >> 6) * MD_S + (e & 63)] = 0.0;
             __syncthreads();
-            for (int pair = tid; pair < rows * H; pair += MD_THREADS) {   // pass 2, per (key row, head): dK, dV in place of K, V
-                const int rk = pair / H, h = pair - rk * H;
+            for (int pair = tid; pair < rows * H; pair += MD_THREADS) {   // pass 2, per (head, key row): dK, dV in place of K, V
+                const int h = pair / rows, rk = pair - h * rows;
                 const int s = rk / T, tp = rk - s * T, r0 = s * T;
                 double kk[HD], vv[HD], dk[HD], dv[HD];
                 _Pragma("unroll") for (int d = 0; d < hd; ++d) {
@@ -424,8 +474,9 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
                     vv[d] = G[(h * hd + d) * MD_S + rk];
                     dk[d] = dv[d] = 0.0;
                 }
-                for (int t = tp; t < T; ++t) {
-                    const int r = r0 + t, pr = r * H + h;
+                for (int t = 0; t < T; ++t) {   // every lane walks the same query rows (broadcast reads); causal: t >= tp only
+                    if (t < tp) continue;
+                    const int r = r0 + t, pr = h * rows + r;
                     double sc = 0.0, dp = 0.0;
                     _Pragma("unroll") for (int d = 0; d < hd; ++d) {
                         sc += B1[(h * hd + d) * MD_S + r] * kk[d];
@@ -467,9 +518,12 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
                     for (int b = 0; b < 4; ++b) tot[a][b] += acc[a][b];
             }
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                for (int ss = 0; ss < 4; ++ss) B1[(tx + 16 * jj) * MD_S + ty * 4 + ss] += tot[ss][jj];
+            for (int jj = 0; jj < 4; ++jj) {
+                double2 *g2 = reinterpret_cast<double2 *>(B1 + (tx + 16 * jj) * MD_S + ty * 4);
+                const double2 u = g2[0], v = g2[1];
+                g2[0] = make_double2(u.x + tot[0][jj], u.y + tot[1][jj]);
+                g2[1] = make_double2(v.x + tot[2][jj], v.y + tot[3][jj]);
+            }
             // the running gradient now lives in B1
             double *tmp = G;
             G = B1;
@@ -486,7 +540,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
         }
     }
     __syncthreads();
-    for (int e = tid; e < TB_NVEC * 64; e += MD_THREADS) ws.vec[(size_t)blockIdx.x * TB_NVEC * 64 + e] = vecs[e];
+    if (PHASE != 0)
+        for (int e = tid; e < TB_NVEC * 64; e += MD_THREADS) ws.vec[(size_t)blockIdx.x * TB_NVEC * 64 + e] = vecs[e];
 }
 
 // LayerNorm weight / bias gradients: sum of the per-CTA partial sums, in CTA order
@@ -526,6 +581,7 @@ static int tb_layout(const anqs_transformer_desc_t *desc, const anqs_transformer
     ws.emb = take(P);
     ws.vec = p;
     ws.P = P;
+    if (!g || !problems) return 0;
     int np = 0;
     auto add = [&](const double *A, int lda, int M, const double *B, double *C, double *colsum) {
         anqs_brg_problem_t q;
@@ -549,64 +605,94 @@ static int tb_layout(const anqs_transformer_desc_t *desc, const anqs_transformer
 
 using namespace anqs;
 
-static int tb_check(const anqs_transformer_desc_t *desc, const anqs_transformer_grads_t *g) {
-    ANQS_REQUIRE(desc && g, "null descriptor");
+static int tb_check_desc(const anqs_transformer_desc_t *desc) {
+    ANQS_REQUIRE(desc, "null descriptor");
     ANQS_REQUIRE(desc->dim == TB_D && desc->depth >= 1 && desc->depth <= 4, "model dimension must be 64, depth 1..4");
     ANQS_REQUIRE(desc->head_num == 1 || desc->head_num == 2 || desc->head_num == 4 || desc->head_num == 8 || desc->head_num == 16,
                  "head_num must be 1, 2, 4, 8 or 16");
     ANQS_REQUIRE(desc->qubit_num >= 1 && desc->qubit_num <= 64, "qubit_num must be in [1, 64]");
+    return 0;
+}
+static int tb_check(const anqs_transformer_desc_t *desc, const anqs_transformer_grads_t *g) {
+    if (int rc = tb_check_desc(desc)) return rc;
+    ANQS_REQUIRE(g, "null gradient descriptor");
     ANQS_REQUIRE(g->tok_emb && g->pos_emb && g->dec_w && g->dec_b, "null embedding / decoder gradient pointer");
     for (int l = 0; l < desc->depth; ++l)
         ANQS_REQUIRE(g->in_proj_w[l] && g->out_proj_w[l] && g->lin1_w[l] && g->lin2_w[l] && g->ln1_w[l] && g->ln1_b[l] && g->ln2_w[l] && g->ln2_b[l],
                      "null weight gradient pointer");
     return 0;
 }
+static int64_t tb_own_bytes(const anqs_transformer_desc_t *desc, int64_t n) {
+    return (n * desc->qubit_num * tb_row_doubles(desc) + (int64_t)sm_count_of_current_device() * TB_NVEC * 64) * 8;
+}
+
+template <int PHASE>
+static int tb_launch(const anqs_transformer_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out, double *d_log_psi,
+                     const TfBwdPtrs &ws, cudaStream_t s) {
+    const int T = desc->qubit_num;
+    const int grid = (int)std::min<int64_t>((n + (64 / T) - 1) / (64 / T), (int64_t)sm_count_of_current_device());
+    auto launch = [&](auto kern) -> int {
+        ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM));
+        kern<<<grid, MD_THREADS, TB_SMEM, s>>>(*desc, d_idx, n, (const double2 *)d_grad_out, (double2 *)d_log_psi, ws);
+        ANQS_LAUNCH_CHECK();
+        return 0;
+    };
+    switch (desc->head_num) {
+        case 1: return launch(transformer_backward_kernel<64, PHASE>);
+        case 2: return launch(transformer_backward_kernel<32, PHASE>);
+        case 4: return launch(transformer_backward_kernel<16, PHASE>);
+        case 8: return launch(transformer_backward_kernel<8, PHASE>);
+        default: return launch(transformer_backward_kernel<4, PHASE>);
+    }
+}
 
 extern "C" {
 
-int64_t anqs_transformer_backward_workspace(const anqs_transformer_desc_t *desc, const anqs_transformer_grads_t *grads, int64_t n) {
-    if (!desc || !grads || n <= 0 || tb_check(desc, grads)) return -1;
+int64_t anqs_transformer_backward_workspace(const anqs_transformer_desc_t *desc, int64_t n) {
+    if (!desc || n <= 0 || tb_check_desc(desc)) return -1;
+    static double dummy[1];
+    anqs_transformer_grads_t g;
+    g.tok_emb = g.pos_emb = g.dec_w = g.dec_b = dummy;
+    for (int l = 0; l < 4; ++l)
+        g.in_proj_w[l] = g.in_proj_b[l] = g.out_proj_w[l] = g.out_proj_b[l] = g.lin1_w[l] = g.lin1_b[l] = g.lin2_w[l] = g.lin2_b[l] = g.ln1_w[l] =
+            g.ln1_b[l] = g.ln2_w[l] = g.ln2_b[l] = dummy;
     TfBwdPtrs ws;
     anqs_brg_problem_t problems[4 * 4 + 3];
-    static double dummy[1];
-    const int np = tb_layout(desc, grads, dummy, n, ws, problems);   // addresses are not dereferenced here
+    const int np = tb_layout(desc, &g, dummy, n, ws, problems);   // addresses are not dereferenced here
     const int64_t brg = anqs_batch_reduce_workspace(problems, np, n * desc->qubit_num);
     if (brg < 0) return -1;
-    const int64_t own = (n * desc->qubit_num * tb_row_doubles(desc) + (int64_t)sm_count_of_current_device() * TB_NVEC * 64) * 8;
-    return own + 256 + brg;
+    return tb_own_bytes(desc, n) + 256 + brg;
+}
+
+int anqs_transformer_log_psi_saving(const anqs_transformer_desc_t *desc, const int64_t *d_idx, int64_t n, double *d_log_psi, void *d_work,
+                                    int64_t work_bytes, void *stream) {
+    if (int rc = tb_check_desc(desc)) return rc;
+    ANQS_REQUIRE(n >= 0, "negative sample count");
+    if (n == 0) return 0;
+    ANQS_REQUIRE(d_idx && d_log_psi && d_work, "null pointer");
+    ANQS_REQUIRE(work_bytes >= anqs_transformer_backward_workspace(desc, n), "workspace too small");
+    TfBwdPtrs ws;
+    tb_layout(desc, nullptr, (double *)d_work, n, ws, nullptr);
+    return tb_launch<0>(desc, d_idx, n, nullptr, d_log_psi, ws, (cudaStream_t)stream);
 }
 
 int anqs_transformer_backward(const anqs_transformer_desc_t *desc, const anqs_transformer_grads_t *grads, const int64_t *d_idx, int64_t n,
-                              const double *d_grad_out, void *d_work, int64_t work_bytes, int accumulate, void *stream) {
+                              const double *d_grad_out, void *d_work, int64_t work_bytes, int saved, int accumulate, void *stream) {
     if (int rc = tb_check(desc, grads)) return rc;
     ANQS_REQUIRE(n >= 0, "negative sample count");
     if (n == 0) return 0;
     ANQS_REQUIRE(d_idx && d_grad_out && d_work, "null pointer");
-    ANQS_REQUIRE(work_bytes >= anqs_transformer_backward_workspace(desc, grads, n), "workspace too small");
+    ANQS_REQUIRE(work_bytes >= anqs_transformer_backward_workspace(desc, n), "workspace too small");
     const int T = desc->qubit_num;
     const int grid = (int)std::min<int64_t>((n + (64 / T) - 1) / (64 / T), (int64_t)sm_count_of_current_device());
     TfBwdPtrs ws;
     anqs_brg_problem_t problems[4 * 4 + 3];
     const int np = tb_layout(desc, grads, (double *)d_work, n, ws, problems);
-    const int64_t own = (n * T * tb_row_doubles(desc) + (int64_t)sm_count_of_current_device() * TB_NVEC * 64) * 8;
+    const int64_t own = tb_own_bytes(desc, n);
     char *brg_ws = (char *)d_work + ((own + 255) / 256) * 256;
     const int64_t brg_bytes = work_bytes - (brg_ws - (char *)d_work);
     cudaStream_t s = (cudaStream_t)stream;
-    auto launch = [&](auto kern) -> int {
-        ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM));
-        kern<<<grid, MD_THREADS, TB_SMEM, s>>>(*desc, d_idx, n, (const double2 *)d_grad_out, ws);
-        ANQS_LAUNCH_CHECK();
-        return 0;
-    };
-    int rc = 0;
-    switch (desc->head_num) {
-        case 1: rc = launch(transformer_backward_kernel<64>); break;
-        case 2: rc = launch(transformer_backward_kernel<32>); break;
-        case 4: rc = launch(transformer_backward_kernel<16>); break;
-        case 8: rc = launch(transformer_backward_kernel<8>); break;
-        default: rc = launch(transformer_backward_kernel<4>); break;
-    }
-    if (rc) return rc;
+    if (int rc = saved ? tb_launch<1>(desc, d_idx, n, d_grad_out, nullptr, ws, s) : tb_launch<2>(desc, d_idx, n, d_grad_out, nullptr, ws, s)) return rc;
     transformer_vec_finish_kernel<<<(desc->depth * 4 * 64 + 255) / 256, 256, 0, s>>>(ws.vec, grid, accumulate, desc->depth, *grads);
     ANQS_LAUNCH_CHECK();
     if (!accumulate)   // the last positional row (position qubit_num) never enters the network

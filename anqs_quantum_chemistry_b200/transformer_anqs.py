@@ -67,15 +67,32 @@ class TransformerMADE(nn.Module):
         return self.decoder(self.transformer(h, mask=causal, is_causal=True))
 
 
-_BWD_SCRATCH_BYTES = 2 << 30   # per-row workspace of one backward chunk
+_BWD_SCRATCH_BYTES = 8 << 30   # workspace of the backward pass (activations + per-row gradient signals, ~18 kB per token)
 
 
 class _TransformerLogPsi(pt.autograd.Function):
-    """log psi of the transformer wave function with a hand-written backward (include/anqs_b200.h: anqs_transformer_backward)."""
+    """log psi of the transformer wave function with a hand-written backward (include/anqs_b200.h: anqs_transformer_backward).
+    When the activations of the whole batch fit the workspace the forward pass keeps them (anqs_transformer_log_psi_saving)
+    and the backward pass starts from them; otherwise the forward pass is the inference kernel and the backward pass walks
+    the batch in chunks, recomputing the activations of each."""
 
     @staticmethod
     def forward(ctx, wf, idx, *params):
         ctx.wf, ctx.idx = wf, idx
+        dev, B = idx.device, idx.shape[0]
+        lib, desc = _lib.lib(), wf._descriptor()
+        need = int(lib.anqs_transformer_backward_workspace(ctypes.byref(desc), B)) if B > 0 else 0
+        if need < 0:
+            raise RuntimeError('anqs_transformer_backward_workspace: unsupported network shape')
+        ctx.saved_in = None
+        if 0 < need <= _BWD_SCRATCH_BYTES:
+            work = wf._bwd_workspace(need)
+            out = pt.empty(B, dtype=pt.complex128, device=dev)
+            _lib.check(lib.anqs_transformer_log_psi_saving(ctypes.byref(desc), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(out)),
+                                                           _lib.dptr(work), work.numel() * 8, _lib.stream_ptr(dev)))
+            wf._bwd_token += 1
+            ctx.saved_in = (work, wf._bwd_token)
+            return out
         return wf.log_psi_kernel(idx, precision='fp64')
 
     @staticmethod
@@ -103,17 +120,21 @@ class _TransformerLogPsi(pt.autograd.Function):
                 getattr(gd, field)[l] = grads[lp + name].data_ptr()
         lib, sp = _lib.lib(), _lib.stream_ptr(dev)
         if B > 0:
-            per_sample = max(1, int(lib.anqs_transformer_backward_workspace(ctypes.byref(desc), ctypes.byref(gd), 1024)) // 1024)
-            chunk = max(1, min(B, _BWD_SCRATCH_BYTES // per_sample))
-            need = int(lib.anqs_transformer_backward_workspace(ctypes.byref(desc), ctypes.byref(gd), chunk))
-            if need < 0:
-                raise RuntimeError('anqs_transformer_backward_workspace: unsupported network shape')
-            work = wf._bwd_workspace(need)
-            for lo in range(0, B, chunk):
-                m = min(B, lo + chunk) - lo
-                _lib.check(lib.anqs_transformer_backward(ctypes.byref(desc), ctypes.byref(gd), _lib.dptr(idx[lo:lo + m]), m,
-                                                         _lib.dptr(pt.view_as_real(g[lo:lo + m])), _lib.dptr(work), work.numel() * 8,
-                                                         int(lo > 0), sp))
+            saved = ctx.saved_in is not None and ctx.saved_in[1] == wf._bwd_token and ctx.saved_in[0] is wf._bwd_work
+            if saved:   # the workspace still holds this call's activations (no other forward with gradients ran since)
+                work = ctx.saved_in[0]
+                _lib.check(lib.anqs_transformer_backward(ctypes.byref(desc), ctypes.byref(gd), _lib.dptr(idx), B, _lib.dptr(pt.view_as_real(g)),
+                                                         _lib.dptr(work), work.numel() * 8, 1, 0, sp))
+            else:
+                per_sample = max(1, int(lib.anqs_transformer_backward_workspace(ctypes.byref(desc), 1024)) // 1024)
+                chunk = max(1, min(B, _BWD_SCRATCH_BYTES // per_sample))
+                wf._bwd_token += 1   # the workspace is about to be overwritten
+                work = wf._bwd_workspace(int(lib.anqs_transformer_backward_workspace(ctypes.byref(desc), chunk)))
+                for lo in range(0, B, chunk):
+                    m = min(B, lo + chunk) - lo
+                    _lib.check(lib.anqs_transformer_backward(ctypes.byref(desc), ctypes.byref(gd), _lib.dptr(idx[lo:lo + m]), m,
+                                                             _lib.dptr(pt.view_as_real(g[lo:lo + m])), _lib.dptr(work), work.numel() * 8,
+                                                             0, int(lo > 0), sp))
         return (None, None) + tuple(grads[n] for n in names)
 
 
@@ -143,6 +164,7 @@ class TransformerANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         self._packed_key = None
         self.inference_precision = 'fp64'   # 'tf32': no-grad amplitudes and the samplers' conditionals run on tcgen05
         self._bwd_work = None            # workspace of the backward kernel, kept between iterations
+        self._bwd_token = 0              # which forward call's activations the workspace holds
         self._init_sampler()
 
     qudit_num = property(lambda self: self.qubit_grouping.qudit_num)

@@ -331,10 +331,14 @@ int anqs_transformer_cond_log_abs(const anqs_transformer_desc_t *desc, int qubit
  * TransformerMADE (legacy/anqs_primitives/made/transformer_made.py:9-48) and the masked normalisation (ANQS:392-405).
  * `grads` mirrors the descriptor's parameter pointers with the destinations of the gradients (same shapes; bias pointers
  * may be null).  d_grad_out[n] complex128 = dLoss/d(log|psi|), dLoss/d(arg psi) per sample, i.e. the gradient is
- * sum_i  grad_out[i].re * d log|psi_i| / d theta + grad_out[i].im * d arg psi_i / d theta.  The forward pass is recomputed
- * (nothing has to be saved by anqs_transformer_log_psi).  accumulate != 0 adds to the destinations - the way a caller
- * walks a large batch in chunks of n samples with one workspace of anqs_transformer_backward_workspace(desc, grads, n) bytes
- * (256-byte aligned).  All sums over the batch run in a fixed order: results are reproducible bit for bit. */
+ * sum_i  grad_out[i].re * d log|psi_i| / d theta + grad_out[i].im * d arg psi_i / d theta.
+ * Two ways to call it, with a workspace of anqs_transformer_backward_workspace(desc, n) bytes (256-byte aligned):
+ *   saved != 0: anqs_transformer_log_psi_saving(desc, d_idx, n, d_log_psi, d_work, ...) ran before on the same samples and
+ *               the same workspace (it computes the same d_log_psi as anqs_transformer_log_psi, bit for bit, and leaves
+ *               the activations in d_work); the backward pass starts from them;
+ *   saved == 0: the forward pass is recomputed inside; with accumulate != 0 (adds to the destinations) this is how a
+ *               caller walks a batch too large for one workspace in chunks of n samples.
+ * All sums over the batch run in a fixed order: results are reproducible bit for bit. */
 typedef struct {
     double *tok_emb, *pos_emb;
     double *in_proj_w[4], *in_proj_b[4], *out_proj_w[4], *out_proj_b[4];
@@ -342,9 +346,11 @@ typedef struct {
     double *ln1_w[4], *ln1_b[4], *ln2_w[4], *ln2_b[4];
     double *dec_w, *dec_b;
 } anqs_transformer_grads_t;
-int64_t anqs_transformer_backward_workspace(const anqs_transformer_desc_t *desc, const anqs_transformer_grads_t *grads, int64_t n);
+int64_t anqs_transformer_backward_workspace(const anqs_transformer_desc_t *desc, int64_t n);
+int anqs_transformer_log_psi_saving(const anqs_transformer_desc_t *desc, const int64_t *d_idx, int64_t n, double *d_log_psi, void *d_work,
+                                    int64_t work_bytes, void *stream);
 int anqs_transformer_backward(const anqs_transformer_desc_t *desc, const anqs_transformer_grads_t *grads, const int64_t *d_idx, int64_t n,
-                              const double *d_grad_out, void *d_work, int64_t work_bytes, int accumulate, void *stream);
+                              const double *d_grad_out, void *d_work, int64_t work_bytes, int saved, int accumulate, void *stream);
 
 /* Tensor-core mode of the two functions above: every projection on tcgen05 (kind::tf32, fp32 accumulation in TMEM), attention,
  * LayerNorm and the masked normalisation in fp32.  Inference only; agreement with the fp64 entry points is a stated

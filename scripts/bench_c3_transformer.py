@@ -55,5 +55,24 @@ def one_iter():
     energies.append(float(est.mean.real))
 _, t = wall(one_iter, reps=20, warm=3)
 out['vmc_iteration'] = {'ms_per_iter': t * 1e3, 'iters_per_s': 1 / t, 'n_unq': 10 ** 4, 'energy_first': energies[0], 'energy_last': energies[-1],
-                        'note': 'sampler on the tcgen05 conditionals, E_loc on the fused kernel; the forward with gradients runs through the mirrored torch module (library autograd)'}
+                        'note': 'sampler on the tcgen05 conditionals, E_loc on the fused kernel, gradient through k5_transformer_bwd.cu + k3_batch_reduce.cu'}
+# where the time of an iteration goes
+def timed(fn, reps=10):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(reps): r = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+res, _, _, _ = sample(wf=wf, config=cfg_s)
+indices, perm = wf.sort_base_idx(res.indices)
+parts = {'sample_ms': timed(lambda: sample(wf=wf, config=cfg_s)), 'sort_ms': timed(lambda: wf.sort_base_idx(res.indices))}
+def fwd_bwd():
+    opt.zero_grad()
+    a = wf.amplitude(indices)
+    (a.log_psi.real.sum()).backward()
+parts['amplitude_forward_backward_ms'] = timed(fwd_bwd)
+with torch.no_grad():
+    amps = wf.amplitude(indices)
+parts['local_energy_ms'] = timed(lambda: compute_local_energies(wf=wf, sampling_result=SamplingResult(indices=indices, counts=res.counts[perm]),
+                                                                sampled_amps=amps, ham=ham, config=cfg_e, sample_aware=True))
+out['vmc_iteration']['parts'] = parts
 print(json.dumps(out))

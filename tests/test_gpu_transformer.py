@@ -107,10 +107,27 @@ def test_kernel_matches_torch_path_and_backward_kernel_matches_autograd(name):
     lp_c = wf.log_psi_of_indices(x)
     (a * lp_c.real + b * lp_c.imag).sum().backward()
     assert torch.equal(wf.cat_grad, first)
+    # two forward calls before the first backward: the first one's activations are gone, its backward recomputes them
+    wf.zero_grad()
+    lp_1 = wf.log_psi_of_indices(x)
+    lp_2 = wf.log_psi_of_indices(x[:50])
+    (a * lp_1.real + b * lp_1.imag).sum().backward()
+    for k, p in wf.named_parameters():
+        scale = max(float(ref[k].abs().max()), 1.0)
+        assert float((p.grad - ref[k]).abs().max()) <= 1e-10 * scale, k
+    wf.zero_grad()
+    (a[:50] * lp_2.real + b[:50] * lp_2.imag).sum().backward()     # this one still owns the workspace
+    lp_t = wf.log_psi_torch(x[:50])
+    g_own = wf.cat_grad.clone()
+    wf.zero_grad()
+    (a[:50] * lp_t.real + b[:50] * lp_t.imag).sum().backward()
+    assert float((g_own - wf.cat_grad).abs().max()) <= 1e-10 * max(float(g_own.abs().max()), 1.0)
     # tile boundaries: any batch size gives the same numbers
     for bsz in (1, 2, 3, 4, 61):
         assert torch.equal(wf.log_psi_kernel(x[:bsz]), lp_k[:bsz])
+        assert torch.equal(wf.log_psi_of_indices(x[:bsz]).detach(), lp_k[:bsz])
     assert wf.log_psi_kernel(x[:0]).shape[0] == 0
+    assert wf.log_psi_of_indices(x[:0]).shape[0] == 0
 
 
 def test_normalisation_and_samplers():
