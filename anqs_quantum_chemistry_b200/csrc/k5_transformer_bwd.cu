@@ -34,29 +34,64 @@ struct TfBwdPtrs {   // per-row workspace of one chunk of samples (R = samples *
     int P;
 };
 
-// Tile <-> workspace rows.  A warp moves blocks of 4 rows x 8 columns: lane = (column 0..7) * 4 + (row 0..3), so that a
-// half-warp touches 16 different shared-memory bank pairs (stride MD_S = 68 doubles between columns: 4 * column + row) and
-// every 32-byte sector it touches in global memory is fully used.
+// Tile <-> workspace rows.  A warp moves blocks of 4 rows x 16 columns, a lane two consecutive rows of one column
+// (lane = column * 2 + row pair): one 16-byte shared-memory access - the 8 lanes of a quarter-warp touch 8 different
+// 16-byte bank groups, (2 * column + row pair) mod 8 with the column stride MD_S = 68 doubles - and two 8-byte global
+// accesses that, over the warp, cover two full 128-byte row segments each.
 // dst[j][r] = src[(row0 + r) * 64 + j], zero beyond `rows`
 __device__ __forceinline__ void load_rows(double *dst, const double *__restrict__ src, int64_t row0, int rows) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, rl = lane & 3, jl = lane >> 2;
-    for (int b = warp; b < 128; b += MD_THREADS / 32) {
-        const int r = (b >> 3) * 4 + rl, j = (b & 7) * 8 + jl;
-        dst[j * MD_S + r] = r < rows ? src[(row0 + r) * 64 + j] : 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, rp = lane & 1, jl = lane >> 1;
+    for (int b = warp; b < 64; b += MD_THREADS / 32) {
+        const int r = (b >> 2) * 4 + rp * 2, j = (b & 3) * 16 + jl;
+        const double *g = src + (row0 + r) * 64 + j;
+        double2 v;
+        v.x = r < rows ? g[0] : 0.0;
+        v.y = r + 1 < rows ? g[64] : 0.0;
+        *reinterpret_cast<double2 *>(dst + j * MD_S + r) = v;
     }
 }
 __device__ __forceinline__ void store_rows(const double *src, double *__restrict__ dst, int64_t row0, int rows, int ld = 64, int col0 = 0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, rl = lane & 3, jl = lane >> 2;
-    for (int b = warp; b < 128; b += MD_THREADS / 32) {
-        const int r = (b >> 3) * 4 + rl, j = (b & 7) * 8 + jl;
-        if (r < rows) dst[(row0 + r) * ld + col0 + j] = src[j * MD_S + r];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, rp = lane & 1, jl = lane >> 1;
+    for (int b = warp; b < 64; b += MD_THREADS / 32) {
+        const int r = (b >> 2) * 4 + rp * 2, j = (b & 3) * 16 + jl;
+        const double2 v = *reinterpret_cast<const double2 *>(src + j * MD_S + r);
+        double *g = dst + (row0 + r) * ld + col0 + j;
+        if (r < rows) g[0] = v.x;
+        if (r + 1 < rows) g[ld] = v.y;
     }
 }
-// wt[j][k] = W[(row0 + j) * 64 + k]: the operand of out[r][k] = sum_j in[r][j] W[row0 + j][k] (multiplication by W, not W^T)
-__device__ __forceinline__ void load_weights_n(double *wt, const double *__restrict__ W, int row0) {
-    for (int e = threadIdx.x; e < 64 * 64; e += MD_THREADS) {
-        const int j = e >> 6, k = e & 63;
-        wt[j * MD_S + k] = __ldg(W + (size_t)(row0 + j) * 64 + k);
+// Weight tiles travel global -> registers -> shared memory in two steps, so that the loads of the NEXT tile are in flight
+// while the current one is multiplied (one CTA per SM: nothing else would hide their latency).
+//   transposed (forward):  wt[k][j] = W[(row0 + j) * 64 + k]   (nn.Linear layout [out][in]; mapping of load_weights_t)
+//   plain (backward):      wt[j][k] = W[(row0 + j) * 64 + k]   (out[r][k] = sum_j in[r][j] W[row0 + j][k]: multiplication by W)
+__device__ __forceinline__ void fetch_w_t(double (&v)[16], const double *__restrict__ W, int row0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kq = lane & 3, jo = lane >> 2;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int t = warp + (MD_THREADS / 32) * i, j = (t & 7) * 8 + jo, k = (t >> 3) * 4 + kq;
+        v[i] = __ldg(W + (size_t)(row0 + j) * 64 + k);
+    }
+}
+__device__ __forceinline__ void commit_w_t(double *wt, const double (&v)[16]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kq = lane & 3, jo = lane >> 2;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int t = warp + (MD_THREADS / 32) * i, j = (t & 7) * 8 + jo, k = (t >> 3) * 4 + kq;
+        wt[k * MD_S + j] = v[i];
+    }
+}
+__device__ __forceinline__ void fetch_w_n(double (&v)[16], const double *__restrict__ W, int row0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = threadIdx.x + MD_THREADS * i;
+        v[i] = __ldg(W + (size_t)(row0 + (e >> 6)) * 64 + (e & 63));
+    }
+}
+__device__ __forceinline__ void commit_w_n(double *wt, const double (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = threadIdx.x + MD_THREADS * i;
+        wt[(e >> 6) * MD_S + (e & 63)] = v[i];
     }
 }
 // vec[j] += sum over the tile's rows of c (each thread brings the sums over its own 4 rows for its 4 columns); fixed order
@@ -186,6 +221,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
     const double scale = 1.0 / sqrt((double)hd);
     const int64_t ntiles = (B + S - 1) / S;
     for (int e = tid; e < TB_NVEC * 64; e += MD_THREADS) vecs[e] = 0.0;
+    double wv[16];           // the weight tile in flight
+    bool have_w = false;     // wv holds layer 0's query projection (fetched at the end of the previous tile)
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * S, row0 = base * T;
@@ -196,6 +233,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
         __syncthreads();
         // =========================== forward pass of the tile, keeping what the backward needs ===========================
         if (PHASE != 1) {
+        if (!have_w) fetch_w_t(wv, P.in_proj_w[0], 0);
         for (int e = tid; e < 64 * 64; e += MD_THREADS) {
             const int k = e >> 6, r = e & 63;
             double v = 0.0;
@@ -212,7 +250,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             double *dst[3] = {Qb, Kb, Vb};
             for (int part = 0; part < 3; ++part) {
                 __syncthreads();
-                load_weights_t(wt, P.in_proj_w[l], part * TB_D, TB_D, TB_D);
+                commit_w_t(wt, wv);
+                if (part < 2) fetch_w_t(wv, P.in_proj_w[l], (part + 1) * TB_D); else fetch_w_t(wv, P.out_proj_w[l], 0);
                 __syncthreads();
                 double acc[4][4];
                 gemm_tile(X, wt, TB_D, tx, ty, acc);
@@ -247,7 +286,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             }
             __syncthreads();
             store_rows(Qb, ws.a[l], row0, live);
-            load_weights_t(wt, P.out_proj_w[l], 0, TB_D, TB_D);
+            commit_w_t(wt, wv);
+            fetch_w_t(wv, P.lin1_w[l], 0);
             __syncthreads();
             {
                 double acc[4][4];
@@ -257,7 +297,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             __syncthreads();
             store_rows(Kb, ws.y1[l], row0, live);
             store_rows(X, ws.x1[l], row0, live);
-            load_weights_t(wt, P.lin1_w[l], 0, TB_D, TB_D);
+            commit_w_t(wt, wv);
+            fetch_w_t(wv, P.lin2_w[l], 0);
             __syncthreads();
             {
                 double acc[4][4];
@@ -273,7 +314,14 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             }
             __syncthreads();
             store_rows(Kb, ws.hf[l], row0, live);
-            load_weights_t(wt, P.lin2_w[l], 0, TB_D, TB_D);
+            commit_w_t(wt, wv);
+            have_w = false;
+            if (l + 1 < L) {
+                fetch_w_t(wv, P.in_proj_w[l + 1], 0);
+            } else if (PHASE == 0 && tile + gridDim.x < ntiles) {
+                fetch_w_t(wv, P.in_proj_w[0], 0);   // for this CTA's next tile
+                have_w = true;
+            }
             __syncthreads();
             {
                 double acc[4][4];
@@ -361,6 +409,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
                 for (int c = 0; c < 4; ++c) v = fma(s_dec[r * 4 + c], __ldg(P.dec_w + c * TB_D + k), v);
             G[k * MD_S + r] = v;
         }
+        fetch_w_n(wv, P.lin2_w[L - 1], 0);
         for (int l = L - 1; l >= 0; --l) {
             double *vl = vecs + (size_t)l * 4 * 64;
             __syncthreads();
@@ -370,7 +419,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             layer_norm_backward(G, B1, P.ln2_w[l], P.ln_eps, vl + 2 * 64, vl + 3 * 64, red, live, tx, ty);
             store_rows(G, ws.gy2[l], row0, live);                 // dy2: gradient of the second feed-forward linear's output
             // ---- feed-forward ---------------------------------------------------------------------------------------------
-            load_weights_n(W, P.lin2_w[l], 0);
+            commit_w_n(W, wv);
+            fetch_w_n(wv, P.lin1_w[l], 0);
             load_rows(B2, ws.hf[l], row0, live);
             __syncthreads();
             {
@@ -387,7 +437,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             }
             __syncthreads();
             store_rows(B1, ws.ghp[l], row0, live);
-            load_weights_n(W, P.lin1_w[l], 0);
+            commit_w_n(W, wv);
+            fetch_w_n(wv, P.out_proj_w[l], 0);
             __syncthreads();
             {
                 double acc[4][4];
@@ -407,7 +458,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             layer_norm_backward(G, B2, P.ln1_w[l], P.ln_eps, vl, vl + 64, red, live, tx, ty);
             store_rows(G, ws.gy1[l], row0, live);                 // dy1: gradient of the output projection's output (and of X_in)
             // ---- attention ------------------------------------------------------------------------------------------------
-            load_weights_n(W, P.out_proj_w[l], 0);
+            commit_w_n(W, wv);
+            fetch_w_n(wv, P.in_proj_w[l], 0);
             __syncthreads();
             {
                 double acc[4][4];
@@ -508,7 +560,8 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             double *src[3] = {W, B2, G};
             for (int part = 0; part < 3; ++part) {
                 __syncthreads();
-                load_weights_n(B3, P.in_proj_w[l], part * TB_D);
+                commit_w_n(B3, wv);
+                if (part < 2) fetch_w_n(wv, P.in_proj_w[l], (part + 1) * TB_D); else if (l > 0) fetch_w_n(wv, P.lin2_w[l - 1], 0);
                 __syncthreads();
                 double acc[4][4];
                 gemm_tile(src[part], B3, TB_D, tx, ty, acc);
