@@ -141,6 +141,8 @@ __device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView 
     const int lane = lane_id();
     const FbSlot &sl = *w.sl;
     const uint32_t valid = sl.valid;
+    // per-sample probe constants through a 32-bit shared-space address (a generic pointer costs a window conversion per use)
+    const uint32_t hs_addr = (uint32_t)__cvta_generic_to_shared(sl.hs);
     const uint4 *rows = reinterpret_cast<const uint4 *>(smem_tile);
     const uint2 *mems = reinterpret_cast<const uint2 *>(smem_tile + (size_t)(tile.n_multi + tile.n_single) * sizeof(RowRec));
     // ---- multi-member rows: alpha factor per row, beta factor per member, one probe step per (row step, passing sample) ----
@@ -169,7 +171,9 @@ __device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView 
                 const bool two = any != 0u;
                 const uint32_t sb = two ? __ffs(any) - 1 : sa;
                 any &= any - 1;  // 0 stays 0
-                const uint2 ha = sl.hs[sa], hb = sl.hs[sb];  // uniform addresses
+                uint2 ha, hb;  // uniform addresses
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ha.x), "=r"(ha.y) : "r"(hs_addr + sa * 8u));
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(hb.x), "=r"(hb.y) : "r"(hs_addr + sb * 8u));
                 const uint32_t ua = (((ha.x ^ rec.y) & w.linemask) << 7) ^ (ha.y & 0xFFFFu);
                 const uint32_t ub = (((hb.x ^ rec.y) & w.linemask) << 7) ^ (hb.y & 0xFFFFu);
                 const uint32_t bita = 1u << sa, bitb = two ? 1u << sb : 0u;

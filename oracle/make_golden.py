@@ -430,6 +430,25 @@ def _tfm_case(name, n, n_el, depth, head_num, seed, sample_count=64):
                param_checksums=np.array([[float(p.sum()), float((p * p).sum())] for p in net.parameters()]))
     np.savez_compressed(os.path.join(GOLDEN_DIR, f'{name}.npz'), **out)
     print(f'{name}: P={sum(p.numel() for p in net.parameters())} logits {tuple(logits.shape)}')
+    # gradient golden: autograd through the reference's module of  sum_i a_i log|psi(x_i)| + b_i arg psi(x_i)  over the physical
+    # samples, log psi = masked, normalised sum of the chosen conditionals (ANQS:392-405; masks from the numpy oracle)
+    from oracle import anqs_numpy as onp
+    masks = onp.NumberSpinMasks(n, n_el, qubit_per_qudit=1)
+    xs = phys.view(np.uint64)
+    allowed = np.stack([masks.cont_mask[t][masks.memo_idx_of_prefix(xs, t)] for t in range(n)], axis=1)       # [B, n, 2]
+    a, b = rng.standard_normal(phys.shape[0]), rng.standard_normal(phys.shape[0])
+    net.zero_grad()
+    o = net(bits[:phys.shape[0]])[:, :n, :].reshape(phys.shape[0], n, 2, 2)
+    re = torch.where(torch.from_numpy(allowed), o[..., 0], torch.full_like(o[..., 0], -np.inf))
+    re = re - 0.5 * torch.logsumexp(2.0 * re, dim=-1, keepdim=True)
+    pick = bits[:phys.shape[0]].unsqueeze(-1)
+    log_abs = torch.gather(re, -1, pick).squeeze(-1).sum(-1)
+    phase = torch.gather(o[..., 1], -1, pick).squeeze(-1).sum(-1)
+    (torch.from_numpy(a) * log_abs + torch.from_numpy(b) * phase).sum().backward()
+    grads = {f'grad_{i:02d}': p.grad.numpy() for i, (_, p) in enumerate(net.named_parameters())}
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f'{name}_grad.npz'), a=a, b=b, log_abs=log_abs.detach().numpy(),
+                        phase=phase.detach().numpy(), **grads)
+    print(f'{name}_grad: |g| = {float(sum((g * g).sum() for g in grads.values())) ** 0.5:.6g}')
 
 
 def make_tfm():

@@ -130,6 +130,28 @@ def test_kernel_matches_torch_path_and_backward_kernel_matches_autograd(name):
     assert wf.log_psi_of_indices(x[:0]).shape[0] == 0
 
 
+@pytest.mark.parametrize('name', CASES)
+def test_backward_kernel_matches_reference_module_gradient(name):
+    """Gradient golden (oracle/make_golden.py: autograd through the REFERENCE's TransformerMADE + the masked normalisation) of
+    sum_i a_i log|psi(x_i)| + b_i arg psi(x_i): every parameter tensor of k5_transformer_bwd.cu's result within 1e-10."""
+    g, masks, wf = case(name)
+    gg = load_golden(name + '_grad')
+    nphys = int(g['n_phys'])
+    x = _dev(g['samples'][:nphys]).view(-1, 1)
+    a, b = _dev(gg['a']), _dev(gg['b'])
+    wf.zero_grad()
+    lp = wf.log_psi_of_indices(x)
+    assert float((lp.real - _dev(gg['log_abs'])).abs().max()) < 1e-10 and float((lp.imag - _dev(gg['phase'])).abs().max()) < 1e-10
+    (a * lp.real + b * lp.imag).sum().backward()
+    names = [str(k) for k in g['param_names']]
+    ours = dict(wf.transformer_made.named_parameters())
+    assert list(ours) == names
+    for i, k in enumerate(names):
+        ref = _dev(gg[f'grad_{i:02d}'])
+        err = float((ours[k].grad - ref).abs().max())
+        assert err <= 1e-10 * max(1.0, float(ref.abs().max())), (k, err)
+
+
 def test_normalisation_and_samplers():
     g, masks, wf = case('tfm_n12')
     allx = torch.arange(2 ** 12, dtype=torch.int64, device=DEV).view(-1, 1)
