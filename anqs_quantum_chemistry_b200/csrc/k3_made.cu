@@ -70,7 +70,7 @@ made_forward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in
                 load_weights_t(wt, Ws[l], 0, MD_W, K);
                 __syncthreads();
                 double acc[4][4];
-                gemm_tile(cur, wt, K, tx, ty, acc);
+                gemm_tile(cur, wt, K, tx, ty, acc, nxt);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = tx + 16 * jj;
@@ -115,7 +115,7 @@ made_forward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in
                     }
                     __syncthreads();
                     double acc[4][4];
-                    gemm_tile(cur, wt, MD_W, tx, ty, acc);
+                    gemm_tile(cur, wt, MD_W, tx, ty, acc, nxt);
                     const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start;
 #pragma unroll
                     for (int ss = 0; ss < 4; ++ss) {

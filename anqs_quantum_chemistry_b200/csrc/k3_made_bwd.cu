@@ -22,21 +22,14 @@ namespace anqs {
 
 constexpr size_t MDB_SMEM = (size_t)2 * 64 * MD_S * sizeof(double) + 64 * sizeof(uint64_t) + 64 * sizeof(double2);
 
-// acc[ss][jj] += sum_k act[k][ty*4+ss] * wt[k][tx+16*jj]
-__device__ __forceinline__ void gemm_tile_acc(const double *act, const double *wt, int K, int tx, int ty, double (&acc)[4][4]) {
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        const double2 a01 = *reinterpret_cast<const double2 *>(act + k * MD_S + ty * 4);
-        const double2 a23 = *reinterpret_cast<const double2 *>(act + k * MD_S + ty * 4 + 2);
-        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-        double w[4];
+// acc[ss][jj] += sum_k act[k][ty*4+ss] * wt[k][tx+16*jj]; `act` is consumed (its rows serve as the hand-over scratch of gemm_tile)
+__device__ __forceinline__ void gemm_tile_acc(double *act, const double *wt, int K, int tx, int ty, double (&acc)[4][4]) {
+    double p[4][4];
+    gemm_tile(act, wt, K, tx, ty, p, act);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) w[jj] = wt[k * MD_S + tx + 16 * jj];
+    for (int ss = 0; ss < 4; ++ss)
 #pragma unroll
-        for (int ss = 0; ss < 4; ++ss)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[ss][jj] = fma(a[ss], w[jj], acc[ss][jj]);
-    }
+        for (int jj = 0; jj < 4; ++jj) acc[ss][jj] += p[ss][jj];
 }
 
 __global__ void __launch_bounds__(MD_THREADS, 2)

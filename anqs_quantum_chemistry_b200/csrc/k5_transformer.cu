@@ -109,7 +109,7 @@ transformer_forward_kernel(const anqs_transformer_desc_t P, const int64_t *__res
                 load_weights_t(wt, P.in_proj_w[l], part * TF_D, TF_D, TF_D);
                 __syncthreads();
                 double acc[4][4];
-                gemm_tile(X, wt, TF_D, tx, ty, acc);
+                gemm_tile(X, wt, TF_D, tx, ty, acc, dst[part]);
                 store_tile(dst[part], acc, P.in_proj_b[l] ? P.in_proj_b[l] + part * TF_D : nullptr, tx, ty);
             }
             __syncthreads();
@@ -162,7 +162,7 @@ transformer_forward_kernel(const anqs_transformer_desc_t P, const int64_t *__res
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(Qb, wt, TF_D, tx, ty, acc);
+                gemm_tile(Qb, wt, TF_D, tx, ty, acc, Kb);
                 residual_layer_norm(X, acc, P.out_proj_b[l], P.ln1_w[l], P.ln1_b[l], P.ln_eps, tx, ty);
             }
             __syncthreads();
@@ -171,7 +171,7 @@ transformer_forward_kernel(const anqs_transformer_desc_t P, const int64_t *__res
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(X, wt, TF_D, tx, ty, acc);
+                gemm_tile(X, wt, TF_D, tx, ty, acc, Kb);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = tx + 16 * jj;
@@ -185,7 +185,7 @@ transformer_forward_kernel(const anqs_transformer_desc_t P, const int64_t *__res
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(Kb, wt, TF_D, tx, ty, acc);
+                gemm_tile(Kb, wt, TF_D, tx, ty, acc, Vb);
                 residual_layer_norm(X, acc, P.lin2_b[l], P.ln2_w[l], P.ln2_b[l], P.ln_eps, tx, ty);
             }
             __syncthreads();

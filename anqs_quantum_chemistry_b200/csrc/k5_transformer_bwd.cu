@@ -254,7 +254,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
                 if (part < 2) fetch_w_t(wv, P.in_proj_w[l], (part + 1) * TB_D); else fetch_w_t(wv, P.out_proj_w[l], 0);
                 __syncthreads();
                 double acc[4][4];
-                gemm_tile(X, wt, TB_D, tx, ty, acc);
+                gemm_tile(X, wt, TB_D, tx, ty, acc, dst[part]);
                 store_acc(dst[part], acc, P.in_proj_b[l] ? P.in_proj_b[l] + part * TB_D : nullptr, tx, ty);
             }
             __syncthreads();
@@ -291,7 +291,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(Qb, wt, TB_D, tx, ty, acc);
+                gemm_tile(Qb, wt, TB_D, tx, ty, acc, Kb);
                 residual_layer_norm_save(X, Kb, acc, P.out_proj_b[l], P.ln1_w[l], P.ln1_b[l], P.ln_eps, tx, ty);
             }
             __syncthreads();
@@ -302,7 +302,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(X, wt, TB_D, tx, ty, acc);
+                gemm_tile(X, wt, TB_D, tx, ty, acc, Kb);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = tx + 16 * jj;
@@ -325,7 +325,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(Kb, wt, TB_D, tx, ty, acc);
+                gemm_tile(Kb, wt, TB_D, tx, ty, acc, Qb);
                 residual_layer_norm_save(X, Qb, acc, P.lin2_b[l], P.ln2_w[l], P.ln2_b[l], P.ln_eps, tx, ty);
             }
             __syncthreads();
@@ -425,7 +425,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(G, W, TB_D, tx, ty, acc);               // dHf = dy2 * W2
+                gemm_tile(G, W, TB_D, tx, ty, acc, B1);           // dHf = dy2 * W2
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj)
                 {
@@ -442,7 +442,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(B1, W, TB_D, tx, ty, acc);              // dX1 = dy2 (residual) + dHpre * W1
+                gemm_tile(B1, W, TB_D, tx, ty, acc, B1);          // dX1 = dy2 (residual) + dHpre * W1 (B1 is consumed)
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
                     double2 *g2 = reinterpret_cast<double2 *>(G + (tx + 16 * jj) * MD_S + ty * 4);
@@ -463,7 +463,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
             __syncthreads();
             {
                 double acc[4][4];
-                gemm_tile(G, W, TB_D, tx, ty, acc);               // dA = dy1 * W_o
+                gemm_tile(G, W, TB_D, tx, ty, acc, B3);           // dA = dy1 * W_o
                 store_acc(B3, acc, nullptr, tx, ty);
             }
             __syncthreads();
@@ -564,7 +564,7 @@ transformer_backward_kernel(const anqs_transformer_desc_t P, const int64_t *__re
                 if (part < 2) fetch_w_n(wv, P.in_proj_w[l], (part + 1) * TB_D); else if (l > 0) fetch_w_n(wv, P.lin2_w[l - 1], 0);
                 __syncthreads();
                 double acc[4][4];
-                gemm_tile(src[part], B3, TB_D, tx, ty, acc);
+                gemm_tile(src[part], B3, TB_D, tx, ty, acc, src[part]);   // dQ / dK / dV are consumed
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll

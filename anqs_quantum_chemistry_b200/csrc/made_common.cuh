@@ -51,25 +51,62 @@ __device__ __forceinline__ void load_weights_t(double *wt, const double *__restr
     }
 }
 
-// acc[ss][jj] = sum_k act[k][ty*4+ss] * wt[k][tx+16*jj]
-__device__ __forceinline__ void gemm_tile(const double *act, const double *wt, int K, int tx, int ty, double (&acc)[4][4]) {
+// acc[ss][jj] = sum_k act[k][ty*4+ss] * wt[k][tx+16*jj]   (a 64 x 64 x K tile per CTA of 256 threads)
+//
+// The products run on the FP64 tensor-core path: mma.sync m8n8k4 f64 reaches the same 37 TFLOP/s as DFMA on B200
+// (scripts/microbench_dmma.cu) with one warp instruction per 256 multiply-adds instead of one per 32, and its operands come
+// from 9 conflict-free 8-byte shared-memory loads per 4 k (row stride MD_S = 68 = 4 mod 16: the half-warp's addresses
+// 4 * (lane % 4) + lane / 4 cover the 16 bank pairs) instead of 24 loads.  A warp multiplies its own 8 rows (samples
+// 8 warp .. 8 warp + 7, the rows ty * 4 + ss of its threads) by all 64 columns: 8 accumulator fragments.  The fragments
+// (lane: row lane / 4, columns 8 t + 2 (lane % 4) + {0, 1}) are then handed to the layout every epilogue is written in
+// (thread: rows ty * 4 + ss, columns tx + 16 jj) through the warp's own 8 rows of `scratch`, a [64][MD_S] buffer the caller
+// can spare at this point - the destination of the epilogue, or `act` itself when its values are not needed afterwards (only
+// this warp reads rows 8 warp .. 8 warp + 7 of `act`).  No block-wide barrier is involved.
+__device__ __forceinline__ void mma_m8n8k4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void gemm_tile(const double *act, const double *wt, int K, int tx, int ty, double (&acc)[4][4], double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;   // A fragment: (row fr, k fk); B fragment: (k fk, column fr)
+    double c[8][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int t = 0; t < 8; ++t) c[t][0] = c[t][1] = 0.0;
+    const double *ap = act + fk * MD_S + warp * 8 + fr;
+    const double *bp = wt + fk * MD_S + fr;
+    const int Kfull = K & ~3;
+#pragma unroll 2
+    for (int k0 = 0; k0 < Kfull; k0 += 4) {
+        const double a = ap[k0 * MD_S];
+        double b[8];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        const double2 a01 = *reinterpret_cast<const double2 *>(act + k * MD_S + ty * 4);
-        const double2 a23 = *reinterpret_cast<const double2 *>(act + k * MD_S + ty * 4 + 2);
-        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-        double w[4];
+        for (int t = 0; t < 8; ++t) b[t] = bp[k0 * MD_S + 8 * t];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) w[jj] = wt[k * MD_S + tx + 16 * jj];
-#pragma unroll
-        for (int ss = 0; ss < 4; ++ss)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[ss][jj] = fma(a[ss], w[jj], acc[ss][jj]);
+        for (int t = 0; t < 8; ++t) mma_m8n8k4(c[t], a, b[t]);
     }
+    if (Kfull < K) {   // ragged K (first MADE layer of an odd qubit count, narrow NADE outputs): zero operands beyond K
+        const bool ok = Kfull + fk < K;
+        const double a = ok ? ap[Kfull * MD_S] : 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) mma_m8n8k4(c[t], a, ok ? bp[Kfull * MD_S + 8 * t] : 0.0);
+    }
+    __syncwarp();   // scratch may be act: every lane of the warp has read its operands
+    double *sp = scratch + (2 * fk) * MD_S + warp * 8 + fr;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        sp[(8 * t) * MD_S] = c[t][0];
+        sp[(8 * t + 1) * MD_S] = c[t][1];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const double2 v01 = *reinterpret_cast<const double2 *>(scratch + (tx + 16 * jj) * MD_S + ty * 4);
+        const double2 v23 = *reinterpret_cast<const double2 *>(scratch + (tx + 16 * jj) * MD_S + ty * 4 + 2);
+        acc[0][jj] = v01.x;
+        acc[1][jj] = v01.y;
+        acc[2][jj] = v23.x;
+        acc[3][jj] = v23.y;
+    }
+    __syncwarp();   // the epilogue may write these positions
 }
 
 __device__ __forceinline__ double row_sum16(double v) {
