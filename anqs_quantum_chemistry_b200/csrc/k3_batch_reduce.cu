@@ -5,8 +5,8 @@
 // batch (10^5..10^6), M <= 640, N <= 64: a tiny output and an enormous reduction dimension.  Library fp64 GEMMs pick
 // 32x32 tiles for that shape (measured 5 TFLOP/s on B200); here the output is cut into 128 x 64 tiles, the batch into S
 // slices so that all CTAs together are one wave (a 128-row tile gets 3/2 of the slices of a 64-row tile, which runs 4 x 8
-// per thread), and each CTA keeps its whole output tile in registers (8 x 8 per thread) while its slice of A and B streams through a double-buffered shared-memory tile by cp.async — 8 LDS.128 per
-// 64 DFMA, so the FP64 pipe and not the shared-memory pipe is the limit.  The column sums of A (bias gradients) ride along
+// per thread), and each CTA keeps its whole output tile in registers (mma accumulator fragments) while its slice of A and B
+// streams through a double-buffered shared-memory tile by cp.async.  The column sums of A (bias gradients) ride along
 // from the same shared-memory tile.  Partial tiles go to a caller-supplied workspace and a second small kernel adds them up
 // in a fixed order: the result is deterministic.
 #include <algorithm>
@@ -37,25 +37,31 @@ __device__ __forceinline__ void br_cp_async8(double *dst, const double *src, boo
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
-// One K slice of one output tile with MT (128 or 64) rows: thread = (MT / 16) x 8 outputs.
+// One K slice of one output tile with MT (128 or 64) rows.  The products run on the FP64 tensor-core path (mma.sync m8n8k4 f64:
+// the DFMA rate at an eighth of the issue slots, scripts/microbench_dmma.cu): warp w of the four owns rows w MT/4 ..
+// (w + 1) MT/4 - 1 of the tile (MT / 32 row fragments) and all 64 columns (8 column fragments), MT / 32 + 8 shared-memory
+// loads of 8 bytes per 8 MT / 32 mma.  Row k of a shared tile is stored rotated by 4 (k mod 4) columns, so that the
+// half-warp's fragment addresses (k = lane % 4, column = lane / 4) fall on 16 different bank pairs without padding.
+__device__ __forceinline__ void br_mma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
 template <int MT>
 __device__ __forceinline__ void br_slice(const BrTile &T, int64_t k0, int64_t k1, double (*As)[BR_KT][BR_MT], double (*Bs)[BR_KT][BR_NT],
                                          double *__restrict__ out) {
-    constexpr int RJ = MT / 32;              // row blocks of 32 per thread: rows 2 og + {0,1} + 32 j, j < RJ
+    constexpr int RM = MT / 32;              // row fragments (8 rows each) per warp
     const int lda = T.lda, ldb = T.ldb, M = T.M, N = T.N;
     const bool want_sums = T.colsum != nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ig = lane & 7;                 // 8 column groups: columns 2 ig + {0,1} + 16 j, j < 4
-    const int og = warp * 4 + (lane >> 3);   // 16 row groups
+    const int fr = lane >> 2, fk = lane & 3;                 // A fragment: (row fr, k fk); B fragment: (k fk, column fr)
     const int b_col = tid & (BR_NT - 1), b_row = tid >> 6;   // B tile: 8 elements per thread, rows b_row + 2 j
     const bool a_ok = tid < M, b_ok = b_col < N;             // A tile: 16 elements per thread, column tid, rows j
     const double *Ap = T.A + (a_ok ? tid : 0), *Bp = T.B + (b_ok ? b_col : 0);
 
-    double acc[2 * RJ][8];
+    double acc[RM][8][2];
 #pragma unroll
-    for (int i = 0; i < 2 * RJ; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+        for (int t = 0; t < 8; ++t) acc[i][t][0] = acc[i][t][1] = 0.0;
     double csum = 0.0;
 
     auto fetch = [&](int64_t kb, int buf) {
@@ -64,17 +70,25 @@ __device__ __forceinline__ void br_slice(const BrTile &T, int64_t k0, int64_t k1
             for (int j = 0; j < BR_KT; ++j) {
                 const int64_t k = kb + j;
                 const bool ok = a_ok && k < k1;
-                br_cp_async8(&As[buf][j][tid], Ap + (ok ? k : k0) * lda, ok);
+                br_cp_async8(&As[buf][j][(tid + 4 * (j & 3)) & (BR_MT - 1)], Ap + (ok ? k : k0) * lda, ok);
             }
         }
 #pragma unroll
         for (int j = 0; j < BR_KT / 2; ++j) {
-            const int64_t k = kb + b_row + 2 * j;
+            const int r = b_row + 2 * j;
+            const int64_t k = kb + r;
             const bool ok = b_ok && k < k1;
-            br_cp_async8(&Bs[buf][b_row + 2 * j][b_col], Bp + (ok ? k : k0) * ldb, ok);
+            br_cp_async8(&Bs[buf][r][(b_col + 4 * (r & 3)) & (BR_NT - 1)], Bp + (ok ? k : k0) * ldb, ok);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
+
+    // this lane's fragment columns (rotation of its k row included)
+    int a_col[RM], b_colf[8];
+#pragma unroll
+    for (int i = 0; i < RM; ++i) a_col[i] = (warp * 8 * RM + 8 * i + fr + 4 * fk) & (BR_MT - 1);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) b_colf[t] = (8 * t + fr + 4 * fk) & (BR_NT - 1);
 
     if (k0 < k1) fetch(k0, 0);
     int buf = 0;
@@ -83,37 +97,29 @@ __device__ __forceinline__ void br_slice(const BrTile &T, int64_t k0, int64_t k1
         __syncthreads();                                  // tile `buf` has landed; everyone is done with tile `buf ^ 1`
         if (kb + BR_KT < k1) fetch(kb + BR_KT, buf ^ 1);
 #pragma unroll
-        for (int kk = 0; kk < BR_KT; ++kk) {
-            double a[2 * RJ], b[8];
+        for (int kk = 0; kk < BR_KT; kk += 4) {
+            double a[RM], b[8];
 #pragma unroll
-            for (int j = 0; j < RJ; ++j) {
-                const double2 v = *reinterpret_cast<const double2 *>(&As[buf][kk][2 * og + 32 * j]);
-                a[2 * j] = v.x;
-                a[2 * j + 1] = v.y;
-            }
+            for (int i = 0; i < RM; ++i) a[i] = As[buf][kk + fk][a_col[i]];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double2 w = *reinterpret_cast<const double2 *>(&Bs[buf][kk][2 * ig + 16 * j]);
-                b[2 * j] = w.x;
-                b[2 * j + 1] = w.y;
-            }
+            for (int t = 0; t < 8; ++t) b[t] = Bs[buf][kk + fk][b_colf[t]];
 #pragma unroll
-            for (int i = 0; i < 2 * RJ; ++i)
+            for (int i = 0; i < RM; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int t = 0; t < 8; ++t) br_mma(acc[i][t], a[i], b[t]);
         }
         if (want_sums && tid < MT) {
 #pragma unroll
-            for (int kk = 0; kk < BR_KT; ++kk) csum += As[buf][kk][tid];
+            for (int kk = 0; kk < BR_KT; ++kk) csum += As[buf][kk][(tid + 4 * (kk & 3)) & (BR_MT - 1)];
         }
     }
 
 #pragma unroll
-    for (int i = 0; i < 2 * RJ; ++i) {
-        const int r = 2 * og + (i & 1) + 32 * (i >> 1);
+    for (int i = 0; i < RM; ++i) {
+        const int r = warp * 8 * RM + 8 * i + fr;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<double2 *>(out + r * BR_NT + 2 * ig + 16 * j) = make_double2(acc[i][2 * j], acc[i][2 * j + 1]);
+        for (int t = 0; t < 8; ++t)
+            *reinterpret_cast<double2 *>(out + r * BR_NT + 8 * t + 2 * fk) = make_double2(acc[i][t][0], acc[i][t][1]);
     }
     if (tid < MT) out[BR_MT * BR_NT + tid] = csum;
 }
