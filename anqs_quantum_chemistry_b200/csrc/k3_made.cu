@@ -58,6 +58,9 @@ made_forward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in
             const double *const *Ws = net == 0 ? P.w_abs : P.w_phase;
             const double *const *bs = net == 0 ? P.b_abs : P.b_phase;
             __syncthreads();
+            double wv[16];   // weight tile in flight: fetched one product ahead, committed to shared memory when `wt` is free
+            fetch_weights_t(wv, Ws[0], 0, MD_W, n);
+            const int q_lo = MODE == MADE_COND ? level_q : 0, q_hi = MODE == MADE_COND ? level_q + 1 : Q;
             // input encoding: 1 - 2*bit for known positions, 0 beyond the prefix (MLP:205-225)
             for (int e = tid; e < n * 64; e += MD_THREADS) {
                 int k = e >> 6, s = e & 63;
@@ -67,7 +70,9 @@ made_forward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in
             double *cur = act0, *nxt = act1;
             for (int l = 0; l < depth; ++l) {
                 const int K = l == 0 ? n : MD_W;
-                load_weights_t(wt, Ws[l], 0, MD_W, K);
+                commit_weights_t(wt, wv, K);
+                if (l + 1 < depth) fetch_weights_t(wv, Ws[l + 1], 0, MD_W, MD_W);
+                else if (net == 0) fetch_weights_t(wv, Ws[depth], q_lo * DM, DM, MD_W);
                 __syncthreads();
                 double acc[4][4];
                 gemm_tile(cur, wt, K, tx, ty, acc, nxt);
@@ -92,9 +97,9 @@ made_forward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in
             }
             // cur = last hidden activations [64][samples]
             if (net == 0) {
-                const int q_lo = MODE == MADE_COND ? level_q : 0, q_hi = MODE == MADE_COND ? level_q + 1 : Q;
                 for (int q = q_lo; q < q_hi; ++q) {
-                    load_weights_t(wt, Ws[depth], q * DM, DM, MD_W);
+                    commit_weights_t(wt, wv, MD_W);
+                    if (q + 1 < q_hi) fetch_weights_t(wv, Ws[depth], (q + 1) * DM, DM, MD_W);
                     if (tid < 64) {
                         const int start = P.qudit_starts[q];
                         const uint64_t x = s_idx[tid];

@@ -34,21 +34,31 @@ __device__ __forceinline__ long long memo_index(const anqs_made_desc_t &P, uint6
 // wt[k][j] = W[(row0 + j) * K + k] for j < rows, 0 otherwise  (nn.Linear layout [out][in])
 // A warp moves 8 rows x 4 consecutive k at a time: every row contributes one full 32-byte sector of W, and the 32 stores
 // land on (4 k + j) mod 16 = every 8-byte bank pair exactly twice (MD_S = 68 = 4 mod 16), the two-wavefront minimum.
-__device__ __forceinline__ void load_weights_t(double *wt, const double *__restrict__ W, int row0, int rows, int K) {
+__device__ __forceinline__ void fetch_weights_t(double (&v)[16], const double *__restrict__ W, int row0, int rows, int K) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kq = lane & 3, jo = lane >> 2;
     // K <= 64: at most 16 steps per warp; all loads of a thread are issued before the first store
-    double v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int t = warp + (MD_THREADS / 32) * i, j = (t & 7) * 8 + jo, k = (t >> 3) * 4 + kq;
         v[i] = (k < K && j < rows) ? __ldg(W + (size_t)(row0 + j) * K + k) : 0.0;
     }
+}
+__device__ __forceinline__ void commit_weights_t(double *wt, const double (&v)[16], int K) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kq = lane & 3, jo = lane >> 2;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int t = warp + (MD_THREADS / 32) * i, j = (t & 7) * 8 + jo, k = (t >> 3) * 4 + kq;
         if (k < K) wt[k * MD_S + j] = v[i];
     }
+}
+// The two halves can be pulled apart by a caller that has other work between them: fetch the NEXT tile's weights before the
+// current product, commit them after it (made_forward_kernel, transformer_backward_kernel).
+__device__ __forceinline__ void load_weights_t(double *wt, const double *__restrict__ W, int row0, int rows, int K) {
+    double v[16];
+    fetch_weights_t(v, W, row0, rows, K);
+    commit_weights_t(wt, v, K);
 }
 
 // acc[ss][jj] = sum_k act[k][ty*4+ss] * wt[k][tx+16*jj]   (a 64 x 64 x K tile per CTA of 256 threads)
