@@ -54,6 +54,9 @@ _SIGNATURES = {
     'anqs_made_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_made_cond_log_abs': (_c_int, [_vp, _c_int, _vp, _c_i64, _vp, _vp]),
     'anqs_made_backward_chain': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'anqs_made_backward_chain_abs': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'anqs_made_phase_output_workspace': (_c_i64, [_vp]),
+    'anqs_made_phase_output_grad': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _c_int, _vp, _vp, _vp, _c_i64, _vp]),
     'anqs_batch_reduce_workspace': (_c_i64, [_vp, _c_int, _c_i64]),
     'anqs_batch_reduce_gemm': (_c_int, [_vp, _c_int, _c_i64, _c_int, _vp, _c_i64, _vp]),
     'anqs_nade_log_psi': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),

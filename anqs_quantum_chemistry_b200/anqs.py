@@ -229,26 +229,31 @@ class _MadeLogPsi(pt.autograd.Function):
         desc = wf._descriptor()
         lib, sp = _lib.lib(), _lib.stream_ptr(dev)
         QD, width = Q * DM, wf.width
-        chunk = max(1, min(B, _MADE_BWD_SCRATCH_BYTES // (16 * QD + 16 * depth * width + 8 * n)))
+        chunk = max(1, min(B, _MADE_BWD_SCRATCH_BYTES // (8 * QD + 16 * depth * width + 8 * n)))
         f64 = dict(dtype=pt.float64, device=dev)
         alloc = pt.zeros if B == 0 else pt.empty
         gW_out, gb_out = alloc((2, QD, width), **f64), alloc((2, QD), **f64)
         gW0, gb_h = alloc((2, width, n), **f64), alloc((2, depth, width), **f64)
         gWm = alloc((2, depth - 1, width, width), **f64) if depth > 1 else None
+        po_work = wf._phase_output_workspace(desc) if B > 0 else None
         for lo in range(0, B, chunk):
             hi = min(B, lo + chunk)
             m = hi - lo
-            dY = pt.empty((2, m, QD), **f64)
+            dY = pt.empty((m, QD), **f64)                  # log-abs network only: the phase network's is one entry per qudit
             da = pt.empty((2, depth, m, width), **f64)
             x = pt.empty((m, n), **f64)
             h = save_h if m == B else save_h[:, :, lo:hi].contiguous()
             p = save_p if m == B else save_p[lo:hi]
-            _lib.check(lib.anqs_made_backward_chain(ctypes.byref(desc), _lib.dptr(idx[lo:hi]), m, _lib.dptr(pt.view_as_real(g[lo:hi])),
-                                                    _lib.dptr(h), _lib.dptr(p), _lib.dptr(dY), _lib.dptr(da), _lib.dptr(x), sp))
-            problems = []
-            for net in range(2):   # k3_batch_reduce.cu: all batch reductions of both sub-networks in one launch pair
-                problems.append((dY[net].data_ptr(), QD, QD, h[net, depth - 1].data_ptr(), width, width,
-                                 gW_out[net].data_ptr(), width, gb_out[net].data_ptr()))
+            gl = pt.view_as_real(g[lo:hi])
+            _lib.check(lib.anqs_made_backward_chain_abs(ctypes.byref(desc), _lib.dptr(idx[lo:hi]), m, _lib.dptr(gl),
+                                                        _lib.dptr(h), _lib.dptr(p), _lib.dptr(dY), _lib.dptr(da), _lib.dptr(x), sp))
+            # phase network, output layer: a row scatter (k3_made_bwd.cu: made_phase_output_kernel)
+            _lib.check(lib.anqs_made_phase_output_grad(ctypes.byref(desc), _lib.dptr(idx[lo:hi]), m, _lib.dptr(gl), _lib.dptr(h[1, depth - 1]),
+                                                       int(lo > 0), _lib.dptr(gW_out[1]), _lib.dptr(gb_out[1]), _lib.dptr(po_work),
+                                                       po_work.numel() * 8, sp))
+            problems = []   # k3_batch_reduce.cu: every other batch reduction of both sub-networks in one launch pair
+            problems.append((dY.data_ptr(), QD, QD, h[0, depth - 1].data_ptr(), width, width, gW_out[0].data_ptr(), width, gb_out[0].data_ptr()))
+            for net in range(2):
                 problems.append((da[net, 0].data_ptr(), width, width, x.data_ptr(), n, n, gW0[net].data_ptr(), n, gb_h[net, 0].data_ptr()))
                 for l in range(1, depth):
                     problems.append((da[net, l].data_ptr(), width, width, h[net, l - 1].data_ptr(), width, width,
@@ -463,6 +468,14 @@ class LogAbsPhaseANQS(AutoregressiveSamplerMixin, ParameterVectorMixin, Abstract
         d._keep = keep
         self._desc_cache = (ptr_key, d)
         return d
+
+    def _phase_output_workspace(self, desc) -> pt.Tensor:
+        """Per-CTA partial sums of the phase network's output-layer gradient (anqs_made_phase_output_grad), kept between calls."""
+        need = int(_lib.lib().anqs_made_phase_output_workspace(ctypes.byref(desc)))
+        ws = getattr(self, '_po_work', None)
+        if ws is None or ws.numel() * 8 < need or ws.device != self.device:
+            ws = self._po_work = pt.empty((need + 7) // 8, dtype=pt.float64, device=self.device)
+        return ws
 
     def _descriptor(self):
         if self.de_mode == 'NADE':

@@ -32,6 +32,9 @@ __device__ __forceinline__ void gemm_tile_acc(double *act, const double *wt, int
         for (int jj = 0; jj < 4; ++jj) acc[ss][jj] += p[ss][jj];
 }
 
+// PHASE_DY = false: the phase network's output-layer gradient (one non-zero per sample and qudit) is not written out; its
+// weight gradient is the row scatter of made_phase_output_kernel below instead of a dense product with 63/64 zeros.
+template <bool PHASE_DY>
 __global__ void __launch_bounds__(MD_THREADS, 2)
 made_backward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in, int64_t B, const double2 *__restrict__ grad_out,
                      const double *__restrict__ save_h, const double *__restrict__ save_p, double *__restrict__ dY,
@@ -107,11 +110,13 @@ made_backward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_i
                 // phase network: only the chosen outcome of every qudit carries a gradient (arg psi = pi * sum_q y[q, chosen])
                 for (int q = 0; q < Q; ++q) {
                     const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start;
-                    for (int e = tid; e < 64 * 64; e += MD_THREADS) {
-                        const int s = e >> 6, d = e & 63;
-                        if (d < DM && base + s < B) {
-                            const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
-                            dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = d == chosen ? PI * s_g[s].y : 0.0;
+                    if (PHASE_DY) {
+                        for (int e = tid; e < 64 * 64; e += MD_THREADS) {
+                            const int s = e >> 6, d = e & 63;
+                            if (d < DM && base + s < B) {
+                                const int chosen = (int)((s_idx[s] >> start) & ((1ull << bits) - 1ull));
+                                dYn[(size_t)(base + s) * QD + (size_t)q * DM + d] = d == chosen ? PI * s_g[s].y : 0.0;
+                            }
                         }
                     }
 #pragma unroll
@@ -166,6 +171,87 @@ made_backward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_i
             }
         }
     }
+}
+
+// Output-layer gradient of the phase network (arg psi = pi * sum_q y[q, chosen_q], LAP:97, ANQS:450-454):
+//   grad W_out[q DM + d][j] = sum_s [chosen_q(s) = d] pi g_s h_s[j],   grad b_out[q DM + d] = sum_s [chosen_q(s) = d] pi g_s
+// - one row of 64 numbers per (sample, qudit), where the dense product dY^T h multiplies 63 zeros for every one of them.
+// A CTA owns a slice of the samples; for one qudit at a time each of its warps adds its samples' rows into a private
+// [DM][64] (+ [DM] bias) tile in shared memory, walking the samples in order; the warps' tiles are then added in warp order
+// into the CTA's partial result, and made_phase_output_finish_kernel adds the partial results in CTA order: deterministic.
+// The hidden rows are re-read once per qudit (from L2 when the chunk fits).
+constexpr int PO_WARPS = 4, PO_TILE = 64 * 64 + 64;
+constexpr size_t PO_SMEM = (size_t)PO_WARPS * PO_TILE * sizeof(double);
+
+__global__ void __launch_bounds__(PO_WARPS * 32, 1)
+made_phase_output_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in, int64_t B, const double2 *__restrict__ grad_out,
+                         const double *__restrict__ h_last, double *__restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char po_smem[];
+    double *tiles = reinterpret_cast<double *>(po_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *acc = tiles + (size_t)warp * PO_TILE;
+    const int Q = P.qudit_num, DM = P.max_qudit_dim;
+    const double PI = 3.14159265358979323846;
+    const int64_t per = (B + gridDim.x - 1) / gridDim.x;
+    const int64_t s0 = (int64_t)blockIdx.x * per, s1 = min(B, s0 + per);
+    for (int q = 0; q < Q; ++q) {
+        const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start;
+        const uint64_t omask = (1ull << bits) - 1ull;
+        for (int e = lane; e < PO_TILE; e += 32) acc[e] = 0.0;
+        __syncwarp();
+        int64_t s = s0 + warp;
+        for (; s + 3 * PO_WARPS < s1; s += 4 * PO_WARPS) {   // four samples per step: twelve loads in flight per lane
+            uint64_t x[4];
+            double g[4], h0[4], h1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t r = s + u * PO_WARPS;
+                x[u] = (uint64_t)__ldg(idx_in + r);
+                g[u] = PI * __ldg(&grad_out[r].y);
+                h0[u] = __ldg(h_last + r * MD_W + lane);
+                h1[u] = __ldg(h_last + r * MD_W + 32 + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = (int)((x[u] >> start) & omask);
+                acc[c * 64 + lane] = fma(g[u], h0[u], acc[c * 64 + lane]);
+                acc[c * 64 + 32 + lane] = fma(g[u], h1[u], acc[c * 64 + 32 + lane]);
+                if (lane == 0) acc[64 * 64 + c] += g[u];
+            }
+        }
+        for (; s < s1; s += PO_WARPS) {
+            const uint64_t x = (uint64_t)__ldg(idx_in + s);
+            const double g = PI * __ldg(&grad_out[s].y);
+            const int c = (int)((x >> start) & omask);
+            acc[c * 64 + lane] = fma(g, __ldg(h_last + s * MD_W + lane), acc[c * 64 + lane]);
+            acc[c * 64 + 32 + lane] = fma(g, __ldg(h_last + s * MD_W + 32 + lane), acc[c * 64 + 32 + lane]);
+            if (lane == 0) acc[64 * 64 + c] += g;
+        }
+        __syncthreads();
+        double *out = partial + ((size_t)blockIdx.x * Q + q) * PO_TILE;
+        for (int e = tid; e < PO_TILE; e += PO_WARPS * 32) {
+            double v = tiles[e];
+#pragma unroll
+            for (int w = 1; w < PO_WARPS; ++w) v += tiles[(size_t)w * PO_TILE + e];
+            out[e] = v;
+        }
+        __syncthreads();
+        (void)DM;
+    }
+}
+
+__global__ void made_phase_output_finish_kernel(const double *__restrict__ partial, int n_cta, int Q, int DM, int accumulate,
+                                                double *__restrict__ gW, double *__restrict__ gb) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;   // over Q * PO_TILE
+    if (e >= Q * PO_TILE) return;
+    const int q = e / PO_TILE, r = e - q * PO_TILE;
+    const bool is_bias = r >= 64 * 64;
+    const int d = is_bias ? r - 64 * 64 : r >> 6, j = r & 63;
+    if (d >= DM || (is_bias && gb == nullptr)) return;
+    double v = 0.0;
+    for (int c = 0; c < n_cta; ++c) v += partial[((size_t)c * Q + q) * PO_TILE + r];
+    double *dst = is_bias ? gb + (size_t)q * DM + d : gW + ((size_t)q * DM + d) * MD_W + j;
+    *dst = accumulate ? *dst + v : v;
 }
 
 // NADE mode: the same chain for every (sub-network, qudit) MLP (LAP:24-42): output width D_q = 2^bits of the qudit, first layer
@@ -284,19 +370,56 @@ nade_backward_kernel(const anqs_nade_desc_t P, const int64_t *__restrict__ idx_i
 
 using namespace anqs;
 
-extern "C" int anqs_made_backward_chain(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
-                                        const double *d_save_h, const double *d_save_p, double *d_dY, double *d_da, double *d_x,
-                                        void *stream) {
+static int made_chain_launch(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out, const double *d_save_h,
+                             const double *d_save_p, double *d_dY, double *d_da, double *d_x, bool phase_dy, void *stream) {
     ANQS_REQUIRE(desc, "null network descriptor");
     ANQS_REQUIRE(desc->width == MD_W && desc->max_qudit_dim <= 64 && desc->depth >= 1 && desc->depth <= 4, "unsupported network shape");
     ANQS_REQUIRE(n >= 0, "negative sample count");
     if (n == 0) return 0;
     ANQS_REQUIRE(d_idx && d_grad_out && d_save_h && d_save_p && d_dY && d_da && d_x, "null pointer");
-    ANQS_CUDA(cudaFuncSetAttribute(made_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MDB_SMEM));
+    auto kern = phase_dy ? made_backward_kernel<true> : made_backward_kernel<false>;
+    ANQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MDB_SMEM));
     const int64_t ntiles = (n + MD_TB - 1) / MD_TB;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)sm_count_of_current_device() * 2);
-    made_backward_kernel<<<grid, MD_THREADS, MDB_SMEM, (cudaStream_t)stream>>>(*desc, d_idx, n, (const double2 *)d_grad_out, d_save_h,
-                                                                              d_save_p, d_dY, d_da, d_x);
+    kern<<<grid, MD_THREADS, MDB_SMEM, (cudaStream_t)stream>>>(*desc, d_idx, n, (const double2 *)d_grad_out, d_save_h, d_save_p, d_dY, d_da, d_x);
+    ANQS_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int anqs_made_backward_chain(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                                        const double *d_save_h, const double *d_save_p, double *d_dY, double *d_da, double *d_x,
+                                        void *stream) {
+    return made_chain_launch(desc, d_idx, n, d_grad_out, d_save_h, d_save_p, d_dY, d_da, d_x, true, stream);
+}
+
+extern "C" int anqs_made_backward_chain_abs(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                                            const double *d_save_h, const double *d_save_p, double *d_dY_abs, double *d_da, double *d_x,
+                                            void *stream) {
+    return made_chain_launch(desc, d_idx, n, d_grad_out, d_save_h, d_save_p, d_dY_abs, d_da, d_x, false, stream);
+}
+
+extern "C" int64_t anqs_made_phase_output_workspace(const anqs_made_desc_t *desc) {
+    if (!desc || desc->qudit_num < 1) return -1;
+    return (int64_t)sm_count_of_current_device() * desc->qudit_num * PO_TILE * (int64_t)sizeof(double);
+}
+
+extern "C" int anqs_made_phase_output_grad(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                                           const double *d_h_last, int accumulate, double *d_gW, double *d_gb, void *d_work,
+                                           int64_t work_bytes, void *stream) {
+    ANQS_REQUIRE(desc, "null network descriptor");
+    ANQS_REQUIRE(desc->width == MD_W && desc->max_qudit_dim <= 64, "unsupported network shape");
+    ANQS_REQUIRE(n >= 0, "negative sample count");
+    if (n == 0) return 0;
+    ANQS_REQUIRE(d_idx && d_grad_out && d_h_last && d_gW && d_work, "null pointer");
+    ANQS_REQUIRE(work_bytes >= anqs_made_phase_output_workspace(desc), "workspace too small");
+    const int grid = (int)std::min<int64_t>((n + PO_WARPS - 1) / PO_WARPS, (int64_t)sm_count_of_current_device());
+    cudaStream_t s = (cudaStream_t)stream;
+    ANQS_CUDA(cudaFuncSetAttribute(made_phase_output_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PO_SMEM));
+    made_phase_output_kernel<<<grid, PO_WARPS * 32, PO_SMEM, s>>>(*desc, d_idx, n, (const double2 *)d_grad_out, d_h_last, (double *)d_work);
+    ANQS_LAUNCH_CHECK();
+    const int total = desc->qudit_num * PO_TILE;
+    made_phase_output_finish_kernel<<<(total + 255) / 256, 256, 0, s>>>((const double *)d_work, grid, desc->qudit_num, desc->max_qudit_dim,
+                                                                        accumulate, d_gW, d_gb);
     ANQS_LAUNCH_CHECK();
     return 0;
 }

@@ -124,11 +124,12 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
         // probabilities = softmax(2 * logits), nan -> 0 (ANQS:560-561)
         const double l0 = lane < D ? 2.0 * cond[b * DM + lane] : -INFINITY;
         const double l1 = lane + 32 < D ? 2.0 * cond[b * DM + lane + 32] : -INFINITY;
-        const double mx = warp_max(fmax(l0, l1));
-        double e0 = lane < D ? exp(l0 - mx) : 0.0, e1 = lane + 32 < D ? exp(l1 - mx) : 0.0;
-        if (!(mx > -INFINITY)) e0 = e1 = 0.0;
-        double p0 = e0, p1 = e1;   // random mode: unnormalised weights do (every use below is a ratio of partial sums)
+        double p0, p1;
+        float w0 = 0.0f, w1 = 0.0f;
         if (draw_mode == 0) {
+            const double mx = warp_max(fmax(l0, l1));
+            double e0 = lane < D ? exp(l0 - mx) : 0.0, e1 = lane + 32 < D ? exp(l1 - mx) : 0.0;
+            if (!(mx > -INFINITY)) e0 = e1 = 0.0;
             const double sum = warp_sum(e0 + e1);
             p0 = e0 / sum, p1 = e1 / sum;
             if (!(sum > 0.0)) p0 = p1 = 0.0;
@@ -136,6 +137,19 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
             cum[1 + lane] = p0;
             cum[33 + lane] = p1;
             __syncwarp();
+        } else {
+            // random draws: unnormalised weights with a single-precision exponential do (every use below is a ratio of partial
+            // sums, and an unbiased relative error of 1e-7 per weight is far below anything 10^6..10^9 draws can resolve); the
+            // shift is taken in double, so the weights do not inherit the rounding of the logits' magnitude, and the partial
+            // sums are accumulated in double (single-precision sums fail the chi-square test at 10^7 samples: cancellation)
+            float mf = (float)fmax(l0, l1);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mf = fmaxf(mf, __shfl_xor_sync(0xffffffffu, mf, d));
+            if (mf > -INFINITY) {
+                w0 = lane < D ? __expf((float)(l0 - (double)mf)) : 0.0f;
+                w1 = lane + 32 < D ? __expf((float)(l1 - (double)mf)) : 0.0f;
+            }
+            p0 = w0, p1 = w1;
         }
         double cnt = counts[b];  // count of tree node `lane` (valid for lane < 2^j in round j)
         double c_even = 0.0, c_odd = 0.0;
@@ -148,7 +162,8 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
                     cum[d] = acc;
                 }
             }
-        } else {              // random draws: any summation order is as good, take the warp scan
+        } else {              // random draws: any summation order is as good, take the warp scan (in double: the draws below
+                              // take differences of these partial sums)
             double s0 = p0, s1 = p1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {

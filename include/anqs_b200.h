@@ -236,6 +236,20 @@ int anqs_made_cond_log_abs(const anqs_made_desc_t *desc, int qudit_idx, const in
 int anqs_made_backward_chain(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
                              const double *d_save_h, const double *d_save_p, double *d_dY, double *d_da, double *d_x,
                              void *stream);
+/* The same chain without the phase network's half of d_dY: d_dY_abs[n][qudit_num * max_qudit_dim] is the log-abs
+ * network's output-layer gradient only.  The phase network's output-layer gradient has one non-zero per sample and qudit
+ * (arg psi = pi * sum_q y[q, chosen_q], LAP:97, ANQS:450-454), so its weight / bias gradient
+ *   d_gW[qudit_num * max_qudit_dim][width] (+)= sum_s pi g_s.im h_s   into row  q * max_qudit_dim + chosen_q(s),   d_gb likewise,
+ * is a row scatter (anqs_made_phase_output_grad; d_h_last[n][width] = the phase network's last hidden activations, i.e.
+ * d_save_h[1][depth - 1]) instead of a dense product with 63/64 zeros.  Deterministic (fixed summation order);
+ * d_work: anqs_made_phase_output_workspace(desc) bytes; d_gb may be null. */
+int anqs_made_backward_chain_abs(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                                 const double *d_save_h, const double *d_save_p, double *d_dY_abs, double *d_da, double *d_x,
+                                 void *stream);
+int64_t anqs_made_phase_output_workspace(const anqs_made_desc_t *desc);
+int anqs_made_phase_output_grad(const anqs_made_desc_t *desc, const int64_t *d_idx, int64_t n, const double *d_grad_out,
+                                const double *d_h_last, int accumulate, double *d_gW, double *d_gb, void *d_work,
+                                int64_t work_bytes, void *stream);
 
 /* ---- A9  kernel 3, NADE mode (ANQS:410-428, LAP:24-42): one (log-abs, phase) MLP pair per qudit --------------------------
  * Same scalar fields as anqs_made_desc_t.  d_ptrs is a DEVICE array of 2 * qudit_num * (depth + 1) * 2 device pointers:
