@@ -120,10 +120,31 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *cum = cum_all[warp];
     const int D = 1 << k;
-    for (int64_t b = (int64_t)blockIdx.x * K4_WARPS + warp; b < B; b += (int64_t)gridDim.x * K4_WARPS) {
+    // The inputs of parent b + stride are loaded while parent b is processed (a warp walks its parents one after the other and
+    // every one of them starts with dependent loads: without this the kernel waits on memory for half of its time).
+    const int64_t stride = (int64_t)gridDim.x * K4_WARPS;
+    int64_t b = (int64_t)blockIdx.x * K4_WARPS + warp;
+    double n_c0 = 0.0, n_c1 = 0.0, n_cnt = 0.0;
+    int n_mi = -1;
+    uint64_t n_key = 0;
+    auto load_inputs = [&](int64_t bb) {
+        n_c0 = lane < D ? cond[bb * DM + lane] : 0.0;
+        n_c1 = lane + 32 < D ? cond[bb * DM + lane + 32] : 0.0;
+        n_cnt = counts[bb];
+        n_mi = memo_idx[bb];
+        n_key = rng_keys ? (uint64_t)rng_keys[bb] : (uint64_t)(parent_offset + bb);
+    };
+    if (b < B) load_inputs(b);
+    for (; b < B; b += stride) {
+        const double c0 = n_c0, c1 = n_c1, cnt_in = n_cnt;
+        const int mi = n_mi;
+        const uint64_t parent = n_key;
+        unsigned long long mw = 0ull;
+        if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];   // needed at the end of the iteration only
+        if (b + stride < B) load_inputs(b + stride);
         // probabilities = softmax(2 * logits), nan -> 0 (ANQS:560-561)
-        const double l0 = lane < D ? 2.0 * cond[b * DM + lane] : -INFINITY;
-        const double l1 = lane + 32 < D ? 2.0 * cond[b * DM + lane + 32] : -INFINITY;
+        const double l0 = lane < D ? 2.0 * c0 : -INFINITY;
+        const double l1 = lane + 32 < D ? 2.0 * c1 : -INFINITY;
         double p0, p1;
         float w0 = 0.0f, w1 = 0.0f;
         if (draw_mode == 0) {
@@ -151,7 +172,7 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
             }
             p0 = w0, p1 = w1;
         }
-        double cnt = counts[b];  // count of tree node `lane` (valid for lane < 2^j in round j)
+        double cnt = cnt_in;     // count of tree node `lane` (valid for lane < 2^j in round j)
         double c_even = 0.0, c_odd = 0.0;
         if (draw_mode == 0) {
             if (lane == 0) {  // sequential prefix sum, like a cumsum along the row (ANQS:562-565): the order the goldens were made with
@@ -181,7 +202,6 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
         if (single) {
             // a multinomial with one trial is one categorical draw: invert the cumulative distribution with one uniform
             // instead of walking the binomial tree with k of them (most nodes of a deep level carry a single sample)
-            const uint64_t parent = rng_keys ? (uint64_t)rng_keys[b] : (uint64_t)(parent_offset + b);
             Philox g(seed, (uint32_t)parent, (uint32_t)(parent >> 32), ((uint32_t)level << 16) | 0xFF00u, 0u);
             const uint4 r = g();
             const double t = u01(r.x, r.y) * cum[D];
@@ -210,7 +230,6 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
                 } else {
                     // key of the node: its packed prefix when given (independent of how nodes are spread over launches,
                     // ranks or GPUs), else its position
-                    const uint64_t parent = rng_keys ? (uint64_t)rng_keys[b] : (uint64_t)(parent_offset + b);
                     left = binomial_draw(cnt, pr, seed, (uint32_t)parent, (uint32_t)(parent >> 32),
                                          ((uint32_t)level << 16) | ((uint32_t)j << 8) | (uint32_t)lane);
                 }
@@ -225,9 +244,6 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
             }
         }
         const int half = D >> 1;
-        unsigned long long mw = 0ull;
-        const int mi = memo_idx[b];
-        if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];
         const bool s_even = lane < half && ((mw >> (2 * lane)) & 1ull) && c_even > 0.0;
         const bool s_odd = lane < half && ((mw >> (2 * lane + 1)) & 1ull) && c_odd > 0.0;
         const unsigned be = __ballot_sync(0xffffffffu, s_even), bo = __ballot_sync(0xffffffffu, s_odd);
