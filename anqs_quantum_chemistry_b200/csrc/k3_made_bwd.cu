@@ -180,7 +180,7 @@ made_backward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_i
 // [DM][64] (+ [DM] bias) tile in shared memory, walking the samples in order; the warps' tiles are then added in warp order
 // into the CTA's partial result, and made_phase_output_finish_kernel adds the partial results in CTA order: deterministic.
 // The hidden rows are re-read once per qudit (from L2 when the chunk fits).
-constexpr int PO_WARPS = 4, PO_TILE = 64 * 64 + 64;
+constexpr int PO_WARPS = 6, PO_TILE = 64 * 64 + 64;   // 6 x 33 KB of accumulator tiles per SM
 constexpr size_t PO_SMEM = (size_t)PO_WARPS * PO_TILE * sizeof(double);
 
 __global__ void __launch_bounds__(PO_WARPS * 32, 1)

@@ -143,6 +143,26 @@ def make_ham():
     _hilbert_case()
 
 
+def make_ham_c5():
+    # the headline Hamiltonian itself (bench.py: 56 qubits, 14 e-, 8 irreps, seed 0, all T = 114 305 terms): the reference's
+    # own sample-aware local energies of 256 sampled configurations, coupling 'ham' only (its trie / all_to_all passes over
+    # this table take tens of minutes on these cores and are covered by the smaller cases)
+    _ham_case('ham_c5_full', 56, 14, 8, 256, seed=0, keep_terms=None, store_lists=False, methods=('ham',), chunk_size=64)
+    # the inputs are regenerable (synthetic_hamiltonian(56, 8, seed 0) shuffled by default_rng(7)): keep checksums of them
+    # and of the reference's tables instead of 2.6 MB of arrays
+    path = os.path.join(GOLDEN_DIR, 'ham_c5_full.npz')
+    g = dict(np.load(path))
+    keep = {k: g[k] for k in ('qubit_num', 'particle_num', 'samples', 'amps', 'eloc_ham', 'eloc_ham_chunked', 'conn_count_per_sample',
+                              'conn_H_sum', 'conn_xprime_xor', 'conn_in_count')}
+    keep['in_checksums'] = np.array([int(np.bitwise_xor.reduce(g['in_xy'])), int(np.bitwise_xor.reduce(g['in_yz'])), int(g['in_xy'].shape[0])],
+                                    dtype=np.int64)
+    keep['in_w_sum'] = np.array([g['in_w'].sum().real, (np.abs(g['in_w']) ** 2).sum()])
+    keep['tables_checksums'] = np.array([int(np.bitwise_xor.reduce(g['unq_xy_masks'])), int(g['unq_xy_masks'].shape[0]),
+                                         int(np.bitwise_xor.reduce(g['rearranged_yz'])), int(g['unq_xy_to_yz_num'].sum())], dtype=np.int64)
+    keep['rearranged_weights_probe'] = g['rearranged_weights'][::997]
+    np.savez_compressed(path, **keep)
+
+
 # ---- wave function, masks, samplers -------------------------------------------------------------------------------
 def made_weights(n, Q, DM, depth=2, width=64, seed=0):
     """Deterministic (numpy PCG64) network weights shared by the golden generator and the tests, so that fixtures
@@ -457,7 +477,7 @@ def make_tfm():
     _tfm_case('tfm_n14', 14, 10, depth=3, head_num=2, seed=9)     # head_dim 32: the wide-head path of the kernel
 
 
-GROUPS = {'ham': make_ham, 'anqs': make_anqs, 'nade': make_nade, 'vmc': make_vmc, 'tfm': make_tfm}
+GROUPS = {'ham': make_ham, 'ham_c5': make_ham_c5, 'anqs': make_anqs, 'nade': make_nade, 'vmc': make_vmc, 'tfm': make_tfm}
 
 
 def main(argv):

@@ -83,6 +83,31 @@ def test_local_energy_matches_reference(case, tmp_path):
         assert torch.equal(w, e[lo:lo + ln])
 
 
+def test_headline_hamiltonian_matches_reference_output(tmp_path):
+    """The bench's own Hamiltonian (56 qubits, T = 114 305, U = 23 157) against output of the REFERENCE on it (golden
+    ham_c5_full: PauliObservable.compute_var_local_energy_proxy, coupling 'ham', 256 sampled configurations): tables by
+    checksum, connection counts exactly, sample-aware local energies to 1e-10 through every kernel variant."""
+    from conftest import c5_full_inputs
+    g, xy, yz, w = c5_full_inputs()
+    hs = HilbertSpace(qubit_num=56, device=DEV, parent_dir=str(tmp_path), rng_seed=0)
+    ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, 56))
+    tc = g['tables_checksums']
+    assert ham.unq_xy_masks_num == int(tc[1]) and int(ham.unq_xy_to_yz_num.sum()) == int(tc[3])
+    assert int(np.bitwise_xor.reduce(ham.unq_xy_masks.cpu().numpy().reshape(-1))) == int(tc[0])
+    assert int(np.bitwise_xor.reduce(ham.rearranged_yz.cpu().numpy().reshape(-1))) == int(tc[2])
+    np.testing.assert_array_equal(ham.rearranged_weights.cpu().numpy()[::997], g['rearranged_weights_probe'])
+    s, a = _dev(g['samples']).view(-1, 1), _dev(g['amps'])
+    conn = ham.connected_configurations(_dev(g['samples']), 7, 7, matrix_elements='complex')
+    np.testing.assert_array_equal(np.bincount(conn['dest'].cpu().numpy(), minlength=s.shape[0]), g['conn_count_per_sample'])
+    assert int(np.bitwise_xor.reduce(conn['xprime'].cpu().numpy().reshape(-1))) == int(g['conn_xprime_xor'])
+    assert abs(complex(conn['H'].sum().item()) - complex(g['conn_H_sum'])) < 1e-8
+    scale = max(1.0, np.abs(g['eloc_ham']).max())
+    for variant in (0, 1, 2, 3):   # chosen by size, warp-per-sample, bit-sliced, pair-join
+        e = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
+                                               alpha_num=7, beta_num=7, kernel_variant=variant)[0]
+        assert np.abs(e.cpu().numpy() - g['eloc_ham']).max() < 1e-10 * scale, variant
+
+
 @pytest.mark.parametrize('case', HAM_CASES_WITH_LISTS)
 def test_reference_method_surface(case, tmp_path):
     """find_sampled_and_coupled_via_ham (PO:569-600) and compute_matrix_elements (PO:255-324)."""
