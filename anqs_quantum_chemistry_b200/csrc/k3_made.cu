@@ -192,11 +192,24 @@ made_forward_kernel(const anqs_made_desc_t P, const int64_t *__restrict__ idx_in
                 for (int q = g; q < Q; q += 4) {
                     const int start = P.qudit_starts[q], bits = P.qudit_starts[q + 1] - start;
                     const int row = q * DM + (int)((x >> start) & ((1ull << bits) - 1ull));
-                    const double *w = Ws[depth] + (size_t)row * MD_W;
-                    double dot = bs[depth] ? __ldg(bs[depth] + row) : 0.0;
-#pragma unroll 8
-                    for (int k = 0; k < MD_W; ++k) dot = fma(__ldg(w + k), cur[k * MD_S + s], dot);
-                    part += dot;
+                    // the row is 512 contiguous bytes: 16-byte loads (every 32-byte sector is used up by two instructions), eight
+                    // of them issued before the first use, four partial sums instead of one dependent chain
+                    const double2 *w = reinterpret_cast<const double2 *>(Ws[depth] + (size_t)row * MD_W);
+                    double d0 = bs[depth] ? __ldg(bs[depth] + row) : 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+                    for (int k0 = 0; k0 < MD_W; k0 += 16) {
+                        double2 v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __ldg(w + (k0 >> 1) + i);
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2) {
+                            d0 = fma(v[i].x, cur[(k0 + 2 * i) * MD_S + s], d0);
+                            d1 = fma(v[i].y, cur[(k0 + 2 * i + 1) * MD_S + s], d1);
+                            d2 = fma(v[i + 1].x, cur[(k0 + 2 * i + 2) * MD_S + s], d2);
+                            d3 = fma(v[i + 1].y, cur[(k0 + 2 * i + 3) * MD_S + s], d3);
+                        }
+                    }
+                    part += (d0 + d1) + (d2 + d3);
                 }
                 s_im[g * 64 + s] = part;
                 __syncthreads();

@@ -200,7 +200,7 @@ def vmc_iteration_rate(dev, n=20, n_el=14, sample_num=10 ** 4, iters=20, with_sr
             'note': 'reference on 8 CPU threads: 0.17 it/s (MADE, ham) to 0.37 it/s (NADE, trie) at this size, incl. SR (BASELINE.md section 2)'}
 
 
-def vmc_iteration_c5(ham, wf, dev, n_el, sample_num=10 ** 6, iters=5):
+def vmc_iteration_c5(ham, wf, dev, n_el, sample_num=10 ** 6, iters=7):
     """VMC iterations/s on the C5 shape itself (this GPU only; scripts/bench_vmc_sharded.py shards the same iteration over
     1/2/4/8 GPUs): count-splitting sampler of 1e6 samples (tf32 conditionals) -> float64 amplitudes with the graph ->
     sample-aware local energy -> loss EXP:609 -> float64 backward -> Adam."""
@@ -218,22 +218,25 @@ def vmc_iteration_c5(ham, wf, dev, n_el, sample_num=10 ** 6, iters=5):
         mean, _, _ = step(idx)
         opt.step()
         return idx.shape[0], mean
-    for it in range(2):
+    for it in range(3):   # the first iterations size the allocator's pools and the sampler's level capacities
         one_iter(it)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    marks[0].record()
     for it in range(iters):
-        n_unq, mean = one_iter(2 + it)
-    e1.record()
+        n_unq, mean = one_iter(3 + it)
+        marks[it + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    per_iter = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(iters))
+    ms_mean = marks[0].elapsed_time(marks[iters]) / iters
+    ms = per_iter[iters // 2]   # median: one iteration in ~20 pays an allocator refill (59 -> 68 ms), short runs should not hinge on it
     wf.set_inference_precision(prec)
     for p_ in wf.parameters():
         p_.grad = None
-    return {'iters_per_s': 1e3 / ms, 'ms_per_iter': ms, 'samples': sample_num, 'n_unq_last': int(n_unq), 'qubits': int(wf.qubit_num),
+    return {'iters_per_s': 1e3 / ms, 'ms_per_iter': ms, 'ms_per_iter_mean': ms_mean, 'timing': f'median of {iters} device-timed iterations after 3 warm-up',
+            'samples': sample_num, 'n_unq_last': int(n_unq), 'qubits': int(wf.qubit_num),
             'sampler': 'count splitting (ANQS:494-525), tf32 conditionals', 'gradient': 'float64', 'energy_last': float(mean.real),
-            'multi_gpu': 'profiles/r1_vmc_c5_{1,2,4,8}gpu.json (scripts/bench_vmc_sharded.py)'}
+            'multi_gpu': 'profiles/r2_vmc_c5_{1,2,4,8}gpu.json (scripts/bench_vmc_sharded.py)'}
 
 
 def secondary_measurements(ham, hs, d_idx, na, nb, dev):

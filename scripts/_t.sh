@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_hamiltonian.py -x -q -k "headline" 2>&1 | tail -5
 timeout 900 python -m pytest tests/test_gpu_anqs.py -x -q 2>&1 | tail -2
-timeout 300 python scripts/vmc_c5_phases.py 1048576 MADE 2>&1 | grep "rows\|made_backward\|batch_reduce_gemm\|phase_output" | cut -c1-220
+timeout 300 python scripts/vmc_c5_phases.py 1048576 MADE 2>&1 | grep "rows\|anqs::" | cut -c1-250

@@ -85,6 +85,8 @@ barrier()
 for marks in all_marks:
     for k in range(3):
         phase[k] += marks[k].elapsed_time(marks[k + 1])
+if rank == 0:
+    print('per-iteration ms (rank 0):', ' '.join(f'{m[0].elapsed_time(m[3]):.1f}' for m in all_marks), file=sys.stderr, flush=True)
 t = torch.tensor([start.elapsed_time(stop)] + (phase / args.steps).tolist() + [0.0], dtype=torch.float64, device=dev)
 r = torch.tensor([float(rows)], dtype=torch.float64, device=dev)
 if world > 1:
