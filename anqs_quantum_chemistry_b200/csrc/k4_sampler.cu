@@ -115,15 +115,18 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
                    const int32_t *__restrict__ memo_idx, const unsigned long long *__restrict__ cont_mask_q,
                    int64_t memo_size, int64_t B, int level, int draw_mode, uint64_t seed, int64_t parent_offset,
                    const int64_t *__restrict__ rng_keys, double *__restrict__ child_counts, int64_t *__restrict__ n_children,
-                   signed char *__restrict__ single_out) {
+                   signed char *__restrict__ single_out, int skip_singles, int block_shift) {
     __shared__ double cum_all[K4_WARPS][66];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *cum = cum_all[warp];
     const int D = 1 << k;
-    // The inputs of parent b + stride are loaded while parent b is processed (a warp walks its parents one after the other and
-    // every one of them starts with dependent loads: without this the kernel waits on memory for half of its time).
-    const int64_t stride = (int64_t)gridDim.x * K4_WARPS;
-    int64_t b = (int64_t)blockIdx.x * K4_WARPS + warp;
+    // A warp takes blocks of 32 parents, looks at their counts at once and walks the ones it has to process (all of them, or -
+    // skip_singles - those that carry more than one sample: split_single_kernel took the others).  The inputs of the next
+    // parent of the walk are loaded while the current one is processed (every parent starts with dependent loads: without
+    // this the kernel waits on memory for half of its time).
+    // blocks of 2^block_shift <= 32 parents: small levels keep one parent per warp (all warps busy), large ones 32
+    const int bw = 1 << block_shift;
+    const int64_t nblocks = (B + bw - 1) >> block_shift;
     double n_c0 = 0.0, n_c1 = 0.0, n_cnt = 0.0;
     int n_mi = -1;
     uint64_t n_key = 0;
@@ -134,14 +137,21 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
         n_mi = memo_idx[bb];
         n_key = rng_keys ? (uint64_t)rng_keys[bb] : (uint64_t)(parent_offset + bb);
     };
-    if (b < B) load_inputs(b);
-    for (; b < B; b += stride) {
+    for (int64_t blk = (int64_t)blockIdx.x * K4_WARPS + warp; blk < nblocks; blk += (int64_t)gridDim.x * K4_WARPS) {
+    const int64_t b0 = blk << block_shift;
+    const bool in_range = lane < bw && b0 + lane < B;
+    const double cnt_lane = in_range ? counts[b0 + lane] : 0.0;
+    unsigned todo = __ballot_sync(0xffffffffu, in_range && !(skip_singles && cnt_lane == 1.0));
+    if (todo) load_inputs(b0 + (__ffs(todo) - 1));
+    while (todo) {
+        const int64_t b = b0 + (__ffs(todo) - 1);
+        todo &= todo - 1;
         const double c0 = n_c0, c1 = n_c1, cnt_in = n_cnt;
         const int mi = n_mi;
         const uint64_t parent = n_key;
         unsigned long long mw = 0ull;
         if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];   // needed at the end of the iteration only
-        if (b + stride < B) load_inputs(b + stride);
+        if (todo) load_inputs(b0 + (__ffs(todo) - 1));
         // probabilities = softmax(2 * logits), nan -> 0 (ANQS:560-561)
         const double l0 = lane < D ? 2.0 * c0 : -INFINITY;
         const double l1 = lane + 32 < D ? 2.0 * c1 : -INFINITY;
@@ -258,6 +268,86 @@ split_level_kernel(const double *__restrict__ cond, int DM, int k, const double 
             if (single_out != nullptr && lane == 0) single_out[b] = (signed char)-2;
         }
         if (lane == 0) n_children[b] = __popc(be) + __popc(bo);
+    }
+    }
+}
+
+// Parents that carry ONE sample - nearly all nodes of the deep levels of a large sparse batch - need one categorical draw, and a
+// warp per parent spends ~450 instructions on it (shuffle reductions, a scan, ballots, all for one number).  Here a LANE owns
+// a parent: a warp stages the 32 conditional rows of its parents in shared memory with coalesced loads (row stride D + 1:
+// conflict-free per-lane walks), each lane then walks its own row three times - maximum, total weight, first outcome whose
+// running sum passes u * total - with single-precision exponentials, the shift and the sums in double.  Same generator, same
+// key (the parent's packed prefix or position) and the same inversion rule as the single-sample branch of
+// split_level_kernel, so a parent's draw does not depend on which launch, rank or GPU processes it.  Parents with another
+// count are left to split_level_kernel (skip_singles).
+constexpr int SS_WARPS = 2;   // 33 KB of staged rows per CTA: six CTAs per SM
+__global__ void __launch_bounds__(SS_WARPS * 32)
+split_single_kernel(const double *__restrict__ cond, int DM, int k, const double *__restrict__ counts,
+                    const int32_t *__restrict__ memo_idx, const unsigned long long *__restrict__ cont_mask_q, int64_t memo_size,
+                    int64_t B, int level, uint64_t seed, int64_t parent_offset, const int64_t *__restrict__ rng_keys,
+                    int64_t *__restrict__ n_children, signed char *__restrict__ single_out) {
+    __shared__ double rows_all[SS_WARPS][32 * 65];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *rows = rows_all[warp];
+    const int D = 1 << k;
+    const int64_t nblocks = (B + 31) >> 5;
+    for (int64_t blk = (int64_t)blockIdx.x * SS_WARPS + warp; blk < nblocks; blk += (int64_t)gridDim.x * SS_WARPS) {
+        const int64_t b0 = blk << 5, b = b0 + lane;
+        const bool mine = b < B && counts[b] == 1.0;
+        const unsigned any = __ballot_sync(0xffffffffu, mine);
+        if (!any) continue;
+        // stage the rows of the block's single-sample parents: one coalesced 8 D-byte row per step, eight steps in flight
+        __syncwarp();
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+            double v0[8], v1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool want = (any >> (r0 + i)) & 1u;
+                v0[i] = (want && lane < D) ? cond[(b0 + r0 + i) * DM + lane] : 0.0;
+                v1[i] = (want && lane + 32 < D) ? cond[(b0 + r0 + i) * DM + lane + 32] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                rows[(r0 + i) * 65 + lane] = v0[i];
+                rows[(r0 + i) * 65 + 32 + lane] = v1[i];
+            }
+        }
+        __syncwarp();
+        if (mine) {
+            const double *row = rows + lane * 65;
+            const int mi = memo_idx[b];
+            unsigned long long mw = 0ull;
+            if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];
+            const uint64_t parent = rng_keys ? (uint64_t)rng_keys[b] : (uint64_t)(parent_offset + b);
+            double mx = -INFINITY;
+            for (int d = 0; d < D; ++d) mx = fmax(mx, row[d]);
+            int pick = D - 1;
+            if (mx > -INFINITY) {
+                const float mf = (float)(2.0 * mx);
+                double total = 0.0;
+                int last_pos = -1;
+                for (int d = 0; d < D; ++d) {
+                    const float w = __expf((float)(2.0 * row[d] - (double)mf));   // exp(-inf) = 0 for masked outcomes
+                    total += (double)w;
+                    if (w > 0.0f) last_pos = d;
+                }
+                Philox g(seed, (uint32_t)parent, (uint32_t)(parent >> 32), ((uint32_t)level << 16) | 0xFF00u, 0u);
+                const uint4 r = g();
+                const double t = u01(r.x, r.y) * total;
+                double cum = 0.0;
+                pick = last_pos >= 0 ? last_pos : D - 1;   // rounding at the upper end: the last outcome of non-zero weight
+                for (int d = 0; d < D; ++d) {
+                    cum += (double)__expf((float)(2.0 * row[d] - (double)mf));
+                    if (cum > t) {
+                        pick = d;
+                        break;
+                    }
+                }
+            }
+            const bool allowed = (mw >> pick) & 1ull;
+            single_out[b] = allowed ? (signed char)pick : (signed char)-1;
+            n_children[b] = allowed ? 1 : 0;
+        }
     }
 }
 
@@ -424,10 +514,25 @@ int anqs_sampler_split_level(const double *d_cond, int max_qudit_dim, int qubits
     ANQS_REQUIRE(draw_mode == 0 || draw_mode == 1, "draw_mode must be 0 (rounded mean) or 1 (Philox binomial)");
     if (n == 0) return 0;
     ANQS_REQUIRE(d_cond && d_counts && d_memo_idx && d_cont_mask_q && d_child_counts && d_n_children, "null pointer");
-    int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
+    // parents per warp block: as many as keeps every warp of the chip with at least one block, at most 32
+    const int64_t warps = (int64_t)sm_count_of_current_device() * 8 * K4_WARPS;
+    int block_shift = 0;
+    while (block_shift < 5 && (n >> (block_shift + 1)) >= warps) ++block_shift;
+    const int64_t nblk = (n + (1 << block_shift) - 1) >> block_shift;
+    int grid = (int)std::min<int64_t>((nblk + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
+    // random draws with the one-byte hand-over: single-sample parents go through the lane-per-parent kernel
+    const int skip_singles = draw_mode != 0 && d_single != nullptr;
+    if (skip_singles) {
+        const int64_t nblocks = (n + 31) / 32;
+        const int g1 = (int)std::min<int64_t>((nblocks + SS_WARPS - 1) / SS_WARPS, (int64_t)sm_count_of_current_device() * 24);
+        split_single_kernel<<<g1, SS_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            d_cond, max_qudit_dim, qubits_in_qudit, d_counts, d_memo_idx, (const unsigned long long *)d_cont_mask_q, memo_size, n, level, seed,
+            parent_offset, d_rng_keys, d_n_children, (signed char *)d_single);
+        ANQS_LAUNCH_CHECK();
+    }
     split_level_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d_cond, max_qudit_dim, qubits_in_qudit, d_counts, d_memo_idx, (const unsigned long long *)d_cont_mask_q, memo_size, n,
-        level, draw_mode, seed, parent_offset, d_rng_keys, d_child_counts, d_n_children, (signed char *)d_single);
+        level, draw_mode, seed, parent_offset, d_rng_keys, d_child_counts, d_n_children, (signed char *)d_single, skip_singles, block_shift);
     ANQS_LAUNCH_CHECK();
     return 0;
 }
