@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_anqs.py -x -q 2>&1 | tail -2
-timeout 300 python scripts/vmc_c5_phases.py 1048576 MADE 2>&1 | grep "rows\|anqs::" | cut -c1-250
+timeout 900 python -m pytest tests/test_gpu_hamiltonian.py tests/test_gpu_vmc.py -x -q 2>&1 | tail -3
+timeout 600 python scripts/bench_vmc_sharded.py --steps 20 2>&1 | grep "per-iteration\|vmc_iterations" | cut -c1-700

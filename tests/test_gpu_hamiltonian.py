@@ -72,6 +72,15 @@ def test_local_energy_matches_reference(case, tmp_path):
     with pytest.raises(NotImplementedError):
         ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='hamming_ball',
                                            alpha_num=na, beta_num=nb)
+    # rows walked in the strided order (what large batches do by default), whole batch and a window of it
+    e_s = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
+                                             alpha_num=na, beta_num=nb, row_order='strided')[0]
+    assert np.abs(e_s.cpu().numpy() - g['eloc_ham']).max() < 1e-10 * scale
+    if s.shape[0] >= 6:
+        lo_s, ln_s = s.shape[0] // 3, s.shape[0] // 2
+        w_s = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham', alpha_num=na,
+                                                 beta_num=nb, row_start=lo_s, row_len=ln_s, row_order='strided')[0]
+        assert np.abs(w_s.cpu().numpy() - g['eloc_ham'][lo_s:lo_s + ln_s]).max() < 1e-10 * scale
     # a window of rows (the multi-GPU shard path) equals the same rows of the full evaluation
     n = s.shape[0]
     lo, ln = n // 3, n // 2
