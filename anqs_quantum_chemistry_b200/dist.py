@@ -201,3 +201,19 @@ def sharded_sample_stats(wf, sample_num: int, seed: int, world_size: int = None,
         g_idx, g_cnt, _, _ = all_gather_shards(prefix, pt.complex(counts, pt.zeros_like(counts)), group)
         return g_idx.view(-1, 1), g_cnt
     return prefix.view(-1, 1), counts.to(pt.complex128)
+
+
+def reserve_device_memory(device, nbytes: int = None, headroom: float = 1.6) -> int:
+    """Puts ONE block of `nbytes` (default: `headroom` x the peak allocation so far) into torch's caching allocator, so that the
+    iterations that follow carve their tensors out of it instead of calling cudaMalloc.  Batch sizes drift from one VMC
+    iteration to the next (the number of unique samples; each rank's share of them), and every new maximum is a cudaMalloc;
+    with peer access enabled (any NCCL job) one such call was measured at 20 - 160 ms on 4 B200s, against 17 ms for the
+    whole iteration.  Call it once after a warm-up iteration; returns the number of bytes reserved."""
+    dev = pt.device(device)
+    if nbytes is None:
+        nbytes = int(headroom * pt.cuda.max_memory_allocated(dev))
+    pt.cuda.synchronize(dev)
+    pt.cuda.empty_cache()
+    block = pt.empty(int(nbytes), dtype=pt.uint8, device=dev)
+    del block
+    return int(nbytes)

@@ -18,6 +18,11 @@ inputs and the E_loc vector read back, copies inside the timed region.
 import argparse
 import json
 import os
+# Batch sizes drift from one VMC iteration to the next (the number of unique samples, each rank's share of them): without size
+# classes the caching allocator meets a slightly larger request every few iterations, cannot reuse the cached block and
+# calls cudaMalloc again - measured on 4 GPUs: one rank grew from 7 to 15 GiB reserved in ten iterations and single
+# iterations took 35-195 ms instead of 18.  Must be set before the first CUDA allocation.
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'roundup_power2_divisions:8')
 import subprocess
 import sys
 import tempfile
@@ -220,6 +225,8 @@ def vmc_iteration_c5(ham, wf, dev, n_el, sample_num=10 ** 6, iters=7):
         return idx.shape[0], mean
     for it in range(3):   # the first iterations size the allocator's pools and the sampler's level capacities
         one_iter(it)
+        if it == 0:
+            adist.reserve_device_memory(dev)
     torch.cuda.synchronize()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
     marks[0].record()
@@ -556,7 +563,7 @@ class GpuEngine:
                                            _lib.stream_ptr(self.device)))
         return float(counts.double().mean().item())
 
-    def vmc_collective(self, iters=5, warm=2, sample_num=10 ** 6):
+    def vmc_collective(self, iters=7, warm=3, sample_num=10 ** 6):
         """ALL ranks, inside the live process group: VMC iterations/s (the second half of BASELINE.json's metric) on the C5 shape
         with the whole iteration sharded over the ranks - sub-tree sharded count-splitting sampler of 1e6 samples, float64
         amplitudes of the local rows, all-gather of (index, amplitude), sample-aware local energies of the local rows, all-reduce
@@ -583,6 +590,8 @@ class GpuEngine:
             return idx.shape[0], mean
         for it in range(warm):
             one_iter(it)
+            if it == 0:
+                adist.reserve_device_memory(dev)   # no cudaMalloc in the iterations that follow (dist.py)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

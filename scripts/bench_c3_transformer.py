@@ -1,6 +1,11 @@
 """BASELINE config 3 (C3): 20 qubits, 14 electrons, dense synthetic H, transformer wave function (dim 64, depth 2, 4 heads) with
 particle-number / S_z masks: amplitudes/s of the hand-written kernel, unique samples/s of both samplers, VMC iterations/s."""
 import sys, os, tempfile, time, json
+# Batch sizes drift from one VMC iteration to the next (the number of unique samples, each rank's share of them): without size
+# classes the caching allocator meets a slightly larger request every few iterations, cannot reuse the cached block and
+# calls cudaMalloc again - measured on 4 GPUs: one rank grew from 7 to 15 GiB reserved in ten iterations and single
+# iterations took 35-195 ms instead of 18.  Must be set before the first CUDA allocation.
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'roundup_power2_divisions:8')
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from anqs_quantum_chemistry_b200 import (HilbertSpace, PauliObservable, PauliArraysOperator, ParticleNumberSymmetry, SpinHalfProjectionSymmetry,

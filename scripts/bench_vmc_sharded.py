@@ -9,6 +9,11 @@ Adam step (replicated parameters).  Strong scaling: the number of samples per it
 
 One JSON line on rank 0; times are CUDA-event times, max over ranks."""
 import argparse, json, os, sys, tempfile
+# Batch sizes drift from one VMC iteration to the next (the number of unique samples, each rank's share of them): without size
+# classes the caching allocator meets a slightly larger request every few iterations, cannot reuse the cached block and
+# calls cudaMalloc again - measured on 4 GPUs: one rank grew from 7 to 15 GiB reserved in ten iterations and single
+# iterations took 35-195 ms instead of 18.  Must be set before the first CUDA allocation.
+os.environ.setdefault('PYTORCH_CUDA_ALLOC_CONF', 'roundup_power2_divisions:8')
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
@@ -70,6 +75,8 @@ def iteration(it, marks=None):
 
 for it in range(args.warmup):
     iteration(it)
+    if it == 0:
+        adist.reserve_device_memory(dev)   # no cudaMalloc in the iterations that follow (dist.py)
 barrier()
 start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 phase = torch.zeros(3, dtype=torch.float64)
@@ -80,6 +87,12 @@ for it in range(args.steps):
     n_rows, mean = iteration(args.warmup + it, marks)
     all_marks.append(marks)
     rows += n_rows
+    if os.environ.get('ANQS_ALLOC_TRACE'):
+        torch.cuda.synchronize()
+        st = torch.cuda.memory_stats()
+        print(f"rank {rank} iteration {it}: rows {n_rows} sampler {marks[0].elapsed_time(marks[1]):.1f} ms step {marks[1].elapsed_time(marks[2]):.1f} ms "
+              f"cudaMalloc {st.get('num_device_alloc')} cudaFree {st.get('num_device_free')} retries {st.get('num_alloc_retries')} "
+              f"reserved {st.get('reserved_bytes.all.current', 0) / 2**30:.2f} GiB", file=sys.stderr, flush=True)
 stop.record()
 barrier()
 for marks in all_marks:
