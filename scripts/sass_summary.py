@@ -8,7 +8,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, 'anqs_quantum_chemistry_b200', 'libanqs_b200.so')
 MNEMONICS = ['UTCHMMA', 'UTCQMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTCCP', 'UBLKCP', 'UTMALDG', 'UTMASTG', 'SYNCS', 'MATCH', 'REDUX', 'POPC',
-             'DFMA', 'DADD', 'LDS', 'STS', 'LDG', 'STG', 'ATOMG', 'ATOMS', 'SHFL', 'VOTE', 'BAR']
+             'DMMA', 'DFMA', 'DADD', 'LDS', 'STS', 'LDG', 'STG', 'ATOMG', 'ATOMS', 'SHFL', 'VOTE', 'BAR']
 out = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
 arch = sorted(set(re.findall(r'arch = (sm_\w+)', out)))
 kern, counts, total = None, collections.OrderedDict(), collections.Counter()
@@ -28,6 +28,7 @@ for line in out.splitlines():
                 counts[kern][mn] += 1
                 total[mn] += 1
 print(f'# SASS summary of {os.path.relpath(so, ROOT)} (cuobjdump -sass; architectures in the fatbin: {", ".join(arch)})')
+print('# mma.sync.m8n8k4.f64 -> DMMA (FP64 tensor-core path of the float64 network kernels);')
 print('# tcgen05.mma -> UTCHMMA (tf32/f16 kinds), tcgen05.ld -> LDTM, tcgen05.commit / mbarrier -> UTCBAR / SYNCS, cp.async.bulk -> UBLKCP,')
 print('# __match_any_sync -> MATCH, __reduce_*_sync -> REDUX.  Counts are static instruction counts per kernel (all template instances summed).')
 used = [mn for mn in MNEMONICS if total[mn]]
