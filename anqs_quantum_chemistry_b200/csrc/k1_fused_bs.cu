@@ -42,7 +42,7 @@ struct __align__(16) FbSlot {   // one group of 32 samples (shared memory)
     uint32_t Xa[34], Xb[34];    // slices of the alpha / beta halves; [32] = all zeros, [33] = all ones
     uint2 hs[32];               // per sample: {line hash, probe constants (offset part | bit part << 16)}
     uint32_t xa[32], xb[32];
-    double acc[64];             // (re, im) of sum H psi(x') per sample
+    double acc[64];             // (re, im) of sum H psi(x') per sample: the PRIVATE accumulator of the warp with this slot's index
     uint32_t valid, slow, pad0, pad1;
 };
 
@@ -74,6 +74,7 @@ __device__ __forceinline__ uint32_t fb_test(uint32_t word, uint32_t hb) {
 
 struct FbWarp {
     FbSlot *sl;
+    double *wacc;   // this warp's private accumulators (slots[warp].acc): nobody else adds to them
     uint4 *q;
     int qlen;
     const uint8_t *filter;
@@ -97,14 +98,37 @@ __device__ __forceinline__ void fb_resolve(const Tables &t, const HashView &hv, 
     if (__any_sync(0xffffffffu, hit)) {
         double hr, hi;
         warp_matrix_elements<REAL>(t, hit, g, key, hr, hi);
+        // Deterministic accumulation: the contributions of a sample are added in queue order - across batches because the
+        // batches are resolved in order into accumulators only this warp writes, inside a batch because lanes that hold the
+        // same sample are summed in lane order and added by their first lane (plain adds, no atomics).
+        double vr = 0.0, vi = 0.0;
         if (hit) {
-            double *acc = w.sl->acc + 2 * e.w;
-            if (REAL) {
-                atomicAdd(acc, hr * ar);
-                atomicAdd(acc + 1, hr * ai);
-            } else {
-                atomicAdd(acc, hr * ar - hi * ai);
-                atomicAdd(acc + 1, hr * ai + hi * ar);
+            vr = REAL ? hr * ar : hr * ar - hi * ai;
+            vi = REAL ? hr * ai : hr * ai + hi * ar;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, hit ? e.w : 32u + (unsigned)lane_id());
+        const int nmax = __reduce_max_sync(0xffffffffu, hit ? __popc(peers) : 0);
+        double *acc = w.wacc + 2 * e.w;
+        if (nmax <= 1) {
+            if (hit) {
+                acc[0] += vr;
+                acc[1] += vi;
+            }
+        } else {
+            double sr = 0.0, si = 0.0;
+            unsigned m = peers;
+            for (int i = 0; i < nmax; ++i) {
+                const int src = m ? __ffs(m) - 1 : lane_id();
+                const double a = __shfl_sync(0xffffffffu, vr, src), b = __shfl_sync(0xffffffffu, vi, src);
+                if (m) {
+                    sr += a;
+                    si += b;
+                }
+                m &= m - 1;
+            }
+            if (hit && lane_id() == __ffs(peers) - 1) {
+                acc[0] += sr;
+                acc[1] += si;
             }
         }
     }
@@ -299,6 +323,7 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
     uint32_t parity = 0;
     FbWarp w;
     w.sl = slots + slot;
+    w.wacc = slots[warp].acc;
     w.q = queues + warp * FB_QCAP;
     w.filter = hv.filter;
     w.linemask = hv.linemask;
@@ -339,14 +364,14 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
             sl.hs[lane] = make_uint2(hl, fb_off(hp, w.gmask) | (fb_bits(hp) << 16));
             sl.xa[lane] = xa;
             sl.xb[lane] = xb;
-            sl.acc[2 * lane] = 0.0;
-            sl.acc[2 * lane + 1] = 0.0;
             const uint32_t valid = __ballot_sync(0xffffffffu, ok && insec), slow = __ballot_sync(0xffffffffu, ok && !insec);
             if (lane == 0) {
                 sl.valid = valid;
                 sl.slow = slow;
             }
         }
+        w.wacc[2 * lane] = 0.0;   // every warp clears its own accumulators (the previous groups' sums were taken before the barrier above)
+        w.wacc[2 * lane + 1] = 0.0;
         __syncthreads();
         w.qlen = 0;
         for (int ti = 0; ti < t.n_tiles; ++ti) {
@@ -376,21 +401,25 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
         }
         __syncthreads();  // every contribution to the accumulators of this CTA's groups has landed
         if (k == 0 && have) {
+            // the group's sums: the private accumulators of its R warps, added in warp order
+            double sr = 0.0, si = 0.0;
+            for (int kk = 0; kk < R; ++kk) {
+                sr += slots[slot * R + kk].acc[2 * lane];
+                si += slots[slot * R + kk].acc[2 * lane + 1];
+            }
             uint32_t slow = sl.slow;
             while (slow) {
                 const uint32_t s = __ffs(slow) - 1;
                 slow &= slow - 1;
                 double er, ei;
                 fb_slow_sample<REAL>(t, hv, sl.xa[s], sl.xb[s], alpha, beta, er, ei);
-                if (lane == 0) {
-                    sl.acc[2 * s] = er;
-                    sl.acc[2 * s + 1] = ei;
+                if (lane == (int)s) {
+                    sr = er;
+                    si = ei;
                 }
             }
-            __syncwarp();
             if (((sl.valid | sl.slow) >> lane) & 1u) {
                 const int64_t r = g * 32 + lane;
-                const double sr = sl.acc[2 * lane], si = sl.acc[2 * lane + 1];
                 const double2 a = amps[row_start + r];
                 const double den = a.x * a.x + a.y * a.y;
                 eloc[r] = make_double2((sr * a.x + si * a.y) / den, (si * a.x - sr * a.y) / den);

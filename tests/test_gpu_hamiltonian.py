@@ -375,6 +375,12 @@ def test_bit_sliced_local_energy_equals_per_sample_kernel(qubits, electrons, irr
     scale = max(1.0, np.abs(res[1]).max())
     assert np.abs(res[2] - res[1]).max() < 1e-11 * scale
     assert np.abs(res[0] - res[1]).max() < 1e-11 * scale
+    # the bit-sliced kernel adds a sample's contributions in a fixed order (private accumulators per warp, lane-ordered sums
+    # inside a batch of resolved hits, warps added in order): the same call gives the same bits every time
+    for _ in range(3):
+        again = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='ham',
+                                                   alpha_num=na, beta_num=nb, table=table, kernel_variant=2)[0].cpu().numpy()
+        assert np.array_equal(again, res[2])
     if samples.shape[0] <= 40000:  # the pair-join kernel (what 'trie' / 'all_to_all' run on small batches): same energies
         e_pj = ham.compute_var_local_energy_proxy(unq_batch_as_base_indices=s, unq_batch_as_amps=a, coupling_method='trie',
                                                   alpha_num=na, beta_num=nb, kernel_variant=3)[0].cpu().numpy()
