@@ -360,20 +360,17 @@ emit_children_kernel(const double *__restrict__ child_counts, int k, int start, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = lanemask_lt();
     const int D = 1 << k, half = D >> 1;
-    for (int64_t b = (int64_t)blockIdx.x * K4_WARPS + warp; b < B; b += (int64_t)gridDim.x * K4_WARPS) {
+    // a warp looks at 32 parents at once and walks those that carry a dense row of child counts; single-sample parents (their
+    // child named by one byte) are written by emit_single_kernel, a thread per parent
+    const int64_t nblocks = (B + 31) >> 5;
+    for (int64_t blk = (int64_t)blockIdx.x * K4_WARPS + warp; blk < nblocks; blk += (int64_t)gridDim.x * K4_WARPS) {
+    const int64_t b0 = blk << 5;
+    const bool in_range = b0 + lane < B;
+    unsigned todo = __ballot_sync(0xffffffffu, in_range && (single_in == nullptr || single_in[b0 + lane] == -2));
+    while (todo) {
+        const int64_t b = b0 + (__ffs(todo) - 1);
+        todo &= todo - 1;
         const int mi = memo_idx[b];
-        if (single_in != nullptr) {
-            const int sd = single_in[b];
-            if (sd != -2) {   // single-sample parent: the split already named its child
-                if (sd >= 0 && lane == 0 && offsets[b] < out_cap) {
-                    const int64_t r = offsets[b];
-                    out_prefix[r] = (int64_t)((uint64_t)prefix[b] | ((uint64_t)sd << start));
-                    out_counts[r] = 1.0;
-                    out_memo[r] = next_memo_q[(size_t)mi * D + sd];
-                }
-                continue;
-            }
-        }
         unsigned long long mw = 0ull;
         if (mi >= 0 && mi < memo_size) mw = cont_mask_q[mi];
         double c_even = 0.0, c_odd = 0.0;
@@ -401,6 +398,26 @@ emit_children_kernel(const double *__restrict__ child_counts, int k, int start, 
             out_counts[r] = c_odd;
             out_memo[r] = next_memo_q[(size_t)mi * D + d];
         }
+    }
+    }
+}
+
+// children of the single-sample parents: one thread per parent (coalesced reads of the byte, the offset, the prefix and the
+// memo index; one gathered read of the next memo index)
+__global__ void __launch_bounds__(256)
+emit_single_kernel(int k, int start, const int64_t *__restrict__ prefix, const int32_t *__restrict__ memo_idx,
+                   const int32_t *__restrict__ next_memo_q, int64_t B, const int64_t *__restrict__ offsets,
+                   const signed char *__restrict__ single_in, int64_t out_cap, int64_t *__restrict__ out_prefix,
+                   double *__restrict__ out_counts, int32_t *__restrict__ out_memo) {
+    const int D = 1 << k;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+        const int sd = single_in[b];
+        if (sd < 0) continue;   // -2: dense row (emit_children_kernel), -1: the one child is forbidden by the symmetries
+        const int64_t r = offsets[b];
+        if (r >= out_cap) continue;
+        out_prefix[r] = (int64_t)((uint64_t)prefix[b] | ((uint64_t)sd << start));
+        out_counts[r] = 1.0;
+        out_memo[r] = next_memo_q[(size_t)memo_idx[b] * D + sd];
     }
 }
 
@@ -558,11 +575,19 @@ int anqs_sampler_emit_children_capped(const double *d_child_counts, int qubits_i
     if (n == 0) return 0;
     ANQS_REQUIRE(d_child_counts && d_prefix && d_memo_idx && d_cont_mask_q && d_next_memo_q && d_offsets && d_out_prefix &&
                      d_out_counts && d_out_memo_idx, "null pointer");
-    int grid = (int)std::min<int64_t>((n + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
+    const int64_t nblk = (n + 31) / 32;
+    int grid = (int)std::min<int64_t>((nblk + K4_WARPS - 1) / K4_WARPS, (int64_t)sm_count_of_current_device() * 8);
     emit_children_kernel<<<grid, K4_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d_child_counts, qubits_in_qudit, qudit_start, d_prefix, d_memo_idx, (const unsigned long long *)d_cont_mask_q,
         d_next_memo_q, memo_size, n, d_offsets, (const signed char *)d_single, out_capacity, d_out_prefix, d_out_counts, d_out_memo_idx);
     ANQS_LAUNCH_CHECK();
+    if (d_single != nullptr) {
+        const int g1 = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 8);
+        emit_single_kernel<<<g1, 256, 0, (cudaStream_t)stream>>>(qubits_in_qudit, qudit_start, d_prefix, d_memo_idx, d_next_memo_q, n, d_offsets,
+                                                                 (const signed char *)d_single, out_capacity, d_out_prefix, d_out_counts,
+                                                                 d_out_memo_idx);
+        ANQS_LAUNCH_CHECK();
+    }
     return 0;
 }
 
