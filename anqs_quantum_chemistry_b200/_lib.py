@@ -84,6 +84,8 @@ _SIGNATURES = {
     'anqs_sampler_emit_children': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'anqs_sampler_emit_children_capped': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_sampler_gumbel_select': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'anqs_sampler_gumbel_select_masked': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp,
+                                                   _vp, _vp]),
     'anqs_sampler_gumbel_level': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, ctypes.c_uint64,
                                            _c_i64, _vp, _vp, _vp, _vp]),
     'anqs_sampler_gumbel_level_keyed': (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_int, ctypes.c_uint64,

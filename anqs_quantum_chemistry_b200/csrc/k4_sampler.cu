@@ -492,6 +492,7 @@ __global__ void __launch_bounds__(256)
 gumbel_select_kernel(const int64_t *__restrict__ sorted_idx, const double *__restrict__ sorted_gumbel, int64_t keep, int k,
                      int qudit_start, const int64_t *__restrict__ prefix, const int32_t *__restrict__ memo_idx,
                      const int32_t *__restrict__ next_memo_q, const double *__restrict__ level_log_prob,
+                     const unsigned long long *__restrict__ drop_mask_q, int64_t memo_size,
                      int64_t *__restrict__ out_prefix, int32_t *__restrict__ out_memo, double *__restrict__ out_log_prob,
                      double *__restrict__ out_gumbel, int *__restrict__ n_alive) {
     const int D = 1 << k;
@@ -501,13 +502,19 @@ gumbel_select_kernel(const int64_t *__restrict__ sorted_idx, const double *__res
         const double g = sorted_gumbel[r];
         const int64_t parent = flat >> k;
         const int outcome = (int)(flat & (D - 1));
-        const bool alive = g > -INFINITY;
+        bool alive = g > -INFINITY;
+        if (alive && drop_mask_q != nullptr) {
+            // a level drawn from UNMASKED conditionals ('DU', ANQS:708-709): unphysical children took part in the top-k with
+            // finite Gumbels and are dropped only now (ANQS:804-809), wherever they sit among the kept rows
+            const int mi = memo_idx[parent];
+            alive = mi >= 0 && mi < memo_size && ((drop_mask_q[mi] >> outcome) & 1ull);
+        }
         out_prefix[r] = prefix[parent] | ((int64_t)outcome << qudit_start);
         // dead rows (masked children, children of dead rows) may be carried to the next level: they get no memo index, which
         // masks all of their own children
         out_memo[r] = alive ? next_memo_q[(int64_t)memo_idx[parent] * D + outcome] : -1;
         out_log_prob[r] = alive ? level_log_prob[flat] : -INFINITY;
-        out_gumbel[r] = g;
+        out_gumbel[r] = alive ? g : -INFINITY;
         alive_here += alive ? 1 : 0;
     }
     alive_here = __reduce_add_sync(0xffffffffu, alive_here);
@@ -624,6 +631,16 @@ int anqs_sampler_gumbel_select(const int64_t *d_sorted_idx, const double *d_sort
                                int qudit_start, const int64_t *d_prefix, const int32_t *d_memo_idx, const int32_t *d_next_memo_q,
                                const double *d_level_log_prob, int64_t *d_out_prefix, int32_t *d_out_memo_idx,
                                double *d_out_log_prob, double *d_out_gumbel, int32_t *d_n_alive, void *stream) {
+    return anqs_sampler_gumbel_select_masked(d_sorted_idx, d_sorted_gumbel, keep, qubits_in_qudit, qudit_start, d_prefix, d_memo_idx,
+                                             d_next_memo_q, d_level_log_prob, nullptr, 0, d_out_prefix, d_out_memo_idx, d_out_log_prob,
+                                             d_out_gumbel, d_n_alive, stream);
+}
+
+int anqs_sampler_gumbel_select_masked(const int64_t *d_sorted_idx, const double *d_sorted_gumbel, int64_t keep, int qubits_in_qudit,
+                                      int qudit_start, const int64_t *d_prefix, const int32_t *d_memo_idx,
+                                      const int32_t *d_next_memo_q, const double *d_level_log_prob, const uint64_t *d_drop_mask_q,
+                                      int64_t memo_size, int64_t *d_out_prefix, int32_t *d_out_memo_idx, double *d_out_log_prob,
+                                      double *d_out_gumbel, int32_t *d_n_alive, void *stream) {
     ANQS_REQUIRE(keep >= 0, "negative row count");
     ANQS_REQUIRE(qubits_in_qudit >= 1 && qubits_in_qudit <= 6, "qudit must have 1..6 qubits");
     ANQS_REQUIRE(d_n_alive, "null counter");
@@ -634,8 +651,8 @@ int anqs_sampler_gumbel_select(const int64_t *d_sorted_idx, const double *d_sort
                      d_out_memo_idx && d_out_log_prob && d_out_gumbel, "null pointer");
     const int grid = (int)std::min<int64_t>((keep + 255) / 256, (int64_t)sm_count_of_current_device() * 8);
     gumbel_select_kernel<<<grid, 256, 0, s>>>(d_sorted_idx, d_sorted_gumbel, keep, qubits_in_qudit, qudit_start, d_prefix, d_memo_idx,
-                                              d_next_memo_q, d_level_log_prob, d_out_prefix, d_out_memo_idx, d_out_log_prob, d_out_gumbel,
-                                              d_n_alive);
+                                              d_next_memo_q, d_level_log_prob, (const unsigned long long *)d_drop_mask_q, memo_size,
+                                              d_out_prefix, d_out_memo_idx, d_out_log_prob, d_out_gumbel, d_n_alive);
     ANQS_LAUNCH_CHECK();
     return 0;
 }

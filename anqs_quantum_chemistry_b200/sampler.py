@@ -54,15 +54,22 @@ class AutoregressiveSamplerMixin:
         qg = self.qubit_grouping
         if self._next_memo is None:
             self._next_memo = [pt.from_numpy(np.ascontiguousarray(t.astype(np.int32))).to(self.device) for t in qg.next_memo_host]
-        pattern = getattr(self, 'local_sampling_pattern', None)
-        if pattern is not None and pattern[q] == 'DU':
-            # An unmasked qudit (masking_depth > 0; the reference default is 0).  The reference's samplers draw such a level from
-            # the unmasked conditionals and THEN throw the unphysical children away, with the samples they carry (ANQS:605-606 +
-            # 653-655; ANQS:708-709 + 804-809) - a different level kernel.  Amplitudes, conditionals and gradients of such wave
-            # functions are implemented and tested against the reference; sampling from them is not.
-            raise NotImplementedError('sampling with LocalSamplingConfig(masking_depth > 0) is not implemented by the sm_100a sampler '
-                                      'kernels (amplitude / log_psi / cond_log_abs / gradients are)')
         return qg.cont_mask_words[q], self._next_memo[q]
+
+    def _is_unmasked_level(self, q: int) -> bool:
+        """Strategy 'DU' (LocalSamplingConfig(masking_depth > 0), ANQS:45-46): the level is DRAWN from the unmasked conditionals
+        (cond_log_abs already returns them for such a qudit) and the unphysical children are thrown away afterwards, with the
+        samples they carry (ANQS:605-606 + 653-655; ANQS:708-709 + 804-809).  The count-splitting kernels need nothing extra:
+        they draw from whatever conditionals they are given and filter the children by the TRUE continuation mask at the
+        end.  The Gumbel level lets every child compete (all-ones mask words) and anqs_sampler_gumbel_select_masked drops the
+        unphysical survivors."""
+        pattern = getattr(self, 'local_sampling_pattern', None)
+        return pattern is not None and pattern[q] == 'DU'
+
+    def _all_ones_mask_words(self):
+        if getattr(self, '_ones_words', None) is None:
+            self._ones_words = pt.full((self.masker.memo_size,), -1, dtype=pt.int64, device=self.device)
+        return self._ones_words
 
     def _start_memo_idx(self) -> int:
         start = np.array([[sym.start_eig for sym in self.masker.symmetries]], dtype=np.int64)
@@ -210,8 +217,10 @@ class AutoregressiveSamplerMixin:
             out_lp = pt.empty((B, D), dtype=pt.float64, device=dev)
             out_g = pt.empty((B, D), dtype=pt.float64, device=dev)
             u = uniforms(q, B, D).to(dev).contiguous() if uniforms is not None else None
+            du = self._is_unmasked_level(q)
             _lib.check(lib.anqs_sampler_gumbel_level_keyed(_lib.dptr(cond), self.max_qudit_dim, k, _lib.dptr(log_prob), _lib.dptr(gumbel),
-                                                           _lib.dptr(memo), _lib.dptr(cont_q), self.masker.memo_size, B, q, seed, 0,
+                                                           _lib.dptr(memo), _lib.dptr(self._all_ones_mask_words() if du else cont_q),
+                                                           self.masker.memo_size, B, q, seed, 0,
                                                            _lib.dptr(prefix), _lib.dptr(u), _lib.dptr(out_lp), _lib.dptr(out_g), sp))
             flat_g = out_g.view(-1)
             keep = min(sample_num, flat_g.shape[0])
@@ -223,11 +232,17 @@ class AutoregressiveSamplerMixin:
             new_lp = pt.empty(keep, dtype=pt.float64, device=dev)
             new_g = pt.empty(keep, dtype=pt.float64, device=dev)
             n_alive = pt.empty(1, dtype=pt.int32, device=dev)
-            _lib.check(lib.anqs_sampler_gumbel_select(_lib.dptr(top_i), _lib.dptr(top_g), keep, k, qg.qudit_starts[q], _lib.dptr(prefix),
-                                                      _lib.dptr(memo), _lib.dptr(next_q), _lib.dptr(out_lp), _lib.dptr(new_prefix),
-                                                      _lib.dptr(new_memo), _lib.dptr(new_lp), _lib.dptr(new_g), _lib.dptr(n_alive), sp))
+            _lib.check(lib.anqs_sampler_gumbel_select_masked(_lib.dptr(top_i), _lib.dptr(top_g), keep, k, qg.qudit_starts[q],
+                                                             _lib.dptr(prefix), _lib.dptr(memo), _lib.dptr(next_q), _lib.dptr(out_lp),
+                                                             _lib.dptr(cont_q if du else None), self.masker.memo_size,
+                                                             _lib.dptr(new_prefix), _lib.dptr(new_memo), _lib.dptr(new_lp),
+                                                             _lib.dptr(new_g), _lib.dptr(n_alive), sp))
             if compact_levels:
                 alive = int(n_alive.item())
+                if du and alive < keep:
+                    # the dropped rows of an unmasked level sit anywhere among the kept ones: stable partition, alive rows first
+                    _, order = _lib.sort_pairs(pt.isinf(new_g).to(pt.int64), None, 0, 1)
+                    new_prefix, new_memo, new_lp, new_g = new_prefix[order], new_memo[order], new_lp[order], new_g[order]
                 prefix, memo, log_prob, gumbel = new_prefix[:alive], new_memo[:alive], new_lp[:alive], new_g[:alive]
             else:
                 # no host read here: masked children are carried on as dead rows (they sort last at every level and mask all

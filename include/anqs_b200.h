@@ -440,6 +440,17 @@ int anqs_sampler_gumbel_select(const int64_t *d_sorted_idx, const double *d_sort
                                const double *d_level_log_prob, int64_t *d_out_prefix, int32_t *d_out_memo_idx,
                                double *d_out_log_prob, double *d_out_gumbel, int32_t *d_n_alive, void *stream);
 
+/* The same for a level that was drawn from UNMASKED conditionals (LocalSamplingConfig(masking_depth > 0): strategy 'DU',
+ * ANQS:708-709): there the unphysical children compete in the top-k with finite Gumbels and are dropped afterwards
+ * (ANQS:804-809).  d_drop_mask_q[memo_size] = the qudit's TRUE continuation-mask words; a kept row whose outcome bit is clear
+ * comes out dead (memo index -1, log-probability and Gumbel -inf) and is not counted in *d_n_alive - dead rows may then sit
+ * anywhere among the `keep` rows.  d_drop_mask_q = NULL: anqs_sampler_gumbel_select. */
+int anqs_sampler_gumbel_select_masked(const int64_t *d_sorted_idx, const double *d_sorted_gumbel, int64_t keep, int qubits_in_qudit,
+                                      int qudit_start, const int64_t *d_prefix, const int32_t *d_memo_idx,
+                                      const int32_t *d_next_memo_q, const double *d_level_log_prob, const uint64_t *d_drop_mask_q,
+                                      int64_t memo_size, int64_t *d_out_prefix, int32_t *d_out_memo_idx, double *d_out_log_prob,
+                                      double *d_out_gumbel, int32_t *d_n_alive, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,8 +129,10 @@ def cond_log_abs(x_prefix, q, masks: NumberSpinMasks, W_abs, b_abs, use_res=True
     mi = masks.memo_idx_of_prefix(x_prefix, masks.starts[q])
     m = np.zeros((x_prefix.shape[0], DM), bool)
     m[:, :masks.dims[q]] = masks.cont_mask[q][mi]
-    if du:
-        m[:] = True
+    if du == 'sampler':
+        m[:, :masks.dims[q]] = True                                              # the samplers' all-ones mask has the qudit's own width (ANQS:605-613)
+    elif du:
+        m[:] = True                                                              # log_psi unmasks max_qudit_dim columns (ANQS:417-418, 434-441)
     return _normalise(y, m)
 
 
@@ -188,15 +190,17 @@ def split_counts_rint(cond, counts, k):
     return out
 
 
-def sample_stats_rint(sample_num, masks: NumberSpinMasks, W_abs, b_abs, use_res=True, subtract_mean=True):
-    """ANQS:494-525 with deterministic draws: (indices uint64 [N], counts float64 [N]) in the reference's order."""
+def sample_stats_rint(sample_num, masks: NumberSpinMasks, W_abs, b_abs, use_res=True, subtract_mean=True, masking_depth=0):
+    """ANQS:494-525 with deterministic draws: (indices uint64 [N], counts float64 [N]) in the reference's order.
+    masking_depth: the last `masking_depth` qudits are drawn from the UNMASKED conditionals (strategy 'DU', ANQS:45-46, 605-606)
+    and their unphysical children dropped afterwards with the samples they carry (ANQS:653-655)."""
     n = masks.n
     prefix = np.zeros(1, np.uint64)
     counts = np.array([float(sample_num)])
     memo = np.array([0 + masks.base * (0 + n // 2)])
     for q in range(masks.Q):
         D = masks.dims[q]
-        cond = cond_log_abs(prefix, q, masks, W_abs, b_abs, use_res, subtract_mean)
+        cond = cond_log_abs(prefix, q, masks, W_abs, b_abs, use_res, subtract_mean, du='sampler' if q >= masks.Q - masking_depth else False)
         child = split_counts_rint(cond, counts, masks.bits[q])
         allowed = masks.cont_mask[q][memo]
         keep = allowed & (child > 0)
@@ -218,8 +222,9 @@ def _log1pexp(x):
         return np.where(x < 18.0, np.log1p(np.exp(x)), x + np.exp(-x))
 
 
-def sample_gumbel(sample_num, masks: NumberSpinMasks, W_abs, b_abs, uniform_fn, use_res=True, subtract_mean=True):
-    """ANQS:778-818; uniform_fn(level, B, D) supplies what pt.rand((B, D)) returned in the reference run."""
+def sample_gumbel(sample_num, masks: NumberSpinMasks, W_abs, b_abs, uniform_fn, use_res=True, subtract_mean=True, masking_depth=0):
+    """ANQS:778-818; uniform_fn(level, B, D) supplies what pt.rand((B, D)) returned in the reference run.  masking_depth as in
+    sample_stats_rint (ANQS:708-709: unphysical children of an unmasked level compete in the top-k and are dropped after it)."""
     n = masks.n
     prefix = np.zeros(1, np.uint64)
     lp = np.zeros(1)
@@ -227,7 +232,7 @@ def sample_gumbel(sample_num, masks: NumberSpinMasks, W_abs, b_abs, uniform_fn, 
     memo = np.array([0 + masks.base * (0 + n // 2)])
     for q in range(masks.Q):
         D = masks.dims[q]
-        cond = cond_log_abs(prefix, q, masks, W_abs, b_abs, use_res, subtract_mean)[:, :D]
+        cond = cond_log_abs(prefix, q, masks, W_abs, b_abs, use_res, subtract_mean, du='sampler' if q >= masks.Q - masking_depth else False)[:, :D]
         with np.errstate(invalid='ignore', divide='ignore'):
             phi = np.nan_to_num(lp[:, None] + 2.0 * cond, nan=-np.inf, neginf=-np.inf, posinf=np.inf)
             u = uniform_fn(q, prefix.shape[0], D)

@@ -119,24 +119,21 @@ def test_gradients_match_reference_autograd(name):
 @pytest.mark.parametrize('name', CASES_SYM)
 def test_sample_stats_rint_matches_reference(name):
     g, masks, nets, wf = setup_case(name)
-    if int(g['masking_depth']) if 'masking_depth' in g else 0:
-        with pytest.raises(NotImplementedError):   # unmasked sampling levels: stated gap (sampler.py:_level_tables)
-            wf.sample_stats(int(g['stats_num']), draw_mode='rint')
-        return
-    idx, cnt = wf.sample_stats(int(g['stats_num']), draw_mode='rint')
-    assert idx.dtype == torch.int64 and idx.dim() == 2 and cnt.dtype == torch.complex128
-    assert np.array_equal(idx.view(-1).cpu().numpy(), g['stats_idx'])
-    assert np.array_equal(cnt.real.cpu().numpy(), g['stats_counts'])
-    assert float(cnt.real.sum()) == float(g['stats_num'])
+    md = int(g['masking_depth']) if 'masking_depth' in g else 0
+    for call in range(2):   # the second call sizes its levels from the first one's (one host read): same result
+        idx, cnt = wf.sample_stats(int(g['stats_num']), draw_mode='rint')
+        assert idx.dtype == torch.int64 and idx.dim() == 2 and cnt.dtype == torch.complex128
+        assert np.array_equal(idx.view(-1).cpu().numpy(), g['stats_idx'])
+        assert np.array_equal(cnt.real.cpu().numpy(), g['stats_counts'])
+        if md == 0:
+            assert float(cnt.real.sum()) == float(g['stats_num'])
+        else:   # an unmasked level ('DU') loses the samples that fell on unphysical children (ANQS:653-655)
+            assert float(cnt.real.sum()) < float(g['stats_num'])
 
 
 @pytest.mark.parametrize('name', CASES_SYM)
 def test_gumbel_matches_reference(name):
     g, masks, nets, wf = setup_case(name)
-    if int(g['masking_depth']) if 'masking_depth' in g else 0:
-        with pytest.raises(NotImplementedError):
-            wf.sample_indices_gumbel(int(g['gumbel_num']))
-        return
     urng = np.random.default_rng(int(g['weight_seed']) + 4)
     idx, freqs = wf.sample_indices_gumbel(int(g['gumbel_num']), uniforms=lambda q, B, D: torch.from_numpy(urng.random((B, D))))
     assert np.array_equal(idx.view(-1).cpu().numpy(), g['gumbel_idx'])
@@ -194,6 +191,42 @@ def test_sample_stats_philox_properties():
     big = expect > 20
     chi2 = float((((c - expect) ** 2) / expect)[big].sum() / big.sum())
     assert 0.8 < chi2 < 1.2, chi2
+
+
+def test_unmasked_level_sampling_philox():
+    """LocalSamplingConfig(masking_depth=1): the last qudit is drawn from its UNMASKED conditionals and the unphysical children
+    are dropped with their samples (ANQS:605-606, 653-655; Gumbel: ANQS:708-709, 804-809).  Production (Philox) draws: only
+    physical, unique configurations come back, fewer samples than asked for, reproducibly, and the counts follow the product
+    of the conditionals the sampler drew from."""
+    hs, masker, wf = build(20, 14, masking_depth=1)
+    qg = wf.qubit_grouping
+    N = 4 * 10 ** 6
+    idx, cnt = wf.sample_stats(N, seed=11)
+    idx2, cnt2 = wf.sample_stats(N, seed=11)           # second call: predicted level sizes, one host read
+    assert torch.equal(idx, idx2) and torch.equal(cnt, cnt2)
+    c, x = cnt.real, idx.view(-1)
+    assert 0 < float(c.sum()) < float(N) and float(c.min()) >= 1.0 and torch.equal(c, c.round())
+    assert x.unique().shape[0] == x.shape[0]
+    assert bool((hs.popcount(x & 0x5555555555555555) == 7).all()) and bool((hs.popcount(x & ~0x5555555555555555) == 7).all())
+    logp = torch.zeros(x.shape[0], dtype=torch.float64, device=DEV)
+    for q in range(qg.qudit_num):
+        start, D = qg.qudit_starts[q], qg.qudit_dims_host[q]
+        cond = wf.cond_log_abs(qudit_idx=q, prefix_idx=x & ((1 << start) - 1))
+        logp += 2.0 * cond.gather(1, ((x >> start) & (D - 1)).view(-1, 1)).view(-1)
+    expect = torch.exp(logp) * N
+    assert float(expect.sum()) < N                     # probability mass sits on unphysical children of the unmasked level
+    big = expect > 20
+    chi2 = float((((c - expect) ** 2) / expect)[big].sum() / big.sum())
+    assert 0.8 < chi2 < 1.2, chi2
+    # Gumbel top-k: dead rows carried to the end (default) and compacted after every level give the same set and frequencies
+    gi, gf = wf.sample_indices_gumbel(3000, seed=5)
+    gi2, gf2 = wf.sample_indices_gumbel(3000, seed=5, compact_levels=True)
+    g = gi.view(-1)
+    assert 0 < g.shape[0] <= 3000 and g.unique().shape[0] == g.shape[0]
+    assert bool((hs.popcount(g & 0x5555555555555555) == 7).all()) and bool((hs.popcount(g & ~0x5555555555555555) == 7).all())
+    o1, o2 = torch.argsort(g), torch.argsort(gi2.view(-1))
+    assert torch.equal(g[o1], gi2.view(-1)[o2]) and torch.allclose(gf[o1], gf2[o2], rtol=0, atol=1e-12)
+    assert abs(float(gf.sum()) - 1.0) < 1e-12
 
 
 def test_sample_stats_philox_small_counts():
