@@ -73,46 +73,161 @@ __global__ void filter_pick_spread_kernel(const unsigned long long *__restrict__
     hdr->n_keys = n_keys;
 }
 
+// One key into the table and the filter.  `first` = the amplitude of position j when the caller already holds it (a record
+// of the partitioned build), else it is read from amps[j].
+__device__ __forceinline__ void insert_key(uint64_t key, long long j, const double2 *first, const double2 *__restrict__ amps,
+                                           HashSlot *slots, uint32_t *filter_words, uint32_t gmask, uint32_t capmask,
+                                           uint32_t linemask) {
+    uint32_t hl, hp;
+    key_hashes(key, hl, hp);
+    const uint32_t line = (hl ^ ((hp >> 15) & gmask)) & linemask;
+    atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), (1u << (hp & 31u)) | (1u << ((hp >> 10) & 31u)));
+    HashSlot *sl;
+    if (key == EMPTY_KEY) {
+        sl = slots + (size_t)capmask + 1;
+    } else {
+        uint32_t h = hash_key((uint32_t)key, (uint32_t)(key >> 32)) & capmask;
+        for (;;) {
+            unsigned long long prev = atomicCAS((unsigned long long *)&slots[h].key, (unsigned long long)EMPTY_KEY,
+                                                (unsigned long long)key);
+            if (prev == EMPTY_KEY || prev == key) break;
+            h = (h + 1) & capmask;
+        }
+        sl = slots + h;
+    }
+    // duplicates: the largest position wins, which is what a sequential scatter_ leaves behind.  The amplitude has to follow
+    // the position: a thread that raised idx writes its amplitude, then re-reads idx and, if a larger position has arrived
+    // meanwhile, writes THAT position's amplitude - so whichever store lands last carries the amplitude of the final idx.
+    long long old = atomicMax(&sl->idx, j);
+    if (old < j && amps) {
+        long long cur = j;
+        double2 a = first ? *first : amps[cur];
+        for (;;) {
+            sl->re = a.x;
+            sl->im = a.y;
+            __threadfence();
+            const long long now = *reinterpret_cast<volatile long long *>(&sl->idx);
+            if (now == cur) break;
+            cur = now;
+            a = amps[cur];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 hash_build_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ amps, int64_t n, HashSlot *slots,
                   uint32_t *filter_words, const FilterHeader *hdr, uint32_t capmask, uint32_t linemask) {
     const uint32_t gmask = hdr->gmask;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        uint64_t key = deinterleave((uint64_t)keys[j]);
-        uint32_t hl, hp;
-        key_hashes(key, hl, hp);
-        const uint32_t line = (hl ^ ((hp >> 15) & gmask)) & linemask;
-        atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), (1u << (hp & 31u)) | (1u << ((hp >> 10) & 31u)));
-        HashSlot *sl;
-        if (key == EMPTY_KEY) {
-            sl = slots + (size_t)capmask + 1;
-        } else {
-            uint32_t h = hash_key((uint32_t)key, (uint32_t)(key >> 32)) & capmask;
-            for (;;) {
-                unsigned long long prev = atomicCAS((unsigned long long *)&slots[h].key, (unsigned long long)EMPTY_KEY,
-                                                    (unsigned long long)key);
-                if (prev == EMPTY_KEY || prev == key) break;
-                h = (h + 1) & capmask;
-            }
-            sl = slots + h;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        insert_key(deinterleave((uint64_t)keys[j]), (long long)j, nullptr, amps, slots, filter_words, gmask, capmask, linemask);
+}
+
+// ---- partitioned build for tables that do not fit the L2 cache -------------------------------------------------------------
+// A direct build of an 8.4M-key table (537 MB of slots) sends every key to a random 32-byte sector of DRAM and back: 1.12 ms on
+// B200, 7.5 G keys/s - the rate of random DRAM accesses, not a bandwidth (profiles/r2_table_build.txt).  Here the keys are
+// first grouped by the leading bits of their home slot into partitions of PART_BYTES of slots (three streaming passes:
+// histogram, scan, scatter of 32-byte records {key, position, amplitude}), and the insert kernel walks the records in that
+// order: at any moment its threads work on one or two partitions, which the L2 holds, and the slots reach DRAM as whole
+// lines when they are evicted.  The order of the records inside a partition is arbitrary; the result does not depend on it
+// (largest position wins, amplitude follows).
+constexpr int PART_CHUNK = 8;                     // keys per thread of the histogram / scatter kernels
+constexpr int PART_MAX = 1024;
+constexpr size_t PART_BYTES = (size_t)16 << 20;   // slots per partition, in bytes
+
+struct __align__(16) KeyRecord {
+    uint64_t key;   // de-interleaved
+    long long j;
+    double re, im;
+};
+
+__device__ __forceinline__ uint32_t home_partition(uint64_t key, uint32_t capmask, int part_shift) {
+    return key == EMPTY_KEY ? 0u : (hash_key((uint32_t)key, (uint32_t)(key >> 32)) & capmask) >> part_shift;
+}
+
+__global__ void __launch_bounds__(256)
+part_count_kernel(const int64_t *__restrict__ keys, int64_t n, uint32_t capmask, int part_shift, int parts,
+                  unsigned long long *__restrict__ counts) {
+    __shared__ uint32_t hist[PART_MAX];
+    for (int p = threadIdx.x; p < parts; p += blockDim.x) hist[p] = 0u;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * (256 * PART_CHUNK);
+#pragma unroll
+    for (int c = 0; c < PART_CHUNK; ++c) {
+        const int64_t j = base + c * 256 + threadIdx.x;
+        if (j < n) atomicAdd(&hist[home_partition(deinterleave((uint64_t)keys[j]), capmask, part_shift)], 1u);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < parts; p += blockDim.x)
+        if (hist[p]) atomicAdd(&counts[p], (unsigned long long)hist[p]);
+}
+
+// exclusive scan of the partition sizes into cursors (one block; at most 1 024 partitions)
+__global__ void __launch_bounds__(PART_MAX)
+part_scan_kernel(const unsigned long long *__restrict__ counts, int parts, unsigned long long *__restrict__ cursors) {
+    __shared__ unsigned long long sh[PART_MAX];
+    const int t = threadIdx.x;
+    sh[t] = t < parts ? counts[t] : 0ull;
+    __syncthreads();
+    for (int d = 1; d < PART_MAX; d <<= 1) {
+        const unsigned long long v = t >= d ? sh[t - d] : 0ull;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    if (t < parts) cursors[t] = sh[t] - counts[t];
+}
+
+__global__ void __launch_bounds__(256)
+part_scatter_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ amps, int64_t n, uint32_t capmask,
+                    int part_shift, int parts, unsigned long long *__restrict__ cursors, KeyRecord *__restrict__ records) {
+    __shared__ uint32_t hist[PART_MAX];
+    __shared__ unsigned long long start[PART_MAX];
+    for (int p = threadIdx.x; p < parts; p += blockDim.x) hist[p] = 0u;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * (256 * PART_CHUNK);
+    uint64_t key[PART_CHUNK];
+    uint32_t part[PART_CHUNK], rank[PART_CHUNK];
+#pragma unroll
+    for (int c = 0; c < PART_CHUNK; ++c) {
+        const int64_t j = base + c * 256 + threadIdx.x;
+        if (j < n) {
+            key[c] = deinterleave((uint64_t)keys[j]);
+            part[c] = home_partition(key[c], capmask, part_shift);
+            rank[c] = atomicAdd(&hist[part[c]], 1u);
         }
-        // duplicates: the largest position wins, which is what a sequential scatter_ leaves behind.  The amplitude has to follow
-        // the position: a thread that raised idx writes its amplitude, then re-reads idx and, if a larger position has arrived
-        // meanwhile, writes THAT position's amplitude - so whichever store lands last carries the amplitude of the final idx.
-        long long old = atomicMax(&sl->idx, (long long)j);
-        if (old < j && amps) {
-            long long cur = j;
-            for (;;) {
-                const double2 a = amps[cur];
-                sl->re = a.x;
-                sl->im = a.y;
-                __threadfence();
-                const long long now = *reinterpret_cast<volatile long long *>(&sl->idx);
-                if (now == cur) break;
-                cur = now;
-            }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < parts; p += blockDim.x)
+        if (hist[p]) start[p] = atomicAdd(&cursors[p], (unsigned long long)hist[p]);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < PART_CHUNK; ++c) {
+        const int64_t j = base + c * 256 + threadIdx.x;
+        if (j < n) {
+            KeyRecord r;
+            r.key = key[c];
+            r.j = (long long)j;
+            const double2 a = amps ? amps[j] : make_double2(0.0, 0.0);
+            r.re = a.x;
+            r.im = a.y;
+            records[start[part[c]] + rank[c]] = r;
         }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hash_build_records_kernel(const KeyRecord *__restrict__ records, const double2 *__restrict__ amps, int64_t n, HashSlot *slots,
+                          uint32_t *filter_words, const FilterHeader *hdr, uint32_t capmask, uint32_t linemask) {
+    const uint32_t gmask = hdr->gmask;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(records + i));
+        const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(records + i) + 1);
+        const uint64_t key = ((uint64_t)lo.y << 32) | lo.x;
+        const long long j = (long long)(((uint64_t)lo.w << 32) | lo.z);
+        const double2 a = make_double2(__hiloint2double((int)hi.y, (int)hi.x), __hiloint2double((int)hi.w, (int)hi.z));
+        insert_key(key, j, &a, amps, slots, filter_words, gmask, capmask, linemask);
     }
 }
 
@@ -133,8 +248,18 @@ hash_probe_kernel(HashView hv, const int64_t *__restrict__ queries, int64_t m, i
 
 using namespace anqs;
 
+// number of partitions of the partitioned build, 0 = the table is small enough for the direct build
+static int partition_count(int64_t capacity) {
+    const size_t slot_bytes = (size_t)capacity * sizeof(HashSlot);
+    if (slot_bytes < ((size_t)96 << 20)) return 0;
+    return (int)std::min<size_t>(slot_bytes / PART_BYTES, (size_t)PART_MAX);
+}
+static size_t partition_workspace(int64_t n, int64_t capacity) {
+    return partition_count(capacity) == 0 ? 0 : (size_t)n * sizeof(KeyRecord) + 2 * PART_MAX * sizeof(unsigned long long);
+}
+
 static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
-                       int forced_spread, void *stream) {
+                       int forced_spread, void *stream, void *d_work = nullptr, size_t work_bytes = 0) {
     ANQS_REQUIRE(n >= 0, "negative key count");
     ANQS_REQUIRE(d_table, "null table buffer");
     ANQS_REQUIRE(capacity >= 1024 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 1024");
@@ -169,6 +294,29 @@ static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, v
     filter_pick_spread_kernel<<<1, 32, 0, s>>>(acc, nlines, (uint32_t)n, hdr, forced_spread);
     ANQS_LAUNCH_CHECK();
     if (forced_spread < 0) ANQS_CUDA(cudaMemsetAsync(filter_words, 0, (size_t)nlines * sizeof(uint32_t), s));
+    const int parts = partition_count(capacity);
+    if (parts > 0 && d_work != nullptr && work_bytes >= partition_workspace(n, capacity)) {
+        ANQS_REQUIRE(((uintptr_t)d_work & 15) == 0, "workspace must be 16-byte aligned");
+        KeyRecord *records = (KeyRecord *)d_work;
+        unsigned long long *counts = (unsigned long long *)(records + n), *cursors = counts + PART_MAX;
+        int log2cap = 0;
+        while (((int64_t)1 << log2cap) < capacity) ++log2cap;
+        int log2parts = 0;
+        while ((1 << log2parts) < parts) ++log2parts;
+        const int part_shift = log2cap - log2parts;
+        ANQS_CUDA(cudaMemsetAsync(counts, 0, 2 * PART_MAX * sizeof(unsigned long long), s));
+        const int pgrid = (int)((n + 256 * PART_CHUNK - 1) / (256 * PART_CHUNK));
+        part_count_kernel<<<pgrid, 256, 0, s>>>(d_keys, n, hv.capmask, part_shift, parts, counts);
+        ANQS_LAUNCH_CHECK();
+        part_scan_kernel<<<1, PART_MAX, 0, s>>>(counts, parts, cursors);
+        ANQS_LAUNCH_CHECK();
+        part_scatter_kernel<<<pgrid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, hv.capmask, part_shift, parts, cursors, records);
+        ANQS_LAUNCH_CHECK();
+        hash_build_records_kernel<<<grid, 256, 0, s>>>(records, (const double2 *)d_amps, n, slots, filter_words, hdr, hv.capmask,
+                                                       hv.linemask);
+        ANQS_LAUNCH_CHECK();
+        return 0;
+    }
     hash_build_kernel<<<grid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, filter_words, hdr, hv.capmask, hv.linemask);
     ANQS_LAUNCH_CHECK();
     return 0;
@@ -194,6 +342,15 @@ int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void
 int anqs_hash_build_spread(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                            int spread_bits, void *stream) {
     return build_table(d_keys, d_amps, n, d_table, capacity, spread_bits, stream);
+}
+
+size_t anqs_hash_build_workspace(int64_t n, int64_t capacity) {
+    return n <= 0 ? 0 : partition_workspace(n, capacity);
+}
+
+int anqs_hash_build_ws(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity, int spread_bits,
+                       void *d_work, size_t work_bytes, void *stream) {
+    return build_table(d_keys, d_amps, n, d_table, capacity, spread_bits, stream, d_work, work_bytes);
 }
 
 int anqs_hash_filter_info(const void *d_table, int64_t capacity, int *spread_bits, int64_t *overloaded_keys, void *stream) {

@@ -123,6 +123,15 @@ int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void
 /* Same with G forced to spread_bits (0..6) instead of chosen from the data. */
 int anqs_hash_build_spread(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                            int spread_bits, void *stream);
+/* Build with a caller-owned workspace.  Tables whose slots do not fit the L2 cache (anqs_hash_build_workspace(n, capacity) > 0:
+ * 96 MiB of slots and more) are built PARTITIONED when d_work holds at least that many bytes (16-byte aligned): the keys are
+ * first grouped by the leading bits of their home slot (histogram, scan, scatter of 32-byte records), then inserted in that
+ * order, so that the inserts of any moment fall into a few L2-resident partitions of 16 MiB instead of random DRAM sectors
+ * (8.4M keys: 1.27 -> see profiles/r2_table_build.txt).  Same table either way.  d_work = NULL or too small, or a small
+ * table: the direct build.  spread_bits = -1: G from the data (anqs_hash_build), 0..6: forced (anqs_hash_build_spread). */
+size_t anqs_hash_build_workspace(int64_t n, int64_t capacity);
+int anqs_hash_build_ws(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity, int spread_bits,
+                       void *d_work, size_t work_bytes, void *stream);
 /* Reads back G and overloaded_keys[g] (g = 0..6) = keys living in lines that hold more than 128 << g keys.
  * Synchronises the stream. */
 int anqs_hash_filter_info(const void *d_table, int64_t capacity, int *spread_bits, int64_t *overloaded_keys, void *stream);
