@@ -26,6 +26,8 @@ _SIGNATURES = {
     'anqs_tables_info': (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     'anqs_k1_filter': (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp]),
     'anqs_scan_workspace': (ctypes.c_size_t, [_c_i64]),
+    'anqs_energy_stats_workspace': (ctypes.c_size_t, [_c_i64]),
+    'anqs_energy_stats': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp]),
     'anqs_exclusive_scan_i64': (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
     'anqs_k1_emit': (_c_int, [_vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),
     'anqs_k1_enum_tiles': (_c_int, [_vp]),
@@ -38,8 +40,6 @@ _SIGNATURES = {
     'anqs_hash_bytes': (ctypes.c_size_t, [_c_i64]),
     'anqs_hash_build': (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _vp]),
     'anqs_hash_build_spread': (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _c_int, _vp]),
-    'anqs_hash_build_workspace': (ctypes.c_size_t, [_c_i64, _c_i64]),
-    'anqs_hash_build_ws': (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _c_int, _vp, ctypes.c_size_t, _vp]),
     'anqs_hash_filter_info': (_c_int, [_vp, _c_i64, _vp, _vp, _vp]),
     'anqs_hash_probe': (_c_int, [_vp, _c_i64, _vp, _c_i64, _vp, _vp, _vp]),
     'anqs_pair_join_workspace': (ctypes.c_size_t, [_c_i64, _c_i64]),

@@ -498,6 +498,54 @@ static void build_enum_tiles(int n, const std::vector<uint64_t> &xy, const std::
     }
 }
 
+
+// ---- A13 estimator: packed partial sums of the MonteCarloEstimator (CLE:48-62) in one pass --------------------------------
+// out[5] = [sum w, Re sum w E, Im sum w E, Re sum w E^2, Im sum w E^2], w = |psi|^2 (complex square of E, as the reference's
+// variance takes it).  One read of both vectors (32 B per row); per-thread partial sums over a grid-stride walk, lanes and
+// warps added by shuffles, one partial per block into the workspace, and the block that finishes last adds the partials in
+// block order - a fixed summation order for a given n, so two calls return the same bits.
+constexpr int STATS_THREADS = 256;
+__global__ void __launch_bounds__(STATS_THREADS)
+energy_stats_kernel(const double2 *__restrict__ eloc, const double2 *__restrict__ amps, int64_t n, double *__restrict__ partials,
+                    unsigned int *__restrict__ done, double *__restrict__ out) {
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * STATS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * STATS_THREADS) {
+        const double2 e = eloc[i], a = amps[i];
+        const double w = a.x * a.x + a.y * a.y;
+        const double wer = w * e.x, wei = w * e.y;
+        acc[0] += w;
+        acc[1] += wer;
+        acc[2] += wei;
+        acc[3] += wer * e.x - wei * e.y;
+        acc[4] += wer * e.y + wei * e.x;
+    }
+    __shared__ double warp_part[STATS_THREADS / 32][5];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], d);
+        if (lane == 0) warp_part[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0.0;
+        for (int wv = 0; wv < STATS_THREADS / 32; ++wv) t += warp_part[wv][threadIdx.x];
+        partials[(size_t)blockIdx.x * 5 + threadIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x < 5) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double *>(partials)[(size_t)b * 5 + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+}
+
 }  // namespace anqs
 
 using namespace anqs;
@@ -539,6 +587,30 @@ int anqs_popcount_i64(const int64_t *d_in, int64_t *d_out, int64_t n, void *stre
 size_t anqs_scan_workspace(int64_t n) {
     int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     return (size_t)(ntiles + 1) * sizeof(int64_t);
+}
+
+static int stats_grid(int64_t n) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + 4 * STATS_THREADS - 1) / (4 * STATS_THREADS), (int64_t)sm_count_of_current_device() * 4));
+}
+
+size_t anqs_energy_stats_workspace(int64_t n) { return (size_t)stats_grid(n) * 5 * sizeof(double) + 16; }
+
+int anqs_energy_stats(const double *d_eloc, const double *d_amps, int64_t n, double *d_out5, void *d_work, void *stream) {
+    ANQS_REQUIRE(n >= 0, "negative row count");
+    ANQS_REQUIRE(d_out5 && d_work, "null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        ANQS_CUDA(cudaMemsetAsync(d_out5, 0, 5 * sizeof(double), s));
+        return 0;
+    }
+    ANQS_REQUIRE(d_eloc && d_amps, "null pointer");
+    const int grid = stats_grid(n);
+    unsigned int *done = reinterpret_cast<unsigned int *>(d_work);
+    double *partials = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(d_work) + 16);
+    ANQS_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned int), s));
+    energy_stats_kernel<<<grid, STATS_THREADS, 0, s>>>((const double2 *)d_eloc, (const double2 *)d_amps, n, partials, done, d_out5);
+    ANQS_LAUNCH_CHECK();
+    return 0;
 }
 
 int anqs_exclusive_scan_i64(const int64_t *d_in, int64_t *d_out, int64_t n, void *d_work, void *stream) {

@@ -9,8 +9,9 @@
 // candidates.  The all-ones key is the EMPTY sentinel; a real all-ones key (only possible at qubit_num == 64, or for
 // generic int64 inputs such as -1) lives in a dedicated slot at index `capacity`.
 //
-// Build = 5 stream-ordered launches, no host synchronisation:
-//   memset -> count keys per line (in the filter region itself) -> pick the spread G -> memset filter -> insert.
+// Build = stream-ordered launches, no host synchronisation:
+//   memset -> count keys per line (in the filter region itself) -> pick the spread G -> memset filter -> insert
+//   -> amplitude fix-up (returns at once unless the insert saw duplicated keys).
 // G spreads the keys that share an alpha half over 2^G lines (selected by hash bits of the beta half) when sample
 // sets concentrate on few alpha strings; G = 0 when at most 5 % of the keys sit in lines holding more than 128 keys.
 #include <algorithm>
@@ -19,18 +20,41 @@
 
 namespace anqs {
 
-__device__ __forceinline__ void key_hashes(uint64_t key, uint32_t &hl, uint32_t &hp) {
-    const uint32_t ka = (uint32_t)key, kb = (uint32_t)(key >> 32);
-    hl = lin_dev(LIN_LINE, ka);
-    hp = (lin_dev(LIN_POSA, ka) & POSA_MASK) ^ (lin_dev(LIN_POSB, kb) & POSB_MASK);
-}
+// The three GF(2)-linear hashes of a key through byte tables in shared memory: lin(f, v) = T[f][0][v & 255] ^ T[f][1][v >> 8 & 255]
+// ^ ..., four loads per hash instead of a loop over the set bits with one table load each (that loop was 700 of the insert
+// kernel's 940 warp instructions per 32 keys, profiles/r2_table_build.txt).  Line and first position hash share the alpha half
+// and sit side by side: one 8-byte load serves both.  12 KB per CTA.
+struct LinByteTables {
+    uint2 a[4][256];      // .x = LIN_LINE, .y = LIN_POSA contribution of byte b of the alpha half
+    uint32_t b[4][256];   // LIN_POSB contribution of byte b of the beta half
+    __device__ __forceinline__ void fill() {   // 256 threads
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+#pragma unroll
+            for (int byte = 0; byte < 4; ++byte) {
+                const uint32_t v = (uint32_t)t << (8 * byte);
+                a[byte][t] = make_uint2(lin_dev(LIN_LINE, v), lin_dev(LIN_POSA, v));
+                b[byte][t] = lin_dev(LIN_POSB, v);
+            }
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void hashes(uint64_t key, uint32_t &hl, uint32_t &hp) const {
+        const uint32_t ka = (uint32_t)key, kb = (uint32_t)(key >> 32);
+        const uint2 a0 = a[0][ka & 255u], a1 = a[1][(ka >> 8) & 255u], a2 = a[2][(ka >> 16) & 255u], a3 = a[3][ka >> 24];
+        const uint32_t pb = b[0][kb & 255u] ^ b[1][(kb >> 8) & 255u] ^ b[2][(kb >> 16) & 255u] ^ b[3][kb >> 24];
+        hl = a0.x ^ a1.x ^ a2.x ^ a3.x;
+        hp = ((a0.y ^ a1.y ^ a2.y ^ a3.y) & POSA_MASK) ^ (pb & POSB_MASK);
+    }
+};
 
 __global__ void __launch_bounds__(256)
 filter_count_kernel(const int64_t *__restrict__ keys, int64_t n, uint32_t *counts, uint32_t linemask) {
+    __shared__ LinByteTables lin;
+    lin.fill();
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         uint32_t hl, hp;
-        key_hashes(deinterleave((uint64_t)keys[j]), hl, hp);
+        lin.hashes(deinterleave((uint64_t)keys[j]), hl, hp);
         atomicAdd(counts + (hl & linemask), 1u);
     }
 }
@@ -57,7 +81,7 @@ filter_overload_kernel(const uint32_t *__restrict__ counts, uint32_t nlines, uns
     if (threadIdx.x <= FILTER_MAX_SPREAD_BITS && sacc[threadIdx.x]) atomicAdd(&acc[threadIdx.x], sacc[threadIdx.x]);
 }
 
-__global__ void filter_pick_spread_kernel(const unsigned long long *__restrict__ acc, uint32_t nlines, uint32_t n_keys,
+__global__ void filter_pick_spread_kernel(unsigned long long *__restrict__ acc, uint32_t nlines, uint32_t n_keys,
                                           FilterHeader *hdr, int forced_spread) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int G = FILTER_MAX_SPREAD_BITS;
@@ -71,163 +95,100 @@ __global__ void filter_pick_spread_kernel(const unsigned long long *__restrict__
     hdr->spread_bits = (uint32_t)G;
     hdr->gmask = (1u << G) - 1u;
     hdr->n_keys = n_keys;
+    acc[0] = 0ull;   // from here on the first accumulator is the insert kernels' "duplicate keys seen" flag
 }
 
-// One key into the table and the filter.  `first` = the amplitude of position j when the caller already holds it (a record
-// of the partitioned build), else it is read from amps[j].
-__device__ __forceinline__ void insert_key(uint64_t key, long long j, const double2 *first, const double2 *__restrict__ amps,
-                                           HashSlot *slots, uint32_t *filter_words, uint32_t gmask, uint32_t capmask,
-                                           uint32_t linemask) {
-    uint32_t hl, hp;
-    key_hashes(key, hl, hp);
-    const uint32_t line = (hl ^ ((hp >> 15) & gmask)) & linemask;
-    atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), (1u << (hp & 31u)) | (1u << ((hp >> 10) & 31u)));
-    HashSlot *sl;
-    if (key == EMPTY_KEY) {
-        sl = slots + (size_t)capmask + 1;
-    } else {
-        uint32_t h = hash_key((uint32_t)key, (uint32_t)(key >> 32)) & capmask;
-        for (;;) {
-            unsigned long long prev = atomicCAS((unsigned long long *)&slots[h].key, (unsigned long long)EMPTY_KEY,
-                                                (unsigned long long)key);
-            if (prev == EMPTY_KEY || prev == key) break;
-            h = (h + 1) & capmask;
-        }
-        sl = slots + h;
-    }
-    // duplicates: the largest position wins, which is what a sequential scatter_ leaves behind.  The amplitude has to follow
-    // the position: a thread that raised idx writes its amplitude, then re-reads idx and, if a larger position has arrived
-    // meanwhile, writes THAT position's amplitude - so whichever store lands last carries the amplitude of the final idx.
-    long long old = atomicMax(&sl->idx, j);
-    if (old < j && amps) {
-        long long cur = j;
-        double2 a = first ? *first : amps[cur];
-        for (;;) {
-            sl->re = a.x;
-            sl->im = a.y;
-            __threadfence();
-            const long long now = *reinterpret_cast<volatile long long *>(&sl->idx);
-            if (now == cur) break;
-            cur = now;
-            a = amps[cur];
-        }
-    }
-}
-
+// Insert kernel: keys into the table and the filter.  An insert is a chain of dependent round trips to the L2 / DRAM (key ->
+// compare-and-swap on the home slot -> maximum on the position -> amplitude stores) and the kernel is latency-bound (ncu, 8.4M
+// keys: 36-43 warps stalled on the long scoreboard per issue, DRAM at 30 %, L2 at 20 %; profiles/r2_table_build.txt).
+// INSERT_WAYS keys per thread go through the chain side by side.  Measured: 4 ways are SLOWER than 1 (1.35 against 1.0 ms for
+// 8.4M keys) - 57 registers halve the resident warps and the linear-probing loops of the four keys run one after the other -,
+// so the kernel runs with 1 and full occupancy; the structure is kept for the day the probing loop is interleaved too.
+// Duplicates: the largest position wins, which is what a sequential scatter_ leaves behind, and the amplitude has to follow the
+// position.  Every thread that raises idx stores its amplitude; when two positions of one key race, the stores may land in
+// either order - so a thread that finds the slot already claimed (old position >= 0) raises *dup_flag, and
+// hash_fix_amplitudes_kernel, launched behind this kernel, then rewrites every slot's amplitude from its final position.
+// No fence and no re-read inside the insert (__threadfence() is a gpu-scope MEMBAR plus an L1 invalidation per key), and
+// batches without duplicates - the normal case: the sampler returns unique configurations - never run the second pass.
+constexpr int INSERT_WAYS = 1;
 __global__ void __launch_bounds__(256)
 hash_build_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ amps, int64_t n, HashSlot *slots,
-                  uint32_t *filter_words, const FilterHeader *hdr, uint32_t capmask, uint32_t linemask) {
+                  uint32_t *filter_words, const FilterHeader *hdr, unsigned long long *dup_flag, uint32_t capmask, uint32_t linemask) {
+    __shared__ LinByteTables lin;
+    lin.fill();
     const uint32_t gmask = hdr->gmask;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
-        insert_key(deinterleave((uint64_t)keys[j]), (long long)j, nullptr, amps, slots, filter_words, gmask, capmask, linemask);
-}
-
-// ---- partitioned build for tables that do not fit the L2 cache -------------------------------------------------------------
-// A direct build of an 8.4M-key table (537 MB of slots) sends every key to a random 32-byte sector of DRAM and back: 1.12 ms on
-// B200, 7.5 G keys/s - the rate of random DRAM accesses, not a bandwidth (profiles/r2_table_build.txt).  Here the keys are
-// first grouped by the leading bits of their home slot into partitions of PART_BYTES of slots (three streaming passes:
-// histogram, scan, scatter of 32-byte records {key, position, amplitude}), and the insert kernel walks the records in that
-// order: at any moment its threads work on one or two partitions, which the L2 holds, and the slots reach DRAM as whole
-// lines when they are evicted.  The order of the records inside a partition is arbitrary; the result does not depend on it
-// (largest position wins, amplitude follows).
-constexpr int PART_CHUNK = 8;                     // keys per thread of the histogram / scatter kernels
-constexpr int PART_MAX = 1024;
-constexpr size_t PART_BYTES = (size_t)16 << 20;   // slots per partition, in bytes
-
-struct __align__(16) KeyRecord {
-    uint64_t key;   // de-interleaved
-    long long j;
-    double re, im;
-};
-
-__device__ __forceinline__ uint32_t home_partition(uint64_t key, uint32_t capmask, int part_shift) {
-    return key == EMPTY_KEY ? 0u : (hash_key((uint32_t)key, (uint32_t)(key >> 32)) & capmask) >> part_shift;
-}
-
-__global__ void __launch_bounds__(256)
-part_count_kernel(const int64_t *__restrict__ keys, int64_t n, uint32_t capmask, int part_shift, int parts,
-                  unsigned long long *__restrict__ counts) {
-    __shared__ uint32_t hist[PART_MAX];
-    for (int p = threadIdx.x; p < parts; p += blockDim.x) hist[p] = 0u;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * (256 * PART_CHUNK);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    bool dup = false;
+    for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < n; j0 += INSERT_WAYS * stride) {
+        uint64_t key[INSERT_WAYS];
+        double2 a[INSERT_WAYS];
+        uint32_t h[INSERT_WAYS];
+        unsigned long long prev[INSERT_WAYS];
+        bool live[INSERT_WAYS];
 #pragma unroll
-    for (int c = 0; c < PART_CHUNK; ++c) {
-        const int64_t j = base + c * 256 + threadIdx.x;
-        if (j < n) atomicAdd(&hist[home_partition(deinterleave((uint64_t)keys[j]), capmask, part_shift)], 1u);
-    }
-    __syncthreads();
-    for (int p = threadIdx.x; p < parts; p += blockDim.x)
-        if (hist[p]) atomicAdd(&counts[p], (unsigned long long)hist[p]);
-}
-
-// exclusive scan of the partition sizes into cursors (one block; at most 1 024 partitions)
-__global__ void __launch_bounds__(PART_MAX)
-part_scan_kernel(const unsigned long long *__restrict__ counts, int parts, unsigned long long *__restrict__ cursors) {
-    __shared__ unsigned long long sh[PART_MAX];
-    const int t = threadIdx.x;
-    sh[t] = t < parts ? counts[t] : 0ull;
-    __syncthreads();
-    for (int d = 1; d < PART_MAX; d <<= 1) {
-        const unsigned long long v = t >= d ? sh[t - d] : 0ull;
-        __syncthreads();
-        sh[t] += v;
-        __syncthreads();
-    }
-    if (t < parts) cursors[t] = sh[t] - counts[t];
-}
-
-__global__ void __launch_bounds__(256)
-part_scatter_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ amps, int64_t n, uint32_t capmask,
-                    int part_shift, int parts, unsigned long long *__restrict__ cursors, KeyRecord *__restrict__ records) {
-    __shared__ uint32_t hist[PART_MAX];
-    __shared__ unsigned long long start[PART_MAX];
-    for (int p = threadIdx.x; p < parts; p += blockDim.x) hist[p] = 0u;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * (256 * PART_CHUNK);
-    uint64_t key[PART_CHUNK];
-    uint32_t part[PART_CHUNK], rank[PART_CHUNK];
+        for (int c = 0; c < INSERT_WAYS; ++c) {
+            const int64_t j = j0 + c * stride;
+            live[c] = j < n;
+            key[c] = live[c] ? (uint64_t)keys[j] : 0ull;
+            a[c] = (live[c] && amps) ? amps[j] : make_double2(0.0, 0.0);
+        }
 #pragma unroll
-    for (int c = 0; c < PART_CHUNK; ++c) {
-        const int64_t j = base + c * 256 + threadIdx.x;
-        if (j < n) {
-            key[c] = deinterleave((uint64_t)keys[j]);
-            part[c] = home_partition(key[c], capmask, part_shift);
-            rank[c] = atomicAdd(&hist[part[c]], 1u);
+        for (int c = 0; c < INSERT_WAYS; ++c) {
+            key[c] = deinterleave(key[c]);
+            uint32_t hl, hp;
+            lin.hashes(key[c], hl, hp);
+            const uint32_t line = (hl ^ ((hp >> 15) & gmask)) & linemask;
+            if (live[c]) atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), (1u << (hp & 31u)) | (1u << ((hp >> 10) & 31u)));
+            h[c] = hash_key((uint32_t)key[c], (uint32_t)(key[c] >> 32)) & capmask;
+            // the all-ones key is the EMPTY sentinel: it lives in a dedicated slot behind the table and needs no claim
+            prev[c] = key[c];
+            if (live[c] && key[c] != EMPTY_KEY)
+                prev[c] = atomicCAS((unsigned long long *)&slots[h[c]].key, (unsigned long long)EMPTY_KEY, (unsigned long long)key[c]);
+        }
+        long long old[INSERT_WAYS];
+#pragma unroll
+        for (int c = 0; c < INSERT_WAYS; ++c) {
+            while (prev[c] != EMPTY_KEY && prev[c] != key[c]) {   // occupied by another key: linear probing
+                h[c] = (h[c] + 1) & capmask;
+                prev[c] = atomicCAS((unsigned long long *)&slots[h[c]].key, (unsigned long long)EMPTY_KEY, (unsigned long long)key[c]);
+            }
+            HashSlot *sl = key[c] == EMPTY_KEY ? slots + (size_t)capmask + 1 : slots + h[c];
+            old[c] = live[c] ? atomicMax(&sl->idx, (long long)(j0 + c * stride)) : -1;
+        }
+#pragma unroll
+        for (int c = 0; c < INSERT_WAYS; ++c) {
+            HashSlot *sl = key[c] == EMPTY_KEY ? slots + (size_t)capmask + 1 : slots + h[c];
+            if (live[c] && old[c] < (long long)(j0 + c * stride) && amps) {
+                sl->re = a[c].x;
+                sl->im = a[c].y;
+            }
+            dup |= old[c] >= 0;
         }
     }
-    __syncthreads();
-    for (int p = threadIdx.x; p < parts; p += blockDim.x)
-        if (hist[p]) start[p] = atomicAdd(&cursors[p], (unsigned long long)hist[p]);
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < PART_CHUNK; ++c) {
-        const int64_t j = base + c * 256 + threadIdx.x;
-        if (j < n) {
-            KeyRecord r;
-            r.key = key[c];
-            r.j = (long long)j;
-            const double2 a = amps ? amps[j] : make_double2(0.0, 0.0);
-            r.re = a.x;
-            r.im = a.y;
-            records[start[part[c]] + rank[c]] = r;
-        }
-    }
+    if (dup) *dup_flag = 1ull;
 }
 
+// Second pass, only when the insert saw duplicates: position j rewrites the amplitude of its key's slot if it is the winner.
 __global__ void __launch_bounds__(256)
-hash_build_records_kernel(const KeyRecord *__restrict__ records, const double2 *__restrict__ amps, int64_t n, HashSlot *slots,
-                          uint32_t *filter_words, const FilterHeader *hdr, uint32_t capmask, uint32_t linemask) {
-    const uint32_t gmask = hdr->gmask;
+hash_fix_amplitudes_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ amps, int64_t n, HashSlot *slots,
+                           const unsigned long long *__restrict__ dup_flag, uint32_t capmask) {
+    if (*dup_flag == 0ull) return;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(records + i));
-        const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(records + i) + 1);
-        const uint64_t key = ((uint64_t)lo.y << 32) | lo.x;
-        const long long j = (long long)(((uint64_t)lo.w << 32) | lo.z);
-        const double2 a = make_double2(__hiloint2double((int)hi.y, (int)hi.x), __hiloint2double((int)hi.w, (int)hi.z));
-        insert_key(key, j, &a, amps, slots, filter_words, gmask, capmask, linemask);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t key = deinterleave((uint64_t)keys[j]);
+        HashSlot *sl;
+        if (key == EMPTY_KEY) {
+            sl = slots + (size_t)capmask + 1;
+        } else {
+            uint32_t h = hash_key((uint32_t)key, (uint32_t)(key >> 32)) & capmask;
+            while (slots[h].key != key) h = (h + 1) & capmask;   // present: the insert kernel has finished
+            sl = slots + h;
+        }
+        if (sl->idx == (long long)j) {
+            const double2 a = amps[j];
+            sl->re = a.x;
+            sl->im = a.y;
+        }
     }
 }
 
@@ -248,18 +209,8 @@ hash_probe_kernel(HashView hv, const int64_t *__restrict__ queries, int64_t m, i
 
 using namespace anqs;
 
-// number of partitions of the partitioned build, 0 = the table is small enough for the direct build
-static int partition_count(int64_t capacity) {
-    const size_t slot_bytes = (size_t)capacity * sizeof(HashSlot);
-    if (slot_bytes < ((size_t)96 << 20)) return 0;
-    return (int)std::min<size_t>(slot_bytes / PART_BYTES, (size_t)PART_MAX);
-}
-static size_t partition_workspace(int64_t n, int64_t capacity) {
-    return partition_count(capacity) == 0 ? 0 : (size_t)n * sizeof(KeyRecord) + 2 * PART_MAX * sizeof(unsigned long long);
-}
-
 static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
-                       int forced_spread, void *stream, void *d_work = nullptr, size_t work_bytes = 0) {
+                       int forced_spread, void *stream) {
     ANQS_REQUIRE(n >= 0, "negative key count");
     ANQS_REQUIRE(d_table, "null table buffer");
     ANQS_REQUIRE(capacity >= 1024 && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 1024");
@@ -279,7 +230,16 @@ static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, v
     ANQS_CUDA(cudaMemsetAsync(filter_words, 0, (size_t)FILTER_BYTES_PER_SLOT * capacity, s));
     if (n == 0) return 0;
     ANQS_REQUIRE(d_keys, "null key array");
-    int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 16);
+    // eight resident blocks per SM (each fills 12 KB of hash byte tables first); the insert keeps INSERT_WAYS keys in flight per thread
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 8);
+    static int insert_blocks_per_sm = 0;   // resident blocks of the insert kernel (register-limited): one wave of them
+    if (insert_blocks_per_sm == 0) {
+        int b = 0;
+        ANQS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, hash_build_kernel, 256, 0));
+        insert_blocks_per_sm = std::max(1, b);
+    }
+    const int grid_insert = (int)std::min<int64_t>((n + 256 * INSERT_WAYS - 1) / (256 * INSERT_WAYS),
+                                                   (int64_t)sm_count_of_current_device() * insert_blocks_per_sm);
     if (forced_spread < 0) {
         // per-line key counts, kept in the (still empty) filter region: nlines * 4 bytes <= the filter's size
         filter_count_kernel<<<grid, 256, 0, s>>>(d_keys, n, filter_words, hv.linemask);
@@ -294,31 +254,12 @@ static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, v
     filter_pick_spread_kernel<<<1, 32, 0, s>>>(acc, nlines, (uint32_t)n, hdr, forced_spread);
     ANQS_LAUNCH_CHECK();
     if (forced_spread < 0) ANQS_CUDA(cudaMemsetAsync(filter_words, 0, (size_t)nlines * sizeof(uint32_t), s));
-    const int parts = partition_count(capacity);
-    if (parts > 0 && d_work != nullptr && work_bytes >= partition_workspace(n, capacity)) {
-        ANQS_REQUIRE(((uintptr_t)d_work & 15) == 0, "workspace must be 16-byte aligned");
-        KeyRecord *records = (KeyRecord *)d_work;
-        unsigned long long *counts = (unsigned long long *)(records + n), *cursors = counts + PART_MAX;
-        int log2cap = 0;
-        while (((int64_t)1 << log2cap) < capacity) ++log2cap;
-        int log2parts = 0;
-        while ((1 << log2parts) < parts) ++log2parts;
-        const int part_shift = log2cap - log2parts;
-        ANQS_CUDA(cudaMemsetAsync(counts, 0, 2 * PART_MAX * sizeof(unsigned long long), s));
-        const int pgrid = (int)((n + 256 * PART_CHUNK - 1) / (256 * PART_CHUNK));
-        part_count_kernel<<<pgrid, 256, 0, s>>>(d_keys, n, hv.capmask, part_shift, parts, counts);
-        ANQS_LAUNCH_CHECK();
-        part_scan_kernel<<<1, PART_MAX, 0, s>>>(counts, parts, cursors);
-        ANQS_LAUNCH_CHECK();
-        part_scatter_kernel<<<pgrid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, hv.capmask, part_shift, parts, cursors, records);
-        ANQS_LAUNCH_CHECK();
-        hash_build_records_kernel<<<grid, 256, 0, s>>>(records, (const double2 *)d_amps, n, slots, filter_words, hdr, hv.capmask,
-                                                       hv.linemask);
-        ANQS_LAUNCH_CHECK();
-        return 0;
-    }
-    hash_build_kernel<<<grid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, filter_words, hdr, hv.capmask, hv.linemask);
+    hash_build_kernel<<<grid_insert, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, filter_words, hdr, acc, hv.capmask, hv.linemask);
     ANQS_LAUNCH_CHECK();
+    if (d_amps != nullptr) {
+        hash_fix_amplitudes_kernel<<<grid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, acc, hv.capmask);
+        ANQS_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -342,15 +283,6 @@ int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void
 int anqs_hash_build_spread(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                            int spread_bits, void *stream) {
     return build_table(d_keys, d_amps, n, d_table, capacity, spread_bits, stream);
-}
-
-size_t anqs_hash_build_workspace(int64_t n, int64_t capacity) {
-    return n <= 0 ? 0 : partition_workspace(n, capacity);
-}
-
-int anqs_hash_build_ws(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity, int spread_bits,
-                       void *d_work, size_t work_bytes, void *stream) {
-    return build_table(d_keys, d_amps, n, d_table, capacity, spread_bits, stream, d_work, work_bytes);
 }
 
 int anqs_hash_filter_info(const void *d_table, int64_t capacity, int *spread_bits, int64_t *overloaded_keys, void *stream) {

@@ -81,7 +81,20 @@ def all_gather_shards(local_idx: pt.Tensor, local_amps: pt.Tensor, group=None, s
 
 
 def local_energy_stats(eloc: pt.Tensor, amps: pt.Tensor) -> pt.Tensor:
-    """Packed partial sums [sum w, Re sum wE, Im sum wE, Re sum wE^2, Im sum wE^2], w = |psi|^2."""
+    """Packed partial sums [sum w, Re sum wE, Im sum wE, Re sum wE^2, Im sum wE^2], w = |psi|^2.
+    Device tensors: one pass of energy_stats_kernel (anqs_energy_stats; the chain of elementwise products and five reductions
+    it replaces cost 0.16 ms per 2^20 rows, 1 % of a bench step).  The expression below is what it computes; it serves the
+    host-side tests of this module's collective logic (gloo, CPU tensors) only."""
+    if eloc.is_cuda:
+        from . import _lib
+        dev = _lib.require_cuda(eloc.device)
+        assert eloc.dtype == pt.complex128 and amps.dtype == pt.complex128 and eloc.shape == amps.shape and eloc.dim() == 1
+        e, a = pt.view_as_real(eloc.contiguous()), pt.view_as_real(amps.contiguous())
+        out = pt.empty(5, dtype=pt.float64, device=dev)
+        work = _lib._workspace(_lib.lib().anqs_energy_stats_workspace(eloc.shape[0]), dev)
+        _lib.check(_lib.lib().anqs_energy_stats(_lib.dptr(e), _lib.dptr(a), eloc.shape[0], _lib.dptr(out), _lib.dptr(work),
+                                                _lib.stream_ptr(dev)))
+        return out
     w = (amps.real * amps.real + amps.imag * amps.imag)
     we = w * eloc
     wee = we * eloc

@@ -147,17 +147,13 @@ class HilbertSpace:
 class SampleTable:
     """Open-addressing table {configuration -> (position, amplitude)} plus its presence filter, in device memory."""
 
-    def __init__(self, keys: pt.Tensor, amps: pt.Tensor = None, spread_bits: int = None, partitioned: bool = True):
+    def __init__(self, keys: pt.Tensor, amps: pt.Tensor = None, spread_bits: int = None):
         dev = _lib.require_cuda(keys.device)
         n = keys.shape[0]
         self.capacity = int(_lib.lib().anqs_hash_capacity(n))
         nbytes = int(_lib.lib().anqs_hash_bytes(self.capacity))
         self.slots = pt.empty(((nbytes + 7) // 8,), dtype=pt.int64, device=dev)  # slots + header + filter
         assert self.slots.data_ptr() % 128 == 0
-        # tables that do not fit the L2 cache are built partitioned (k2_hash.cu) and need room for one 32-byte record per key;
-        # sized for the most keys this capacity takes, so that rebuild() never allocates
-        wbytes = int(_lib.lib().anqs_hash_build_workspace(self.capacity // 2, self.capacity)) if partitioned else 0
-        self.work = pt.empty(((wbytes + 7) // 8,), dtype=pt.int64, device=dev) if wbytes else None
         self.rebuild(keys, amps, spread_bits)
 
     def rebuild(self, keys: pt.Tensor, amps: pt.Tensor = None, spread_bits: int = None):
@@ -174,9 +170,12 @@ class SampleTable:
             assert amps.dtype == pt.complex128 and amps.shape[0] == n
             amps_real = pt.view_as_real(amps.contiguous())
         self._keep = (keys, amps_real)
-        _lib.check(_lib.lib().anqs_hash_build_ws(_lib.dptr(keys), _lib.dptr(amps_real), n, _lib.dptr(self.slots), self.capacity,
-                                                 -1 if spread_bits is None else int(spread_bits), _lib.dptr(self.work),
-                                                 0 if self.work is None else self.work.numel() * 8, _lib.stream_ptr(dev)))
+        if spread_bits is None:
+            _lib.check(_lib.lib().anqs_hash_build(_lib.dptr(keys), _lib.dptr(amps_real), n, _lib.dptr(self.slots), self.capacity,
+                                                  _lib.stream_ptr(dev)))
+        else:
+            _lib.check(_lib.lib().anqs_hash_build_spread(_lib.dptr(keys), _lib.dptr(amps_real), n, _lib.dptr(self.slots),
+                                                         self.capacity, int(spread_bits), _lib.stream_ptr(dev)))
         return self
 
     def filter_info(self):

@@ -514,9 +514,9 @@ class GpuEngine:
         self.kernel_name = ('fused_eloc_bs_kernel' if (self.rows + 31) // 32 >= 8 * torch.cuda.get_device_properties(dev).multi_processor_count
                             else 'fused_eloc_kernel')
         self.table = self.eloc = None
-        # filter_count, filter_overload, filter_pick_spread, hash_build (k2_hash.cu) + the fused kernel; tables of 96 MiB of slots and
-        # more (more than 2^20 keys: every multi-GPU run) are built partitioned: part_count, part_scan, part_scatter on top
-        self.launches_per_step = 5 + (3 if self.n_set > (1 << 20) else 0)
+        # filter_count, filter_overload, filter_pick_spread, hash_build, hash_fix_amplitudes (k2_hash.cu), the fused kernel,
+        # energy_stats (abi_core.cu)
+        self.launches_per_step = 7
 
     def flush_l2(self):
         self.flush.fill_(1)

@@ -65,6 +65,14 @@ int anqs_tables_info(const anqs_tables_t *t, int *qubit_num, int64_t *U, int64_t
 int anqs_k1_filter(const anqs_tables_t *t, const int64_t *d_samples, int64_t n, int alpha_num, int beta_num,
                    int64_t *d_counts, uint32_t *d_bitmap, void *stream);
 
+/* ---- A13  packed partial sums of the energy estimator (MonteCarloEstimator with theoretical frequencies, CLE:48-62,
+ * 107-113) in one pass over the local energies and the amplitudes of the same rows (both complex128, n rows):
+ * d_out5 = [sum w, Re sum w E, Im sum w E, Re sum w E^2, Im sum w E^2], w = |psi|^2 (E^2 = the complex square, as the
+ * reference's variance takes it).  mean = sum w E / sum w, var = sum w E^2 / sum w - mean^2; across GPUs the five sums are what
+ * one all-reduce adds.  Fixed summation order for a given n.  d_work: >= anqs_energy_stats_workspace(n) bytes, 16-byte aligned. */
+size_t anqs_energy_stats_workspace(int64_t n);
+int anqs_energy_stats(const double *d_eloc, const double *d_amps, int64_t n, double *d_out5, void *d_work, void *stream);
+
 /* d_out[0] = 0, d_out[i+1] = d_out[i] + d_in[i]  (n+1 outputs).  d_work: >= anqs_scan_workspace(n) bytes. */
 size_t anqs_scan_workspace(int64_t n);
 int anqs_exclusive_scan_i64(const int64_t *d_in, int64_t *d_out, int64_t n, void *d_work, void *stream);
@@ -123,15 +131,6 @@ int anqs_hash_build(const int64_t *d_keys, const double *d_amps, int64_t n, void
 /* Same with G forced to spread_bits (0..6) instead of chosen from the data. */
 int anqs_hash_build_spread(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity,
                            int spread_bits, void *stream);
-/* Build with a caller-owned workspace.  Tables whose slots do not fit the L2 cache (anqs_hash_build_workspace(n, capacity) > 0:
- * 96 MiB of slots and more) are built PARTITIONED when d_work holds at least that many bytes (16-byte aligned): the keys are
- * first grouped by the leading bits of their home slot (histogram, scan, scatter of 32-byte records), then inserted in that
- * order, so that the inserts of any moment fall into a few L2-resident partitions of 16 MiB instead of random DRAM sectors
- * (8.4M keys: 1.27 -> see profiles/r2_table_build.txt).  Same table either way.  d_work = NULL or too small, or a small
- * table: the direct build.  spread_bits = -1: G from the data (anqs_hash_build), 0..6: forced (anqs_hash_build_spread). */
-size_t anqs_hash_build_workspace(int64_t n, int64_t capacity);
-int anqs_hash_build_ws(const int64_t *d_keys, const double *d_amps, int64_t n, void *d_table, int64_t capacity, int spread_bits,
-                       void *d_work, size_t work_bytes, void *stream);
 /* Reads back G and overloaded_keys[g] (g = 0..6) = keys living in lines that hold more than 128 << g keys.
  * Synchronises the stream. */
 int anqs_hash_filter_info(const void *d_table, int64_t capacity, int *spread_bits, int64_t *overloaded_keys, void *stream);
