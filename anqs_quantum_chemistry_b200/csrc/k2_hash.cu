@@ -20,41 +20,23 @@
 
 namespace anqs {
 
-// The three GF(2)-linear hashes of a key through byte tables in shared memory: lin(f, v) = T[f][0][v & 255] ^ T[f][1][v >> 8 & 255]
-// ^ ..., four loads per hash instead of a loop over the set bits with one table load each (that loop was 700 of the insert
-// kernel's 940 warp instructions per 32 keys, profiles/r2_table_build.txt).  Line and first position hash share the alpha half
-// and sit side by side: one 8-byte load serves both.  12 KB per CTA.
-struct LinByteTables {
-    uint2 a[4][256];      // .x = LIN_LINE, .y = LIN_POSA contribution of byte b of the alpha half
-    uint32_t b[4][256];   // LIN_POSB contribution of byte b of the beta half
-    __device__ __forceinline__ void fill() {   // 256 threads
-        for (int t = threadIdx.x; t < 256; t += blockDim.x) {
-#pragma unroll
-            for (int byte = 0; byte < 4; ++byte) {
-                const uint32_t v = (uint32_t)t << (8 * byte);
-                a[byte][t] = make_uint2(lin_dev(LIN_LINE, v), lin_dev(LIN_POSA, v));
-                b[byte][t] = lin_dev(LIN_POSB, v);
-            }
-        }
-        __syncthreads();
-    }
-    __device__ __forceinline__ void hashes(uint64_t key, uint32_t &hl, uint32_t &hp) const {
-        const uint32_t ka = (uint32_t)key, kb = (uint32_t)(key >> 32);
-        const uint2 a0 = a[0][ka & 255u], a1 = a[1][(ka >> 8) & 255u], a2 = a[2][(ka >> 16) & 255u], a3 = a[3][ka >> 24];
-        const uint32_t pb = b[0][kb & 255u] ^ b[1][(kb >> 8) & 255u] ^ b[2][(kb >> 16) & 255u] ^ b[3][kb >> 24];
-        hl = a0.x ^ a1.x ^ a2.x ^ a3.x;
-        hp = ((a0.y ^ a1.y ^ a2.y ^ a3.y) & POSA_MASK) ^ (pb & POSB_MASK);
-    }
-};
+// The three GF(2)-linear hashes of a key, per thread: a loop over the set bits of each half (N_alpha / N_beta of them).
+// Measured alternative: byte tables in shared memory (four loads per hash, 12 KB filled by every block first) cut the insert
+// kernel's instructions by two thirds and made the build SLOWER (1.237 against 1.207 ms for 8.4M keys, 0.140 against 0.117 ms for
+// 1M): the kernel waits on its atomics, not on the issue slots, and the table fill delays every block's first key
+// (profiles/r2_table_build.txt).
+__device__ __forceinline__ void key_hashes(uint64_t key, uint32_t &hl, uint32_t &hp) {
+    const uint32_t ka = (uint32_t)key, kb = (uint32_t)(key >> 32);
+    hl = lin_dev(LIN_LINE, ka);
+    hp = (lin_dev(LIN_POSA, ka) & POSA_MASK) ^ (lin_dev(LIN_POSB, kb) & POSB_MASK);
+}
 
 __global__ void __launch_bounds__(256)
 filter_count_kernel(const int64_t *__restrict__ keys, int64_t n, uint32_t *counts, uint32_t linemask) {
-    __shared__ LinByteTables lin;
-    lin.fill();
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         uint32_t hl, hp;
-        lin.hashes(deinterleave((uint64_t)keys[j]), hl, hp);
+        key_hashes(deinterleave((uint64_t)keys[j]), hl, hp);
         atomicAdd(counts + (hl & linemask), 1u);
     }
 }
@@ -100,70 +82,48 @@ __global__ void filter_pick_spread_kernel(unsigned long long *__restrict__ acc, 
 
 // Insert kernel: keys into the table and the filter.  An insert is a chain of dependent round trips to the L2 / DRAM (key ->
 // compare-and-swap on the home slot -> maximum on the position -> amplitude stores) and the kernel is latency-bound (ncu, 8.4M
-// keys: 36-43 warps stalled on the long scoreboard per issue, DRAM at 30 %, L2 at 20 %; profiles/r2_table_build.txt).
-// INSERT_WAYS keys per thread go through the chain side by side.  Measured: 4 ways are SLOWER than 1 (1.35 against 1.0 ms for
-// 8.4M keys) - 57 registers halve the resident warps and the linear-probing loops of the four keys run one after the other -,
-// so the kernel runs with 1 and full occupancy; the structure is kept for the day the probing loop is interleaved too.
+// keys: 36-43 warps stalled on the long scoreboard per issue, DRAM at 30 %, L2 at 20 %; profiles/r2_table_build.txt).  Tried
+// and measured slower: four keys per thread side by side (57 registers halve the resident warps and the probing loops of the
+// four keys run one after the other: 1.35 against 1.0 ms), keys grouped by home slot into L2-sized partitions first (same DRAM
+// traffic - every sector still comes from DRAM once after the memset - plus 0.2 ms of partitioning).
 // Duplicates: the largest position wins, which is what a sequential scatter_ leaves behind, and the amplitude has to follow the
 // position.  Every thread that raises idx stores its amplitude; when two positions of one key race, the stores may land in
 // either order - so a thread that finds the slot already claimed (old position >= 0) raises *dup_flag, and
 // hash_fix_amplitudes_kernel, launched behind this kernel, then rewrites every slot's amplitude from its final position.
 // No fence and no re-read inside the insert (__threadfence() is a gpu-scope MEMBAR plus an L1 invalidation per key), and
 // batches without duplicates - the normal case: the sampler returns unique configurations - never run the second pass.
-constexpr int INSERT_WAYS = 1;
 __global__ void __launch_bounds__(256)
 hash_build_kernel(const int64_t *__restrict__ keys, const double2 *__restrict__ amps, int64_t n, HashSlot *slots,
                   uint32_t *filter_words, const FilterHeader *hdr, unsigned long long *dup_flag, uint32_t capmask, uint32_t linemask) {
-    __shared__ LinByteTables lin;
-    lin.fill();
     const uint32_t gmask = hdr->gmask;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     bool dup = false;
-    for (int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < n; j0 += INSERT_WAYS * stride) {
-        uint64_t key[INSERT_WAYS];
-        double2 a[INSERT_WAYS];
-        uint32_t h[INSERT_WAYS];
-        unsigned long long prev[INSERT_WAYS];
-        bool live[INSERT_WAYS];
-#pragma unroll
-        for (int c = 0; c < INSERT_WAYS; ++c) {
-            const int64_t j = j0 + c * stride;
-            live[c] = j < n;
-            key[c] = live[c] ? (uint64_t)keys[j] : 0ull;
-            a[c] = (live[c] && amps) ? amps[j] : make_double2(0.0, 0.0);
-        }
-#pragma unroll
-        for (int c = 0; c < INSERT_WAYS; ++c) {
-            key[c] = deinterleave(key[c]);
-            uint32_t hl, hp;
-            lin.hashes(key[c], hl, hp);
-            const uint32_t line = (hl ^ ((hp >> 15) & gmask)) & linemask;
-            if (live[c]) atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), (1u << (hp & 31u)) | (1u << ((hp >> 10) & 31u)));
-            h[c] = hash_key((uint32_t)key[c], (uint32_t)(key[c] >> 32)) & capmask;
-            // the all-ones key is the EMPTY sentinel: it lives in a dedicated slot behind the table and needs no claim
-            prev[c] = key[c];
-            if (live[c] && key[c] != EMPTY_KEY)
-                prev[c] = atomicCAS((unsigned long long *)&slots[h[c]].key, (unsigned long long)EMPTY_KEY, (unsigned long long)key[c]);
-        }
-        long long old[INSERT_WAYS];
-#pragma unroll
-        for (int c = 0; c < INSERT_WAYS; ++c) {
-            while (prev[c] != EMPTY_KEY && prev[c] != key[c]) {   // occupied by another key: linear probing
-                h[c] = (h[c] + 1) & capmask;
-                prev[c] = atomicCAS((unsigned long long *)&slots[h[c]].key, (unsigned long long)EMPTY_KEY, (unsigned long long)key[c]);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint64_t key = deinterleave((uint64_t)keys[j]);
+        uint32_t hl, hp;
+        key_hashes(key, hl, hp);
+        const uint32_t line = (hl ^ ((hp >> 15) & gmask)) & linemask;
+        atomicOr(filter_words + (size_t)line * 32 + ((hp >> 5) & 31u), (1u << (hp & 31u)) | (1u << ((hp >> 10) & 31u)));
+        HashSlot *sl;
+        if (key == EMPTY_KEY) {   // the all-ones key is the EMPTY sentinel: it lives in a dedicated slot behind the table
+            sl = slots + (size_t)capmask + 1;
+        } else {
+            uint32_t h = hash_key((uint32_t)key, (uint32_t)(key >> 32)) & capmask;
+            for (;;) {
+                unsigned long long prev = atomicCAS((unsigned long long *)&slots[h].key, (unsigned long long)EMPTY_KEY,
+                                                    (unsigned long long)key);
+                if (prev == EMPTY_KEY || prev == key) break;
+                h = (h + 1) & capmask;   // occupied by another key: linear probing
             }
-            HashSlot *sl = key[c] == EMPTY_KEY ? slots + (size_t)capmask + 1 : slots + h[c];
-            old[c] = live[c] ? atomicMax(&sl->idx, (long long)(j0 + c * stride)) : -1;
+            sl = slots + h;
         }
-#pragma unroll
-        for (int c = 0; c < INSERT_WAYS; ++c) {
-            HashSlot *sl = key[c] == EMPTY_KEY ? slots + (size_t)capmask + 1 : slots + h[c];
-            if (live[c] && old[c] < (long long)(j0 + c * stride) && amps) {
-                sl->re = a[c].x;
-                sl->im = a[c].y;
-            }
-            dup |= old[c] >= 0;
+        const long long old = atomicMax(&sl->idx, (long long)j);
+        if (old < (long long)j && amps) {
+            const double2 a = amps[j];
+            sl->re = a.x;
+            sl->im = a.y;
         }
+        dup |= old >= 0;
     }
     if (dup) *dup_flag = 1ull;
 }
@@ -230,16 +190,7 @@ static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, v
     ANQS_CUDA(cudaMemsetAsync(filter_words, 0, (size_t)FILTER_BYTES_PER_SLOT * capacity, s));
     if (n == 0) return 0;
     ANQS_REQUIRE(d_keys, "null key array");
-    // eight resident blocks per SM (each fills 12 KB of hash byte tables first); the insert keeps INSERT_WAYS keys in flight per thread
-    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 8);
-    static int insert_blocks_per_sm = 0;   // resident blocks of the insert kernel (register-limited): one wave of them
-    if (insert_blocks_per_sm == 0) {
-        int b = 0;
-        ANQS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, hash_build_kernel, 256, 0));
-        insert_blocks_per_sm = std::max(1, b);
-    }
-    const int grid_insert = (int)std::min<int64_t>((n + 256 * INSERT_WAYS - 1) / (256 * INSERT_WAYS),
-                                                   (int64_t)sm_count_of_current_device() * insert_blocks_per_sm);
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count_of_current_device() * 16);
     if (forced_spread < 0) {
         // per-line key counts, kept in the (still empty) filter region: nlines * 4 bytes <= the filter's size
         filter_count_kernel<<<grid, 256, 0, s>>>(d_keys, n, filter_words, hv.linemask);
@@ -254,10 +205,10 @@ static int build_table(const int64_t *d_keys, const double *d_amps, int64_t n, v
     filter_pick_spread_kernel<<<1, 32, 0, s>>>(acc, nlines, (uint32_t)n, hdr, forced_spread);
     ANQS_LAUNCH_CHECK();
     if (forced_spread < 0) ANQS_CUDA(cudaMemsetAsync(filter_words, 0, (size_t)nlines * sizeof(uint32_t), s));
-    hash_build_kernel<<<grid_insert, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, filter_words, hdr, acc, hv.capmask, hv.linemask);
+    hash_build_kernel<<<grid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, filter_words, hdr, acc, hv.capmask, hv.linemask);
     ANQS_LAUNCH_CHECK();
     if (d_amps != nullptr) {
-        hash_fix_amplitudes_kernel<<<grid, 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, acc, hv.capmask);
+        hash_fix_amplitudes_kernel<<<std::min(grid, sm_count_of_current_device() * 8), 256, 0, s>>>(d_keys, (const double2 *)d_amps, n, slots, acc, hv.capmask);
         ANQS_LAUNCH_CHECK();
     }
     return 0;
