@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 re-entry evidence on one B200 (run under gpurun): all GPU tests, table build timing, the bench line, its launch list
+# round-2 final evidence on one B200 (run under gpurun): all GPU tests, table build timing, the bench line, its launch list
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python scripts/table_build_time.py 2>&1 | tee gpurun_out/table_build_time.txt
