@@ -1,6 +1,6 @@
 #!/bin/bash
-# ncu --set full of the table insert kernels at 8.4M keys (run under gpurun)
+# last check of the round on one B200 (run under gpurun): all GPU tests, smoke(), table build timing with the shipped insert kernel
 mkdir -p gpurun_out
-SIZES=8388608 REPS=1 ncu --set full --clock-control none --import-source on -k regex:'hash_build' -c 4 -o gpurun_out/hash_build_8m -f python scripts/table_build_time.py > gpurun_out/hash_build_ncu.log 2>&1
-tail -3 gpurun_out/hash_build_ncu.log
-ls -la gpurun_out/
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python scripts/table_build_time.py 2>&1 | tee gpurun_out/table_build_time_final.txt
