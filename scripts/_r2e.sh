@@ -1,5 +1,7 @@
 #!/bin/bash
-# experiment: L2 access-policy variants for the presence filter of an 8.4M-key table (run under gpurun)
+# experiment: L2 access-policy variants for the presence filter of an 8.4M-key table (run under gpurun).  The modes are read
+# from ANQS_EXP_L2 by a build with scripts/exp_l2_policy.patch applied to csrc/k1_fused_bs.cu (not part of the shipped library):
+# 0 no window, 1 persisting + streaming misses (shipped), 2 persisting + normal misses, 3 hit ratio 0.6 + streaming, 4 0.6 + normal
 mkdir -p gpurun_out
 python - <<'P' 2>&1 | tee gpurun_out/l2_policy_experiment.txt
 import os, sys, tempfile
