@@ -72,6 +72,40 @@ __device__ __forceinline__ uint32_t fb_test(uint32_t word, uint32_t hb) {
     return __funnelshift_r(word, 0u, hb) & __funnelshift_r(word, 0u, hb >> 5) & 1u;
 }
 
+
+// Slot reads of a table far larger than the L2 cache (8.4M keys: 537 MB of slots) are random DRAM sectors that are never
+// reused, yet every one of them takes an L2 line from the filter words the kernel lives on: such tables are read with an
+// evict-first L2 policy and no L1 allocation.  Measured on one B200, 2^20 rows (profiles/r2b_cache_hint_experiment.txt):
+// 8.4M keys 18.85 -> 18.55 ms; on a 1M-key table (64 MB of slots, L2-resident and reused) the same hint costs 1 % (17.72 ->
+// 17.94 ms), so it is taken from 2^22 slots on.  An evict-last policy on the filter words was also tried: +3 to +6 %, dropped.
+constexpr uint32_t FB_STREAM_SLOTS_FROM = 1u << 22;
+__device__ __forceinline__ long long hash_lookup_stream(const HashView &hv, uint64_t key, double &re, double &im) {
+    if (key == EMPTY_KEY) return hash_lookup(hv, key, re, im);
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    uint32_t h = hash_key((uint32_t)key, (uint32_t)(key >> 32)) & hv.capmask;
+    for (;;) {
+        unsigned long long kx, ky;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+                     : "=l"(kx), "=l"(ky) : "l"(hv.slots + h), "l"(pol));
+        if (kx == key) {
+            double2 a = __ldg(reinterpret_cast<const double2 *>(hv.slots + h) + 1);
+            re = a.x;
+            im = a.y;
+            return (long long)ky;
+        }
+        if (kx == EMPTY_KEY) return -1;
+        h = (h + 1) & hv.capmask;
+    }
+}
+
+// filter word of one candidate, 0 when the lane has none
+__device__ __forceinline__ uint32_t fb_ldg(bool cond, const uint32_t *p) {
+    uint32_t v = 0;
+    if (cond) v = __ldg(p);
+    return v;
+}
+
 struct FbWarp {
     FbSlot *sl;
     double *wacc;   // this warp's private accumulators (slots[warp].acc): nobody else adds to them
@@ -79,6 +113,7 @@ struct FbWarp {
     int qlen;
     const uint8_t *filter;
     uint32_t linemask, gmask;
+    bool stream_slots;   // table beyond the L2 cache: slot reads with the evict-first policy (warp-uniform)
 };
 
 template <bool REAL>
@@ -88,7 +123,7 @@ __device__ __forceinline__ void fb_resolve(const Tables &t, const HashView &hv, 
     double ar = 0.0, ai = 0.0;
     int2 g = make_int2(0, 0);
     if (active) {
-        j = hash_lookup(hv, key, ar, ai);
+        j = w.stream_slots ? hash_lookup_stream(hv, key, ar, ai) : hash_lookup(hv, key, ar, ai);
         if (j >= 0) {
             const uint32_t u = (e.z & FB_UREF_ROW) ? __ldg(t.prod_row_u + (e.z & ~FB_UREF_ROW)) : __ldg(t.prod_mem_u + e.z);
             g = __ldg(t.grp + u);
@@ -201,13 +236,13 @@ __device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView 
                 const uint32_t ua = (((ha.x ^ rec.y) & w.linemask) << 7) ^ (ha.y & 0xFFFFu);
                 const uint32_t ub = (((hb.x ^ rec.y) & w.linemask) << 7) ^ (hb.y & 0xFFFFu);
                 const uint32_t bita = 1u << sa, bitb = two ? 1u << sb : 0u;
-                uint32_t wa1 = 0, wa2 = 0, wb1 = 0, wb2 = 0;
+                uint32_t wa1, wa2, wb1, wb2;
                 // filter is FILTER_ALIGN-aligned and mo < FILTER_ALIGN: (filter + u) ^ mo == filter + (u ^ mo), one LOP3 per probe
                 const uintptr_t pa = (uintptr_t)(w.filter + ua), pb = (uintptr_t)(w.filter + ub);
-                if (w1 & bita) wa1 = __ldg(reinterpret_cast<const uint32_t *>(pa ^ mo1));
-                if (w2 & bita) wa2 = __ldg(reinterpret_cast<const uint32_t *>(pa ^ mo2));
-                if (w1 & bitb) wb1 = __ldg(reinterpret_cast<const uint32_t *>(pb ^ mo1));
-                if (w2 & bitb) wb2 = __ldg(reinterpret_cast<const uint32_t *>(pb ^ mo2));
+                wa1 = fb_ldg(w1 & bita, reinterpret_cast<const uint32_t *>(pa ^ mo1));
+                wa2 = fb_ldg(w2 & bita, reinterpret_cast<const uint32_t *>(pa ^ mo2));
+                wb1 = fb_ldg(w1 & bitb, reinterpret_cast<const uint32_t *>(pb ^ mo1));
+                wb2 = fb_ldg(w2 & bitb, reinterpret_cast<const uint32_t *>(pb ^ mo2));
                 const uint32_t ka = ha.y >> 16, kb = hb.y >> 16;
                 const bool fa1 = fb_test(wa1, ka ^ mh1), fa2 = fb_test(wa2, ka ^ mh2);
                 const bool fb1 = fb_test(wb1, kb ^ mh1), fb2 = fb_test(wb2, kb ^ mh2);
@@ -243,9 +278,8 @@ __device__ __forceinline__ void fb_process_tile(const Tables &t, const HashView 
             const uint2 ha = sl.hs[sa], hb = sl.hs[sb];
             const uint32_t offa = ((((ha.x ^ c.y) & w.linemask) << 7) ^ (ha.y & 0xFFFFu)) ^ mo;
             const uint32_t offb = ((((hb.x ^ c.y) & w.linemask) << 7) ^ (hb.y & 0xFFFFu)) ^ mo;
-            uint32_t worda = 0, wordb = 0;
-            if (acta) worda = __ldg(reinterpret_cast<const uint32_t *>(w.filter + offa));
-            if (actb) wordb = __ldg(reinterpret_cast<const uint32_t *>(w.filter + offb));
+            const uint32_t worda = fb_ldg(acta, reinterpret_cast<const uint32_t *>(w.filter + offa));
+            const uint32_t wordb = fb_ldg(actb, reinterpret_cast<const uint32_t *>(w.filter + offb));
             const bool fa = fb_test(worda, (ha.y >> 16) ^ mh), fb = fb_test(wordb, (hb.y >> 16) ^ mh);
             if (__any_sync(0xffffffffu, fa | fb)) {
                 unsigned b = __ballot_sync(0xffffffffu, fa);
@@ -328,6 +362,7 @@ fused_eloc_bs_kernel(Tables t, HashView hv, const int64_t *__restrict__ samples,
     w.filter = hv.filter;
     w.linemask = hv.linemask;
     w.gmask = __ldg(&hv.header->gmask);
+    w.stream_slots = hv.capmask >= FB_STREAM_SLOTS_FROM - 1u;
     FbSlot &sl = *w.sl;
 
     const bool resident = t.n_tiles == 1;

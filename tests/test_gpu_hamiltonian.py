@@ -301,6 +301,22 @@ def test_large_table_with_duplicated_keys():
     for _ in range(3):
         table.rebuild(s, a)
         assert torch.equal(occupied(table), occ)
+    # the bit-sliced fused kernel reads the slots of a table of this size (2^22 slots and more) with an evict-first L2 policy
+    # (k1_fused_bs.cu:hash_lookup_stream): same local energies as the warp-per-sample kernel, which reads them plainly
+    xy, yz, w = synthetic.synthetic_hamiltonian(56, n_irreps=8, seed=0)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        hs = HilbertSpace(qubit_num=56, device=DEV, parent_dir=tmp, rng_seed=0)
+        ham = PauliObservable(hilbert_space=hs, of_qubit_operator=PauliArraysOperator(xy, yz, w, 56))
+        rows, out = 8192, {}
+        for variant in (1, 2):
+            e = torch.empty(rows, dtype=torch.complex128, device=DEV)
+            _lib.check(_lib.lib().anqs_local_energy_sample_aware_variant(ham.tables, _lib.dptr(s), _lib.dptr(torch.view_as_real(a)), s.shape[0], 0, rows,
+                                                                         _lib.dptr(table.slots), cap, 7, 7, _lib.dptr(torch.view_as_real(e)), variant,
+                                                                         _lib.stream_ptr(DEV)))
+            out[variant] = e.cpu().numpy()
+        assert np.abs(out[1] - out[2]).max() < 1e-10 * max(1.0, np.abs(out[1]).max())
+        assert np.abs(out[1]).max() > 0
 
 
 def test_multi_tile_product_layout(tmp_path):
