@@ -1,6 +1,7 @@
 #!/bin/bash
 # experiment: L2 cache hints on the slot reads (evict-first, no L1 allocation) and the filter words (evict-last) of the bit-sliced fused
-# kernel, builds libanqs_b200_exp{0,1,2}.so = k1_fused_bs.cu with -DANQS_EXP_CACHE=0/1/2 (run under gpurun)
+# kernel (run under gpurun).  libanqs_b200_exp{0,1,2}.so were one-off builds of k1_fused_bs.cu with the three variants described in
+# profiles/r2b_cache_hint_experiment.txt; the winner (evict-first slot reads for tables beyond the L2) is now in the shipped kernel.
 mkdir -p gpurun_out
 python - <<'P' 2>&1 | tee gpurun_out/cache_hint_experiment.txt
 import os, sys, tempfile, ctypes
