@@ -33,11 +33,14 @@ class LocalSamplingConfig:
     """ANQS:20-50."""
 
     def __init__(self, *args, pattern_type: str = 'uniform', strategy: str = 'MU', masking_depth: int = 0, **kwargs):
+        if args or kwargs:
+            raise TypeError(f'LocalSamplingConfig: unexpected arguments {args} {sorted(kwargs)}')
         self.pattern_type, self.strategy, self.masking_depth = pattern_type, strategy, masking_depth
 
     def create_local_sampling_pattern(self, qudit_num: int = None):
         assert self.pattern_type == 'uniform'
         assert self.strategy in LOCAL_SAMPLING_STRATEGIES
+        assert 0 <= self.masking_depth <= qudit_num, f'masking_depth {self.masking_depth} outside [0, {qudit_num}]'
         return (self.strategy,) * (qudit_num - self.masking_depth) + ('DU',) * self.masking_depth
 
 

@@ -108,3 +108,37 @@ def test_loss_on_attached_log_psi_equals_the_reference_loss():
     assert abs(float(l0) - float(l1)) < 1e-12 * max(1.0, abs(float(l0)))
     for a, b in zip(g0, g1):
         assert float((a - b).abs().max()) < 1e-12
+
+
+def test_config_keywords_are_the_references_and_nothing_is_swallowed():
+    """ANQS:68-109, MLP:13-99, ANQS:20-50: the reference's keyword surface.  What the kernels do not implement raises
+    NotImplementedError, unknown keywords raise TypeError (the reference's Config hands them to object.__init__), and the
+    defaults are the reference's (de_mode 'NADE', depth 2, width 64, tanh, residuals, bias, masking_depth 0)."""
+    import torch.nn as nn
+    from anqs_quantum_chemistry_b200.anqs import (ANQSConfig, MLPConfig, WidthConfig, BiasConfig, ActivationConfig, LocalSamplingConfig)
+    c = ANQSConfig()
+    assert c.de_mode == 'NADE' and c.subtract_mean is True and c.use_sign_structure is False
+    assert c.local_sampling_config.masking_depth == 0 and c.local_sampling_config.strategy == 'MU'
+    m = c.main_subnet_config
+    assert (m.depth, m.width, m.use_res, m.use_bias, m.activation, m.activate_last_layer) == (2, 64, True, True, nn.Tanh, False)
+    m = MLPConfig(depth=3, width_config=WidthConfig(width=64), bias_config=BiasConfig(use_bias=False),
+                  activation_config=ActivationConfig(activation=nn.Tanh), use_res=False)
+    assert (m.depth, m.width, m.use_bias, m.use_res) == (3, 64, False, False)
+    assert m.width_config.create_pattern(3) == (64, 64, 64)
+    for bad in (dict(width_config=WidthConfig(width=128)), dict(activation_config=ActivationConfig(activation=nn.ReLU)),
+                dict(activate_last_layer=True), dict(depth=5), dict(width=32)):
+        with pytest.raises(NotImplementedError):
+            MLPConfig(**bad)
+    with pytest.raises(NotImplementedError):
+        WidthConfig(pattern_type='custom')
+    with pytest.raises(NotImplementedError):
+        ANQSConfig(use_sign_structure=True)
+    for cls, kw in ((MLPConfig, dict(hidden=64)), (ANQSConfig, dict(mode='MADE')), (WidthConfig, dict(widths=(64,))),
+                    (LocalSamplingConfig, dict(depth=1))):
+        with pytest.raises(TypeError):
+            cls(**kw)
+    with pytest.raises(TypeError):
+        MLPConfig(width=64, width_config=WidthConfig())
+    assert LocalSamplingConfig(masking_depth=2).create_local_sampling_pattern(qudit_num=4) == ('MU', 'MU', 'DU', 'DU')
+    with pytest.raises(AssertionError):
+        LocalSamplingConfig(masking_depth=5).create_local_sampling_pattern(qudit_num=4)
