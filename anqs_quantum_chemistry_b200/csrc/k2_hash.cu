@@ -21,8 +21,8 @@
 namespace anqs {
 
 // The three GF(2)-linear hashes of a key, per thread: a loop over the set bits of each half (N_alpha / N_beta of them).
-// Measured alternative: byte tables in shared memory (four loads per hash, 12 KB filled by every block first) cut the insert
-// kernel's instructions by two thirds and made the build SLOWER (1.237 against 1.207 ms for 8.4M keys, 0.140 against 0.117 ms for
+// These loops are ~70 % of the insert kernel's instructions.  Measured alternative: byte tables in shared memory (four loads per
+// hash, 12 KB filled by every block first) made the build SLOWER (1.237 against 1.207 ms for 8.4M keys, 0.140 against 0.117 ms for
 // 1M): the kernel waits on its atomics, not on the issue slots, and the table fill delays every block's first key
 // (profiles/r2_table_build.txt).
 __device__ __forceinline__ void key_hashes(uint64_t key, uint32_t &hl, uint32_t &hp) {
